@@ -1,0 +1,264 @@
+/*
+ * blingcu.h -- C ABI of the B200 path-tracing core for waldheinz/bling.
+ *
+ * This is the drop-in boundary for ONE hot path of the reference: the body of
+ *   prender / tile            (src/lib/Graphics/Bling/Rendering.hs:111-150)
+ * i.e. sampler -> fireRay -> surfaceLi (path integrator + NEE) -> addSample.
+ * A Haskell `Renderer` instance (Rendering.hs:77-78) binds these entry points
+ * with `foreign import ccall safe` (see INTEGRATION.md and haskell/).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a BLINGCU_E* code otherwise; the
+ *     message is available from blingcu_last_error().
+ *   - all input buffers are caller-owned HOST memory and are copied on upload.
+ *   - all output buffers are caller-allocated HOST memory unless the name says
+ *     `_device`.
+ *   - POD structs, fixed-width types only; no C++ types, no torch types.
+ *   - a context belongs to one host thread at a time and to ONE GPU; multi-GPU
+ *     runs use one context per GPU (one process per GPU) and sum films
+ *     (blingcu_film_device + an NCCL allreduce on the host side, or
+ *     blingcu_film_add_host).
+ *
+ * The flat scene IR (`blingcu_scene`) is what the Haskell host produces where
+ * the scene is built (the parser), because the reference's scene objects are
+ * closures (Primitive.hs:21-27, Reflection.hs:42) and cannot be flattened later.
+ */
+#ifndef BLINGCU_H
+#define BLINGCU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BLINGCU_BANDS 16 /* Spectrum.hs:34-36: 16 bands, 400-700nm */
+
+enum {
+   BLINGCU_OK = 0,
+   BLINGCU_EINVAL = 1,  /* bad argument / malformed IR                    */
+   BLINGCU_ECUDA = 2,   /* CUDA runtime error                             */
+   BLINGCU_ENOGPU = 3,  /* no usable device: there is NO CPU fallback      */
+   BLINGCU_ESTATE = 4   /* call out of order (e.g. render before upload)  */
+};
+
+/* Shape.hs:23-38 */
+enum {
+   BLINGCU_SHAPE_BOX = 0,      /* p[0..2]=pmin p[3..5]=pmax               */
+   BLINGCU_SHAPE_CYLINDER = 1, /* p = radius zmin zmax phimax(rad)        */
+   BLINGCU_SHAPE_DISK = 2,     /* p = height radius innerRadius phimax    */
+   BLINGCU_SHAPE_QUAD = 3,     /* p = sx sy                               */
+   BLINGCU_SHAPE_SPHERE = 4    /* p = radius                              */
+};
+
+/* Material.hs:32-96 (the five materials the configs use) + blackbody */
+enum {
+   BLINGCU_MAT_MATTE = 0,   /* tex[0]=kd          f[0]=sigma              */
+   BLINGCU_MAT_GLASS = 1,   /* tex[0]=kr tex[1]=kt f[0]=ior               */
+   BLINGCU_MAT_MIRROR = 2,  /* tex[0]=kr                                  */
+   BLINGCU_MAT_PLASTIC = 3, /* tex[0]=kd tex[1]=ks f[0]=rough             */
+   BLINGCU_MAT_METAL = 4,   /* tex[0]=eta tex[1]=k f[0]=rough             */
+   BLINGCU_MAT_BLACKBODY = 5, /* Reflection.hs:337-338: no BxDFs          */
+   BLINGCU_MAT_KINDS = 6
+};
+
+/* Texture.hs:159-207 */
+enum {
+   BLINGCU_TEX_CONSTANT = 0,   /* s                                       */
+   BLINGCU_TEX_GRAPHPAPER = 1  /* f[0]=lineWidth f[1..4]=su sv ou ov (uvMapping), child[0]=paper child[1]=line */
+};
+
+/* Light.hs:31-45 */
+enum {
+   BLINGCU_LIGHT_INFINITE = 0,    /* env = index into envs                 */
+   BLINGCU_LIGHT_DIRECTIONAL = 1, /* s = radiance, v = normalized normal   */
+   BLINGCU_LIGHT_POINT = 2,       /* s = intensity, v = position           */
+   BLINGCU_LIGHT_AREA = 3         /* s = radiance, shape = index into shapes */
+};
+
+enum {
+   BLINGCU_ENV_CONSTANT = 0, /* s                                          */
+   BLINGCU_ENV_RGBTABLE = 1, /* rgb[h][w][3], nearest, flipped (IO/Bitmap.hs:22-29) */
+   BLINGCU_ENV_SUNSKY = 2    /* analytic Perez model (SunSky.hs:12-94)     */
+};
+
+enum { BLINGCU_CAM_PERSPECTIVE = 0, BLINGCU_CAM_ENVIRONMENT = 1 };
+enum { BLINGCU_SAMPLER_STRATIFIED = 0, BLINGCU_SAMPLER_RANDOM = 1 };
+
+typedef struct blingcu_spectrum { float v[BLINGCU_BANDS]; } blingcu_spectrum;
+
+/* One analytic shape wrapped by mkGeom (Primitive/Geometry.hs:14-36).
+ * Matrices are row-major 4x4, m[r*4+c] (Transform.hs:40-42). */
+typedef struct blingcu_shape {
+   int32_t kind;
+   int32_t material;  /* index into materials                              */
+   int32_t light;     /* index into lights (area light) or -1              */
+   int32_t prim_id;   /* position in the list handed to mkScene            */
+   float p[8];
+   float o2w[16];
+   float w2o[16];
+} blingcu_shape;
+
+typedef struct blingcu_texture {
+   int32_t kind;
+   int32_t child[2];
+   int32_t _pad;
+   float f[8];
+   blingcu_spectrum s;
+} blingcu_texture;
+
+typedef struct blingcu_material {
+   int32_t kind;
+   int32_t tex[3];
+   float f[4];
+} blingcu_material;
+
+typedef struct blingcu_light {
+   int32_t kind;
+   int32_t shape; /* AREA: index into shapes                               */
+   int32_t env;   /* INFINITE: index into envs                             */
+   int32_t _pad;
+   float v[4];
+   blingcu_spectrum s;
+} blingcu_light;
+
+/* SunSky.hs:27-36 SkyData + the precomputed sun radiance */
+typedef struct blingcu_sunsky {
+   float sun_dir[3];      /* initSky: normalize (worldToLocal basis (normalize sdw)) */
+   float sun_theta;
+   float sun_disc_dir[3]; /* mkSunSkyLight: normalize (worldToLocal basis sdw), used by sunSpectrum */
+   float _pad;
+   float perez_x[5], perez_y[5], perez_Y[5];
+   float zenith_x, zenith_y, zenith_Y;
+   float s0xyz[3], s1xyz[3], s2xyz[3]; /* Spectrum.hs:226-244 chromaticityToXYZ */
+   blingcu_spectrum sun_radiance;      /* SunSky.hs:96-126 (black below horizon) */
+} blingcu_sunsky;
+
+/* The radiance map + Dist2D of mkInfiniteAreaLight (Light.hs:72-82,
+ * Montecarlo.hs:34-104). nu,nv = texSize. */
+typedef struct blingcu_envmap {
+   int32_t kind;
+   int32_t nu, nv;
+   int32_t _pad;
+   float w2l[16];             /* _infw2l                                    */
+   float l2w[16];             /* inverse                                    */
+   blingcu_spectrum s;        /* CONSTANT                                   */
+   const float *rgb;          /* RGBTABLE: nv*nu*3                          */
+   blingcu_sunsky sky;        /* SUNSKY                                     */
+   const float *cond_func;    /* nv*nu      conditional distFunc            */
+   const float *cond_cdf;     /* nv*(nu+1)  conditional cdf                 */
+   const float *cond_int;     /* nv         conditional funcInt             */
+   const float *marg_func;    /* nv                                         */
+   const float *marg_cdf;     /* nv+1                                       */
+   float marg_int;
+   float _pad2;
+} blingcu_envmap;
+
+typedef struct blingcu_camera {
+   int32_t kind;
+   float raster2cam[16];      /* Camera.hs:105-116 _raster2cam (matrix)     */
+   float cam2world[16];
+   float lens_radius, focal_distance;
+   float env_sx, env_sy;      /* Environment camera (Camera.hs:70-76)       */
+} blingcu_camera;
+
+typedef struct blingcu_scene {
+   /* triangles (TriangleMesh.hs, IO/WaveFront.hs) in world space */
+   uint64_t n_triangles;
+   const float *tri_verts;      /* n*9: p1 p2 p3                            */
+   const float *tri_uvs;        /* n*6 (TriangleMesh.hs:119-120 default 0,0,1,0,1,1) */
+   const float *tri_normals;    /* n*9 or NULL (flat shaded)                */
+   const int32_t *tri_material; /* n                                        */
+   const int32_t *tri_prim_id;  /* n, or NULL => prim id = prim_id_base + i */
+   int32_t tri_prim_id_base;
+
+   uint32_t n_shapes;    const blingcu_shape *shapes;
+   uint32_t n_materials; const blingcu_material *materials;
+   uint32_t n_textures;  const blingcu_texture *textures;
+   uint32_t n_lights;    const blingcu_light *lights; /* sceneLights order, Scene.hs:38-42 */
+   uint32_t n_envs;      const blingcu_envmap *envs;
+
+   blingcu_camera camera;
+
+   /* film + filter (Image.hs:40-61, Filter.hs:61-96) */
+   int32_t width, height;
+   float filter_w, filter_h;
+   float filter_table[256];
+
+   /* sampler + integrator (Sampling.hs:112-132, Integrator/Path.hs:30-39) */
+   int32_t sampler_kind;
+   int32_t nu, nv;       /* stratified nu nv; random: nu = spp, nv = 1      */
+   int32_t max_depth, sample_depth;
+
+   /* Spectrum.hs:337-347 (CIE tables as 16-band spectra) and :146-159 (illuminant basis r g b c m y w) */
+   blingcu_spectrum cie_x, cie_y, cie_z;
+   float cie_y_sum;
+   blingcu_spectrum illum_basis[7];
+} blingcu_scene;
+
+typedef struct blingcu_ray { float o[3]; float tmin; float d[3]; float tmax; } blingcu_ray;
+
+/* nearest-hit record; prim < 0 = miss */
+typedef struct blingcu_hit { float t; int32_t prim; float b1, b2; } blingcu_hit;
+
+/* counters; the traversal pair mirrors TraversalStats (Primitive/KdTree.hs:252-258) */
+typedef struct blingcu_stats {
+   uint64_t samples;
+   uint64_t rays_camera, rays_extension, rays_mis, rays_shadow;
+   uint64_t dropped_samples;   /* NaN/Inf samples skipped (Image.hs:253-256) */
+   uint64_t nodes_traversed, intersections;  /* only filled by blingcu_trace_stats */
+   uint64_t kernel_launches;
+   uint64_t bvh_nodes, bvh_leaf_items;
+   double last_pass_ms;        /* device time of the last render call        */
+} blingcu_stats;
+
+typedef struct blingcu_ctx blingcu_ctx;
+
+/* create a context on one CUDA device. Fails with BLINGCU_ENOGPU if there is none. */
+int blingcu_create(int device, blingcu_ctx **out);
+void blingcu_destroy(blingcu_ctx *);
+const char *blingcu_last_error(const blingcu_ctx *); /* ctx may be NULL: last create() error */
+
+/* replaces mkScene (Scene.hs:37-43): copies the IR, builds the BVH, uploads. */
+int blingcu_upload_scene(blingcu_ctx *, const blingcu_scene *ir);
+
+/* replaces scIntersect / occluded (Scene.hs:45-51) on explicit ray batches -- parity check (a) */
+int blingcu_trace_nearest(blingcu_ctx *, const blingcu_ray *rays, size_t n, blingcu_hit *out);
+int blingcu_trace_occluded(blingcu_ctx *, const blingcu_ray *rays, size_t n, uint8_t *out);
+/* same as trace_nearest with per-ray node visits / primitive tests (dbgTraverse, KdTree.hs:260-281) */
+int blingcu_trace_stats(blingcu_ctx *, const blingcu_ray *rays, size_t n, blingcu_hit *out,
+                        uint32_t *nodes, uint32_t *prims);
+
+/* replaces one `onePass` of prender (Rendering.hs:127-138): all nu*nv samples of every pixel of
+ * the sample extent, accumulated into the device film. */
+int blingcu_render_pass(blingcu_ctx *, uint32_t pass_index, uint64_t seed);
+/* the sharding unit: sample indices [s_begin, s_end) of every pixel of pass `pass_index`.
+ * render_pass == render_slice(0, nu*nv). */
+int blingcu_render_slice(blingcu_ctx *, uint32_t pass_index, uint64_t seed, uint32_t s_begin, uint32_t s_end);
+
+/* debug/parity: radiance of individual samples (no film). pixel coordinates are in sample-extent
+ * space (may be negative, Image.hs:162-168); out_L = n*16 floats; out_xy = n*2 image positions. */
+int blingcu_render_samples(blingcu_ctx *, uint32_t pass_index, uint64_t seed, const int32_t *px,
+                           const int32_t *py, const uint32_t *sample, size_t n, float *out_L, float *out_xy);
+
+/* film = Img._imgP layout [H][W]{weight, X*w, Y*w, Z*w} f32 (Image.hs:123-129,291-299) */
+int blingcu_read_film(blingcu_ctx *, float *wxyz);
+int blingcu_clear_film(blingcu_ctx *);
+int blingcu_film_add_host(blingcu_ctx *, const float *wxyz); /* film += host buffer (resume / manual reduce) */
+int blingcu_film_device(blingcu_ctx *, void **dptr, size_t *n_floats); /* for NCCL allreduce by the host */
+int blingcu_synchronize(blingcu_ctx *);
+
+int blingcu_get_stats(blingcu_ctx *, blingcu_stats *out);
+int blingcu_reset_stats(blingcu_ctx *);
+
+/* tuning knobs (optional): "batch_samples" (paths per wavefront), "bvh_leaf" ... returns EINVAL if unknown */
+int blingcu_set_option(blingcu_ctx *, const char *key, double value);
+
+/* sample extent of the film: x0,x1,y0,y1 inclusive (Image.hs:162-168) */
+int blingcu_sample_extent(blingcu_ctx *, int32_t *x0, int32_t *x1, int32_t *y0, int32_t *y1);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,563 @@
+// ORACLE (test infrastructure, NOT product code). See oracle_math.h header. PARITY UNPINNED.
+// Materials, lights, the path integrator, camera, film and the C API of the oracle.
+// Restates Material.hs, Texture.hs, Light.hs, Scene.hs, Integrator/Path.hs, Camera.hs, Image.hs,
+// Rendering.hs (tile decomposition) of /root/reference/src/lib/Graphics/Bling.
+#include "oracle_shade.h"
+#include "oracle.h"
+#include <atomic>
+#include <chrono>
+#include <string>
+#include <thread>
+
+namespace orc {
+
+struct Scene {
+   Geometry geo;
+   std::vector<blingcu_material> materials;
+   std::vector<blingcu_texture> textures;
+   std::vector<blingcu_light> lights;
+   std::vector<blingcu_envmap> envs;
+   std::vector<std::vector<float>> envData;  // owns copies of env arrays
+   std::vector<int> triMaterial;
+   std::vector<float> triNormals;  // 9 per tri or empty
+   blingcu_camera cam;
+   SpectralTables T;
+   int W, H;
+   float fw, fh;
+   float ftbl[256];
+   int samplerKind, nu, nv, maxDepth, sampleDepth;
+   bool useKd = true;
+   // film
+   std::vector<float> film;  // H*W*4
+   // stats
+   std::atomic<uint64_t> nSamples{0}, rCam{0}, rExt{0}, rMis{0}, rShadow{0}, dropped{0};
+};
+
+struct RayCounters { uint64_t cam = 0, ext = 0, mis = 0, shadow = 0; };
+
+// ----------------------------------------------------------------------------- textures (Texture.hs:159-207)
+static Spec evalSpectrumTexture(const Scene &sc, int id, const DG &dg) {
+   for (int guard = 0; guard < 16; ++guard) {
+      const blingcu_texture &t = sc.textures[id];
+      if (t.kind == BLINGCU_TEX_CONSTANT) return fromC(t.s);
+      // graphPaper lw m p l (Texture.hs:191-207) with uvMapping (:166-170)
+      float lw = t.f[0];
+      float x = t.f[1] * dg.u + t.f[3], z = t.f[2] * dg.v + t.f[4];
+      float xi = std::trunc(x), zi = std::trunc(z);  // properFraction: integer part truncates toward zero
+      float xpp = x - xi, zpp = z - zi;
+      float xp = std::fabs(xpp), zp = std::fabs(zpp);
+      float lo = lw / 2, hi = 1.0f - lo;
+      if (xp < lo || zp < lo || xp > hi || zp > hi) id = t.child[1]; else id = t.child[0];
+   }
+   return sConst(0);
+}
+
+// ----------------------------------------------------------------------------- materials (Material.hs:32-96)
+static BxDF mkLambertian(const Spec &r) { BxDF b{}; b.kind = K_LAMBERT; b.type = BX_REFLECTION | BX_DIFFUSE; b.r = r; return b; }
+static BxDF mkOrenNayar(const Spec &r, float sig) {  // Diffuse.hs:29-36
+   BxDF b{}; b.kind = K_ORENNAYAR; b.type = BX_REFLECTION | BX_DIFFUSE; b.r = r;
+   float s = clampf(sig, 0, 1); float sig2 = s * s;
+   b.a = 1 - (sig2 / (2 * (sig2 + 0.33f)));
+   b.b = 0.45f * sig2 / (sig2 + 0.09f);
+   return b;
+}
+static float fixExponent(float e) { return (e > 10000 || std::isnan(e)) ? 10000 : e; }  // Microfacet.hs:127-129
+
+// Primitive.hs:57-65 mkIntersection: bsdf = mat dg (shadingGeometry p dg mempty); Reflection.hs:209-225 mkBsdf'
+static Bsdf makeBsdf(const Scene &sc, const Hit &hit) {
+   const Prim &pr = sc.geo.prims[hit.prim];
+   DG dgs = hit.dg;
+   int matId;
+   if (pr.is_tri) {
+      matId = sc.triMaterial[pr.idx];
+      if (!sc.triNormals.empty()) {  // triangleShadingGeometry (TriangleMesh.hs:122-134) with o2w = mempty
+         const float *N = &sc.triNormals[9 * (size_t)pr.idx];
+         V3 n0 = mk(N[0], N[1], N[2]), n1 = mk(N[3], N[4], N[5]), n2 = mk(N[6], N[7], N[8]);
+         float b1 = hit.dg.b1, b2 = hit.dg.b2, b0 = 1 - b1 - b2;
+         V3 nsp = (scl(b0, n0) + scl(b1, n1)) + scl(b2, n2);
+         V3 ns = normalize(nsp);  // transNormal identity
+         V3 ssp = normalize(hit.dg.dpdu);
+         V3 tsp = cross(ssp, ns);
+         if (sqLen(tsp) > 0) { dgs.dpdu = cross(normalize(tsp), ns); dgs.dpdv = normalize(tsp); }
+         else { Frame f = coordinateSystem(ns); dgs.dpdu = f.s; dgs.dpdv = f.t; }
+         dgs.n = ns;
+      }
+   } else matId = sc.geo.shapes[pr.idx].material;
+   const blingcu_material &m = sc.materials[matId];
+   Bsdf b; b.n = 0;
+   switch (m.kind) {
+   case BLINGCU_MAT_MATTE: {
+      Spec r = evalSpectrumTexture(sc, m.tex[0], dgs);
+      float s = m.f[0];
+      b.bx[0] = (s == 0) ? mkLambertian(r) : mkOrenNayar(r, s);
+      b.n = 1; break;
+   }
+   case BLINGCU_MAT_GLASS: {
+      Spec r = sClamp(0, 1, evalSpectrumTexture(sc, m.tex[0], dgs));
+      Spec t = sClamp(0, 1, evalSpectrumTexture(sc, m.tex[1], dgs));
+      float ior = m.f[0];
+      BxDF refl{}; refl.kind = K_SPECREFL; refl.type = BX_REFLECTION | BX_SPECULAR; refl.r = r; refl.fr = FR_DIELECTRIC; refl.etai = 1; refl.etat = ior;
+      BxDF tr{}; tr.kind = K_SPECTRANS; tr.type = BX_TRANSMISSION | BX_SPECULAR; tr.r = t; tr.etai = 1; tr.etat = ior;
+      b.bx[0] = refl; b.bx[1] = tr; b.n = 2; break;
+   }
+   case BLINGCU_MAT_MIRROR: {
+      BxDF refl{}; refl.kind = K_SPECREFL; refl.type = BX_REFLECTION | BX_SPECULAR; refl.fr = FR_NOOP;
+      refl.r = sClamp(0, 1, evalSpectrumTexture(sc, m.tex[0], dgs));
+      b.bx[0] = refl; b.n = 1; break;
+   }
+   case BLINGCU_MAT_PLASTIC: {
+      Spec rd = evalSpectrumTexture(sc, m.tex[0], dgs), rs = evalSpectrumTexture(sc, m.tex[1], dgs);
+      BxDF spec{}; spec.kind = K_MICROFACET; spec.type = BX_REFLECTION | BX_GLOSSY; spec.r = rs;
+      spec.fr = FR_DIELECTRIC; spec.etai = 1.0f; spec.etat = 1.5f; spec.e = fixExponent(1 / m.f[0]);
+      b.bx[0] = mkLambertian(rd); b.bx[1] = spec; b.n = 2; break;
+   }
+   case BLINGCU_MAT_METAL: {
+      BxDF spec{}; spec.kind = K_MICROFACET; spec.type = BX_REFLECTION | BX_GLOSSY; spec.r = sConst(1);
+      spec.fr = FR_CONDUCTOR; spec.eta = evalSpectrumTexture(sc, m.tex[0], dgs); spec.k = evalSpectrumTexture(sc, m.tex[1], dgs);
+      spec.e = fixExponent(1 / m.f[0]);
+      b.bx[0] = spec; b.n = 1; break;
+   }
+   default: break;  // blackbody: no BxDFs
+   }
+   // mkBsdf (Reflection.hs:209-218)
+   V3 nn = dgs.n, sn = normalize(dgs.dpdu);
+   b.cs = Frame{sn, cross(nn, sn), nn};
+   b.p = dgs.p;
+   b.ng = hit.dg.n;
+   return b;
+}
+
+// ----------------------------------------------------------------------------- lights (Light.hs)
+static int hitLight(const Scene &sc, const Hit &h) {  // intLight
+   const Prim &pr = sc.geo.prims[h.prim];
+   return pr.is_tri ? -1 : sc.geo.shapes[pr.idx].light;
+}
+// intLe (Primitive.hs:68-76) + lEmit (Light.hs:85-96)
+static Spec intLe(const Scene &sc, const Hit &h, V3 wo) {
+   int li = hitLight(sc, h);
+   if (li < 0) return sConst(0);
+   const blingcu_light &l = sc.lights[li];
+   if (l.kind != BLINGCU_LIGHT_AREA) return sConst(0);
+   return (dot(h.dg.n, wo) > 0) ? fromC(l.s) : sConst(0);
+}
+// le (Light.hs:98-106)
+static Spec lightLe(const Scene &sc, const blingcu_light &l, const Ray &ray) {
+   if (l.kind != BLINGCU_LIGHT_INFINITE) return sConst(0);
+   const blingcu_envmap &e = sc.envs[l.env];
+   V3 wh = normalize(transVector(e.w2l, ray.d));
+   float phi = sphericalPhi(wh), theta = sphericalTheta(wh);
+   return envEval(sc.T, e, phi / (2 * kPi), theta / kPi);   // sphToCart, Types.hs:36-39
+}
+struct LightSample { Spec de; V3 wi; Ray testRay; float pdf; bool delta; };
+// Light.hs:122-160
+static LightSample lightSample(const Scene &sc, const blingcu_light &l, V3 p, float eps, V3 n, float u1, float u2) {
+   LightSample black{sConst(0), mk(0, 1, 0), Ray{mk(0, 0, 0), mk(0, 1, 0), 0, 1}, 0, false};
+   switch (l.kind) {
+   case BLINGCU_LIGHT_INFINITE: {
+      const blingcu_envmap &e = sc.envs[l.env];
+      float u, v, mapPdf;
+      sampleContinuous2D(e, u1, u2, u, v, mapPdf);
+      if (mapPdf == 0) return black;
+      float phi = u * 2 * kPi, theta = v * kPi;  // cartToSph, Types.hs:31-33
+      float sint = std::sin(theta);
+      if (sint == 0) return black;
+      Spec ls = envEval(sc.T, e, u, v);
+      V3 wi = transVector(e.l2w, sphericalDirection(std::sin(theta), std::cos(theta), phi));
+      return LightSample{ls, wi, Ray{p, wi, eps, kInf}, mapPdf / (2 * kPi * kPi * sint), false};
+   }
+   case BLINGCU_LIGHT_DIRECTIONAL: {
+      V3 d = mk(l.v[0], l.v[1], l.v[2]);
+      return LightSample{sScale(fromC(l.s), absDot(n, d)), d, Ray{p, d, eps, kInf}, 1, true};
+   }
+   case BLINGCU_LIGHT_POINT: {
+      V3 pos = mk(l.v[0], l.v[1], l.v[2]);
+      return LightSample{sScale(fromC(l.s), 1 / sqLen(pos - p)), normalize(pos - p), Ray{p, pos - p, eps, kInf}, 1, true};
+   }
+   default: {  // AreaLight: sample in light-local space (Q11)
+      const blingcu_shape &s = sc.geo.shapes[l.shape];
+      V3 pl = transPoint(s.w2o, p);
+      V3 ps, ns; sampleShape(s, pl, u1, u2, ps, ns);
+      V3 wi = normalize(ps - pl);
+      float pd = shapePdf(s, pl, wi);
+      Ray ray{pl, wi, eps, len(ps - pl) - eps};
+      Spec r = (dot(ns, wi) < 0) ? fromC(l.s) : sConst(0);
+      return LightSample{r, transVector(s.o2w, wi), transRay(s.o2w, ray), pd, false};
+   }
+   }
+}
+// Light.hs:215-229
+static float lightPdf(const Scene &sc, const blingcu_light &l, V3 p, V3 wiW) {
+   switch (l.kind) {
+   case BLINGCU_LIGHT_INFINITE: {
+      const blingcu_envmap &e = sc.envs[l.env];
+      V3 w = transVector(e.w2l, wiW);
+      float phi = sphericalPhi(w), theta = sphericalTheta(w);
+      float sint = std::sin(theta);
+      if (sint == 0) return 0;
+      return pdfDist2D(e, phi / (2 * kPi), theta / kPi) / (2 * kPi * kPi * sint);
+   }
+   case BLINGCU_LIGHT_AREA: {
+      const blingcu_shape &s = sc.geo.shapes[l.shape];
+      return shapePdf(s, transPoint(s.w2o, p), transVector(s.w2o, wiW));
+   }
+   default: return 0;
+   }
+}
+
+static Hit sceneIntersect(const Scene &sc, const Ray &r) { return sc.useKd ? sc.geo.kdNearest(r) : sc.geo.bruteNearest(r); }  // Scene.hs:49-51
+static bool sceneOccluded(const Scene &sc, const Ray &r) { return sc.useKd ? sc.geo.kdOccluded(r) : sc.geo.bruteOccluded(r); }  // Scene.hs:45-47
+
+// Scene.hs:61-69
+static Spec sampleLightMis(const Scene &sc, const LightSample &ls, const Bsdf &bsdf, V3 wo, RayCounters &rc) {
+   if (ls.pdf == 0 || isBlack(ls.de)) return sConst(0);
+   Spec f = evalBsdf(bsdf, wo, ls.wi);
+   if (isBlack(f)) return sConst(0);
+   rc.shadow++;
+   if (sceneOccluded(sc, ls.testRay)) return sConst(0);
+   if (ls.delta) return sScale(f * ls.de, 1 / ls.pdf);
+   float weight = powerHeuristic(1, ls.pdf, 1, bsdfPdf(bsdf, wo, ls.wi));
+   return sScale(f * ls.de, weight / ls.pdf);
+}
+// Scene.hs:71-82
+static Spec sampleBsdfMis(const Scene &sc, int lightIdx, const BsdfSample &bs, V3 p, float epsilon, RayCounters &rc) {
+   if (bs.pdf == 0 || isBlack(bs.f)) return sConst(0);
+   const blingcu_light &l = sc.lights[lightIdx];
+   Ray ray{p, bs.wi, epsilon, kInf};
+   rc.mis++;
+   Hit lint = sceneIntersect(sc, ray);
+   Spec li;
+   if (lint.valid) {
+      int hl = hitLight(sc, lint);
+      if (hl < 0) return sConst(0);
+      // Eq Light: only two area lights with the same id are equal (Light.hs:48-50)
+      if (!(sc.lights[hl].kind == BLINGCU_LIGHT_AREA && l.kind == BLINGCU_LIGHT_AREA && hl == lightIdx)) return sConst(0);
+      li = intLe(sc, lint, -bs.wi);
+   } else li = lightLe(sc, l, ray);
+   float lPdf = lightPdf(sc, l, p, bs.wi);
+   return sScale(bs.f * li, powerHeuristic(1, bs.pdf, 1, lPdf));  // Q3: also for specular samples
+}
+
+// ----------------------------------------------------------------------------- camera (Camera.hs:49-76)
+static Ray fireRay(const Scene &sc, float ix, float iy, float lu, float lv) {
+   const blingcu_camera &c = sc.cam;
+   if (c.kind == BLINGCU_CAM_ENVIRONMENT) {
+      float t = kPi * iy / c.env_sy, p = 2 * kPi * ix / c.env_sx;
+      Ray r{mk(0, 0, 0), mk(std::sin(t) * std::cos(p), std::cos(t), std::sin(t) * std::sin(p)), 0, kInf};
+      return transRay(c.cam2world, r);
+   }
+   V3 pCamera = transPoint(c.raster2cam, mk(ix, iy, 0));
+   Ray ray{mk(0, 0, 0), normalize(pCamera), 0, kInf};
+   if (c.lens_radius > 0) {
+      float dx, dy; concentricSampleDisk(lu, lv, dx, dy);
+      V3 ro = mk(dx * c.lens_radius, dy * c.lens_radius, 0);
+      V3 pFocus = rayAt(ray, c.focal_distance / ray.d.z);
+      ray = Ray{ro, normalize(pFocus - ro), 0, kInf};
+   }
+   return transRay(c.cam2world, ray);
+}
+
+// ----------------------------------------------------------------------------- Integrator/Path.hs:41-87
+static Spec pathLi(const Scene &sc, const SampleCtx &smp, Ray ray, RayCounters &rc) {
+   const int md = sc.maxDepth;
+   Spec t = sConst(1), l = sConst(0);
+   bool spec = true;
+   rc.cam++;
+   Hit hit = sceneIntersect(sc, ray);
+   for (int depth = 0;; ++depth) {
+      if (!hit.valid) {
+         if (spec) {  // :44
+            Spec s = sConst(0);
+            for (const blingcu_light &lt : sc.lights) s = s + lightLe(sc, lt, ray);
+            return l + t * s;
+         }
+         return l;  // :47
+      }
+      if (depth == md) return l;  // :51
+      float lNumU = rnd1D(smp, 1 + 4 * depth);
+      float lDir1, lDir2; rnd2D(smp, 1 + 3 * depth, lDir1, lDir2);
+      float bCompU = rnd1D(smp, 2 + 4 * depth);
+      float bDir1, bDir2; rnd2D(smp, 2 + 3 * depth, bDir1, bDir2);
+      V3 rd = ray.d;
+      Spec intl = spec ? intLe(sc, hit, rd) : sConst(0);  // Q1: ray direction, not wo
+      V3 wo = -rd;
+      Bsdf bsdf = makeBsdf(sc, hit);
+      V3 n = bsdf.cs.n, p = bsdf.p;
+      float eps = hit.eps;
+      // sampleOneLight (Scene.hs:110-118) / estimateDirect (:84-99)
+      Spec direct = sConst(0);
+      int lc = (int)sc.lights.size();
+      if (lc > 0) {
+         int ln = (lc == 1) ? 0 : std::min((int)std::floor(lNumU * (float)lc), lc - 1);
+         const blingcu_light &lt = sc.lights[ln];
+         Spec ls = sampleLightMis(sc, lightSample(sc, lt, p, eps, n, lDir1, lDir2), bsdf, wo, rc);
+         Spec bs = sampleBsdfMis(sc, ln, sampleBsdf(bsdf, wo, bCompU, bDir1, bDir2), p, eps, rc);
+         direct = ls + bs;
+         if (lc > 1) direct = sScale(direct, (float)lc);
+      }
+      Spec lHere = intl + direct;
+      l = l + t * lHere;
+      float pc = (depth <= 7) ? 1.0f : hmin(0.75f, sY(sc.T, t));
+      float x = rnd1D(smp, 3 + 4 * depth);
+      if (x > pc) return l;
+      float uc = rnd1D(smp, 0 + 4 * depth);
+      float ud1, ud2; rnd2D(smp, 0 + 3 * depth, ud1, ud2);
+      BsdfSample s = sampleBsdf(bsdf, wo, uc, ud1, ud2);
+      if (s.pdf == 0 || isBlack(s.f)) return l;
+      ray = Ray{p, s.wi, eps, kInf};
+      spec = (s.type & BX_SPECULAR) != 0;
+      t = sScale(s.f * t, 1 / pc);
+      rc.ext++;
+      hit = sceneIntersect(sc, ray);
+   }
+}
+
+// ----------------------------------------------------------------------------- film (Image.hs)
+struct Window { int x0, x1, y0, y1; };  // inclusive (Sampling.hs:36-41)
+static Window sampleExtent(const Scene &sc) {  // Image.hs:162-168
+   return Window{(int)std::floor(0.5f - sc.fw), (int)std::floor(0.5f + (float)sc.W + sc.fw),
+                 (int)std::floor(0.5f - sc.fh), (int)std::floor(0.5f + (float)sc.H + sc.fh)};
+}
+struct TileImage { int w, h, ox, oy; std::vector<float> px; };
+static TileImage mkImageTile(const Scene &sc, const Window &wnd) {  // Image.hs:108-120
+   TileImage t;
+   t.ox = std::max(0, wnd.x0); t.oy = std::max(0, wnd.y0);
+   t.w = wnd.x1 - t.ox + (int)std::floor(0.5f + sc.fw);
+   t.h = wnd.y1 - t.oy + (int)std::floor(0.5f + sc.fh);
+   t.px.assign((size_t)std::max(0, t.w) * std::max(0, t.h) * 4, 0.0f);
+   return t;
+}
+// Image.hs:250-299
+static bool addSample(const Scene &sc, TileImage &img, float sx, float sy, const Spec &ss) {
+   if (sNaN(ss) || sInfinite(ss)) return false;
+   float smx, smy, smz; spectrumToXYZ(sc.T, ss, smx, smy, smz);
+   float fw = sc.fw, fh = sc.fh;
+   float ifw = 1 / fw, ifh = 1 / fw;  // Q10: ifh = 1 / fw
+   float dx = sx - 0.5f, dy = sy - 0.5f;
+   int x0 = std::max(img.ox, (int)std::ceil(dx - fw)), x1 = std::min(img.ox + img.w - 1, (int)std::floor(dx + fw));
+   int y0 = std::max(img.oy, (int)std::ceil(dy - fh)), y1 = std::min(img.oy + img.h - 1, (int)std::floor(dy + fh));
+   if ((x1 - x0) < 0 || (y1 - y0) < 0) return true;
+   for (int y = y0; y <= y1; ++y) {
+      float fy = std::fabs(((float)y - dy) * ifh * 16.0f);
+      int iy = std::min((int)std::floor(fy), 15);
+      for (int x = x0; x <= x1; ++x) {
+         float fx = std::fabs(((float)x - dx) * ifw * 16.0f);
+         int ix = std::min((int)std::floor(fx), 15);
+         float w = sc.ftbl[iy * 16 + ix];
+         float *p = &img.px[4 * ((size_t)(x - img.ox) + (size_t)(y - img.oy) * img.w)];
+         p[0] = p[0] + w;
+         p[1] = p[1] + smx * w;
+         p[2] = p[2] + smy * w;
+         p[3] = p[3] + smz * w;
+      }
+   }
+   return true;
+}
+static void addTile(Scene &sc, const TileImage &t) {  // Image.hs:178-199
+   for (int y = 0; y < t.h; ++y) for (int x = 0; x < t.w; ++x) {
+      int fx = x + t.ox, fy = y + t.oy;
+      if (fy >= sc.H || fx >= sc.W) continue;
+      float *d = &sc.film[4 * ((size_t)fy * sc.W + fx)];
+      const float *s = &t.px[4 * ((size_t)y * t.w + x)];
+      for (int o = 0; o < 4; ++o) d[o] = d[o] + s[o];
+   }
+}
+
+static SampleCtx mkSampleCtx(const Scene &sc, const Window &ext, uint64_t seed, uint32_t pass, int ix, int iy, uint32_t s) {
+   uint32_t ew = (uint32_t)(ext.x1 - ext.x0 + 1);
+   uint32_t pix = (uint32_t)(iy - ext.y0) * ew + (uint32_t)(ix - ext.x0);
+   SampleCtx c;
+   c.kp = pixelKey(seed, pass, pix); c.s = s; c.nu = sc.nu; c.nv = sc.nv;
+   c.n1d = 4 * sc.sampleDepth; c.n2d = 3 * sc.sampleDepth;
+   c.stratified = sc.samplerKind == BLINGCU_SAMPLER_STRATIFIED;
+   return c;
+}
+// one iteration of the `tile` body (Rendering.hs:142-150): fireRay >>= surfaceLi, then the camera sample position
+static Spec renderSample(const Scene &sc, const Window &ext, uint64_t seed, uint32_t pass, int ix, int iy, uint32_t s,
+                         float &sx, float &sy, RayCounters &rc) {
+   SampleCtx c = mkSampleCtx(sc, ext, seed, pass, ix, iy, s);
+   float ox, oy, lu, lv; cameraSample(c, ox, oy, lu, lv);
+   sx = (float)ix + ox; sy = (float)iy + oy;
+   Ray r = fireRay(sc, sx, sy, lu, lv);
+   return pathLi(sc, c, r, rc);
+}
+
+}  // namespace orc
+
+// =============================================================================================
+// C API
+// =============================================================================================
+using namespace orc;
+struct oracle_ctx { Scene sc; std::string err; };
+
+extern "C" {
+
+int oracle_create(const blingcu_scene *ir, int build_kdtree, oracle_ctx **out) {
+   oracle_ctx *c = new oracle_ctx();
+   Scene &sc = c->sc;
+   size_t nt = (size_t)ir->n_triangles;
+   sc.geo.tris.resize(nt);
+   sc.triMaterial.resize(nt);
+   size_t nprims = nt + ir->n_shapes;
+   sc.geo.prims.resize(nprims);
+   std::vector<char> seen(nprims, 0);
+   for (size_t i = 0; i < nt; ++i) {
+      const float *v = ir->tri_verts + 9 * i;
+      Tri &T = sc.geo.tris[i];
+      T.p1 = mk(v[0], v[1], v[2]); T.p2 = mk(v[3], v[4], v[5]); T.p3 = mk(v[6], v[7], v[8]);
+      for (int k = 0; k < 6; ++k) T.uv[k] = ir->tri_uvs[6 * i + k];
+      sc.triMaterial[i] = ir->tri_material[i];
+      size_t pid = ir->tri_prim_id ? (size_t)ir->tri_prim_id[i] : (size_t)ir->tri_prim_id_base + i;
+      if (pid >= nprims || seen[pid]) { delete c; return BLINGCU_EINVAL; }
+      seen[pid] = 1;
+      AABB wb = extendP(extendP(extendP(emptyBox(), T.p1), T.p2), T.p3);  // TriangleMesh.hs:136-138
+      sc.geo.prims[pid] = Prim{true, (uint32_t)i, wb};
+   }
+   if (ir->tri_normals) sc.triNormals.assign(ir->tri_normals, ir->tri_normals + 9 * nt);
+   sc.geo.shapes.assign(ir->shapes, ir->shapes + ir->n_shapes);
+   for (uint32_t i = 0; i < ir->n_shapes; ++i) {
+      size_t pid = (size_t)ir->shapes[i].prim_id;
+      if (pid >= nprims || seen[pid]) { delete c; return BLINGCU_EINVAL; }
+      seen[pid] = 1;
+      sc.geo.prims[pid] = Prim{false, i, transBox(ir->shapes[i].o2w, shapeObjectBounds(ir->shapes[i]))};  // Shape.hs:287-294
+   }
+   sc.materials.assign(ir->materials, ir->materials + ir->n_materials);
+   sc.textures.assign(ir->textures, ir->textures + ir->n_textures);
+   sc.lights.assign(ir->lights, ir->lights + ir->n_lights);
+   sc.envs.assign(ir->envs, ir->envs + ir->n_envs);
+   for (blingcu_envmap &e : sc.envs) {  // own the arrays
+      auto own = [&](const float *&p, size_t n) {
+         if (!p) return;
+         sc.envData.emplace_back(p, p + n);
+         p = sc.envData.back().data();
+      };
+      size_t nu = (size_t)e.nu, nv = (size_t)e.nv;
+      if (e.kind == BLINGCU_ENV_RGBTABLE) own(e.rgb, nu * nv * 3);
+      own(e.cond_func, nu * nv); own(e.cond_cdf, (nu + 1) * nv); own(e.cond_int, nv);
+      own(e.marg_func, nv); own(e.marg_cdf, nv + 1);
+   }
+   sc.cam = ir->camera;
+   sc.T.cieX = fromC(ir->cie_x); sc.T.cieY = fromC(ir->cie_y); sc.T.cieZ = fromC(ir->cie_z); sc.T.ySum = ir->cie_y_sum;
+   for (int i = 0; i < 7; ++i) sc.T.illum[i] = fromC(ir->illum_basis[i]);
+   sc.W = ir->width; sc.H = ir->height; sc.fw = ir->filter_w; sc.fh = ir->filter_h;
+   std::memcpy(sc.ftbl, ir->filter_table, sizeof(sc.ftbl));
+   sc.samplerKind = ir->sampler_kind; sc.nu = ir->nu; sc.nv = ir->nv;
+   sc.maxDepth = ir->max_depth; sc.sampleDepth = ir->sample_depth;
+   sc.film.assign((size_t)sc.W * sc.H * 4, 0.0f);
+   sc.useKd = build_kdtree != 0;
+   if (sc.useKd) sc.geo.buildKd();
+   *out = c;
+   return 0;
+}
+void oracle_destroy(oracle_ctx *c) { delete c; }
+
+static Ray toRay(const blingcu_ray &r) { return Ray{mk(r.o[0], r.o[1], r.o[2]), mk(r.d[0], r.d[1], r.d[2]), r.tmin, r.tmax}; }
+
+// mode 0 = brute force (ground truth), 1 = kd-tree
+int oracle_trace_nearest(oracle_ctx *c, const blingcu_ray *rays, size_t n, blingcu_hit *out, int mode,
+                         uint64_t *nodes_traversed, uint64_t *intersections) {
+   if (mode == 1 && !c->sc.geo.kd_built) return BLINGCU_ESTATE;
+   uint64_t nt = 0, ni = 0;
+   for (size_t i = 0; i < n; ++i) {
+      Ray r = toRay(rays[i]);
+      Hit h = (mode == 1) ? c->sc.geo.kdNearest(r, &nt, &ni) : c->sc.geo.bruteNearest(r);
+      out[i].t = h.valid ? h.t : 0; out[i].prim = h.valid ? h.prim : -1;
+      out[i].b1 = (h.valid && h.dg.tri) ? h.dg.b1 : 0; out[i].b2 = (h.valid && h.dg.tri) ? h.dg.b2 : 0;
+   }
+   if (nodes_traversed) *nodes_traversed = nt;
+   if (intersections) *intersections = ni;
+   return 0;
+}
+int oracle_trace_occluded(oracle_ctx *c, const blingcu_ray *rays, size_t n, uint8_t *out, int mode) {
+   if (mode == 1 && !c->sc.geo.kd_built) return BLINGCU_ESTATE;
+   for (size_t i = 0; i < n; ++i) {
+      Ray r = toRay(rays[i]);
+      out[i] = (mode == 1) ? c->sc.geo.kdOccluded(r) : c->sc.geo.bruteOccluded(r);
+   }
+   return 0;
+}
+
+int oracle_sample_extent(oracle_ctx *c, int32_t *x0, int32_t *x1, int32_t *y0, int32_t *y1) {
+   Window w = sampleExtent(c->sc);
+   *x0 = w.x0; *x1 = w.x1; *y0 = w.y0; *y1 = w.y1;
+   return 0;
+}
+
+int oracle_render_samples(oracle_ctx *c, uint32_t pass, uint64_t seed, const int32_t *px, const int32_t *py,
+                          const uint32_t *sample, size_t n, float *out_L, float *out_xy) {
+   Window ext = sampleExtent(c->sc);
+   RayCounters rc;
+   for (size_t i = 0; i < n; ++i) {
+      float sx, sy;
+      Spec L = renderSample(c->sc, ext, seed, pass, px[i], py[i], sample[i], sx, sy, rc);
+      std::memcpy(out_L + 16 * i, L.v, sizeof(L.v));
+      out_xy[2 * i] = sx; out_xy[2 * i + 1] = sy;
+   }
+   return 0;
+}
+
+// one pass slice with the reference's decomposition: 16x16 sample windows (Sampling.hs:55-58), one worker per
+// tile (parBuffer numCapabilities, Rendering.hs:118), sequential addTile (:130-134).
+int oracle_render_slice(oracle_ctx *c, uint32_t pass, uint64_t seed, uint32_t s_begin, uint32_t s_end, int nthreads) {
+   Scene &sc = c->sc;
+   Window ext = sampleExtent(sc);
+   std::vector<Window> wnds;
+   for (int y = ext.y0; y <= ext.y1; y += 16) for (int x = ext.x0; x <= ext.x1; x += 16)
+      wnds.push_back(Window{x, std::min(x + 15, ext.x1), y, std::min(y + 15, ext.y1)});
+   std::vector<TileImage> tiles(wnds.size());
+   std::atomic<size_t> next{0};
+   auto worker = [&]() {
+      RayCounters rc; uint64_t ns = 0, nd = 0;
+      for (;;) {
+         size_t ti = next.fetch_add(1);
+         if (ti >= wnds.size()) break;
+         const Window &w = wnds[ti];
+         TileImage img = mkImageTile(sc, w);
+         for (int iy = w.y0; iy <= w.y1; ++iy) for (int ix = w.x0; ix <= w.x1; ++ix)
+            for (uint32_t s = s_begin; s < s_end; ++s) {
+               float sx, sy;
+               Spec L = renderSample(sc, ext, seed, pass, ix, iy, s, sx, sy, rc);
+               if (!addSample(sc, img, sx, sy, L)) nd++;
+               ns++;
+            }
+         tiles[ti] = std::move(img);
+      }
+      sc.nSamples += ns; sc.dropped += nd;
+      sc.rCam += rc.cam; sc.rExt += rc.ext; sc.rMis += rc.mis; sc.rShadow += rc.shadow;
+   };
+   if (nthreads <= 1) worker();
+   else {
+      std::vector<std::thread> th;
+      for (int i = 0; i < nthreads; ++i) th.emplace_back(worker);
+      for (auto &t : th) t.join();
+   }
+   for (const TileImage &t : tiles) addTile(sc, t);
+   return 0;
+}
+
+int oracle_read_film(oracle_ctx *c, float *wxyz) { std::memcpy(wxyz, c->sc.film.data(), c->sc.film.size() * sizeof(float)); return 0; }
+int oracle_clear_film(oracle_ctx *c) { std::fill(c->sc.film.begin(), c->sc.film.end(), 0.0f); return 0; }
+int oracle_get_stats(oracle_ctx *c, blingcu_stats *s) {
+   std::memset(s, 0, sizeof(*s));
+   s->samples = c->sc.nSamples; s->rays_camera = c->sc.rCam; s->rays_extension = c->sc.rExt;
+   s->rays_mis = c->sc.rMis; s->rays_shadow = c->sc.rShadow; s->dropped_samples = c->sc.dropped;
+   s->bvh_nodes = c->sc.geo.nodes.size(); s->bvh_leaf_items = c->sc.geo.leafPrims.size();
+   return 0;
+}
+int oracle_reset_stats(oracle_ctx *c) {
+   c->sc.nSamples = 0; c->sc.rCam = 0; c->sc.rExt = 0; c->sc.rMis = 0; c->sc.rShadow = 0; c->sc.dropped = 0;
+   return 0;
+}
+
+// unit-test hooks: BSDF sampling/evaluation of a material at a canonical frame, filter/film on a single tile
+int oracle_add_sample_tile(oracle_ctx *c, int wx0, int wx1, int wy0, int wy1, float sx, float sy, const float *L16,
+                           float *out_tile, int *ox, int *oy, int *w, int *h) {
+   Window wnd{wx0, wx1, wy0, wy1};
+   TileImage img = mkImageTile(c->sc, wnd);
+   Spec s; std::memcpy(s.v, L16, sizeof(s.v));
+   addSample(c->sc, img, sx, sy, s);
+   *ox = img.ox; *oy = img.oy; *w = img.w; *h = img.h;
+   if (out_tile) std::memcpy(out_tile, img.px.data(), img.px.size() * sizeof(float));
+   return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,29 @@
+/* ORACLE (test infrastructure, NOT product code): C API of the CPU restatement of waldheinz/bling's
+ * path-integrator hot path. PARITY UNPINNED (no reference golden vectors exist; GHC absent).
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it. */
+#ifndef BLING_ORACLE_H
+#define BLING_ORACLE_H
+#include "../include/blingcu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+typedef struct oracle_ctx oracle_ctx;
+int oracle_create(const blingcu_scene *ir, int build_kdtree, oracle_ctx **out);
+void oracle_destroy(oracle_ctx *);
+int oracle_trace_nearest(oracle_ctx *, const blingcu_ray *rays, size_t n, blingcu_hit *out, int mode,
+                         uint64_t *nodes_traversed, uint64_t *intersections);
+int oracle_trace_occluded(oracle_ctx *, const blingcu_ray *rays, size_t n, uint8_t *out, int mode);
+int oracle_sample_extent(oracle_ctx *, int32_t *x0, int32_t *x1, int32_t *y0, int32_t *y1);
+int oracle_render_samples(oracle_ctx *, uint32_t pass, uint64_t seed, const int32_t *px, const int32_t *py,
+                          const uint32_t *sample, size_t n, float *out_L, float *out_xy);
+int oracle_render_slice(oracle_ctx *, uint32_t pass, uint64_t seed, uint32_t s_begin, uint32_t s_end, int nthreads);
+int oracle_read_film(oracle_ctx *, float *wxyz);
+int oracle_clear_film(oracle_ctx *);
+int oracle_get_stats(oracle_ctx *, blingcu_stats *);
+int oracle_reset_stats(oracle_ctx *);
+int oracle_add_sample_tile(oracle_ctx *, int wx0, int wx1, int wy0, int wy1, float sx, float sy, const float *L16,
+                           float *out_tile, int *ox, int *oy, int *w, int *h);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,53 @@
+#!/usr/bin/env python
+"""Flattens the reference's example scenes (BASELINE.json configs 1-4) into IR fixtures under
+tests/golden/scenes/. Needs /root/reference (build container only); the fixtures travel to the GPU box.
+Per-config fix-ups follow SURVEY.md §8(d) / BASELINE.md and are listed inline.
+
+    python tools/make_scenes.py
+"""
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from bling_b200.host.envmap import synthetic_hdr  # noqa: E402
+from bling_b200.host.loader import load_scene  # noqa: E402
+
+EX = Path("/root/reference/examples")
+OUT = ROOT / "tests" / "golden" / "scenes"
+
+RGB_FIX = [(r"emission\s*\{\s*rgb\b", "emission { rgbI"), (r"\brgb\b", "rgbR")]
+
+CONFIGS = {
+    # cfg 1: the last renderer line selects SPPM (:24) -> dropped; 512x512; stratified 8 8
+    "cornell-box": dict(file="cornell-box.bling", drop_lines=(24,), image_size=(512, 512), sampler=("stratified", 8, 8)),
+    # cfg 2a: parses as shipped (it holds a glass BOX); 1024x1024; 64 spp
+    "glass-torus": dict(file="glass-torus.bling", image_size=(1024, 1024), sampler=("stratified", 8, 8)),
+    # cfg 2b: stale syntax: `stratified xSamples 2 ySamples 2`, sppm without maxDepth, graphPaper without map{}, rgb spectra
+    "specular": dict(file="specular.bling", image_size=(1024, 1024), sampler=("stratified", 8, 8),
+                     fixups=[(r"stratified xSamples 2 ySamples 2", "stratified 8 8"),
+                             (r"renderer \{ sppm photonCount 5000 radius 0.5 \}", ""),
+                             (r"graphPaper 0.1", "graphPaper 0.1 map { uv 1 1 0 0 }")] + RGB_FIX),
+    # cfg 3: 1920x1080, stratified 16 16
+    "ducky": dict(file="ducky.bling", image_size=(1920, 1080), sampler=("stratified", 16, 16)),
+    # cfg 4a: graphPaper lacks map{}; last renderer is SPPM (:20)
+    "sun-sky": dict(file="sun-sky.bling", image_size=(1920, 1080), sampler=("stratified", 8, 8), drop_lines=(20,),
+                    fixups=[(r"graphPaper 0.05", "graphPaper 0.05 map { uv 10 10 0 0 }")]),
+    # cfg 4b: the HDR is a missing blob -> synthetic 1024x512 map; the SPPM renderer precedes the sampler one, fine
+    "environment": dict(file="environment.bling", image_size=(1920, 1080), env_files={"*": synthetic_hdr()}),
+}
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    for name, cfg in CONFIGS.items():
+        cfg = dict(cfg)
+        ir = load_scene(EX / cfg.pop("file"), name=name, **cfg)
+        ir.save(OUT / f"{name}.npz")
+        print(f"{name}: {len(ir.tri_verts)} tris, {len(ir.shapes)} shapes, {len(ir.lights)} lights, "
+              f"{len(ir.materials)} materials, {ir.width}x{ir.height}, {ir.nu}x{ir.nv} spp, "
+              f"depth {ir.max_depth}/{ir.sample_depth}, extent {ir.sample_extent()}")
+
+
+if __name__ == "__main__":
+    main()
