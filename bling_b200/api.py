@@ -1,0 +1,171 @@
+"""ctypes binding of the C ABI in include/blingcu.h (libblingcu.so).
+
+There is NO CPU fallback: importing is cheap, but `Context()` raises if the CUDA extension is missing or no
+GPU is visible (the library returns BLINGCU_ENOGPU).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import ir as IR
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libblingcu.so"
+
+# every symbol include/blingcu.h declares
+SYMBOLS = ["create", "destroy", "last_error", "upload_scene", "trace_nearest", "trace_occluded", "trace_stats",
+           "render_pass", "render_slice", "render_samples", "read_film", "clear_film", "film_add_host", "film_device",
+           "synchronize", "get_stats", "reset_stats", "set_option", "sample_extent", "kernel_times"]
+
+
+class BlingCuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"blingcu error {code}: {msg}")
+        self.code = code
+
+
+def load_library(path=LIB_PATH, prefix="blingcu"):
+    path = Path(path)
+    if not path.exists():
+        raise ImportError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          f"(there is no CPU fallback)")
+    L = C.CDLL(str(path))
+    P = C.c_void_p
+    f = lambda n: getattr(L, f"{prefix}_{n}")
+    f("create").argtypes = [C.c_int, C.POINTER(P)]
+    f("destroy").argtypes = [P]; f("destroy").restype = None
+    f("last_error").argtypes = [P]; f("last_error").restype = C.c_char_p
+    f("upload_scene").argtypes = [P, C.POINTER(IR.SceneC)]
+    f("trace_nearest").argtypes = [P, P, C.c_size_t, P]
+    f("trace_occluded").argtypes = [P, P, C.c_size_t, P]
+    f("trace_stats").argtypes = [P, P, C.c_size_t, P, P, P]
+    f("render_pass").argtypes = [P, C.c_uint32, C.c_uint64]
+    f("render_slice").argtypes = [P, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32]
+    f("render_samples").argtypes = [P, C.c_uint32, C.c_uint64, P, P, P, C.c_size_t, P, P]
+    f("read_film").argtypes = [P, P]
+    f("clear_film").argtypes = [P]
+    f("film_add_host").argtypes = [P, P]
+    f("film_device").argtypes = [P, C.POINTER(P), C.POINTER(C.c_size_t)]
+    f("synchronize").argtypes = [P]
+    f("get_stats").argtypes = [P, C.POINTER(IR.Stats)]
+    f("reset_stats").argtypes = [P]
+    f("set_option").argtypes = [P, C.c_char_p, C.c_double]
+    f("sample_extent").argtypes = [P] + [C.POINTER(C.c_int32)] * 4
+    f("kernel_times").argtypes = [P, P, P, C.c_int]
+    return L
+
+
+class Context:
+    """One GPU context (blingcu_ctx). Mirrors the C ABI one-to-one."""
+
+    _lib_path = LIB_PATH
+    _prefix = "blingcu"
+
+    def __init__(self, device: int = 0):
+        self._L = load_library(self._lib_path, self._prefix)
+        self._h = C.c_void_p()
+        rc = self._f("create")(device, C.byref(self._h))
+        if rc != 0:
+            msg = self._f("last_error")(None)
+            self._h = None
+            raise BlingCuError(rc, (msg or b"").decode())
+        self.scene = None
+
+    def _f(self, n):
+        return getattr(self._L, f"{self._prefix}_{n}")
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise BlingCuError(rc, (self._f("last_error")(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._f("destroy")(self._h); self._h = None
+
+    def __del__(self):
+        try: self.close()
+        except Exception: pass
+
+    def __enter__(self): return self
+    def __exit__(self, *a): self.close()
+
+    # ---- scene
+    def upload_scene(self, scene: IR.SceneIR):
+        sc, keep = scene.to_c()
+        self._chk(self._f("upload_scene")(self._h, C.byref(sc)))
+        self.scene = scene
+
+    def set_option(self, key: str, value: float):
+        self._chk(self._f("set_option")(self._h, key.encode(), float(value)))
+
+    def sample_extent(self):
+        v = [C.c_int32() for _ in range(4)]
+        self._chk(self._f("sample_extent")(self._h, *[C.byref(x) for x in v]))
+        return tuple(x.value for x in v)
+
+    # ---- explicit ray batches
+    def trace_nearest(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, IR.RAY_DTYPE); out = np.zeros(len(rays), IR.HIT_DTYPE)
+        self._chk(self._f("trace_nearest")(self._h, rays.ctypes.data, len(rays), out.ctypes.data))
+        return out
+
+    def trace_occluded(self, rays: np.ndarray) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, IR.RAY_DTYPE); out = np.zeros(len(rays), np.uint8)
+        self._chk(self._f("trace_occluded")(self._h, rays.ctypes.data, len(rays), out.ctypes.data))
+        return out
+
+    def trace_stats(self, rays: np.ndarray):
+        rays = np.ascontiguousarray(rays, IR.RAY_DTYPE); out = np.zeros(len(rays), IR.HIT_DTYPE)
+        nodes = np.zeros(len(rays), np.uint32); prims = np.zeros(len(rays), np.uint32)
+        self._chk(self._f("trace_stats")(self._h, rays.ctypes.data, len(rays), out.ctypes.data, nodes.ctypes.data, prims.ctypes.data))
+        return out, nodes, prims
+
+    # ---- rendering
+    def render_pass(self, pass_index: int, seed: int):
+        self._chk(self._f("render_pass")(self._h, pass_index, seed))
+
+    def render_slice(self, pass_index: int, seed: int, s_begin: int, s_end: int):
+        self._chk(self._f("render_slice")(self._h, pass_index, seed, s_begin, s_end))
+
+    def render_samples(self, pass_index, seed, px, py, sample):
+        px = np.ascontiguousarray(px, np.int32); py = np.ascontiguousarray(py, np.int32)
+        sample = np.ascontiguousarray(sample, np.uint32); n = len(px)
+        L = np.zeros((n, 16), np.float32); xy = np.zeros((n, 2), np.float32)
+        self._chk(self._f("render_samples")(self._h, pass_index, seed, px.ctypes.data, py.ctypes.data, sample.ctypes.data, n,
+                                            L.ctypes.data, xy.ctypes.data))
+        return L, xy
+
+    def read_film(self, out: np.ndarray = None) -> np.ndarray:
+        if out is None:
+            out = np.zeros((self.scene.height, self.scene.width, 4), np.float32)
+        self._chk(self._f("read_film")(self._h, out.ctypes.data))
+        return out
+
+    def clear_film(self): self._chk(self._f("clear_film")(self._h))
+
+    def film_add_host(self, film: np.ndarray):
+        film = np.ascontiguousarray(film, np.float32)
+        self._chk(self._f("film_add_host")(self._h, film.ctypes.data))
+
+    def film_device(self):
+        p = C.c_void_p(); n = C.c_size_t()
+        self._chk(self._f("film_device")(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def synchronize(self): self._chk(self._f("synchronize")(self._h))
+
+    def stats(self) -> dict:
+        s = IR.Stats(); self._chk(self._f("get_stats")(self._h, C.byref(s))); return s.as_dict()
+
+    def reset_stats(self): self._chk(self._f("reset_stats")(self._h))
+
+    KERNEL_CLASSES = ["raygen", "trace_nearest", "trace_any", "classify", "shade", "resolve", "film", "other"]
+
+    def kernel_times(self) -> dict:
+        """device ms and launch count per kernel class since reset_stats (needs option profile_kernels=1)."""
+        ms = np.zeros(8, np.float64); n = np.zeros(8, np.uint64)
+        self._chk(self._f("kernel_times")(self._h, ms.ctypes.data, n.ctypes.data, 8))
+        return {k: (float(ms[i]), int(n[i])) for i, k in enumerate(self.KERNEL_CLASSES)}

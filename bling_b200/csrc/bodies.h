@@ -1,0 +1,336 @@
+// bodies.h -- wavefront path state and the per-item kernel bodies (functors).
+// Replaces: a2 runSample (Sampling.hs:112-132), a3 fireRay (Camera.hs:49-76),
+// a10 nextVertex (Integrator/Path.hs:41-87), a11 sampleOneLight/estimateDirect (Scene.hs:61-118),
+// a17 addSample/addTile (Image.hs:178-299).
+//
+// One path = one camera sample. State is SoA over `cap` slots; slot = sl * NPIX + pix where pix is the linear
+// pixel index in the sample extent and sl the sample's position in the batch [s0, s0+k). Queues hold slots.
+#pragma once
+#include "shading.h"
+
+namespace bl {
+
+enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MAT0 = 4, C_DROPPED = 12, N_COUNTERS = 16 };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + material kind
+enum { N_SHADE_KINDS = 1 + BLINGCU_MAT_KINDS };
+enum { S_SAMPLES = 0, S_CAM, S_EXT, S_MIS, S_SHADOW, S_DROPPED, N_STATS = 8 };
+
+struct PathState {
+   uint32_t cap;
+   F4 *rayO, *rayD;        // extension ray: (o, tmin) (d, tmax)
+   F4 *hit;                // (t, b1, b2, prim bits)
+   F4 *T, *L;              // throughput / radiance, quarter q of slot i at [q*cap + i]
+   F4 *shO, *shD, *PS;     // NEE shadow ray + pending contribution (already x T x nLights)
+   uint8_t *occl;
+   F4 *miO, *miD, *mihit, *PM;   // BSDF-MIS ray, its hit, pending T x f x nLights
+   F2 *miInfo;             // (bsdf pdf, light index bits)
+   uint32_t *meta;         // depth | spec << 8
+   uint64_t *kp;           // pixel key of the sampler
+   uint32_t *sidx;         // sample index within the pixel
+   F2 *spos;               // image position of the sample
+   F4 *xyz;                // finalised sample: X, Y, Z, valid
+   uint32_t *qA, *qB;      // active queues (ping-pong)
+   uint32_t *qShadow, *qMis;
+   uint32_t *qMat;         // N_SHADE_KINDS * cap
+   uint32_t *counters;     // N_COUNTERS
+   unsigned long long *stats;   // N_STATS
+};
+
+HD Spec loadSpec4(const F4 *base, uint32_t cap, uint32_t i) {
+   Spec s;
+   BL_UNROLL for (int q = 0; q < 4; ++q) { F4 v = base[(size_t)q * cap + i]; s.v[4 * q] = v.x; s.v[4 * q + 1] = v.y; s.v[4 * q + 2] = v.z; s.v[4 * q + 3] = v.w; }
+   return s;
+}
+HD void storeSpec4(F4 *base, uint32_t cap, uint32_t i, const Spec &s) {
+   BL_UNROLL for (int q = 0; q < 4; ++q) { F4 v; v.x = s.v[4 * q]; v.y = s.v[4 * q + 1]; v.z = s.v[4 * q + 2]; v.w = s.v[4 * q + 3]; base[(size_t)q * cap + i] = v; }
+}
+HD void storeRay(F4 *o, F4 *d, uint32_t i, const Ray &r) { F4 a, b; a.x = r.o.x; a.y = r.o.y; a.z = r.o.z; a.w = r.tmin; b.x = r.d.x; b.y = r.d.y; b.z = r.d.z; b.w = r.tmax; o[i] = a; d[i] = b; }
+HD Ray loadRay(const F4 *o, const F4 *d, uint32_t i) { F4 a = o[i], b = d[i]; Ray r; r.o = mk3(a.x, a.y, a.z); r.tmin = a.w; r.d = mk3(b.x, b.y, b.z); r.tmax = b.w; return r; }
+
+// queue append: warp-aggregated atomic on the device, plain increment in the single-threaded emulator
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void qPush(uint32_t *q, uint32_t *counter, uint32_t v) {
+   unsigned m = __activemask();
+   unsigned lane = threadIdx.x & 31u;
+   int leader = __ffs(m) - 1;
+   uint32_t base = 0;
+   if ((int)lane == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+   base = __shfl_sync(m, base, leader);
+   q[base + __popc(m & ((1u << lane) - 1u))] = v;
+}
+__device__ __forceinline__ void statAdd(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
+__device__ __forceinline__ void cntAdd(uint32_t *p, uint32_t v) { atomicAdd(p, v); }
+#else
+inline void qPush(uint32_t *q, uint32_t *counter, uint32_t v) { q[(*counter)++] = v; }
+inline void statAdd(unsigned long long *p, unsigned long long v) { *p += v; }
+inline void cntAdd(uint32_t *p, uint32_t v) { *p += v; }
+#endif
+
+HD Sampler mkSampler(const DScene &sc, uint64_t kp, uint32_t s) {
+   Sampler c; c.kp = kp; c.s = s; c.nu = sc.nu; c.nv = sc.nv; c.n1d = 4 * sc.sample_depth; c.n2d = 3 * sc.sample_depth;   // Path.hs:18-36
+   c.stratified = sc.sampler_kind == BLINGCU_SAMPLER_STRATIFIED;
+   return c;
+}
+
+// ------------------------------------------------------------------------------------------ K1 raygen
+struct RaygenBody {
+   const DScene *sc; PathState ps;
+   uint64_t seed; uint32_t pass, s0, npix;
+   const int32_t *px, *py; const uint32_t *smp;   // explicit sample list (render_samples) or null
+   HD void operator()(uint32_t i) const {
+      const DScene &S = *sc;
+      int ix, iy; uint32_t s, pix;
+      if (px) { ix = px[i]; iy = py[i]; s = smp[i]; pix = (uint32_t)(iy - S.ey0) * (uint32_t)S.EW + (uint32_t)(ix - S.ex0); }
+      else { pix = i % npix; s = s0 + i / npix; ix = S.ex0 + (int)(pix % (uint32_t)S.EW); iy = S.ey0 + (int)(pix / (uint32_t)S.EW); }
+      uint64_t kp = pixelKey(seed, pass, pix);
+      Sampler c = mkSampler(S, kp, s);
+      float ox, oy, lu, lv; cameraSample(c, ox, oy, lu, lv);
+      float sx = (float)ix + ox, sy = (float)iy + oy;
+      Ray r = fireRay(S.cam, sx, sy, lu, lv);
+      storeRay(ps.rayO, ps.rayD, i, r);
+      storeSpec4(ps.T, ps.cap, i, sConst(1)); storeSpec4(ps.L, ps.cap, i, sConst(0));   // Path.hs:38-39: t = white, l = black
+      ps.meta[i] = 0u | (1u << 8);   // depth 0, spec = True
+      ps.kp[i] = kp; ps.sidx[i] = s;
+      F2 p; p.x = sx; p.y = sy; ps.spos[i] = p;
+      ps.qA[i] = i;
+   }
+};
+
+// ------------------------------------------------------------------------------------------ trace (v1 bodies; the CUDA backend has its own kernels)
+struct TraceNearestBody {
+   const DScene *sc; const F4 *o, *d; F4 *hit;
+   HD void operator()(uint32_t i) const {
+      HitRec h = traceNearest<false>(sc->bvh, loadRay(o, d, i), 0, 0);
+      F4 v; v.x = h.t; v.y = h.b1; v.z = h.b2; v.w = i2f(h.prim); hit[i] = v;
+   }
+};
+struct TraceAnyBody {
+   const DScene *sc; const F4 *o, *d; uint8_t *occl;
+   HD void operator()(uint32_t i) const { occl[i] = traceAny(sc->bvh, loadRay(o, d, i)) ? 1 : 0; }
+};
+
+// ------------------------------------------------------------------------------------------ K4 classify: material-sorted queues
+struct ClassifyBody {
+   const DScene *sc; PathState ps;
+   HD void operator()(uint32_t i) const {
+      const DScene &S = *sc;
+      int prim = f2i(ps.hit[i].w);
+      int kind;
+      if (prim < 0) kind = 0;
+      else {
+         if ((int)(ps.meta[i] & 0xffu) == S.max_depth) return;   // Path.hs:51: depth == md -> return l
+         uint32_t ref = S.prim_ref[prim];
+         int mat = (ref >> 31) ? S.shapes[ref & 0x7fffffffu].material : f2i(ld4(S.tri_p + 3 * (size_t)ref).w);
+         kind = 1 + S.materials[mat].kind;
+      }
+      qPush(ps.qMat + (size_t)kind * ps.cap, ps.counters + C_MAT0 + kind, i);
+   }
+};
+
+// ------------------------------------------------------------------------------------------ K5 shade (miss)
+struct ShadeMissBody {   // Path.hs:43-47
+   const DScene *sc; PathState ps;
+   HD void operator()(uint32_t i) const {
+      const DScene &S = *sc;
+      if (!((ps.meta[i] >> 8) & 1u)) return;   // non-specular bounce: nothing
+      F4 d = ps.rayD[i];
+      Spec sum = sConst(0);
+      for (int l = 0; l < S.n_lights; ++l) sum = sum + lightLe(S, S.lights[l], mk3(d.x, d.y, d.z));
+      Spec L = loadSpec4(ps.L, ps.cap, i), T = loadSpec4(ps.T, ps.cap, i);
+      storeSpec4(ps.L, ps.cap, i, L + T * sum);
+   }
+};
+
+// ------------------------------------------------------------------------------------------ K5 shade (hit)
+struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118
+   const DScene *sc; PathState ps; uint32_t *qNext;
+   HD void operator()(uint32_t i) const {
+      const DScene &S = *sc;
+      Ray ray = loadRay(ps.rayO, ps.rayD, i);
+      F4 hv = ps.hit[i];
+      uint32_t meta = ps.meta[i];
+      int depth = (int)(meta & 0xffu); bool spec = ((meta >> 8) & 1u) != 0;
+      Sampler smp = mkSampler(S, ps.kp[i], ps.sidx[i]);
+      SurfaceHit sh; DG dgs;
+      surfaceAt(S, ray, hv.x, hv.y, hv.z, f2i(hv.w), sh, dgs);
+      Bsdf bsdf; makeBsdf(S, sh, dgs, bsdf);
+      Spec T = loadSpec4(ps.T, ps.cap, i);
+      V3 rd = ray.d, wo = -rd;
+      // emitted light, only after specular bounces / from the camera; Q1: tested against the RAY direction
+      if (spec && sh.light >= 0) {
+         const blingcu_light &el = S.lights[sh.light];
+         if (el.kind == BLINGCU_LIGHT_AREA && areaEmits(sh.dgg.n, rd)) {
+            Spec L = loadSpec4(ps.L, ps.cap, i);
+            storeSpec4(ps.L, ps.cap, i, L + T * loadSpec(el.s.v));
+         }
+      }
+      V3 n = bsdf.cs.n, p = bsdf.p; float eps = sh.eps;
+      float lNumU = rnd1D(smp, 1 + 4 * depth);
+      float lD1, lD2; rnd2D(smp, 1 + 3 * depth, lD1, lD2);
+      float bCompU = rnd1D(smp, 2 + 4 * depth);
+      float bD1, bD2; rnd2D(smp, 2 + 3 * depth, bD1, bD2);
+      int lc = S.n_lights;
+      if (lc > 0) {   // sampleOneLight (Scene.hs:110-118)
+         int ln = (lc == 1) ? 0 : imin((int)floorf(lNumU * (float)lc), lc - 1);
+         const blingcu_light &lt = S.lights[ln];
+         float lcf = (lc == 1) ? 1.0f : (float)lc;
+         {   // sampleLightMis (Scene.hs:61-69)
+            LightSample ls; lightSample(S, lt, p, eps, n, lD1, lD2, ls);
+            if (ls.pdf != 0 && !isBlack(ls.de)) {
+               Spec f = evalBsdf(bsdf, wo, ls.wi);
+               if (!isBlack(f)) {
+                  float w = ls.delta ? 1 / ls.pdf : powerHeuristic(ls.pdf, bsdfPdf(bsdf, wo, ls.wi)) / ls.pdf;
+                  Spec c = sScale(f * ls.de, w);
+                  if (lc > 1) c = sScale(c, lcf);
+                  storeSpec4(ps.PS, ps.cap, i, T * c);
+                  storeRay(ps.shO, ps.shD, i, ls.testRay);
+                  qPush(ps.qShadow, ps.counters + C_SHADOW, i);
+               }
+            }
+         }
+         {   // sampleBsdfMis (Scene.hs:71-82): the ray is traced now, the light lookup happens in ResolveMisBody
+            BsdfSample bs; sampleBsdf(bsdf, wo, bCompU, bD1, bD2, bs);
+            if (bs.pdf != 0 && !isBlack(bs.f)) {
+               Spec c = bs.f;
+               if (lc > 1) c = sScale(c, lcf);
+               storeSpec4(ps.PM, ps.cap, i, T * c);
+               Ray mr; mr.o = p; mr.d = bs.wi; mr.tmin = eps; mr.tmax = BL_INF;
+               storeRay(ps.miO, ps.miD, i, mr);
+               F2 info; info.x = bs.pdf; info.y = i2f(ln); ps.miInfo[i] = info;
+               qPush(ps.qMis, ps.counters + C_MIS, i);
+            }
+         }
+      }
+      // Russian roulette (Path.hs:68-72)
+      float pc = (depth <= 7) ? 1.0f : hminf(0.75f, sY(S, T));
+      float x = rnd1D(smp, 3 + 4 * depth);
+      if (x > pc) return;
+      float uc = rnd1D(smp, 0 + 4 * depth);
+      float ud1, ud2; rnd2D(smp, 0 + 3 * depth, ud1, ud2);
+      BsdfSample s; sampleBsdf(bsdf, wo, uc, ud1, ud2, s);
+      if (s.pdf == 0 || isBlack(s.f)) return;
+      Ray nr; nr.o = p; nr.d = s.wi; nr.tmin = eps; nr.tmax = BL_INF;
+      storeRay(ps.rayO, ps.rayD, i, nr);
+      storeSpec4(ps.T, ps.cap, i, sScale(s.f * T, 1 / pc));   // Path.hs:82: no pdf / cosine factor, the weight carries them
+      ps.meta[i] = (uint32_t)(depth + 1) | (((s.type & BX_SPECULAR) ? 1u : 0u) << 8);
+      qPush(qNext, ps.counters + C_NEXT, i);
+   }
+};
+
+// ------------------------------------------------------------------------------------------ K6 resolve
+struct ResolveShadowBody {   // Scene.hs:64: `occluded scene ray` -> black
+   PathState ps;
+   HD void operator()(uint32_t i) const {
+      if (ps.occl[i]) return;
+      storeSpec4(ps.L, ps.cap, i, loadSpec4(ps.L, ps.cap, i) + loadSpec4(ps.PS, ps.cap, i));
+   }
+};
+struct ResolveMisBody {   // Scene.hs:75-82
+   const DScene *sc; PathState ps;
+   HD void operator()(uint32_t i) const {
+      const DScene &S = *sc;
+      F4 hv = ps.mihit[i];
+      F2 info = ps.miInfo[i];
+      int ln = f2i(info.y);
+      const blingcu_light &l = S.lights[ln];
+      Ray ray = loadRay(ps.miO, ps.miD, i);
+      int prim = f2i(hv.w);
+      Spec li;
+      if (prim >= 0) {
+         uint32_t ref = S.prim_ref[prim];
+         if (!(ref >> 31)) return;                                  // triangles carry no light (TriangleMesh.hs:105)
+         const blingcu_shape &s = S.shapes[ref & 0x7fffffffu];
+         if (s.light != ln || l.kind != BLINGCU_LIGHT_AREA) return;   // Eq Light: same area-light id (Light.hs:48-50)
+         SurfaceHit sh; DG dgs;
+         surfaceAt(S, ray, hv.x, hv.y, hv.z, prim, sh, dgs);
+         if (!areaEmits(sh.dgg.n, -ray.d)) return;                   // intLe int (-wi)
+         li = loadSpec(l.s.v);
+      } else {
+         li = lightLe(S, l, ray.d);
+         if (isBlack(li)) return;
+      }
+      float w = powerHeuristic(info.x, lightPdf(S, l, ray.o, ray.d));   // Q3: also for specular samples
+      Spec c = sScale(loadSpec4(ps.PM, ps.cap, i) * li, w);
+      storeSpec4(ps.L, ps.cap, i, loadSpec4(ps.L, ps.cap, i) + c);
+   }
+};
+
+// one thread: fold the queue counters into the statistics and rotate the queues (end of a bounce)
+struct AdvanceBody {
+   PathState ps;
+   HD void operator()(uint32_t) const {
+      uint32_t *c = ps.counters;
+      statAdd(ps.stats + S_EXT, c[C_NEXT]); statAdd(ps.stats + S_SHADOW, c[C_SHADOW]); statAdd(ps.stats + S_MIS, c[C_MIS]);
+      c[C_ACTIVE] = c[C_NEXT]; c[C_NEXT] = 0; c[C_SHADOW] = 0; c[C_MIS] = 0;
+      for (int k = 0; k < N_SHADE_KINDS; ++k) c[C_MAT0 + k] = 0;
+   }
+};
+struct BeginBatchBody {
+   PathState ps; uint32_t n;
+   HD void operator()(uint32_t) const {
+      uint32_t *c = ps.counters;
+      for (int k = 0; k < N_COUNTERS; ++k) if (k != C_DROPPED) c[k] = 0;
+      c[C_ACTIVE] = n;
+      statAdd(ps.stats + S_CAM, n); statAdd(ps.stats + S_SAMPLES, n);
+   }
+};
+
+// ------------------------------------------------------------------------------------------ finalize: spectrum -> XYZ (Image.hs:253-258)
+struct FinalizeBody {
+   const DScene *sc; PathState ps;
+   HD void operator()(uint32_t i) const {
+      Spec L = loadSpec4(ps.L, ps.cap, i);
+      F4 o; o.x = o.y = o.z = o.w = 0;
+      if (sBad(L)) { statAdd(ps.stats + S_DROPPED, 1); }   // NaN / infinite samples are skipped
+      else { spectrumToXYZ(*sc, L, o.x, o.y, o.z); o.w = 1.0f; }
+      ps.xyz[i] = o;
+   }
+};
+
+// ------------------------------------------------------------------------------------------ K7 film: atomic-free gather, one thread per film pixel
+// Reproduces addSample on per-tile images + addTile (Image.hs:108-120,178-199,250-299, Q10): a sample only
+// reaches pixels of ITS 16x16 sample window's tile image, which has no left/top apron and extends
+// floor(0.5+f) pixels right/bottom.
+struct FilmBody {
+   const DScene *sc; PathState ps; F4 *film; uint32_t k, npix;
+   HD void operator()(uint32_t fp) const {
+      const DScene &S = *sc;
+      int x = (int)(fp % (uint32_t)S.W), y = (int)(fp / (uint32_t)S.W);
+      float fw = S.fw, fh = S.fh;
+      float ifw = 1 / fw, ifh = 1 / fw;   // Q10
+      int rx = (int)ceilf(fw + 0.5f) + 1, ry = (int)ceilf(fh + 0.5f) + 1;
+      int extx = (int)floorf(0.5f + fw), exty = (int)floorf(0.5f + fh);
+      float aw = 0, ax = 0, ay = 0, az = 0;
+      for (int iy = imax(S.ey0, y - ry); iy <= imin(S.ey1, y + ry); ++iy) {
+         int ty0 = S.ey0 + ((iy - S.ey0) >> 4) * 16, ty1 = imin(ty0 + 15, S.ey1);
+         int toy = imax(0, ty0), tymax = ty1 + exty - 1;
+         if (y < toy || y > tymax) continue;
+         for (int ix = imax(S.ex0, x - rx); ix <= imin(S.ex1, x + rx); ++ix) {
+            int tx0 = S.ex0 + ((ix - S.ex0) >> 4) * 16, tx1 = imin(tx0 + 15, S.ex1);
+            int tox = imax(0, tx0), txmax = tx1 + extx - 1;
+            if (x < tox || x > txmax) continue;
+            uint32_t pix = (uint32_t)(iy - S.ey0) * (uint32_t)S.EW + (uint32_t)(ix - S.ex0);
+            for (uint32_t sl = 0; sl < k; ++sl) {
+               uint32_t slot = sl * npix + pix;
+               F4 c = ps.xyz[slot];
+               if (c.w == 0) continue;
+               F2 sp = ps.spos[slot];
+               float dx = sp.x - 0.5f, dy = sp.y - 0.5f;
+               int x0 = imax(tox, (int)ceilf(dx - fw)), x1 = imin(txmax, (int)floorf(dx + fw));
+               int y0 = imax(toy, (int)ceilf(dy - fh)), y1 = imin(tymax, (int)floorf(dy + fh));
+               if (x < x0 || x > x1 || y < y0 || y > y1) continue;
+               int tix = imin((int)floorf(fabsf(((float)x - dx) * ifw * 16.0f)), 15);
+               int tiy = imin((int)floorf(fabsf(((float)y - dy) * ifh * 16.0f)), 15);
+               float w = S.ftbl[tiy * 16 + tix];
+               aw = aw + w; ax = ax + c.x * w; ay = ay + c.y * w; az = az + c.z * w;
+            }
+         }
+      }
+      F4 f = film[fp];
+      f.x = f.x + aw; f.y = f.y + ax; f.z = f.z + ay; f.w = f.w + az;
+      film[fp] = f;
+   }
+};
+
+struct AddFilmBody { F4 *dst; const F4 *src; HD void operator()(uint32_t i) const { F4 a = dst[i], b = src[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; dst[i] = a; } };
+
+}  // namespace bl

@@ -1,0 +1,162 @@
+// bvh_build.cpp -- host-side binned-SAH BVH2 builder (setup, not per-ray). Plays the role of
+// mkKdTree/buildTree (KdTree.hs:107-203) for the GPU path; the tree shape is free to differ because the
+// traversal result (globally nearest hit) does not depend on it.
+//
+// Item boxes are inflated by eps = 4e-6 * scene extent (+ 1e-30) on every side before they are merged, so the
+// slab test in bvh.h needs no epsilon: its rounding error (~2e-7 * t) is below eps * |1/d| for any ray that
+// starts within ~20 scene diameters.
+#include "bvh.h"
+#include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <future>
+#include <vector>
+
+namespace bl {
+
+namespace {
+struct Box {
+   float lo[3], hi[3];
+   void reset() { for (int k = 0; k < 3; ++k) { lo[k] = BL_INF; hi[k] = -BL_INF; } }
+   void grow(const float *l, const float *h) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], l[k]); hi[k] = std::max(hi[k], h[k]); } }
+   void grow(const Box &b) { grow(b.lo, b.hi); }
+   void growP(const float *p) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+   float area() const { float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2]; return (dx < 0) ? 0.0f : 2 * (dx * dy + dx * dz + dy * dz); }
+};
+struct Item { float lo[3], hi[3], c[3]; uint32_t id; };
+
+constexpr int NBINS = 16;
+
+struct Builder {
+   std::vector<Item> items;
+   F4 *nodes;
+   std::atomic<int> nextNode{0};
+   int maxLeaf;
+   int parLevels;
+
+   int allocNode() { return nextNode.fetch_add(1); }
+
+   // builds [b,e), returns the child reference and its box
+   int build(size_t b, size_t e, int depth, Box &box) {
+      size_t n = e - b;
+      box.reset();
+      Box cb; cb.reset();
+      for (size_t i = b; i < e; ++i) { box.grow(items[i].lo, items[i].hi); cb.growP(items[i].c); }
+      if ((int)n <= maxLeaf) return ~(int)((b << 4) | n);
+      size_t mid = 0;
+      bool done = false;
+      if (depth < 32) {
+         float bestCost = BL_INF; int bestAxis = -1, bestBin = -1;
+         for (int axis = 0; axis < 3; ++axis) {
+            float cmin = cb.lo[axis], cext = cb.hi[axis] - cb.lo[axis];
+            if (!(cext > 0)) continue;
+            Box bb[NBINS]; int cnt[NBINS];
+            for (int k = 0; k < NBINS; ++k) { bb[k].reset(); cnt[k] = 0; }
+            float scale = NBINS / cext;
+            for (size_t i = b; i < e; ++i) {
+               int k = std::min(NBINS - 1, std::max(0, (int)((items[i].c[axis] - cmin) * scale)));
+               bb[k].grow(items[i].lo, items[i].hi); cnt[k]++;
+            }
+            float rightArea[NBINS]; int rightCnt[NBINS];
+            Box acc; acc.reset(); int c = 0;
+            for (int k = NBINS - 1; k > 0; --k) { acc.grow(bb[k]); c += cnt[k]; rightArea[k] = acc.area(); rightCnt[k] = c; }
+            acc.reset(); c = 0;
+            for (int k = 0; k < NBINS - 1; ++k) {
+               acc.grow(bb[k]); c += cnt[k];
+               if (c == 0 || rightCnt[k + 1] == 0) continue;
+               float cost = acc.area() * c + rightArea[k + 1] * rightCnt[k + 1];
+               if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = k; }
+            }
+         }
+         float leafCost = box.area() * (float)n;
+         if (bestAxis >= 0 && (bestCost < leafCost || (int)n > 15)) {
+            float cmin = cb.lo[bestAxis], scale = NBINS / (cb.hi[bestAxis] - cb.lo[bestAxis]);
+            auto it = std::partition(items.begin() + b, items.begin() + e, [&](const Item &x) {
+               int k = std::min(NBINS - 1, std::max(0, (int)((x.c[bestAxis] - cmin) * scale)));
+               return k <= bestBin;
+            });
+            mid = (size_t)(it - items.begin());
+            done = mid > b && mid < e;
+         } else if (bestAxis >= 0 && (int)n <= 15) {
+            return ~(int)((b << 4) | n);   // SAH says a leaf is cheaper
+         }
+      }
+      if (!done) {   // median split along the widest centroid axis (also the depth guard)
+         int axis = 0; float ext = -1;
+         for (int k = 0; k < 3; ++k) if (cb.hi[k] - cb.lo[k] > ext) { ext = cb.hi[k] - cb.lo[k]; axis = k; }
+         if (!(ext > 0) && (int)n <= 15) return ~(int)((b << 4) | n);
+         mid = b + n / 2;
+         std::nth_element(items.begin() + b, items.begin() + mid, items.begin() + e,
+                          [axis](const Item &x, const Item &y) { return x.c[axis] < y.c[axis]; });
+      }
+      int idx = allocNode();
+      Box lb, rb; int lc, rc;
+      if (depth < parLevels && n > 65536) {
+         auto fut = std::async(std::launch::async, [&]() { lc = build(b, mid, depth + 1, lb); });
+         rc = build(mid, e, depth + 1, rb);
+         fut.get();
+      } else {
+         lc = build(b, mid, depth + 1, lb);
+         rc = build(mid, e, depth + 1, rb);
+      }
+      F4 *np = nodes + 4 * (size_t)idx;
+      np[0] = F4{lb.lo[0], lb.hi[0], lb.lo[1], lb.hi[1]};
+      np[1] = F4{rb.lo[0], rb.hi[0], rb.lo[1], rb.hi[1]};
+      np[2] = F4{lb.lo[2], lb.hi[2], rb.lo[2], rb.hi[2]};
+      np[3] = F4{i2f(lc), i2f(rc), 0, 0};
+      return idx;
+   }
+};
+}  // namespace
+
+int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
+   std::memset(&out, 0, sizeof(out));
+   out.root = -1;
+   if (in.n == 0) return 0;
+   if (in.n >= (1u << 27)) return 1;
+   Box scene; scene.reset();
+   for (size_t i = 0; i < in.n; ++i) scene.grow(in.lo + 3 * i, in.hi + 3 * i);
+   float ext = 0;
+   for (int k = 0; k < 3; ++k) {
+      ext = std::max(ext, scene.hi[k] - scene.lo[k]);
+      ext = std::max(ext, std::max(std::fabs(scene.lo[k]), std::fabs(scene.hi[k])));
+      out.scene_lo[k] = scene.lo[k]; out.scene_hi[k] = scene.hi[k];
+   }
+   float eps = 4e-6f * ext + 1e-30f;
+   Builder B;
+   B.items.resize(in.n);
+   for (size_t i = 0; i < in.n; ++i) {
+      Item &it = B.items[i];
+      for (int k = 0; k < 3; ++k) {
+         it.lo[k] = in.lo[3 * i + k] - eps; it.hi[k] = in.hi[3 * i + k] + eps;
+         it.c[k] = 0.5f * (in.lo[3 * i + k] + in.hi[3 * i + k]);
+      }
+      it.id = (uint32_t)i;
+   }
+   B.maxLeaf = std::min(15, std::max(1, in.max_leaf));
+   int th = std::max(1, in.threads);
+   B.parLevels = 0; while ((1 << B.parLevels) < th) B.parLevels++;
+   B.parLevels += 1;
+   size_t maxNodes = std::max<size_t>(1, in.n);   // a binary tree over n leaves has n-1 inner nodes
+   B.nodes = (F4 *)std::malloc(sizeof(F4) * 4 * (maxNodes + 1));
+   Box rootBox;
+   int root = B.build(0, in.n, 0, rootBox);
+   if (root < 0) {   // single leaf: wrap it so traversal always starts at a node
+      int idx = B.allocNode();
+      F4 *np = B.nodes + 4 * (size_t)idx;
+      np[0] = F4{rootBox.lo[0], rootBox.hi[0], rootBox.lo[1], rootBox.hi[1]};
+      np[1] = F4{BL_INF, -BL_INF, BL_INF, -BL_INF};
+      np[2] = F4{rootBox.lo[2], rootBox.hi[2], BL_INF, -BL_INF};
+      np[3] = F4{i2f(root), i2f(~0), 0, 0};
+      root = idx;
+   }
+   out.nodes = B.nodes;
+   out.n_nodes = B.nextNode.load();
+   out.root = root;
+   out.order = (uint32_t *)std::malloc(sizeof(uint32_t) * in.n);
+   for (size_t i = 0; i < in.n; ++i) out.order[i] = B.items[i].id;
+   return 0;
+}
+
+}  // namespace bl

@@ -1,0 +1,160 @@
+// cuda_backend.cu -- the product: sm_100a kernels + the C ABI (libblingcu.so).
+//
+// Kernels:
+//   K1 raygen, K4 classify, K5 shade (miss + one launch per material kind present), K6 resolve, K7 film,
+//   finalize, advance                    -> kRun / kRunQueue over the functors of bodies.h
+//   K2 trace_nearest, K3 trace_any       -> trace_kernels.cuh (persistent-thread BVH traversal)
+// All queue-driven kernels read their item count from device memory, so the whole bounce loop is enqueued
+// without a host round trip. Grids are sized in multiples of the SM count.
+#include "api_impl.h"
+#include "trace_kernels.cuh"
+#include <cuda_runtime.h>
+#include <vector>
+
+namespace bl {
+
+struct CudaError { cudaError_t e; const char *what; };
+#define CU(x) do { cudaError_t _e = (x); if (_e != cudaSuccess) throw CudaError{_e, #x}; } while (0)
+
+
+template <class B> __global__ void __launch_bounds__(256) kRun(B b, uint32_t n) {
+   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b(i);
+}
+template <class B> __global__ void __launch_bounds__(256) kRunQueue(B b, const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt) {
+   uint32_t n = *cnt;
+   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b(q[i]);
+}
+// the shade kernel carries 16-band spectra in registers: smaller blocks, one item per thread per trip
+template <class B> __global__ void __launch_bounds__(128) kRunQueueHeavy(B b, const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt) {
+   uint32_t n = *cnt;
+   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b(q[i]);
+}
+
+struct CudaBackend {
+   int device = -1, sms = 148;
+   cudaStream_t stream = nullptr;
+   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+   TraceConfig tcfg;
+   // optional per-class kernel timing (option "profile_kernels"): one event pair per launch on the launching stream
+   bool profile = false; int curClass = BLINGCU_KC_OTHER;
+   struct Rec { cudaEvent_t a, b; int cls; };
+   std::vector<Rec> recs; std::vector<cudaEvent_t> pool;
+   double clsMs[BLINGCU_KC_COUNT] = {}; uint64_t clsLaunches[BLINGCU_KC_COUNT] = {};
+
+   void tag(int c) { curClass = c; }
+   cudaEvent_t getEvent() { if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; } cudaEvent_t e; CU(cudaEventCreate(&e)); return e; }
+   struct Scope {
+      CudaBackend *b; Rec r; bool on;
+      Scope(CudaBackend *be) : b(be), on(be->profile) { if (on) { r.a = b->getEvent(); r.b = b->getEvent(); r.cls = b->curClass; cudaEventRecord(r.a, b->stream); } else b->clsLaunches[b->curClass]++; }
+      ~Scope() { if (on) { cudaEventRecord(r.b, b->stream); b->recs.push_back(r); if (b->recs.size() > 4096) b->collect(); } }
+   };
+   void collect() {
+      if (recs.empty()) return;
+      cudaStreamSynchronize(stream);
+      for (Rec &r : recs) { float ms = 0; if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { clsMs[r.cls] += ms; clsLaunches[r.cls]++; } pool.push_back(r.a); pool.push_back(r.b); }
+      recs.clear();
+   }
+   void kernelTimes(double *ms, uint64_t *l, int n) { collect(); for (int i = 0; i < n; ++i) { ms[i] = i < BLINGCU_KC_COUNT ? clsMs[i] : 0; l[i] = i < BLINGCU_KC_COUNT ? clsLaunches[i] : 0; } }
+   void resetProfile() { collect(); for (int i = 0; i < BLINGCU_KC_COUNT; ++i) { clsMs[i] = 0; clsLaunches[i] = 0; } if (tcfg.travCounters) cudaMemsetAsync(tcfg.travCounters, 0, 3 * sizeof(unsigned long long), stream); }
+   void traversalTotals(uint64_t &nodes, uint64_t &prims, uint64_t &rays) {
+      nodes = prims = rays = 0;
+      if (!tcfg.travCounters) return;
+      unsigned long long h[3]; download(h, tcfg.travCounters, sizeof(h)); nodes = h[0]; prims = h[1]; rays = h[2];
+   }
+
+   int init(int dev, std::string &err) {
+      int n = 0;
+      cudaError_t e = cudaGetDeviceCount(&n);
+      if (e != cudaSuccess || n == 0) { err = std::string("no CUDA device visible (") + cudaGetErrorString(e) + "); this library has no CPU fallback"; return BLINGCU_ENOGPU; }
+      if (dev < 0 || dev >= n) { err = "device index out of range"; return BLINGCU_EINVAL; }
+      if ((e = cudaSetDevice(dev)) != cudaSuccess) { err = cudaGetErrorString(e); return BLINGCU_ECUDA; }
+      cudaDeviceProp p;
+      if ((e = cudaGetDeviceProperties(&p, dev)) != cudaSuccess) { err = cudaGetErrorString(e); return BLINGCU_ECUDA; }
+      if (p.major < 10) { err = "built for sm_100a (B200); found sm_" + std::to_string(p.major * 10 + p.minor); return BLINGCU_ENOGPU; }
+      device = dev; sms = p.multiProcessorCount;
+      if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ev0) != cudaSuccess || cudaEventCreate(&ev1) != cudaSuccess) { err = "stream/event creation failed"; return BLINGCU_ECUDA; }
+      tcfg.sms = sms;
+      return 0;
+   }
+   void shutdown() {
+      if (device >= 0) cudaSetDevice(device);
+      if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); stream = nullptr; }
+      collect(); for (cudaEvent_t e : pool) cudaEventDestroy(e); pool.clear();
+      if (ev0) cudaEventDestroy(ev0);
+      if (ev1) cudaEventDestroy(ev1);
+      ev0 = ev1 = nullptr;
+   }
+   template <class F> int guard(std::string &err, F f) {
+      try {
+         CU(cudaSetDevice(device));
+         int rc = f();
+         cudaError_t e = cudaGetLastError();
+         if (e != cudaSuccess) { err = std::string("CUDA: ") + cudaGetErrorString(e); return BLINGCU_ECUDA; }
+         return rc;
+      } catch (const CudaError &c) { err = std::string("CUDA: ") + cudaGetErrorString(c.e) + " in " + c.what; return BLINGCU_ECUDA; }
+      catch (const std::bad_alloc &) { err = "host out of memory"; return BLINGCU_EINVAL; }
+   }
+   bool setOption(const std::string &k, double v) {
+      if (k == "trace_variant") { tcfg.variant = (int)v; return true; }
+      if (k == "profile_kernels") { collect(); profile = v != 0; return true; }
+      if (k == "traversal_stats") {
+         tcfg.countStats = v != 0;
+         if (tcfg.countStats && !tcfg.travCounters) { tcfg.travCounters = (unsigned long long *)alloc(3 * sizeof(unsigned long long)); zero(tcfg.travCounters, 3 * sizeof(unsigned long long)); }
+         return true;
+      }
+      if (k == "trace_blocks_per_sm") { tcfg.blocksPerSm = (int)v; return true; }
+      return false;
+   }
+   void *alloc(size_t n) { void *p = nullptr; CU(cudaMalloc(&p, n ? n : 1)); return p; }
+   void free(void *p) { if (p) cudaFree(p); }
+   void upload(void *d, const void *s, size_t n) { CU(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream)); CU(cudaStreamSynchronize(stream)); }
+   void download(void *d, const void *s, size_t n) { CU(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream)); CU(cudaStreamSynchronize(stream)); }
+   void zero(void *d, size_t n) { CU(cudaMemsetAsync(d, 0, n, stream)); }
+   void sync() { CU(cudaStreamSynchronize(stream)); }
+   int timerStart() { CU(cudaEventRecord(ev0, stream)); return 0; }
+   double timerStop(int) { CU(cudaEventRecord(ev1, stream)); CU(cudaEventSynchronize(ev1)); float ms = 0; CU(cudaEventElapsedTime(&ms, ev0, ev1)); return ms; }
+
+   uint32_t gridFor(uint32_t n, uint32_t block, uint32_t perSm) const {
+      uint32_t need = (n + block - 1) / block;
+      uint32_t full = (uint32_t)sms * perSm;
+      if (need >= full) return full;
+      return need ? need : 1;
+   }
+   template <class B> void run(const B &b, uint32_t n) {
+      if (n == 0) return;
+      Scope sc_(this);
+      kRun<B><<<gridFor(n, 256, 8), 256, 0, stream>>>(b, n);
+   }
+   template <class B> void runQueue(const B &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
+      if (bound == 0) return;
+      Scope sc_(this);
+      kRunQueue<B><<<gridFor(bound, 256, 8), 256, 0, stream>>>(b, q, cnt);
+   }
+   void runQueue(const ShadeHitBody &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
+      if (bound == 0) return;
+      Scope sc_(this);
+      kRunQueueHeavy<ShadeHitBody><<<gridFor(bound, 128, 8), 128, 0, stream>>>(b, q, cnt);
+   }
+   void runQueue(const ResolveMisBody &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
+      if (bound == 0) return;
+      Scope sc_(this);
+      kRunQueueHeavy<ResolveMisBody><<<gridFor(bound, 128, 8), 128, 0, stream>>>(b, q, cnt);
+   }
+   void traceNearest(const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc, const F4 *o, const F4 *d, F4 *hit) {
+      if (!n) return;
+      Scope sc_(this);
+      launchTraceNearest(tcfg, stream, q, cnt, n, sc, o, d, hit);
+   }
+   void traceAny(const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc, const F4 *o, const F4 *d, uint8_t *occl) {
+      if (!n) return;
+      Scope sc_(this);
+      launchTraceAny(tcfg, stream, q, cnt, n, sc, o, d, occl);
+   }
+   void traceStats(uint32_t n, const DScene *sc, const F4 *o, const F4 *d, F4 *hit, uint32_t *nodes, uint32_t *prims) {
+      if (n) launchTraceStats(tcfg, stream, n, sc, o, d, hit, nodes, prims);
+   }
+};
+
+}  // namespace bl
+
+BL_DEFINE_API(blingcu, bl::CudaBackend)

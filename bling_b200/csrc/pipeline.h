@@ -1,0 +1,339 @@
+// pipeline.h -- scene upload and the wavefront schedule, templated on the execution backend.
+// Backend = CudaBackend (cuda_backend.cu: the product) or the single-threaded kernel-body emulator used by the
+// no-GPU CI tests (tests/emu/emu.cpp). The schedule replaces prender/tile (Rendering.hs:111-150):
+//
+//   per batch of k samples/pixel:  raygen -> { extend-trace -> classify -> shade[miss, matte, glass, ...] ->
+//                                  shadow-trace + MIS-trace -> resolve -> advance } x (maxDepth+1)
+//                                  -> finalize (spectrum->XYZ) -> film gather
+//
+// Backend contract: alloc/free/upload/download/zero, run(body, n), runQueue(body, queue, countPtr, cap),
+// traceNearest(queue,countPtr,cap,o,d,hit), traceAny(queue,countPtr,cap,o,d,occl), sync().
+#pragma once
+#include "bodies.h"
+#include <chrono>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace bl {
+
+template <class Backend>
+struct Pipeline {
+   Backend be;
+   std::string err;
+   bool uploaded = false;
+   // host copies / geometry
+   DScene hs;                 // host-side mirror of the device scene struct (pointers are DEVICE pointers)
+   DScene *dscene = nullptr;  // device copy
+   std::vector<void *> sceneAllocs;
+   PathState ps{}; std::vector<void *> stateAllocs;
+   F4 *film = nullptr;
+   uint32_t npix = 0;
+   uint32_t batchTarget = 1u << 23;
+   int maxLeaf = 4;
+   uint64_t nNodes = 0, nItems = 0;
+   uint64_t launches = 0;
+   double lastMs = 0;
+
+   int fail(int code, const std::string &m) { err = m; return code; }
+
+   template <class T> T *up(const T *src, size_t n) {
+      if (n == 0) n = 1;
+      T *d = (T *)be.alloc(sizeof(T) * n);
+      if (src) be.upload(d, src, sizeof(T) * n);
+      sceneAllocs.push_back(d);
+      return d;
+   }
+   void freeScene() { for (void *p : sceneAllocs) be.free(p); sceneAllocs.clear(); dscene = nullptr; if (film) { be.free(film); film = nullptr; } uploaded = false; }
+   void freeState() { for (void *p : stateAllocs) be.free(p); stateAllocs.clear(); ps = PathState{}; }
+
+   int upload(const blingcu_scene *ir) {
+      freeScene();
+      if (!ir) return fail(BLINGCU_EINVAL, "null scene");
+      if (ir->width <= 0 || ir->height <= 0) return fail(BLINGCU_EINVAL, "bad image size");
+      if (ir->nu <= 0 || ir->nv <= 0) return fail(BLINGCU_EINVAL, "bad sampler");
+      if (ir->max_depth < 0 || ir->max_depth > 254) return fail(BLINGCU_EINVAL, "max_depth out of range");
+      size_t nt = (size_t)ir->n_triangles, ns = ir->n_shapes, nprim = nt + ns;
+      // ---- validate indices
+      for (size_t i = 0; i < nt; ++i) if (ir->tri_material[i] < 0 || (uint32_t)ir->tri_material[i] >= ir->n_materials) return fail(BLINGCU_EINVAL, "triangle material out of range");
+      for (size_t i = 0; i < ns; ++i) {
+         const blingcu_shape &s = ir->shapes[i];
+         if (s.material < 0 || (uint32_t)s.material >= ir->n_materials) return fail(BLINGCU_EINVAL, "shape material out of range");
+         if (s.light >= (int)ir->n_lights) return fail(BLINGCU_EINVAL, "shape light out of range");
+         if (s.kind < 0 || s.kind > BLINGCU_SHAPE_SPHERE) return fail(BLINGCU_EINVAL, "unknown shape kind");
+      }
+      for (uint32_t i = 0; i < ir->n_materials; ++i) {
+         const blingcu_material &m = ir->materials[i];
+         if (m.kind < 0 || m.kind >= BLINGCU_MAT_KINDS) return fail(BLINGCU_EINVAL, "unknown material kind");
+         int need = (m.kind == BLINGCU_MAT_MATTE || m.kind == BLINGCU_MAT_MIRROR) ? 1 : (m.kind == BLINGCU_MAT_BLACKBODY ? 0 : 2);
+         for (int k = 0; k < need; ++k) if (m.tex[k] < 0 || (uint32_t)m.tex[k] >= ir->n_textures) return fail(BLINGCU_EINVAL, "material texture out of range");
+      }
+      for (uint32_t i = 0; i < ir->n_textures; ++i) {
+         const blingcu_texture &t = ir->textures[i];
+         if (t.kind == BLINGCU_TEX_GRAPHPAPER) { for (int k = 0; k < 2; ++k) if (t.child[k] < 0 || (uint32_t)t.child[k] >= ir->n_textures) return fail(BLINGCU_EINVAL, "texture child out of range"); }
+         else if (t.kind != BLINGCU_TEX_CONSTANT) return fail(BLINGCU_EINVAL, "unknown texture kind");
+      }
+      for (uint32_t i = 0; i < ir->n_lights; ++i) {
+         const blingcu_light &l = ir->lights[i];
+         if (l.kind == BLINGCU_LIGHT_AREA && (l.shape < 0 || (uint32_t)l.shape >= ir->n_shapes)) return fail(BLINGCU_EINVAL, "area light shape out of range");
+         if (l.kind == BLINGCU_LIGHT_INFINITE && (l.env < 0 || (uint32_t)l.env >= ir->n_envs)) return fail(BLINGCU_EINVAL, "infinite light env out of range");
+      }
+      // ---- prim table + leaf items
+      std::vector<uint32_t> primRef(nprim ? nprim : 1, 0xffffffffu);
+      std::vector<float> lo(3 * nprim), hi(3 * nprim);
+      std::vector<int32_t> itemPrim(nprim);
+      for (size_t i = 0; i < nt; ++i) {
+         size_t pid = ir->tri_prim_id ? (size_t)ir->tri_prim_id[i] : (size_t)ir->tri_prim_id_base + i;
+         if (pid >= nprim || primRef[pid] != 0xffffffffu) return fail(BLINGCU_EINVAL, "prim ids must be a permutation of 0..n-1");
+         primRef[pid] = (uint32_t)i;
+         const float *v = ir->tri_verts + 9 * i;
+         for (int k = 0; k < 3; ++k) {
+            lo[3 * i + k] = std::min(v[k], std::min(v[3 + k], v[6 + k]));
+            hi[3 * i + k] = std::max(v[k], std::max(v[3 + k], v[6 + k]));
+         }
+         itemPrim[i] = (int32_t)pid;
+      }
+      for (size_t j = 0; j < ns; ++j) {
+         const blingcu_shape &s = ir->shapes[j];
+         size_t pid = (size_t)s.prim_id;
+         if (pid >= nprim || primRef[pid] != 0xffffffffu) return fail(BLINGCU_EINVAL, "prim ids must be a permutation of 0..n-1");
+         primRef[pid] = 0x80000000u | (uint32_t)j;
+         // worldBounds = transBox o2w (objectBounds s) (Shape.hs:287-311)
+         const float *P = s.p; float olo[3], ohi[3];
+         switch (s.kind) {
+         case BLINGCU_SHAPE_BOX: for (int k = 0; k < 3; ++k) { olo[k] = P[k]; ohi[k] = P[3 + k]; } break;
+         case BLINGCU_SHAPE_CYLINDER: olo[0] = olo[1] = -P[0]; ohi[0] = ohi[1] = P[0]; olo[2] = P[1]; ohi[2] = P[2]; break;
+         case BLINGCU_SHAPE_DISK: olo[0] = olo[1] = -P[1]; ohi[0] = ohi[1] = P[1]; olo[2] = ohi[2] = P[0]; break;
+         case BLINGCU_SHAPE_QUAD: olo[0] = -P[0]; ohi[0] = P[0]; olo[1] = -P[1]; ohi[1] = P[1]; olo[2] = ohi[2] = 0; break;
+         default: for (int k = 0; k < 3; ++k) { olo[k] = -P[0]; ohi[k] = P[0]; } break;
+         }
+         size_t it = nt + j;
+         for (int k = 0; k < 3; ++k) { lo[3 * it + k] = BL_INF; hi[3 * it + k] = -BL_INF; }
+         for (int c = 0; c < 8; ++c) {
+            V3 q = transPoint(s.o2w, mk3((c & 4) ? ohi[0] : olo[0], (c & 2) ? ohi[1] : olo[1], (c & 1) ? ohi[2] : olo[2]));
+            float qq[3] = {q.x, q.y, q.z};
+            for (int k = 0; k < 3; ++k) { lo[3 * it + k] = std::min(lo[3 * it + k], qq[k]); hi[3 * it + k] = std::max(hi[3 * it + k], qq[k]); }
+         }
+         itemPrim[it] = (int32_t)pid;
+      }
+      BvhBuildInput bi; bi.n = nprim; bi.lo = lo.data(); bi.hi = hi.data(); bi.max_leaf = maxLeaf;
+      bi.threads = (int)std::max(1u, std::thread::hardware_concurrency());
+      BvhBuildOutput bo;
+      if (bvhBuild(bi, bo)) return fail(BLINGCU_EINVAL, "too many primitives");
+      std::vector<F4> items(3 * (nprim ? nprim : 1));
+      for (size_t k = 0; k < nprim; ++k) {
+         uint32_t src = bo.order[k];
+         F4 *q = &items[3 * k];
+         if (src < nt) {
+            const float *v = ir->tri_verts + 9 * (size_t)src;
+            q[0] = F4{v[0], v[1], v[2], i2f(itemPrim[src])};
+            q[1] = F4{v[3] - v[0], v[4] - v[1], v[5] - v[2], i2f(0)};   // e1 = p2 - p1 (TriangleMesh.hs:169)
+            q[2] = F4{v[6] - v[0], v[7] - v[1], v[8] - v[2], 0};        // e2 = p3 - p1
+         } else {
+            q[0] = F4{0, 0, 0, i2f(itemPrim[src])};
+            q[1] = F4{0, 0, 0, i2f(1 + (int)(src - nt))};
+            q[2] = F4{0, 0, 0, 0};
+         }
+      }
+      std::memset(&hs, 0, sizeof(hs));
+      hs.bvh.nodes = up<F4>(bo.nodes, 4 * (size_t)bo.n_nodes);
+      hs.bvh.items = up<F4>(items.data(), items.size());
+      hs.bvh.root = bo.root; hs.bvh.n_nodes = bo.n_nodes;
+      nNodes = (uint64_t)bo.n_nodes; nItems = nprim;
+      std::free(bo.nodes); std::free(bo.order);
+      // ---- shading geometry
+      {
+         std::vector<F4> tp(3 * (nt ? nt : 1)); std::vector<F2> tu(3 * (nt ? nt : 1));
+         for (size_t i = 0; i < nt; ++i) {
+            const float *v = ir->tri_verts + 9 * i, *u = ir->tri_uvs + 6 * i;
+            tp[3 * i] = F4{v[0], v[1], v[2], i2f(ir->tri_material[i])};
+            tp[3 * i + 1] = F4{v[3], v[4], v[5], 0}; tp[3 * i + 2] = F4{v[6], v[7], v[8], 0};
+            tu[3 * i] = F2{u[0], u[1]}; tu[3 * i + 1] = F2{u[2], u[3]}; tu[3 * i + 2] = F2{u[4], u[5]};
+         }
+         hs.tri_p = up<F4>(tp.data(), tp.size()); hs.tri_uv = up<F2>(tu.data(), tu.size());
+         hs.tri_n = (ir->tri_normals && nt) ? up<float>(ir->tri_normals, 9 * nt) : nullptr;
+      }
+      hs.prim_ref = up<uint32_t>(primRef.data(), primRef.size());
+      hs.shapes = up<blingcu_shape>(ir->shapes, ns); hs.bvh.shapes = hs.shapes;
+      hs.materials = up<blingcu_material>(ir->materials, ir->n_materials);
+      hs.textures = up<blingcu_texture>(ir->textures, ir->n_textures);
+      hs.lights = up<blingcu_light>(ir->lights, ir->n_lights); hs.n_lights = (int)ir->n_lights;
+      {
+         std::vector<blingcu_envmap> envs(ir->envs, ir->envs + ir->n_envs);
+         for (blingcu_envmap &e : envs) {
+            size_t nu = (size_t)e.nu, nv = (size_t)e.nv;
+            if (e.nu <= 0 || e.nv <= 0 || !e.cond_func || !e.cond_cdf || !e.cond_int || !e.marg_func || !e.marg_cdf) return fail(BLINGCU_EINVAL, "environment map without distribution");
+            if (e.kind == BLINGCU_ENV_RGBTABLE) { if (!e.rgb) return fail(BLINGCU_EINVAL, "rgb table missing"); e.rgb = up<float>(e.rgb, nu * nv * 3); } else e.rgb = nullptr;
+            e.cond_func = up<float>(e.cond_func, nu * nv); e.cond_cdf = up<float>(e.cond_cdf, (nu + 1) * nv); e.cond_int = up<float>(e.cond_int, nv);
+            e.marg_func = up<float>(e.marg_func, nv); e.marg_cdf = up<float>(e.marg_cdf, nv + 1);
+         }
+         hs.envs = up<blingcu_envmap>(envs.data(), envs.size());
+      }
+      hs.ftbl = up<float>(ir->filter_table, 256);
+      hs.cam = ir->camera;
+      hs.W = ir->width; hs.H = ir->height; hs.fw = ir->filter_w; hs.fh = ir->filter_h;
+      hs.ex0 = (int)floorf(0.5f - hs.fw); hs.ex1 = (int)floorf(0.5f + (float)hs.W + hs.fw);   // Image.hs:162-168
+      hs.ey0 = (int)floorf(0.5f - hs.fh); hs.ey1 = (int)floorf(0.5f + (float)hs.H + hs.fh);
+      hs.EW = hs.ex1 - hs.ex0 + 1; hs.EH = hs.ey1 - hs.ey0 + 1;
+      hs.sampler_kind = ir->sampler_kind; hs.nu = ir->nu; hs.nv = ir->nv;
+      hs.max_depth = ir->max_depth; hs.sample_depth = ir->sample_depth;
+      for (int i = 0; i < NB; ++i) { hs.cieX[i] = ir->cie_x.v[i]; hs.cieY[i] = ir->cie_y.v[i]; hs.cieZ[i] = ir->cie_z.v[i]; }
+      hs.ySum = ir->cie_y_sum;
+      for (int b = 0; b < 7; ++b) for (int i = 0; i < NB; ++i) hs.illum[b][i] = ir->illum_basis[b].v[i];
+      dscene = up<DScene>(&hs, 1);
+      npix = (uint32_t)hs.EW * (uint32_t)hs.EH;
+      film = (F4 *)be.alloc(sizeof(F4) * (size_t)hs.W * hs.H);
+      be.zero(film, sizeof(F4) * (size_t)hs.W * hs.H);
+      scanKinds(ir);
+      uploaded = true;
+      return 0;
+   }
+
+   template <class T> T *st(size_t n) { T *p = (T *)be.alloc(sizeof(T) * n); stateAllocs.push_back(p); return p; }
+   int ensureState(uint32_t cap) {
+      if (ps.cap >= cap) return 0;
+      freeState();
+      ps.cap = cap;
+      size_t c = cap;
+      ps.rayO = st<F4>(c); ps.rayD = st<F4>(c); ps.hit = st<F4>(c);
+      ps.T = st<F4>(4 * c); ps.L = st<F4>(4 * c);
+      ps.shO = st<F4>(c); ps.shD = st<F4>(c); ps.PS = st<F4>(4 * c); ps.occl = st<uint8_t>(c);
+      ps.miO = st<F4>(c); ps.miD = st<F4>(c); ps.mihit = st<F4>(c); ps.PM = st<F4>(4 * c); ps.miInfo = st<F2>(c);
+      ps.meta = st<uint32_t>(c); ps.kp = st<uint64_t>(c); ps.sidx = st<uint32_t>(c); ps.spos = st<F2>(c); ps.xyz = st<F4>(c);
+      ps.qA = st<uint32_t>(c); ps.qB = st<uint32_t>(c); ps.qShadow = st<uint32_t>(c); ps.qMis = st<uint32_t>(c);
+      ps.qMat = st<uint32_t>((size_t)N_SHADE_KINDS * c);
+      ps.counters = st<uint32_t>(N_COUNTERS); ps.stats = st<unsigned long long>(N_STATS);
+      be.zero(ps.counters, sizeof(uint32_t) * N_COUNTERS); be.zero(ps.stats, sizeof(unsigned long long) * N_STATS);
+      return 0;
+   }
+
+   // the bounce loop over n freshly generated paths (slots 0..n-1, qA = identity)
+   void bounces(uint32_t n) {
+      uint32_t cap = ps.cap;
+      uint32_t *qa = ps.qA, *qb = ps.qB;
+      for (int d = 0; d <= hs.max_depth; ++d) {
+         uint32_t bound = n;   // queues never exceed n
+         be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(qa, ps.counters + C_ACTIVE, bound, dscene, ps.rayO, ps.rayD, ps.hit);
+         be.tag(BLINGCU_KC_CLASSIFY); be.runQueue(ClassifyBody{dscene, ps}, qa, ps.counters + C_ACTIVE, bound);
+         be.tag(BLINGCU_KC_SHADE); be.runQueue(ShadeMissBody{dscene, ps}, ps.qMat, ps.counters + C_MAT0, bound);
+         launches += 3;
+         if (d < hs.max_depth) {
+            for (int k = 1; k < N_SHADE_KINDS; ++k) {
+               if (!kindPresent[k]) continue;
+               be.runQueue(ShadeHitBody{dscene, ps, qb}, ps.qMat + (size_t)k * cap, ps.counters + C_MAT0 + k, bound);
+               launches++;
+            }
+            be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl);
+            be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, bound, dscene, ps.miO, ps.miD, ps.mihit);
+            be.tag(BLINGCU_KC_RESOLVE); be.runQueue(ResolveShadowBody{ps}, ps.qShadow, ps.counters + C_SHADOW, bound);
+            be.runQueue(ResolveMisBody{dscene, ps}, ps.qMis, ps.counters + C_MIS, bound);
+            launches += 4;
+         }
+         be.tag(BLINGCU_KC_OTHER); be.run(AdvanceBody{ps}, 1); launches++;
+         uint32_t *t = qa; qa = qb; qb = t;
+      }
+   }
+
+   bool kindPresent[N_SHADE_KINDS] = {};
+   void scanKinds(const blingcu_scene *ir) {
+      for (int k = 0; k < N_SHADE_KINDS; ++k) kindPresent[k] = false;
+      kindPresent[0] = true;
+      for (uint32_t i = 0; i < ir->n_materials; ++i) kindPresent[1 + ir->materials[i].kind] = true;
+   }
+
+   int renderSlice(uint32_t pass, uint64_t seed, uint32_t sBegin, uint32_t sEnd) {
+      if (!uploaded) return fail(BLINGCU_ESTATE, "render before upload_scene");
+      uint32_t spp = (uint32_t)(hs.nu * hs.nv);
+      if (sBegin > sEnd || sEnd > spp) return fail(BLINGCU_EINVAL, "sample range out of bounds");
+      uint32_t kmax = std::max(1u, batchTarget / npix);
+      uint32_t need = std::min(kmax, std::max(1u, sEnd - sBegin)) * npix;
+      ensureState(need);
+      auto t0 = be.timerStart();
+      for (uint32_t s = sBegin; s < sEnd;) {
+         uint32_t k = std::min(kmax, sEnd - s);
+         uint32_t n = k * npix;
+         be.tag(BLINGCU_KC_OTHER); be.run(BeginBatchBody{ps, n}, 1);
+         be.tag(BLINGCU_KC_RAYGEN); be.run(RaygenBody{dscene, ps, seed, pass, s, npix, nullptr, nullptr, nullptr}, n);
+         launches += 2;
+         bounces(n);
+         be.tag(BLINGCU_KC_FILM); be.run(FinalizeBody{dscene, ps}, n);
+         be.run(FilmBody{dscene, ps, film, k, npix}, (uint32_t)hs.W * (uint32_t)hs.H);
+         launches += 2;
+         s += k;
+      }
+      lastMs = be.timerStop(t0);
+      return 0;
+   }
+
+   int renderSamples(uint32_t pass, uint64_t seed, const int32_t *px, const int32_t *py, const uint32_t *smp, size_t n, float *outL, float *outXY) {
+      if (!uploaded) return fail(BLINGCU_ESTATE, "render before upload_scene");
+      if (n == 0) return 0;
+      if (n > 0x7fffffffu) return fail(BLINGCU_EINVAL, "too many samples");
+      for (size_t i = 0; i < n; ++i)
+         if (px[i] < hs.ex0 || px[i] > hs.ex1 || py[i] < hs.ey0 || py[i] > hs.ey1 || smp[i] >= (uint32_t)(hs.nu * hs.nv)) return fail(BLINGCU_EINVAL, "sample outside the sample extent");
+      ensureState((uint32_t)n);
+      int32_t *dpx = (int32_t *)be.alloc(4 * n), *dpy = (int32_t *)be.alloc(4 * n); uint32_t *ds = (uint32_t *)be.alloc(4 * n);
+      be.upload(dpx, px, 4 * n); be.upload(dpy, py, 4 * n); be.upload(ds, smp, 4 * n);
+      be.run(BeginBatchBody{ps, (uint32_t)n}, 1);
+      be.run(RaygenBody{dscene, ps, seed, pass, 0, npix, dpx, dpy, ds}, (uint32_t)n);
+      bounces((uint32_t)n);
+      be.sync();
+      std::vector<F4> L(4 * (size_t)ps.cap); std::vector<F2> xy(n);
+      for (int q = 0; q < 4; ++q) be.download(L.data() + (size_t)q * n, ps.L + (size_t)q * ps.cap, sizeof(F4) * n);
+      be.download(xy.data(), ps.spos, sizeof(F2) * n);
+      for (size_t i = 0; i < n; ++i) {
+         for (int q = 0; q < 4; ++q) { F4 v = L[(size_t)q * n + i]; float *o = outL + 16 * i + 4 * q; o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+         outXY[2 * i] = xy[i].x; outXY[2 * i + 1] = xy[i].y;
+      }
+      be.free(dpx); be.free(dpy); be.free(ds);
+      return 0;
+   }
+
+   // explicit ray batches (parity check (a))
+   int traceBatch(const blingcu_ray *rays, size_t n, blingcu_hit *outHit, uint8_t *outOccl, uint32_t *nodes, uint32_t *prims) {
+      if (!uploaded) return fail(BLINGCU_ESTATE, "trace before upload_scene");
+      if (n == 0) return 0;
+      if (n > 0x7fffffffu) return fail(BLINGCU_EINVAL, "too many rays");
+      std::vector<F4> o(n), d(n);
+      for (size_t i = 0; i < n; ++i) { o[i] = F4{rays[i].o[0], rays[i].o[1], rays[i].o[2], rays[i].tmin}; d[i] = F4{rays[i].d[0], rays[i].d[1], rays[i].d[2], rays[i].tmax}; }
+      F4 *dO = (F4 *)be.alloc(sizeof(F4) * n), *dD = (F4 *)be.alloc(sizeof(F4) * n);
+      be.upload(dO, o.data(), sizeof(F4) * n); be.upload(dD, d.data(), sizeof(F4) * n);
+      if (outHit) {
+         F4 *dH = (F4 *)be.alloc(sizeof(F4) * n);
+         uint32_t *dN = nullptr, *dP = nullptr;
+         if (nodes) { dN = (uint32_t *)be.alloc(4 * n); dP = (uint32_t *)be.alloc(4 * n); be.traceStats((uint32_t)n, dscene, dO, dD, dH, dN, dP); }
+         else be.traceNearest(nullptr, nullptr, (uint32_t)n, dscene, dO, dD, dH);
+         be.sync();
+         std::vector<F4> h(n); be.download(h.data(), dH, sizeof(F4) * n);
+         for (size_t i = 0; i < n; ++i) { outHit[i].t = h[i].x; outHit[i].b1 = h[i].y; outHit[i].b2 = h[i].z; outHit[i].prim = f2i(h[i].w); }
+         if (nodes) { be.download(nodes, dN, 4 * n); be.download(prims, dP, 4 * n); be.free(dN); be.free(dP); }
+         be.free(dH);
+      }
+      if (outOccl) {
+         uint8_t *dC = (uint8_t *)be.alloc(n);
+         be.traceAny(nullptr, nullptr, (uint32_t)n, dscene, dO, dD, dC);
+         be.sync();
+         be.download(outOccl, dC, n);
+         be.free(dC);
+      }
+      be.free(dO); be.free(dD);
+      return 0;
+   }
+
+   int getStats(blingcu_stats *out) {
+      std::memset(out, 0, sizeof(*out));
+      if (ps.stats) {
+         be.sync();
+         unsigned long long s[N_STATS]; be.download(s, ps.stats, sizeof(s));
+         out->samples = s[S_SAMPLES]; out->rays_camera = s[S_CAM]; out->rays_extension = s[S_EXT]; out->rays_mis = s[S_MIS];
+         out->rays_shadow = s[S_SHADOW]; out->dropped_samples = s[S_DROPPED];
+      }
+      be.traversalTotals(out->nodes_traversed, out->intersections, out->rays_counted);
+      out->kernel_launches = launches; out->bvh_nodes = nNodes; out->bvh_leaf_items = nItems; out->last_pass_ms = lastMs;
+      return 0;
+   }
+   void resetStats() { if (ps.stats) be.zero(ps.stats, sizeof(unsigned long long) * N_STATS); launches = 0; be.resetProfile(); }
+};
+
+}  // namespace bl

@@ -1,0 +1,137 @@
+"""Host-side mirror of bling's renderer plug-in seam for the path-integrator hot path.
+
+Reference interface (Graphics/Bling/Rendering.hs):
+    class Renderer a where render :: a -> RenderJob -> ProgressReporter -> IO ()      (:77-78)
+    data RenderJob = MkJob { jobScene, jobPixelFilter, jobImageSize }                 (:37-41)
+    data Progress  = Started | ... | PassDone { progPassNum, finalImg, splatWeight }  (:60-73)
+    type ProgressReporter = Progress -> IO Bool     -- False stops the progressive loop (:75, :137-138)
+
+`CudaRenderer.render(job, report)` is `prender` (:111-140) with the tile loop replaced by the CUDA core: upload
+the flat scene once, then per pass { render this rank's sample shard; sum films over ranks; report PassDone }.
+Multi-GPU = one process per GPU (torch.distributed, NCCL): every rank holds a full scene replica and renders the
+sample indices [rank*spp/world, (rank+1)*spp/world) of every pixel; the only exchange is one all-reduce(sum) of
+the [H][W][4] f32 film per report, the analogue of the reference's sequential addTile merge.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import api
+from . import ir as IR
+
+
+@dataclass
+class RenderJob:
+    """mkJob scene filter size: the flat IR already carries the pixel filter table and the image size."""
+    scene: IR.SceneIR
+
+    @property
+    def image_size(self):
+        return (self.scene.width, self.scene.height)
+
+
+@dataclass
+class Started:
+    pass
+
+
+@dataclass
+class PassDone:
+    pass_num: int
+    final_img: np.ndarray      # [H][W]{weight, X*w, Y*w, Z*w}: Img._imgP (Image.hs:123-129)
+    splat_weight: float = 1.0
+
+
+ProgressReporter = Callable[[object], bool]
+
+
+def shard_range(spp: int, rank: int, world: int):
+    """sample indices of one pass owned by `rank` (contiguous, balanced, covers [0,spp) exactly once)."""
+    return (spp * rank) // world, (spp * (rank + 1)) // world
+
+
+class _DevFilm:
+    """zero-copy view of the device film for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, n_floats):
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class CudaRenderer:
+    """The `Renderer` instance backed by libblingcu.so (keyword `renderer { cuda sampled {...} }` on the bling side)."""
+
+    def __init__(self, device: Optional[int] = None, seed: int = 0x5EED, context_cls=api.Context, process_group=None):
+        self.seed = seed
+        self.rank, self.world = 0, 1
+        self._dist = None
+        self._pg = process_group
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self._dist = dist
+                self.rank, self.world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        except ImportError:
+            pass
+        if device is None:
+            import os
+            device = int(os.environ.get("LOCAL_RANK", "0")) if self._dist is not None else 0
+        self.ctx = context_cls(device) if context_cls is api.Context else context_cls()
+        self._job = None
+
+    def pretty_print(self) -> str:
+        return "cuda sampler renderer"
+
+    def upload(self, job: RenderJob):
+        self.ctx.upload_scene(job.scene)
+        self._job = job
+
+    def render_pass_shard(self, pass_num: int):
+        """this rank's share of pass `pass_num` (device-side accumulate, asynchronous)."""
+        s0, s1 = shard_range(self._job.scene.spp, self.rank, self.world)
+        if s1 > s0:
+            self.ctx.render_slice(pass_num, self.seed, s0, s1)
+
+    def gather_film(self) -> np.ndarray:
+        """sum of the per-rank films (all-reduce), returned on the host in Img._imgP layout."""
+        sc = self._job.scene
+        if self._dist is None or self.world == 1:
+            return self.ctx.read_film()
+        import torch
+        dist = self._dist
+        backend = dist.get_backend(self._pg)
+        if backend == "nccl":
+            ptr, n = self.ctx.film_device()
+            self.ctx.synchronize()
+            local = torch.as_tensor(_DevFilm(ptr, n), device=torch.device("cuda", torch.cuda.current_device()))
+            total = local.clone()
+            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self._pg)
+            return total.cpu().numpy().reshape(sc.height, sc.width, 4)
+        total = torch.from_numpy(self.ctx.read_film())     # gloo (CPU tests of the host logic)
+        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self._pg)
+        return total.numpy()
+
+    def render(self, job: RenderJob, report: ProgressReporter, first_pass: int = 1):
+        """prender (Rendering.hs:111-140): progressive passes until the reporter returns False."""
+        self.upload(job)
+        report(Started())
+        p = first_pass
+        while True:
+            self.render_pass_shard(p)
+            img = self.gather_film()
+            cont = report(PassDone(p, img, 1.0))
+            if self._dist is not None and self.world > 1:      # every rank must take the same decision
+                import torch
+                flag = torch.tensor([1 if cont else 0], dtype=torch.int32)
+                if self._dist.get_backend(self._pg) == "nccl":
+                    flag = flag.cuda()
+                self._dist.broadcast(flag, src=0, group=self._pg)
+                cont = bool(flag.item())
+            if not cont:
+                break
+            p += 1
+
+    def close(self):
+        self.ctx.close()

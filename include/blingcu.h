@@ -207,7 +207,8 @@ typedef struct blingcu_stats {
    uint64_t samples;
    uint64_t rays_camera, rays_extension, rays_mis, rays_shadow;
    uint64_t dropped_samples;   /* NaN/Inf samples skipped (Image.hs:253-256) */
-   uint64_t nodes_traversed, intersections;  /* only filled by blingcu_trace_stats */
+   uint64_t nodes_traversed, intersections;  /* nearest-hit kernel totals while option "traversal_stats" = 1 */
+   uint64_t rays_counted;      /* nearest-hit rays traced while "traversal_stats" = 1 (denominator of the two above) */
    uint64_t kernel_launches;
    uint64_t bvh_nodes, bvh_leaf_items;
    double last_pass_ms;        /* device time of the last render call        */
@@ -251,6 +252,14 @@ int blingcu_synchronize(blingcu_ctx *);
 
 int blingcu_get_stats(blingcu_ctx *, blingcu_stats *out);
 int blingcu_reset_stats(blingcu_ctx *);
+
+/* per-kernel-class device time, measured with CUDA events on the launching stream while option
+ * "profile_kernels" = 1. Classes: see BLINGCU_KC_*. Arrays have n_classes entries (<= BLINGCU_KC_COUNT). */
+enum {
+   BLINGCU_KC_RAYGEN = 0, BLINGCU_KC_TRACE_NEAREST = 1, BLINGCU_KC_TRACE_ANY = 2, BLINGCU_KC_CLASSIFY = 3,
+   BLINGCU_KC_SHADE = 4, BLINGCU_KC_RESOLVE = 5, BLINGCU_KC_FILM = 6, BLINGCU_KC_OTHER = 7, BLINGCU_KC_COUNT = 8
+};
+int blingcu_kernel_times(blingcu_ctx *, double *ms, uint64_t *launches, int n_classes);
 
 /* tuning knobs (optional): "batch_samples" (paths per wavefront), "bvh_leaf" ... returns EINVAL if unknown */
 int blingcu_set_option(blingcu_ctx *, const char *key, double value);

@@ -1,0 +1,93 @@
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from bling_b200 import ir as IR  # noqa: E402
+from bling_b200.host.loader import resized  # noqa: E402
+
+SCENES = ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def load_scene(name) -> IR.SceneIR:
+    return IR.SceneIR.load(ROOT / "tests" / "golden" / "scenes" / f"{name}.npz")
+
+
+@pytest.fixture(scope="session")
+def scenes():
+    return {n: load_scene(n) for n in SCENES}
+
+
+def small(scene, w=48, h=36, nu=4, nv=4):
+    return resized(scene, w, h, nu, nv)
+
+
+def random_rays(scene: IR.SceneIR, n: int, seed: int) -> np.ndarray:
+    """rays that exercise the accelerator: origins inside/around the scene bounds, random directions, plus
+    axis-parallel directions (zero components -> infinite reciprocals, Q12) and finite ranges."""
+    rng = np.random.default_rng(seed)
+    pts = [scene.tri_verts.reshape(-1, 3)] if len(scene.tri_verts) else []
+    for s in scene.shapes:
+        m = np.array(list(s.o2w), np.float32).reshape(4, 4)
+        r = max(abs(x) for x in list(s.p)[:6]) or 1.0
+        c = m[:3, 3]
+        pts.append(np.stack([c - r, c + r]))
+    pts = np.concatenate(pts)
+    lo, hi = pts.min(0), pts.max(0)
+    lo = np.maximum(lo, -2000); hi = np.minimum(hi, 2000)      # huge ground quads would dilute the sampling
+    ext = hi - lo
+    rays = np.zeros(n, IR.RAY_DTYPE)
+    rays["o"] = (lo - 0.25 * ext + rng.random((n, 3)) * 1.5 * ext).astype(np.float32)
+    d = rng.normal(size=(n, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    k = n // 10
+    axis = rng.integers(0, 3, k); sign = rng.choice([-1.0, 1.0], k)
+    d[:k] = 0; d[np.arange(k), axis] = sign
+    rays["d"] = d.astype(np.float32)
+    rays["tmin"] = np.where(rng.random(n) < 0.5, 0.0, 1e-3).astype(np.float32)
+    tmax = np.full(n, np.inf, np.float32)
+    fin = rng.random(n) < 0.3
+    tmax[fin] = (rng.random(fin.sum()) * np.linalg.norm(ext)).astype(np.float32)
+    rays["tmax"] = tmax
+    return rays
+
+
+def camera_rays(ctx_or_oracle, scene, n, seed):
+    """primary-ray-like batch: from the camera position towards random points of the scene bounds."""
+    rng = np.random.default_rng(seed)
+    c2w = np.array(list(scene.camera.cam2world), np.float32).reshape(4, 4)
+    o = c2w[:3, 3]
+    fwd = c2w[:3, 2]; right = c2w[:3, 0]; up = c2w[:3, 1]
+    uv = (rng.random((n, 2)) - 0.5) * 0.7
+    d = fwd[None] + uv[:, :1] * right[None] + uv[:, 1:] * up[None]
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros(n, IR.RAY_DTYPE)
+    rays["o"] = o; rays["d"] = d.astype(np.float32); rays["tmin"] = 0; rays["tmax"] = np.inf
+    return rays
+
+
+def compare_hits(got, ref, rays=None):
+    """parity (a): prim id exact except measured t-ties; t within 1e-5 relative. Returns (n_ties, n_bad)."""
+    same = got["prim"] == ref["prim"]
+    both = (got["prim"] >= 0) & (ref["prim"] >= 0)
+    tclose = np.abs(got["t"] - ref["t"]) <= 1e-5 * np.maximum(np.abs(ref["t"]), 1e-30)
+    ties = (~same) & both & tclose
+    bad = ~(same | ties)
+    bad |= same & both & ~tclose
+    return int(ties.sum()), int(bad.sum())
+
+
+def has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False

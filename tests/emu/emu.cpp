@@ -1,0 +1,45 @@
+// emu.cpp -- CPU kernel-body EMULATOR. TEST INFRASTRUCTURE ONLY (tests -m "not gpu").
+// It drives the exact kernel bodies of bling_b200/csrc/bodies.h one item at a time on the host so that the
+// no-GPU CI can check the wavefront logic against the oracle. It is NOT a fallback: libblingcu.so does not
+// contain it, bling_b200/ never loads it, and blingcu_create() fails with BLINGCU_ENOGPU without a device.
+#include "../../bling_b200/csrc/api_impl.h"
+#include <chrono>
+#include <cstdlib>
+
+struct EmuBackend {
+   int init(int, std::string &) { return 0; }
+   void shutdown() {}
+   template <class F> int guard(std::string &, F f) { return f(); }
+   bool setOption(const std::string &, double) { return false; }
+   void *alloc(size_t n) { return std::malloc(n ? n : 1); }
+   void free(void *p) { std::free(p); }
+   void upload(void *d, const void *s, size_t n) { std::memcpy(d, s, n); }
+   void download(void *d, const void *s, size_t n) { std::memcpy(d, s, n); }
+   void zero(void *d, size_t n) { std::memset(d, 0, n); }
+   void sync() {}
+   void tag(int) {}
+   void kernelTimes(double *ms, uint64_t *l, int n) { for (int i = 0; i < n; ++i) { ms[i] = 0; l[i] = 0; } }
+   void traversalTotals(uint64_t &a, uint64_t &b, uint64_t &c) { a = b = c = 0; }
+   void resetProfile() {}
+   std::chrono::steady_clock::time_point timerStart() { return std::chrono::steady_clock::now(); }
+   double timerStop(std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+   template <class B> void run(const B &b, uint32_t n) { for (uint32_t i = 0; i < n; ++i) b(i); }
+   template <class B> void runQueue(const B &b, const uint32_t *q, const uint32_t *cnt, uint32_t) { uint32_t n = *cnt; for (uint32_t i = 0; i < n; ++i) b(q[i]); }
+   void traceNearest(const uint32_t *q, const uint32_t *cnt, uint32_t n, const bl::DScene *sc, const bl::F4 *o, const bl::F4 *d, bl::F4 *hit) {
+      bl::TraceNearestBody b{sc, o, d, hit};
+      if (q) runQueue(b, q, cnt, n); else run(b, n);
+   }
+   void traceAny(const uint32_t *q, const uint32_t *cnt, uint32_t n, const bl::DScene *sc, const bl::F4 *o, const bl::F4 *d, uint8_t *occl) {
+      bl::TraceAnyBody b{sc, o, d, occl};
+      if (q) runQueue(b, q, cnt, n); else run(b, n);
+   }
+   void traceStats(uint32_t n, const bl::DScene *sc, const bl::F4 *o, const bl::F4 *d, bl::F4 *hit, uint32_t *nodes, uint32_t *prims) {
+      for (uint32_t i = 0; i < n; ++i) {
+         nodes[i] = 0; prims[i] = 0;
+         bl::HitRec h = bl::traceNearest<true>(sc->bvh, bl::loadRay(o, d, i), nodes + i, prims + i);
+         hit[i] = bl::F4{h.t, h.b1, h.b2, bl::i2f(h.prim)};
+      }
+   }
+};
+
+BL_DEFINE_API(blingemu, EmuBackend)

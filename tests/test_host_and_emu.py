@@ -1,0 +1,186 @@
+"""CPU suite, part 2: the C-ABI library loads and exports every declared symbol (no compute without a GPU),
+the kernel BODIES (bling_b200/csrc/bodies.h) driven by the CPU emulator agree with the oracle, the host-side
+renderer logic and its 2-rank (gloo) sharding."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from bling_b200 import api, ir as IR
+from bling_b200.renderer import CudaRenderer, PassDone, RenderJob, shard_range
+from oracle.oracle_py import Oracle
+from tests.conftest import ROOT, SCENES, camera_rays, compare_hits, has_gpu, load_scene, random_rays, small
+from tests.emu.emu_py import EmuContext
+
+
+def test_abi_exports_every_declared_symbol():
+    import __graft_entry__ as g
+    so = g.build_cuda()
+    hdr = (ROOT / "include" / "blingcu.h").read_text()
+    declared = sorted(set(re.findall(r"\b(blingcu_[a-z_]+)\s*\(", hdr)))
+    assert len(declared) == len(api.SYMBOLS) == 20
+    L = ctypes.CDLL(str(so))
+    for name in declared:
+        assert hasattr(L, name), name
+    assert sorted("blingcu_" + s for s in api.SYMBOLS) == declared
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_product_fails_loudly_without_gpu():
+    """no CPU fallback: creating a context without a device is an error, not a silent CPU path."""
+    with pytest.raises(api.BlingCuError) as e:
+        api.Context(0)
+    assert e.value.code == 3 and "no CPU fallback" in str(e.value)
+
+
+def test_ir_roundtrip(tmp_path):
+    sc = load_scene("environment")
+    sc.save(tmp_path / "x.npz")
+    sc2 = IR.SceneIR.load(tmp_path / "x.npz")
+    assert np.array_equal(sc.env_arrays[0].rgb, sc2.env_arrays[0].rgb)
+    assert bytes(sc.shapes[3]) == bytes(sc2.shapes[3]) and sc2.max_depth == sc.max_depth
+    a, _ = sc.to_c(); b, _ = sc2.to_c()
+    assert a.n_shapes == b.n_shapes == 7 and a.width == 1920
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_emulated_traversal_matches_oracle(name):
+    """parity (a) for the traversal BODY + BVH builder: prim id exact except measured t-ties, t within 1e-5."""
+    sc = load_scene(name)
+    o = Oracle(sc, kdtree=(name == "ducky")); e = EmuContext(); e.upload_scene(sc)
+    n = 3000
+    rays = np.concatenate([random_rays(sc, n, 3), camera_rays(None, sc, n, 4)])
+    ref = o.trace_nearest(rays, "kd" if name == "ducky" else "brute")
+    got = e.trace_nearest(rays)
+    ties, bad = compare_hits(got, ref)
+    assert bad == 0 and ties <= 0.01 * len(rays), (ties, bad)
+    hit = ref["prim"] >= 0
+    assert np.array_equal(got["t"][hit & (got["prim"] == ref["prim"])], ref["t"][hit & (got["prim"] == ref["prim"])])   # bit-exact t
+    occ_ref = o.trace_occluded(rays, "kd" if name == "ducky" else "brute")
+    assert (e.trace_occluded(rays) != occ_ref).mean() < 2e-3
+    _, nodes, prims = e.trace_stats(rays[:500])
+    assert nodes.max() > 0 and prims.sum() > 0
+
+
+@pytest.mark.parametrize("name", SCENES)
+def test_emulated_path_samples_match_oracle(name):
+    """per-sample radiance of the wavefront bodies == oracle's recursive nextVertex on the same sampler SPEC."""
+    sc = small(load_scene(name), 40, 30, 4, 4)
+    o = Oracle(sc); e = EmuContext(); e.upload_scene(sc)
+    x0, x1, y0, y1 = o.sample_extent()
+    rng = np.random.default_rng(5)
+    n = 1500
+    px, py, s = rng.integers(x0, x1 + 1, n), rng.integers(y0, y1 + 1, n), rng.integers(0, 16, n)
+    Lo, xyo = o.render_samples(2, 77, px, py, s)
+    Le, xye = e.render_samples(2, 77, px, py, s)
+    assert np.array_equal(xyo, xye)
+    rel = np.abs(Lo - Le).max(1) / (np.abs(Lo).max(1) + 1e-6)
+    assert (rel < 1e-4).mean() > 0.999, rel.max()
+
+
+def test_emulated_film_matches_oracle_tiles():
+    """the atomic-free film gather reproduces per-tile addSample + addTile (Q10) to float rounding."""
+    for name, wh in (("cornell-box", (37, 29)), ("sun-sky", (33, 20)), ("ducky", (30, 18))):
+        sc = small(load_scene(name), *wh, 2, 2)
+        o = Oracle(sc); e = EmuContext(); e.upload_scene(sc)
+        o.render_pass(1, 21, threads=4); e.render_pass(1, 21)
+        fo, fe = o.read_film(), e.read_film()
+        assert np.abs(fo - fe).max() <= 2e-5 * max(1.0, np.abs(fo).max()), name
+        so, se = o.stats(), e.stats()
+        for k in ("samples", "rays_camera", "rays_extension", "rays_mis", "rays_shadow", "dropped_samples"):
+            assert so[k] == se[k], (name, k)
+
+
+def test_slices_and_batches_compose():
+    """render_pass == union of slices == any batch size (linearity of the film in the sample set)."""
+    sc = small(load_scene("glass-torus"), 32, 24, 4, 4)
+    a = EmuContext(); a.upload_scene(sc); a.render_pass(3, 9)
+    b = EmuContext(); b.set_option("batch_samples", 3000); b.upload_scene(sc)
+    b.render_slice(3, 9, 0, 5); b.render_slice(3, 9, 5, 16)
+    fa, fb = a.read_film(), b.read_film()
+    assert np.abs(fa - fb).max() <= 1e-5 * np.abs(fa).max()
+    with pytest.raises(api.BlingCuError):
+        b.render_slice(3, 9, 4, 17)
+    b.clear_film(); assert b.read_film().max() == 0
+    b.film_add_host(fa); assert np.array_equal(b.read_film(), fa)
+
+
+def test_api_error_paths():
+    e = EmuContext()
+    with pytest.raises(api.BlingCuError) as ex:
+        e.render_pass(1, 1)
+    assert ex.value.code == 4
+    sc = small(load_scene("cornell-box"), 16, 16, 1, 1)
+    bad = IR.SceneIR.load(ROOT / "tests" / "golden" / "scenes" / "cornell-box.npz")
+    bad.tri_material = bad.tri_material.copy(); bad.tri_material[0] = 99
+    with pytest.raises(api.BlingCuError) as ex:
+        e.upload_scene(bad)
+    assert ex.value.code == 1 and "material" in str(ex.value)
+    e.upload_scene(sc)
+    assert len(e.trace_nearest(np.zeros(0, IR.RAY_DTYPE))) == 0
+    with pytest.raises(api.BlingCuError):
+        e.set_option("no_such_option", 1)
+
+
+def test_renderer_progressive_loop():
+    """prender semantics: PassDone per pass with the accumulated film; returning False stops (Rendering.hs:137-138)."""
+    sc = small(load_scene("cornell-box"), 24, 24, 2, 2)
+    r = CudaRenderer(context_cls=EmuContext, seed=5)
+    seen = []
+
+    def report(p):
+        if isinstance(p, PassDone):
+            seen.append((p.pass_num, float(p.final_img[..., 0].sum())))
+            return p.pass_num < 3
+        return True
+    r.render(RenderJob(sc), report)
+    assert [p for p, _ in seen] == [1, 2, 3]
+    assert seen[0][1] < seen[1][1] < seen[2][1]            # filter weights accumulate over passes
+    assert abs(seen[2][1] / seen[0][1] - 3.0) < 2e-2
+
+
+def test_shard_range_partitions():
+    for spp in (1, 4, 64, 1024):
+        for world in (1, 2, 3, 8):
+            r = [shard_range(spp, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == spp and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch.distributed as dist
+from bling_b200.renderer import CudaRenderer, RenderJob, PassDone
+from tests.emu.emu_py import EmuContext
+from tests.conftest import load_scene, small
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+sc = small(load_scene("cornell-box"), 24, 20, 4, 4)
+r = CudaRenderer(context_cls=EmuContext, seed=31)
+out = []
+r.render(RenderJob(sc), lambda p: (out.append(p.final_img) or False) if isinstance(p, PassDone) else True)
+if dist.get_rank() == 0: np.save({out!r}, out[0])
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_sample_sharding_gloo(tmp_path):
+    """world_size 2: each rank renders half of the pass' sample indices, one all-reduce sums the films; the result
+    equals the single-process pass (same sampler keys) to float rounding."""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    out = str(tmp_path / "film.npy")
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER.format(root=str(ROOT), port=port, out=out))
+    procs = [subprocess.Popen([sys.executable, str(script), str(k)], env=dict(os.environ, OMP_NUM_THREADS="1")) for k in range(2)]
+    for p in procs:
+        assert p.wait(timeout=240) == 0
+    film2 = np.load(out)
+    sc = small(load_scene("cornell-box"), 24, 20, 4, 4)
+    e = EmuContext(); e.upload_scene(sc); e.render_pass(1, 31)
+    film1 = e.read_film()
+    assert np.abs(film1 - film2).max() <= 1e-5 * np.abs(film1).max()

@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Converged ORACLE renders (>= 4096 spp) of every config scene at reduced resolution, committed under
+tests/golden/renders/ and used by tests/test_gpu_parity.py::test_converged_render_vs_golden (parity check (b)).
+NOTE: these are outputs of the CPU restatement, not of GHC-built bling (absent: parity unpinned).
+The rel-MSE bound is 3x the rel-MSE between two independent 2048-spp halves of the oracle render (the noise floor).
+
+    python tools/make_golden_renders.py [scene ...]
+"""
+import os
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from bling_b200 import image, ir as IR  # noqa: E402
+from bling_b200.host.loader import resized  # noqa: E402
+from oracle.oracle_py import Oracle  # noqa: E402
+
+W, H, NU, NV, PASSES, SEED = 80, 60, 4, 4, 256, 0xB11D6
+OUT = ROOT / "tests" / "golden" / "renders"
+
+
+def rel_mse(a, b):
+    return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-3)))
+
+
+def main(names):
+    OUT.mkdir(parents=True, exist_ok=True)
+    for name in names:
+        sc = resized(IR.SceneIR.load(ROOT / "tests" / "golden" / "scenes" / f"{name}.npz"), W, H, NU, NV)
+        t = time.time()
+        halves = []
+        for half in range(2):
+            o = Oracle(sc)
+            for p in range(1 + half * PASSES // 2, 1 + (half + 1) * PASSES // 2):
+                o.render_pass(p, SEED, threads=os.cpu_count())
+            halves.append(o.read_film())
+        full = halves[0] + halves[1]
+        xa, xb, xf = (image.film_xyz(f) for f in (halves[0], halves[1], full))
+        floor = rel_mse(xa, xb)
+        np.savez_compressed(OUT / f"{name}.npz", xyz=xf, cfg=np.array([W, H, NU, NV, PASSES]), relmse_halves=floor,
+                            relmse_bound=3 * floor, seed=SEED)
+        print(f"{name}: {time.time() - t:.0f}s, rel-MSE between 2048-spp halves {floor:.3e}, mean XYZ {xf.mean((0, 1))}", flush=True)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"])
