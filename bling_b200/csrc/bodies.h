@@ -49,7 +49,9 @@ HD Ray loadRay(const F4 *o, const F4 *d, uint32_t i) { F4 a = o[i], b = d[i]; Ra
 // queue append: warp-aggregated atomic on the device, plain increment in the single-threaded emulator
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ void qPush(uint32_t *q, uint32_t *counter, uint32_t v) {
-   unsigned m = __activemask();
+   // lanes of one warp may push to DIFFERENT queues at the same call site (classify: one queue per material
+   // kind), so the aggregation groups lanes by counter address
+   unsigned m = __match_any_sync(__activemask(), (unsigned long long)(uintptr_t)counter);
    unsigned lane = threadIdx.x & 31u;
    int leader = __ffs(m) - 1;
    uint32_t base = 0;
