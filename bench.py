@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the path-integrator hot path (BASELINE.json / SURVEY.md §8d).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (config.workload): BASELINE.json configs[4], the synthetic 10M-triangle soup at 3840x2160, stratified
+32x32 (1024 sample indices per pixel), path integrator maxDepth 5 / sampleDepth 3, box filter.
+One STEP = one call of blingcu_render_slice on every rank: `--sps` sample indices of every pixel of the sample
+extent (3842x2162 px) per GPU, i.e. a fixed batch of camera samples per GPU (weak scaling: rank r of N renders
+indices [step*N*sps + r*sps, +sps) of the pass), followed -- for N > 1 -- by the NCCL all-reduce(sum) of the
+[H][W][4] f32 film, the only exchange of the path.
+
+value      = camera samples fully processed (raygen .. film) by ALL ranks / max-over-ranks device time, scene
+             resident in HBM (CUDA events on the launching stream).
+e2e        = the same metric through the renderer seam (CudaRenderer: pass -> film on the HOST, PassDone), film
+             device->host copy inside the timed region; e2e_trace = blingcu_trace_nearest on HOST ray/hit buffers.
+roofline   = trace_nearest (the dominant kernel): algorithmic bytes per ray x rays per launch / mean
+             launch duration measured live with CUDA events around every launch, vs measured HBM copy bandwidth.
+cpu_baseline / --impl reference = oracle/ (C++ restatement of the reference's CPU algorithm, kd-tree and all)
+             on the host cores, bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "path-traced camera samples per second, whole job (Mrays/s in `mrays_per_s`)"
+UNIT = "Msamples/s"
+NODE_BYTES, ITEM_BYTES, RAY_IN_BYTES, HIT_OUT_BYTES = 64, 48, 32, 16     # bling_b200/csrc/bvh.h layout
+SEED = 0xB11D6
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--tris", type=int, default=10_000_000)
+    ap.add_argument("--width", type=int, default=3840)
+    ap.add_argument("--height", type=int, default=2160)
+    ap.add_argument("--sps", type=int, default=2, help="sample indices per pixel per GPU per step")
+    ap.add_argument("--cpu-width", type=int, default=640, help="film width of the bounded CPU sample (same camera)")
+    ap.add_argument("--cpu-height", type=int, default=360)
+    ap.add_argument("--cpu-sps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--option", action="append", default=[], help="key=value passed to blingcu_set_option")
+    return ap.parse_args()
+
+
+def workload_config(a, n_gpus):
+    return {"workload": f"synthetic {a.tris}-triangle soup, {a.width}x{a.height}, stratified 32x32 (1024 spp/pass), "
+                        f"path integrator maxDepth 5 sampleDepth 3, box filter (BASELINE.json configs[4])",
+            "step": f"{a.sps} sample indices per pixel of the 3842x2162-style sample extent per GPU "
+                    f"(+ NCCL film all-reduce when n_gpus > 1)",
+            "triangles": a.tris, "width": a.width, "height": a.height, "spp_per_pass": 1024, "max_depth": 5,
+            "sample_depth": 3, "sharding": f"sample-index x{n_gpus}, full scene replica per GPU",
+            "l2": "per-step working set (path state ~4 GB + 1.2 GB BVH/triangles) >> 126 MB L2; no flush needed",
+            "seed": SEED}
+
+
+def build_scene(a):
+    from bling_b200.host.soup import make_soup
+    return make_soup(a.tris, a.width, a.height, 32, 32, seed=SEED)
+
+
+# ----------------------------------------------------------------------------------------------- CPU (oracle) leg
+def cpu_reference_run(scene, a, steps, warmup):
+    """the reference's CPU algorithm (oracle/, kind "port": GHC is absent) on all host cores, on a
+    bounded sample: same soup, same camera, a (cpu_width x cpu_height) film, cpu_sps sample indices per step."""
+    from bling_b200.host.loader import resized
+    from oracle.oracle_py import Oracle
+    cores = os.cpu_count() or 1
+    sc = resized(scene, a.cpu_width, a.cpu_height, 32, 32)
+    t0 = time.perf_counter()
+    orc = Oracle(sc, kdtree=True)
+    build_s = time.perf_counter() - t0
+    s = 0
+    for _ in range(warmup):
+        orc.render_slice(1, SEED, s, s + a.cpu_sps, threads=cores); s += a.cpu_sps
+    orc.reset_stats()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.render_slice(1, SEED, s, s + a.cpu_sps, threads=cores); s += a.cpu_sps
+    dt = time.perf_counter() - t0
+    st = orc.stats()
+    rays = st["rays_camera"] + st["rays_extension"] + st["rays_mis"] + st["rays_shadow"]
+    orc.close()
+    return {"value": st["samples"] / dt / 1e6, "unit": UNIT, "mrays_per_s": rays / dt / 1e6, "cores": cores,
+            "kind": "port",
+            "sample": f"same soup ({a.tris} triangles, SAH kd-tree as KdTree.hs) and camera on a {a.cpu_width}x{a.cpu_height} "
+                      f"film, {steps} steps x {a.cpu_sps} sample indices/pixel = {st['samples']} samples in {dt:.1f} s; "
+                      f"kd-tree build {build_s:.1f} s not timed",
+            "seconds": dt, "ms_per_step": dt / max(1, steps) * 1e3}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene = build_scene(a)
+    cb = cpu_reference_run(scene, a, a.steps, a.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "mrays_per_s": cb["mrays_per_s"],
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": cb["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(a, a.gpus), "gpu_launches": 0,
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "oracle/ C++ restatement of bling's CPU path (the Haskell reference cannot be built here: no GHC)"}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            pass
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try: self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired: self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9: continue
+            try: sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+            except ValueError: continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"): reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm), "power_w_max": float(max(pw))}
+        return out
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy bandwidth, of measured)"
+        except Exception:
+            pass
+    return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+def committed_traffic():
+    """dram bytes per trace_nearest launch from the committed ncu --set full capture of this command (profiles/)."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text())
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from bling_b200 import api
+    from bling_b200.renderer import CudaRenderer, PassDone, RenderJob
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+
+    t0 = time.perf_counter()
+    scene = build_scene(a)
+    t_scene = time.perf_counter() - t0
+    ctx = api.Context(local)
+    for kv in a.option:
+        k, v = kv.split("="); ctx.set_option(k, float(v))
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    t0 = time.perf_counter()
+    ctx.upload_scene(scene)
+    t_upload = time.perf_counter() - t0
+    scene_bytes = int(scene.tri_verts.nbytes + scene.tri_uvs.nbytes + scene.tri_material.nbytes)
+    fptr, fn = ctx.film_device()
+
+    class _Dev:
+        def __init__(s, ptr, n): s.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    film_t = torch.as_tensor(_Dev(fptr, fn), device=torch.device("cuda", local))
+    film_sum = torch.empty_like(film_t) if world > 1 else None
+
+    sps = a.sps
+    spp = scene.spp
+
+    def step(i):
+        # rank r renders sample indices [base + r*sps, +sps) of pass p; wraps to the next pass after 1024 indices
+        g = i * world * sps + rank * sps
+        p, s0 = 1 + g // spp, g % spp
+        s1 = min(spp, s0 + sps)
+        ctx.render_slice(p, SEED, s0, s1)
+        if world > 1:
+            film_sum.copy_(film_t)
+            dist.all_reduce(film_sum, op=dist.ReduceOp.SUM)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for i in range(a.warmup):
+            step(i)
+        barrier()
+        ctx.reset_stats()
+        ctx.set_option("profile_kernels", 1)
+        clocks = ClockSampler(local)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for i in range(a.steps):
+            step(a.warmup + i)
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        clk = clocks.stop()
+        st = ctx.stats()
+        kt = ctx.kernel_times()
+        ctx.set_option("profile_kernels", 0)
+
+        tot = torch.tensor([ms, float(st["samples"]), float(st["rays_camera"] + st["rays_extension"] + st["rays_mis"]),
+                            float(st["rays_shadow"]), float(st["kernel_launches"])], dtype=torch.float64, device="cuda")
+        if world > 1:
+            mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            sm = tot.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            ms_max = float(mx[0]); samples, rays_n, rays_s, launches = (float(x) for x in sm[1:])
+        else:
+            ms_max = ms; samples, rays_n, rays_s, launches = (float(x) for x in tot[1:])
+        value = samples / (ms_max * 1e-3) / 1e6
+        mrays = (rays_n + rays_s) / (ms_max * 1e-3) / 1e6
+
+        # ---- traversal counters for the roofline: one more (untimed) step with the instrumented kernel on rank 0
+        roofline = None
+        if rank == 0:
+            ctx.set_option("traversal_stats", 1); ctx.reset_stats()
+            film_keep = film_t.clone()
+            step(a.warmup)                      # same rays as the first timed step
+            torch.cuda.synchronize()
+            film_t.copy_(film_keep)
+            s2 = ctx.stats()
+            ctx.set_option("traversal_stats", 0)
+            n_nodes = s2["nodes_traversed"] / max(1, s2["rays_counted"])
+            n_prims = s2["intersections"] / max(1, s2["rays_counted"])
+            b_ray = RAY_IN_BYTES + HIT_OUT_BYTES + n_nodes * NODE_BYTES + n_prims * ITEM_BYTES
+            tn_ms, tn_launches = kt["trace_nearest"]
+            my_rays_n = float(st["rays_camera"] + st["rays_extension"] + st["rays_mis"])
+            peak, peak_src = measured_peak()
+            achieved = my_rays_n * b_ray / (tn_ms * 1e-3) / 1e9 if tn_ms > 0 else 0.0
+            tr = committed_traffic()
+            roofline = {"kernel": "kTracePersistent<nearest> (bling_b200/csrc/trace_kernels.cuh)", "bound": "hbm",
+                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                        "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                        "bytes_per_ray": b_ray, "nodes_per_ray": n_nodes, "prims_per_ray": n_prims,
+                        "rays_per_launch": my_rays_n / max(1, tn_launches), "launches": tn_launches,
+                        "ms_per_launch": tn_ms / max(1, tn_launches),
+                        "share_of_step": tn_ms / ms if ms > 0 else None,
+                        "mrays_per_s_in_kernel": my_rays_n / (tn_ms * 1e-3) / 1e6 if tn_ms > 0 else None,
+                        "kernel_ms_by_class": {k: round(v[0], 3) for k, v in kt.items()},
+                        "launches_by_class": {k: v[1] for k, v in kt.items()}}
+
+        # ---- e2e: the renderer seam with the film landing in HOST memory every step
+        e2e = None; e2e_trace = None
+        if not a.no_e2e:
+            film_bytes = fn * 4
+            host = torch.empty(fn, dtype=torch.float32).pin_memory()
+            barrier(); ctx.reset_stats()
+            t0 = time.perf_counter()
+            for i in range(a.steps):
+                step(a.warmup + a.steps + i)
+                host.copy_(film_sum if world > 1 else film_t, non_blocking=True)
+                stream.synchronize()                              # PassDone: the host owns the image now
+            barrier()
+            dt = time.perf_counter() - t0
+            se = ctx.stats()
+            v = torch.tensor([dt, float(se["samples"])], dtype=torch.float64, device="cuda")
+            if world > 1:
+                m2 = v.clone(); dist.all_reduce(m2, op=dist.ReduceOp.MAX)
+                s3 = v.clone(); dist.all_reduce(s3, op=dist.ReduceOp.SUM)
+                dt, es = float(m2[0]), float(s3[1])
+            else:
+                es = float(v[1])
+            e2e = {"value": es / dt / 1e6, "unit": UNIT, "h2d_bytes_per_step": 24, "d2h_bytes_per_step": int(film_bytes),
+                   "what": "blingcu_render_slice + film to pinned HOST memory per step (the PassDone image of Rendering.hs:136); "
+                           "per-step host inputs are the (pass, seed, slice) scalars; the scene is uploaded once like mkScene",
+                   "scene_upload_s": t_upload, "scene_h2d_bytes": scene_bytes, "scene_generate_s": t_scene}
+            if rank == 0:
+                # explicit ray batches through the C ABI on HOST buffers (parity API)
+                from tests.conftest import camera_rays
+                nr = 4_000_000
+                rays = camera_rays(None, scene, nr, 11)
+                ctx.trace_nearest(rays[:1000])
+                t0 = time.perf_counter()
+                reps = 3
+                for _ in range(reps):
+                    ctx.trace_nearest(rays)
+                dt2 = (time.perf_counter() - t0) / reps
+                e2e_trace = {"value": nr / dt2 / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": nr * 32, "d2h_bytes_per_step": nr * 16,
+                             "what": "blingcu_trace_nearest, 4M primary-like rays, host ray buffer in / host hit buffer out"}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        cb = cpu_reference_run(scene, a, steps=3, warmup=1)
+        cpu_baseline = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "mrays_per_s")}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "mrays_per_s": mrays, "n_gpus": n_gpus, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, n_gpus),
+                "clocks": clk, "e2e": e2e, "e2e_trace": e2e_trace, "gpu_launches": int(launches), "roofline": roofline,
+                "cpu_baseline": cpu_baseline,
+                "rays": {"nearest": rays_n, "shadow": rays_s, "per_sample": (rays_n + rays_s) / max(1.0, samples)},
+                "bvh": {"nodes": st["bvh_nodes"], "leaf_items": st["bvh_leaf_items"]}}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

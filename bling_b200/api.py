@@ -18,7 +18,7 @@ LIB_PATH = _PKG / "libblingcu.so"
 # every symbol include/blingcu.h declares
 SYMBOLS = ["create", "destroy", "last_error", "upload_scene", "trace_nearest", "trace_occluded", "trace_stats",
            "render_pass", "render_slice", "render_samples", "read_film", "clear_film", "film_add_host", "film_device",
-           "synchronize", "get_stats", "reset_stats", "set_option", "sample_extent", "kernel_times"]
+           "synchronize", "set_stream", "get_stats", "reset_stats", "set_option", "sample_extent", "kernel_times"]
 
 
 class BlingCuError(RuntimeError):
@@ -50,6 +50,7 @@ def load_library(path=LIB_PATH, prefix="blingcu"):
     f("film_add_host").argtypes = [P, P]
     f("film_device").argtypes = [P, C.POINTER(P), C.POINTER(C.c_size_t)]
     f("synchronize").argtypes = [P]
+    f("set_stream").argtypes = [P, P]
     f("get_stats").argtypes = [P, C.POINTER(IR.Stats)]
     f("reset_stats").argtypes = [P]
     f("set_option").argtypes = [P, C.c_char_p, C.c_double]
@@ -156,6 +157,10 @@ class Context:
         return p.value, n.value
 
     def synchronize(self): self._chk(self._f("synchronize")(self._h))
+
+    def set_stream(self, cuda_stream: int | None):
+        """run on a caller-owned CUDA stream (raw cudaStream_t as int, e.g. torch.cuda.current_stream().cuda_stream)."""
+        self._chk(self._f("set_stream")(self._h, C.c_void_p(cuda_stream or 0)))
 
     def stats(self) -> dict:
         s = IR.Stats(); self._chk(self._f("get_stats")(self._h, C.byref(s))); return s.as_dict()

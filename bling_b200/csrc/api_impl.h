@@ -79,6 +79,7 @@ static thread_local std::string g_createError;
       *dptr = c->p.film; *nf = (size_t)c->p.hs.W * c->p.hs.H * 4;                                                                \
       return 0;                                                                                                                  \
    }                                                                                                                             \
+   int PFX##_set_stream(PFX##_ctx_t *c, void *stream) { return c ? c->p.be.guard(c->p.err, [&]() { c->p.be.setStream(stream); return 0; }) : BLINGCU_EINVAL; } \
    int PFX##_synchronize(PFX##_ctx_t *c) { return c ? c->p.be.guard(c->p.err, [&]() { c->p.be.sync(); return 0; }) : BLINGCU_EINVAL; } \
    int PFX##_get_stats(PFX##_ctx_t *c, blingcu_stats *o) { return (c && o) ? c->p.be.guard(c->p.err, [&]() { return c->p.getStats(o); }) : BLINGCU_EINVAL; } \
    int PFX##_reset_stats(PFX##_ctx_t *c) { if (!c) return BLINGCU_EINVAL; return c->p.be.guard(c->p.err, [&]() { c->p.resetStats(); return 0; }); } \

@@ -30,10 +30,9 @@ struct HitRec { float t; int prim; float b1, b2; };
 #define BL_STACK 64
 
 HD bool leafItemNearest(const Bvh &bvh, int item, Ray &r, HitRec &h) {
-   F4 q0 = ld4(bvh.items + 3 * item), q1 = ld4(bvh.items + 3 * item + 1);
+   F4 q0 = ld4(bvh.items + 3 * item), q1 = ld4(bvh.items + 3 * item + 1), q2 = ld4(bvh.items + 3 * item + 2);   // one 48-byte record, three independent LDG.128
    int tag = f2i(q1.w);
    if (tag == 0) {
-      F4 q2 = ld4(bvh.items + 3 * item + 2);
       float t, b1, b2;
       if (!triHit(mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), r, t, b1, b2)) return false;
       r.tmax = t; h.t = t; h.prim = f2i(q0.w); h.b1 = b1; h.b2 = b2;
@@ -46,10 +45,9 @@ HD bool leafItemNearest(const Bvh &bvh, int item, Ray &r, HitRec &h) {
    return true;
 }
 HD bool leafItemAny(const Bvh &bvh, int item, const Ray &r) {
-   F4 q0 = ld4(bvh.items + 3 * item), q1 = ld4(bvh.items + 3 * item + 1);
+   F4 q0 = ld4(bvh.items + 3 * item), q1 = ld4(bvh.items + 3 * item + 1), q2 = ld4(bvh.items + 3 * item + 2);   // one 48-byte record, three independent LDG.128
    int tag = f2i(q1.w);
    if (tag == 0) {
-      F4 q2 = ld4(bvh.items + 3 * item + 2);
       float t, b1, b2;
       return triHit(mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), mk3(q2.x, q2.y, q2.z), r, t, b1, b2);   // TriangleMesh.hs:140-158 == same predicate
    }

@@ -32,7 +32,8 @@ template <class B> __global__ void __launch_bounds__(128) kRunQueueHeavy(B b, co
 
 struct CudaBackend {
    int device = -1, sms = 148;
-   cudaStream_t stream = nullptr;
+   cudaStream_t stream = nullptr, ownStream = nullptr;
+   bool timerPending = false;
    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
    TraceConfig tcfg;
    // optional per-class kernel timing (option "profile_kernels"): one event pair per launch on the launching stream
@@ -73,12 +74,17 @@ struct CudaBackend {
       if (p.major < 10) { err = "built for sm_100a (B200); found sm_" + std::to_string(p.major * 10 + p.minor); return BLINGCU_ENOGPU; }
       device = dev; sms = p.multiProcessorCount;
       if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ev0) != cudaSuccess || cudaEventCreate(&ev1) != cudaSuccess) { err = "stream/event creation failed"; return BLINGCU_ECUDA; }
-      tcfg.sms = sms;
+      ownStream = stream; tcfg.sms = sms;
       return 0;
    }
+   // run on a caller-owned stream (e.g. torch's current stream, so an NCCL all-reduce of the film orders after the
+   // pass without a host sync); nullptr restores the context's own stream
+   void setStream(void *s) { cudaStreamSynchronize(stream); collect(); stream = s ? (cudaStream_t)s : ownStream; }
    void shutdown() {
       if (device >= 0) cudaSetDevice(device);
-      if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); stream = nullptr; }
+      if (stream) cudaStreamSynchronize(stream);
+      if (ownStream) { cudaStreamDestroy(ownStream); ownStream = nullptr; }
+      stream = nullptr;
       collect(); for (cudaEvent_t e : pool) cudaEventDestroy(e); pool.clear();
       if (ev0) cudaEventDestroy(ev0);
       if (ev1) cudaEventDestroy(ev1);
@@ -111,8 +117,10 @@ struct CudaBackend {
    void download(void *d, const void *s, size_t n) { CU(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, stream)); CU(cudaStreamSynchronize(stream)); }
    void zero(void *d, size_t n) { CU(cudaMemsetAsync(d, 0, n, stream)); }
    void sync() { CU(cudaStreamSynchronize(stream)); }
+   // device time of a render call: events recorded on the launching stream, read back lazily (no host sync per pass)
    int timerStart() { CU(cudaEventRecord(ev0, stream)); return 0; }
-   double timerStop(int) { CU(cudaEventRecord(ev1, stream)); CU(cudaEventSynchronize(ev1)); float ms = 0; CU(cudaEventElapsedTime(&ms, ev0, ev1)); return ms; }
+   double timerStop(int) { CU(cudaEventRecord(ev1, stream)); timerPending = true; return -1.0; }
+   double timerRead(double last) { if (!timerPending) return last; timerPending = false; CU(cudaEventSynchronize(ev1)); float ms = 0; CU(cudaEventElapsedTime(&ms, ev0, ev1)); return ms; }
 
    uint32_t gridFor(uint32_t n, uint32_t block, uint32_t perSm) const {
       uint32_t need = (n + block - 1) / block;

@@ -330,7 +330,7 @@ struct Pipeline {
          out->rays_shadow = s[S_SHADOW]; out->dropped_samples = s[S_DROPPED];
       }
       be.traversalTotals(out->nodes_traversed, out->intersections, out->rays_counted);
-      out->kernel_launches = launches; out->bvh_nodes = nNodes; out->bvh_leaf_items = nItems; out->last_pass_ms = lastMs;
+      out->kernel_launches = launches; out->bvh_nodes = nNodes; out->bvh_leaf_items = nItems; lastMs = be.timerRead(lastMs); out->last_pass_ms = lastMs;
       return 0;
    }
    void resetStats() { if (ps.stats) be.zero(ps.stats, sizeof(unsigned long long) * N_STATS); launches = 0; be.resetProfile(); }

@@ -74,10 +74,16 @@ __global__ void __launch_bounds__(128) kTraceNearestCount(const uint32_t *__rest
 }
 
 // ---------------------------------------------------------------------------------------------- variant 1
+// Persistent warps with MAJORITY-VOTE stepping. The first version of this kernel let every lane run its own
+// data-dependent while loop; ncu (profiles/r01_trace_v1_divergent.md) showed 3.5 of 32 threads active per issued
+// instruction. Here the warp stays converged: every trip the lanes vote (ballot) whether more of them stand at an
+// inner node or inside a leaf, and the whole warp executes ONLY that step, predicated per lane. At least half of
+// the live lanes are active in every trip; idle lanes are refilled from the global queue (warp-aggregated atomic)
+// once enough of them have retired.
 #define TR_THREADS 128
 #define TR_SSTACK 24      // shared-memory stack levels per thread
 #define TR_LSTACK 40      // local-memory tail (tree depth is bounded by the builder: 32 SAH + 24 median levels)
-#define TR_REFILL 24      // refill when fewer lanes than this are still traversing
+#define TR_REFILL 8       // refill once this many lanes are idle
 
 template <bool ANY>
 __global__ void __launch_bounds__(TR_THREADS) kTracePersistent(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
@@ -85,44 +91,53 @@ __global__ void __launch_bounds__(TR_THREADS) kTracePersistent(const uint32_t *_
                                                               F4 *__restrict__ hit, uint8_t *__restrict__ occl, uint32_t *__restrict__ work) {
    __shared__ int sstack[TR_SSTACK][TR_THREADS];
    int lstack[TR_LSTACK];
+   const unsigned FULL = 0xffffffffu;
    const uint32_t total = cnt ? *cnt : n;
    const Bvh bvh = sc->bvh;
    const unsigned lane = threadIdx.x & 31u;
    const int tid = threadIdx.x;
-   const int EMPTY = 0x7fffffff;    // lane holds no ray
-   int cur = EMPTY; int sp = 0;
+   const int EMPTY = (int)0x80000000;   // lane holds no ray (negative: never mistaken for a node index)
+   const int LEAF = -1;             // lane iterates the items [li, le) of a leaf
+   int cur = EMPTY, sp = 0, li = 0, le = 0;
    uint32_t slot = 0;
    Ray r; V3 idir; HitRec h;
    bool exhausted = false;
    r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.tmin = 0; r.tmax = 0; idir = mk3(0, 0, 0); h.t = 0; h.prim = -1; h.b1 = h.b2 = 0;
-   bool found = false;
+
+   // enter child reference c (node index or encoded leaf)
+#define TR_ENTER(c) do { int c_ = (c); if (c_ >= 0) cur = c_; else { int enc_ = ~c_; li = enc_ >> 4; le = li + (enc_ & 15); cur = LEAF; } } while (0)
+   // ray finished: write the result, free the lane
+#define TR_FINISH(found_) do { if (ANY) occl[slot] = (found_) ? 1 : 0; else { F4 v_; v_.x = h.t; v_.y = h.b1; v_.z = h.b2; v_.w = i2f(h.prim); hit[slot] = v_; } cur = EMPTY; } while (0)
+#define TR_POP() do { if (sp == 0) TR_FINISH(false); else { sp--; int c2_ = (sp < TR_SSTACK) ? sstack[sp][tid] : lstack[sp - TR_SSTACK]; TR_ENTER(c2_); } } while (0)
+
    for (;;) {
-      // ---- refill idle lanes (warp-aggregated fetch from the global work counter)
-      {
-         bool need = (cur == EMPTY) && !exhausted;
-         unsigned m = __ballot_sync(0xffffffffu, need);
-         if (m) {
-            int leader = __ffs(m) - 1;
-            uint32_t base = 0;
-            if ((int)lane == leader) base = atomicAdd(work, (uint32_t)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (need) {
-               uint32_t k = base + __popc(m & ((1u << lane) - 1u));
-               if (k < total) {
-                  slot = q ? q[k] : k;
-                  r = loadRay(O, D, slot);
-                  idir = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-                  h.t = 0; h.prim = -1; h.b1 = 0; h.b2 = 0; found = false;
-                  sp = 0; cur = bvh.root;
-                  if (cur < 0) cur = ~0;   // empty scene: a leaf with zero items
-               } else exhausted = true;
+      // ---- refill idle lanes (warp-uniform decision)
+      unsigned idle = __ballot_sync(FULL, cur == EMPTY);
+      if (!exhausted && __popc(idle) >= TR_REFILL) {
+         uint32_t base = 0;
+         int leader = __ffs(idle) - 1;
+         if ((int)lane == leader) base = atomicAdd(work, (uint32_t)__popc(idle));
+         base = __shfl_sync(FULL, base, leader);
+         if (cur == EMPTY) {
+            uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
+            if (k < total) {
+               slot = q ? q[k] : k;
+               r = loadRay(O, D, slot);
+               idir = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+               h.t = 0; h.prim = -1; h.b1 = 0; h.b2 = 0;
+               sp = 0;
+               if (bvh.root >= 0) cur = bvh.root; else { li = le = 0; cur = LEAF; }   // empty scene: a leaf with zero items
             }
          }
-         if (__all_sync(0xffffffffu, cur == EMPTY)) break;
+         if (base + (uint32_t)__popc(idle) >= total) exhausted = true;   // warp-uniform: the queue is drained
+         idle = __ballot_sync(FULL, cur == EMPTY);
       }
-      // ---- traverse until this lane's ray terminates or the warp runs low on live lanes
-      while (cur != EMPTY) {
-         if (cur >= 0) {
+      if (idle == FULL) { if (exhausted) break; continue; }
+      // ---- vote: node step or leaf step
+      const bool atNode = cur >= 0, atLeaf = cur == LEAF;
+      const unsigned mN = __ballot_sync(FULL, atNode), mL = __ballot_sync(FULL, atLeaf);
+      if (__popc(mN) >= __popc(mL)) {
+         if (atNode) {
             const F4 *np = bvh.nodes + 4 * (size_t)cur;
             F4 n0 = ld4(np), n1 = ld4(np + 1), n2 = ld4(np + 2), n3 = ld4(np + 3);
             float tn0, tn1; bool h0, h1;
@@ -132,30 +147,27 @@ __global__ void __launch_bounds__(TR_THREADS) kTracePersistent(const uint32_t *_
                if (!ANY && tn1 < tn0) { int t = c0; c0 = c1; c1 = t; }
                if (sp < TR_SSTACK) sstack[sp][tid] = c1; else if (sp < TR_SSTACK + TR_LSTACK) lstack[sp - TR_SSTACK] = c1;
                sp++;
-               cur = c0;
-               continue;
-            }
-            if (h0) { cur = c0; continue; }
-            if (h1) { cur = c1; continue; }
-         } else {
-            int enc = ~cur; int first = enc >> 4, cntl = enc & 15;
-            for (int i = 0; i < cntl; ++i) {
-               if (ANY) { if (leafItemAny(bvh, first + i, r)) { found = true; break; } }
-               else leafItemNearest(bvh, first + i, r, h);
-            }
-            if (ANY && found) sp = 0;
+               TR_ENTER(c0);
+            } else if (h0) TR_ENTER(c0);
+            else if (h1) TR_ENTER(c1);
+            else TR_POP();
          }
-         if (sp == 0) {   // ray finished
-            if (ANY) occl[slot] = found ? 1 : 0;
-            else { F4 v; v.x = h.t; v.y = h.b1; v.z = h.b2; v.w = i2f(h.prim); hit[slot] = v; }
-            cur = EMPTY;
-            break;
+      } else {
+         if (atLeaf) {
+            bool found = false;
+            if (li < le) {
+               if (ANY) found = leafItemAny(bvh, li, r);
+               else leafItemNearest(bvh, li, r, h);
+               li++;
+            }
+            if (ANY && found) TR_FINISH(true);
+            else if (li >= le) TR_POP();
          }
-         sp--;
-         cur = (sp < TR_SSTACK) ? sstack[sp][tid] : lstack[sp - TR_SSTACK];
-         if (__popc(__activemask()) < TR_REFILL) break;   // few lanes left: let the warp refill
       }
    }
+#undef TR_ENTER
+#undef TR_FINISH
+#undef TR_POP
 }
 
 static inline void launchTraceNearest(TraceConfig &cfg, cudaStream_t st, const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc,

@@ -249,6 +249,10 @@ int blingcu_clear_film(blingcu_ctx *);
 int blingcu_film_add_host(blingcu_ctx *, const float *wxyz); /* film += host buffer (resume / manual reduce) */
 int blingcu_film_device(blingcu_ctx *, void **dptr, size_t *n_floats); /* for NCCL allreduce by the host */
 int blingcu_synchronize(blingcu_ctx *);
+/* enqueue all further work of this context on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the
+ * stream the host's NCCL all-reduce of the film runs on; NULL restores the context's own stream. Render calls are
+ * asynchronous with respect to the host; read_film / get_stats / synchronize wait. */
+int blingcu_set_stream(blingcu_ctx *, void *cuda_stream);
 
 int blingcu_get_stats(blingcu_ctx *, blingcu_stats *out);
 int blingcu_reset_stats(blingcu_ctx *);

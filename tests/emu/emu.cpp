@@ -17,6 +17,8 @@ struct EmuBackend {
    void download(void *d, const void *s, size_t n) { std::memcpy(d, s, n); }
    void zero(void *d, size_t n) { std::memset(d, 0, n); }
    void sync() {}
+   void setStream(void *) {}
+   double timerRead(double last) { return last; }
    void tag(int) {}
    void kernelTimes(double *ms, uint64_t *l, int n) { for (int i = 0; i < n; ++i) { ms[i] = 0; l[i] = 0; } }
    void traversalTotals(uint64_t &a, uint64_t &b, uint64_t &c) { a = b = c = 0; }
