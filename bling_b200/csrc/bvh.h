@@ -5,10 +5,12 @@
 // `near` shrinks rayMax), so any conservative accelerator returns the same (t, prim) as long as
 // the primitive tests are the same arithmetic. The library builds its own BVH (bvh_build.cpp).
 //
-// Node = 64 B = 4 x 16-byte loads, holding BOTH children's boxes (one fetch decides both):
-//   n0 = c0.lo.x c0.hi.x c0.lo.y c0.hi.y     n1 = c1.lo.x c1.hi.x c1.lo.y c1.hi.y
-//   n2 = c0.lo.z c0.hi.z c1.lo.z c1.hi.z     n3 = child0 child1 (int bits) - -
-// child >= 0: node index. child < 0: leaf, ~child = (first_item << 4) | count.
+// Node = 128 B (one L1/L2 line) = a 4-wide BVH node, one 32-byte record per child:
+//   child k at F4[2k], F4[2k+1] = (lo.x lo.y lo.z hi.x) (hi.y hi.z ref -)
+// so the four lanes of a quad each fetch ONE child with one 32-byte load and the quad's four loads coalesce into a
+// single 128-byte L1 wavefront (trace_kernels.cuh). ref >= 0: node index. ref < 0: leaf, ~ref = (first_item << 4) |
+// count. Unused child slots carry the box (+inf, -inf), which no ray hits. The builder (bvh_build.cpp) builds a
+// binned-SAH binary tree and collapses it into 4-wide nodes by repeatedly opening the child with the largest area.
 // Leaf item = 48 B = 3 x 16-byte loads:
 //   triangle: (p1.xyz, prim_id) (e1.xyz, 0) (e2.xyz, -)       shape: (-, -, -, prim_id) (-, -, -, 1 + shape index) -
 // Boxes are inflated by the builder, so the slab test needs no epsilon (see bvh_build.cpp).
@@ -23,11 +25,11 @@ struct Bvh {
    const blingcu_shape *shapes;
    int root;          // node index (there is always at least one node unless the scene is empty: root = -1 and n_nodes = 0)
    int n_nodes;
+   int max_stack;     // worst-case traversal stack entries (from the builder)
 };
 
 struct HitRec { float t; int prim; float b1, b2; };
 
-#define BL_STACK 64
 
 HD bool leafItemNearest(const Bvh &bvh, int item, Ray &r, HitRec &h) {
    F4 q0 = ld4(bvh.items + 3 * item), q1 = ld4(bvh.items + 3 * item + 1), q2 = ld4(bvh.items + 3 * item + 2);   // one 48-byte record, three independent LDG.128
@@ -55,45 +57,70 @@ HD bool leafItemAny(const Bvh &bvh, int item, const Ray &r) {
    return shapeIntersects(s, transRay(s.w2o, r));
 }
 
-// slab test of both children of one node against [r.tmin, r.tmax]
-HD void nodeTest(const F4 &n0, const F4 &n1, const F4 &n2, const Ray &r, V3 idir, float &tn0, float &tn1, bool &h0, bool &h1) {
-   float c0lx = (n0.x - r.o.x) * idir.x, c0hx = (n0.y - r.o.x) * idir.x;
-   float c0ly = (n0.z - r.o.y) * idir.y, c0hy = (n0.w - r.o.y) * idir.y;
-   float c0lz = (n2.x - r.o.z) * idir.z, c0hz = (n2.y - r.o.z) * idir.z;
-   float c1lx = (n1.x - r.o.x) * idir.x, c1hx = (n1.y - r.o.x) * idir.x;
-   float c1ly = (n1.z - r.o.y) * idir.y, c1hy = (n1.w - r.o.y) * idir.y;
-   float c1lz = (n2.z - r.o.z) * idir.z, c1hz = (n2.w - r.o.z) * idir.z;
-   tn0 = fmaxf(fmaxf(fminf(c0lx, c0hx), fminf(c0ly, c0hy)), fmaxf(fminf(c0lz, c0hz), r.tmin));
-   float tf0 = fminf(fminf(fmaxf(c0lx, c0hx), fmaxf(c0ly, c0hy)), fminf(fmaxf(c0lz, c0hz), r.tmax));
-   tn1 = fmaxf(fmaxf(fminf(c1lx, c1hx), fminf(c1ly, c1hy)), fmaxf(fminf(c1lz, c1hz), r.tmin));
-   float tf1 = fminf(fminf(fmaxf(c1lx, c1hx), fmaxf(c1ly, c1hy)), fminf(fmaxf(c1lz, c1hz), r.tmax));
-   h0 = tn0 <= tf0; h1 = tn1 <= tf1;
+#define BL_NODE_F4 8     // F4 per node (128 B)
+#define BL_STACK 192     // worst case 3 pushes per level of a 56-level binary tree; real scenes use < 48
+
+#if defined(__CUDA_ARCH__)
+#define BL_FMA(a, b, c) __fmaf_rn(a, b, c)
+#else
+#define BL_FMA(a, b, c) fmaf(a, b, c)
+#endif
+HD float c4(const F4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
+struct RayPre { V3 idir, ood; };   // 1/d and o/d: plane distance = plane * idir - ood (one FMA)
+// |1/d| is clamped to 1e18 so that plane * idir - ood never evaluates inf - inf: an axis-parallel ray then sees
+// (-huge, +huge) when its origin is inside the slab and two same-signed huge values (a miss) when it is outside.
+HD float safeInv(float d) { return fminf(fmaxf(1.0f / d, -1e18f), 1e18f); }
+HD RayPre rayPre(const Ray &r) { RayPre p; p.idir = mk3(safeInv(r.d.x), safeInv(r.d.y), safeInv(r.d.z)); p.ood = p.idir * r.o; return p; }
+
+// slab test of ONE child box against [r.tmin, r.tmax]. Returns the child's sort key:
+// hit -> (bits(tnear) & ~3) | slot  (tnear >= tmin >= 0, so unsigned order == distance order), miss -> 0xffffffff.
+// fminf/fmaxf drop NaNs (0 * huge cannot occur after safeInv; inf box bounds of unused slots give inf/-inf), which
+// keeps the test conservative.
+HD uint32_t childKey(const F4 &a, const F4 &b, const Ray &r, const RayPre &p, uint32_t slot) {
+   float ax = BL_FMA(a.x, p.idir.x, -p.ood.x), bx = BL_FMA(a.w, p.idir.x, -p.ood.x);
+   float ay = BL_FMA(a.y, p.idir.y, -p.ood.y), by = BL_FMA(b.x, p.idir.y, -p.ood.y);
+   float az = BL_FMA(a.z, p.idir.z, -p.ood.z), bz = BL_FMA(b.y, p.idir.z, -p.ood.z);
+   float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), r.tmin));
+   float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), r.tmax));
+   return (tn <= tf) ? (((uint32_t)f2i(tn) & ~3u) | slot) : 0xffffffffu;
 }
+// all four children of a node (single-lane traversal: CPU emulator, instrumented and reference kernels)
+HD void node4Keys(const F4 *np, const Ray &r, const RayPre &p, uint32_t key[4], int ref[4]) {
+   BL_UNROLL for (int k = 0; k < 4; ++k) {
+      F4 a = ld4(np + 2 * k), b = ld4(np + 2 * k + 1);
+      key[k] = childKey(a, b, r, p, (uint32_t)k); ref[k] = f2i(b.z);
+   }
+}
+HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
+HD uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
+HD void sort4(uint32_t k[4]) {   // 5-comparator network, ascending
+   uint32_t a = umin32(k[0], k[1]), b = umax32(k[0], k[1]), c = umin32(k[2], k[3]), d = umax32(k[2], k[3]);
+   uint32_t lo = umin32(a, c), m1 = umax32(a, c), m2 = umin32(b, d), hi = umax32(b, d);
+   k[0] = lo; k[1] = umin32(m1, m2); k[2] = umax32(m1, m2); k[3] = hi;
+}
+HD int pick4(const int c[4], uint32_t slot) { return slot == 0 ? c[0] : (slot == 1 ? c[1] : (slot == 2 ? c[2] : c[3])); }
 
 // nearest hit (Primitive.intersect). STATS counts node fetches / primitive tests like dbgTraverse (KdTree.hs:260-281).
+// Children are entered nearest-first; every variant of the traversal kernel follows this same order.
 template <bool STATS>
 HD HitRec traceNearest(const Bvh &bvh, Ray r, uint32_t *nNodes, uint32_t *nPrims) {
    HitRec h; h.t = 0; h.prim = -1; h.b1 = 0; h.b2 = 0;
    if (bvh.root < 0) return h;
-   V3 idir = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+   RayPre pre = rayPre(r);
    int stack[BL_STACK]; int sp = 0;
    int cur = bvh.root;
    for (;;) {
       if (cur >= 0) {
-         const F4 *np = bvh.nodes + 4 * (size_t)cur;
-         F4 n0 = ld4(np), n1 = ld4(np + 1), n2 = ld4(np + 2), n3 = ld4(np + 3);
+         const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
          if (STATS) (*nNodes)++;
-         float tn0, tn1; bool h0, h1;
-         nodeTest(n0, n1, n2, r, idir, tn0, tn1, h0, h1);
-         int c0 = f2i(n3.x), c1 = f2i(n3.y);
-         if (h0 && h1) {
-            if (tn1 < tn0) { int t = c0; c0 = c1; c1 = t; }
-            if (sp < BL_STACK) stack[sp++] = c1;
-            cur = c0;
+         uint32_t key[4]; int n6[4];
+         node4Keys(np, r, pre, key, n6);
+         sort4(key);
+         if (key[0] != 0xffffffffu) {
+            for (int j = 3; j >= 1; --j) if (key[j] != 0xffffffffu && sp < BL_STACK) stack[sp++] = pick4(n6, key[j] & 3u);
+            cur = pick4(n6, key[0] & 3u);
             continue;
          }
-         if (h0) { cur = c0; continue; }
-         if (h1) { cur = c1; continue; }
       } else {
          int enc = ~cur; int first = enc >> 4, cnt = enc & 15;
          for (int i = 0; i < cnt; ++i) { if (STATS) (*nPrims)++; leafItemNearest(bvh, first + i, r, h); }
@@ -107,19 +134,17 @@ HD HitRec traceNearest(const Bvh &bvh, Ray r, uint32_t *nNodes, uint32_t *nPrims
 // any hit (Primitive.intersects)
 HD bool traceAny(const Bvh &bvh, const Ray &r) {
    if (bvh.root < 0) return false;
-   V3 idir = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+   RayPre pre = rayPre(r);
    int stack[BL_STACK]; int sp = 0;
    int cur = bvh.root;
    for (;;) {
       if (cur >= 0) {
-         const F4 *np = bvh.nodes + 4 * (size_t)cur;
-         F4 n0 = ld4(np), n1 = ld4(np + 1), n2 = ld4(np + 2), n3 = ld4(np + 3);
-         float tn0, tn1; bool h0, h1;
-         nodeTest(n0, n1, n2, r, idir, tn0, tn1, h0, h1);
-         int c0 = f2i(n3.x), c1 = f2i(n3.y);
-         if (h0 && h1) { if (sp < BL_STACK) stack[sp++] = c1; cur = c0; continue; }
-         if (h0) { cur = c0; continue; }
-         if (h1) { cur = c1; continue; }
+         const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
+         uint32_t key[4]; int n6[4];
+         node4Keys(np, r, pre, key, n6);
+         int next = 0; bool have = false;
+         for (int k = 0; k < 4; ++k) if (key[k] != 0xffffffffu) { int c = pick4(n6, (uint32_t)k); if (!have) { next = c; have = true; } else if (sp < BL_STACK) stack[sp++] = c; }
+         if (have) { cur = next; continue; }
       } else {
          int enc = ~cur; int first = enc >> 4, cnt = enc & 15;
          for (int i = 0; i < cnt; ++i) if (leafItemAny(bvh, first + i, r)) return true;
@@ -139,10 +164,11 @@ struct BvhBuildInput {
    int threads;
 };
 struct BvhBuildOutput {
-   F4 *nodes;            // malloc'ed, 4*n_nodes
+   F4 *nodes;            // malloc'ed, BL_NODE_F4*n_nodes (4-wide nodes)
    uint32_t *order;      // malloc'ed, n: order[k] = input item stored at leaf position k
    int n_nodes;
    int root;
+   int max_stack;        // worst-case number of stack entries a traversal of this tree can hold
    float scene_lo[3], scene_hi[3];
 };
 int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out);

@@ -1,4 +1,4 @@
-// bvh_build.cpp -- host-side binned-SAH BVH2 builder (setup, not per-ray). Plays the role of
+// bvh_build.cpp -- host-side binned-SAH builder (binary tree, then collapsed to 4-wide nodes; setup, not per-ray). Plays the role of
 // mkKdTree/buildTree (KdTree.hs:107-203) for the GPU path; the tree shape is free to differ because the
 // traversal result (globally nearest hit) does not depend on it.
 //
@@ -151,9 +151,69 @@ int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
       np[3] = F4{i2f(root), i2f(~0), 0, 0};
       root = idx;
    }
-   out.nodes = B.nodes;
-   out.n_nodes = B.nextNode.load();
-   out.root = root;
+   // ---- collapse the binary tree into 4-wide nodes (bvh.h layout): open the inner child with the largest area
+   // until the node has four children; emitted in depth-first order so a subtree is contiguous in memory
+   int n2 = B.nextNode.load();
+   F4 *n4 = (F4 *)std::malloc(sizeof(F4) * BL_NODE_F4 * (size_t)(n2 + 1));
+   int next4 = 0;
+   struct Child { Box box; int ref; };
+   auto childrenOf = [&](int idx, Child &l, Child &r) {
+      const F4 *np = B.nodes + 4 * (size_t)idx;
+      l.box.lo[0] = np[0].x; l.box.hi[0] = np[0].y; l.box.lo[1] = np[0].z; l.box.hi[1] = np[0].w; l.box.lo[2] = np[2].x; l.box.hi[2] = np[2].y;
+      r.box.lo[0] = np[1].x; r.box.hi[0] = np[1].y; r.box.lo[1] = np[1].z; r.box.hi[1] = np[1].w; r.box.lo[2] = np[2].z; r.box.hi[2] = np[2].w;
+      l.ref = f2i(np[3].x); r.ref = f2i(np[3].y);
+   };
+   struct Work { int n2idx; int n4idx; };
+   std::vector<Work> work;
+   int root4 = next4++;
+   work.push_back(Work{root, root4});
+   while (!work.empty()) {
+      Work w = work.back(); work.pop_back();
+      Child c[4]; int nc = 2;
+      childrenOf(w.n2idx, c[0], c[1]);
+      while (nc < 4) {
+         int best = -1; float bestArea = -1;
+         for (int k = 0; k < nc; ++k) if (c[k].ref >= 0 && c[k].box.area() > bestArea) { bestArea = c[k].box.area(); best = k; }
+         if (best < 0) break;
+         Child l, r; childrenOf(c[best].ref, l, r);
+         c[best] = l; c[nc++] = r;
+      }
+      F4 *np = n4 + BL_NODE_F4 * (size_t)w.n4idx;
+      int refs[4];
+      for (int k = 0; k < 4; ++k) {
+         bool used = k < nc && !(c[k].ref < 0 && ((~c[k].ref) & 15) == 0);   // drop empty leaves
+         refs[k] = used ? c[k].ref : ~0;
+         if (!used) { c[k].box.reset(); }
+      }
+      // inner children get their 4-wide index now: siblings are contiguous in memory
+      for (int k = nc - 1; k >= 0; --k) if (k < nc && refs[k] >= 0) { int id = next4++; work.push_back(Work{refs[k], id}); refs[k] = id; }
+      for (int k = 0; k < 4; ++k) {
+         const Box &bx = c[k].box;
+         np[2 * k] = F4{bx.lo[0], bx.lo[1], bx.lo[2], bx.hi[0]};
+         np[2 * k + 1] = F4{bx.hi[1], bx.hi[2], i2f(refs[k]), 0};
+      }
+   }
+   // worst-case traversal stack (entries) of the push-all-then-pop scheme: children indices are always larger than
+   // the parent's, so one reverse sweep suffices
+   {
+      std::vector<int> cap((size_t)next4, 0);
+      for (int i = next4 - 1; i >= 0; --i) {
+         const F4 *np = n4 + BL_NODE_F4 * (size_t)i;
+         int nc = 0, deepest = 0;
+         for (int k = 0; k < 4; ++k) {
+            int ref = f2i(np[2 * k + 1].z);
+            if (ref == ~0) continue;
+            nc++;
+            if (ref >= 0) deepest = std::max(deepest, cap[(size_t)ref]);
+         }
+         cap[(size_t)i] = std::max(nc, nc - 1 + deepest);
+      }
+      out.max_stack = cap[(size_t)root4];
+   }
+   std::free(B.nodes);
+   out.nodes = n4;
+   out.n_nodes = next4;
+   out.root = root4;
    out.order = (uint32_t *)std::malloc(sizeof(uint32_t) * in.n);
    for (size_t i = 0; i < in.n; ++i) out.order[i] = B.items[i].id;
    return 0;

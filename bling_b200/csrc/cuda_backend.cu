@@ -111,6 +111,7 @@ struct CudaBackend {
       if (k == "trace_blocks_per_sm") { tcfg.blocksPerSm = (int)v; return true; }
       return false;
    }
+   void setMaxStack(int m) { tcfg.maxStack = m; }
    void *alloc(size_t n) { void *p = nullptr; CU(cudaMalloc(&p, n ? n : 1)); return p; }
    void free(void *p) { if (p) cudaFree(p); }
    void upload(void *d, const void *s, size_t n) { CU(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream)); CU(cudaStreamSynchronize(stream)); }

@@ -137,10 +137,11 @@ struct Pipeline {
          }
       }
       std::memset(&hs, 0, sizeof(hs));
-      hs.bvh.nodes = up<F4>(bo.nodes, 4 * (size_t)bo.n_nodes);
+      hs.bvh.nodes = up<F4>(bo.nodes, BL_NODE_F4 * (size_t)bo.n_nodes);
       hs.bvh.items = up<F4>(items.data(), items.size());
-      hs.bvh.root = bo.root; hs.bvh.n_nodes = bo.n_nodes;
-      nNodes = (uint64_t)bo.n_nodes; nItems = nprim;
+      hs.bvh.root = bo.root; hs.bvh.n_nodes = bo.n_nodes; hs.bvh.max_stack = bo.max_stack;
+      if (bo.max_stack > BL_STACK) { std::free(bo.nodes); std::free(bo.order); return fail(BLINGCU_EINVAL, "acceleration structure too deep for the traversal stack"); }
+      nNodes = (uint64_t)bo.n_nodes; nItems = nprim; be.setMaxStack(bo.max_stack);
       std::free(bo.nodes); std::free(bo.order);
       // ---- shading geometry
       {

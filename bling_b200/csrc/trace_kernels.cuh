@@ -2,11 +2,7 @@
 // Replaces the per-ray recursion of KdTree.hs:210-246 (a4, a5 in SURVEY.md §8a).
 //
 // variant 0  one ray per thread, grid-stride, traversal stack in local memory (the reference point)
-// variant 1  persistent threads: grid = SMs x blocksPerSm, rays pulled from a global work counter with a
-//            warp-aggregated atomic; lanes that finish refill themselves once the warp's live-lane count
-//            drops below a threshold (ballot compaction); traversal stack lives in shared memory
-//            ([level][thread], conflict-free) with a local-memory tail; nodes are fetched as 4 x LDG.128,
-//            leaf items as 3 x LDG.128 through the read-only path.
+// variant 1  persistent warps, one ray per QUAD, majority-vote stepping (kTraceQuad below; the product path)
 // B200 has no RT cores and traversal is not a contraction: no tensor cores here. The bound is L2/HBM latency
 // and bandwidth on the node/triangle fetches (DESIGN.md "Roofline").
 #pragma once
@@ -18,7 +14,8 @@ namespace bl {
 struct TraceConfig {
    int sms = 148;
    int variant = 1;
-   int blocksPerSm = 8;
+   int blocksPerSm = 10;
+   int maxStack = 64;                 // worst-case stack entries of the uploaded tree (Bvh::max_stack)
    uint32_t *workCounter = nullptr;   // device, one uint32 per launch slot
    bool countStats = false;           // option "traversal_stats": nearest-hit launches count node fetches / primitive tests
    unsigned long long *travCounters = nullptr;   // device: nodes, prims, rays
@@ -74,122 +71,146 @@ __global__ void __launch_bounds__(128) kTraceNearestCount(const uint32_t *__rest
 }
 
 // ---------------------------------------------------------------------------------------------- variant 1
-// Persistent warps with MAJORITY-VOTE stepping. The first version of this kernel let every lane run its own
-// data-dependent while loop; ncu (profiles/r01_trace_v1_divergent.md) showed 3.5 of 32 threads active per issued
-// instruction. Here the warp stays converged: every trip the lanes vote (ballot) whether more of them stand at an
-// inner node or inside a leaf, and the whole warp executes ONLY that step, predicated per lane. At least half of
-// the live lanes are active in every trip; idle lanes are refilled from the global queue (warp-aggregated atomic)
-// once enough of them have retired.
+// Persistent warps, ONE RAY PER QUAD (4 lanes), majority-vote stepping.
+//
+// History (profiles/): v1 let every lane run its own while loop -> 3.5 of 32 threads active per instruction. v2 kept
+// the warp converged by voting between "node step" and "leaf step" -> 2.1x, but with one ray per lane every node
+// fetch costs one L1 wavefront per lane per 16-byte load (7 LDG.128 x lanes): ncu showed the LSU data pipe at 81 %
+// (l1tex__data_pipe_lsu_wavefronts) with DRAM at 12 %. Here the four lanes of a quad own one ray and each lane
+// tests ONE child of the 4-wide node: the quad's four 32-byte loads fall into one 128-byte line = one wavefront per
+// node visit, the box test costs a quarter of the instructions per lane, and leaf items are tested four at a time.
+//   - the quad's traversal stack lives in shared memory ([level][quad], sized from the builder's worst case);
+//     a node step pushes every hit child, nearest on top (rank by three quad shuffles of the sort key), then pops;
+//   - every trip the warp votes (ballot) whether more quads stand at a node or at a leaf and executes only that
+//     step; idle quads refill from the global queue with a warp-aggregated atomic once enough quads have retired.
 #define TR_THREADS 128
-#define TR_SSTACK 24      // shared-memory stack levels per thread
-#define TR_LSTACK 40      // local-memory tail (tree depth is bounded by the builder: 32 SAH + 24 median levels)
-#define TR_REFILL 8       // refill once this many lanes are idle
+#define TR_QUADS (TR_THREADS / 4)
+#define TR_REFILL_Q 2     // refill once this many quads of the warp are idle
+
+__device__ __forceinline__ void ld8(const F4 *p, F4 &a, F4 &b) {   // one 32-byte load (LDG.E.256 on sm_100)
+   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
 
 template <bool ANY>
-__global__ void __launch_bounds__(TR_THREADS) kTracePersistent(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
-                                                              const DScene *__restrict__ sc, const F4 *__restrict__ O, const F4 *__restrict__ D,
-                                                              F4 *__restrict__ hit, uint8_t *__restrict__ occl, uint32_t *__restrict__ work) {
-   __shared__ int sstack[TR_SSTACK][TR_THREADS];
-   int lstack[TR_LSTACK];
+__global__ void __launch_bounds__(TR_THREADS, 10) kTraceQuad(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
+                                                           const DScene *__restrict__ sc, const F4 *__restrict__ O, const F4 *__restrict__ D,
+                                                           F4 *__restrict__ hit, uint8_t *__restrict__ occl, uint32_t *__restrict__ work) {
+   extern __shared__ int qstack[];            // [level][TR_QUADS]
    const unsigned FULL = 0xffffffffu;
    const uint32_t total = cnt ? *cnt : n;
    const Bvh bvh = sc->bvh;
    const unsigned lane = threadIdx.x & 31u;
-   const int tid = threadIdx.x;
-   const int EMPTY = (int)0x80000000;   // lane holds no ray (negative: never mistaken for a node index)
-   const int LEAF = -1;             // lane iterates the items [li, le) of a leaf
-   int cur = EMPTY, sp = 0, li = 0, le = 0;
+   const unsigned sub = lane & 3u;            // which child / leaf item this lane tests
+   const unsigned qshift = lane & ~3u;        // first lane of my quad
+   const unsigned qmask = 0xfu << qshift;
+   int *const myStack = qstack + (threadIdx.x >> 2);
+   const int EMPTY = (int)0x80000000;         // quad holds no ray
+   int cur = EMPTY, sp = 0;
    uint32_t slot = 0;
-   Ray r; V3 idir; HitRec h;
+   Ray r; RayPre pre; int hPrim = -1; float hB1 = 0, hB2 = 0;
    bool exhausted = false;
-   r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.tmin = 0; r.tmax = 0; idir = mk3(0, 0, 0); h.t = 0; h.prim = -1; h.b1 = h.b2 = 0;
+   r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.tmin = 0; r.tmax = 0; pre.idir = mk3(0, 0, 0); pre.ood = mk3(0, 0, 0);
 
-   // enter child reference c (node index or encoded leaf)
-#define TR_ENTER(c) do { int c_ = (c); if (c_ >= 0) cur = c_; else { int enc_ = ~c_; li = enc_ >> 4; le = li + (enc_ & 15); cur = LEAF; } } while (0)
-   // ray finished: write the result, free the lane
-#define TR_FINISH(found_) do { if (ANY) occl[slot] = (found_) ? 1 : 0; else { F4 v_; v_.x = h.t; v_.y = h.b1; v_.z = h.b2; v_.w = i2f(h.prim); hit[slot] = v_; } cur = EMPTY; } while (0)
-#define TR_POP() do { if (sp == 0) TR_FINISH(false); else { sp--; int c2_ = (sp < TR_SSTACK) ? sstack[sp][tid] : lstack[sp - TR_SSTACK]; TR_ENTER(c2_); } } while (0)
+#define TQ_FINISH(found_) do { if (sub == 0) { if (ANY) occl[slot] = (found_) ? 1 : 0; else { F4 v_; v_.x = hPrim >= 0 ? r.tmax : 0.0f; v_.y = hB1; v_.z = hB2; v_.w = i2f(hPrim); hit[slot] = v_; } } cur = EMPTY; } while (0)
+#define TQ_POP() do { if (sp == 0) TQ_FINISH(false); else { sp--; cur = myStack[sp * TR_QUADS]; } } while (0)
 
    for (;;) {
-      // ---- refill idle lanes (warp-uniform decision)
-      unsigned idle = __ballot_sync(FULL, cur == EMPTY);
-      if (!exhausted && __popc(idle) >= TR_REFILL) {
+      // ---- refill idle quads (warp-uniform decision)
+      unsigned idle = __ballot_sync(FULL, cur == EMPTY) & 0x11111111u;   // one bit per quad
+      if (!exhausted && __popc(idle) >= TR_REFILL_Q) {
          uint32_t base = 0;
          int leader = __ffs(idle) - 1;
          if ((int)lane == leader) base = atomicAdd(work, (uint32_t)__popc(idle));
          base = __shfl_sync(FULL, base, leader);
          if (cur == EMPTY) {
-            uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
+            uint32_t k = base + __popc(idle & ((1u << qshift) - 1u));
             if (k < total) {
                slot = q ? q[k] : k;
                r = loadRay(O, D, slot);
-               idir = mk3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-               h.t = 0; h.prim = -1; h.b1 = 0; h.b2 = 0;
+               pre = rayPre(r);
+               hPrim = -1; hB1 = 0; hB2 = 0;
                sp = 0;
-               if (bvh.root >= 0) cur = bvh.root; else { li = le = 0; cur = LEAF; }   // empty scene: a leaf with zero items
+               cur = bvh.root;
+               if (bvh.root < 0) TQ_FINISH(false);   // empty scene
             }
          }
          if (base + (uint32_t)__popc(idle) >= total) exhausted = true;   // warp-uniform: the queue is drained
-         idle = __ballot_sync(FULL, cur == EMPTY);
+         idle = __ballot_sync(FULL, cur == EMPTY) & 0x11111111u;
       }
-      if (idle == FULL) { if (exhausted) break; continue; }
+      if (idle == 0x11111111u) { if (exhausted) break; continue; }
       // ---- vote: node step or leaf step
-      const bool atNode = cur >= 0, atLeaf = cur == LEAF;
+      const bool atNode = cur >= 0, atLeaf = cur < 0 && cur != EMPTY;
       const unsigned mN = __ballot_sync(FULL, atNode), mL = __ballot_sync(FULL, atLeaf);
       if (__popc(mN) >= __popc(mL)) {
          if (atNode) {
-            const F4 *np = bvh.nodes + 4 * (size_t)cur;
-            F4 n0 = ld4(np), n1 = ld4(np + 1), n2 = ld4(np + 2), n3 = ld4(np + 3);
-            float tn0, tn1; bool h0, h1;
-            nodeTest(n0, n1, n2, r, idir, tn0, tn1, h0, h1);
-            int c0 = f2i(n3.x), c1 = f2i(n3.y);
-            if (h0 && h1) {
-               if (!ANY && tn1 < tn0) { int t = c0; c0 = c1; c1 = t; }
-               if (sp < TR_SSTACK) sstack[sp][tid] = c1; else if (sp < TR_SSTACK + TR_LSTACK) lstack[sp - TR_SSTACK] = c1;
-               sp++;
-               TR_ENTER(c0);
-            } else if (h0) TR_ENTER(c0);
-            else if (h1) TR_ENTER(c1);
-            else TR_POP();
+            F4 a, b;
+            ld8(bvh.nodes + BL_NODE_F4 * (size_t)cur + 2 * sub, a, b);
+            const uint32_t key = childKey(a, b, r, pre, sub);
+            const bool hitc = key != 0xffffffffu;
+            const uint32_t k1 = __shfl_xor_sync(qmask, key, 1), k2 = __shfl_xor_sync(qmask, key, 2), k3 = __shfl_xor_sync(qmask, key, 3);
+            const int nh = (int)hitc + (int)(k1 != 0xffffffffu) + (int)(k2 != 0xffffffffu) + (int)(k3 != 0xffffffffu);
+            if (hitc) {
+               const int rank = (int)(k1 < key) + (int)(k2 < key) + (int)(k3 < key);   // 0 = nearest (keys are distinct)
+               myStack[(sp + nh - 1 - rank) * TR_QUADS] = f2i(b.z);
+            }
+            sp += nh;
+            __syncwarp(qmask);
+            TQ_POP();
          }
       } else {
          if (atLeaf) {
+            const int enc = ~cur; const int first = enc >> 4, cntl = enc & 15;
             bool found = false;
-            if (li < le) {
-               if (ANY) found = leafItemAny(bvh, li, r);
-               else leafItemNearest(bvh, li, r, h);
-               li++;
+            for (int base = 0; base < cntl; base += 4) {   // quad-uniform trip count (leaves hold <= 4 items by default)
+               const int it = base + (int)sub;
+               bool hitp = false; float t = BL_INF, b1 = 0, b2 = 0; int prim = -1;
+               if (it < cntl) {
+                  if (ANY) hitp = leafItemAny(bvh, first + it, r);
+                  else { HitRec hh; hh.t = 0; hh.prim = -1; hh.b1 = hh.b2 = 0; Ray rr = r; hitp = leafItemNearest(bvh, first + it, rr, hh); if (hitp) { t = hh.t; b1 = hh.b1; b2 = hh.b2; prim = hh.prim; } }
+               }
+               const unsigned hb = __ballot_sync(qmask, hitp) & qmask;
+               if (hb) {
+                  if (ANY) { found = true; break; }
+                  // nearest of the quad's hits; on equal t the later item wins, as in the sequential fold (Primitive.hs:29-43)
+                  float tt = t; unsigned w = sub;
+                  { float o = __shfl_xor_sync(qmask, tt, 1); unsigned ow = sub ^ 1u; if (o < tt || (o == tt && ow > w)) { tt = o; w = ow; } }
+                  { float o = __shfl_xor_sync(qmask, tt, 2); unsigned ow = __shfl_xor_sync(qmask, w, 2); if (o < tt || (o == tt && ow > w)) { tt = o; w = ow; } }
+                  const int src = (int)(qshift + w);
+                  r.tmax = tt;
+                  hPrim = __shfl_sync(qmask, prim, src); hB1 = __shfl_sync(qmask, b1, src); hB2 = __shfl_sync(qmask, b2, src);
+               }
             }
-            if (ANY && found) TR_FINISH(true);
-            else if (li >= le) TR_POP();
+            if (ANY && found) TQ_FINISH(true);
+            else TQ_POP();
          }
       }
    }
-#undef TR_ENTER
-#undef TR_FINISH
-#undef TR_POP
+#undef TQ_FINISH
+#undef TQ_POP
 }
 
+static inline size_t traceSmemBytes(int maxStack) { int lv = maxStack < 16 ? 16 : maxStack; return (size_t)lv * TR_QUADS * sizeof(int); }
+
+static inline uint32_t traceGrid(const TraceConfig &cfg, uint32_t n, uint32_t raysPerBlock) {
+   uint32_t need = (n + raysPerBlock - 1) / raysPerBlock;
+   uint32_t full = (uint32_t)cfg.sms * (uint32_t)cfg.blocksPerSm;
+   return need < full ? (need ? need : 1) : full;
+}
 static inline void launchTraceNearest(TraceConfig &cfg, cudaStream_t st, const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc,
                                       const F4 *O, const F4 *D, F4 *hit) {
-   uint32_t need = (n + TR_THREADS - 1) / TR_THREADS;
-   uint32_t full = (uint32_t)cfg.sms * (uint32_t)cfg.blocksPerSm;
-   uint32_t grid = need < full ? (need ? need : 1) : full;
-   if (cfg.countStats && cfg.travCounters) { kTraceNearestCount<<<grid, 128, 0, st>>>(q, cnt, n, sc, O, D, hit, cfg.travCounters); return; }
-   if (cfg.variant == 0) { kTraceNearestSimple<<<grid, 128, 0, st>>>(q, cnt, n, sc, O, D, hit); return; }
+   if (cfg.countStats && cfg.travCounters) { kTraceNearestCount<<<traceGrid(cfg, n, 128), 128, 0, st>>>(q, cnt, n, sc, O, D, hit, cfg.travCounters); return; }
+   if (cfg.variant == 0) { kTraceNearestSimple<<<traceGrid(cfg, n, 128), 128, 0, st>>>(q, cnt, n, sc, O, D, hit); return; }
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
-   kTracePersistent<false><<<grid, TR_THREADS, 0, st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter);
+   kTraceQuad<false><<<traceGrid(cfg, n, TR_QUADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter);
 }
 static inline void launchTraceAny(TraceConfig &cfg, cudaStream_t st, const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc,
                                   const F4 *O, const F4 *D, uint8_t *occl) {
-   uint32_t need = (n + TR_THREADS - 1) / TR_THREADS;
-   uint32_t full = (uint32_t)cfg.sms * (uint32_t)cfg.blocksPerSm;
-   uint32_t grid = need < full ? (need ? need : 1) : full;
-   if (cfg.variant == 0) { kTraceAnySimple<<<grid, 128, 0, st>>>(q, cnt, n, sc, O, D, occl); return; }
+   if (cfg.variant == 0) { kTraceAnySimple<<<traceGrid(cfg, n, 128), 128, 0, st>>>(q, cnt, n, sc, O, D, occl); return; }
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
-   kTracePersistent<true><<<grid, TR_THREADS, 0, st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter);
+   kTraceQuad<true><<<traceGrid(cfg, n, TR_QUADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter);
 }
 static inline void launchTraceStats(TraceConfig &cfg, cudaStream_t st, uint32_t n, const DScene *sc, const F4 *O, const F4 *D, F4 *hit, uint32_t *nodes, uint32_t *prims) {
    uint32_t need = (n + 127) / 128;

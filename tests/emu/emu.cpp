@@ -18,6 +18,7 @@ struct EmuBackend {
    void zero(void *d, size_t n) { std::memset(d, 0, n); }
    void sync() {}
    void setStream(void *) {}
+   void setMaxStack(int) {}
    double timerRead(double last) { return last; }
    void tag(int) {}
    void kernelTimes(double *ms, uint64_t *l, int n) { for (int i = 0; i < n; ++i) { ms[i] = 0; l[i] = 0; } }
