@@ -75,6 +75,9 @@ struct CudaBackend {
       device = dev; sms = p.multiProcessorCount;
       if (cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&ev0) != cudaSuccess || cudaEventCreate(&ev1) != cudaSuccess) { err = "stream/event creation failed"; return BLINGCU_ECUDA; }
       ownStream = stream; tcfg.sms = sms;
+      // the traversal stack lives in dynamic shared memory: allow the builder's worst case (BL_STACK levels)
+      cudaFuncSetAttribute(kTracePersistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceSmemBytes(BL_STACK));
+      cudaFuncSetAttribute(kTracePersistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceSmemBytes(BL_STACK));
       return 0;
    }
    // run on a caller-owned stream (e.g. torch's current stream, so an NCCL all-reduce of the film orders after the

@@ -31,7 +31,7 @@ struct Pipeline {
    F4 *film = nullptr;
    uint32_t npix = 0;
    uint32_t batchTarget = 1u << 23;
-   int maxLeaf = 4;
+   int maxLeaf = 2;
    uint64_t nNodes = 0, nItems = 0;
    uint64_t launches = 0;
    double lastMs = 0;
@@ -304,7 +304,7 @@ struct Pipeline {
          F4 *dH = (F4 *)be.alloc(sizeof(F4) * n);
          uint32_t *dN = nullptr, *dP = nullptr;
          if (nodes) { dN = (uint32_t *)be.alloc(4 * n); dP = (uint32_t *)be.alloc(4 * n); be.traceStats((uint32_t)n, dscene, dO, dD, dH, dN, dP); }
-         else be.traceNearest(nullptr, nullptr, (uint32_t)n, dscene, dO, dD, dH);
+         else { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(nullptr, nullptr, (uint32_t)n, dscene, dO, dD, dH); }
          be.sync();
          std::vector<F4> h(n); be.download(h.data(), dH, sizeof(F4) * n);
          for (size_t i = 0; i < n; ++i) { outHit[i].t = h[i].x; outHit[i].b1 = h[i].y; outHit[i].b2 = h[i].z; outHit[i].prim = f2i(h[i].w); }
@@ -313,7 +313,7 @@ struct Pipeline {
       }
       if (outOccl) {
          uint8_t *dC = (uint8_t *)be.alloc(n);
-         be.traceAny(nullptr, nullptr, (uint32_t)n, dscene, dO, dD, dC);
+         be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(nullptr, nullptr, (uint32_t)n, dscene, dO, dD, dC);
          be.sync();
          be.download(outOccl, dC, n);
          be.free(dC);
@@ -331,7 +331,7 @@ struct Pipeline {
          out->rays_shadow = s[S_SHADOW]; out->dropped_samples = s[S_DROPPED];
       }
       be.traversalTotals(out->nodes_traversed, out->intersections, out->rays_counted);
-      out->kernel_launches = launches; out->bvh_nodes = nNodes; out->bvh_leaf_items = nItems; lastMs = be.timerRead(lastMs); out->last_pass_ms = lastMs;
+      out->kernel_launches = launches; out->bvh_nodes = nNodes; out->bvh_leaf_items = nItems; lastMs = be.timerRead(lastMs); out->last_pass_ms = lastMs; out->bvh_max_stack = (uint64_t)hs.bvh.max_stack;
       return 0;
    }
    void resetStats() { if (ps.stats) be.zero(ps.stats, sizeof(unsigned long long) * N_STATS); launches = 0; be.resetProfile(); }

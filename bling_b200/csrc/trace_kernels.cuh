@@ -2,7 +2,8 @@
 // Replaces the per-ray recursion of KdTree.hs:210-246 (a4, a5 in SURVEY.md §8a).
 //
 // variant 0  one ray per thread, grid-stride, traversal stack in local memory (the reference point)
-// variant 1  persistent warps, one ray per QUAD, majority-vote stepping (kTraceQuad below; the product path)
+// variant 1  persistent warps, one ray per lane, majority-vote stepping, LDG.256 node fetch, shared-memory stack
+//            (kTracePersistent below; the product path)
 // B200 has no RT cores and traversal is not a contraction: no tensor cores here. The bound is L2/HBM latency
 // and bandwidth on the node/triangle fetches (DESIGN.md "Roofline").
 #pragma once
@@ -14,7 +15,7 @@ namespace bl {
 struct TraceConfig {
    int sms = 148;
    int variant = 1;
-   int blocksPerSm = 10;
+   int blocksPerSm = 8;
    int maxStack = 64;                 // worst-case stack entries of the uploaded tree (Bvh::max_stack)
    uint32_t *workCounter = nullptr;   // device, one uint32 per launch slot
    bool countStats = false;           // option "traversal_stats": nearest-hit launches count node fetches / primitive tests
@@ -71,21 +72,29 @@ __global__ void __launch_bounds__(128) kTraceNearestCount(const uint32_t *__rest
 }
 
 // ---------------------------------------------------------------------------------------------- variant 1
-// Persistent warps, ONE RAY PER QUAD (4 lanes), majority-vote stepping.
+// Persistent warps, one ray per lane, MAJORITY-VOTE stepping (the product path).
 //
-// History (profiles/): v1 let every lane run its own while loop -> 3.5 of 32 threads active per instruction. v2 kept
-// the warp converged by voting between "node step" and "leaf step" -> 2.1x, but with one ray per lane every node
-// fetch costs one L1 wavefront per lane per 16-byte load (7 LDG.128 x lanes): ncu showed the LSU data pipe at 81 %
-// (l1tex__data_pipe_lsu_wavefronts) with DRAM at 12 %. Here the four lanes of a quad own one ray and each lane
-// tests ONE child of the 4-wide node: the quad's four 32-byte loads fall into one 128-byte line = one wavefront per
-// node visit, the box test costs a quarter of the instructions per lane, and leaf items are tested four at a time.
-//   - the quad's traversal stack lives in shared memory ([level][quad], sized from the builder's worst case);
-//     a node step pushes every hit child, nearest on top (rank by three quad shuffles of the sort key), then pops;
-//   - every trip the warp votes (ballot) whether more quads stand at a node or at a leaf and executes only that
-//     step; idle quads refill from the global queue with a warp-aggregated atomic once enough quads have retired.
+// History (profiles/r01_trace_experiments.md): v1 let every lane run its own while loop -> 3.5 of 32 threads active
+// per instruction. v2 keeps the warp converged: every trip the lanes vote (ballot) whether more of them stand at an
+// inner node or inside a leaf, and the whole warp executes ONLY that step, predicated per lane (2.1x). v3 went to
+// 4-wide nodes; ncu then showed the LSU data pipe at 81 % because a node cost 7 LDG.128 per lane, each one L1
+// wavefront per lane. v4 (one ray per quad) cut the wavefronts 4x but doubled the instructions per ray. This
+// version (v5) keeps one ray per lane and fetches a node as 4 x LDG.256 (one 32-byte child record each), keeps the
+// whole traversal stack in shared memory (sized from the builder's worst case, no local-memory tail), and refills
+// idle lanes from the global queue with a warp-aggregated atomic once enough lanes have retired.
 #define TR_THREADS 128
-#define TR_QUADS (TR_THREADS / 4)
-#define TR_REFILL_Q 2     // refill once this many quads of the warp are idle
+#ifndef TR_REFILL
+#define TR_REFILL 8       // refill once this many lanes are idle
+#endif
+#ifndef TR_MINBLOCKS
+#define TR_MINBLOCKS 8
+#endif
+#ifndef TR_LEAF_WHOLE
+#define TR_LEAF_WHOLE 0   // 1: a leaf step tests every item of the leaf; 0: one item per step (li kept across trips)
+#endif
+#ifndef TR_PUSH_BF
+#define TR_PUSH_BF 1      // 1: branch-free push of the far children
+#endif
 
 __device__ __forceinline__ void ld8(const F4 *p, F4 &a, F4 &b) {   // one 32-byte load (LDG.E.256 on sm_100)
    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -93,104 +102,113 @@ __device__ __forceinline__ void ld8(const F4 *p, F4 &a, F4 &b) {   // one 32-byt
 }
 
 template <bool ANY>
-__global__ void __launch_bounds__(TR_THREADS, 10) kTraceQuad(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
-                                                           const DScene *__restrict__ sc, const F4 *__restrict__ O, const F4 *__restrict__ D,
-                                                           F4 *__restrict__ hit, uint8_t *__restrict__ occl, uint32_t *__restrict__ work) {
-   extern __shared__ int qstack[];            // [level][TR_QUADS]
+__global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
+                                                                 const DScene *__restrict__ sc, const F4 *__restrict__ O, const F4 *__restrict__ D,
+                                                                 F4 *__restrict__ hit, uint8_t *__restrict__ occl, uint32_t *__restrict__ work) {
+   extern __shared__ int sstack[];            // [level][TR_THREADS]: conflict-free, one column per thread
    const unsigned FULL = 0xffffffffu;
    const uint32_t total = cnt ? *cnt : n;
    const Bvh bvh = sc->bvh;
    const unsigned lane = threadIdx.x & 31u;
-   const unsigned sub = lane & 3u;            // which child / leaf item this lane tests
-   const unsigned qshift = lane & ~3u;        // first lane of my quad
-   const unsigned qmask = 0xfu << qshift;
-   int *const myStack = qstack + (threadIdx.x >> 2);
-   const int EMPTY = (int)0x80000000;         // quad holds no ray
-   int cur = EMPTY, sp = 0;
+   int *const myStack = sstack + threadIdx.x;
+   const int EMPTY = (int)0x80000000;   // lane holds no ray; otherwise cur = child reference (>= 0 node, < 0 encoded leaf)
+   int cur = EMPTY, sp = 0, li = 0;
    uint32_t slot = 0;
-   Ray r; RayPre pre; int hPrim = -1; float hB1 = 0, hB2 = 0;
+   Ray r; RayPre pre; HitRec h;
    bool exhausted = false;
-   r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.tmin = 0; r.tmax = 0; pre.idir = mk3(0, 0, 0); pre.ood = mk3(0, 0, 0);
-
-#define TQ_FINISH(found_) do { if (sub == 0) { if (ANY) occl[slot] = (found_) ? 1 : 0; else { F4 v_; v_.x = hPrim >= 0 ? r.tmax : 0.0f; v_.y = hB1; v_.z = hB2; v_.w = i2f(hPrim); hit[slot] = v_; } } cur = EMPTY; } while (0)
-#define TQ_POP() do { if (sp == 0) TQ_FINISH(false); else { sp--; cur = myStack[sp * TR_QUADS]; } } while (0)
+   r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.tmin = 0; r.tmax = 0; pre.idir = mk3(0, 0, 0); pre.ood = mk3(0, 0, 0); h.t = 0; h.prim = -1; h.b1 = h.b2 = 0;
 
    for (;;) {
-      // ---- refill idle quads (warp-uniform decision)
-      unsigned idle = __ballot_sync(FULL, cur == EMPTY) & 0x11111111u;   // one bit per quad
-      if (!exhausted && __popc(idle) >= TR_REFILL_Q) {
+      // ---- where does every lane stand?
+      bool atNode = cur >= 0, atLeaf = cur < 0 && cur != EMPTY;
+      unsigned mN = __ballot_sync(FULL, atNode), mL = __ballot_sync(FULL, atLeaf);
+      // ---- refill idle lanes (warp-uniform decision)
+      if (!exhausted && __popc(mN | mL) <= 32 - TR_REFILL) {
+         const unsigned idle = ~(mN | mL);
          uint32_t base = 0;
-         int leader = __ffs(idle) - 1;
+         const int leader = __ffs(idle) - 1;
          if ((int)lane == leader) base = atomicAdd(work, (uint32_t)__popc(idle));
          base = __shfl_sync(FULL, base, leader);
          if (cur == EMPTY) {
-            uint32_t k = base + __popc(idle & ((1u << qshift) - 1u));
+            const uint32_t k = base + __popc(idle & ((1u << lane) - 1u));
             if (k < total) {
                slot = q ? q[k] : k;
                r = loadRay(O, D, slot);
                pre = rayPre(r);
-               hPrim = -1; hB1 = 0; hB2 = 0;
+               h.t = 0; h.prim = -1; h.b1 = 0; h.b2 = 0;
                sp = 0;
-               cur = bvh.root;
-               if (bvh.root < 0) TQ_FINISH(false);   // empty scene
+               cur = (bvh.root >= 0) ? bvh.root : ~0;   // empty scene: a leaf with zero items
+               li = 0;
             }
          }
          if (base + (uint32_t)__popc(idle) >= total) exhausted = true;   // warp-uniform: the queue is drained
-         idle = __ballot_sync(FULL, cur == EMPTY) & 0x11111111u;
+         atNode = cur >= 0; atLeaf = cur < 0 && cur != EMPTY;
+         mN = __ballot_sync(FULL, atNode); mL = __ballot_sync(FULL, atLeaf);
       }
-      if (idle == 0x11111111u) { if (exhausted) break; continue; }
+      if ((mN | mL) == 0) { if (exhausted) break; continue; }
+      bool pop = false;
       // ---- vote: node step or leaf step
-      const bool atNode = cur >= 0, atLeaf = cur < 0 && cur != EMPTY;
-      const unsigned mN = __ballot_sync(FULL, atNode), mL = __ballot_sync(FULL, atLeaf);
       if (__popc(mN) >= __popc(mL)) {
          if (atNode) {
-            F4 a, b;
-            ld8(bvh.nodes + BL_NODE_F4 * (size_t)cur + 2 * sub, a, b);
-            const uint32_t key = childKey(a, b, r, pre, sub);
-            const bool hitc = key != 0xffffffffu;
-            const uint32_t k1 = __shfl_xor_sync(qmask, key, 1), k2 = __shfl_xor_sync(qmask, key, 2), k3 = __shfl_xor_sync(qmask, key, 3);
-            const int nh = (int)hitc + (int)(k1 != 0xffffffffu) + (int)(k2 != 0xffffffffu) + (int)(k3 != 0xffffffffu);
-            if (hitc) {
-               const int rank = (int)(k1 < key) + (int)(k2 < key) + (int)(k3 < key);   // 0 = nearest (keys are distinct)
-               myStack[(sp + nh - 1 - rank) * TR_QUADS] = f2i(b.z);
-            }
-            sp += nh;
-            __syncwarp(qmask);
-            TQ_POP();
+            const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
+            F4 a0, b0, a1, b1, a2, b2, a3, b3;
+            ld8(np, a0, b0); ld8(np + 2, a1, b1); ld8(np + 4, a2, b2); ld8(np + 6, a3, b3);
+            uint32_t key[4];
+            key[0] = childKey(a0, b0, r, pre, 0u); key[1] = childKey(a1, b1, r, pre, 1u);
+            key[2] = childKey(a2, b2, r, pre, 2u); key[3] = childKey(a3, b3, r, pre, 3u);
+            const int ref[4] = {f2i(b0.z), f2i(b1.z), f2i(b2.z), f2i(b3.z)};
+            sort4(key);   // hits first, nearest first (any-hit only needs "hits first")
+            // branch-free push of the far hits (nearest on top), then enter the nearest
+            const int nh = (int)(key[0] != 0xffffffffu) + (int)(key[1] != 0xffffffffu) + (int)(key[2] != 0xffffffffu) + (int)(key[3] != 0xffffffffu);
+            const int r0 = pick4(ref, key[0] & 3u), r1 = pick4(ref, key[1] & 3u), r2 = pick4(ref, key[2] & 3u), r3 = pick4(ref, key[3] & 3u);
+#if TR_PUSH_BF
+            int *top = myStack + (sp + nh - 2) * TR_THREADS;   // slot of the entry that ends up on top (key[1])
+            if (nh > 1) top[0] = r1;
+            if (nh > 2) top[-TR_THREADS] = r2;
+            if (nh > 3) top[-2 * TR_THREADS] = r3;
+            sp += (nh > 0) ? nh - 1 : 0;
+#else
+            if (nh > 3) { myStack[sp * TR_THREADS] = r3; sp++; }
+            if (nh > 2) { myStack[sp * TR_THREADS] = r2; sp++; }
+            if (nh > 1) { myStack[sp * TR_THREADS] = r1; sp++; }
+#endif
+            cur = r0; li = 0;
+            pop = nh == 0;
          }
       } else {
          if (atLeaf) {
             const int enc = ~cur; const int first = enc >> 4, cntl = enc & 15;
             bool found = false;
-            for (int base = 0; base < cntl; base += 4) {   // quad-uniform trip count (leaves hold <= 4 items by default)
-               const int it = base + (int)sub;
-               bool hitp = false; float t = BL_INF, b1 = 0, b2 = 0; int prim = -1;
-               if (it < cntl) {
-                  if (ANY) hitp = leafItemAny(bvh, first + it, r);
-                  else { HitRec hh; hh.t = 0; hh.prim = -1; hh.b1 = hh.b2 = 0; Ray rr = r; hitp = leafItemNearest(bvh, first + it, rr, hh); if (hitp) { t = hh.t; b1 = hh.b1; b2 = hh.b2; prim = hh.prim; } }
-               }
-               const unsigned hb = __ballot_sync(qmask, hitp) & qmask;
-               if (hb) {
-                  if (ANY) { found = true; break; }
-                  // nearest of the quad's hits; on equal t the later item wins, as in the sequential fold (Primitive.hs:29-43)
-                  float tt = t; unsigned w = sub;
-                  { float o = __shfl_xor_sync(qmask, tt, 1); unsigned ow = sub ^ 1u; if (o < tt || (o == tt && ow > w)) { tt = o; w = ow; } }
-                  { float o = __shfl_xor_sync(qmask, tt, 2); unsigned ow = __shfl_xor_sync(qmask, w, 2); if (o < tt || (o == tt && ow > w)) { tt = o; w = ow; } }
-                  const int src = (int)(qshift + w);
-                  r.tmax = tt;
-                  hPrim = __shfl_sync(qmask, prim, src); hB1 = __shfl_sync(qmask, b1, src); hB2 = __shfl_sync(qmask, b2, src);
-               }
+#if TR_LEAF_WHOLE
+            for (int i = 0; i < cntl; ++i) {
+               if (ANY) { if (leafItemAny(bvh, first + i, r)) { found = true; break; } }
+               else leafItemNearest(bvh, first + i, r, h);
             }
-            if (ANY && found) TQ_FINISH(true);
-            else TQ_POP();
+            if (ANY && found) { occl[slot] = 1; cur = EMPTY; }
+            else pop = true;
+#else
+            if (li < cntl) {
+               if (ANY) found = leafItemAny(bvh, first + li, r);
+               else leafItemNearest(bvh, first + li, r, h);
+               li++;
+            }
+            if (ANY && found) { occl[slot] = 1; cur = EMPTY; }
+            else pop = li >= cntl;
+#endif
          }
       }
+      if (pop) {
+         if (sp == 0) {   // ray finished: write the result, free the lane
+            if (ANY) occl[slot] = 0;
+            else { F4 v; v.x = h.t; v.y = h.b1; v.z = h.b2; v.w = i2f(h.prim); hit[slot] = v; }
+            cur = EMPTY;
+         } else { sp--; cur = myStack[sp * TR_THREADS]; li = 0; }
+      }
    }
-#undef TQ_FINISH
-#undef TQ_POP
 }
 
-static inline size_t traceSmemBytes(int maxStack) { int lv = maxStack < 16 ? 16 : maxStack; return (size_t)lv * TR_QUADS * sizeof(int); }
+// levels of shared-memory stack per thread: the builder's worst case (a pop precedes every push burst of <= 3)
+static inline size_t traceSmemBytes(int maxStack) { int lv = maxStack < 8 ? 8 : maxStack; return (size_t)lv * TR_THREADS * sizeof(int); }
 
 static inline uint32_t traceGrid(const TraceConfig &cfg, uint32_t n, uint32_t raysPerBlock) {
    uint32_t need = (n + raysPerBlock - 1) / raysPerBlock;
@@ -203,14 +221,14 @@ static inline void launchTraceNearest(TraceConfig &cfg, cudaStream_t st, const u
    if (cfg.variant == 0) { kTraceNearestSimple<<<traceGrid(cfg, n, 128), 128, 0, st>>>(q, cnt, n, sc, O, D, hit); return; }
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
-   kTraceQuad<false><<<traceGrid(cfg, n, TR_QUADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter);
+   kTracePersistent<false><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter);
 }
 static inline void launchTraceAny(TraceConfig &cfg, cudaStream_t st, const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc,
                                   const F4 *O, const F4 *D, uint8_t *occl) {
    if (cfg.variant == 0) { kTraceAnySimple<<<traceGrid(cfg, n, 128), 128, 0, st>>>(q, cnt, n, sc, O, D, occl); return; }
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
-   kTraceQuad<true><<<traceGrid(cfg, n, TR_QUADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter);
+   kTracePersistent<true><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter);
 }
 static inline void launchTraceStats(TraceConfig &cfg, cudaStream_t st, uint32_t n, const DScene *sc, const F4 *O, const F4 *D, F4 *hit, uint32_t *nodes, uint32_t *prims) {
    uint32_t need = (n + 127) / 128;

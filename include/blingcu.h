@@ -212,6 +212,7 @@ typedef struct blingcu_stats {
    uint64_t kernel_launches;
    uint64_t bvh_nodes, bvh_leaf_items;
    double last_pass_ms;        /* device time of the last render call        */
+   uint64_t bvh_max_stack;     /* worst-case traversal stack entries of the uploaded tree */
 } blingcu_stats;
 
 typedef struct blingcu_ctx blingcu_ctx;
