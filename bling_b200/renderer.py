@@ -85,6 +85,9 @@ class CudaRenderer:
         return "cuda sampler renderer"
 
     def upload(self, job: RenderJob):
+        if self._dist is not None and self.world > 1 and self._dist.get_backend(self._pg) == "nccl":
+            import torch
+            self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         self.ctx.upload_scene(job.scene)
         self._job = job
 
@@ -103,8 +106,9 @@ class CudaRenderer:
         dist = self._dist
         backend = dist.get_backend(self._pg)
         if backend == "nccl":
+            # the pass was enqueued on torch's current stream (blingcu_set_stream in upload()), so the copy and
+            # the all-reduce order after it on the device; the only host sync is the final .cpu()
             ptr, n = self.ctx.film_device()
-            self.ctx.synchronize()
             local = torch.as_tensor(_DevFilm(ptr, n), device=torch.device("cuda", torch.cuda.current_device()))
             total = local.clone()
             dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self._pg)
