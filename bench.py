@@ -195,7 +195,8 @@ def run_b200(a):
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     n_gpus = world
 
     t0 = time.perf_counter()
@@ -220,13 +221,13 @@ def run_b200(a):
     sps = a.sps
     spp = scene.spp
 
-    def step(i):
+    def step(i, reduce=True):
         # rank r renders sample indices [base + r*sps, +sps) of pass p; wraps to the next pass after 1024 indices
         g = i * world * sps + rank * sps
         p, s0 = 1 + g // spp, g % spp
         s1 = min(spp, s0 + sps)
         ctx.render_slice(p, SEED, s0, s1)
-        if world > 1:
+        if world > 1 and reduce:
             film_sum.copy_(film_t)
             dist.all_reduce(film_sum, op=dist.ReduceOp.SUM)
 
@@ -271,7 +272,7 @@ def run_b200(a):
         if rank == 0:
             ctx.set_option("traversal_stats", 1); ctx.reset_stats()
             film_keep = film_t.clone()
-            step(a.warmup)                      # same rays as the first timed step
+            step(a.warmup, reduce=False)        # same rays as the first timed step (rank-local: no collective)
             torch.cuda.synchronize()
             film_t.copy_(film_keep)
             s2 = ctx.stats()
