@@ -256,8 +256,10 @@ def run_b200(a):
         kt = ctx.kernel_times()
         ctx.set_option("profile_kernels", 0)
 
-        tot = torch.tensor([ms, float(st["samples"]), float(st["rays_camera"] + st["rays_extension"] + st["rays_mis"]),
-                            float(st["rays_shadow"]), float(st["kernel_launches"])], dtype=torch.float64, device="cuda")
+        # nearest-hit kernel: camera + extension + MIS rays towards area lights; any-hit kernel: shadow + MIS rays
+        # towards infinite lights (only hit/miss matters for those)
+        tot = torch.tensor([ms, float(st["samples"]), float(st["rays_camera"] + st["rays_extension"] + st["rays_mis"] - st["rays_mis_any"]),
+                            float(st["rays_shadow"] + st["rays_mis_any"]), float(st["kernel_launches"])], dtype=torch.float64, device="cuda")
         if world > 1:
             mx = tot.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             sm = tot.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
@@ -281,7 +283,7 @@ def run_b200(a):
             n_prims = s2["intersections"] / max(1, s2["rays_counted"])
             b_ray = RAY_IN_BYTES + HIT_OUT_BYTES + n_nodes * NODE_BYTES + n_prims * ITEM_BYTES
             tn_ms, tn_launches = kt["trace_nearest"]
-            my_rays_n = float(st["rays_camera"] + st["rays_extension"] + st["rays_mis"])
+            my_rays_n = float(st["rays_camera"] + st["rays_extension"] + st["rays_mis"] - st["rays_mis_any"])
             peak, peak_src = measured_peak()
             achieved = my_rays_n * b_ray / (tn_ms * 1e-3) / 1e9 if tn_ms > 0 else 0.0
             tr = committed_traffic()
@@ -346,7 +348,7 @@ def run_b200(a):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, n_gpus),
                 "clocks": clk, "e2e": e2e, "e2e_trace": e2e_trace, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_baseline,
-                "rays": {"nearest": rays_n, "shadow": rays_s, "per_sample": (rays_n + rays_s) / max(1.0, samples)},
+                "rays": {"nearest_hit_queries": rays_n, "any_hit_queries": rays_s, "per_sample": (rays_n + rays_s) / max(1.0, samples)},
                 "bvh": {"nodes": st["bvh_nodes"], "leaf_items": st["bvh_leaf_items"]}}
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -10,9 +10,9 @@
 
 namespace bl {
 
-enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MAT0 = 4, C_DROPPED = 12, N_COUNTERS = 16 };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + material kind
+enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MAT0 = 4, C_MISANY = 11, C_DROPPED = 12, C_MISCULL = 13, N_COUNTERS = 16 };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + material kind
 enum { N_SHADE_KINDS = 1 + BLINGCU_MAT_KINDS };
-enum { S_SAMPLES = 0, S_CAM, S_EXT, S_MIS, S_SHADOW, S_DROPPED, N_STATS = 8 };
+enum { S_SAMPLES = 0, S_CAM, S_EXT, S_MIS, S_SHADOW, S_DROPPED, S_MISCULL, S_MISANY, N_STATS = 12 };
 
 struct PathState {
    uint32_t cap;
@@ -20,7 +20,7 @@ struct PathState {
    F4 *hit;                // (t, b1, b2, prim bits)
    F4 *T, *L;              // throughput / radiance, quarter q of slot i at [q*cap + i]
    F4 *shO, *shD, *PS;     // NEE shadow ray + pending contribution (already x T x nLights)
-   uint8_t *occl;
+   uint8_t *occl, *occlM;  // shadow-ray / any-hit MIS-ray occlusion flags
    F4 *miO, *miD, *mihit, *PM;   // BSDF-MIS ray, its hit, pending T x f x nLights
    F2 *miInfo;             // (bsdf pdf, light index bits)
    uint32_t *meta;         // depth | spec << 8
@@ -29,7 +29,7 @@ struct PathState {
    F2 *spos;               // image position of the sample
    F4 *xyz;                // finalised sample: X, Y, Z, valid
    uint32_t *qA, *qB;      // active queues (ping-pong)
-   uint32_t *qShadow, *qMis;
+   uint32_t *qShadow, *qMis, *qMisAny;   // qMis: nearest-hit MIS rays (area lights); qMisAny: any-hit MIS rays (infinite lights)
    uint32_t *qMat;         // N_SHADE_KINDS * cap
    uint32_t *counters;     // N_COUNTERS
    unsigned long long *stats;   // N_STATS
@@ -189,16 +189,30 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118
                }
             }
          }
-         {   // sampleBsdfMis (Scene.hs:71-82): the ray is traced now, the light lookup happens in ResolveMisBody
+         {   // sampleBsdfMis (Scene.hs:71-82): the ray is traced now, the light lookup happens in the resolve bodies.
+            // The reference traces a nearest-hit ray and keeps the sample only if the hit primitive IS the chosen
+            // light, or, on a miss, adds `le l ray`. Same result with less traversal:
+            //   infinite light  -> only hit/miss matters: any-hit query (qMisAny);
+            //   area light      -> a ray that does not even reach the light's own shape contributes nothing: culled;
+            //   delta lights    -> never hit, `le` is black: culled.
             BsdfSample bs; sampleBsdf(bsdf, wo, bCompU, bD1, bD2, bs);
             if (bs.pdf != 0 && !isBlack(bs.f)) {
-               Spec c = bs.f;
-               if (lc > 1) c = sScale(c, lcf);
-               storeSpec4(ps.PM, ps.cap, i, T * c);
                Ray mr; mr.o = p; mr.d = bs.wi; mr.tmin = eps; mr.tmax = BL_INF;
-               storeRay(ps.miO, ps.miD, i, mr);
-               F2 info; info.x = bs.pdf; info.y = i2f(ln); ps.miInfo[i] = info;
-               qPush(ps.qMis, ps.counters + C_MIS, i);
+               bool any = lt.kind == BLINGCU_LIGHT_INFINITE, keep = any;
+               if (lt.kind == BLINGCU_LIGHT_AREA) {
+                  const blingcu_shape &ls = S.shapes[lt.shape];
+                  float tl; DG dgl;
+                  keep = shapeIntersect<false>(ls, transRay(ls.w2o, mr), tl, dgl);
+               }
+               if (keep) {
+                  Spec c = bs.f;
+                  if (lc > 1) c = sScale(c, lcf);
+                  storeSpec4(ps.PM, ps.cap, i, T * c);
+                  storeRay(ps.miO, ps.miD, i, mr);
+                  F2 info; info.x = bs.pdf; info.y = i2f(ln); ps.miInfo[i] = info;
+                  if (any) qPush(ps.qMisAny, ps.counters + C_MISANY, i);
+                  else qPush(ps.qMis, ps.counters + C_MIS, i);
+               } else cntAdd(ps.counters + C_MISCULL, 1u);
             }
          }
       }
@@ -256,13 +270,30 @@ struct ResolveMisBody {   // Scene.hs:75-82
    }
 };
 
+struct ResolveMisAnyBody {   // Scene.hs:75-82, miss branch: `le l ray` of an infinite light
+   const DScene *sc; PathState ps;
+   HD void operator()(uint32_t i) const {
+      if (ps.occlM[i]) return;
+      const DScene &S = *sc;
+      F2 info = ps.miInfo[i];
+      const blingcu_light &l = S.lights[f2i(info.y)];
+      Ray ray = loadRay(ps.miO, ps.miD, i);
+      Spec li = lightLe(S, l, ray.d);
+      if (isBlack(li)) return;
+      float w = powerHeuristic(info.x, lightPdf(S, l, ray.o, ray.d));   // Q3: also for specular samples
+      Spec c = sScale(loadSpec4(ps.PM, ps.cap, i) * li, w);
+      storeSpec4(ps.L, ps.cap, i, loadSpec4(ps.L, ps.cap, i) + c);
+   }
+};
+
 // one thread: fold the queue counters into the statistics and rotate the queues (end of a bounce)
 struct AdvanceBody {
    PathState ps;
    HD void operator()(uint32_t) const {
       uint32_t *c = ps.counters;
-      statAdd(ps.stats + S_EXT, c[C_NEXT]); statAdd(ps.stats + S_SHADOW, c[C_SHADOW]); statAdd(ps.stats + S_MIS, c[C_MIS]);
-      c[C_ACTIVE] = c[C_NEXT]; c[C_NEXT] = 0; c[C_SHADOW] = 0; c[C_MIS] = 0;
+      statAdd(ps.stats + S_EXT, c[C_NEXT]); statAdd(ps.stats + S_SHADOW, c[C_SHADOW]); statAdd(ps.stats + S_MIS, c[C_MIS] + c[C_MISANY]);
+      statAdd(ps.stats + S_MISCULL, c[C_MISCULL]); statAdd(ps.stats + S_MISANY, c[C_MISANY]);
+      c[C_ACTIVE] = c[C_NEXT]; c[C_NEXT] = 0; c[C_SHADOW] = 0; c[C_MIS] = 0; c[C_MISANY] = 0; c[C_MISCULL] = 0;
       for (int k = 0; k < N_SHADE_KINDS; ++k) c[C_MAT0 + k] = 0;
    }
 };

@@ -199,10 +199,10 @@ struct Pipeline {
       size_t c = cap;
       ps.rayO = st<F4>(c); ps.rayD = st<F4>(c); ps.hit = st<F4>(c);
       ps.T = st<F4>(4 * c); ps.L = st<F4>(4 * c);
-      ps.shO = st<F4>(c); ps.shD = st<F4>(c); ps.PS = st<F4>(4 * c); ps.occl = st<uint8_t>(c);
+      ps.shO = st<F4>(c); ps.shD = st<F4>(c); ps.PS = st<F4>(4 * c); ps.occl = st<uint8_t>(c); ps.occlM = st<uint8_t>(c);
       ps.miO = st<F4>(c); ps.miD = st<F4>(c); ps.mihit = st<F4>(c); ps.PM = st<F4>(4 * c); ps.miInfo = st<F2>(c);
       ps.meta = st<uint32_t>(c); ps.kp = st<uint64_t>(c); ps.sidx = st<uint32_t>(c); ps.spos = st<F2>(c); ps.xyz = st<F4>(c);
-      ps.qA = st<uint32_t>(c); ps.qB = st<uint32_t>(c); ps.qShadow = st<uint32_t>(c); ps.qMis = st<uint32_t>(c);
+      ps.qA = st<uint32_t>(c); ps.qB = st<uint32_t>(c); ps.qShadow = st<uint32_t>(c); ps.qMis = st<uint32_t>(c); ps.qMisAny = st<uint32_t>(c);
       ps.qMat = st<uint32_t>((size_t)N_SHADE_KINDS * c);
       ps.counters = st<uint32_t>(N_COUNTERS); ps.stats = st<unsigned long long>(N_STATS);
       be.zero(ps.counters, sizeof(uint32_t) * N_COUNTERS); be.zero(ps.stats, sizeof(unsigned long long) * N_STATS);
@@ -226,10 +226,13 @@ struct Pipeline {
                launches++;
             }
             be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl);
-            be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, bound, dscene, ps.miO, ps.miD, ps.mihit);
+            launches++;
+            if (hasInfinite) { be.traceAny(ps.qMisAny, ps.counters + C_MISANY, bound, dscene, ps.miO, ps.miD, ps.occlM); launches++; }
+            if (hasArea) { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, bound, dscene, ps.miO, ps.miD, ps.mihit); launches++; }
             be.tag(BLINGCU_KC_RESOLVE); be.runQueue(ResolveShadowBody{ps}, ps.qShadow, ps.counters + C_SHADOW, bound);
-            be.runQueue(ResolveMisBody{dscene, ps}, ps.qMis, ps.counters + C_MIS, bound);
-            launches += 4;
+            launches++;
+            if (hasArea) { be.runQueue(ResolveMisBody{dscene, ps}, ps.qMis, ps.counters + C_MIS, bound); launches++; }
+            if (hasInfinite) { be.runQueue(ResolveMisAnyBody{dscene, ps}, ps.qMisAny, ps.counters + C_MISANY, bound); launches++; }
          }
          be.tag(BLINGCU_KC_OTHER); be.run(AdvanceBody{ps}, 1); launches++;
          uint32_t *t = qa; qa = qb; qb = t;
@@ -237,10 +240,13 @@ struct Pipeline {
    }
 
    bool kindPresent[N_SHADE_KINDS] = {};
+   bool hasInfinite = false, hasArea = false;
    void scanKinds(const blingcu_scene *ir) {
       for (int k = 0; k < N_SHADE_KINDS; ++k) kindPresent[k] = false;
       kindPresent[0] = true;
       for (uint32_t i = 0; i < ir->n_materials; ++i) kindPresent[1 + ir->materials[i].kind] = true;
+      hasInfinite = hasArea = false;
+      for (uint32_t i = 0; i < ir->n_lights; ++i) { hasInfinite |= ir->lights[i].kind == BLINGCU_LIGHT_INFINITE; hasArea |= ir->lights[i].kind == BLINGCU_LIGHT_AREA; }
    }
 
    int renderSlice(uint32_t pass, uint64_t seed, uint32_t sBegin, uint32_t sEnd) {
@@ -328,7 +334,7 @@ struct Pipeline {
          be.sync();
          unsigned long long s[N_STATS]; be.download(s, ps.stats, sizeof(s));
          out->samples = s[S_SAMPLES]; out->rays_camera = s[S_CAM]; out->rays_extension = s[S_EXT]; out->rays_mis = s[S_MIS];
-         out->rays_shadow = s[S_SHADOW]; out->dropped_samples = s[S_DROPPED];
+         out->rays_shadow = s[S_SHADOW]; out->dropped_samples = s[S_DROPPED]; out->rays_mis_culled = s[S_MISCULL]; out->rays_mis_any = s[S_MISANY];
       }
       be.traversalTotals(out->nodes_traversed, out->intersections, out->rays_counted);
       out->kernel_launches = launches; out->bvh_nodes = nNodes; out->bvh_leaf_items = nItems; lastMs = be.timerRead(lastMs); out->last_pass_ms = lastMs; out->bvh_max_stack = (uint64_t)hs.bvh.max_stack;

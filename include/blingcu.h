@@ -213,6 +213,9 @@ typedef struct blingcu_stats {
    uint64_t bvh_nodes, bvh_leaf_items;
    double last_pass_ms;        /* device time of the last render call        */
    uint64_t bvh_max_stack;     /* worst-case traversal stack entries of the uploaded tree */
+   uint64_t rays_mis_culled;   /* BSDF-MIS rays of Scene.hs:71-82 NOT traced because they cannot reach the chosen light
+                                  (miss its shape / delta light); rays_mis counts the traced ones only */
+   uint64_t rays_mis_any;      /* the part of rays_mis traced as any-hit queries (infinite lights: only hit/miss matters) */
 } blingcu_stats;
 
 typedef struct blingcu_ctx blingcu_ctx;

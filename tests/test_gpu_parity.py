@@ -99,7 +99,8 @@ def test_film_matches_oracle(ctx, name):
     assert abs(xg[..., 1].mean() / xo[..., 1].mean() - 1) < 5e-3
     so, sg = o.stats(), ctx.stats()
     assert sg["samples"] == so["samples"] == sg["rays_camera"]
-    for k in ("rays_extension", "rays_mis", "rays_shadow"):
+    sg["rays_mis_logical"] = sg["rays_mis"] + sg["rays_mis_culled"]; so["rays_mis_logical"] = so["rays_mis"]
+    for k in ("rays_extension", "rays_mis_logical", "rays_shadow"):
         assert abs(sg[k] / max(1, so[k]) - 1) < 5e-3, (k, sg[k], so[k])
     assert sg["kernel_launches"] > 0
 

@@ -92,8 +92,12 @@ def test_emulated_film_matches_oracle_tiles():
         fo, fe = o.read_film(), e.read_film()
         assert np.abs(fo - fe).max() <= 2e-5 * max(1.0, np.abs(fo).max()), name
         so, se = o.stats(), e.stats()
-        for k in ("samples", "rays_camera", "rays_extension", "rays_mis", "rays_shadow", "dropped_samples"):
+        for k in ("samples", "rays_camera", "rays_extension", "rays_shadow", "dropped_samples"):
             assert so[k] == se[k], (name, k)
+        # the product does not trace BSDF-MIS rays that cannot reach the chosen light; traced + culled == reference count
+        assert so["rays_mis"] == se["rays_mis"] + se["rays_mis_culled"], name
+        if name == "cornell-box":
+            assert se["rays_mis_culled"] > se["rays_mis"]
 
 
 def test_slices_and_batches_compose():
