@@ -45,18 +45,19 @@ SEED = 0xB11D6
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--tris", type=int, default=10_000_000)
     ap.add_argument("--width", type=int, default=3840)
     ap.add_argument("--height", type=int, default=2160)
-    ap.add_argument("--sps", type=int, default=2, help="sample indices per pixel per GPU per step")
+    ap.add_argument("--sps", type=int, default=8, help="sample indices per pixel per GPU per step")
     ap.add_argument("--cpu-width", type=int, default=640, help="film width of the bounded CPU sample (same camera)")
     ap.add_argument("--cpu-height", type=int, default=360)
     ap.add_argument("--cpu-sps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-scenes", action="store_true", help="skip the per-scene throughput table (BASELINE.json configs[0..3])")
     ap.add_argument("--option", action="append", default=[], help="key=value passed to blingcu_set_option")
     return ap.parse_args()
 
@@ -337,6 +338,32 @@ def run_b200(a):
                 e2e_trace = {"value": nr / dt2 / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": nr * 32, "d2h_bytes_per_step": nr * 16,
                              "what": "blingcu_trace_nearest, 4M primary-like rays, host ray buffer in / host hit buffer out"}
 
+    # ---- the named scenes of BASELINE.json configs[0..3] at their config sizes (rank 0, one GPU): one warm-up slice,
+    # then a timed slice of sample indices through blingcu_render_slice (device time from the library's own events)
+    scenes = None
+    if rank == 0 and world == 1 and not a.no_scenes:
+        scenes = {}
+        from bling_b200 import ir as IR
+        for name in ("cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"):
+            f = ROOT / "tests" / "golden" / "scenes" / f"{name}.npz"
+            if not f.exists():
+                continue
+            sc = IR.SceneIR.load(f)
+            c2 = api.Context(local)
+            c2.upload_scene(sc)
+            ex = c2.sample_extent(); npx = (ex[1] - ex[0] + 1) * (ex[3] - ex[2] + 1)
+            k = max(1, min(sc.spp // 2, int(48e6 // npx)))
+            c2.render_slice(1, SEED, 0, k); c2.synchronize(); c2.reset_stats()
+            c2.render_slice(1, SEED, k, 2 * k)
+            s3 = c2.stats()
+            rays = s3["rays_camera"] + s3["rays_extension"] + s3["rays_mis"] + s3["rays_shadow"]
+            sec = s3["last_pass_ms"] * 1e-3
+            scenes[name] = {"size": [sc.width, sc.height], "prims": sc.n_prims, "samples": s3["samples"],
+                            "msamples_per_s": s3["samples"] / sec / 1e6, "mrays_per_s": rays / sec / 1e6,
+                            "rays_per_sample": rays / max(1, s3["samples"]), "launches": s3["kernel_launches"],
+                            "hbm_roofline": "n/a (scene lives in L1/L2)" if sc.n_prims < 1000 else "see roofline of cfg 5"}
+            c2.close()
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         cb = cpu_reference_run(scene, a, steps=3, warmup=1)
@@ -349,7 +376,8 @@ def run_b200(a):
                 "clocks": clk, "e2e": e2e, "e2e_trace": e2e_trace, "gpu_launches": int(launches), "roofline": roofline,
                 "cpu_baseline": cpu_baseline,
                 "rays": {"nearest_hit_queries": rays_n, "any_hit_queries": rays_s, "per_sample": (rays_n + rays_s) / max(1.0, samples)},
-                "bvh": {"nodes": st["bvh_nodes"], "leaf_items": st["bvh_leaf_items"]}}
+                "bvh": {"nodes": st["bvh_nodes"], "leaf_items": st["bvh_leaf_items"], "max_stack": st["bvh_max_stack"]},
+                "scenes": scenes}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:

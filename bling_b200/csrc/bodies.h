@@ -364,6 +364,10 @@ struct FilmBody {
    }
 };
 
+// explicit ray batches: ABI layout <-> kernel layout
+struct SplitRaysBody { const F4 *rays; F4 *o, *d; HD void operator()(uint32_t i) const { o[i] = rays[2 * (size_t)i]; d[i] = rays[2 * (size_t)i + 1]; } };
+struct HitToAbiBody { F4 *h; HD void operator()(uint32_t i) const { F4 v = h[i]; F4 r; r.x = v.x; r.y = v.w; r.z = v.y; r.w = v.z; h[i] = r; } };   // (t,b1,b2,prim) -> {t, prim, b1, b2}
+
 struct AddFilmBody { F4 *dst; const F4 *src; HD void operator()(uint32_t i) const { F4 a = dst[i], b = src[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; dst[i] = a; } };
 
 }  // namespace bl

@@ -30,7 +30,7 @@ struct Pipeline {
    PathState ps{}; std::vector<void *> stateAllocs;
    F4 *film = nullptr;
    uint32_t npix = 0;
-   uint32_t batchTarget = 1u << 23;
+   uint32_t batchTarget = 1u << 26;   // paths per wavefront (~490 B of state each: 33 GB at the cap, sized for 180 GB HBM)
    int maxLeaf = 2;
    uint64_t nNodes = 0, nItems = 0;
    uint64_t launches = 0;
@@ -45,7 +45,7 @@ struct Pipeline {
       sceneAllocs.push_back(d);
       return d;
    }
-   void freeScene() { for (void *p : sceneAllocs) be.free(p); sceneAllocs.clear(); dscene = nullptr; if (film) { be.free(film); film = nullptr; } uploaded = false; }
+   void freeScene() { freeTraceScratch(); for (void *p : sceneAllocs) be.free(p); sceneAllocs.clear(); dscene = nullptr; if (film) { be.free(film); film = nullptr; } uploaded = false; }
    void freeState() { for (void *p : stateAllocs) be.free(p); stateAllocs.clear(); ps = PathState{}; }
 
    int upload(const blingcu_scene *ir) {
@@ -297,34 +297,37 @@ struct Pipeline {
       return 0;
    }
 
-   // explicit ray batches (parity check (a))
+   // explicit ray batches (parity check (a)). The ABI ray {o, tmin, d, tmax} is two float4 and the ABI hit
+   // {t, prim, b1, b2} one, so host buffers are copied as they are and (de)interleaved on the device; the device
+   // scratch is grow-only.
+   void *tb[6] = {}; size_t tbCap = 0;
+   void freeTraceScratch() { for (void *&p : tb) { be.free(p); p = nullptr; } tbCap = 0; }
    int traceBatch(const blingcu_ray *rays, size_t n, blingcu_hit *outHit, uint8_t *outOccl, uint32_t *nodes, uint32_t *prims) {
       if (!uploaded) return fail(BLINGCU_ESTATE, "trace before upload_scene");
       if (n == 0) return 0;
       if (n > 0x7fffffffu) return fail(BLINGCU_EINVAL, "too many rays");
-      std::vector<F4> o(n), d(n);
-      for (size_t i = 0; i < n; ++i) { o[i] = F4{rays[i].o[0], rays[i].o[1], rays[i].o[2], rays[i].tmin}; d[i] = F4{rays[i].d[0], rays[i].d[1], rays[i].d[2], rays[i].tmax}; }
-      F4 *dO = (F4 *)be.alloc(sizeof(F4) * n), *dD = (F4 *)be.alloc(sizeof(F4) * n);
-      be.upload(dO, o.data(), sizeof(F4) * n); be.upload(dD, d.data(), sizeof(F4) * n);
+      if (n > tbCap) {
+         freeTraceScratch();
+         tb[0] = be.alloc(sizeof(F4) * 2 * n); tb[1] = be.alloc(sizeof(F4) * n); tb[2] = be.alloc(sizeof(F4) * n);
+         tb[3] = be.alloc(sizeof(F4) * n); tb[4] = be.alloc(4 * n); tb[5] = be.alloc(4 * n);
+         tbCap = n;
+      }
+      F4 *dR = (F4 *)tb[0], *dO = (F4 *)tb[1], *dD = (F4 *)tb[2], *dH = (F4 *)tb[3];
+      be.upload(dR, rays, sizeof(F4) * 2 * n);
+      be.tag(BLINGCU_KC_OTHER); be.run(SplitRaysBody{dR, dO, dD}, (uint32_t)n);
       if (outHit) {
-         F4 *dH = (F4 *)be.alloc(sizeof(F4) * n);
-         uint32_t *dN = nullptr, *dP = nullptr;
-         if (nodes) { dN = (uint32_t *)be.alloc(4 * n); dP = (uint32_t *)be.alloc(4 * n); be.traceStats((uint32_t)n, dscene, dO, dD, dH, dN, dP); }
+         uint32_t *dN = (uint32_t *)tb[4], *dP = (uint32_t *)tb[5];
+         if (nodes) be.traceStats((uint32_t)n, dscene, dO, dD, dH, dN, dP);
          else { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(nullptr, nullptr, (uint32_t)n, dscene, dO, dD, dH); }
-         be.sync();
-         std::vector<F4> h(n); be.download(h.data(), dH, sizeof(F4) * n);
-         for (size_t i = 0; i < n; ++i) { outHit[i].t = h[i].x; outHit[i].b1 = h[i].y; outHit[i].b2 = h[i].z; outHit[i].prim = f2i(h[i].w); }
-         if (nodes) { be.download(nodes, dN, 4 * n); be.download(prims, dP, 4 * n); be.free(dN); be.free(dP); }
-         be.free(dH);
+         be.tag(BLINGCU_KC_OTHER); be.run(HitToAbiBody{dH}, (uint32_t)n);
+         be.download(outHit, dH, sizeof(F4) * n);
+         if (nodes) { be.download(nodes, dN, 4 * n); be.download(prims, dP, 4 * n); }
       }
       if (outOccl) {
-         uint8_t *dC = (uint8_t *)be.alloc(n);
+         uint8_t *dC = (uint8_t *)tb[4];
          be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(nullptr, nullptr, (uint32_t)n, dscene, dO, dD, dC);
-         be.sync();
          be.download(outOccl, dC, n);
-         be.free(dC);
       }
-      be.free(dO); be.free(dD);
       return 0;
    }
 
