@@ -38,7 +38,7 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "path-traced camera samples per second, whole job (Mrays/s in `mrays_per_s`)"
 UNIT = "Msamples/s"
-NODE_BYTES, ITEM_BYTES, RAY_IN_BYTES, HIT_OUT_BYTES = 128, 48, 32, 16     # bling_b200/csrc/bvh.h layout
+NODE_BYTES, ITEM_BYTES, RAY_IN_BYTES, HIT_OUT_BYTES = 64, 48, 32, 16     # bling_b200/csrc/bvh.h layout
 SEED = 0xB11D6
 
 

@@ -5,12 +5,19 @@
 // `near` shrinks rayMax), so any conservative accelerator returns the same (t, prim) as long as
 // the primitive tests are the same arithmetic. The library builds its own BVH (bvh_build.cpp).
 //
-// Node = 128 B (one L1/L2 line) = a 4-wide BVH node, one 32-byte record per child:
-//   child k at F4[2k], F4[2k+1] = (lo.x lo.y lo.z hi.x) (hi.y hi.z ref -)
-// so the four lanes of a quad each fetch ONE child with one 32-byte load and the quad's four loads coalesce into a
-// single 128-byte L1 wavefront (trace_kernels.cuh). ref >= 0: node index. ref < 0: leaf, ~ref = (first_item << 4) |
-// count. Unused child slots carry the box (+inf, -inf), which no ray hits. The builder (bvh_build.cpp) builds a
-// binned-SAH binary tree and collapses it into 4-wide nodes by repeatedly opening the child with the largest area.
+// Node = 64 B = a 4-wide BVH node with child boxes quantised to 8 bits on a node-local grid (two 32-byte loads):
+//   F4[0] = (P.x P.y P.z  E)      grid origin (f32) and the three grid exponents packed as biased float exponents
+//                                  (E = ex | ey << 8 | ez << 16, cell size 2^(e-127) per axis)
+//   F4[1] = child refs [0..3]      ref >= 0: node index. ref < 0: leaf, ~ref = (first_item << 4) | count
+//   F4[2] = (qlo.x qlo.y qlo.z qhi.x), F4[3] = (qhi.y qhi.z - -)   each word packs the byte of the four children
+// Dequantised plane = P + cell * q. The ray/plane distance is ONE fma per plane: q_as_float * (cell/d) + (P/d - o/d),
+// with q_as_float built by a byte permute into the mantissa of 2^23 (bits 0x4B000000 | q) and the 2^23 folded into
+// the addend; that folding costs up to half a cell of accuracy, so the builder rounds every bound outwards by one
+// extra cell (and keeps bytes 0 and 255 free for it). Unused child slots carry qlo = 255 > qhi = 0, which the
+// direction-sign based near/far selection rejects on its own. Why quantise: ncu showed the LSU data pipe as the
+// limiter with 128-byte nodes (one L1 wavefront per lane per 16 bytes); 64-byte nodes halve it and halve the
+// L2/DRAM bytes per visit. The builder (bvh_build.cpp) builds a binned-SAH binary tree, collapses it into 4-wide
+// nodes by repeatedly opening the child with the largest area, then quantises.
 // Leaf item = 48 B = 3 x 16-byte loads:
 //   triangle: (p1.xyz, prim_id) (e1.xyz, 0) (e2.xyz, -)       shape: (-, -, -, prim_id) (-, -, -, 1 + shape index) -
 // Boxes are inflated by the builder, so the slab test needs no epsilon (see bvh_build.cpp).
@@ -57,7 +64,7 @@ HD bool leafItemAny(const Bvh &bvh, int item, const Ray &r) {
    return shapeIntersects(s, transRay(s.w2o, r));
 }
 
-#define BL_NODE_F4 8     // F4 per node (128 B)
+#define BL_NODE_F4 4     // F4 per node (64 B)
 #define BL_STACK 192     // worst case 3 pushes per level of a 56-level binary tree; real scenes use < 48
 
 #if defined(__CUDA_ARCH__)
@@ -72,23 +79,31 @@ struct RayPre { V3 idir, ood; };   // 1/d and o/d: plane distance = plane * idir
 HD float safeInv(float d) { return fminf(fmaxf(1.0f / d, -1e18f), 1e18f); }
 HD RayPre rayPre(const Ray &r) { RayPre p; p.idir = mk3(safeInv(r.d.x), safeInv(r.d.y), safeInv(r.d.z)); p.ood = p.idir * r.o; return p; }
 
-// slab test of ONE child box against [r.tmin, r.tmax]. Returns the child's sort key:
+HD uint32_t f2u(float f) { return (uint32_t)f2i(f); }
+HD float u2f(uint32_t u) { return i2f((int)u); }
+// float with bits 0x4B000000 | byte k of w  ==  2^23 + q   (one PRMT on the device)
+#if defined(__CUDA_ARCH__)
+#define BL_QF(w, k) __uint_as_float(__byte_perm((w), 0x4B000000u, 0x7650u + (k)))
+#else
+#define BL_QF(w, k) u2f(0x4B000000u | (((w) >> (8 * (k))) & 0xffu))
+#endif
+
+// slab test of the four children of one quantised node against [r.tmin, r.tmax]. Returns the sort keys:
 // hit -> (bits(tnear) & ~3) | slot  (tnear >= tmin >= 0, so unsigned order == distance order), miss -> 0xffffffff.
-// fminf/fmaxf drop NaNs (0 * huge cannot occur after safeInv; inf box bounds of unused slots give inf/-inf), which
-// keeps the test conservative.
-HD uint32_t childKey(const F4 &a, const F4 &b, const Ray &r, const RayPre &p, uint32_t slot) {
-   float ax = BL_FMA(a.x, p.idir.x, -p.ood.x), bx = BL_FMA(a.w, p.idir.x, -p.ood.x);
-   float ay = BL_FMA(a.y, p.idir.y, -p.ood.y), by = BL_FMA(b.x, p.idir.y, -p.ood.y);
-   float az = BL_FMA(a.z, p.idir.z, -p.ood.z), bz = BL_FMA(b.y, p.idir.z, -p.ood.z);
-   float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), r.tmin));
-   float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), r.tmax));
-   return (tn <= tf) ? (((uint32_t)f2i(tn) & ~3u) | slot) : 0xffffffffu;
-}
-// all four children of a node (single-lane traversal: CPU emulator, instrumented and reference kernels)
-HD void node4Keys(const F4 *np, const Ray &r, const RayPre &p, uint32_t key[4], int ref[4]) {
+HD void node4Keys(const F4 &n0, const F4 &n2, const F4 &n3, const Ray &r, const RayPre &p, uint32_t key[4]) {
+   const uint32_t E = f2u(n0.w);
+   const float ax = u2f((E & 0xffu) << 23) * p.idir.x, ay = u2f(((E >> 8) & 0xffu) << 23) * p.idir.y, az = u2f(((E >> 16) & 0xffu) << 23) * p.idir.z;
+   // addend: P/d - o/d - 2^23 * cell/d
+   const float bx = BL_FMA(-8388608.0f, ax, BL_FMA(n0.x, p.idir.x, -p.ood.x));
+   const float by = BL_FMA(-8388608.0f, ay, BL_FMA(n0.y, p.idir.y, -p.ood.y));
+   const float bz = BL_FMA(-8388608.0f, az, BL_FMA(n0.z, p.idir.z, -p.ood.z));
+   const uint32_t qlx = f2u(n2.x), qly = f2u(n2.y), qlz = f2u(n2.z), qhx = f2u(n2.w), qhy = f2u(n3.x), qhz = f2u(n3.y);
+   const bool px = p.idir.x >= 0.0f, py = p.idir.y >= 0.0f, pz = p.idir.z >= 0.0f;
+   const uint32_t nx = px ? qlx : qhx, fx = px ? qhx : qlx, ny = py ? qly : qhy, fy = py ? qhy : qly, nz = pz ? qlz : qhz, fz = pz ? qhz : qlz;
    BL_UNROLL for (int k = 0; k < 4; ++k) {
-      F4 a = ld4(np + 2 * k), b = ld4(np + 2 * k + 1);
-      key[k] = childKey(a, b, r, p, (uint32_t)k); ref[k] = f2i(b.z);
+      float tn = fmaxf(fmaxf(BL_FMA(BL_QF(nx, k), ax, bx), BL_FMA(BL_QF(ny, k), ay, by)), fmaxf(BL_FMA(BL_QF(nz, k), az, bz), r.tmin));
+      float tf = fminf(fminf(BL_FMA(BL_QF(fx, k), ax, bx), BL_FMA(BL_QF(fy, k), ay, by)), fminf(BL_FMA(BL_QF(fz, k), az, bz), r.tmax));
+      key[k] = (tn <= tf) ? ((f2u(tn) & ~3u) | (uint32_t)k) : 0xffffffffu;
    }
 }
 HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
@@ -113,8 +128,10 @@ HD HitRec traceNearest(const Bvh &bvh, Ray r, uint32_t *nNodes, uint32_t *nPrims
       if (cur >= 0) {
          const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
          if (STATS) (*nNodes)++;
-         uint32_t key[4]; int n6[4];
-         node4Keys(np, r, pre, key, n6);
+         uint32_t key[4];
+         F4 n0 = ld4(np), n1 = ld4(np + 1), n2 = ld4(np + 2), n3 = ld4(np + 3);
+         node4Keys(n0, n2, n3, r, pre, key);
+         const int n6[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};
          sort4(key);
          if (key[0] != 0xffffffffu) {
             for (int j = 3; j >= 1; --j) if (key[j] != 0xffffffffu && sp < BL_STACK) stack[sp++] = pick4(n6, key[j] & 3u);
@@ -140,8 +157,10 @@ HD bool traceAny(const Bvh &bvh, const Ray &r) {
    for (;;) {
       if (cur >= 0) {
          const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
-         uint32_t key[4]; int n6[4];
-         node4Keys(np, r, pre, key, n6);
+         uint32_t key[4];
+         F4 n0 = ld4(np), n1 = ld4(np + 1), n2 = ld4(np + 2), n3 = ld4(np + 3);
+         node4Keys(n0, n2, n3, r, pre, key);
+         const int n6[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};
          int next = 0; bool have = false;
          for (int k = 0; k < 4; ++k) if (key[k] != 0xffffffffu) { int c = pick4(n6, (uint32_t)k); if (!have) { next = c; have = true; } else if (sp < BL_STACK) stack[sp++] = c; }
          if (have) { cur = next; continue; }

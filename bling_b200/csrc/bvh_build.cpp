@@ -7,6 +7,7 @@
 // starts within ~20 scene diameters.
 #include "bvh.h"
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
@@ -180,18 +181,41 @@ int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
       }
       F4 *np = n4 + BL_NODE_F4 * (size_t)w.n4idx;
       int refs[4];
+      Box nb; nb.reset();
       for (int k = 0; k < 4; ++k) {
          bool used = k < nc && !(c[k].ref < 0 && ((~c[k].ref) & 15) == 0);   // drop empty leaves
          refs[k] = used ? c[k].ref : ~0;
-         if (!used) { c[k].box.reset(); }
+         if (used) nb.grow(c[k].box);
       }
       // inner children get their 4-wide index now: siblings are contiguous in memory
       for (int k = nc - 1; k >= 0; --k) if (k < nc && refs[k] >= 0) { int id = next4++; work.push_back(Work{refs[k], id}); refs[k] = id; }
-      for (int k = 0; k < 4; ++k) {
-         const Box &bx = c[k].box;
-         np[2 * k] = F4{bx.lo[0], bx.lo[1], bx.lo[2], bx.hi[0]};
-         np[2 * k + 1] = F4{bx.hi[1], bx.hi[2], i2f(refs[k]), 0};
+      // quantise the child boxes on a node-local grid of 2^e cells; bytes 1..254 cover the node box, every bound is
+      // rounded outwards and then moved out by one more cell (the kernel's folded 2^23 costs up to half a cell)
+      float P[3]; uint32_t E = 0; uint32_t qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0};
+      for (int a = 0; a < 3; ++a) {
+         double lo = nb.lo[a], ext = (double)nb.hi[a] - (double)nb.lo[a];
+         if (!(ext > 0)) ext = 0;
+         int e = -100;
+         if (ext > 0) { e = (int)std::ceil(std::log2(ext / 252.0)); while (std::ldexp(252.0, e) < ext) e++; }
+         e = std::max(-120, std::min(120, e));
+         double cell = std::ldexp(1.0, e);
+         float Pf = (float)(lo - cell);
+         while ((double)Pf + cell > lo) Pf = std::nextafterf(Pf, -BL_INF);   // byte 1 must not lie above the node's low bound
+         P[a] = Pf; E |= (uint32_t)(e + 127) << (8 * a);
+         for (int k = 0; k < 4; ++k) {
+            int ql = 255, qh = 0;   // unused slot: inverted, never hit
+            if (refs[k] != ~0) {
+               ql = (int)std::floor(((double)c[k].box.lo[a] - (double)Pf) / cell) - 1;
+               qh = (int)std::ceil(((double)c[k].box.hi[a] - (double)Pf) / cell) + 1;
+               ql = std::max(0, std::min(255, ql)); qh = std::max(0, std::min(255, qh));
+            }
+            qlo[a] |= (uint32_t)ql << (8 * k); qhi[a] |= (uint32_t)qh << (8 * k);
+         }
       }
+      np[0] = F4{P[0], P[1], P[2], i2f((int)E)};
+      np[1] = F4{i2f(refs[0]), i2f(refs[1]), i2f(refs[2]), i2f(refs[3])};
+      np[2] = F4{i2f((int)qlo[0]), i2f((int)qlo[1]), i2f((int)qlo[2]), i2f((int)qhi[0])};
+      np[3] = F4{i2f((int)qhi[1]), i2f((int)qhi[2]), 0, 0};
    }
    // worst-case traversal stack (entries) of the push-all-then-pop scheme: children indices are always larger than
    // the parent's, so one reverse sweep suffices
@@ -201,7 +225,7 @@ int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
          const F4 *np = n4 + BL_NODE_F4 * (size_t)i;
          int nc = 0, deepest = 0;
          for (int k = 0; k < 4; ++k) {
-            int ref = f2i(np[2 * k + 1].z);
+            int ref = f2i(k == 0 ? np[1].x : (k == 1 ? np[1].y : (k == 2 ? np[1].z : np[1].w)));
             if (ref == ~0) continue;
             nc++;
             if (ref >= 0) deepest = std::max(deepest, cap[(size_t)ref]);

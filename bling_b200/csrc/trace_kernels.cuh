@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128) kTraceNearestCount(const uint32_t *__rest
 // inner node or inside a leaf, and the whole warp executes ONLY that step, predicated per lane (2.1x). v3 went to
 // 4-wide nodes; ncu then showed the LSU data pipe at 81 % because a node cost 7 LDG.128 per lane, each one L1
 // wavefront per lane. v4 (one ray per quad) cut the wavefronts 4x but doubled the instructions per ray. This
-// version (v5) keeps one ray per lane and fetches a node as 4 x LDG.256 (one 32-byte child record each), keeps the
+// version keeps one ray per lane, fetches a (now 64-byte, quantised: bvh.h) node as 2 x LDG.256, keeps the
 // whole traversal stack in shared memory (sized from the builder's worst case, no local-memory tail), and refills
 // idle lanes from the global queue with a warp-aggregated atomic once enough lanes have retired.
 #define TR_THREADS 128
@@ -151,12 +151,11 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
       if (__popc(mN) >= __popc(mL)) {
          if (atNode) {
             const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
-            F4 a0, b0, a1, b1, a2, b2, a3, b3;
-            ld8(np, a0, b0); ld8(np + 2, a1, b1); ld8(np + 4, a2, b2); ld8(np + 6, a3, b3);
+            F4 n0, n1, n2, n3;
+            ld8(np, n0, n1); ld8(np + 2, n2, n3);
             uint32_t key[4];
-            key[0] = childKey(a0, b0, r, pre, 0u); key[1] = childKey(a1, b1, r, pre, 1u);
-            key[2] = childKey(a2, b2, r, pre, 2u); key[3] = childKey(a3, b3, r, pre, 3u);
-            const int ref[4] = {f2i(b0.z), f2i(b1.z), f2i(b2.z), f2i(b3.z)};
+            node4Keys(n0, n2, n3, r, pre, key);
+            const int ref[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};
             sort4(key);   // hits first, nearest first (any-hit only needs "hits first")
             // branch-free push of the far hits (nearest on top), then enter the nearest
             const int nh = (int)(key[0] != 0xffffffffu) + (int)(key[1] != 0xffffffffu) + (int)(key[2] != 0xffffffffu) + (int)(key[3] != 0xffffffffu);
