@@ -89,16 +89,27 @@ __global__ void __launch_bounds__(128) kTraceNearestCount(const uint32_t *__rest
 #ifndef TR_MINBLOCKS
 #define TR_MINBLOCKS 8
 #endif
-#ifndef TR_LEAF_WHOLE
-#define TR_LEAF_WHOLE 0   // 1: a leaf step tests every item of the leaf; 0: one item per step (li kept across trips)
-#endif
-#ifndef TR_PUSH_BF
-#define TR_PUSH_BF 1      // 1: branch-free push of the far children
-#endif
 
 __device__ __forceinline__ void ld8(const F4 *p, F4 &a, F4 &b) {   // one 32-byte load (LDG.E.256 on sm_100)
    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
+// ---- small PTX helpers: keep the hot loop free of compiler-made branches and generic->shared address conversions
+__device__ __forceinline__ void stsIf(uint32_t addr, int v, bool p) {   // predicated st.shared.b32
+   asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.shared.b32 [%0], %1; }" ::"r"(addr), "r"(v), "r"((int)p) : "memory");
+}
+__device__ __forceinline__ int ldsIf(uint32_t addr, int old, bool p) {   // predicated ld.shared.b32, keeps `old` otherwise
+   int v = old;
+   asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q ld.shared.b32 %0, [%1]; }" : "+r"(v) : "r"(addr), "r"((int)p) : "memory");
+   return v;
+}
+__device__ __forceinline__ int sel4(int c0, int c1, int c2, int c3, uint32_t slot) {   // c[slot], three selp, no branch
+   int lo, hi, out;
+   asm("{ .reg .pred p0, p1; and.b32 %0, %7, 1; setp.ne.b32 p0, %0, 0; and.b32 %1, %7, 2; setp.ne.b32 p1, %1, 0;\n"
+       "  selp.b32 %0, %4, %3, p0; selp.b32 %1, %6, %5, p0; selp.b32 %2, %1, %0, p1; }"
+       : "=&r"(lo), "=&r"(hi), "=r"(out) : "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(slot));
+   return out;
 }
 
 template <bool ANY>
@@ -110,9 +121,11 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
    const uint32_t total = cnt ? *cnt : n;
    const Bvh bvh = sc->bvh;
    const unsigned lane = threadIdx.x & 31u;
-   int *const myStack = sstack + threadIdx.x;
+   const uint32_t stackBase = (uint32_t)__cvta_generic_to_shared(sstack + threadIdx.x);   // 32-bit shared address of my column
+   const uint32_t LV = TR_THREADS * (uint32_t)sizeof(int);                                // bytes per stack level
    const int EMPTY = (int)0x80000000;   // lane holds no ray; otherwise cur = child reference (>= 0 node, < 0 encoded leaf)
-   int cur = EMPTY, sp = 0, li = 0;
+   int cur = EMPTY, li = 0;
+   uint32_t spa = stackBase;            // shared address of the next free stack entry
    uint32_t slot = 0;
    Ray r; RayPre pre; HitRec h;
    bool exhausted = false;
@@ -136,7 +149,7 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
                r = loadRay(O, D, slot);
                pre = rayPre(r);
                h.t = 0; h.prim = -1; h.b1 = 0; h.b2 = 0;
-               sp = 0;
+               spa = stackBase;
                cur = (bvh.root >= 0) ? bvh.root : ~0;   // empty scene: a leaf with zero items
                li = 0;
             }
@@ -155,22 +168,16 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
             ld8(np, n0, n1); ld8(np + 2, n2, n3);
             uint32_t key[4];
             node4Keys(n0, n2, n3, r, pre, key);
-            const int ref[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};
+            const int c0 = f2i(n1.x), c1 = f2i(n1.y), c2 = f2i(n1.z), c3 = f2i(n1.w);
             sort4(key);   // hits first, nearest first (any-hit only needs "hits first")
             // branch-free push of the far hits (nearest on top), then enter the nearest
             const int nh = (int)(key[0] != 0xffffffffu) + (int)(key[1] != 0xffffffffu) + (int)(key[2] != 0xffffffffu) + (int)(key[3] != 0xffffffffu);
-            const int r0 = pick4(ref, key[0] & 3u), r1 = pick4(ref, key[1] & 3u), r2 = pick4(ref, key[2] & 3u), r3 = pick4(ref, key[3] & 3u);
-#if TR_PUSH_BF
-            int *top = myStack + (sp + nh - 2) * TR_THREADS;   // slot of the entry that ends up on top (key[1])
-            if (nh > 1) top[0] = r1;
-            if (nh > 2) top[-TR_THREADS] = r2;
-            if (nh > 3) top[-2 * TR_THREADS] = r3;
-            sp += (nh > 0) ? nh - 1 : 0;
-#else
-            if (nh > 3) { myStack[sp * TR_THREADS] = r3; sp++; }
-            if (nh > 2) { myStack[sp * TR_THREADS] = r2; sp++; }
-            if (nh > 1) { myStack[sp * TR_THREADS] = r1; sp++; }
-#endif
+            const int r0 = sel4(c0, c1, c2, c3, key[0]), r1 = sel4(c0, c1, c2, c3, key[1]), r2 = sel4(c0, c1, c2, c3, key[2]), r3 = sel4(c0, c1, c2, c3, key[3]);
+            const uint32_t top = spa + (uint32_t)(nh - 2) * LV;   // entry that ends up on top (key[1])
+            stsIf(top, r1, nh > 1);
+            stsIf(top - LV, r2, nh > 2);
+            stsIf(top - 2 * LV, r3, nh > 3);
+            spa += (nh > 0) ? (uint32_t)(nh - 1) * LV : 0u;
             cur = r0; li = 0;
             pop = nh == 0;
          }
@@ -178,14 +185,6 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
          if (atLeaf) {
             const int enc = ~cur; const int first = enc >> 4, cntl = enc & 15;
             bool found = false;
-#if TR_LEAF_WHOLE
-            for (int i = 0; i < cntl; ++i) {
-               if (ANY) { if (leafItemAny(bvh, first + i, r)) { found = true; break; } }
-               else leafItemNearest(bvh, first + i, r, h);
-            }
-            if (ANY && found) { occl[slot] = 1; cur = EMPTY; }
-            else pop = true;
-#else
             if (li < cntl) {
                if (ANY) found = leafItemAny(bvh, first + li, r);
                else leafItemNearest(bvh, first + li, r, h);
@@ -193,15 +192,17 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
             }
             if (ANY && found) { occl[slot] = 1; cur = EMPTY; }
             else pop = li >= cntl;
-#endif
          }
       }
-      if (pop) {
-         if (sp == 0) {   // ray finished: write the result, free the lane
-            if (ANY) occl[slot] = 0;
-            else { F4 v; v.x = h.t; v.y = h.b1; v.z = h.b2; v.w = i2f(h.prim); hit[slot] = v; }
-            cur = EMPTY;
-         } else { sp--; cur = myStack[sp * TR_THREADS]; li = 0; }
+      // ---- pop (predicated load) or, with an empty stack, finish the ray (rare: once per ray)
+      const bool more = spa != stackBase;
+      spa -= (pop && more) ? LV : 0u;
+      cur = ldsIf(spa, cur, pop && more);
+      li = pop ? 0 : li;
+      if (pop && !more) {
+         if (ANY) occl[slot] = 0;
+         else { F4 v; v.x = h.t; v.y = h.b1; v.z = h.b2; v.w = i2f(h.prim); hit[slot] = v; }
+         cur = EMPTY;
       }
    }
 }
@@ -221,6 +222,7 @@ static inline void launchTraceNearest(TraceConfig &cfg, cudaStream_t st, const u
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
    kTracePersistent<false><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter);
+
 }
 static inline void launchTraceAny(TraceConfig &cfg, cudaStream_t st, const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc,
                                   const F4 *O, const F4 *D, uint8_t *occl) {
@@ -228,6 +230,7 @@ static inline void launchTraceAny(TraceConfig &cfg, cudaStream_t st, const uint3
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
    kTracePersistent<true><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter);
+
 }
 static inline void launchTraceStats(TraceConfig &cfg, cudaStream_t st, uint32_t n, const DScene *sc, const F4 *O, const F4 *D, F4 *hit, uint32_t *nodes, uint32_t *prims) {
    uint32_t need = (n + 127) / 128;
