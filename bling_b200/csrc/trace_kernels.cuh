@@ -84,10 +84,13 @@ __global__ void __launch_bounds__(128) kTraceNearestCount(const uint32_t *__rest
 // idle lanes from the global queue with a warp-aggregated atomic once enough lanes have retired.
 #define TR_THREADS 128
 #ifndef TR_REFILL
-#define TR_REFILL 8       // refill once this many lanes are idle
+#define TR_REFILL 4       // refill once this many lanes are idle
 #endif
 #ifndef TR_MINBLOCKS
 #define TR_MINBLOCKS 8
+#endif
+#ifndef TR_LEAF_W
+#define TR_LEAF_W 6       // vote weights (quarters): leaf step when TR_LEAF_W * #leaf lanes > 4 * #node lanes
 #endif
 
 __device__ __forceinline__ void ld8(const F4 *p, F4 &a, F4 &b) {   // one 32-byte load (LDG.E.256 on sm_100)
@@ -161,7 +164,7 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
       if ((mN | mL) == 0) { if (exhausted) break; continue; }
       bool pop = false;
       // ---- vote: node step or leaf step
-      if (__popc(mN) >= __popc(mL)) {
+      if (4 * __popc(mN) >= TR_LEAF_W * __popc(mL)) {
          if (atNode) {
             const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
             F4 n0, n1, n2, n3;
