@@ -25,7 +25,10 @@ template <class B> __global__ void __launch_bounds__(256) kRunQueue(B b, const u
    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b(q[i]);
 }
 // the shade kernel carries 16-band spectra in registers: smaller blocks, one item per thread per trip
-template <class B> __global__ void __launch_bounds__(128) kRunQueueHeavy(B b, const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt) {
+#ifndef SH_MINBLOCKS
+#define SH_MINBLOCKS 3
+#endif
+template <class B> __global__ void __launch_bounds__(128, SH_MINBLOCKS) kRunQueueHeavy(B b, const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt) {
    uint32_t n = *cnt;
    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b(q[i]);
 }
