@@ -11,7 +11,11 @@ sys.path.insert(0, str(ROOT))
 from bling_b200 import ir as IR  # noqa: E402
 from bling_b200.host.loader import resized  # noqa: E402
 
-SCENES = ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"]
+SCENES = ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"]      # BASELINE.json configs[0..3]
+# this repository's own coverage scenes (tests/golden/scenes_src/*.bling): every shape / material / light / camera /
+# sampler kind of SURVEY.md §8a that the config scenes do not reach
+COVERAGE = ["zoo", "envcam"]
+ALL_SCENES = SCENES + COVERAGE
 
 
 def pytest_configure(config):

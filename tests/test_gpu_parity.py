@@ -12,7 +12,7 @@ from bling_b200 import api, image, ir as IR
 from bling_b200.host.soup import make_soup
 from bling_b200.renderer import CudaRenderer, PassDone, RenderJob
 from oracle.oracle_py import Oracle
-from tests.conftest import ROOT, SCENES, camera_rays, compare_hits, load_scene, random_rays, small
+from tests.conftest import ALL_SCENES, ROOT, SCENES, camera_rays, compare_hits, load_scene, random_rays, small
 
 pytestmark = pytest.mark.gpu
 NCPU = os.cpu_count() or 1
@@ -26,7 +26,7 @@ def ctx():
 
 
 @pytest.mark.parametrize("variant", [0, 1])
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL_SCENES)
 def test_nearest_and_any_hit_parity(ctx, name, variant):
     sc = load_scene(name)
     ctx.set_option("trace_variant", variant)
@@ -66,7 +66,7 @@ def test_soup_traversal_parity(ctx, variant):
     ctx.set_option("trace_variant", 1)
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL_SCENES)
 def test_path_samples_match_oracle(ctx, name):
     sc = small(load_scene(name), 64, 48, 4, 4)
     ctx.upload_scene(sc)
@@ -85,7 +85,7 @@ def test_path_samples_match_oracle(ctx, name):
     assert abs(Lg.mean() / Lo.mean() - 1) < 5e-3
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL_SCENES)
 def test_film_matches_oracle(ctx, name):
     sc = small(load_scene(name), 96, 64, 4, 4)
     ctx.upload_scene(sc); ctx.reset_stats()
@@ -109,7 +109,7 @@ def rel_mse(a, b):
     return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-3)))
 
 
-@pytest.mark.parametrize("name", SCENES)
+@pytest.mark.parametrize("name", ALL_SCENES)
 def test_converged_render_vs_golden(ctx, name):
     """parity (b): >= 4096 spp on the GPU vs the committed converged oracle render (tests/golden/renders, made by
     tools/make_golden_renders.py with a DIFFERENT seed): rel-MSE bound and per-channel mean within 0.5 %."""
