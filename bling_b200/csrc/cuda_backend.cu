@@ -135,25 +135,32 @@ struct CudaBackend {
       if (need >= full) return full;
       return need ? need : 1;
    }
+   // CTAs of `kernel` that fit on one SM (registers / shared memory), cached per kernel: grid-stride kernels are
+   // launched with exactly sms x resident CTAs so that every SM holds the same amount of work (no partial last wave)
+   template <class K> uint32_t resident(K kernel, int block) {
+      static thread_local int cached = 0;   // one instantiation of this function template per kernel
+      if (!cached) { int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, block, 0); cached = nb > 0 ? nb : 1; }
+      return (uint32_t)cached;
+   }
    template <class B> void run(const B &b, uint32_t n) {
       if (n == 0) return;
       Scope sc_(this);
-      kRun<B><<<gridFor(n, 256, 8), 256, 0, stream>>>(b, n);
+      kRun<B><<<gridFor(n, 256, resident(kRun<B>, 256)), 256, 0, stream>>>(b, n);
    }
    template <class B> void runQueue(const B &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
       if (bound == 0) return;
       Scope sc_(this);
-      kRunQueue<B><<<gridFor(bound, 256, 8), 256, 0, stream>>>(b, q, cnt);
+      kRunQueue<B><<<gridFor(bound, 256, resident(kRunQueue<B>, 256)), 256, 0, stream>>>(b, q, cnt);
    }
    void runQueue(const ShadeHitBody &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
       if (bound == 0) return;
       Scope sc_(this);
-      kRunQueueHeavy<ShadeHitBody><<<gridFor(bound, 128, 8), 128, 0, stream>>>(b, q, cnt);
+      kRunQueueHeavy<ShadeHitBody><<<gridFor(bound, 128, resident(kRunQueueHeavy<ShadeHitBody>, 128)), 128, 0, stream>>>(b, q, cnt);
    }
    void runQueue(const ResolveMisBody &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
       if (bound == 0) return;
       Scope sc_(this);
-      kRunQueueHeavy<ResolveMisBody><<<gridFor(bound, 128, 8), 128, 0, stream>>>(b, q, cnt);
+      kRunQueueHeavy<ResolveMisBody><<<gridFor(bound, 128, resident(kRunQueueHeavy<ResolveMisBody>, 128)), 128, 0, stream>>>(b, q, cnt);
    }
    void traceNearest(const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc, const F4 *o, const F4 *d, F4 *hit) {
       if (!n) return;

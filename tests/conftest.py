@@ -95,3 +95,19 @@ def has_gpu():
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+def stripped(scene, prims=True, lights=False):
+    """edge-case scenes: the same camera/film with no primitives and/or no lights."""
+    import copy
+    out = copy.copy(scene)
+    if prims:
+        out.tri_verts = np.zeros((0, 9), np.float32); out.tri_uvs = np.zeros((0, 6), np.float32)
+        out.tri_material = np.zeros((0,), np.int32); out.tri_normals = None; out.tri_prim_id = None
+        out.shapes = []
+        out.lights = [l for l in scene.lights if l.kind != IR.LIGHT_AREA]
+    if lights:
+        out.lights = []
+        for sh in out.shapes:
+            sh.light = -1
+    return out

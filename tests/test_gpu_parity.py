@@ -105,6 +105,25 @@ def test_film_matches_oracle(ctx, name):
     assert sg["kernel_launches"] > 0
 
 
+def test_edge_scenes_empty_and_unlit(ctx):
+    """no primitives / no lights / one-ray and odd-sized batches through the C ABI."""
+    from tests.conftest import stripped
+    base = small(load_scene("envcam"), 24, 12, 2, 2)
+    for sc, lit in ((stripped(base), True), (stripped(base, prims=False, lights=True), False)):
+        ctx.upload_scene(sc); ctx.reset_stats()
+        ctx.render_pass(1, 3)
+        o = Oracle(sc); o.render_pass(1, 3, threads=2)
+        fg, fo = ctx.read_film(), o.read_film()
+        assert np.isfinite(fg).all() and np.abs(fo - fg).max() <= 1e-3 * max(1.0, np.abs(fo).max())
+        assert (fg[..., 1:].sum() > 0) == lit
+        rays = random_rays(load_scene("envcam"), 33, 1)
+        if not len(sc.shapes):
+            assert (ctx.trace_nearest(rays)["prim"] == -1).all() and not ctx.trace_occluded(rays).any()
+        else:
+            assert np.array_equal(ctx.trace_nearest(rays)["prim"], o.trace_nearest(rays, "brute")["prim"])
+            assert len(ctx.trace_nearest(rays[:1])) == 1
+
+
 def rel_mse(a, b):
     return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-3)))
 

@@ -114,6 +114,23 @@ def test_slices_and_batches_compose():
     b.film_add_host(fa); assert np.array_equal(b.read_film(), fa)
 
 
+def test_edge_scenes_empty_and_unlit():
+    """no primitives (every ray escapes to the environment) and no lights (black film, no NEE rays)."""
+    from tests.conftest import stripped
+    base = small(load_scene("envcam"), 24, 12, 2, 2)
+    for sc, lit in ((stripped(base), True), (stripped(base, prims=False, lights=True), False)):
+        o = Oracle(sc); e = EmuContext(); e.upload_scene(sc)
+        o.render_pass(1, 3, threads=2); e.render_pass(1, 3)
+        fo, fe = o.read_film(), e.read_film()
+        assert np.isfinite(fe).all() and np.abs(fo - fe).max() <= 2e-5 * max(1.0, np.abs(fo).max())
+        assert (fe[..., 1:].sum() > 0) == lit
+        so, se = o.stats(), e.stats()
+        assert so["samples"] == se["samples"] and se["rays_shadow"] == so["rays_shadow"]
+        rays = random_rays(load_scene("envcam"), 100, 1)
+        if not len(sc.shapes):
+            assert (e.trace_nearest(rays)["prim"] == -1).all() and not e.trace_occluded(rays).any()
+
+
 def test_api_error_paths():
     e = EmuContext()
     with pytest.raises(api.BlingCuError) as ex:
