@@ -143,7 +143,9 @@ struct ShadeMissBody {   // Path.hs:43-47
 };
 
 // ------------------------------------------------------------------------------------------ K5 shade (hit)
-struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118
+template <int MATKIND>
+struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118; one instantiation per material kind (material-sorted queues)
+   typedef MatOf<MATKIND> M;
    const DScene *sc; PathState ps; uint32_t *qNext;
    HD void operator()(uint32_t i) const {
       const DScene &S = *sc;
@@ -154,15 +156,17 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118
       Sampler smp = mkSampler(S, ps.kp[i], ps.sidx[i]);
       SurfaceHit sh; DG dgs;
       surfaceAt(S, ray, hv.x, hv.y, hv.z, f2i(hv.w), sh, dgs);
-      Bsdf bsdf; makeBsdf(S, sh, dgs, bsdf);
-      Spec T = loadSpec4(ps.T, ps.cap, i);
+      Bsdf bsdf; makeBsdf<M>(S, sh, dgs, bsdf);
+      // T (16 registers) is re-read from L1/L2 at each use instead of being kept live across the whole body: the
+      // kernel is register-bound (occupancy), not bandwidth-bound
+#define BL_T() loadSpec4(ps.T, ps.cap, i)
       V3 rd = ray.d, wo = -rd;
       // emitted light, only after specular bounces / from the camera; Q1: tested against the RAY direction
       if (spec && sh.light >= 0) {
          const blingcu_light &el = S.lights[sh.light];
          if (el.kind == BLINGCU_LIGHT_AREA && areaEmits(sh.dgg.n, rd)) {
             Spec L = loadSpec4(ps.L, ps.cap, i);
-            storeSpec4(ps.L, ps.cap, i, L + T * loadSpec(el.s.v));
+            storeSpec4(ps.L, ps.cap, i, L + BL_T() * loadSpec(el.s.v));
          }
       }
       V3 n = bsdf.cs.n, p = bsdf.p; float eps = sh.eps;
@@ -178,12 +182,12 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118
          {   // sampleLightMis (Scene.hs:61-69)
             LightSample ls; lightSample(S, lt, p, eps, n, lD1, lD2, ls);
             if (ls.pdf != 0 && !isBlack(ls.de)) {
-               Spec f = evalBsdf(bsdf, wo, ls.wi);
+               Spec f = evalBsdf<M>(bsdf, wo, ls.wi);
                if (!isBlack(f)) {
-                  float w = ls.delta ? 1 / ls.pdf : powerHeuristic(ls.pdf, bsdfPdf(bsdf, wo, ls.wi)) / ls.pdf;
+                  float w = ls.delta ? 1 / ls.pdf : powerHeuristic(ls.pdf, bsdfPdf<M>(bsdf, wo, ls.wi)) / ls.pdf;
                   Spec c = sScale(f * ls.de, w);
                   if (lc > 1) c = sScale(c, lcf);
-                  storeSpec4(ps.PS, ps.cap, i, T * c);
+                  storeSpec4(ps.PS, ps.cap, i, BL_T() * c);
                   storeRay(ps.shO, ps.shD, i, ls.testRay);
                   qPush(ps.qShadow, ps.counters + C_SHADOW, i);
                }
@@ -195,7 +199,7 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118
             //   infinite light  -> only hit/miss matters: any-hit query (qMisAny);
             //   area light      -> a ray that does not even reach the light's own shape contributes nothing: culled;
             //   delta lights    -> never hit, `le` is black: culled.
-            BsdfSample bs; sampleBsdf(bsdf, wo, bCompU, bD1, bD2, bs);
+            BsdfSample bs; sampleBsdf<M>(bsdf, wo, bCompU, bD1, bD2, bs);
             if (bs.pdf != 0 && !isBlack(bs.f)) {
                Ray mr; mr.o = p; mr.d = bs.wi; mr.tmin = eps; mr.tmax = BL_INF;
                bool any = lt.kind == BLINGCU_LIGHT_INFINITE, keep = any;
@@ -207,7 +211,7 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118
                if (keep) {
                   Spec c = bs.f;
                   if (lc > 1) c = sScale(c, lcf);
-                  storeSpec4(ps.PM, ps.cap, i, T * c);
+                  storeSpec4(ps.PM, ps.cap, i, BL_T() * c);
                   storeRay(ps.miO, ps.miD, i, mr);
                   F2 info; info.x = bs.pdf; info.y = i2f(ln); ps.miInfo[i] = info;
                   if (any) qPush(ps.qMisAny, ps.counters + C_MISANY, i);
@@ -217,18 +221,19 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118
          }
       }
       // Russian roulette (Path.hs:68-72)
-      float pc = (depth <= 7) ? 1.0f : hminf(0.75f, sY(S, T));
+      float pc = (depth <= 7) ? 1.0f : hminf(0.75f, sY(S, BL_T()));
       float x = rnd1D(smp, 3 + 4 * depth);
       if (x > pc) return;
       float uc = rnd1D(smp, 0 + 4 * depth);
       float ud1, ud2; rnd2D(smp, 0 + 3 * depth, ud1, ud2);
-      BsdfSample s; sampleBsdf(bsdf, wo, uc, ud1, ud2, s);
+      BsdfSample s; sampleBsdf<M>(bsdf, wo, uc, ud1, ud2, s);
       if (s.pdf == 0 || isBlack(s.f)) return;
       Ray nr; nr.o = p; nr.d = s.wi; nr.tmin = eps; nr.tmax = BL_INF;
       storeRay(ps.rayO, ps.rayD, i, nr);
-      storeSpec4(ps.T, ps.cap, i, sScale(s.f * T, 1 / pc));   // Path.hs:82: no pdf / cosine factor, the weight carries them
+      storeSpec4(ps.T, ps.cap, i, sScale(s.f * BL_T(), 1 / pc));   // Path.hs:82: no pdf / cosine factor, the weight carries them
       ps.meta[i] = (uint32_t)(depth + 1) | (((s.type & BX_SPECULAR) ? 1u : 0u) << 8);
       qPush(qNext, ps.counters + C_NEXT, i);
+#undef BL_T
    }
 };
 
@@ -330,14 +335,18 @@ struct FilmBody {
       int x = (int)(fp % (uint32_t)S.W), y = (int)(fp / (uint32_t)S.W);
       float fw = S.fw, fh = S.fh;
       float ifw = 1 / fw, ifh = 1 / fw;   // Q10
-      int rx = (int)ceilf(fw + 0.5f) + 1, ry = (int)ceilf(fh + 0.5f) + 1;
+      // sample pixels whose samples can reach this film pixel: a sample of pixel ix sits at dx = ix + o - 0.5 with
+      // o in [0,1] (the sum may round up to ix + 1), and covers x iff ceil(dx - fw) <= x <= floor(dx + fw)
+      //   => ix in [ceil(x - fw - 0.5), floor(x + fw + 0.5)]   (5x5 pixels for a radius-2 filter, not 9x9)
+      int ixlo = (int)ceilf((float)x - fw - 0.5f), ixhi = (int)floorf((float)x + fw + 0.5f);
+      int iylo = (int)ceilf((float)y - fh - 0.5f), iyhi = (int)floorf((float)y + fh + 0.5f);
       int extx = (int)floorf(0.5f + fw), exty = (int)floorf(0.5f + fh);
       float aw = 0, ax = 0, ay = 0, az = 0;
-      for (int iy = imax(S.ey0, y - ry); iy <= imin(S.ey1, y + ry); ++iy) {
+      for (int iy = imax(S.ey0, iylo); iy <= imin(S.ey1, iyhi); ++iy) {
          int ty0 = S.ey0 + ((iy - S.ey0) >> 4) * 16, ty1 = imin(ty0 + 15, S.ey1);
          int toy = imax(0, ty0), tymax = ty1 + exty - 1;
          if (y < toy || y > tymax) continue;
-         for (int ix = imax(S.ex0, x - rx); ix <= imin(S.ex1, x + rx); ++ix) {
+         for (int ix = imax(S.ex0, ixlo); ix <= imin(S.ex1, ixhi); ++ix) {
             int tx0 = S.ex0 + ((ix - S.ex0) >> 4) * 16, tx1 = imin(tx0 + 15, S.ex1);
             int tox = imax(0, tx0), txmax = tx1 + extx - 1;
             if (x < tox || x > txmax) continue;

@@ -152,10 +152,10 @@ struct CudaBackend {
       Scope sc_(this);
       kRunQueue<B><<<gridFor(bound, 256, resident(kRunQueue<B>, 256)), 256, 0, stream>>>(b, q, cnt);
    }
-   void runQueue(const ShadeHitBody &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
+   template <int MK> void runQueue(const ShadeHitBody<MK> &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
       if (bound == 0) return;
       Scope sc_(this);
-      kRunQueueHeavy<ShadeHitBody><<<gridFor(bound, 128, resident(kRunQueueHeavy<ShadeHitBody>, 128)), 128, 0, stream>>>(b, q, cnt);
+      kRunQueueHeavy<ShadeHitBody<MK>><<<gridFor(bound, 128, resident(kRunQueueHeavy<ShadeHitBody<MK>>, 128)), 128, 0, stream>>>(b, q, cnt);
    }
    void runQueue(const ResolveMisBody &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
       if (bound == 0) return;

@@ -222,7 +222,15 @@ struct Pipeline {
          if (d < hs.max_depth) {
             for (int k = 1; k < N_SHADE_KINDS; ++k) {
                if (!kindPresent[k]) continue;
-               be.runQueue(ShadeHitBody{dscene, ps, qb}, ps.qMat + (size_t)k * cap, ps.counters + C_MAT0 + k, bound);
+               const uint32_t *qk = ps.qMat + (size_t)k * cap; const uint32_t *ck = ps.counters + C_MAT0 + k;
+               switch (k - 1) {   // one instantiation of the shade kernel per material kind
+               case BLINGCU_MAT_MATTE: be.runQueue(ShadeHitBody<BLINGCU_MAT_MATTE>{dscene, ps, qb}, qk, ck, bound); break;
+               case BLINGCU_MAT_GLASS: be.runQueue(ShadeHitBody<BLINGCU_MAT_GLASS>{dscene, ps, qb}, qk, ck, bound); break;
+               case BLINGCU_MAT_MIRROR: be.runQueue(ShadeHitBody<BLINGCU_MAT_MIRROR>{dscene, ps, qb}, qk, ck, bound); break;
+               case BLINGCU_MAT_PLASTIC: be.runQueue(ShadeHitBody<BLINGCU_MAT_PLASTIC>{dscene, ps, qb}, qk, ck, bound); break;
+               case BLINGCU_MAT_METAL: be.runQueue(ShadeHitBody<BLINGCU_MAT_METAL>{dscene, ps, qb}, qk, ck, bound); break;
+               default: be.runQueue(ShadeHitBody<BLINGCU_MAT_BLACKBODY>{dscene, ps, qb}, qk, ck, bound); break;
+               }
                launches++;
             }
             be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl);

@@ -152,6 +152,19 @@ enum { BX_REFLECTION = 1, BX_TRANSMISSION = 2, BX_DIFFUSE = 4, BX_GLOSSY = 8, BX
 enum { K_LAMBERT = 0, K_ORENNAYAR, K_SPECREFL, K_SPECTRANS, K_MICROFACET };
 enum { FR_NOOP = 0, FR_DIELECTRIC, FR_CONDUCTOR };
 
+// Compile-time description of what a material can contain. The shade kernel is launched once per material KIND
+// (material-sorted queues), so each launch is instantiated for its kind and the BxDF code of every other kind drops
+// out (fewer registers, more resident warps). AnyMat keeps everything (resolve kernels, generic callers).
+struct AnyMat { static const unsigned KM = 0x1fu, FM = 0x7u; static const int NC = 2, MK = -1; };
+template <int MATKIND> struct MatOf : AnyMat {};
+#define BL_K(k) (1u << (k))
+template <> struct MatOf<BLINGCU_MAT_MATTE> { static const unsigned KM = BL_K(0) | BL_K(1), FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_MATTE; };
+template <> struct MatOf<BLINGCU_MAT_GLASS> { static const unsigned KM = BL_K(2) | BL_K(3), FM = BL_K(1); static const int NC = 2, MK = BLINGCU_MAT_GLASS; };
+template <> struct MatOf<BLINGCU_MAT_MIRROR> { static const unsigned KM = BL_K(2), FM = BL_K(0); static const int NC = 1, MK = BLINGCU_MAT_MIRROR; };
+template <> struct MatOf<BLINGCU_MAT_PLASTIC> { static const unsigned KM = BL_K(0) | BL_K(4), FM = BL_K(1); static const int NC = 2, MK = BLINGCU_MAT_PLASTIC; };
+template <> struct MatOf<BLINGCU_MAT_METAL> { static const unsigned KM = BL_K(4), FM = BL_K(2); static const int NC = 1, MK = BLINGCU_MAT_METAL; };
+template <> struct MatOf<BLINGCU_MAT_BLACKBODY> { static const unsigned KM = 0u, FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_BLACKBODY; };
+
 struct BxDF {
    int kind, type, fr, clamp01;   // clamp01: sClamp' applied to r on read (glass, mirror; Material.hs:63-64,71)
    const float *r;                // reflectance / transmittance spectrum; null = white
@@ -161,10 +174,11 @@ struct BxDF {
 HD float bxR(const BxDF &b, int i) { float v = b.r ? b.r[i] : 1.0f; return b.clamp01 ? hmaxf(0.0f, hminf(1.0f, v)) : v; }
 HD Spec bxScaledR(const BxDF &b, float f) { Spec s; BL_UNROLL for (int i = 0; i < NB; ++i) s.v[i] = bxR(b, i) * f; return s; }
 // r * fr(cosi) (spectral product, then the caller scales)
+template <class M = AnyMat>
 HD Spec bxRFresnel(const BxDF &b, float cosi) {
    Spec s;
-   if (b.fr == FR_CONDUCTOR) { float ac = fabsf(cosi); BL_UNROLL for (int i = 0; i < NB; ++i) s.v[i] = bxR(b, i) * frConductorBand(b.eta[i], b.k[i], ac); }
-   else { float f = (b.fr == FR_DIELECTRIC) ? frDielectric(b.etai, b.etat, cosi) : 1.0f; BL_UNROLL for (int i = 0; i < NB; ++i) s.v[i] = bxR(b, i) * f; }
+   if ((M::FM & BL_K(FR_CONDUCTOR)) && b.fr == FR_CONDUCTOR) { float ac = fabsf(cosi); BL_UNROLL for (int i = 0; i < NB; ++i) s.v[i] = bxR(b, i) * frConductorBand(b.eta[i], b.k[i], ac); }
+   else { float f = ((M::FM & BL_K(FR_DIELECTRIC)) && b.fr == FR_DIELECTRIC) ? frDielectric(b.etai, b.etat, cosi) : 1.0f; BL_UNROLL for (int i = 0; i < NB; ++i) s.v[i] = bxR(b, i) * f; }
    return s;
 }
 HD float mfG(V3 wo, V3 wi, V3 wh) {   // Microfacet.hs:113-120
@@ -181,11 +195,11 @@ HD float orenNayarF(const BxDF &b, V3 wo, V3 wi) {   // Diffuse.hs:52-65 (scalar
    return b.a + b.b * maxcos * sina * tanb;
 }
 // bxdfEval b wo wi -- callers pass flipped arguments for the non-adjoint case (Reflection.hs:310,330)
+template <class M = AnyMat>
 HD Spec bxdfEval(const BxDF &b, V3 wo, V3 wi) {
-   switch (b.kind) {
-   case K_LAMBERT: return bxScaledR(b, BL_INVPI * absCosTheta(wo));
-   case K_ORENNAYAR: return sScale(bxScaledR(b, orenNayarF(b, wo, wi)), BL_INVPI * absCosTheta(wo));
-   case K_MICROFACET: {   // Microfacet.hs:20-33
+   if ((M::KM & BL_K(K_LAMBERT)) && b.kind == K_LAMBERT) return bxScaledR(b, BL_INVPI * absCosTheta(wo));
+   if ((M::KM & BL_K(K_ORENNAYAR)) && b.kind == K_ORENNAYAR) return sScale(bxScaledR(b, orenNayarF(b, wo, wi)), BL_INVPI * absCosTheta(wo));
+   if ((M::KM & BL_K(K_MICROFACET)) && b.kind == K_MICROFACET) {   // Microfacet.hs:20-33
       float costo = absCosTheta(wo), costi = absCosTheta(wi);
       if (costi == 0 || costo == 0) return sConst(0);
       V3 whp = wi + wo;
@@ -194,15 +208,15 @@ HD Spec bxdfEval(const BxDF &b, V3 wo, V3 wi) {
       if (cosTheta(wh) < 0) return sConst(0);
       float costh = dot3(wi, wh);
       float x = (b.e + 2) * BL_INVTWOPI * powf(absCosTheta(wh), b.e) * mfG(wo, wi, wh) / (4 * costi);
-      return sScale(bxRFresnel(b, costh), x);
+      return sScale(bxRFresnel<M>(b, costh), x);
    }
-   default: return sConst(0);
-   }
+   return sConst(0);
 }
 HD float cosPdf(V3 wo, V3 wi) { return sameHemisphere(wo, wi) ? BL_INVPI * absCosTheta(wi) : 0.0f; }
+template <class M = AnyMat>
 HD float bxdfPdf(const BxDF &b, V3 wo, V3 wi) {
-   if (b.kind == K_LAMBERT || b.kind == K_ORENNAYAR) return cosPdf(wo, wi);
-   if (b.kind == K_MICROFACET) {   // Microfacet.hs:35-41
+   if ((M::KM & (BL_K(K_LAMBERT) | BL_K(K_ORENNAYAR))) && (b.kind == K_LAMBERT || b.kind == K_ORENNAYAR)) return cosPdf(wo, wi);
+   if ((M::KM & BL_K(K_MICROFACET)) && b.kind == K_MICROFACET) {   // Microfacet.hs:35-41
       V3 whp = wo + wi;
       if (sqLen(whp) == 0) return 0;
       V3 wh = normalize3(whp);
@@ -211,16 +225,16 @@ HD float bxdfPdf(const BxDF &b, V3 wo, V3 wi) {
    }
    return 0;
 }
+template <class M = AnyMat>
 HD void bxdfSample(const BxDF &b, V3 wo, float u1, float u2, Spec &f, V3 &wi, float &pdf) {   // adj = False
-   switch (b.kind) {
-   case K_LAMBERT: case K_ORENNAYAR: {   // Diffuse.hs:14-22,38-42
+   if ((M::KM & (BL_K(K_LAMBERT) | BL_K(K_ORENNAYAR))) && (b.kind == K_LAMBERT || b.kind == K_ORENNAYAR)) {   // Diffuse.hs:14-22,38-42
       wi = toSameHemisphere(wo, cosineSampleHemisphere(u1, u2));
       if (sameHemisphere(wo, wi)) { f = bxScaledR(b, b.kind == K_LAMBERT ? 1.0f : orenNayarF(b, wo, wi)); pdf = cosPdf(wo, wi); }
       else { f = sConst(0); pdf = 0; }
       return;
    }
-   case K_SPECREFL: f = bxRFresnel(b, cosTheta(wo)); wi = mk3(-wo.x, -wo.y, wo.z); pdf = 1; return;   // Specular.hs:11-20
-   case K_SPECTRANS: {   // Specular.hs:34-57
+   if ((M::KM & BL_K(K_SPECREFL)) && b.kind == K_SPECREFL) { f = bxRFresnel<M>(b, cosTheta(wo)); wi = mk3(-wo.x, -wo.y, wo.z); pdf = 1; return; }   // Specular.hs:11-20
+   if ((M::KM & BL_K(K_SPECTRANS)) && b.kind == K_SPECTRANS) {   // Specular.hs:34-57
       bool entering = cosTheta(wo) > 0;
       float ei = entering ? b.etai : b.etat, et = entering ? b.etat : b.etai;
       float eta = ei / et, eta2 = eta * eta, sint2 = eta2 * sinTheta2(wo);
@@ -233,7 +247,7 @@ HD void bxdfSample(const BxDF &b, V3 wo, float u1, float u2, Spec &f, V3 &wi, fl
       pdf = 1;
       return;
    }
-   default: {   // microfacet, Blinn (Microfacet.hs:43-54,175-182)
+   if (M::KM & BL_K(K_MICROFACET)) {   // microfacet, Blinn (Microfacet.hs:43-54,175-182)
       float cost = powf(u1, 1 / (b.e + 1));
       float sint = sqrtf(hmaxf(0, 1 - cost * cost));
       V3 whp = sphericalDirection(sint, cost, u2 * 2 * BL_PI);
@@ -244,11 +258,11 @@ HD void bxdfSample(const BxDF &b, V3 wo, float u1, float u2, Spec &f, V3 &wi, fl
       wi = scl(2 * costH, wh) - wo;
       if (!sameHemisphere(wo, wi)) { f = sConst(0); wi = wo; pdf = 0; return; }
       float fact = d * fabsf(costH) / dpdf * mfG(wo, wi, wh);
-      f = sScale(bxRFresnel(b, costH), fact / absCosTheta(wi));   // Q7
+      f = sScale(bxRFresnel<M>(b, costH), fact / absCosTheta(wi));   // Q7
       pdf = dpdf / (4 * fabsf(costH));
       return;
    }
-   }
+   f = sConst(0); wi = wo; pdf = 0;
 }
 
 struct Bsdf { int n; BxDF bx[2]; Frame cs; V3 p, ng; };
@@ -257,16 +271,17 @@ struct BsdfSample { int type; float pdf; Spec f; V3 wi; };
 HD bool bxMatch(const BxDF &b, bool wantTrans) { return (b.type & (wantTrans ? BX_TRANSMISSION : BX_REFLECTION)) != 0; }
 
 // Reflection.hs:278-316, adj = False, flags = bxdfAll
+template <class M = AnyMat>
 HD void sampleBsdf(const Bsdf &bsdf, V3 woW, float uComp, float u1, float u2, BsdfSample &out) {
    out.type = BX_REFLECTION | BX_DIFFUSE; out.pdf = 0; out.f = sConst(0); out.wi = mk3(0, 1, 0);
-   int cntm = bsdf.n;
-   if (cntm == 0) return;
+   const int cntm = (M::NC == 1) ? imin(bsdf.n, 1) : bsdf.n;
+   if (M::KM == 0u || cntm == 0) return;
    V3 wo = worldToLocal(bsdf.cs, woW);
    float cntf = (float)cntm, invCnt = 1 / cntf;
-   int sNum = imax(0, imin(cntm - 1, (int)floorf(uComp * cntf)));
+   const int sNum = (M::NC == 1) ? 0 : imax(0, imin(cntm - 1, (int)floorf(uComp * cntf)));
    const BxDF &bx = bsdf.bx[sNum];
    Spec fS; V3 wi = mk3(0, 1, 0); float pdfp = 0;
-   bxdfSample(bx, wo, u1, u2, fS, wi, pdfp);
+   bxdfSample<M>(bx, wo, u1, u2, fS, wi, pdfp);
    V3 wiW = localToWorld(bsdf.cs, wi);
    float sideTest = dot3(wiW, bsdf.ng) / dot3(woW, bsdf.ng);
    if (pdfp == 0 || sideTest == 0) return;
@@ -274,15 +289,17 @@ HD void sampleBsdf(const Bsdf &bsdf, V3 woW, float uComp, float u1, float u2, Bs
    if (!bxMatch(bx, wantTrans)) return;
    out.type = bx.type; out.wi = wiW;
    if (bx.type & BX_SPECULAR) { out.pdf = pdfp * invCnt; out.f = sScale(fS, cntf); return; }
-   if (cntm == 1) { out.pdf = pdfp; out.f = fS; return; }
+   if (M::NC == 1 || cntm == 1) { out.pdf = pdfp; out.f = fS; return; }
    const BxDF &o = bsdf.bx[1 - sNum];
-   float pdf = (pdfp + bxdfPdf(o, wo, wi)) * invCnt;
+   float pdf = (pdfp + bxdfPdf<M>(o, wo, wi)) * invCnt;
    Spec fOthers = sConst(0);
-   if (bxMatch(o, wantTrans)) fOthers = fOthers + bxdfEval(o, wi, wo);
+   if (bxMatch(o, wantTrans)) fOthers = fOthers + bxdfEval<M>(o, wi, wo);
    out.pdf = pdf; out.f = sScale(sScale(fS, pdfp) + fOthers, 1 / pdf);
 }
 // Reflection.hs:318-332, adj = False
+template <class M = AnyMat>
 HD Spec evalBsdf(const Bsdf &bsdf, V3 woW, V3 wiW) {
+   if (M::KM == 0u) return sConst(0);
    float cosWo = dot3(woW, bsdf.ng);
    float sideTest = dot3(wiW, bsdf.ng) / cosWo;
    if (sideTest == 0) return sConst(0);
@@ -290,14 +307,15 @@ HD Spec evalBsdf(const Bsdf &bsdf, V3 woW, V3 wiW) {
    bool wantTrans = sideTest < 0;
    V3 wo = worldToLocal(bsdf.cs, woW), wi = worldToLocal(bsdf.cs, wiW);
    Spec f = sConst(0);
-   for (int i = 0; i < bsdf.n; ++i) if (bxMatch(bsdf.bx[i], wantTrans)) f = f + bxdfEval(bsdf.bx[i], wi, wo);
+   BL_UNROLL for (int i = 0; i < M::NC; ++i) if (i < bsdf.n && bxMatch(bsdf.bx[i], wantTrans)) f = f + bxdfEval<M>(bsdf.bx[i], wi, wo);
    return f;
 }
+template <class M = AnyMat>
 HD float bsdfPdf(const Bsdf &bsdf, V3 woW, V3 wiW) {   // Reflection.hs:251-257 (Q6)
-   if (bsdf.n == 0) return 0;
+   if (M::KM == 0u || bsdf.n == 0) return 0;
    V3 wo = worldToLocal(bsdf.cs, woW), wi = worldToLocal(bsdf.cs, wiW);
    float s = 0;
-   for (int i = 0; i < bsdf.n; ++i) s = s + bxdfPdf(bsdf.bx[i], wo, wi);
+   BL_UNROLL for (int i = 0; i < M::NC; ++i) if (i < bsdf.n) s = s + bxdfPdf<M>(bsdf.bx[i], wo, wi);
    return s / (float)bsdf.n;
 }
 
@@ -355,11 +373,13 @@ HD void surfaceAt(const DScene &sc, const Ray &ray, float t, float b1, float b2,
 }
 
 // Material.hs:32-96 + mkBsdf' (Reflection.hs:209-225)
+template <class M = AnyMat>
 HD void makeBsdf(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b) {
    const blingcu_material &m = sc.materials[sh.material];
+   const int mk = (M::MK >= 0) ? M::MK : m.kind;   // compile-time constant in the per-kind shade kernels
    b.n = 0;
-   for (int i = 0; i < 2; ++i) { BxDF &x = b.bx[i]; x.kind = 0; x.type = 0; x.fr = FR_NOOP; x.clamp01 = 0; x.r = 0; x.eta = 0; x.k = 0; x.a = x.b = x.e = 0; x.etai = x.etat = 1; }
-   switch (m.kind) {
+   BL_UNROLL for (int i = 0; i < 2; ++i) { BxDF &x = b.bx[i]; x.kind = 0; x.type = 0; x.fr = FR_NOOP; x.clamp01 = 0; x.r = 0; x.eta = 0; x.k = 0; x.a = x.b = x.e = 0; x.etai = x.etat = 1; }
+   switch (mk) {
    case BLINGCU_MAT_MATTE: {
       BxDF &x = b.bx[0]; x.r = evalSpectrumTexture(sc, m.tex[0], dgs); x.type = BX_REFLECTION | BX_DIFFUSE;
       float s = m.f[0];

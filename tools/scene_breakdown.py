@@ -1,0 +1,21 @@
+#!/usr/bin/env python
+"""Per-kernel-class device time of one timed slice of each named scene (BASELINE.json configs[0..3]) at config size."""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from bling_b200 import api, ir as IR
+
+names = sys.argv[1:] or ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"]
+for name in names:
+    sc = IR.SceneIR.load(ROOT / "tests" / "golden" / "scenes" / f"{name}.npz")
+    c = api.Context(0); c.upload_scene(sc)
+    ex = c.sample_extent(); npx = (ex[1] - ex[0] + 1) * (ex[3] - ex[2] + 1)
+    k = max(1, min(sc.spp // 2, int(48e6 // npx)))
+    c.render_slice(1, 1, 0, k); c.synchronize(); c.reset_stats(); c.set_option("profile_kernels", 1)
+    c.render_slice(1, 1, k, 2 * k); c.synchronize()
+    kt = c.kernel_times(); st = c.stats()
+    tot = sum(v[0] for v in kt.values())
+    print(f"{name:12s} {st['samples'] / st['last_pass_ms'] / 1e3:7.1f} Msamples/s  pass {st['last_pass_ms']:7.1f} ms  launches {st['kernel_launches']:4d}  " +
+          "  ".join(f"{k_}:{100 * v[0] / tot:4.1f}%" for k_, v in kt.items()), flush=True)
+    c.close()
