@@ -9,7 +9,7 @@
 //   F4[0] = (P.x P.y P.z  E)      grid origin (f32) and the three grid exponents packed as biased float exponents
 //                                  (E = ex | ey << 8 | ez << 16, cell size 2^(e-127) per axis)
 //   F4[1] = child refs [0..3]      ref >= 0: node index. ref < 0: leaf, ~ref = (first_item << 4) | count
-//   F4[2] = (qlo.x qlo.y qlo.z qhi.x), F4[3] = (qhi.y qhi.z - -)   each word packs the byte of the four children
+//   F4[2] = (qlo.x qlo.y qlo.z qhi.x), F4[3] = (qhi.y qhi.z 0x4B000000 -)   each q word packs the byte of the four children
 // Dequantised plane = P + cell * q. The ray/plane distance is ONE fma per plane: q_as_float * (cell/d) + (P/d - o/d),
 // with q_as_float built by a byte permute into the mantissa of 2^23 (bits 0x4B000000 | q) and the 2^23 folded into
 // the addend; that folding costs up to half a cell of accuracy, so the builder rounds every bound outwards by one
@@ -83,14 +83,20 @@ HD uint32_t f2u(float f) { return (uint32_t)f2i(f); }
 HD float u2f(uint32_t u) { return i2f((int)u); }
 // float with bits 0x4B000000 | byte k of w  ==  2^23 + q   (one PRMT on the device)
 #if defined(__CUDA_ARCH__)
-#define BL_QF(w, k) __uint_as_float(__byte_perm((w), 0x4B000000u, 0x7650u + (k)))
+// the 2^23 pattern comes from the node itself (word F4[3].z, written by the builder) so that it sits in a register and
+// the byte selector can be the PRMT's immediate; as a literal it would take the immediate slot and every PRMT would
+// need a MOV of its selector first
+#define BL_QF(w, k) __uint_as_float(__byte_perm((w), bl_k23, 0x7650u + (k)))
 #else
 #define BL_QF(w, k) u2f(0x4B000000u | (((w) >> (8 * (k))) & 0xffu))
 #endif
 
-// slab test of the four children of one quantised node against [r.tmin, r.tmax]. Returns the sort keys:
-// hit -> (bits(tnear) & ~3) | slot  (tnear >= tmin >= 0, so unsigned order == distance order), miss -> 0xffffffff.
-HD void node4Keys(const F4 &n0, const F4 &n2, const F4 &n3, const Ray &r, const RayPre &p, uint32_t key[4]) {
+// slab test of the four children of one quantised node against [r.tmin, r.tmax]: tn[k] = entry distance of child k,
+// +inf when the ray misses it.
+HD void node4Near(const F4 &n0, const F4 &n2, const F4 &n3, const Ray &r, const RayPre &p, float tnear[4]) {
+#if defined(__CUDA_ARCH__)
+   const uint32_t bl_k23 = f2u(n3.z);   // 0x4B000000
+#endif
    const uint32_t E = f2u(n0.w);
    const float ax = u2f((E & 0xffu) << 23) * p.idir.x, ay = u2f(((E >> 8) & 0xffu) << 23) * p.idir.y, az = u2f(((E >> 16) & 0xffu) << 23) * p.idir.z;
    // addend: P/d - o/d - 2^23 * cell/d
@@ -103,17 +109,22 @@ HD void node4Keys(const F4 &n0, const F4 &n2, const F4 &n3, const Ray &r, const 
    BL_UNROLL for (int k = 0; k < 4; ++k) {
       float tn = fmaxf(fmaxf(BL_FMA(BL_QF(nx, k), ax, bx), BL_FMA(BL_QF(ny, k), ay, by)), fmaxf(BL_FMA(BL_QF(nz, k), az, bz), r.tmin));
       float tf = fminf(fminf(BL_FMA(BL_QF(fx, k), ax, bx), BL_FMA(BL_QF(fy, k), ay, by)), fminf(BL_FMA(BL_QF(fz, k), az, bz), r.tmax));
-      key[k] = (tn <= tf) ? ((f2u(tn) & ~3u) | (uint32_t)k) : 0xffffffffu;
+      tnear[k] = (tn <= tf) ? tn : BL_INF;
    }
 }
-HD uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
-HD uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
-HD void sort4(uint32_t k[4]) {   // 5-comparator network, ascending
-   uint32_t a = umin32(k[0], k[1]), b = umax32(k[0], k[1]), c = umin32(k[2], k[3]), d = umax32(k[2], k[3]);
-   uint32_t lo = umin32(a, c), m1 = umax32(a, c), m2 = umin32(b, d), hi = umax32(b, d);
-   k[0] = lo; k[1] = umin32(m1, m2); k[2] = umax32(m1, m2); k[3] = hi;
+// sort the four (entry distance, child reference) pairs by distance: 5 compare-exchanges, each one compare + four
+// selects (no key packing, no indexed pick afterwards). Misses carry +inf and end up last. On equal distances the
+// lower slot stays first; every traversal variant uses this same network, so they all visit nodes in the same order.
+HD void cswap(float &ta, int &ra, float &tb, int &rb) {
+   const bool p = tb < ta;
+   const float t0 = p ? tb : ta, t1 = p ? ta : tb; const int r0 = p ? rb : ra, r1 = p ? ra : rb;
+   ta = t0; tb = t1; ra = r0; rb = r1;
 }
-HD int pick4(const int c[4], uint32_t slot) { return slot == 0 ? c[0] : (slot == 1 ? c[1] : (slot == 2 ? c[2] : c[3])); }
+HD void sort4(float t[4], int c[4]) {
+   cswap(t[0], c[0], t[1], c[1]); cswap(t[2], c[2], t[3], c[3]);
+   cswap(t[0], c[0], t[2], c[2]); cswap(t[1], c[1], t[3], c[3]);
+   cswap(t[1], c[1], t[2], c[2]);
+}
 
 // nearest hit (Primitive.intersect). STATS counts node fetches / primitive tests like dbgTraverse (KdTree.hs:260-281).
 // Children are entered nearest-first; every variant of the traversal kernel follows this same order.
@@ -128,14 +139,14 @@ HD HitRec traceNearest(const Bvh &bvh, Ray r, uint32_t *nNodes, uint32_t *nPrims
       if (cur >= 0) {
          const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
          if (STATS) (*nNodes)++;
-         uint32_t key[4];
+         float tn[4];
          F4 n0 = ld4(np), n1 = ld4(np + 1), n2 = ld4(np + 2), n3 = ld4(np + 3);
-         node4Keys(n0, n2, n3, r, pre, key);
-         const int n6[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};
-         sort4(key);
-         if (key[0] != 0xffffffffu) {
-            for (int j = 3; j >= 1; --j) if (key[j] != 0xffffffffu && sp < BL_STACK) stack[sp++] = pick4(n6, key[j] & 3u);
-            cur = pick4(n6, key[0] & 3u);
+         node4Near(n0, n2, n3, r, pre, tn);
+         int n6[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};
+         sort4(tn, n6);
+         if (tn[0] < BL_INF) {
+            for (int j = 3; j >= 1; --j) if (tn[j] < BL_INF && sp < BL_STACK) stack[sp++] = n6[j];
+            cur = n6[0];
             continue;
          }
       } else {
@@ -157,12 +168,12 @@ HD bool traceAny(const Bvh &bvh, const Ray &r) {
    for (;;) {
       if (cur >= 0) {
          const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
-         uint32_t key[4];
+         float tn[4];
          F4 n0 = ld4(np), n1 = ld4(np + 1), n2 = ld4(np + 2), n3 = ld4(np + 3);
-         node4Keys(n0, n2, n3, r, pre, key);
+         node4Near(n0, n2, n3, r, pre, tn);
          const int n6[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};
          int next = 0; bool have = false;
-         for (int k = 0; k < 4; ++k) if (key[k] != 0xffffffffu) { int c = pick4(n6, (uint32_t)k); if (!have) { next = c; have = true; } else if (sp < BL_STACK) stack[sp++] = c; }
+         for (int k = 0; k < 4; ++k) if (tn[k] < BL_INF) { int c = n6[k]; if (!have) { next = c; have = true; } else if (sp < BL_STACK) stack[sp++] = c; }
          if (have) { cur = next; continue; }
       } else {
          int enc = ~cur; int first = enc >> 4, cnt = enc & 15;

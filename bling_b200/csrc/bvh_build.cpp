@@ -215,7 +215,7 @@ int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
       np[0] = F4{P[0], P[1], P[2], i2f((int)E)};
       np[1] = F4{i2f(refs[0]), i2f(refs[1]), i2f(refs[2]), i2f(refs[3])};
       np[2] = F4{i2f((int)qlo[0]), i2f((int)qlo[1]), i2f((int)qlo[2]), i2f((int)qhi[0])};
-      np[3] = F4{i2f((int)qhi[1]), i2f((int)qhi[2]), 0, 0};
+      np[3] = F4{i2f((int)qhi[1]), i2f((int)qhi[2]), i2f(0x4B000000), 0};   // .z: the 2^23 bit pattern the kernel permutes bytes into
    }
    // worst-case traversal stack (entries) of the push-all-then-pop scheme: children indices are always larger than
    // the parent's, so one reverse sweep suffices

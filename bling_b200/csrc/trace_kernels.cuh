@@ -107,14 +107,6 @@ __device__ __forceinline__ int ldsIf(uint32_t addr, int old, bool p) {   // pred
    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q ld.shared.b32 %0, [%1]; }" : "+r"(v) : "r"(addr), "r"((int)p) : "memory");
    return v;
 }
-__device__ __forceinline__ int sel4(int c0, int c1, int c2, int c3, uint32_t slot) {   // c[slot], three selp, no branch
-   int lo, hi, out;
-   asm("{ .reg .pred p0, p1; and.b32 %0, %7, 1; setp.ne.b32 p0, %0, 0; and.b32 %1, %7, 2; setp.ne.b32 p1, %1, 0;\n"
-       "  selp.b32 %0, %4, %3, p0; selp.b32 %1, %6, %5, p0; selp.b32 %2, %1, %0, p1; }"
-       : "=&r"(lo), "=&r"(hi), "=r"(out) : "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(slot));
-   return out;
-}
-
 template <bool ANY>
 __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
                                                                  const DScene *__restrict__ sc, const F4 *__restrict__ O, const F4 *__restrict__ D,
@@ -169,20 +161,21 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
             const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
             F4 n0, n1, n2, n3;
             ld8(np, n0, n1); ld8(np + 2, n2, n3);
-            uint32_t key[4];
-            node4Keys(n0, n2, n3, r, pre, key);
-            const int c0 = f2i(n1.x), c1 = f2i(n1.y), c2 = f2i(n1.z), c3 = f2i(n1.w);
-            sort4(key);   // hits first, nearest first (any-hit only needs "hits first")
+            float tn[4];
+            node4Near(n0, n2, n3, r, pre, tn);
+            int c[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};
+            sort4(tn, c);   // nearest first, misses (+inf) last
             // branch-free push of the far hits (nearest on top), then enter the nearest
-            const int nh = (int)(key[0] != 0xffffffffu) + (int)(key[1] != 0xffffffffu) + (int)(key[2] != 0xffffffffu) + (int)(key[3] != 0xffffffffu);
-            const int r0 = sel4(c0, c1, c2, c3, key[0]), r1 = sel4(c0, c1, c2, c3, key[1]), r2 = sel4(c0, c1, c2, c3, key[2]), r3 = sel4(c0, c1, c2, c3, key[3]);
+            const bool h0 = tn[0] < BL_INF, h1 = tn[1] < BL_INF, h2 = tn[2] < BL_INF, h3 = tn[3] < BL_INF;
+            const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
+            const int r0 = c[0], r1 = c[1], r2 = c[2], r3 = c[3];
             const uint32_t top = spa + (uint32_t)(nh - 2) * LV;   // entry that ends up on top (key[1])
-            stsIf(top, r1, nh > 1);
-            stsIf(top - LV, r2, nh > 2);
-            stsIf(top - 2 * LV, r3, nh > 3);
+            stsIf(top, r1, h1);
+            stsIf(top - LV, r2, h2);
+            stsIf(top - 2 * LV, r3, h3);
             spa += (nh > 0) ? (uint32_t)(nh - 1) * LV : 0u;
             cur = r0; li = 0;
-            pop = nh == 0;
+            pop = !h0;
          }
       } else {
          if (atLeaf) {
