@@ -67,11 +67,7 @@ inline void statAdd(unsigned long long *p, unsigned long long v) { *p += v; }
 inline void cntAdd(uint32_t *p, uint32_t v) { *p += v; }
 #endif
 
-HD Sampler mkSampler(const DScene &sc, uint64_t kp, uint32_t s) {
-   Sampler c; c.kp = kp; c.s = s; c.nu = sc.nu; c.nv = sc.nv; c.n1d = 4 * sc.sample_depth; c.n2d = 3 * sc.sample_depth;   // Path.hs:18-36
-   c.stratified = sc.sampler_kind == BLINGCU_SAMPLER_STRATIFIED;
-   return c;
-}
+HD Sampler mkSampler(const DScene &sc, uint64_t kp, uint32_t s) { Sampler c; c.kp = kp; c.s = s; c.k = &sc.smp; return c; }
 
 // ------------------------------------------------------------------------------------------ K1 raygen
 struct RaygenBody {

@@ -139,50 +139,70 @@ HD uint64_t pixelKey(uint64_t seed, uint32_t pass, uint32_t pix) {
 HD uint32_t dimKey(uint64_t kp, uint32_t dim) { return hash32(hash32((uint32_t)kp ^ (dim * 0x9E3779B9U)) + (uint32_t)(kp >> 32)); }
 HD float u01(uint32_t h) { return (float)(h >> 8) * (1.0f / 16777216.0f); }
 HD uint32_t sampleHash(uint32_t kd, uint32_t s) { return hash32(kd + s * 0x9E3779B9U + 0x7F4A7C15U); }
-HD uint32_t permute(uint32_t i, uint32_t l, uint32_t p) {
+// Kensler's permutation of [0, l). `w` = (next power of two >= l) - 1 is a per-scene constant, and so is `pow2`
+// (l is a power of two: every config's strata count is); both only shorten the arithmetic, the value is the SPEC's.
+HD uint32_t permuteW(uint32_t i, uint32_t l, uint32_t p, uint32_t w, bool pow2) {
    if (l <= 1) return 0;
-   uint32_t w = l - 1;
-   w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
    do {
       i ^= p; i *= 0xe170893dU; i ^= p >> 16; i ^= (i & w) >> 4; i ^= p >> 8; i *= 0x0929eb3fU; i ^= p >> 23;
       i ^= (i & w) >> 1; i *= 1 | p >> 27; i *= 0x6935fa69U; i ^= (i & w) >> 11; i *= 0x74dcb303U;
       i ^= (i & w) >> 2; i *= 0x9e501cc3U; i ^= (i & w) >> 2; i *= 0xc860a3dfU; i &= w; i ^= i >> 5;
    } while (i >= l);
-   return (i + p) % l;
+   return pow2 ? ((i + p) & w) : ((i + p) % l);
 }
+HD uint32_t smear(uint32_t l) { uint32_t w = l - 1; w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16; return w; }
+HD uint32_t permute(uint32_t i, uint32_t l, uint32_t p) { return l <= 1 ? 0u : permuteW(i, l, p, smear(l), (l & (l - 1)) == 0); }
 #define BL_ALMOST_ONE 0.9999999403953552f
 enum { DIM_IMAGE = 0, DIM_LENS = 1, DIM_1D_BASE = 16, DIM_2D_BASE = 4096 };
 
-struct Sampler {   // per-sample view of the pixel's stratified sets
-   uint64_t kp; uint32_t s; int nu, nv, n1d, n2d; int stratified;
+// per-scene constants of the stratified sampler, computed once on the host (pipeline.h) with the same f32 operations
+// the per-sample code used to repeat: 1/nu, 1/nv, 1/(nu nv) are IEEE divisions, so the bits are identical
+struct SamplerConst {
+   int nu, nv, n1d, n2d, stratified;
+   uint32_t N, wmask;      // strata per pixel, smear(N)
+   int pow2N;              // N is a power of two
+   int nuShift;            // log2(nu) when nu is a power of two, else -1
+   float du, dv, invN;
 };
-HD void strat2D(uint32_t i, int nu, int nv, float ju, float jv, float &u, float &v) {   // Sampling.hs:163-171 (Q9)
-   float du = 1.0f / (float)nu, dv = 1.0f / (float)nv;
-   uint32_t q = i / (uint32_t)nu, r = i % (uint32_t)nu;
-   u = hminf(BL_ALMOST_ONE, ((float)q + ju) * du);
-   v = hminf(BL_ALMOST_ONE, ((float)r + jv) * dv);
+HD SamplerConst mkSamplerConst(int nu, int nv, int sampleDepth, int stratified) {
+   SamplerConst k; k.nu = nu; k.nv = nv; k.n1d = 4 * sampleDepth; k.n2d = 3 * sampleDepth; k.stratified = stratified;   // Path.hs:18-36
+   k.N = (uint32_t)(nu * nv); k.wmask = k.N > 1 ? smear(k.N) : 0u; k.pow2N = (k.N & (k.N - 1)) == 0;
+   k.nuShift = -1; for (int b = 0; b < 31; ++b) if ((1u << b) == (uint32_t)nu) k.nuShift = b;
+   k.du = 1.0f / (float)nu; k.dv = 1.0f / (float)nv; k.invN = 1.0f / (float)k.N;
+   return k;
+}
+struct Sampler {   // per-sample view of the pixel's stratified sets
+   uint64_t kp; uint32_t s; const SamplerConst *k;
+};
+HD void strat2D(uint32_t i, const SamplerConst &k, float ju, float jv, float &u, float &v) {   // Sampling.hs:163-171 (Q9)
+   uint32_t q, r;
+   if (k.nuShift >= 0) { q = i >> k.nuShift; r = i & ((uint32_t)k.nu - 1u); } else { q = i / (uint32_t)k.nu; r = i % (uint32_t)k.nu; }
+   u = hminf(BL_ALMOST_ONE, ((float)q + ju) * k.du);
+   v = hminf(BL_ALMOST_ONE, ((float)r + jv) * k.dv);
 }
 HD float rnd1D(const Sampler &c, int n) {                                               // rnd' Sampling.hs:203-211
+   const SamplerConst &k = *c.k;
    uint32_t kd = dimKey(c.kp, DIM_1D_BASE + (uint32_t)n);
    uint32_t h = sampleHash(kd, c.s);
-   if (!c.stratified || n >= c.n1d) return u01(h);
-   uint32_t N = (uint32_t)(c.nu * c.nv);
-   uint32_t i = permute(c.s, N, kd);
-   return hminf(BL_ALMOST_ONE, ((float)i + u01(h)) * (1.0f / (float)N));
+   if (!k.stratified || n >= k.n1d) return u01(h);
+   uint32_t i = permuteW(c.s, k.N, kd, k.wmask, k.pow2N != 0);
+   return hminf(BL_ALMOST_ONE, ((float)i + u01(h)) * k.invN);
 }
 HD void rnd2D(const Sampler &c, int n, float &u, float &v) {                            // rnd2D' Sampling.hs:213-221
+   const SamplerConst &k = *c.k;
    uint32_t kd = dimKey(c.kp, DIM_2D_BASE + (uint32_t)n);
    uint32_t h = sampleHash(kd, c.s), h2 = hash32(h ^ 0x85ebca6bU);
-   if (!c.stratified || n >= c.n2d) { u = u01(h); v = u01(h2); return; }
-   strat2D(permute(c.s, (uint32_t)(c.nu * c.nv), kd), c.nu, c.nv, u01(h), u01(h2), u, v);
+   if (!k.stratified || n >= k.n2d) { u = u01(h); v = u01(h2); return; }
+   strat2D(permuteW(c.s, k.N, kd, k.wmask, k.pow2N != 0), k, u01(h), u01(h2), u, v);
 }
 HD void cameraSample(const Sampler &c, float &ox, float &oy, float &lu, float &lv) {    // Sampling.hs:112-132
+   const SamplerConst &k = *c.k;
    uint32_t ki = dimKey(c.kp, DIM_IMAGE), kl = dimKey(c.kp, DIM_LENS);
    uint32_t h = sampleHash(ki, c.s), h2 = hash32(h ^ 0x85ebca6bU);
    uint32_t g = sampleHash(kl, c.s), g2 = hash32(g ^ 0x85ebca6bU);
-   if (!c.stratified) { ox = u01(h); oy = u01(h2); lu = u01(g); lv = u01(g2); return; }
-   strat2D(c.s, c.nu, c.nv, u01(h), u01(h2), ox, oy);
-   strat2D(permute(c.s, (uint32_t)(c.nu * c.nv), kl), c.nu, c.nv, u01(g), u01(g2), lu, lv);
+   if (!k.stratified) { ox = u01(h); oy = u01(h2); lu = u01(g); lv = u01(g2); return; }
+   strat2D(c.s, k, u01(h), u01(h2), ox, oy);
+   strat2D(permuteW(c.s, k.N, kl, k.wmask, k.pow2N != 0), k, u01(g), u01(g2), lu, lv);
 }
 
 }  // namespace bl

@@ -179,6 +179,7 @@ struct Pipeline {
       hs.EW = hs.ex1 - hs.ex0 + 1; hs.EH = hs.ey1 - hs.ey0 + 1;
       hs.sampler_kind = ir->sampler_kind; hs.nu = ir->nu; hs.nv = ir->nv;
       hs.max_depth = ir->max_depth; hs.sample_depth = ir->sample_depth;
+      hs.smp = mkSamplerConst(hs.nu, hs.nv, hs.sample_depth, hs.sampler_kind == BLINGCU_SAMPLER_STRATIFIED);
       for (int i = 0; i < NB; ++i) { hs.cieX[i] = ir->cie_x.v[i]; hs.cieY[i] = ir->cie_y.v[i]; hs.cieZ[i] = ir->cie_z.v[i]; }
       hs.ySum = ir->cie_y_sum;
       for (int b = 0; b < 7; ++b) for (int i = 0; i < NB; ++i) hs.illum[b][i] = ir->illum_basis[b].v[i];

@@ -28,6 +28,7 @@ struct DScene {
    int W, H; float fw, fh;
    int ex0, ex1, ey0, ey1, EW, EH;   // sample extent (Image.hs:162-168)
    int sampler_kind, nu, nv, max_depth, sample_depth;
+   SamplerConst smp;           // per-scene sampler constants (hd.h)
    float cieX[NB], cieY[NB], cieZ[NB], ySum;
    float illum[7][NB];         // r g b c m y w
 };

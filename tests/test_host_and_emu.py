@@ -83,6 +83,21 @@ def test_emulated_path_samples_match_oracle(name):
     assert (rel < 1e-4).mean() > 0.999, rel.max()
 
 
+def test_sampler_non_power_of_two_strata():
+    """3x5 strata: the general (division / modulo) path of the sampler SPEC, the configs only reach the power-of-two one."""
+    sc = small(load_scene("cornell-box"), 24, 18, 3, 5)
+    o = Oracle(sc); e = EmuContext(); e.upload_scene(sc)
+    x0, x1, y0, y1 = o.sample_extent()
+    rng = np.random.default_rng(9)
+    n = 600
+    px, py, s = rng.integers(x0, x1 + 1, n), rng.integers(y0, y1 + 1, n), rng.integers(0, 15, n)
+    Lo, xyo = o.render_samples(1, 5, px, py, s)
+    Le, xye = e.render_samples(1, 5, px, py, s)
+    assert np.array_equal(xyo, xye)
+    rel = np.abs(Lo - Le).max(1) / (np.abs(Lo).max(1) + 1e-6)
+    assert (rel < 1e-4).mean() > 0.995
+
+
 def test_emulated_film_matches_oracle_tiles():
     """the atomic-free film gather reproduces per-tile addSample + addTile (Q10) to float rounding."""
     for name, wh in (("cornell-box", (37, 29)), ("sun-sky", (33, 20)), ("ducky", (30, 18))):
