@@ -72,7 +72,6 @@ HD bool leafItemAny(const Bvh &bvh, int item, const Ray &r) {
 #else
 #define BL_FMA(a, b, c) fmaf(a, b, c)
 #endif
-HD float c4(const F4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w)); }
 struct RayPre { V3 idir, ood; };   // 1/d and o/d: plane distance = plane * idir - ood (one FMA)
 // |1/d| is clamped to 1e18 so that plane * idir - ood never evaluates inf - inf: an axis-parallel ray then sees
 // (-huge, +huge) when its origin is inside the slab and two same-signed huge values (a miss) when it is outside.

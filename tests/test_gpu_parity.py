@@ -177,3 +177,28 @@ def test_full_size_soup_smoke(ctx):
     assert np.isfinite(f).all() and (f[..., 0] > 0).all()
     assert st["samples"] == 962 * 542 * 4 and st["dropped_samples"] == 0
     assert st["rays_extension"] <= st["samples"] * sc.max_depth
+
+
+def test_cfg5_full_size_properties(ctx):
+    """BASELINE.json configs[4] at FULL size (10 M triangles, 3840x2160): properties that need no CPU reference --
+    any-hit == (nearest-hit found something) on the same rays, both traversal variants agree bit for bit, the film
+    is finite and fully covered, sample/ray accounting is exact, a pass is deterministic and slices compose."""
+    sc = make_soup(10_000_000, 3840, 2160, 32, 32)
+    ctx.upload_scene(sc)
+    rays = np.concatenate([random_rays(sc, 500_000, 21), camera_rays(None, sc, 500_000, 22)])
+    hit = ctx.trace_nearest(rays); occ = ctx.trace_occluded(rays)
+    assert np.array_equal(occ != 0, hit["prim"] >= 0)
+    assert 0.05 < (hit["prim"] >= 0).mean() < 0.999
+    ctx.set_option("trace_variant", 0)
+    ref = ctx.trace_nearest(rays[:200_000])
+    ctx.set_option("trace_variant", 1)
+    assert np.array_equal(ref["prim"], hit["prim"][:200_000]) and np.array_equal(ref["t"], hit["t"][:200_000])
+    ctx.reset_stats(); ctx.clear_film()
+    ctx.render_slice(1, 7, 0, 2); a = ctx.read_film(); st = ctx.stats()
+    assert np.isfinite(a).all() and (a[..., 0] > 0).all()
+    assert st["samples"] == 3842 * 2162 * 2 == st["rays_camera"] and st["dropped_samples"] == 0
+    assert st["rays_extension"] <= st["samples"] * sc.max_depth and st["rays_mis"] == st["rays_mis_any"]
+    ctx.clear_film(); ctx.render_slice(1, 7, 0, 1); ctx.render_slice(1, 7, 1, 2); b = ctx.read_film()
+    assert np.abs(a - b).max() <= 1e-5 * np.abs(a).max()
+    ctx.clear_film(); ctx.render_slice(1, 7, 0, 2)
+    assert np.array_equal(ctx.read_film(), a)
