@@ -27,7 +27,10 @@ struct Box {
 };
 struct Item { float lo[3], hi[3], c[3]; uint32_t id; };
 
-constexpr int NBINS = 16;
+#ifndef BL_NBINS
+#define BL_NBINS 16
+#endif
+constexpr int NBINS = BL_NBINS;
 
 struct Builder {
    std::vector<Item> items;
