@@ -9,6 +9,7 @@
 #include "api_impl.h"
 #include "trace_kernels.cuh"
 #include <cuda_runtime.h>
+#include <utility>
 #include <vector>
 
 namespace bl {
@@ -137,10 +138,13 @@ struct CudaBackend {
    }
    // CTAs of `kernel` that fit on one SM (registers / shared memory), cached per kernel: grid-stride kernels are
    // launched with exactly sms x resident CTAs so that every SM holds the same amount of work (no partial last wave)
+   std::vector<std::pair<const void *, int>> residentCache;
    template <class K> uint32_t resident(K kernel, int block) {
-      static thread_local int cached = 0;   // one instantiation of this function template per kernel
-      if (!cached) { int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, block, 0); cached = nb > 0 ? nb : 1; }
-      return (uint32_t)cached;
+      const void *key = (const void *)kernel;
+      for (auto &e : residentCache) if (e.first == key) return (uint32_t)e.second;
+      int nb = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, block, 0);
+      residentCache.emplace_back(key, nb > 0 ? nb : 1);
+      return (uint32_t)residentCache.back().second;
    }
    template <class B> void run(const B &b, uint32_t n) {
       if (n == 0) return;
