@@ -111,14 +111,12 @@ struct ClassifyBody {
    const DScene *sc; PathState ps;
    HD void operator()(uint32_t i) const {
       const DScene &S = *sc;
-      int prim = f2i(ps.hit[i].w);
+      const int href = f2i(ps.hit[i].w);
       int kind;
-      if (prim < 0) kind = 0;
+      if (href == BL_REF_MISS) kind = 0;
       else {
          if ((int)(ps.meta[i] & 0xffu) == S.max_depth) return;   // Path.hs:51: depth == md -> return l
-         uint32_t ref = S.prim_ref[prim];
-         int mat = (ref >> 31) ? S.shapes[ref & 0x7fffffffu].material : f2i(ld4(S.tri_p + 3 * (size_t)ref).w);
-         kind = 1 + S.materials[mat].kind;
+         kind = 1 + refKind(href);                                // the material kind travels in the hit record
       }
       qPush(ps.qMat + (size_t)kind * ps.cap, ps.counters + C_MAT0 + kind, i);
    }
@@ -250,15 +248,14 @@ struct ResolveMisBody {   // Scene.hs:75-82
       int ln = f2i(info.y);
       const blingcu_light &l = S.lights[ln];
       Ray ray = loadRay(ps.miO, ps.miD, i);
-      int prim = f2i(hv.w);
+      const int href = f2i(hv.w);
       Spec li;
-      if (prim >= 0) {
-         uint32_t ref = S.prim_ref[prim];
-         if (!(ref >> 31)) return;                                  // triangles carry no light (TriangleMesh.hs:105)
-         const blingcu_shape &s = S.shapes[ref & 0x7fffffffu];
+      if (href != BL_REF_MISS) {
+         if (!refIsShape(href)) return;                             // triangles carry no light (TriangleMesh.hs:105)
+         const blingcu_shape &s = S.shapes[refIndex(href)];
          if (s.light != ln || l.kind != BLINGCU_LIGHT_AREA) return;   // Eq Light: same area-light id (Light.hs:48-50)
          SurfaceHit sh; DG dgs;
-         surfaceAt(S, ray, hv.x, hv.y, hv.z, prim, sh, dgs);
+         surfaceAt(S, ray, hv.x, hv.y, hv.z, href, sh, dgs);
          if (!areaEmits(sh.dgg.n, -ray.d)) return;                   // intLe int (-wi)
          li = loadSpec(l.s.v);
       } else {
@@ -371,7 +368,15 @@ struct FilmBody {
 
 // explicit ray batches: ABI layout <-> kernel layout
 struct SplitRaysBody { const F4 *rays; F4 *o, *d; HD void operator()(uint32_t i) const { o[i] = rays[2 * (size_t)i]; d[i] = rays[2 * (size_t)i + 1]; } };
-struct HitToAbiBody { F4 *h; HD void operator()(uint32_t i) const { F4 v = h[i]; F4 r; r.x = v.x; r.y = v.w; r.z = v.y; r.w = v.z; h[i] = r; } };   // (t,b1,b2,prim) -> {t, prim, b1, b2}
+struct HitToAbiBody {   // kernel hit (t, b1, b2, ref) -> ABI hit {t, prim id, b1, b2}
+   const DScene *sc; F4 *h;
+   HD void operator()(uint32_t i) const {
+      F4 v = h[i]; const int href = f2i(v.w);
+      int prim = -1;
+      if (href != BL_REF_MISS) prim = refIsShape(href) ? sc->shapes[refIndex(href)].prim_id : sc->tri_prim[refIndex(href)];
+      F4 r; r.x = v.x; r.y = i2f(prim); r.z = v.y; r.w = v.z; h[i] = r;
+   }
+};
 
 struct AddFilmBody { F4 *dst; const F4 *src; HD void operator()(uint32_t i) const { F4 a = dst[i], b = src[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; dst[i] = a; } };
 

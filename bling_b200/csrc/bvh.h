@@ -19,7 +19,7 @@
 // L2/DRAM bytes per visit. The builder (bvh_build.cpp) builds a binned-SAH binary tree, collapses it into 4-wide
 // nodes by repeatedly opening the child with the largest area, then quantises.
 // Leaf item = 48 B = 3 x 16-byte loads:
-//   triangle: (p1.xyz, prim_id) (e1.xyz, 0) (e2.xyz, -)       shape: (-, -, -, prim_id) (-, -, -, 1 + shape index) -
+//   triangle: (p1.xyz, ref) (e1.xyz, 0) (e2.xyz, -)       shape: (-, -, -, ref) (-, -, -, 1 + shape index) -      (ref: see HitRec)
 // Boxes are inflated by the builder, so the slab test needs no epsilon (see bvh_build.cpp).
 #pragma once
 #include "geom.h"
@@ -35,7 +35,16 @@ struct Bvh {
    int max_stack;     // worst-case traversal stack entries (from the builder)
 };
 
+// Hit record. `prim` is the leaf item's REFERENCE, not the reference implementation's primitive id:
+//   bit 31 = analytic shape, bits 28..30 = material kind (BLINGCU_MAT_*), bits 0..27 = triangle / shape index;  -1 = miss.
+// The wavefront classifies by material kind straight from this word and finds the geometry without an indirection;
+// the C ABI converts it to the primitive id of `mkScene`'s list on the way out (HitToAbiBody).
 struct HitRec { float t; int prim; float b1, b2; };
+#define BL_REF_MISS (-1)
+HD bool refIsShape(int ref) { return ((uint32_t)ref >> 31) != 0; }
+HD int refKind(int ref) { return (int)(((uint32_t)ref >> 28) & 7u); }
+HD uint32_t refIndex(int ref) { return (uint32_t)ref & 0x0fffffffu; }
+HD int mkRef(bool shape, int kind, uint32_t index) { return (int)((shape ? 0x80000000u : 0u) | ((uint32_t)kind << 28) | index); }
 
 
 HD bool leafItemNearest(const Bvh &bvh, int item, Ray &r, HitRec &h) {

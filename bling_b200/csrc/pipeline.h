@@ -127,11 +127,11 @@ struct Pipeline {
          F4 *q = &items[3 * k];
          if (src < nt) {
             const float *v = ir->tri_verts + 9 * (size_t)src;
-            q[0] = F4{v[0], v[1], v[2], i2f(itemPrim[src])};
+            q[0] = F4{v[0], v[1], v[2], i2f(mkRef(false, ir->materials[ir->tri_material[src]].kind, (uint32_t)src))};
             q[1] = F4{v[3] - v[0], v[4] - v[1], v[5] - v[2], i2f(0)};   // e1 = p2 - p1 (TriangleMesh.hs:169)
             q[2] = F4{v[6] - v[0], v[7] - v[1], v[8] - v[2], 0};        // e2 = p3 - p1
          } else {
-            q[0] = F4{0, 0, 0, i2f(itemPrim[src])};
+            q[0] = F4{0, 0, 0, i2f(mkRef(true, ir->materials[ir->shapes[src - nt].material].kind, (uint32_t)(src - nt)))};
             q[1] = F4{0, 0, 0, i2f(1 + (int)(src - nt))};
             q[2] = F4{0, 0, 0, 0};
          }
@@ -155,7 +155,7 @@ struct Pipeline {
          hs.tri_p = up<F4>(tp.data(), tp.size()); hs.tri_uv = up<F2>(tu.data(), tu.size());
          hs.tri_n = (ir->tri_normals && nt) ? up<float>(ir->tri_normals, 9 * nt) : nullptr;
       }
-      hs.prim_ref = up<uint32_t>(primRef.data(), primRef.size());
+      { std::vector<int32_t> tprim(nt ? nt : 1, 0); for (size_t i = 0; i < nt; ++i) tprim[i] = itemPrim[i]; hs.tri_prim = up<int32_t>(tprim.data(), tprim.size()); }
       hs.shapes = up<blingcu_shape>(ir->shapes, ns); hs.bvh.shapes = hs.shapes;
       hs.materials = up<blingcu_material>(ir->materials, ir->n_materials);
       hs.textures = up<blingcu_texture>(ir->textures, ir->n_textures);
@@ -328,7 +328,7 @@ struct Pipeline {
          uint32_t *dN = (uint32_t *)tb[4], *dP = (uint32_t *)tb[5];
          if (nodes) be.traceStats((uint32_t)n, dscene, dO, dD, dH, dN, dP);
          else { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(nullptr, nullptr, (uint32_t)n, dscene, dO, dD, dH); }
-         be.tag(BLINGCU_KC_OTHER); be.run(HitToAbiBody{dH}, (uint32_t)n);
+         be.tag(BLINGCU_KC_OTHER); be.run(HitToAbiBody{dscene, dH}, (uint32_t)n);
          be.download(outHit, dH, sizeof(F4) * n);
          if (nodes) { be.download(nodes, dN, 4 * n); be.download(prims, dP, 4 * n); }
       }

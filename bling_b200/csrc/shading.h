@@ -16,7 +16,7 @@ struct DScene {
    const F4 *tri_p;            // 3 per triangle: (p1.xyz, material), (p2.xyz, -), (p3.xyz, -)
    const F2 *tri_uv;           // 3 per triangle
    const float *tri_n;         // 9 per triangle or null
-   const uint32_t *prim_ref;   // per prim id: bit 31 = analytic shape, low bits = triangle/shape index
+   const int32_t *tri_prim;    // per triangle: primitive id in mkScene's list (only the C-ABI hit conversion reads it)
    const blingcu_shape *shapes;
    const blingcu_material *materials;
    const blingcu_texture *textures;
@@ -341,9 +341,9 @@ struct SurfaceHit {   // what mkIntersection carries (Primitive.hs:49-65)
 };
 
 // geometric DG of a hit from (ray, t, b1, b2, prim): re-derives what the reference stores in Intersection
-HD void surfaceAt(const DScene &sc, const Ray &ray, float t, float b1, float b2, int prim, SurfaceHit &sh, DG &dgs) {
-   uint32_t ref = sc.prim_ref[prim];
-   if (!(ref >> 31)) {
+HD void surfaceAt(const DScene &sc, const Ray &ray, float t, float b1, float b2, int href, SurfaceHit &sh, DG &dgs) {
+   const uint32_t ref = refIndex(href);
+   if (!refIsShape(href)) {
       const F4 *tp = sc.tri_p + 3 * (size_t)ref;
       F4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
       const F2 *up = sc.tri_uv + 3 * (size_t)ref;
@@ -363,7 +363,7 @@ HD void surfaceAt(const DScene &sc, const Ray &ray, float t, float b1, float b2,
       }
       return;
    }
-   const blingcu_shape &s = sc.shapes[ref & 0x7fffffffu];
+   const blingcu_shape &s = sc.shapes[ref];
    Ray ro = transRay(s.w2o, ray); ro.tmax = t;   // same arithmetic as the traversal => same t
    float t2; DG dgo;
    shapeIntersect<true>(s, ro, t2, dgo);
