@@ -338,10 +338,11 @@ def run_b200(a):
                 e2e_trace = {"value": nr / dt2 / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": nr * 32, "d2h_bytes_per_step": nr * 16,
                              "what": "blingcu_trace_nearest, 4M primary-like rays, host ray buffer in / host hit buffer out"}
 
-    # ---- the named scenes of BASELINE.json configs[0..3] at their config sizes (rank 0, one GPU): one warm-up slice,
-    # then a timed slice of sample indices through blingcu_render_slice (device time from the library's own events)
+    # ---- the named scenes of BASELINE.json configs[0..3] at their config sizes, on all N GPUs: every rank renders k
+    # sample indices of its own pass (pass 1 + rank: independent sample sets, the same weak scaling as the headline),
+    # then the films are all-reduced; time = max over ranks of (render + all-reduce), CUDA events on the launching stream
     scenes = None
-    if rank == 0 and world == 1 and not a.no_scenes:
+    if not a.no_scenes:
         scenes = {}
         from bling_b200 import ir as IR
         for name in ("cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"):
@@ -350,17 +351,34 @@ def run_b200(a):
                 continue
             sc = IR.SceneIR.load(f)
             c2 = api.Context(local)
+            c2.set_stream(stream.cuda_stream)
             c2.upload_scene(sc)
             ex = c2.sample_extent(); npx = (ex[1] - ex[0] + 1) * (ex[3] - ex[2] + 1)
             k = max(1, min(sc.spp // 2, int(48e6 // npx)))
-            c2.render_slice(1, SEED, 0, k); c2.synchronize(); c2.reset_stats()
-            c2.render_slice(1, SEED, k, 2 * k)
-            s3 = c2.stats()
-            rays = s3["rays_camera"] + s3["rays_extension"] + s3["rays_mis"] + s3["rays_shadow"]
-            sec = s3["last_pass_ms"] * 1e-3
-            scenes[name] = {"size": [sc.width, sc.height], "prims": sc.n_prims, "samples": s3["samples"],
-                            "msamples_per_s": s3["samples"] / sec / 1e6, "mrays_per_s": rays / sec / 1e6,
-                            "rays_per_sample": rays / max(1, s3["samples"]), "launches": s3["kernel_launches"],
+            p2, n2 = c2.film_device()
+            f2 = torch.as_tensor(_Dev(p2, n2), device=torch.device("cuda", local))
+            with torch.cuda.stream(stream):
+                c2.render_slice(1 + rank, SEED, 0, k)
+                barrier(); c2.reset_stats()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                c2.render_slice(1 + rank, SEED, k, 2 * k)
+                if world > 1:
+                    tot2 = f2.clone(); dist.all_reduce(tot2, op=dist.ReduceOp.SUM)
+                e1.record(stream)
+                barrier()
+                s3 = c2.stats()
+                rays = s3["rays_camera"] + s3["rays_extension"] + s3["rays_mis"] + s3["rays_shadow"]
+                v = torch.tensor([e0.elapsed_time(e1), float(s3["samples"]), float(rays)], dtype=torch.float64, device="cuda")
+                if world > 1:
+                    vm = v.clone(); dist.all_reduce(vm, op=dist.ReduceOp.MAX)
+                    vs = v.clone(); dist.all_reduce(vs, op=dist.ReduceOp.SUM)
+                    ms2, ns, nr = float(vm[0]), float(vs[1]), float(vs[2])
+                else:
+                    ms2, ns, nr = (float(x) for x in v)
+            scenes[name] = {"size": [sc.width, sc.height], "prims": sc.n_prims, "samples": ns,
+                            "msamples_per_s": ns / (ms2 * 1e-3) / 1e6, "mrays_per_s": nr / (ms2 * 1e-3) / 1e6,
+                            "rays_per_sample": nr / max(1.0, ns), "launches_per_gpu": s3["kernel_launches"],
                             "hbm_roofline": "n/a (scene lives in L1/L2)" if sc.n_prims < 1000 else "see roofline of cfg 5"}
             c2.close()
 
