@@ -89,6 +89,9 @@ __global__ void __launch_bounds__(128) kTraceNearestCount(const uint32_t *__rest
 #ifndef TR_MINBLOCKS
 #define TR_MINBLOCKS 8
 #endif
+#ifndef TR_SS
+#define TR_SS 16        // stack levels per thread kept in shared memory; deeper levels live in local memory (see below)
+#endif
 #ifndef TR_LEAF_W
 #define TR_LEAF_W 6       // vote weights (quarters): leaf step when TR_LEAF_W * #leaf lanes > 4 * #node lanes
 #endif
@@ -118,9 +121,12 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
    const unsigned lane = threadIdx.x & 31u;
    const uint32_t stackBase = (uint32_t)__cvta_generic_to_shared(sstack + threadIdx.x);   // 32-bit shared address of my column
    const uint32_t LV = TR_THREADS * (uint32_t)sizeof(int);                                // bytes per stack level
+   // Only the first TR_SS levels live in shared memory (8 KB per CTA whatever the tree depth, so 8 CTAs per SM always
+   // fit and most of the 256 KB L1/shared array stays L1); deeper levels (rare) spill to a local-memory tail.
+   int tail[BL_STACK - TR_SS];
    const int EMPTY = (int)0x80000000;   // lane holds no ray; otherwise cur = child reference (>= 0 node, < 0 encoded leaf)
    int cur = EMPTY, li = 0;
-   uint32_t spa = stackBase;            // shared address of the next free stack entry
+   int sp = 0;                          // stack entries in use
    uint32_t slot = 0;
    Ray r; RayPre pre; HitRec h;
    bool exhausted = false;
@@ -144,7 +150,7 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
                r = loadRay(O, D, slot);
                pre = rayPre(r);
                h.t = 0; h.prim = -1; h.b1 = 0; h.b2 = 0;
-               spa = stackBase;
+               sp = 0;
                cur = (bvh.root >= 0) ? bvh.root : ~0;   // empty scene: a leaf with zero items
                li = 0;
             }
@@ -169,11 +175,17 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
             const bool h0 = tn[0] < BL_INF, h1 = tn[1] < BL_INF, h2 = tn[2] < BL_INF, h3 = tn[3] < BL_INF;
             const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
             const int r0 = c[0], r1 = c[1], r2 = c[2], r3 = c[3];
-            const uint32_t top = spa + (uint32_t)(nh - 2) * LV;   // entry that ends up on top (key[1])
-            stsIf(top, r1, h1);
-            stsIf(top - LV, r2, h2);
-            stsIf(top - 2 * LV, r3, h3);
-            spa += (nh > 0) ? (uint32_t)(nh - 1) * LV : 0u;
+            // far hits go to levels sp .. sp+nh-2, the nearest of them on top
+            const int l1 = sp + nh - 2, l2 = l1 - 1, l3 = l1 - 2;
+            if (l1 < TR_SS) {   // common case: everything fits in the shared-memory part (l3 <= l2 <= l1)
+               const uint32_t top = stackBase + (uint32_t)l1 * LV;
+               stsIf(top, r1, h1); stsIf(top - LV, r2, h2); stsIf(top - 2 * LV, r3, h3);
+            } else {
+               if (h1) { if (l1 < TR_SS) stsIf(stackBase + (uint32_t)l1 * LV, r1, true); else tail[l1 - TR_SS] = r1; }
+               if (h2) { if (l2 < TR_SS) stsIf(stackBase + (uint32_t)l2 * LV, r2, true); else tail[l2 - TR_SS] = r2; }
+               if (h3) { if (l3 < TR_SS) stsIf(stackBase + (uint32_t)l3 * LV, r3, true); else tail[l3 - TR_SS] = r3; }
+            }
+            sp += (nh > 0) ? nh - 1 : 0;
             cur = r0; li = 0;
             pop = !h0;
          }
@@ -191,9 +203,10 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
          }
       }
       // ---- pop (predicated load) or, with an empty stack, finish the ray (rare: once per ray)
-      const bool more = spa != stackBase;
-      spa -= (pop && more) ? LV : 0u;
-      cur = ldsIf(spa, cur, pop && more);
+      const bool more = sp != 0;
+      sp -= (pop && more) ? 1 : 0;
+      if (pop && more && sp >= TR_SS) cur = tail[sp - TR_SS];
+      else cur = ldsIf(stackBase + (uint32_t)sp * LV, cur, pop && more);
       li = pop ? 0 : li;
       if (pop && !more) {
          if (ANY) occl[slot] = 0;
@@ -204,7 +217,7 @@ __global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(con
 }
 
 // levels of shared-memory stack per thread: the builder's worst case (a pop precedes every push burst of <= 3)
-static inline size_t traceSmemBytes(int maxStack) { int lv = maxStack < 8 ? 8 : maxStack; return (size_t)lv * TR_THREADS * sizeof(int); }
+static inline size_t traceSmemBytes(int maxStack) { int lv = maxStack < TR_SS ? maxStack : TR_SS; if (lv < 1) lv = 1; return (size_t)lv * TR_THREADS * sizeof(int); }
 
 static inline uint32_t traceGrid(const TraceConfig &cfg, uint32_t n, uint32_t raysPerBlock) {
    uint32_t need = (n + raysPerBlock - 1) / raysPerBlock;
