@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(128) kTraceNearestCount(const uint32_t *__rest
 #define TR_REFILL 4       // refill once this many lanes are idle
 #endif
 #ifndef TR_MINBLOCKS
-#define TR_MINBLOCKS 8
-#endif
+#define TR_MINBLOCKS 8    // resident CTAs per SM of the nearest-hit kernel (64 registers); the any-hit kernel carries no hit
+#endif                  // record and fits 9 (56 registers, no spills): +5 % on shadow / MIS rays
 #ifndef TR_SS
 #define TR_SS 16        // stack levels per thread kept in shared memory; deeper levels live in local memory (see below)
 #endif
@@ -111,7 +111,7 @@ __device__ __forceinline__ int ldsIf(uint32_t addr, int old, bool p) {   // pred
    return v;
 }
 template <bool ANY>
-__global__ void __launch_bounds__(TR_THREADS, TR_MINBLOCKS) kTracePersistent(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
+__global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLOCKS) kTracePersistent(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
                                                                  const DScene *__restrict__ sc, const F4 *__restrict__ O, const F4 *__restrict__ D,
                                                                  F4 *__restrict__ hit, uint8_t *__restrict__ occl, uint32_t *__restrict__ work) {
    extern __shared__ int sstack[];            // [level][TR_THREADS]: conflict-free, one column per thread
@@ -238,7 +238,8 @@ static inline void launchTraceAny(TraceConfig &cfg, cudaStream_t st, const uint3
    if (cfg.variant == 0) { kTraceAnySimple<<<traceGrid(cfg, n, 128), 128, 0, st>>>(q, cnt, n, sc, O, D, occl); return; }
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
-   kTracePersistent<true><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter);
+   TraceConfig c9 = cfg; c9.blocksPerSm = cfg.blocksPerSm + 1;
+   kTracePersistent<true><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter);
 
 }
 static inline void launchTraceStats(TraceConfig &cfg, cudaStream_t st, uint32_t n, const DScene *sc, const F4 *O, const F4 *D, F4 *hit, uint32_t *nodes, uint32_t *prims) {
