@@ -128,9 +128,9 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
    int cur = EMPTY, li = 0;
    int sp = 0;                          // stack entries in use
    uint32_t slot = 0;
-   Ray r; RayPre pre; HitRec h;
+   Ray r; RayPre pre;
    bool exhausted = false;
-   r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.tmin = 0; r.tmax = 0; pre.idir = mk3(0, 0, 0); pre.ood = mk3(0, 0, 0); h.t = 0; h.prim = -1; h.b1 = h.b2 = 0;
+   r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.tmin = 0; r.tmax = 0; pre.idir = mk3(0, 0, 0); pre.ood = mk3(0, 0, 0);
 
    for (;;) {
       // ---- where does every lane stand?
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
                slot = q ? q[k] : k;
                r = loadRay(O, D, slot);
                pre = rayPre(r);
-               h.t = 0; h.prim = -1; h.b1 = 0; h.b2 = 0;
+               if (!ANY) { F4 v_; v_.x = 0; v_.y = 0; v_.z = 0; v_.w = i2f(-1); hit[slot] = v_; }   // a miss until a leaf step says otherwise
                sp = 0;
                cur = (bvh.root >= 0) ? bvh.root : ~0;   // empty scene: a leaf with zero items
                li = 0;
@@ -195,7 +195,11 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
             bool found = false;
             if (li < cntl) {
                if (ANY) found = leafItemAny(bvh, first + li, r);
-               else leafItemNearest(bvh, first + li, r, h);
+               else {   // an accepted hit shrinks r.tmax and goes straight to the output record (a few stores per ray) instead
+                  // of riding in three registers for the whole traversal
+                  HitRec hh; hh.t = 0; hh.prim = -1; hh.b1 = hh.b2 = 0;
+                  if (leafItemNearest(bvh, first + li, r, hh)) { F4 v_; v_.x = hh.t; v_.y = hh.b1; v_.z = hh.b2; v_.w = i2f(hh.prim); hit[slot] = v_; }
+               }
                li++;
             }
             if (ANY && found) { occl[slot] = 1; cur = EMPTY; }
@@ -210,7 +214,6 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
       li = pop ? 0 : li;
       if (pop && !more) {
          if (ANY) occl[slot] = 0;
-         else { F4 v; v.x = h.t; v.y = h.b1; v.z = h.b2; v.w = i2f(h.prim); hit[slot] = v; }
          cur = EMPTY;
       }
    }
