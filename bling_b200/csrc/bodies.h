@@ -321,42 +321,59 @@ struct FinalizeBody {
 // Reproduces addSample on per-tile images + addTile (Image.hs:108-120,178-199,250-299, Q10): a sample only
 // reaches pixels of ITS 16x16 sample window's tile image, which has no left/top apron and extends
 // floor(0.5+f) pixels right/bottom.
+// shared pieces of the two film kernels (FilmBody: one thread per pixel straight from global memory; kFilmTile in
+// cuda_backend.cu: one CTA per 16x16 pixel tile with the candidate samples staged in shared memory)
+struct FilmGeom {   // per-scene constants of the gather
+   float fw, fh, ifw, ifh; int extx, exty;
+};
+HD FilmGeom filmGeom(const DScene &S) {
+   FilmGeom g; g.fw = S.fw; g.fh = S.fh; g.ifw = 1 / S.fw; g.ifh = 1 / S.fw;   // Q10: ifh = 1 / fw
+   g.extx = (int)floorf(0.5f + S.fw); g.exty = (int)floorf(0.5f + S.fh);
+   return g;
+}
+// sample pixels whose samples can reach film pixel column/row v: a sample of pixel i sits at d = i + o - 0.5 with o in
+// [0,1] (the sum may round up to i + 1), and covers v iff ceil(d - f) <= v <= floor(d + f)
+//   => i in [ceil(v - f - 0.5), floor(v + f + 0.5)]   (5x5 pixels for a radius-2 filter, not 9x9)
+HD int filmCellLo(int v, float f) { return (int)ceilf((float)v - f - 0.5f); }
+HD int filmCellHi(int v, float f) { return (int)floorf((float)v + f + 0.5f); }
+// the tile image of the 16x16 sample window that holds sample pixel i covers [to, tmax] along one axis (Image.hs:108-120:
+// no left/top apron, `ext` pixels to the right/bottom)
+HD void filmTileSpan(int i, int e0, int e1, int ext, int &to, int &tmax) {
+   int t0 = e0 + ((i - e0) >> 4) * 16, t1 = imin(t0 + 15, e1);
+   to = imax(0, t0); tmax = t1 + ext - 1;
+}
+// addSample of one sample into pixel (x, y) of its tile image (Image.hs:250-299)
+HD void filmAddSample(const DScene &S, const FilmGeom &g, int x, int y, int tox, int txmax, int toy, int tymax, const F4 &c, const F2 &sp,
+                      float &aw, float &ax, float &ay, float &az) {
+   if (c.w == 0) return;
+   float dx = sp.x - 0.5f, dy = sp.y - 0.5f;
+   int x0 = imax(tox, (int)ceilf(dx - g.fw)), x1 = imin(txmax, (int)floorf(dx + g.fw));
+   int y0 = imax(toy, (int)ceilf(dy - g.fh)), y1 = imin(tymax, (int)floorf(dy + g.fh));
+   if (x < x0 || x > x1 || y < y0 || y > y1) return;
+   int tix = imin((int)floorf(fabsf(((float)x - dx) * g.ifw * 16.0f)), 15);
+   int tiy = imin((int)floorf(fabsf(((float)y - dy) * g.ifh * 16.0f)), 15);
+   float w = S.ftbl[tiy * 16 + tix];
+   aw = aw + w; ax = ax + c.x * w; ay = ay + c.y * w; az = az + c.z * w;
+}
+
 struct FilmBody {
    const DScene *sc; PathState ps; F4 *film; uint32_t k, npix;
    HD void operator()(uint32_t fp) const {
       const DScene &S = *sc;
       int x = (int)(fp % (uint32_t)S.W), y = (int)(fp / (uint32_t)S.W);
-      float fw = S.fw, fh = S.fh;
-      float ifw = 1 / fw, ifh = 1 / fw;   // Q10
-      // sample pixels whose samples can reach this film pixel: a sample of pixel ix sits at dx = ix + o - 0.5 with
-      // o in [0,1] (the sum may round up to ix + 1), and covers x iff ceil(dx - fw) <= x <= floor(dx + fw)
-      //   => ix in [ceil(x - fw - 0.5), floor(x + fw + 0.5)]   (5x5 pixels for a radius-2 filter, not 9x9)
-      int ixlo = (int)ceilf((float)x - fw - 0.5f), ixhi = (int)floorf((float)x + fw + 0.5f);
-      int iylo = (int)ceilf((float)y - fh - 0.5f), iyhi = (int)floorf((float)y + fh + 0.5f);
-      int extx = (int)floorf(0.5f + fw), exty = (int)floorf(0.5f + fh);
+      const FilmGeom g = filmGeom(S);
+      int ixlo = filmCellLo(x, g.fw), ixhi = filmCellHi(x, g.fw), iylo = filmCellLo(y, g.fh), iyhi = filmCellHi(y, g.fh);
       float aw = 0, ax = 0, ay = 0, az = 0;
       for (int iy = imax(S.ey0, iylo); iy <= imin(S.ey1, iyhi); ++iy) {
-         int ty0 = S.ey0 + ((iy - S.ey0) >> 4) * 16, ty1 = imin(ty0 + 15, S.ey1);
-         int toy = imax(0, ty0), tymax = ty1 + exty - 1;
+         int toy, tymax; filmTileSpan(iy, S.ey0, S.ey1, g.exty, toy, tymax);
          if (y < toy || y > tymax) continue;
          for (int ix = imax(S.ex0, ixlo); ix <= imin(S.ex1, ixhi); ++ix) {
-            int tx0 = S.ex0 + ((ix - S.ex0) >> 4) * 16, tx1 = imin(tx0 + 15, S.ex1);
-            int tox = imax(0, tx0), txmax = tx1 + extx - 1;
+            int tox, txmax; filmTileSpan(ix, S.ex0, S.ex1, g.extx, tox, txmax);
             if (x < tox || x > txmax) continue;
             uint32_t pix = (uint32_t)(iy - S.ey0) * (uint32_t)S.EW + (uint32_t)(ix - S.ex0);
             for (uint32_t sl = 0; sl < k; ++sl) {
                uint32_t slot = sl * npix + pix;
-               F4 c = ps.xyz[slot];
-               if (c.w == 0) continue;
-               F2 sp = ps.spos[slot];
-               float dx = sp.x - 0.5f, dy = sp.y - 0.5f;
-               int x0 = imax(tox, (int)ceilf(dx - fw)), x1 = imin(txmax, (int)floorf(dx + fw));
-               int y0 = imax(toy, (int)ceilf(dy - fh)), y1 = imin(tymax, (int)floorf(dy + fh));
-               if (x < x0 || x > x1 || y < y0 || y > y1) continue;
-               int tix = imin((int)floorf(fabsf(((float)x - dx) * ifw * 16.0f)), 15);
-               int tiy = imin((int)floorf(fabsf(((float)y - dy) * ifh * 16.0f)), 15);
-               float w = S.ftbl[tiy * 16 + tix];
-               aw = aw + w; ax = ax + c.x * w; ay = ay + c.y * w; az = az + c.z * w;
+               filmAddSample(S, g, x, y, tox, txmax, toy, tymax, ps.xyz[slot], ps.spos[slot], aw, ax, ay, az);
             }
          }
       }

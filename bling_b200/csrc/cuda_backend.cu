@@ -34,6 +34,61 @@ template <class B> __global__ void __launch_bounds__(128, SH_MINBLOCKS) kRunQueu
    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b(q[i]);
 }
 
+// K7 film, tiled: one CTA per 16x16 film-pixel tile. For every sample index of the batch the samples of all sample pixels
+// that can reach the tile ((16 + 2R + 1)^2 of them) are staged in shared memory once, then every thread gathers its own
+// (2R + 1)^2 neighbourhood from there: each sample is read from L2 once per tile instead of once per reached pixel.
+// Atomic-free; same per-sample arithmetic as FilmBody (bodies.h), summed sample-index-major.
+#define FT_TILE 16
+#define FT_MAXC 24   // staged cells per axis: 16 + floor(f + 0.5) + ceil(f + 0.5) + 1 <= 24  <=>  filter radius <= 3.5
+__global__ void __launch_bounds__(FT_TILE * FT_TILE) kFilmTile(const DScene *__restrict__ sc, PathState ps, F4 *__restrict__ film, uint32_t k, uint32_t npix) {
+   __shared__ F4 sXyz[FT_MAXC * FT_MAXC];
+   __shared__ F2 sPos[FT_MAXC * FT_MAXC];
+   const DScene &S = *sc;
+   const FilmGeom g = filmGeom(S);
+   const int tilesX = (S.W + FT_TILE - 1) / FT_TILE;
+   const int X0 = (int)(blockIdx.x % (unsigned)tilesX) * FT_TILE, Y0 = (int)(blockIdx.x / (unsigned)tilesX) * FT_TILE;
+   const int tx = (int)threadIdx.x % FT_TILE, ty = (int)threadIdx.x / FT_TILE;
+   const int x = X0 + tx, y = Y0 + ty;
+   const bool inside = x < S.W && y < S.H;
+   // cells staged for the whole tile, and this thread's own neighbourhood inside them
+   const int cx0 = filmCellLo(X0, g.fw), cy0 = filmCellLo(Y0, g.fh);
+   const int ncx = filmCellHi(X0 + FT_TILE - 1, g.fw) - cx0 + 1, ncy = filmCellHi(Y0 + FT_TILE - 1, g.fh) - cy0 + 1;
+   const int ixlo = imax(S.ex0, filmCellLo(x, g.fw)), ixhi = imin(S.ex1, filmCellHi(x, g.fw));
+   const int iylo = imax(S.ey0, filmCellLo(y, g.fh)), iyhi = imin(S.ey1, filmCellHi(y, g.fh));
+   float aw = 0, ax = 0, ay = 0, az = 0;
+   for (uint32_t sl = 0; sl < k; ++sl) {
+      for (int c = (int)threadIdx.x; c < ncx * ncy; c += FT_TILE * FT_TILE) {
+         const int ix = cx0 + c % ncx, iy = cy0 + c / ncx;
+         F4 v; v.x = v.y = v.z = v.w = 0; F2 p; p.x = p.y = 0;
+         if (ix >= S.ex0 && ix <= S.ex1 && iy >= S.ey0 && iy <= S.ey1) {
+            const uint32_t slot = sl * npix + (uint32_t)(iy - S.ey0) * (uint32_t)S.EW + (uint32_t)(ix - S.ex0);
+            v = ps.xyz[slot]; p = ps.spos[slot];
+         }
+         sXyz[c] = v; sPos[c] = p;
+      }
+      __syncthreads();
+      if (inside) {
+         for (int iy = iylo; iy <= iyhi; ++iy) {
+            int toy, tymax; filmTileSpan(iy, S.ey0, S.ey1, g.exty, toy, tymax);
+            if (y < toy || y > tymax) continue;
+            for (int ix = ixlo; ix <= ixhi; ++ix) {
+               int tox, txmax; filmTileSpan(ix, S.ex0, S.ex1, g.extx, tox, txmax);
+               if (x < tox || x > txmax) continue;
+               const int c = (iy - cy0) * ncx + (ix - cx0);
+               filmAddSample(S, g, x, y, tox, txmax, toy, tymax, sXyz[c], sPos[c], aw, ax, ay, az);
+            }
+         }
+      }
+      __syncthreads();
+   }
+   if (inside) {
+      const size_t fp = (size_t)y * S.W + x;
+      F4 f = film[fp];
+      f.x = f.x + aw; f.y = f.y + ax; f.z = f.z + ay; f.w = f.w + az;
+      film[fp] = f;
+   }
+}
+
 struct CudaBackend {
    int device = -1, sms = 148;
    cudaStream_t stream = nullptr, ownStream = nullptr;
@@ -155,6 +210,21 @@ struct CudaBackend {
       if (bound == 0) return;
       Scope sc_(this);
       kRunQueue<B><<<gridFor(bound, 256, resident(kRunQueue<B>, 256)), 256, 0, stream>>>(b, q, cnt);
+   }
+   // film: tiled shared-memory kernel whenever the filter fits its staging area, else the per-pixel gather
+   void run(const FilmBody &b, uint32_t n) {
+      if (n == 0) return;
+      Scope sc_(this);
+      if (filmTiled) {
+         const uint32_t tiles = (uint32_t)((filmW + FT_TILE - 1) / FT_TILE) * (uint32_t)((filmH + FT_TILE - 1) / FT_TILE);
+         kFilmTile<<<tiles, FT_TILE * FT_TILE, 0, stream>>>(b.sc, b.ps, b.film, b.k, b.npix);
+      } else kRun<FilmBody><<<gridFor(n, 256, resident(kRun<FilmBody>, 256)), 256, 0, stream>>>(b, n);
+   }
+   bool filmTiled = false; int filmW = 0, filmH = 0;
+   void setFilm(int w, int h, float fw, float fh) {
+      filmW = w; filmH = h;
+      auto cells = [](float f) { return FT_TILE + (int)floorf(f + 0.5f) + (int)ceilf(f + 0.5f) + 1; };
+      filmTiled = cells(fw) <= FT_MAXC && cells(fh) <= FT_MAXC;
    }
    template <int MK> void runQueue(const ShadeHitBody<MK> &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
       if (bound == 0) return;

@@ -141,7 +141,7 @@ struct Pipeline {
       hs.bvh.items = up<F4>(items.data(), items.size());
       hs.bvh.root = bo.root; hs.bvh.n_nodes = bo.n_nodes; hs.bvh.max_stack = bo.max_stack;
       if (bo.max_stack > BL_STACK) { std::free(bo.nodes); std::free(bo.order); return fail(BLINGCU_EINVAL, "acceleration structure too deep for the traversal stack"); }
-      nNodes = (uint64_t)bo.n_nodes; nItems = nprim; be.setMaxStack(bo.max_stack);
+      nNodes = (uint64_t)bo.n_nodes; nItems = nprim; be.setMaxStack(bo.max_stack); be.setFilm(ir->width, ir->height, ir->filter_w, ir->filter_h);
       std::free(bo.nodes); std::free(bo.order);
       // ---- shading geometry
       {

@@ -19,6 +19,7 @@ struct EmuBackend {
    void sync() {}
    void setStream(void *) {}
    void setMaxStack(int) {}
+   void setFilm(int, int, float, float) {}
    double timerRead(double last) { return last; }
    void tag(int) {}
    void kernelTimes(double *ms, uint64_t *l, int n) { for (int i = 0; i < n; ++i) { ms[i] = 0; l[i] = 0; } }
