@@ -145,6 +145,8 @@ struct CudaBackend {
    void shutdown() {
       if (device >= 0) cudaSetDevice(device);
       if (stream) cudaStreamSynchronize(stream);
+      if (tcfg.workCounter) { cudaFree(tcfg.workCounter); tcfg.workCounter = nullptr; }
+      if (tcfg.travCounters) { cudaFree(tcfg.travCounters); tcfg.travCounters = nullptr; }
       if (ownStream) { cudaStreamDestroy(ownStream); ownStream = nullptr; }
       stream = nullptr;
       collect(); for (cudaEvent_t e : pool) cudaEventDestroy(e); pool.clear();
