@@ -4,8 +4,8 @@
 // variant 0  one ray per thread, grid-stride, traversal stack in local memory (the reference point)
 // variant 1  persistent warps, one ray per lane, majority-vote stepping, LDG.256 node fetch, shared-memory stack
 //            (kTracePersistent below; the product path)
-// B200 has no RT cores and traversal is not a contraction: no tensor cores here. The bound is L2/HBM latency
-// and bandwidth on the node/triangle fetches (DESIGN.md "Roofline").
+// B200 has no RT cores and traversal is not a contraction: no tensor cores here. Measured limiters (DESIGN.md §5,
+// profiles/): the ALU pipe and issue slots of the slab/sort/push arithmetic, then the LSU data pipe; HBM is at 9-17 %.
 #pragma once
 #include "bodies.h"
 #include <cuda_runtime.h>
@@ -79,9 +79,10 @@ __global__ void __launch_bounds__(128) kTraceNearestCount(const uint32_t *__rest
 // inner node or inside a leaf, and the whole warp executes ONLY that step, predicated per lane (2.1x). v3 went to
 // 4-wide nodes; ncu then showed the LSU data pipe at 81 % because a node cost 7 LDG.128 per lane, each one L1
 // wavefront per lane. v4 (one ray per quad) cut the wavefronts 4x but doubled the instructions per ray. This
-// version keeps one ray per lane, fetches a (now 64-byte, quantised: bvh.h) node as 2 x LDG.256, keeps the
-// whole traversal stack in shared memory (sized from the builder's worst case, no local-memory tail), and refills
-// idle lanes from the global queue with a warp-aggregated atomic once enough lanes have retired.
+// version keeps one ray per lane, fetches a (now 64-byte, quantised: bvh.h) node as 2 x LDG.256, keeps the first
+// TR_SS levels of the traversal stack in shared memory (PTX-predicated pushes/pops, no compiler-made branches) with a
+// local-memory tail for deeper trees, writes accepted hits straight to the output record, and refills idle lanes
+// from the global queue with a warp-aggregated atomic once enough lanes have retired.
 #define TR_THREADS 128
 #ifndef TR_REFILL
 #define TR_REFILL 4       // refill once this many lanes are idle
