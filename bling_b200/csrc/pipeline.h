@@ -66,12 +66,12 @@ struct Pipeline {
       for (uint32_t i = 0; i < ir->n_materials; ++i) {
          const blingcu_material &m = ir->materials[i];
          if (m.kind < 0 || m.kind >= BLINGCU_MAT_KINDS) return fail(BLINGCU_EINVAL, "unknown material kind");
-         int need = (m.kind == BLINGCU_MAT_MATTE || m.kind == BLINGCU_MAT_MIRROR) ? 1 : (m.kind == BLINGCU_MAT_BLACKBODY ? 0 : 2);
-         for (int k = 0; k < need; ++k) if (m.tex[k] < 0 || (uint32_t)m.tex[k] >= ir->n_textures) return fail(BLINGCU_EINVAL, "material texture out of range");
+         int need = (m.kind == BLINGCU_MAT_MATTE || m.kind == BLINGCU_MAT_MIRROR) ? 1 : (m.kind == BLINGCU_MAT_BLACKBODY ? 0 : (m.kind == BLINGCU_MAT_SHINYMETAL ? 4 : 2));
+         for (int k = 0; k < need; ++k) { int tx = k < 3 ? m.tex[k] : m.tex3; if (tx < 0 || (uint32_t)tx >= ir->n_textures) return fail(BLINGCU_EINVAL, "material texture out of range"); }
       }
       for (uint32_t i = 0; i < ir->n_textures; ++i) {
          const blingcu_texture &t = ir->textures[i];
-         if (t.kind == BLINGCU_TEX_GRAPHPAPER) { for (int k = 0; k < 2; ++k) if (t.child[k] < 0 || (uint32_t)t.child[k] >= ir->n_textures) return fail(BLINGCU_EINVAL, "texture child out of range"); }
+         if (t.kind == BLINGCU_TEX_GRAPHPAPER || t.kind == BLINGCU_TEX_CHECKER) { for (int k = 0; k < 2; ++k) if (t.child[k] < 0 || (uint32_t)t.child[k] >= ir->n_textures) return fail(BLINGCU_EINVAL, "texture child out of range"); }
          else if (t.kind != BLINGCU_TEX_CONSTANT) return fail(BLINGCU_EINVAL, "unknown texture kind");
       }
       for (uint32_t i = 0; i < ir->n_lights; ++i) {
@@ -230,6 +230,8 @@ struct Pipeline {
                case BLINGCU_MAT_MIRROR: be.runQueue(ShadeHitBody<BLINGCU_MAT_MIRROR>{dscene, ps, qb}, qk, ck, bound); break;
                case BLINGCU_MAT_PLASTIC: be.runQueue(ShadeHitBody<BLINGCU_MAT_PLASTIC>{dscene, ps, qb}, qk, ck, bound); break;
                case BLINGCU_MAT_METAL: be.runQueue(ShadeHitBody<BLINGCU_MAT_METAL>{dscene, ps, qb}, qk, ck, bound); break;
+               case BLINGCU_MAT_SHINYMETAL: be.runQueue(ShadeHitBody<BLINGCU_MAT_SHINYMETAL>{dscene, ps, qb}, qk, ck, bound); break;
+               case BLINGCU_MAT_TRANSMATTE: be.runQueue(ShadeHitBody<BLINGCU_MAT_TRANSMATTE>{dscene, ps, qb}, qk, ck, bound); break;
                default: be.runQueue(ShadeHitBody<BLINGCU_MAT_BLACKBODY>{dscene, ps, qb}, qk, ck, bound); break;
                }
                launches++;

@@ -164,15 +164,25 @@ template <> struct MatOf<BLINGCU_MAT_GLASS> { static const unsigned KM = BL_K(2)
 template <> struct MatOf<BLINGCU_MAT_MIRROR> { static const unsigned KM = BL_K(2), FM = BL_K(0); static const int NC = 1, MK = BLINGCU_MAT_MIRROR; };
 template <> struct MatOf<BLINGCU_MAT_PLASTIC> { static const unsigned KM = BL_K(0) | BL_K(4), FM = BL_K(1); static const int NC = 2, MK = BLINGCU_MAT_PLASTIC; };
 template <> struct MatOf<BLINGCU_MAT_METAL> { static const unsigned KM = BL_K(4), FM = BL_K(2); static const int NC = 1, MK = BLINGCU_MAT_METAL; };
+template <> struct MatOf<BLINGCU_MAT_SHINYMETAL> { static const unsigned KM = BL_K(2) | BL_K(4), FM = BL_K(2); static const int NC = 2, MK = BLINGCU_MAT_SHINYMETAL; };
+template <> struct MatOf<BLINGCU_MAT_TRANSMATTE> { static const unsigned KM = BL_K(0) | BL_K(1), FM = 0u; static const int NC = 2, MK = BLINGCU_MAT_TRANSMATTE; };
 template <> struct MatOf<BLINGCU_MAT_BLACKBODY> { static const unsigned KM = 0u, FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_BLACKBODY; };
 
 struct BxDF {
    int kind, type, fr, clamp01;   // clamp01: sClamp' applied to r on read (glass, mirror; Material.hs:63-64,71)
+   int flip;                      // brdfToBtdf (Reflection.hs:188-195): the BRDF seen through the other hemisphere
    const float *r;                // reflectance / transmittance spectrum; null = white
+   const float *r2;               // translucentMatte: r is scaled by (1 - clamp01 r2) (Material.hs:51)
    const float *eta, *k;          // conductor
    float a, b, e, etai, etat;     // OrenNayar A,B ; Blinn exponent ; dielectric indices
 };
-HD float bxR(const BxDF &b, int i) { float v = b.r ? b.r[i] : 1.0f; return b.clamp01 ? hmaxf(0.0f, hminf(1.0f, v)) : v; }
+HD float bxR(const BxDF &b, int i) {
+   float v = b.r ? b.r[i] : 1.0f;
+   if (b.clamp01) v = hmaxf(0.0f, hminf(1.0f, v));
+   if (b.r2) v = v * (1.0f - hmaxf(0.0f, hminf(1.0f, b.r2[i])));
+   return v;
+}
+HD V3 flipZ(V3 w) { return mk3(w.x, w.y, -w.z); }
 HD Spec bxScaledR(const BxDF &b, float f) { Spec s; BL_UNROLL for (int i = 0; i < NB; ++i) s.v[i] = bxR(b, i) * f; return s; }
 // r * fr(cosi) (spectral product, then the caller scales)
 template <class M = AnyMat>
@@ -198,6 +208,7 @@ HD float orenNayarF(const BxDF &b, V3 wo, V3 wi) {   // Diffuse.hs:52-65 (scalar
 // bxdfEval b wo wi -- callers pass flipped arguments for the non-adjoint case (Reflection.hs:310,330)
 template <class M = AnyMat>
 HD Spec bxdfEval(const BxDF &b, V3 wo, V3 wi) {
+   if (M::MK == BLINGCU_MAT_TRANSMATTE || M::MK < 0) { if (b.flip) wi = flipZ(wi); }
    if ((M::KM & BL_K(K_LAMBERT)) && b.kind == K_LAMBERT) return bxScaledR(b, BL_INVPI * absCosTheta(wo));
    if ((M::KM & BL_K(K_ORENNAYAR)) && b.kind == K_ORENNAYAR) return sScale(bxScaledR(b, orenNayarF(b, wo, wi)), BL_INVPI * absCosTheta(wo));
    if ((M::KM & BL_K(K_MICROFACET)) && b.kind == K_MICROFACET) {   // Microfacet.hs:20-33
@@ -216,6 +227,7 @@ HD Spec bxdfEval(const BxDF &b, V3 wo, V3 wi) {
 HD float cosPdf(V3 wo, V3 wi) { return sameHemisphere(wo, wi) ? BL_INVPI * absCosTheta(wi) : 0.0f; }
 template <class M = AnyMat>
 HD float bxdfPdf(const BxDF &b, V3 wo, V3 wi) {
+   if (M::MK == BLINGCU_MAT_TRANSMATTE || M::MK < 0) { if (b.flip) wi = flipZ(wi); }
    if ((M::KM & (BL_K(K_LAMBERT) | BL_K(K_ORENNAYAR))) && (b.kind == K_LAMBERT || b.kind == K_ORENNAYAR)) return cosPdf(wo, wi);
    if ((M::KM & BL_K(K_MICROFACET)) && b.kind == K_MICROFACET) {   // Microfacet.hs:35-41
       V3 whp = wo + wi;
@@ -232,6 +244,7 @@ HD void bxdfSample(const BxDF &b, V3 wo, float u1, float u2, Spec &f, V3 &wi, fl
       wi = toSameHemisphere(wo, cosineSampleHemisphere(u1, u2));
       if (sameHemisphere(wo, wi)) { f = bxScaledR(b, b.kind == K_LAMBERT ? 1.0f : orenNayarF(b, wo, wi)); pdf = cosPdf(wo, wi); }
       else { f = sConst(0); pdf = 0; }
+      if (M::MK == BLINGCU_MAT_TRANSMATTE || M::MK < 0) { if (b.flip) wi = flipZ(wi); }
       return;
    }
    if ((M::KM & BL_K(K_SPECREFL)) && b.kind == K_SPECREFL) { f = bxRFresnel<M>(b, cosTheta(wo)); wi = mk3(-wo.x, -wo.y, wo.z); pdf = 1; return; }   // Specular.hs:11-20
@@ -325,6 +338,11 @@ HD const float *evalSpectrumTexture(const DScene &sc, int id, const DG &dg) {   
    for (int guard = 0; guard < 16; ++guard) {
       const blingcu_texture &t = sc.textures[id];
       if (t.kind == BLINGCU_TEX_CONSTANT) return t.s.v;
+      if (t.kind == BLINGCU_TEX_CHECKER) {   // Texture.hs:209-221; Haskell `mod` 2 of a sum of floors: parity of the sum
+         int q = (int)floorf(dg.p.x * t.f[0]) + (int)floorf(dg.p.y * t.f[1]) + (int)floorf(dg.p.z * t.f[2]);
+         id = ((q & 1) == 0) ? t.child[0] : t.child[1];
+         continue;
+      }
       float x = t.f[1] * dg.u + t.f[3], z = t.f[2] * dg.v + t.f[4];   // uvMapping :166-170
       float xp = fabsf(x - truncf(x)), zp = fabsf(z - truncf(z));      // properFraction
       float lo = t.f[0] / 2, hi = 1.0f - lo;
@@ -379,7 +397,7 @@ HD void makeBsdf(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b)
    const blingcu_material &m = sc.materials[sh.material];
    const int mk = (M::MK >= 0) ? M::MK : m.kind;   // compile-time constant in the per-kind shade kernels
    b.n = 0;
-   BL_UNROLL for (int i = 0; i < 2; ++i) { BxDF &x = b.bx[i]; x.kind = 0; x.type = 0; x.fr = FR_NOOP; x.clamp01 = 0; x.r = 0; x.eta = 0; x.k = 0; x.a = x.b = x.e = 0; x.etai = x.etat = 1; }
+   BL_UNROLL for (int i = 0; i < 2; ++i) { BxDF &x = b.bx[i]; x.kind = 0; x.type = 0; x.fr = FR_NOOP; x.clamp01 = 0; x.flip = 0; x.r = 0; x.r2 = 0; x.eta = 0; x.k = 0; x.a = x.b = x.e = 0; x.etai = x.etat = 1; }
    switch (mk) {
    case BLINGCU_MAT_MATTE: {
       BxDF &x = b.bx[0]; x.r = evalSpectrumTexture(sc, m.tex[0], dgs); x.type = BX_REFLECTION | BX_DIFFUSE;
@@ -412,6 +430,23 @@ HD void makeBsdf(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b)
       BxDF &s = b.bx[0]; s.kind = K_MICROFACET; s.type = BX_REFLECTION | BX_GLOSSY; s.r = 0; s.fr = FR_CONDUCTOR;
       s.eta = evalSpectrumTexture(sc, m.tex[0], dgs); s.k = evalSpectrumTexture(sc, m.tex[1], dgs); s.e = fixExponent(1 / m.f[0]);
       b.n = 1; break;
+   }
+   case BLINGCU_MAT_SHINYMETAL: {   // Material.hs:98-108; eta / k textures already carry frApproxEta / frApproxK (host)
+      BxDF &d = b.bx[0], &sp = b.bx[1];
+      d.kind = K_MICROFACET; d.type = BX_REFLECTION | BX_GLOSSY; d.r = 0; d.fr = FR_CONDUCTOR;
+      d.eta = evalSpectrumTexture(sc, m.tex[0], dgs); d.k = evalSpectrumTexture(sc, m.tex[1], dgs); d.e = fixExponent(1 / m.f[0]);
+      sp.kind = K_SPECREFL; sp.type = BX_REFLECTION | BX_SPECULAR; sp.r = 0; sp.fr = FR_CONDUCTOR;
+      sp.eta = evalSpectrumTexture(sc, m.tex[2], dgs); sp.k = evalSpectrumTexture(sc, m.tex3, dgs);
+      b.n = 2; break;
+   }
+   case BLINGCU_MAT_TRANSMATTE: {   // Material.hs:43-53
+      BxDF &rf = b.bx[0], &tr = b.bx[1];
+      const float *kr = evalSpectrumTexture(sc, m.tex[0], dgs), *kt = evalSpectrumTexture(sc, m.tex[1], dgs);
+      float sg = m.f[0], a = 0, bb = 0; int kind = K_LAMBERT;
+      if (sg != 0) { kind = K_ORENNAYAR; float c = clampf(sg, 0, 1), sig2 = c * c; a = 1 - (sig2 / (2 * (sig2 + 0.33f))); bb = 0.45f * sig2 / (sig2 + 0.09f); }
+      rf.kind = kind; rf.type = BX_REFLECTION | BX_DIFFUSE; rf.r = kr; rf.clamp01 = 1; rf.a = a; rf.b = bb;
+      tr.kind = kind; tr.type = BX_TRANSMISSION | BX_DIFFUSE; tr.r = kt; tr.clamp01 = 1; tr.r2 = kr; tr.flip = 1; tr.a = a; tr.b = bb;
+      b.n = 2; break;
    }
    default: break;
    }

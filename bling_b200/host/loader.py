@@ -158,6 +158,7 @@ class Loader:
     def add_material(self, kind, texs, fs) -> int:
         m = IR.Material(); m.kind = kind
         for i in range(3): m.tex[i] = texs[i] if i < len(texs) else -1
+        m.tex3 = texs[3] if len(texs) > 3 else -1
         for i, v in enumerate(fs): m.f[i] = float(v)
         self.ir.materials.append(m); return len(self.ir.materials) - 1
 
@@ -204,10 +205,27 @@ class Loader:
             t = IR.Texture(); t.kind = IR.TEX_GRAPHPAPER; t.child[0] = c0; t.child[1] = c1
             IR.set_arr(t.f, [lw, su, sv, ou, ov])
             self.ir.textures.append(t); tid = len(self.ir.textures) - 1
+        elif tp == "checker":                # MaterialParser.hs:209 -> checkerBoard (Texture.hs:209-221)
+            sc = tk.vec()
+            c0 = self.p_spectrum_texture(tk, "tex1"); c1 = self.p_spectrum_texture(tk, "tex2")
+            t = IR.Texture(); t.kind = IR.TEX_CHECKER; t.child[0] = c0; t.child[1] = c1
+            IR.set_arr(t.f, list(sc))
+            self.ir.textures.append(t); tid = len(self.ir.textures) - 1
         else:
             raise NotImplementedError(f"spectrum texture {tp} (outside SURVEY §8)")
         tk.expect("}")
         return tid
+
+    def map_texture(self, tid: int, fn) -> int:
+        """A copy of spectrum-texture tree `tid` with `fn` applied to every constant leaf. Textures only SELECT among
+        constant leaves (graphPaper, checker), so f(tex dg) == tex' dg: this is how the host hands the device the
+        per-band eta / k spectra of shinyMetal (frApproxEta / frApproxK, Fresnel.hs:72-78) without per-hit arithmetic."""
+        t = self.ir.textures[tid]
+        if t.kind == IR.TEX_CONSTANT:
+            return self.const_tex(fn(np.array(list(t.s.v), F)))
+        n = IR.Texture.from_buffer_copy(t)
+        n.child[0] = self.map_texture(t.child[0], fn); n.child[1] = self.map_texture(t.child[1], fn)
+        self.ir.textures.append(n); return len(self.ir.textures) - 1
 
     def p_material_body(self, tk: Tokens) -> int:   # MaterialParser.hs:30-42
         t = tk.next()
@@ -219,6 +237,13 @@ class Loader:
             return self.add_material(IR.MAT_GLASS, [kr, kt], [ior])
         if t == "mirror":
             return self.add_material(IR.MAT_MIRROR, [self.p_spectrum_texture(tk, "kr")], [])
+        if t == "shinyMetal":                # pShinyMetal -> mkShinyMetal (Material.hs:98-108)
+            kr = self.p_spectrum_texture(tk, "kr"); ks = self.p_spectrum_texture(tk, "ks"); r = self.p_scalar_texture(tk, "rough")
+            return self.add_material(IR.MAT_SHINYMETAL, [self.map_texture(ks, S.fr_approx_eta), self.map_texture(ks, S.fr_approx_k),
+                                                         self.map_texture(kr, S.fr_approx_eta), self.map_texture(kr, S.fr_approx_k)], [r])
+        if t == "transMatte":                # pMatteTranslucent -> translucentMatte (Material.hs:43-53)
+            kr = self.p_spectrum_texture(tk, "kr"); kt = self.p_spectrum_texture(tk, "kt"); sg = self.p_scalar_texture(tk, "ks")
+            return self.add_material(IR.MAT_TRANSMATTE, [kr, kt], [sg])
         if t == "plastic":
             kd = self.p_spectrum_texture(tk, "kd"); ks = self.p_spectrum_texture(tk, "ks"); r = self.p_scalar_texture(tk, "rough")
             return self.add_material(IR.MAT_PLASTIC, [kd, ks], [r])

@@ -165,3 +165,15 @@ def sun_curves():
             IrregularSpd(list(zip(_T["koCurve_l"], _T["koCurve_a"]))),
             IrregularSpd(list(zip(_T["kgCurve_l"], _T["kgCurve_a"]))),
             IrregularSpd(list(zip(_T["kwaCurve_l"], _T["kwaCurve_a"]))))
+
+
+def fr_approx_eta(r: np.ndarray) -> np.ndarray:
+    """frApproxEta (Fresnel.hs:72-74): (1 + sqrt r') / (1 - sqrt r'), r' = clamp 0 0.999 r, in float32."""
+    rp = np.sqrt(np.clip(np.asarray(r, F), F(0), F(0.999))).astype(F)
+    return ((F(1) + rp) / (F(1) - rp)).astype(F)
+
+
+def fr_approx_k(r: np.ndarray) -> np.ndarray:
+    """frApproxK (Fresnel.hs:76-78): 2 * sqrt (refl / (1 - refl)), refl = clamp 0 0.999 r, in float32."""
+    refl = np.clip(np.asarray(r, F), F(0), F(0.999)).astype(F)
+    return (np.sqrt((refl / (F(1) - refl)).astype(F)).astype(F) * F(2)).astype(F)

@@ -15,8 +15,8 @@ import numpy as np
 BANDS = 16
 
 SHAPE_BOX, SHAPE_CYLINDER, SHAPE_DISK, SHAPE_QUAD, SHAPE_SPHERE = range(5)
-MAT_MATTE, MAT_GLASS, MAT_MIRROR, MAT_PLASTIC, MAT_METAL, MAT_BLACKBODY = range(6)
-TEX_CONSTANT, TEX_GRAPHPAPER = range(2)
+MAT_MATTE, MAT_GLASS, MAT_MIRROR, MAT_PLASTIC, MAT_METAL, MAT_BLACKBODY, MAT_SHINYMETAL, MAT_TRANSMATTE = range(8)
+TEX_CONSTANT, TEX_GRAPHPAPER, TEX_CHECKER = range(3)
 LIGHT_INFINITE, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_AREA = range(4)
 ENV_CONSTANT, ENV_RGBTABLE, ENV_SUNSKY = range(3)
 CAM_PERSPECTIVE, CAM_ENVIRONMENT = range(2)
@@ -44,7 +44,7 @@ class Texture(C.Structure):
 
 
 class Material(C.Structure):
-    _fields_ = [("kind", i32), ("tex", i32 * 3), ("f", f32 * 4)]
+    _fields_ = [("kind", i32), ("tex", i32 * 3), ("f", f32 * 3), ("tex3", i32)]
 
 
 class Light(C.Structure):

@@ -60,13 +60,18 @@ enum {
    BLINGCU_MAT_PLASTIC = 3, /* tex[0]=kd tex[1]=ks f[0]=rough             */
    BLINGCU_MAT_METAL = 4,   /* tex[0]=eta tex[1]=k f[0]=rough             */
    BLINGCU_MAT_BLACKBODY = 5, /* Reflection.hs:337-338: no BxDFs          */
-   BLINGCU_MAT_KINDS = 6
+   /* SURVEY §8(f)2, first slice of the remaining materials (Material.hs:43-53,98-108): */
+   BLINGCU_MAT_SHINYMETAL = 6, /* tex[0]=eta(ks) tex[1]=k(ks) tex[2]=eta(kr) tex3=k(kr) f[0]=rough: the HOST applies
+                                  frApproxEta / frApproxK (Fresnel.hs:72-78) to the leaves of the ks / kr texture trees */
+   BLINGCU_MAT_TRANSMATTE = 7, /* tex[0]=kr tex[1]=kt f[0]=sigma (translucentMatte)                                    */
+   BLINGCU_MAT_KINDS = 8
 };
 
 /* Texture.hs:159-207 */
 enum {
    BLINGCU_TEX_CONSTANT = 0,   /* s                                       */
-   BLINGCU_TEX_GRAPHPAPER = 1  /* f[0]=lineWidth f[1..4]=su sv ou ov (uvMapping), child[0]=paper child[1]=line */
+   BLINGCU_TEX_GRAPHPAPER = 1, /* f[0]=lineWidth f[1..4]=su sv ou ov (uvMapping), child[0]=paper child[1]=line */
+   BLINGCU_TEX_CHECKER = 2     /* checkerBoard (Texture.hs:209-221): f[0..2]=scale, child[0]=tex1 child[1]=tex2, on dgP  */
 };
 
 /* Light.hs:31-45 */
@@ -111,7 +116,8 @@ typedef struct blingcu_texture {
 typedef struct blingcu_material {
    int32_t kind;
    int32_t tex[3];
-   float f[4];
+   float f[3];
+   int32_t tex3;   /* fourth texture (shinyMetal); same size and offsets as before for everything else */
 } blingcu_material;
 
 typedef struct blingcu_light {

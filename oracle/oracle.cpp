@@ -40,6 +40,11 @@ static Spec evalSpectrumTexture(const Scene &sc, int id, const DG &dg) {
    for (int guard = 0; guard < 16; ++guard) {
       const blingcu_texture &t = sc.textures[id];
       if (t.kind == BLINGCU_TEX_CONSTANT) return fromC(t.s);
+      if (t.kind == BLINGCU_TEX_CHECKER) {   // checkerBoard (Texture.hs:209-221): (floor x*sx + floor y*sy + floor z*sz) `mod` 2 == 0
+         long q = (long)std::floor(dg.p.x * t.f[0]) + (long)std::floor(dg.p.y * t.f[1]) + (long)std::floor(dg.p.z * t.f[2]);
+         id = (((q % 2) + 2) % 2 == 0) ? t.child[0] : t.child[1];
+         continue;
+      }
       // graphPaper lw m p l (Texture.hs:191-207) with uvMapping (:166-170)
       float lw = t.f[0];
       float x = t.f[1] * dg.u + t.f[3], z = t.f[2] * dg.v + t.f[4];
@@ -116,6 +121,23 @@ static Bsdf makeBsdf(const Scene &sc, const Hit &hit) {
       spec.fr = FR_CONDUCTOR; spec.eta = evalSpectrumTexture(sc, m.tex[0], dgs); spec.k = evalSpectrumTexture(sc, m.tex[1], dgs);
       spec.e = fixExponent(1 / m.f[0]);
       b.bx[0] = spec; b.n = 1; break;
+   }
+   case BLINGCU_MAT_SHINYMETAL: {   // mkShinyMetal (Material.hs:98-108). The IR's four textures are ks / kr passed through
+      // frApproxEta / frApproxK (Fresnel.hs:72-78) leaf by leaf on the host (bling_b200/host/spectra.py)
+      BxDF diff{}; diff.kind = K_MICROFACET; diff.type = BX_REFLECTION | BX_GLOSSY; diff.r = sConst(1); diff.fr = FR_CONDUCTOR;
+      diff.eta = evalSpectrumTexture(sc, m.tex[0], dgs); diff.k = evalSpectrumTexture(sc, m.tex[1], dgs); diff.e = fixExponent(1 / m.f[0]);
+      BxDF spec{}; spec.kind = K_SPECREFL; spec.type = BX_REFLECTION | BX_SPECULAR; spec.r = sConst(1); spec.fr = FR_CONDUCTOR;
+      spec.eta = evalSpectrumTexture(sc, m.tex[2], dgs); spec.k = evalSpectrumTexture(sc, m.tex3, dgs);
+      b.bx[0] = diff; b.bx[1] = spec; b.n = 2; break;
+   }
+   case BLINGCU_MAT_TRANSMATTE: {   // translucentMatte (Material.hs:43-53)
+      Spec r = sClamp(0, 1, evalSpectrumTexture(sc, m.tex[0], dgs));
+      Spec t = sClamp(0, 1, evalSpectrumTexture(sc, m.tex[1], dgs)) * (sConst(1) - r);
+      float s = m.f[0];
+      BxDF refl = (s == 0) ? mkLambertian(r) : mkOrenNayar(r, s);
+      BxDF trans = (s == 0) ? mkLambertian(t) : mkOrenNayar(t, s);
+      trans.flip = true; trans.type = BX_TRANSMISSION | BX_DIFFUSE;   // bxdfTypeFlip [Reflection, Transmission]
+      b.bx[0] = refl; b.bx[1] = trans; b.n = 2; break;
    }
    default: break;  // blackbody: no BxDFs
    }

@@ -172,7 +172,9 @@ struct BxDF {
    float a, b;        // OrenNayar A,B
    int fr; float etai, etat; Spec eta, k;  // Fresnel
    float e;           // Blinn exponent
+   bool flip;         // brdfToBtdf (Reflection.hs:188-195): evaluated / sampled through the other hemisphere
 };
+static inline V3 otherHemisphere(V3 w) { return mk(w.x, w.y, -w.z); }
 
 static inline Spec fresnel(const BxDF &b, float cosi) {
    if (b.fr == FR_DIELECTRIC) return frDielectric(b.etai, b.etat, cosi);
@@ -203,6 +205,7 @@ static inline Spec orenNayar(const BxDF &b, V3 wo, V3 wi) {  // Diffuse.hs:52-65
 
 // bxdfEval b wo wi (the CALLER flips for non-adjoint, Reflection.hs:310,330)
 static inline Spec bxdfEval(const BxDF &b, V3 wo, V3 wi) {
+   if (b.flip) wi = otherHemisphere(wi);   // e wo wi = bxdfEval brdf wo (otherHemisphere wi)
    switch (b.kind) {
    case K_LAMBERT: return sScale(b.r, kInvPi * absCosTheta(wo));                          // Diffuse.hs:24-26
    case K_ORENNAYAR: return sScale(orenNayar(b, wo, wi), kInvPi * absCosTheta(wo));      // Diffuse.hs:50
@@ -222,6 +225,7 @@ static inline Spec bxdfEval(const BxDF &b, V3 wo, V3 wi) {
 }
 static inline float cosPdf(V3 wo, V3 wi) { return sameHemisphere(wo, wi) ? kInvPi * absCosTheta(wi) : 0; }  // Diffuse.hs:9-12
 static inline float bxdfPdf(const BxDF &b, V3 wo, V3 wi) {
+   if (b.flip) wi = otherHemisphere(wi);
    switch (b.kind) {
    case K_LAMBERT: case K_ORENNAYAR: return cosPdf(wo, wi);
    case K_MICROFACET: {  // Microfacet.hs:35-41
@@ -241,12 +245,14 @@ static inline void bxdfSample(const BxDF &b, V3 wo, float u1, float u2, Spec &f,
       wi = toSameHemisphere(wo, cosineSampleHemisphere(u1, u2));
       if (sameHemisphere(wo, wi)) { f = b.r; pdf = cosPdf(wo, wi); }
       else { f = sConst(0); wi = wo; pdf = 0; }
+      if (b.flip) wi = otherHemisphere(wi);   // s adj wo u = (f, otherHemisphere wi, pdf)
       return;
    }
    case K_ORENNAYAR: {  // Diffuse.hs:38-42
       wi = toSameHemisphere(wo, cosineSampleHemisphere(u1, u2));
       if (sameHemisphere(wo, wi)) { f = orenNayar(b, wo, wi); pdf = cosPdf(wo, wi); }
       else { f = sConst(0); pdf = 0; }
+      if (b.flip) wi = otherHemisphere(wi);
       return;
    }
    case K_SPECREFL: {  // Specular.hs:11-20

@@ -124,3 +124,30 @@ def test_quirk_q2_cornell_light():
     f = o.read_film(); Y = f[..., 2] / np.maximum(f[..., 0], 1e-9)
     assert Y[3:6, 14:18].max() > 5.0           # the lamp itself (top centre) is bright
     assert Y[20:, :].mean() > 0.01             # the room is lit
+
+
+def test_shiny_metal_host_transforms():
+    """frApproxEta / frApproxK (Fresnel.hs:72-78) as applied by the host to the leaves of the ks / kr textures."""
+    from bling_b200.host import spectra as S
+    r = np.array([0.0, 0.04, 0.25, 0.81, 0.999, 1.5, -0.3], np.float32)
+    rc = np.clip(r, 0, 0.999)
+    assert np.allclose(S.fr_approx_eta(r), (1 + np.sqrt(rc)) / (1 - np.sqrt(rc)), rtol=1e-6)
+    assert np.allclose(S.fr_approx_k(r), 2 * np.sqrt(rc / (1 - rc)), rtol=1e-6)
+    assert S.fr_approx_eta(r).dtype == np.float32 and np.isfinite(S.fr_approx_k(r)).all()
+
+
+def test_translucent_matte_transmits():
+    """a translucentMatte sheet between the camera and a light passes light (brdfToBtdf, Reflection.hs:188-195); with kt = 0
+    the same sheet is darker."""
+    from tests.conftest import small
+    sc = small(load_scene("extras"), 44, 30, 2, 2)
+    o = Oracle(sc); o.render_pass(1, 3, threads=4); lit = o.read_film()[..., 2].sum()
+    import copy
+    sc2 = copy.copy(sc); sc2.textures = [copy.copy(t) for t in sc.textures]
+    for m in sc2.materials:
+        if m.kind == IR.MAT_TRANSMATTE:
+            t = IR.Texture.from_buffer_copy(sc2.textures[m.tex[1]]); t.kind = IR.TEX_CONSTANT
+            for i in range(16): t.s.v[i] = 0.0
+            sc2.textures[m.tex[1]] = t
+    o2 = Oracle(sc2); o2.render_pass(1, 3, threads=4); dark = o2.read_film()[..., 2].sum()
+    assert lit > dark * 1.01
