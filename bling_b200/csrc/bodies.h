@@ -10,7 +10,7 @@
 
 namespace bl {
 
-enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MAT0 = 4, C_MISANY = 13, C_DROPPED = 14, C_MISCULL = 15, N_COUNTERS = 16 };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + material kind
+enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MISANY = 4, C_DROPPED = 5, C_MISCULL = 6, C_MAT0 = 8, N_COUNTERS = 8 + 1 + BLINGCU_MAT_KINDS };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + material kind
 enum { N_SHADE_KINDS = 1 + BLINGCU_MAT_KINDS };
 enum { S_SAMPLES = 0, S_CAM, S_EXT, S_MIS, S_SHADOW, S_DROPPED, S_MISCULL, S_MISANY, N_STATS = 12 };
 

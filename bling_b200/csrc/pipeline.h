@@ -66,7 +66,7 @@ struct Pipeline {
       for (uint32_t i = 0; i < ir->n_materials; ++i) {
          const blingcu_material &m = ir->materials[i];
          if (m.kind < 0 || m.kind >= BLINGCU_MAT_KINDS) return fail(BLINGCU_EINVAL, "unknown material kind");
-         int need = (m.kind == BLINGCU_MAT_MATTE || m.kind == BLINGCU_MAT_MIRROR) ? 1 : (m.kind == BLINGCU_MAT_BLACKBODY ? 0 : (m.kind == BLINGCU_MAT_SHINYMETAL ? 4 : 2));
+         int need = (m.kind == BLINGCU_MAT_MATTE || m.kind == BLINGCU_MAT_MIRROR) ? 1 : (m.kind == BLINGCU_MAT_BLACKBODY ? 0 : (m.kind == BLINGCU_MAT_SHINYMETAL ? 4 : (m.kind == BLINGCU_MAT_SUBSTRATE ? 3 : 2)));
          for (int k = 0; k < need; ++k) { int tx = k < 3 ? m.tex[k] : m.tex3; if (tx < 0 || (uint32_t)tx >= ir->n_textures) return fail(BLINGCU_EINVAL, "material texture out of range"); }
       }
       for (uint32_t i = 0; i < ir->n_textures; ++i) {
@@ -232,6 +232,7 @@ struct Pipeline {
                case BLINGCU_MAT_METAL: be.runQueue(ShadeHitBody<BLINGCU_MAT_METAL>{dscene, ps, qb}, qk, ck, bound); break;
                case BLINGCU_MAT_SHINYMETAL: be.runQueue(ShadeHitBody<BLINGCU_MAT_SHINYMETAL>{dscene, ps, qb}, qk, ck, bound); break;
                case BLINGCU_MAT_TRANSMATTE: be.runQueue(ShadeHitBody<BLINGCU_MAT_TRANSMATTE>{dscene, ps, qb}, qk, ck, bound); break;
+               case BLINGCU_MAT_SUBSTRATE: be.runQueue(ShadeHitBody<BLINGCU_MAT_SUBSTRATE>{dscene, ps, qb}, qk, ck, bound); break;
                default: be.runQueue(ShadeHitBody<BLINGCU_MAT_BLACKBODY>{dscene, ps, qb}, qk, ck, bound); break;
                }
                launches++;

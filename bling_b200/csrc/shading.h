@@ -150,13 +150,13 @@ HD bool sameHemisphere(V3 a, V3 b) { return a.z * b.z > 0; }
 HD V3 toSameHemisphere(V3 wo, V3 wi) { return wo.z < 0 ? mk3(wi.x, wi.y, -wi.z) : wi; }
 
 enum { BX_REFLECTION = 1, BX_TRANSMISSION = 2, BX_DIFFUSE = 4, BX_GLOSSY = 8, BX_SPECULAR = 16 };
-enum { K_LAMBERT = 0, K_ORENNAYAR, K_SPECREFL, K_SPECTRANS, K_MICROFACET };
+enum { K_LAMBERT = 0, K_ORENNAYAR, K_SPECREFL, K_SPECTRANS, K_MICROFACET, K_FRESNELBLEND };
 enum { FR_NOOP = 0, FR_DIELECTRIC, FR_CONDUCTOR };
 
 // Compile-time description of what a material can contain. The shade kernel is launched once per material KIND
 // (material-sorted queues), so each launch is instantiated for its kind and the BxDF code of every other kind drops
 // out (fewer registers, more resident warps). AnyMat keeps everything (resolve kernels, generic callers).
-struct AnyMat { static const unsigned KM = 0x1fu, FM = 0x7u; static const int NC = 2, MK = -1; };
+struct AnyMat { static const unsigned KM = 0x3fu, FM = 0x7u; static const int NC = 2, MK = -1; };
 template <int MATKIND> struct MatOf : AnyMat {};
 #define BL_K(k) (1u << (k))
 template <> struct MatOf<BLINGCU_MAT_MATTE> { static const unsigned KM = BL_K(0) | BL_K(1), FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_MATTE; };
@@ -166,6 +166,7 @@ template <> struct MatOf<BLINGCU_MAT_PLASTIC> { static const unsigned KM = BL_K(
 template <> struct MatOf<BLINGCU_MAT_METAL> { static const unsigned KM = BL_K(4), FM = BL_K(2); static const int NC = 1, MK = BLINGCU_MAT_METAL; };
 template <> struct MatOf<BLINGCU_MAT_SHINYMETAL> { static const unsigned KM = BL_K(2) | BL_K(4), FM = BL_K(2); static const int NC = 2, MK = BLINGCU_MAT_SHINYMETAL; };
 template <> struct MatOf<BLINGCU_MAT_TRANSMATTE> { static const unsigned KM = BL_K(0) | BL_K(1), FM = 0u; static const int NC = 2, MK = BLINGCU_MAT_TRANSMATTE; };
+template <> struct MatOf<BLINGCU_MAT_SUBSTRATE> { static const unsigned KM = BL_K(5), FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_SUBSTRATE; };
 template <> struct MatOf<BLINGCU_MAT_BLACKBODY> { static const unsigned KM = 0u, FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_BLACKBODY; };
 
 struct BxDF {
@@ -173,8 +174,9 @@ struct BxDF {
    int flip;                      // brdfToBtdf (Reflection.hs:188-195): the BRDF seen through the other hemisphere
    const float *r;                // reflectance / transmittance spectrum; null = white
    const float *r2;               // translucentMatte: r is scaled by (1 - clamp01 r2) (Material.hs:51)
-   const float *eta, *k;          // conductor
-   float a, b, e, etai, etat;     // OrenNayar A,B ; Blinn exponent ; dielectric indices
+   const float *eta, *k;          // conductor; FresnelBlend: eta = specular rs, k = absorption ra (both clamped on read)
+   float a, b, e, etai, etat;     // OrenNayar A,B ; Blinn exponent (FresnelBlend: Anisotropic ex) ; dielectric indices
+   float ey, depth;               // FresnelBlend: Anisotropic ey, coating depth
 };
 HD float bxR(const BxDF &b, int i) {
    float v = b.r ? b.r[i] : 1.0f;
@@ -205,6 +207,53 @@ HD float orenNayarF(const BxDF &b, V3 wo, V3 wi) {   // Diffuse.hs:52-65 (scalar
    if (sinti > 1e-4f && sinto > 1e-4f) maxcos = hmaxf(0, cosPhi(wi) * cosPhi(wo) + sinPhi(wi) * sinPhi(wo));
    return b.a + b.b * maxcos * sina * tanb;
 }
+// Anisotropic distribution (Microfacet.hs:140-173,184-192)
+HD float anisoE(float ex, float ey, V3 wh, float d) { return (ex * wh.x * wh.x + ey * wh.y * wh.y) / d; }
+HD float anisoPdf(float ex, float ey, V3 wh) {
+   float costh = absCosTheta(wh);
+   float e = anisoE(ex, ey, wh, hmaxf(0, 1 - costh * costh));
+   return sqrtf((ex + 1) * (ey + 1)) * BL_INVTWOPI * powf(costh, e);
+}
+HD float anisoD(float ex, float ey, V3 wh) {
+   float costh = absCosTheta(wh);
+   float d = 1 - costh * costh;
+   if (d == 0) return 0;
+   return sqrtf((ex + 2) * (ey + 2)) * BL_INVTWOPI * powf(costh, anisoE(ex, ey, wh, d));
+}
+HD void anisoQuad(float ex, float ey, float u, float u2, float &p, float &c) {   // smpFirstQuadrand
+   p = (ex == ey) ? BL_PI * u * 0.5f : atanf(sqrtf((ex + 1) / (ey + 1)) * tanf(BL_PI * u * 0.5f));
+   float cp = cosf(p), sp = sinf(p);
+   c = powf(u2, 1 / (ex * cp * cp + ey * sp * sp + 1));
+}
+HD void anisoSample(float ex, float ey, float u1, float u2, V3 &wh, float &pdf) {
+   float phi, cost, p;
+   if (u1 < 0.25f) { anisoQuad(ex, ey, 4 * u1, u2, p, cost); phi = p; }
+   else if (u1 < 0.50f) { anisoQuad(ex, ey, 4 * (0.5f - u1), u2, p, cost); phi = BL_PI - p; }
+   else if (u1 < 0.75f) { anisoQuad(ex, ey, 4 * (u1 - 0.5f), u2, p, cost); phi = p + BL_PI; }
+   else { anisoQuad(ex, ey, 4 * (1 - u1), u2, p, cost); phi = 2 * BL_PI - p; }
+   float sint = sqrtf(hmaxf(0, 1 - cost * cost));
+   wh = sphericalDirection(sint, cost, phi);
+   float e = anisoE(ex, ey, wh, 1 - cost * cost);
+   pdf = sqrtf((ex + 1) * (ey + 1)) * (BL_INVTWOPI * powf(cost, e));
+}
+HD V3 halfUp(V3 wi, V3 wo) { V3 w = normalize3(wi + wo); return w.z < 0 ? -w : w; }
+// FresnelBlend `e wo wi` (Microfacet.hs:65-84): r = rd, eta = rs, k = ra, all clamped to [0,1] (mkSubstrate)
+HD Spec fresnelBlendEval(const BxDF &b, V3 wo, V3 wi) {
+   float costi = absCosTheta(wi), costo = absCosTheta(wo);
+   float asc = -(b.depth * (costi + costo) / (costi * costo));
+   float ds = (costo * 28 / 23 * BL_PI) * (1 - powf(1 - 0.5f * costi, 5.0f)) * (1 - powf(1 - 0.5f * costo, 5.0f));
+   V3 wh = halfUp(wi, wo);
+   float costih = absDot(wi, wh);
+   float sch = powf(1 - costih, 5.0f);
+   float ss = anisoD(b.e, b.ey, wh) * costo / (4 * costih * hmaxf(costi, costo));
+   Spec f;
+   BL_UNROLL for (int i = 0; i < NB; ++i) {
+      float rd = hmaxf(0.0f, hminf(1.0f, b.r[i])), rs = hmaxf(0.0f, hminf(1.0f, b.eta[i])), ra = hmaxf(0.0f, hminf(1.0f, b.k[i]));
+      float a = (b.depth > 0) ? expf(ra * asc) : 1.0f;
+      f.v[i] = ((a * rd) * (1.0f - rs)) * ds + (rs + (1.0f - rs) * sch) * ss;
+   }
+   return f;
+}
 // bxdfEval b wo wi -- callers pass flipped arguments for the non-adjoint case (Reflection.hs:310,330)
 template <class M = AnyMat>
 HD Spec bxdfEval(const BxDF &b, V3 wo, V3 wi) {
@@ -222,6 +271,7 @@ HD Spec bxdfEval(const BxDF &b, V3 wo, V3 wi) {
       float x = (b.e + 2) * BL_INVTWOPI * powf(absCosTheta(wh), b.e) * mfG(wo, wi, wh) / (4 * costi);
       return sScale(bxRFresnel<M>(b, costh), x);
    }
+   if ((M::KM & BL_K(K_FRESNELBLEND)) && b.kind == K_FRESNELBLEND) return fresnelBlendEval(b, wo, wi);
    return sConst(0);
 }
 HD float cosPdf(V3 wo, V3 wi) { return sameHemisphere(wo, wi) ? BL_INVPI * absCosTheta(wi) : 0.0f; }
@@ -235,6 +285,11 @@ HD float bxdfPdf(const BxDF &b, V3 wo, V3 wi) {
       V3 wh = normalize3(whp);
       if (cosTheta(wh) < 0) return 0;
       return (b.e + 1) * powf(absCosTheta(wh), b.e) * BL_INVTWOPI / (4 * absDot(wo, wh));
+   }
+   if ((M::KM & BL_K(K_FRESNELBLEND)) && b.kind == K_FRESNELBLEND) {   // Microfacet.hs:103-108
+      if (!sameHemisphere(wo, wi)) return 0;
+      V3 wh = halfUp(wi, wo);
+      return 0.5f * (absCosTheta(wi) * BL_INVPI + anisoPdf(b.e, b.ey, wh) / (4 * absDot(wo, wh)));
    }
    return 0;
 }
@@ -261,7 +316,22 @@ HD void bxdfSample(const BxDF &b, V3 wo, float u1, float u2, Spec &f, V3 &wi, fl
       pdf = 1;
       return;
    }
-   if (M::KM & BL_K(K_MICROFACET)) {   // microfacet, Blinn (Microfacet.hs:43-54,175-182)
+   if ((M::KM & BL_K(K_FRESNELBLEND)) && b.kind == K_FRESNELBLEND) {   // Microfacet.hs:86-101, adj = False
+      float pdfp; V3 wh;
+      if (u1 < 0.5f) {
+         wi = toSameHemisphere(wo, cosineSampleHemisphere(u1 * 2, u2));
+         wh = halfUp(wi, wo);
+         pdfp = anisoPdf(b.e, b.ey, wh);
+      } else {
+         anisoSample(b.e, b.ey, 2 * (u1 - 0.5f), u2, wh, pdfp);
+         wi = scl(2, scl(dot3(wo, wh), wh)) - wo;
+      }
+      if (pdfp == 0) { f = sConst(0); pdf = 0; return; }
+      pdf = 0.5f * (absCosTheta(wi) * BL_INVPI + pdfp / (4 * absDot(wo, wh)));
+      f = sScale(fresnelBlendEval(b, wo, wi), 1 / pdf);
+      return;
+   }
+   if ((M::KM & BL_K(K_MICROFACET)) && (M::MK >= 0 || b.kind == K_MICROFACET)) {   // microfacet, Blinn (Microfacet.hs:43-54,175-182)
       float cost = powf(u1, 1 / (b.e + 1));
       float sint = sqrtf(hmaxf(0, 1 - cost * cost));
       V3 whp = sphericalDirection(sint, cost, u2 * 2 * BL_PI);
@@ -397,7 +467,7 @@ HD void makeBsdf(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b)
    const blingcu_material &m = sc.materials[sh.material];
    const int mk = (M::MK >= 0) ? M::MK : m.kind;   // compile-time constant in the per-kind shade kernels
    b.n = 0;
-   BL_UNROLL for (int i = 0; i < 2; ++i) { BxDF &x = b.bx[i]; x.kind = 0; x.type = 0; x.fr = FR_NOOP; x.clamp01 = 0; x.flip = 0; x.r = 0; x.r2 = 0; x.eta = 0; x.k = 0; x.a = x.b = x.e = 0; x.etai = x.etat = 1; }
+   BL_UNROLL for (int i = 0; i < 2; ++i) { BxDF &x = b.bx[i]; x.kind = 0; x.type = 0; x.fr = FR_NOOP; x.clamp01 = 0; x.flip = 0; x.r = 0; x.r2 = 0; x.eta = 0; x.k = 0; x.a = x.b = x.e = 0; x.etai = x.etat = 1; x.ey = 0; x.depth = 0; }
    switch (mk) {
    case BLINGCU_MAT_MATTE: {
       BxDF &x = b.bx[0]; x.r = evalSpectrumTexture(sc, m.tex[0], dgs); x.type = BX_REFLECTION | BX_DIFFUSE;
@@ -438,6 +508,12 @@ HD void makeBsdf(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b)
       sp.kind = K_SPECREFL; sp.type = BX_REFLECTION | BX_SPECULAR; sp.r = 0; sp.fr = FR_CONDUCTOR;
       sp.eta = evalSpectrumTexture(sc, m.tex[2], dgs); sp.k = evalSpectrumTexture(sc, m.tex3, dgs);
       b.n = 2; break;
+   }
+   case BLINGCU_MAT_SUBSTRATE: {   // mkSubstrate (Material.hs:110-127)
+      BxDF &fb = b.bx[0]; fb.kind = K_FRESNELBLEND; fb.type = BX_REFLECTION | BX_GLOSSY;
+      fb.r = evalSpectrumTexture(sc, m.tex[0], dgs); fb.eta = evalSpectrumTexture(sc, m.tex[1], dgs); fb.k = evalSpectrumTexture(sc, m.tex[2], dgs);
+      fb.e = fixExponent(1 / hmaxf(0.0f, m.f[0])); fb.ey = fixExponent(1 / hmaxf(0.0f, m.f[1])); fb.depth = m.f[2];
+      b.n = 1; break;
    }
    case BLINGCU_MAT_TRANSMATTE: {   // Material.hs:43-53
       BxDF &rf = b.bx[0], &tr = b.bx[1];

@@ -241,6 +241,10 @@ class Loader:
             kr = self.p_spectrum_texture(tk, "kr"); ks = self.p_spectrum_texture(tk, "ks"); r = self.p_scalar_texture(tk, "rough")
             return self.add_material(IR.MAT_SHINYMETAL, [self.map_texture(ks, S.fr_approx_eta), self.map_texture(ks, S.fr_approx_k),
                                                          self.map_texture(kr, S.fr_approx_eta), self.map_texture(kr, S.fr_approx_k)], [r])
+        if t == "substrate":                 # pSubstrateMaterial -> mkSubstrate (Material.hs:110-127)
+            kd = self.p_spectrum_texture(tk, "kd"); ks = self.p_spectrum_texture(tk, "ks"); ka = self.p_spectrum_texture(tk, "ka")
+            ur = self.p_scalar_texture(tk, "urough"); vr = self.p_scalar_texture(tk, "vrough"); dp = self.p_scalar_texture(tk, "depth")
+            return self.add_material(IR.MAT_SUBSTRATE, [kd, ks, ka], [ur, vr, dp])
         if t == "transMatte":                # pMatteTranslucent -> translucentMatte (Material.hs:43-53)
             kr = self.p_spectrum_texture(tk, "kr"); kt = self.p_spectrum_texture(tk, "kt"); sg = self.p_scalar_texture(tk, "ks")
             return self.add_material(IR.MAT_TRANSMATTE, [kr, kt], [sg])

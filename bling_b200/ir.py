@@ -15,7 +15,7 @@ import numpy as np
 BANDS = 16
 
 SHAPE_BOX, SHAPE_CYLINDER, SHAPE_DISK, SHAPE_QUAD, SHAPE_SPHERE = range(5)
-MAT_MATTE, MAT_GLASS, MAT_MIRROR, MAT_PLASTIC, MAT_METAL, MAT_BLACKBODY, MAT_SHINYMETAL, MAT_TRANSMATTE = range(8)
+MAT_MATTE, MAT_GLASS, MAT_MIRROR, MAT_PLASTIC, MAT_METAL, MAT_BLACKBODY, MAT_SHINYMETAL, MAT_TRANSMATTE, MAT_SUBSTRATE = range(9)
 TEX_CONSTANT, TEX_GRAPHPAPER, TEX_CHECKER = range(3)
 LIGHT_INFINITE, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_AREA = range(4)
 ENV_CONSTANT, ENV_RGBTABLE, ENV_SUNSKY = range(3)

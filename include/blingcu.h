@@ -52,7 +52,7 @@ enum {
    BLINGCU_SHAPE_SPHERE = 4    /* p = radius                              */
 };
 
-/* Material.hs:32-96 (the five materials the configs use) + blackbody */
+/* Material.hs:32-127: the five materials the configs use, blackbody, and the rest of the module */
 enum {
    BLINGCU_MAT_MATTE = 0,   /* tex[0]=kd          f[0]=sigma              */
    BLINGCU_MAT_GLASS = 1,   /* tex[0]=kr tex[1]=kt f[0]=ior               */
@@ -64,7 +64,9 @@ enum {
    BLINGCU_MAT_SHINYMETAL = 6, /* tex[0]=eta(ks) tex[1]=k(ks) tex[2]=eta(kr) tex3=k(kr) f[0]=rough: the HOST applies
                                   frApproxEta / frApproxK (Fresnel.hs:72-78) to the leaves of the ks / kr texture trees */
    BLINGCU_MAT_TRANSMATTE = 7, /* tex[0]=kr tex[1]=kt f[0]=sigma (translucentMatte)                                    */
-   BLINGCU_MAT_KINDS = 8
+   BLINGCU_MAT_SUBSTRATE = 8,  /* tex[0]=kd tex[1]=ks tex[2]=ka f[0]=urough f[1]=vrough f[2]=depth (mkSubstrate:
+                                  FresnelBlend over an Anisotropic distribution, Microfacet.hs:56-108,140-192)          */
+   BLINGCU_MAT_KINDS = 9
 };
 
 /* Texture.hs:159-207 */

@@ -139,6 +139,15 @@ static Bsdf makeBsdf(const Scene &sc, const Hit &hit) {
       trans.flip = true; trans.type = BX_TRANSMISSION | BX_DIFFUSE;   // bxdfTypeFlip [Reflection, Transmission]
       b.bx[0] = refl; b.bx[1] = trans; b.n = 2; break;
    }
+   case BLINGCU_MAT_SUBSTRATE: {   // mkSubstrate (Material.hs:110-127)
+      BxDF fb{}; fb.kind = K_FRESNELBLEND; fb.type = BX_REFLECTION | BX_GLOSSY;
+      fb.r = sClamp(0, 1, evalSpectrumTexture(sc, m.tex[0], dgs));
+      fb.rs = sClamp(0, 1, evalSpectrumTexture(sc, m.tex[1], dgs));
+      fb.ra = sClamp(0, 1, evalSpectrumTexture(sc, m.tex[2], dgs));
+      float u = hmax(0, m.f[0]), v = hmax(0, m.f[1]);
+      fb.ex = fixExponent(1 / u); fb.ey = fixExponent(1 / v); fb.depth = m.f[2];
+      b.bx[0] = fb; b.n = 1; break;
+   }
    default: break;  // blackbody: no BxDFs
    }
    // mkBsdf (Reflection.hs:209-218)

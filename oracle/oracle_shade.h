@@ -163,7 +163,7 @@ static inline bool sameHemisphere(V3 a, V3 b) { return a.z * b.z > 0; }
 static inline V3 toSameHemisphere(V3 wo, V3 wi) { return wo.z < 0 ? mk(wi.x, wi.y, -wi.z) : wi; }
 
 enum { BX_REFLECTION = 1, BX_TRANSMISSION = 2, BX_DIFFUSE = 4, BX_GLOSSY = 8, BX_SPECULAR = 16 };  // :94-107
-enum { K_LAMBERT, K_ORENNAYAR, K_SPECREFL, K_SPECTRANS, K_MICROFACET };
+enum { K_LAMBERT, K_ORENNAYAR, K_SPECREFL, K_SPECTRANS, K_MICROFACET, K_FRESNELBLEND };
 enum { FR_NOOP, FR_DIELECTRIC, FR_CONDUCTOR };
 
 struct BxDF {
@@ -172,6 +172,7 @@ struct BxDF {
    float a, b;        // OrenNayar A,B
    int fr; float etai, etat; Spec eta, k;  // Fresnel
    float e;           // Blinn exponent
+   Spec rs, ra; float ex, ey, depth;   // FresnelBlend (Microfacet.hs:56-108): r = rd, specular, absorption, Anisotropic ex ey, coat depth
    bool flip;         // brdfToBtdf (Reflection.hs:188-195): evaluated / sampled through the other hemisphere
 };
 static inline V3 otherHemisphere(V3 w) { return mk(w.x, w.y, -w.z); }
@@ -189,6 +190,51 @@ static inline float mfG(V3 wo, V3 wi, V3 wh) {
 }
 static inline float blinnD(float e, V3 wh) { return (e + 2) * kInvTwoPi * std::pow(absCosTheta(wh), e); }      // :194-195
 static inline float blinnPdf(float e, V3 wh) { return (e + 1) * std::pow(absCosTheta(wh), e) * kInvTwoPi; }    // :146-147
+
+// Anisotropic distribution (Microfacet.hs:140-173,184-192)
+static inline float anisoE(float ex, float ey, V3 wh, float d) { return (ex * wh.x * wh.x + ey * wh.y * wh.y) / d; }
+static inline float anisoPdf(float ex, float ey, V3 wh) {
+   float costh = absCosTheta(wh);
+   float e = anisoE(ex, ey, wh, hmax(0, 1 - costh * costh));
+   return std::sqrt((ex + 1) * (ey + 1)) * kInvTwoPi * std::pow(costh, e);
+}
+static inline float anisoD(float ex, float ey, V3 wh) {
+   float costh = absCosTheta(wh);
+   float d = 1 - costh * costh;
+   if (d == 0) return 0;
+   return std::sqrt((ex + 2) * (ey + 2)) * kInvTwoPi * std::pow(costh, anisoE(ex, ey, wh, d));
+}
+static inline void anisoSample(float ex, float ey, float u1, float u2, V3 &wh, float &pdf) {
+   auto quad = [&](float u, float &p, float &c) {   // smpFirstQuadrand
+      p = (ex == ey) ? kPi * u * 0.5f : std::atan(std::sqrt((ex + 1) / (ey + 1)) * std::tan(kPi * u * 0.5f));
+      float cp = std::cos(p), sp = std::sin(p);
+      c = std::pow(u2, 1 / (ex * cp * cp + ey * sp * sp + 1));
+   };
+   float phi, cost, p;
+   if (u1 < 0.25f) { quad(4 * u1, p, cost); phi = p; }
+   else if (u1 < 0.50f) { quad(4 * (0.5f - u1), p, cost); phi = kPi - p; }
+   else if (u1 < 0.75f) { quad(4 * (u1 - 0.5f), p, cost); phi = p + kPi; }
+   else { quad(4 * (1 - u1), p, cost); phi = 2 * kPi - p; }
+   float sint = std::sqrt(hmax(0, 1 - cost * cost));
+   wh = sphericalDirection(sint, cost, phi);
+   float ds = 1 - cost * cost;
+   float e = anisoE(ex, ey, wh, ds);
+   pdf = std::sqrt((ex + 1) * (ey + 1)) * (kInvTwoPi * std::pow(cost, e));
+}
+static inline V3 halfUp(V3 wi, V3 wo) { V3 w = normalize(wi + wo); return w.z < 0 ? -w : w; }
+// FresnelBlend `e wo wi` (Microfacet.hs:65-84)
+static inline Spec fresnelBlendEval(const BxDF &b, V3 wo, V3 wi) {
+   float costi = absCosTheta(wi), costo = absCosTheta(wo);
+   Spec a = sConst(1);
+   if (b.depth > 0) { float sc = -(b.depth * (costi + costo) / (costi * costo)); for (int i = 0; i < NB; ++i) a.v[i] = std::exp(b.ra.v[i] * sc); }
+   float ds = (costo * 28 / 23 * kPi) * (1 - std::pow(1 - 0.5f * costi, 5.0f)) * (1 - std::pow(1 - 0.5f * costo, 5.0f));
+   Spec diff = sScale(a * b.r * (sConst(1) - b.rs), ds);
+   V3 wh = halfUp(wi, wo);
+   float costih = absDot(wi, wh);
+   Spec schlick = b.rs + sScale(sConst(1) - b.rs, std::pow(1 - costih, 5.0f));
+   Spec spec = sScale(schlick, anisoD(b.ex, b.ey, wh) * costo / (4 * costih * hmax(costi, costo)));
+   return diff + spec;
+}
 
 static inline Spec orenNayar(const BxDF &b, V3 wo, V3 wi) {  // Diffuse.hs:52-65
    float sinti = sinTheta(wi), sinto = sinTheta(wo);
@@ -220,6 +266,7 @@ static inline Spec bxdfEval(const BxDF &b, V3 wo, V3 wi) {
       float x = blinnD(b.e, wh) * mfG(wo, wi, wh) / (4 * costi);
       return sScale(b.r * fresnel(b, costh), x);
    }
+   case K_FRESNELBLEND: return fresnelBlendEval(b, wo, wi);
    default: return sConst(0);  // specular: Specular.hs:17,31
    }
 }
@@ -234,6 +281,11 @@ static inline float bxdfPdf(const BxDF &b, V3 wo, V3 wi) {
       V3 wh = normalize(whp);
       if (cosTheta(wh) < 0) return 0;
       return blinnPdf(b.e, wh) / (4 * absDot(wo, wh));
+   }
+   case K_FRESNELBLEND: {   // Microfacet.hs:103-108
+      if (!sameHemisphere(wo, wi)) return 0;
+      V3 wh = halfUp(wi, wo);
+      return 0.5f * (absCosTheta(wi) * kInvPi + anisoPdf(b.ex, b.ey, wh) / (4 * absDot(wo, wh)));
    }
    default: return 0;
    }
@@ -274,6 +326,21 @@ static inline void bxdfSample(const BxDF &b, V3 wo, float u1, float u2, Spec &f,
       Spec fp = (sConst(1) - fr) * b.r;
       f = sScale(fp, eta2);
       pdf = 1;
+      return;
+   }
+   case K_FRESNELBLEND: {   // Microfacet.hs:86-101, adj = False
+      float pdfp; V3 wh;
+      if (u1 < 0.5f) {
+         wi = toSameHemisphere(wo, cosineSampleHemisphere(u1 * 2, u2));
+         wh = halfUp(wi, wo);
+         pdfp = anisoPdf(b.ex, b.ey, wh);
+      } else {
+         anisoSample(b.ex, b.ey, 2 * (u1 - 0.5f), u2, wh, pdfp);
+         wi = scl(2, scl(dot(wo, wh), wh)) - wo;   // 2 * wo `dot` wh *# wh - wo  (infixl 9 for both `dot` and *#)
+      }
+      if (pdfp == 0) { f = sConst(0); pdf = 0; return; }
+      pdf = 0.5f * (absCosTheta(wi) * kInvPi + pdfp / (4 * absDot(wo, wh)));
+      f = sScale(fresnelBlendEval(b, wo, wi), 1 / pdf);
       return;
    }
    case K_MICROFACET: {  // Microfacet.hs:43-54, Blinn sample :175-182
