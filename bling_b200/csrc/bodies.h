@@ -10,9 +10,9 @@
 
 namespace bl {
 
-enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MISANY = 4, C_DROPPED = 5, C_MISCULL = 6, C_MAT0 = 8, N_COUNTERS = 8 + 1 + BLINGCU_MAT_KINDS };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + material kind
+enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MISANY = 4, C_DROPPED = 5, C_MISCULL = 6, C_EXTCULL = 7, C_MAT0 = 8, N_COUNTERS = 8 + 1 + BLINGCU_MAT_KINDS };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + material kind
 enum { N_SHADE_KINDS = 1 + BLINGCU_MAT_KINDS };
-enum { S_SAMPLES = 0, S_CAM, S_EXT, S_MIS, S_SHADOW, S_DROPPED, S_MISCULL, S_MISANY, N_STATS = 12 };
+enum { S_SAMPLES = 0, S_CAM, S_EXT, S_MIS, S_SHADOW, S_DROPPED, S_MISCULL, S_MISANY, S_EXTCULL, N_STATS = 12 };
 
 struct PathState {
    uint32_t cap;
@@ -222,6 +222,10 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118; one instantiation pe
       float ud1, ud2; rnd2D(smp, 0 + 3 * depth, ud1, ud2);
       BsdfSample s; sampleBsdf<M>(bsdf, wo, uc, ud1, ud2, s);
       if (s.pdf == 0 || isBlack(s.f)) return;
+      // The vertex this ray would find has depth == maxDepth: nextVertex returns l there (Path.hs:51), and a miss only
+      // adds light after a SPECULAR bounce (Path.hs:43-47). After a non-specular sample the ray decides nothing, so
+      // it is not traced (counted in rays_ext_culled; the reference evaluates the intersection and discards it).
+      if (depth + 1 == S.max_depth && !(s.type & BX_SPECULAR)) { cntAdd(ps.counters + C_EXTCULL, 1u); return; }
       Ray nr; nr.o = p; nr.d = s.wi; nr.tmin = eps; nr.tmax = BL_INF;
       storeRay(ps.rayO, ps.rayD, i, nr);
       storeSpec4(ps.T, ps.cap, i, sScale(s.f * BL_T(), 1 / pc));   // Path.hs:82: no pdf / cosine factor, the weight carries them
@@ -290,8 +294,8 @@ struct AdvanceBody {
    HD void operator()(uint32_t) const {
       uint32_t *c = ps.counters;
       statAdd(ps.stats + S_EXT, c[C_NEXT]); statAdd(ps.stats + S_SHADOW, c[C_SHADOW]); statAdd(ps.stats + S_MIS, c[C_MIS] + c[C_MISANY]);
-      statAdd(ps.stats + S_MISCULL, c[C_MISCULL]); statAdd(ps.stats + S_MISANY, c[C_MISANY]);
-      c[C_ACTIVE] = c[C_NEXT]; c[C_NEXT] = 0; c[C_SHADOW] = 0; c[C_MIS] = 0; c[C_MISANY] = 0; c[C_MISCULL] = 0;
+      statAdd(ps.stats + S_MISCULL, c[C_MISCULL]); statAdd(ps.stats + S_MISANY, c[C_MISANY]); statAdd(ps.stats + S_EXTCULL, c[C_EXTCULL]);
+      c[C_ACTIVE] = c[C_NEXT]; c[C_NEXT] = 0; c[C_SHADOW] = 0; c[C_MIS] = 0; c[C_MISANY] = 0; c[C_MISCULL] = 0; c[C_EXTCULL] = 0;
       for (int k = 0; k < N_SHADE_KINDS; ++k) c[C_MAT0 + k] = 0;
    }
 };

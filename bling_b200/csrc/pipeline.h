@@ -349,7 +349,7 @@ struct Pipeline {
          be.sync();
          unsigned long long s[N_STATS]; be.download(s, ps.stats, sizeof(s));
          out->samples = s[S_SAMPLES]; out->rays_camera = s[S_CAM]; out->rays_extension = s[S_EXT]; out->rays_mis = s[S_MIS];
-         out->rays_shadow = s[S_SHADOW]; out->dropped_samples = s[S_DROPPED]; out->rays_mis_culled = s[S_MISCULL]; out->rays_mis_any = s[S_MISANY];
+         out->rays_shadow = s[S_SHADOW]; out->dropped_samples = s[S_DROPPED]; out->rays_mis_culled = s[S_MISCULL]; out->rays_ext_culled = s[S_EXTCULL]; out->rays_mis_any = s[S_MISANY];
       }
       be.traversalTotals(out->nodes_traversed, out->intersections, out->rays_counted);
       out->kernel_launches = launches; out->bvh_nodes = nNodes; out->bvh_leaf_items = nItems; lastMs = be.timerRead(lastMs); out->last_pass_ms = lastMs; out->bvh_max_stack = (uint64_t)hs.bvh.max_stack;

@@ -223,6 +223,8 @@ typedef struct blingcu_stats {
    uint64_t bvh_max_stack;     /* worst-case traversal stack entries of the uploaded tree */
    uint64_t rays_mis_culled;   /* BSDF-MIS rays of Scene.hs:71-82 NOT traced because they cannot reach the chosen light
                                   (miss its shape / delta light); rays_mis counts the traced ones only */
+   uint64_t rays_ext_culled;   /* extension rays NOT traced: their vertex would have depth == maxDepth after a non-specular
+                                  bounce, where neither a hit nor a miss contributes (Path.hs:43-51); rays_extension = traced */
    uint64_t rays_mis_any;      /* the part of rays_mis traced as any-hit queries (infinite lights: only hit/miss matters) */
 } blingcu_stats;
 

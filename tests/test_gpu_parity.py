@@ -103,7 +103,8 @@ def test_film_matches_oracle(ctx, name):
     so, sg = o.stats(), ctx.stats()
     assert sg["samples"] == so["samples"] == sg["rays_camera"]
     sg["rays_mis_logical"] = sg["rays_mis"] + sg["rays_mis_culled"]; so["rays_mis_logical"] = so["rays_mis"]
-    for k in ("rays_extension", "rays_mis_logical", "rays_shadow"):
+    sg["rays_ext_logical"] = sg["rays_extension"] + sg["rays_ext_culled"]; so["rays_ext_logical"] = so["rays_extension"]
+    for k in ("rays_ext_logical", "rays_mis_logical", "rays_shadow"):
         assert abs(sg[k] / max(1, so[k]) - 1) < 5e-3, (k, sg[k], so[k])
     assert sg["kernel_launches"] > 0
 
@@ -200,7 +201,7 @@ def test_cfg5_full_size_properties(ctx):
     ctx.render_slice(1, 7, 0, 2); a = ctx.read_film(); st = ctx.stats()
     assert np.isfinite(a).all() and (a[..., 0] > 0).all()
     assert st["samples"] == 3842 * 2162 * 2 == st["rays_camera"] and st["dropped_samples"] == 0
-    assert st["rays_extension"] <= st["samples"] * sc.max_depth and st["rays_mis"] == st["rays_mis_any"]
+    assert st["rays_extension"] + st["rays_ext_culled"] <= st["samples"] * sc.max_depth and st["rays_mis"] == st["rays_mis_any"]
     ctx.clear_film(); ctx.render_slice(1, 7, 0, 1); ctx.render_slice(1, 7, 1, 2); b = ctx.read_film()
     assert np.abs(a - b).max() <= 1e-5 * np.abs(a).max()
     ctx.clear_film(); ctx.render_slice(1, 7, 0, 2)
