@@ -10,8 +10,10 @@
 
 namespace bl {
 
-enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MISANY = 4, C_DROPPED = 5, C_MISCULL = 6, C_EXTCULL = 7, C_MAT0 = 8, N_COUNTERS = 8 + 1 + BLINGCU_MAT_KINDS };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + material kind
-enum { N_SHADE_KINDS = 1 + BLINGCU_MAT_KINDS };
+enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MISANY = 4, C_DROPPED = 5, C_MISCULL = 6, C_EXTCULL = 7, C_MAT0 = 8, N_COUNTERS = 8 + 2 + BLINGCU_MAT_KINDS };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + shade kind
+// shade kinds: the material kinds, then SK_TEXTURED = materials whose textures compute (textures.h); upload puts the
+// shade kind of each primitive's material into its hit reference
+enum { SK_TEXTURED = BLINGCU_MAT_KINDS, N_SHADE_KINDS = 2 + BLINGCU_MAT_KINDS };
 enum { S_SAMPLES = 0, S_CAM, S_EXT, S_MIS, S_SHADOW, S_DROPPED, S_MISCULL, S_MISANY, S_EXTCULL, N_STATS = 12 };
 
 struct PathState {
@@ -150,7 +152,8 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118; one instantiation pe
       Sampler smp = mkSampler(S, ps.kp[i], ps.sidx[i]);
       SurfaceHit sh; DG dgs;
       surfaceAt(S, ray, hv.x, hv.y, hv.z, f2i(hv.w), sh, dgs);
-      Bsdf bsdf; makeBsdf<M>(S, sh, dgs, bsdf);
+      Spec texScratch[M::TX ? 4 : 1];   // computed texture values of the textured instantiation (unused otherwise)
+      Bsdf bsdf; makeBsdf<M>(S, sh, dgs, bsdf, texScratch);
       // T (16 registers) is re-read from L1/L2 at each use instead of being kept live across the whole body: the
       // kernel is register-bound (occupancy), not bandwidth-bound
 #define BL_T() loadSpec4(ps.T, ps.cap, i)
@@ -190,13 +193,16 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118; one instantiation pe
          {   // sampleBsdfMis (Scene.hs:71-82): the ray is traced now, the light lookup happens in the resolve bodies.
             // The reference traces a nearest-hit ray and keeps the sample only if the hit primitive IS the chosen
             // light, or, on a miss, adds `le l ray`. Same result with less traversal:
-            //   infinite light  -> only hit/miss matters: any-hit query (qMisAny);
+            //   infinite light  -> only hit/miss matters: any-hit query (qMisAny) -- unless the scene holds a Box shape:
+            //                      the reference's Box answers `intersects` for a ray that starts inside it but not
+            //                      `intersect` (Shape.hs:86-93 vs :235), so there the nearest-hit query is kept;
             //   area light      -> a ray that does not even reach the light's own shape contributes nothing: culled;
             //   delta lights    -> never hit, `le` is black: culled.
             BsdfSample bs; sampleBsdf<M>(bsdf, wo, bCompU, bD1, bD2, bs);
             if (bs.pdf != 0 && !isBlack(bs.f)) {
                Ray mr; mr.o = p; mr.d = bs.wi; mr.tmin = eps; mr.tmax = BL_INF;
-               bool any = lt.kind == BLINGCU_LIGHT_INFINITE, keep = any;
+               const bool inf = lt.kind == BLINGCU_LIGHT_INFINITE;
+               bool any = inf && !S.has_box, keep = inf;
                if (lt.kind == BLINGCU_LIGHT_AREA) {
                   const blingcu_shape &ls = S.shapes[lt.shape];
                   float tl; DG dgl;

@@ -15,10 +15,10 @@
 
 #ifdef __CUDACC__
 #define HD __host__ __device__ __forceinline__
-#define HDNI __host__ __device__ __noinline__
+#define HDNI inline __host__ __device__ __noinline__
 #else
 #define HD inline
-#define HDNI
+#define HDNI inline
 #endif
 
 namespace bl {

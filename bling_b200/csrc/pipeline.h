@@ -18,6 +18,17 @@
 
 namespace bl {
 
+// noisePerms (Texture.hs:400-414): Ken Perlin's reference permutation, the constant of perlin3d
+static const uint8_t kNoisePerm[256] = {
+   151,160,137,91,90,15,131,13,201,95,96,53,194,233,7,225,140,36,103,30,69,142,8,99,37,240,21,10,23,190,6,148,247,120,234,75,0,26,
+   197,62,94,252,219,203,117,35,11,32,57,177,33,88,237,149,56,87,174,20,125,136,171,168,68,175,74,165,71,134,139,48,27,166,77,146,
+   158,231,83,111,229,122,60,211,133,230,220,105,92,41,55,46,245,40,244,102,143,54,65,25,63,161,1,216,80,73,209,76,132,187,208,89,
+   18,169,200,196,135,130,116,188,159,86,164,100,109,198,173,186,3,64,52,217,226,250,124,123,5,202,38,147,118,126,255,82,85,212,207,
+   206,59,227,47,16,58,17,182,189,28,42,223,183,170,213,119,248,152,2,44,154,163,70,221,153,101,155,167,43,172,9,129,22,39,253,19,98,
+   108,110,79,113,224,232,178,185,112,104,218,246,97,228,251,34,242,193,238,210,144,12,191,179,162,241,81,51,145,235,249,14,239,107,
+   49,192,214,31,181,199,106,157,184,84,204,176,115,121,50,45,127,4,150,254,138,236,205,93,222,114,67,29,24,72,243,141,128,195,78,66,
+   215,61,156,180};
+
 template <class Backend>
 struct Pipeline {
    Backend be;
@@ -66,13 +77,12 @@ struct Pipeline {
       for (uint32_t i = 0; i < ir->n_materials; ++i) {
          const blingcu_material &m = ir->materials[i];
          if (m.kind < 0 || m.kind >= BLINGCU_MAT_KINDS) return fail(BLINGCU_EINVAL, "unknown material kind");
-         int need = (m.kind == BLINGCU_MAT_MATTE || m.kind == BLINGCU_MAT_MIRROR) ? 1 : (m.kind == BLINGCU_MAT_BLACKBODY ? 0 : (m.kind == BLINGCU_MAT_SHINYMETAL ? 4 : (m.kind == BLINGCU_MAT_SUBSTRATE ? 3 : 2)));
-         for (int k = 0; k < need; ++k) { int tx = k < 3 ? m.tex[k] : m.tex3; if (tx < 0 || (uint32_t)tx >= ir->n_textures) return fail(BLINGCU_EINVAL, "material texture out of range"); }
+         for (int k = 0; k < matTexCount(m.kind); ++k) { int tx = k < 3 ? m.tex[k] : m.tex3; if (tx < 0 || (uint32_t)tx >= ir->n_textures) return fail(BLINGCU_EINVAL, "material texture out of range"); }
+         for (int k = 0; k < 4; ++k) { int tx = k < 3 ? m.ftex[k] : m.bump; if (tx < 0 || (uint32_t)tx > ir->n_textures) return fail(BLINGCU_EINVAL, "material scalar texture out of range"); }
       }
-      for (uint32_t i = 0; i < ir->n_textures; ++i) {
-         const blingcu_texture &t = ir->textures[i];
-         if (t.kind == BLINGCU_TEX_GRAPHPAPER || t.kind == BLINGCU_TEX_CHECKER) { for (int k = 0; k < 2; ++k) if (t.child[k] < 0 || (uint32_t)t.child[k] >= ir->n_textures) return fail(BLINGCU_EINVAL, "texture child out of range"); }
-         else if (t.kind != BLINGCU_TEX_CONSTANT) return fail(BLINGCU_EINVAL, "unknown texture kind");
+      {
+         int rc = validateTextures(ir);
+         if (rc) return rc;
       }
       for (uint32_t i = 0; i < ir->n_lights; ++i) {
          const blingcu_light &l = ir->lights[i];
@@ -117,6 +127,9 @@ struct Pipeline {
          }
          itemPrim[it] = (int32_t)pid;
       }
+      // shade kind per material: its kind, or SK_TEXTURED when its textures compute (the slow, general shade kernel)
+      std::vector<int> shadeKind(ir->n_materials ? ir->n_materials : 1, 0);
+      for (uint32_t i = 0; i < ir->n_materials; ++i) shadeKind[i] = materialComputes(ir, ir->materials[i]) ? (int)SK_TEXTURED : ir->materials[i].kind;
       BvhBuildInput bi; bi.n = nprim; bi.lo = lo.data(); bi.hi = hi.data(); bi.max_leaf = maxLeaf;
       bi.threads = (int)std::max(1u, std::thread::hardware_concurrency());
       BvhBuildOutput bo;
@@ -127,11 +140,11 @@ struct Pipeline {
          F4 *q = &items[3 * k];
          if (src < nt) {
             const float *v = ir->tri_verts + 9 * (size_t)src;
-            q[0] = F4{v[0], v[1], v[2], i2f(mkRef(false, ir->materials[ir->tri_material[src]].kind, (uint32_t)src))};
+            q[0] = F4{v[0], v[1], v[2], i2f(mkRef(false, shadeKind[ir->tri_material[src]], (uint32_t)src))};
             q[1] = F4{v[3] - v[0], v[4] - v[1], v[5] - v[2], i2f(0)};   // e1 = p2 - p1 (TriangleMesh.hs:169)
             q[2] = F4{v[6] - v[0], v[7] - v[1], v[8] - v[2], 0};        // e2 = p3 - p1
          } else {
-            q[0] = F4{0, 0, 0, i2f(mkRef(true, ir->materials[ir->shapes[src - nt].material].kind, (uint32_t)(src - nt)))};
+            q[0] = F4{0, 0, 0, i2f(mkRef(true, shadeKind[ir->shapes[src - nt].material], (uint32_t)(src - nt)))};
             q[1] = F4{0, 0, 0, i2f(1 + (int)(src - nt))};
             q[2] = F4{0, 0, 0, 0};
          }
@@ -160,6 +173,7 @@ struct Pipeline {
       hs.materials = up<blingcu_material>(ir->materials, ir->n_materials);
       hs.textures = up<blingcu_texture>(ir->textures, ir->n_textures);
       hs.lights = up<blingcu_light>(ir->lights, ir->n_lights); hs.n_lights = (int)ir->n_lights;
+      hs.has_box = 0; for (size_t j = 0; j < ns; ++j) if (ir->shapes[j].kind == BLINGCU_SHAPE_BOX) hs.has_box = 1;
       {
          std::vector<blingcu_envmap> envs(ir->envs, ir->envs + ir->n_envs);
          for (blingcu_envmap &e : envs) {
@@ -183,6 +197,7 @@ struct Pipeline {
       for (int i = 0; i < NB; ++i) { hs.cieX[i] = ir->cie_x.v[i]; hs.cieY[i] = ir->cie_y.v[i]; hs.cieZ[i] = ir->cie_z.v[i]; }
       hs.ySum = ir->cie_y_sum;
       for (int b = 0; b < 7; ++b) for (int i = 0; i < NB; ++i) hs.illum[b][i] = ir->illum_basis[b].v[i];
+      for (int i = 0; i < 256; ++i) hs.perm[i] = kNoisePerm[i];
       dscene = up<DScene>(&hs, 1);
       npix = (uint32_t)hs.EW * (uint32_t)hs.EH;
       film = (F4 *)be.alloc(sizeof(F4) * (size_t)hs.W * hs.H);
@@ -233,31 +248,112 @@ struct Pipeline {
                case BLINGCU_MAT_SHINYMETAL: be.runQueue(ShadeHitBody<BLINGCU_MAT_SHINYMETAL>{dscene, ps, qb}, qk, ck, bound); break;
                case BLINGCU_MAT_TRANSMATTE: be.runQueue(ShadeHitBody<BLINGCU_MAT_TRANSMATTE>{dscene, ps, qb}, qk, ck, bound); break;
                case BLINGCU_MAT_SUBSTRATE: be.runQueue(ShadeHitBody<BLINGCU_MAT_SUBSTRATE>{dscene, ps, qb}, qk, ck, bound); break;
+               case SK_TEXTURED: be.runQueue(ShadeHitBody<SK_TEXTURED>{dscene, ps, qb}, qk, ck, bound); break;
                default: be.runQueue(ShadeHitBody<BLINGCU_MAT_BLACKBODY>{dscene, ps, qb}, qk, ck, bound); break;
                }
                launches++;
             }
             be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl);
             launches++;
-            if (hasInfinite) { be.traceAny(ps.qMisAny, ps.counters + C_MISANY, bound, dscene, ps.miO, ps.miD, ps.occlM); launches++; }
-            if (hasArea) { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, bound, dscene, ps.miO, ps.miD, ps.mihit); launches++; }
+            if (hasInfinite && !hasBox) { be.traceAny(ps.qMisAny, ps.counters + C_MISANY, bound, dscene, ps.miO, ps.miD, ps.occlM); launches++; }
+            if (hasArea || (hasInfinite && hasBox)) { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, bound, dscene, ps.miO, ps.miD, ps.mihit); launches++; }
             be.tag(BLINGCU_KC_RESOLVE); be.runQueue(ResolveShadowBody{ps}, ps.qShadow, ps.counters + C_SHADOW, bound);
             launches++;
-            if (hasArea) { be.runQueue(ResolveMisBody{dscene, ps}, ps.qMis, ps.counters + C_MIS, bound); launches++; }
-            if (hasInfinite) { be.runQueue(ResolveMisAnyBody{dscene, ps}, ps.qMisAny, ps.counters + C_MISANY, bound); launches++; }
+            if (hasArea || (hasInfinite && hasBox)) { be.runQueue(ResolveMisBody{dscene, ps}, ps.qMis, ps.counters + C_MIS, bound); launches++; }
+            if (hasInfinite && !hasBox) { be.runQueue(ResolveMisAnyBody{dscene, ps}, ps.qMisAny, ps.counters + C_MISANY, bound); launches++; }
          }
          be.tag(BLINGCU_KC_OTHER); be.run(AdvanceBody{ps}, 1); launches++;
          uint32_t *t = qa; qa = qb; qb = t;
       }
    }
 
+   // ---- textures: validation and the "does this material's texture tree compute" test
+   static int matTexCount(int kind) {
+      return (kind == BLINGCU_MAT_MATTE || kind == BLINGCU_MAT_MIRROR) ? 1 : (kind == BLINGCU_MAT_BLACKBODY ? 0 : (kind == BLINGCU_MAT_SHINYMETAL ? 4 : (kind == BLINGCU_MAT_SUBSTRATE ? 3 : 2)));
+   }
+   static bool isScalarKind(int k) { return k >= BLINGCU_STEX_CONSTANT && k <= BLINGCU_STEX_CRYSTAL; }
+   // nesting depth of blends below spectrum texture `id` (-1: malformed); selecting kinds do not count
+   static int blendDepth(const blingcu_scene *ir, int id, int guard) {
+      if (guard > 32 || id < 0 || (uint32_t)id >= ir->n_textures) return -1;
+      const blingcu_texture &t = ir->textures[id];
+      if (t.kind == BLINGCU_TEX_CONSTANT || t.kind == BLINGCU_TEX_GRADIENT) return 0;
+      if (t.kind == BLINGCU_TEX_GRAPHPAPER || t.kind == BLINGCU_TEX_CHECKER || t.kind == BLINGCU_TEX_BLEND) {
+         int a = blendDepth(ir, t.child[0], guard + 1), b = blendDepth(ir, t.child[1], guard + 1);
+         if (a < 0 || b < 0) return -1;
+         return std::max(a, b) + (t.kind == BLINGCU_TEX_BLEND ? 1 : 0);
+      }
+      return -1;   // a scalar texture where a spectrum texture is expected
+   }
+   static bool spectrumComputes(const blingcu_scene *ir, int id, int guard) {
+      if (guard > 32) return true;
+      const blingcu_texture &t = ir->textures[id];
+      if (t.kind == BLINGCU_TEX_BLEND || t.kind == BLINGCU_TEX_GRADIENT) return true;
+      if (t.kind == BLINGCU_TEX_GRAPHPAPER || t.kind == BLINGCU_TEX_CHECKER) return spectrumComputes(ir, t.child[0], guard + 1) || spectrumComputes(ir, t.child[1], guard + 1);
+      return false;
+   }
+   static bool materialComputes(const blingcu_scene *ir, const blingcu_material &m) {
+      if (m.bump || m.ftex[0] || m.ftex[1] || m.ftex[2]) return true;
+      for (int k = 0; k < matTexCount(m.kind); ++k) if (spectrumComputes(ir, k < 3 ? m.tex[k] : m.tex3, 0)) return true;
+      return false;
+   }
+   int validateTextures(const blingcu_scene *ir) {
+      const uint32_t nt = ir->n_textures;
+      auto inRange = [nt](int i) { return i >= 0 && (uint32_t)i < nt; };
+      for (uint32_t i = 0; i < nt; ++i) {
+         const blingcu_texture &t = ir->textures[i];
+         switch (t.kind) {
+         case BLINGCU_TEX_CONSTANT: case BLINGCU_STEX_CONSTANT: case BLINGCU_STEX_PERLIN: break;
+         case BLINGCU_TEX_GRAPHPAPER: case BLINGCU_TEX_CHECKER:
+            if (!inRange(t.child[0]) || !inRange(t.child[1])) return fail(BLINGCU_EINVAL, "texture child out of range");
+            break;
+         case BLINGCU_TEX_BLEND:
+            if (!inRange(t.child[0]) || !inRange(t.child[1]) || !inRange(t.aux)) return fail(BLINGCU_EINVAL, "texture child out of range");
+            if (!isScalarKind(ir->textures[t.aux].kind)) return fail(BLINGCU_EINVAL, "blend factor must be a scalar texture");
+            break;
+         case BLINGCU_TEX_GRADIENT:
+            if (!inRange(t.aux) || !isScalarKind(ir->textures[t.aux].kind)) return fail(BLINGCU_EINVAL, "gradient input must be a scalar texture");
+            if (t.child[1] < 1 || !inRange(t.child[0]) || !inRange(t.child[0] + t.child[1] - 1)) return fail(BLINGCU_EINVAL, "gradient steps out of range");
+            for (int k = 0; k < t.child[1]; ++k) {
+               const blingcu_texture &st = ir->textures[t.child[0] + k];
+               if (st.kind != BLINGCU_TEX_CONSTANT || (k > 0 && st.f[0] < ir->textures[t.child[0] + k - 1].f[0])) return fail(BLINGCU_EINVAL, "gradient steps must be constant textures sorted by position");
+            }
+            break;
+         case BLINGCU_STEX_SCALE:
+            if (!inRange(t.child[0]) || !isScalarKind(ir->textures[t.child[0]].kind)) return fail(BLINGCU_EINVAL, "scale texture child must be a scalar texture");
+            break;
+         case BLINGCU_STEX_FBM: case BLINGCU_STEX_CRYSTAL:
+            if (t.aux < 0 || t.aux > 64) return fail(BLINGCU_EINVAL, "octaves out of range");
+            break;
+         case BLINGCU_STEX_CELLNOISE:
+            if (t.aux < 0 || t.aux > 3) return fail(BLINGCU_EINVAL, "unknown cell-noise distance");
+            break;
+         default: return fail(BLINGCU_EINVAL, "unknown texture kind");
+         }
+      }
+      for (uint32_t i = 0; i < nt; ++i) {   // scale chains: at most 4 links (evalScalarTexture), no cycles
+         int id = (int)i, n = 0;
+         while (ir->textures[id].kind == BLINGCU_STEX_SCALE) { if (++n > 4) return fail(BLINGCU_EINVAL, "scale textures nested deeper than 4"); id = ir->textures[id].child[0]; }
+      }
+      for (uint32_t i = 0; i < ir->n_materials; ++i) {
+         const blingcu_material &m = ir->materials[i];
+         for (int k = 0; k < matTexCount(m.kind); ++k) {
+            int d = blendDepth(ir, k < 3 ? m.tex[k] : m.tex3, 0);
+            if (d < 0) return fail(BLINGCU_EINVAL, "material texture is not a spectrum texture tree");
+            if (d > BL_BLEND_DEPTH) return fail(BLINGCU_EINVAL, "blend textures nested deeper than 2");
+         }
+         for (int k = 0; k < 4; ++k) { int tx = k < 3 ? m.ftex[k] : m.bump; if (tx && !isScalarKind(ir->textures[tx - 1].kind)) return fail(BLINGCU_EINVAL, "material scalar parameter must be a scalar texture"); }
+      }
+      return 0;
+   }
+
    bool kindPresent[N_SHADE_KINDS] = {};
-   bool hasInfinite = false, hasArea = false;
+   bool hasInfinite = false, hasArea = false, hasBox = false;
    void scanKinds(const blingcu_scene *ir) {
       for (int k = 0; k < N_SHADE_KINDS; ++k) kindPresent[k] = false;
       kindPresent[0] = true;
-      for (uint32_t i = 0; i < ir->n_materials; ++i) kindPresent[1 + ir->materials[i].kind] = true;
-      hasInfinite = hasArea = false;
+      for (uint32_t i = 0; i < ir->n_materials; ++i) kindPresent[1 + (materialComputes(ir, ir->materials[i]) ? (int)SK_TEXTURED : ir->materials[i].kind)] = true;
+      hasInfinite = hasArea = hasBox = false;
+      for (uint32_t i = 0; i < ir->n_shapes; ++i) hasBox |= ir->shapes[i].kind == BLINGCU_SHAPE_BOX;
       for (uint32_t i = 0; i < ir->n_lights; ++i) { hasInfinite |= ir->lights[i].kind == BLINGCU_LIGHT_INFINITE; hasArea |= ir->lights[i].kind == BLINGCU_LIGHT_AREA; }
    }
 

@@ -24,6 +24,7 @@ struct DScene {
    const blingcu_envmap *envs; // pointers inside are device pointers
    const float *ftbl;          // 16x16 filter table
    int n_lights;
+   int has_box;                // some shape is a Box: BSDF-MIS rays towards infinite lights keep the nearest-hit query (bodies.h)
    blingcu_camera cam;
    int W, H; float fw, fh;
    int ex0, ex1, ey0, ey1, EW, EH;   // sample extent (Image.hs:162-168)
@@ -31,7 +32,12 @@ struct DScene {
    SamplerConst smp;           // per-scene sampler constants (hd.h)
    float cieX[NB], cieY[NB], cieZ[NB], ySum;
    float illum[7][NB];         // r g b c m y w
+   uint8_t perm[256];          // noisePerms (Texture.hs:400-414), filled by upload; read by textures.h only
 };
+
+}  // namespace bl
+#include "textures.h"
+namespace bl {
 
 // ------------------------------------------------------------------------------------------ Montecarlo.hs
 HD void concentricSampleDisk(float u1, float u2, float &dx, float &dy) {   // :164-181
@@ -156,18 +162,21 @@ enum { FR_NOOP = 0, FR_DIELECTRIC, FR_CONDUCTOR };
 // Compile-time description of what a material can contain. The shade kernel is launched once per material KIND
 // (material-sorted queues), so each launch is instantiated for its kind and the BxDF code of every other kind drops
 // out (fewer registers, more resident warps). AnyMat keeps everything (resolve kernels, generic callers).
-struct AnyMat { static const unsigned KM = 0x3fu, FM = 0x7u; static const int NC = 2, MK = -1; };
+// TX: the material's textures may COMPUTE (scalar textures, blends, gradients, bump mapping; textures.h) -- only the
+// "textured" shade queue (kind index BLINGCU_MAT_KINDS, assigned by upload to such materials) is instantiated with it.
+struct AnyMat { static const unsigned KM = 0x3fu, FM = 0x7u; static const int NC = 2, MK = -1; static const bool TX = false; };
 template <int MATKIND> struct MatOf : AnyMat {};
+template <> struct MatOf<BLINGCU_MAT_KINDS> : AnyMat { static const bool TX = true; };
 #define BL_K(k) (1u << (k))
-template <> struct MatOf<BLINGCU_MAT_MATTE> { static const unsigned KM = BL_K(0) | BL_K(1), FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_MATTE; };
-template <> struct MatOf<BLINGCU_MAT_GLASS> { static const unsigned KM = BL_K(2) | BL_K(3), FM = BL_K(1); static const int NC = 2, MK = BLINGCU_MAT_GLASS; };
-template <> struct MatOf<BLINGCU_MAT_MIRROR> { static const unsigned KM = BL_K(2), FM = BL_K(0); static const int NC = 1, MK = BLINGCU_MAT_MIRROR; };
-template <> struct MatOf<BLINGCU_MAT_PLASTIC> { static const unsigned KM = BL_K(0) | BL_K(4), FM = BL_K(1); static const int NC = 2, MK = BLINGCU_MAT_PLASTIC; };
-template <> struct MatOf<BLINGCU_MAT_METAL> { static const unsigned KM = BL_K(4), FM = BL_K(2); static const int NC = 1, MK = BLINGCU_MAT_METAL; };
-template <> struct MatOf<BLINGCU_MAT_SHINYMETAL> { static const unsigned KM = BL_K(2) | BL_K(4), FM = BL_K(2); static const int NC = 2, MK = BLINGCU_MAT_SHINYMETAL; };
-template <> struct MatOf<BLINGCU_MAT_TRANSMATTE> { static const unsigned KM = BL_K(0) | BL_K(1), FM = 0u; static const int NC = 2, MK = BLINGCU_MAT_TRANSMATTE; };
-template <> struct MatOf<BLINGCU_MAT_SUBSTRATE> { static const unsigned KM = BL_K(5), FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_SUBSTRATE; };
-template <> struct MatOf<BLINGCU_MAT_BLACKBODY> { static const unsigned KM = 0u, FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_BLACKBODY; };
+template <> struct MatOf<BLINGCU_MAT_MATTE> { static const unsigned KM = BL_K(0) | BL_K(1), FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_MATTE; static const bool TX = false; };
+template <> struct MatOf<BLINGCU_MAT_GLASS> { static const unsigned KM = BL_K(2) | BL_K(3), FM = BL_K(1); static const int NC = 2, MK = BLINGCU_MAT_GLASS; static const bool TX = false; };
+template <> struct MatOf<BLINGCU_MAT_MIRROR> { static const unsigned KM = BL_K(2), FM = BL_K(0); static const int NC = 1, MK = BLINGCU_MAT_MIRROR; static const bool TX = false; };
+template <> struct MatOf<BLINGCU_MAT_PLASTIC> { static const unsigned KM = BL_K(0) | BL_K(4), FM = BL_K(1); static const int NC = 2, MK = BLINGCU_MAT_PLASTIC; static const bool TX = false; };
+template <> struct MatOf<BLINGCU_MAT_METAL> { static const unsigned KM = BL_K(4), FM = BL_K(2); static const int NC = 1, MK = BLINGCU_MAT_METAL; static const bool TX = false; };
+template <> struct MatOf<BLINGCU_MAT_SHINYMETAL> { static const unsigned KM = BL_K(2) | BL_K(4), FM = BL_K(2); static const int NC = 2, MK = BLINGCU_MAT_SHINYMETAL; static const bool TX = false; };
+template <> struct MatOf<BLINGCU_MAT_TRANSMATTE> { static const unsigned KM = BL_K(0) | BL_K(1), FM = 0u; static const int NC = 2, MK = BLINGCU_MAT_TRANSMATTE; static const bool TX = false; };
+template <> struct MatOf<BLINGCU_MAT_SUBSTRATE> { static const unsigned KM = BL_K(5), FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_SUBSTRATE; static const bool TX = false; };
+template <> struct MatOf<BLINGCU_MAT_BLACKBODY> { static const unsigned KM = 0u, FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_BLACKBODY; static const bool TX = false; };
 
 struct BxDF {
    int kind, type, fr, clamp01;   // clamp01: sClamp' applied to r on read (glass, mirror; Material.hs:63-64,71)
@@ -413,7 +422,9 @@ HD const float *evalSpectrumTexture(const DScene &sc, int id, const DG &dg) {   
          id = ((q & 1) == 0) ? t.child[0] : t.child[1];
          continue;
       }
-      float x = t.f[1] * dg.u + t.f[3], z = t.f[2] * dg.v + t.f[4];   // uvMapping :166-170
+      float x, z;
+      if (t.aux == 0) { x = t.f[1] * dg.u + t.f[3]; z = t.f[2] * dg.v + t.f[4]; }   // uvMapping :166-170
+      else map2d(t.s.v, dg, x, z);
       float xp = fabsf(x - truncf(x)), zp = fabsf(z - truncf(z));      // properFraction
       float lo = t.f[0] / 2, hi = 1.0f - lo;
       id = (xp < lo || zp < lo || xp > hi || zp > hi) ? t.child[1] : t.child[0];
@@ -462,16 +473,32 @@ HD void surfaceAt(const DScene &sc, const Ray &ray, float t, float b1, float b2,
 }
 
 // Material.hs:32-96 + mkBsdf' (Reflection.hs:209-225)
+// Texture access of makeBsdf. Fast path: a pointer into the texture table and the constant f[i]. Textured path (M::TX):
+// the spectrum is computed into the caller's scratch (one Spec per texture slot) and scalars come from ftex[i].
+template <class M>
+HD const float *matSpectrum(const DScene &sc, int tex, const DG &dg, Spec *scratch, int slot) {
+   if (M::TX) { scratch[slot] = SpectrumValue<BL_BLEND_DEPTH>::eval(sc, tex, dg); return scratch[slot].v; }
+   return evalSpectrumTexture(sc, tex, dg);
+}
+template <class M>
+HD float matScalar(const DScene &sc, const blingcu_material &m, int i, const DG &dg) {
+   if (M::TX) { if (m.ftex[i]) return evalScalarTexture(sc, m.ftex[i] - 1, dg); }
+   return m.f[i];
+}
 template <class M = AnyMat>
-HD void makeBsdf(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b) {
+HD void makeBsdf(const DScene &sc, const SurfaceHit &sh, const DG &dgsIn, Bsdf &b, Spec *scratch = 0) {
    const blingcu_material &m = sc.materials[sh.material];
    const int mk = (M::MK >= 0) ? M::MK : m.kind;   // compile-time constant in the per-kind shade kernels
+   DG dgs = dgsIn;
+   if (M::TX) { if (m.bump) dgs = bumpDG(sc, m.bump - 1, sh.dgg, dgsIn); }   // bumpMapped d mat dgg dgs = mat dgg (bump d dgg dgs)
+#define BL_TEX(t, slot) matSpectrum<M>(sc, (t), dgs, scratch, (slot))
+#define BL_F(i) matScalar<M>(sc, m, (i), dgs)
    b.n = 0;
    BL_UNROLL for (int i = 0; i < 2; ++i) { BxDF &x = b.bx[i]; x.kind = 0; x.type = 0; x.fr = FR_NOOP; x.clamp01 = 0; x.flip = 0; x.r = 0; x.r2 = 0; x.eta = 0; x.k = 0; x.a = x.b = x.e = 0; x.etai = x.etat = 1; x.ey = 0; x.depth = 0; }
    switch (mk) {
    case BLINGCU_MAT_MATTE: {
-      BxDF &x = b.bx[0]; x.r = evalSpectrumTexture(sc, m.tex[0], dgs); x.type = BX_REFLECTION | BX_DIFFUSE;
-      float s = m.f[0];
+      BxDF &x = b.bx[0]; x.r = BL_TEX(m.tex[0], 0); x.type = BX_REFLECTION | BX_DIFFUSE;
+      float s = BL_F(0);
       if (s == 0) x.kind = K_LAMBERT;
       else {   // Diffuse.hs:29-36
          x.kind = K_ORENNAYAR; float sg = clampf(s, 0, 1), sig2 = sg * sg;
@@ -481,44 +508,45 @@ HD void makeBsdf(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b)
    }
    case BLINGCU_MAT_GLASS: {
       BxDF &r = b.bx[0], &t = b.bx[1];
-      r.kind = K_SPECREFL; r.type = BX_REFLECTION | BX_SPECULAR; r.r = evalSpectrumTexture(sc, m.tex[0], dgs); r.clamp01 = 1; r.fr = FR_DIELECTRIC; r.etai = 1; r.etat = m.f[0];
-      t.kind = K_SPECTRANS; t.type = BX_TRANSMISSION | BX_SPECULAR; t.r = evalSpectrumTexture(sc, m.tex[1], dgs); t.clamp01 = 1; t.etai = 1; t.etat = m.f[0];
+      const float ior = BL_F(0);
+      r.kind = K_SPECREFL; r.type = BX_REFLECTION | BX_SPECULAR; r.r = BL_TEX(m.tex[0], 0); r.clamp01 = 1; r.fr = FR_DIELECTRIC; r.etai = 1; r.etat = ior;
+      t.kind = K_SPECTRANS; t.type = BX_TRANSMISSION | BX_SPECULAR; t.r = BL_TEX(m.tex[1], 1); t.clamp01 = 1; t.etai = 1; t.etat = ior;
       b.n = 2; break;
    }
    case BLINGCU_MAT_MIRROR: {
-      BxDF &r = b.bx[0]; r.kind = K_SPECREFL; r.type = BX_REFLECTION | BX_SPECULAR; r.r = evalSpectrumTexture(sc, m.tex[0], dgs); r.clamp01 = 1; r.fr = FR_NOOP;
+      BxDF &r = b.bx[0]; r.kind = K_SPECREFL; r.type = BX_REFLECTION | BX_SPECULAR; r.r = BL_TEX(m.tex[0], 0); r.clamp01 = 1; r.fr = FR_NOOP;
       b.n = 1; break;
    }
    case BLINGCU_MAT_PLASTIC: {
       BxDF &d = b.bx[0], &s = b.bx[1];
-      d.kind = K_LAMBERT; d.type = BX_REFLECTION | BX_DIFFUSE; d.r = evalSpectrumTexture(sc, m.tex[0], dgs);
-      s.kind = K_MICROFACET; s.type = BX_REFLECTION | BX_GLOSSY; s.r = evalSpectrumTexture(sc, m.tex[1], dgs);
-      s.fr = FR_DIELECTRIC; s.etai = 1.0f; s.etat = 1.5f; s.e = fixExponent(1 / m.f[0]);
+      d.kind = K_LAMBERT; d.type = BX_REFLECTION | BX_DIFFUSE; d.r = BL_TEX(m.tex[0], 0);
+      s.kind = K_MICROFACET; s.type = BX_REFLECTION | BX_GLOSSY; s.r = BL_TEX(m.tex[1], 1);
+      s.fr = FR_DIELECTRIC; s.etai = 1.0f; s.etat = 1.5f; s.e = fixExponent(1 / BL_F(0));
       b.n = 2; break;
    }
    case BLINGCU_MAT_METAL: {
       BxDF &s = b.bx[0]; s.kind = K_MICROFACET; s.type = BX_REFLECTION | BX_GLOSSY; s.r = 0; s.fr = FR_CONDUCTOR;
-      s.eta = evalSpectrumTexture(sc, m.tex[0], dgs); s.k = evalSpectrumTexture(sc, m.tex[1], dgs); s.e = fixExponent(1 / m.f[0]);
+      s.eta = BL_TEX(m.tex[0], 0); s.k = BL_TEX(m.tex[1], 1); s.e = fixExponent(1 / BL_F(0));
       b.n = 1; break;
    }
    case BLINGCU_MAT_SHINYMETAL: {   // Material.hs:98-108; eta / k textures already carry frApproxEta / frApproxK (host)
       BxDF &d = b.bx[0], &sp = b.bx[1];
       d.kind = K_MICROFACET; d.type = BX_REFLECTION | BX_GLOSSY; d.r = 0; d.fr = FR_CONDUCTOR;
-      d.eta = evalSpectrumTexture(sc, m.tex[0], dgs); d.k = evalSpectrumTexture(sc, m.tex[1], dgs); d.e = fixExponent(1 / m.f[0]);
+      d.eta = BL_TEX(m.tex[0], 0); d.k = BL_TEX(m.tex[1], 1); d.e = fixExponent(1 / BL_F(0));
       sp.kind = K_SPECREFL; sp.type = BX_REFLECTION | BX_SPECULAR; sp.r = 0; sp.fr = FR_CONDUCTOR;
-      sp.eta = evalSpectrumTexture(sc, m.tex[2], dgs); sp.k = evalSpectrumTexture(sc, m.tex3, dgs);
+      sp.eta = BL_TEX(m.tex[2], 2); sp.k = BL_TEX(m.tex3, 3);
       b.n = 2; break;
    }
    case BLINGCU_MAT_SUBSTRATE: {   // mkSubstrate (Material.hs:110-127)
       BxDF &fb = b.bx[0]; fb.kind = K_FRESNELBLEND; fb.type = BX_REFLECTION | BX_GLOSSY;
-      fb.r = evalSpectrumTexture(sc, m.tex[0], dgs); fb.eta = evalSpectrumTexture(sc, m.tex[1], dgs); fb.k = evalSpectrumTexture(sc, m.tex[2], dgs);
-      fb.e = fixExponent(1 / hmaxf(0.0f, m.f[0])); fb.ey = fixExponent(1 / hmaxf(0.0f, m.f[1])); fb.depth = m.f[2];
+      fb.r = BL_TEX(m.tex[0], 0); fb.eta = BL_TEX(m.tex[1], 1); fb.k = BL_TEX(m.tex[2], 2);
+      fb.e = fixExponent(1 / hmaxf(0.0f, BL_F(0))); fb.ey = fixExponent(1 / hmaxf(0.0f, BL_F(1))); fb.depth = BL_F(2);
       b.n = 1; break;
    }
    case BLINGCU_MAT_TRANSMATTE: {   // Material.hs:43-53
       BxDF &rf = b.bx[0], &tr = b.bx[1];
-      const float *kr = evalSpectrumTexture(sc, m.tex[0], dgs), *kt = evalSpectrumTexture(sc, m.tex[1], dgs);
-      float sg = m.f[0], a = 0, bb = 0; int kind = K_LAMBERT;
+      const float *kr = BL_TEX(m.tex[0], 0), *kt = BL_TEX(m.tex[1], 1);
+      float sg = BL_F(0), a = 0, bb = 0; int kind = K_LAMBERT;
       if (sg != 0) { kind = K_ORENNAYAR; float c = clampf(sg, 0, 1), sig2 = c * c; a = 1 - (sig2 / (2 * (sig2 + 0.33f))); bb = 0.45f * sig2 / (sig2 + 0.09f); }
       rf.kind = kind; rf.type = BX_REFLECTION | BX_DIFFUSE; rf.r = kr; rf.clamp01 = 1; rf.a = a; rf.b = bb;
       tr.kind = kind; tr.type = BX_TRANSMISSION | BX_DIFFUSE; tr.r = kt; tr.clamp01 = 1; tr.r2 = kr; tr.flip = 1; tr.a = a; tr.b = bb;
@@ -529,6 +557,8 @@ HD void makeBsdf(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b)
    V3 nn = dgs.n, sn = normalize3(dgs.dpdu);
    b.cs.s = sn; b.cs.t = cross3(nn, sn); b.cs.n = nn;
    b.p = dgs.p; b.ng = sh.dgg.n;
+#undef BL_TEX
+#undef BL_F
 }
 
 // ------------------------------------------------------------------------------------------ spectra conversions

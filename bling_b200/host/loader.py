@@ -156,11 +156,19 @@ class Loader:
         self.ir.textures.append(t); return len(self.ir.textures) - 1
 
     def add_material(self, kind, texs, fs) -> int:
+        """fs: scalar parameters, each a float (constant) or ("tex", id) for a computed ScalarTexture."""
         m = IR.Material(); m.kind = kind
         for i in range(3): m.tex[i] = texs[i] if i < len(texs) else -1
         m.tex3 = texs[3] if len(texs) > 3 else -1
-        for i, v in enumerate(fs): m.f[i] = float(v)
+        for i, v in enumerate(fs):
+            if isinstance(v, tuple): m.ftex[i] = v[1] + 1
+            else: m.f[i] = float(v)
         self.ir.materials.append(m); return len(self.ir.materials) - 1
+
+    def add_texture(self, kind, *, child=(-1, -1), aux=0, f=(), s=()) -> int:
+        t = IR.Texture(); t.kind = kind; t.child[0], t.child[1] = child; t.aux = aux
+        IR.set_arr(t.f, list(f)); IR.set_arr(t.s.v, list(s))
+        self.ir.textures.append(t); return len(self.ir.textures) - 1
 
     # ---- spectra / textures (ParserCore.hs:142-176, MaterialParser.hs)
     def p_spectrum(self, tk: Tokens):
@@ -183,12 +191,53 @@ class Loader:
         if t == "temp": return S.black_body(tk.flt())
         raise ValueError(f"unknown spectrum type {t}")
 
-    def p_scalar_texture(self, tk: Tokens, name) -> float:
+    def p_mapping2d(self, tk: Tokens, name):   # pTextureMapping2d (MaterialParser.hs:159-178) -> the 9 floats of blingcu.h
+        tk.expect(name); tk.expect("{"); mk = tk.next()
+        if mk == "uv": m = [0.0, tk.flt(), tk.flt(), tk.flt(), tk.flt()]
+        elif mk == "planar":
+            vu, vv = tk.vec(), tk.vec()
+            m = [1.0] + list(vu) + list(vv) + [tk.flt(), tk.flt()]
+        else: raise ValueError(f"unknown 2d mapping {mk}")
+        tk.expect("}")
+        return m
+
+    def p_mapping3d(self, tk: Tokens, name):   # pTextureMapping3d (:180-187): identityMapping3d w2t = transPoint w2t . dgP
+        tk.expect(name); tk.expect("{"); mk = tk.next()
+        if mk != "identity": raise ValueError(f"unknown 3d mapping {mk}")
+        t = self.p_transform(tk); tk.expect("}")
+        return list(t.m.ravel())
+
+    def p_scalar_texture(self, tk: Tokens, name):
+        """pScalarTexture (MaterialParser.hs:113-154). Returns a float for `constant`, else ("tex", id)."""
         tk.expect(name); tk.expect("{")
         tp = tk.next()
-        if tp != "constant": raise NotImplementedError(f"scalar texture {tp} (outside SURVEY §8)")
-        v = tk.flt(); tk.expect("}")
-        return float(v)
+        if tp == "constant":
+            v = tk.flt(); tk.expect("}")
+            return float(v)
+        if tp == "cellNoise":
+            dn = tk.next()
+            dist = {"euclidian": 0, "euclidian2": 1, "manhattan": 2, "chebyshev": 3}[dn]
+            tid = self.add_texture(IR.STEX_CELLNOISE, aux=dist, s=self.p_mapping3d(tk, "map"))
+        elif tp == "fbm":
+            octaves, omega = tk.named_int("octaves"), tk.named_float("omega")
+            tid = self.add_texture(IR.STEX_FBM, aux=octaves, f=[omega], s=self.p_mapping3d(tk, "map"))
+        elif tp == "perlin":
+            tid = self.add_texture(IR.STEX_PERLIN, s=self.p_mapping3d(tk, "map"))
+        elif tp == "crystal":
+            octaves = tk.named_int("octaves")
+            tid = self.add_texture(IR.STEX_CRYSTAL, aux=octaves, s=self.p_mapping2d(tk, "map"))
+        elif tp == "scale":
+            a, sc = tk.flt(), tk.flt()
+            inner = self.scalar_tex_id(self.p_scalar_texture(tk, "tex"))
+            tid = self.add_texture(IR.STEX_SCALE, child=(inner, -1), f=[a, sc])
+        else:
+            raise NotImplementedError(f"scalar texture {tp} (image textures: SURVEY §8(f)2, not built)")
+        tk.expect("}")
+        return ("tex", tid)
+
+    def scalar_tex_id(self, v) -> int:
+        """A scalar-texture table entry for either form p_scalar_texture returns."""
+        return v[1] if isinstance(v, tuple) else self.add_texture(IR.STEX_CONSTANT, f=[v])
 
     def p_spectrum_texture(self, tk: Tokens, name) -> int:
         tk.expect(name); tk.expect("{")
@@ -197,30 +246,50 @@ class Loader:
             tid = self.const_tex(self.p_spectrum(tk))
         elif tp == "graphPaper":             # MaterialParser.hs:229-233
             lw = tk.flt()
-            tk.expect("map"); tk.expect("{")
-            mk = tk.next()
-            if mk != "uv": raise NotImplementedError(f"2d mapping {mk}")
-            su, sv, ou, ov = tk.flt(), tk.flt(), tk.flt(), tk.flt(); tk.expect("}")
+            m = self.p_mapping2d(tk, "map")
             c0 = self.p_spectrum_texture(tk, "tex1"); c1 = self.p_spectrum_texture(tk, "tex2")
-            t = IR.Texture(); t.kind = IR.TEX_GRAPHPAPER; t.child[0] = c0; t.child[1] = c1
-            IR.set_arr(t.f, [lw, su, sv, ou, ov])
-            self.ir.textures.append(t); tid = len(self.ir.textures) - 1
+            if m[0] == 0.0: tid = self.add_texture(IR.TEX_GRAPHPAPER, child=(c0, c1), f=[lw] + m[1:5])
+            else: tid = self.add_texture(IR.TEX_GRAPHPAPER, child=(c0, c1), aux=1, f=[lw], s=m)
         elif tp == "checker":                # MaterialParser.hs:209 -> checkerBoard (Texture.hs:209-221)
             sc = tk.vec()
             c0 = self.p_spectrum_texture(tk, "tex1"); c1 = self.p_spectrum_texture(tk, "tex2")
             t = IR.Texture(); t.kind = IR.TEX_CHECKER; t.child[0] = c0; t.child[1] = c1
             IR.set_arr(t.f, list(sc))
             self.ir.textures.append(t); tid = len(self.ir.textures) - 1
+        elif tp == "blend":                  # spectrumBlend (Texture.hs:129-141)
+            c0 = self.p_spectrum_texture(tk, "tex1"); c1 = self.p_spectrum_texture(tk, "tex2")
+            f = self.scalar_tex_id(self.p_scalar_texture(tk, "f"))
+            tid = self.add_texture(IR.TEX_BLEND, child=(c0, c1), aux=f)
+        elif tp == "gradient":               # MaterialParser.hs:212-219 -> gradient (mkGradient steps) f
+            f = self.scalar_tex_id(self.p_scalar_texture(tk, "f"))
+            tk.expect("steps"); tk.expect("{"); steps = []
+            while True:
+                pos = tk.flt(); steps.append((pos, self.p_spectrum(tk)))
+                if tk.peek() == ",": tk.next(); continue
+                break
+            tk.expect("}")
+            steps.sort(key=lambda e: e[0])    # mkGradient: sortBy (compare `on` fst), stable
+            first = len(self.ir.textures)
+            for pos, col in steps: self.add_texture(IR.TEX_CONSTANT, f=[pos], s=col)
+            tid = self.add_texture(IR.TEX_GRADIENT, child=(first, len(steps)), aux=f)
         else:
-            raise NotImplementedError(f"spectrum texture {tp} (outside SURVEY §8)")
+            raise NotImplementedError(f"spectrum texture {tp} (image textures: SURVEY §8(f)2, not built)")
         tk.expect("}")
         return tid
+
+    def computes(self, tid: int) -> bool:
+        t = self.ir.textures[tid]
+        if t.kind in (IR.TEX_BLEND, IR.TEX_GRADIENT): return True
+        if t.kind in (IR.TEX_GRAPHPAPER, IR.TEX_CHECKER): return self.computes(t.child[0]) or self.computes(t.child[1])
+        return False
 
     def map_texture(self, tid: int, fn) -> int:
         """A copy of spectrum-texture tree `tid` with `fn` applied to every constant leaf. Textures only SELECT among
         constant leaves (graphPaper, checker), so f(tex dg) == tex' dg: this is how the host hands the device the
         per-band eta / k spectra of shinyMetal (frApproxEta / frApproxK, Fresnel.hs:72-78) without per-hit arithmetic."""
         t = self.ir.textures[tid]
+        if self.computes(tid):
+            raise NotImplementedError("shinyMetal over a blend / gradient texture: frApproxEta / frApproxK do not commute with the blend")
         if t.kind == IR.TEX_CONSTANT:
             return self.const_tex(fn(np.array(list(t.s.v), F)))
         n = IR.Texture.from_buffer_copy(t)
@@ -229,6 +298,12 @@ class Loader:
 
     def p_material_body(self, tk: Tokens) -> int:   # MaterialParser.hs:30-42
         t = tk.next()
+        if t == "bumpMap":                   # pBumpMap (:44-48) -> bumpMapped d m (Reflection.hs:344-345)
+            d = self.scalar_tex_id(self.p_scalar_texture(tk, "bump"))
+            mid = self.p_material_body(tk)
+            if self.ir.materials[mid].bump: raise NotImplementedError("nested bumpMap")
+            self.ir.materials[mid].bump = d + 1
+            return mid
         if t == "matte":
             kd = self.p_spectrum_texture(tk, "kd"); sig = self.p_scalar_texture(tk, "sigma")
             return self.add_material(IR.MAT_MATTE, [kd], [sig])

@@ -16,7 +16,8 @@ BANDS = 16
 
 SHAPE_BOX, SHAPE_CYLINDER, SHAPE_DISK, SHAPE_QUAD, SHAPE_SPHERE = range(5)
 MAT_MATTE, MAT_GLASS, MAT_MIRROR, MAT_PLASTIC, MAT_METAL, MAT_BLACKBODY, MAT_SHINYMETAL, MAT_TRANSMATTE, MAT_SUBSTRATE = range(9)
-TEX_CONSTANT, TEX_GRAPHPAPER, TEX_CHECKER = range(3)
+TEX_CONSTANT, TEX_GRAPHPAPER, TEX_CHECKER, TEX_BLEND, TEX_GRADIENT = range(5)
+STEX_CONSTANT, STEX_SCALE, STEX_PERLIN, STEX_FBM, STEX_CELLNOISE, STEX_CRYSTAL = range(16, 22)
 LIGHT_INFINITE, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_AREA = range(4)
 ENV_CONSTANT, ENV_RGBTABLE, ENV_SUNSKY = range(3)
 CAM_PERSPECTIVE, CAM_ENVIRONMENT = range(2)
@@ -40,10 +41,16 @@ class Shape(C.Structure):
 
 
 class Texture(C.Structure):
-    _fields_ = [("kind", i32), ("child", i32 * 2), ("_pad", i32), ("f", f32 * 8), ("s", Spectrum)]
+    _fields_ = [("kind", i32), ("child", i32 * 2), ("aux", i32), ("f", f32 * 8), ("s", Spectrum)]
 
 
 class Material(C.Structure):
+    # ftex / bump: 0 = none, else 1 + index of a scalar texture (include/blingcu.h)
+    _fields_ = [("kind", i32), ("tex", i32 * 3), ("f", f32 * 3), ("tex3", i32), ("ftex", i32 * 3), ("bump", i32)]
+
+
+class MaterialV1(C.Structure):
+    """Material record of fixtures saved before the scalar-texture fields existed (npz without an `abi` key)."""
     _fields_ = [("kind", i32), ("tex", i32 * 3), ("f", f32 * 3), ("tex3", i32)]
 
 
@@ -282,6 +289,7 @@ class SceneIR:
         d["cie"] = np.stack([self.cie_x, self.cie_y, self.cie_z]).astype(np.float32)
         d["illum_basis"] = np.asarray(self.illum_basis, np.float32)
         d["name"] = np.frombuffer(self.name.encode(), np.uint8)
+        d["abi"] = np.array([2], np.int32)
         np.savez_compressed(path, **d)
 
     @staticmethod
@@ -297,7 +305,15 @@ class SceneIR:
         ir.tri_verts = z["tri_verts"]; ir.tri_uvs = z["tri_uvs"]; ir.tri_material = z["tri_material"]
         ir.tri_normals = z["tri_normals"] if "tri_normals" in z else None
         ir.tri_prim_id = z["tri_prim_id"] if "tri_prim_id" in z else None
-        ir.shapes = unraw("shapes", Shape); ir.materials = unraw("materials", Material)
+        ir.shapes = unraw("shapes", Shape)
+        if "abi" in z:
+            ir.materials = unraw("materials", Material)
+        else:
+            ir.materials = []
+            for o in unraw("materials", MaterialV1):
+                m = Material(); m.kind = o.kind; m.tex3 = o.tex3
+                for i in range(3): m.tex[i] = o.tex[i]; m.f[i] = o.f[i]
+                ir.materials.append(m)
         ir.textures = unraw("textures", Texture); ir.lights = unraw("lights", Light)
         ir.envs = unraw("envs", EnvMap)
         ir.env_arrays = []

@@ -69,11 +69,27 @@ enum {
    BLINGCU_MAT_KINDS = 9
 };
 
-/* Texture.hs:159-207 */
+/* Texture.hs:159-414. Spectrum textures (0..15) and scalar textures (16..) share one table.
+ * 2-D mappings (TextureMapping2d, Texture.hs:166-181) are encoded in s.v: s.v[0] = 0 uvMapping, s.v[1..4] = su sv ou ov;
+ * s.v[0] = 1 planarMapping, s.v[1..3] = vu, s.v[4..6] = vv, s.v[7..8] = ou ov.
+ * 3-D mappings (identityMapping3d, Texture.hs:150-152) are the 16 floats of the world-to-texture matrix in s.v. */
 enum {
-   BLINGCU_TEX_CONSTANT = 0,   /* s                                       */
-   BLINGCU_TEX_GRAPHPAPER = 1, /* f[0]=lineWidth f[1..4]=su sv ou ov (uvMapping), child[0]=paper child[1]=line */
-   BLINGCU_TEX_CHECKER = 2     /* checkerBoard (Texture.hs:209-221): f[0..2]=scale, child[0]=tex1 child[1]=tex2, on dgP  */
+   BLINGCU_TEX_CONSTANT = 0,   /* s (as a gradient step: f[0] = position)  */
+   BLINGCU_TEX_GRAPHPAPER = 1, /* f[0]=lineWidth, child[0]=paper child[1]=line; aux=0: uvMapping in f[1..4]=su sv ou ov;
+                                  aux=1: 2-D mapping in s.v (see above)                                                  */
+   BLINGCU_TEX_CHECKER = 2,    /* checkerBoard (Texture.hs:209-221): f[0..2]=scale, child[0]=tex1 child[1]=tex2, on dgP  */
+   /* SURVEY §8(f)2, second slice: textures that COMPUTE a spectrum (Texture.hs:129-141,223-253) */
+   BLINGCU_TEX_BLEND = 3,      /* spectrumBlend: child[0]=tex1 child[1]=tex2 aux=scalar texture f                        */
+   BLINGCU_TEX_GRADIENT = 4,   /* gradient: aux=scalar texture, child[0]=index of the first step, child[1]=step count; the
+                                  steps are consecutive CONSTANT entries sorted by position f[0] (mkGradient sorts)      */
+   /* scalar textures (MaterialParser.hs:123-154) */
+   BLINGCU_STEX_CONSTANT = 16, /* f[0]                                                                                   */
+   BLINGCU_STEX_SCALE = 17,    /* scaleTexture a s t = a + s * t: f[0]=a f[1]=s child[0]=t                               */
+   BLINGCU_STEX_PERLIN = 18,   /* noiseTexture (Texture.hs:343-380): s.v = 3-D mapping                                   */
+   BLINGCU_STEX_FBM = 19,      /* fbm (Texture.hs:329-339): aux=octaves f[0]=omega, s.v = 3-D mapping                    */
+   BLINGCU_STEX_CELLNOISE = 20,/* cellNoise (Texture.hs:255-303): aux = distance (0 euclidian, 1 euclidian2, 2 manhattan,
+                                  3 chebyshev), s.v = 3-D mapping                                                        */
+   BLINGCU_STEX_CRYSTAL = 21   /* quasiCrystal (Texture.hs:305-326): aux=octaves, s.v = 2-D mapping                      */
 };
 
 /* Light.hs:31-45 */
@@ -110,7 +126,7 @@ typedef struct blingcu_shape {
 typedef struct blingcu_texture {
    int32_t kind;
    int32_t child[2];
-   int32_t _pad;
+   int32_t aux;       /* third reference / small integer parameter, see the kind list */
    float f[8];
    blingcu_spectrum s;
 } blingcu_texture;
@@ -120,6 +136,10 @@ typedef struct blingcu_material {
    int32_t tex[3];
    float f[3];
    int32_t tex3;   /* fourth texture (shinyMetal); same size and offsets as before for everything else */
+   /* scalar textures. 0 = none, so a zero-filled tail keeps the constant-parameter meaning;
+    * otherwise 1 + index into textures of a BLINGCU_STEX_* entry. */
+   int32_t ftex[3]; /* replaces f[i] (sigma / ior / rough / urough / vrough / depth) by a ScalarTexture evaluated at the hit */
+   int32_t bump;    /* bumpMapped d mat (Reflection.hs:344-377): displacement texture */
 } blingcu_material;
 
 typedef struct blingcu_light {

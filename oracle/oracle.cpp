@@ -3,6 +3,7 @@
 // Restates Material.hs, Texture.hs, Light.hs, Scene.hs, Integrator/Path.hs, Camera.hs, Image.hs,
 // Rendering.hs (tile decomposition) of /root/reference/src/lib/Graphics/Bling.
 #include "oracle_shade.h"
+#include "oracle_texture.h"
 #include "oracle.h"
 #include <atomic>
 #include <chrono>
@@ -37,24 +38,43 @@ struct RayCounters { uint64_t cam = 0, ext = 0, mis = 0, shadow = 0; };
 
 // ----------------------------------------------------------------------------- textures (Texture.hs:159-207)
 static Spec evalSpectrumTexture(const Scene &sc, int id, const DG &dg) {
-   for (int guard = 0; guard < 16; ++guard) {
-      const blingcu_texture &t = sc.textures[id];
-      if (t.kind == BLINGCU_TEX_CONSTANT) return fromC(t.s);
-      if (t.kind == BLINGCU_TEX_CHECKER) {   // checkerBoard (Texture.hs:209-221): (floor x*sx + floor y*sy + floor z*sz) `mod` 2 == 0
-         long q = (long)std::floor(dg.p.x * t.f[0]) + (long)std::floor(dg.p.y * t.f[1]) + (long)std::floor(dg.p.z * t.f[2]);
-         id = (((q % 2) + 2) % 2 == 0) ? t.child[0] : t.child[1];
-         continue;
-      }
-      // graphPaper lw m p l (Texture.hs:191-207) with uvMapping (:166-170)
+   const blingcu_texture &t = sc.textures[id];
+   switch (t.kind) {
+   case BLINGCU_TEX_CONSTANT: return fromC(t.s);
+   case BLINGCU_TEX_CHECKER: {   // checkerBoard (Texture.hs:209-221): (floor x*sx + floor y*sy + floor z*sz) `mod` 2 == 0
+      long q = (long)std::floor(dg.p.x * t.f[0]) + (long)std::floor(dg.p.y * t.f[1]) + (long)std::floor(dg.p.z * t.f[2]);
+      return evalSpectrumTexture(sc, (((q % 2) + 2) % 2 == 0) ? t.child[0] : t.child[1], dg);
+   }
+   case BLINGCU_TEX_GRAPHPAPER: {   // graphPaper lw m p l (Texture.hs:191-207); m = uvMapping (:166-170) or planarMapping (:172-181)
       float lw = t.f[0];
-      float x = t.f[1] * dg.u + t.f[3], z = t.f[2] * dg.v + t.f[4];
+      float x, z;
+      if (t.aux == 0) { x = t.f[1] * dg.u + t.f[3]; z = t.f[2] * dg.v + t.f[4]; } else mapping2d(t.s.v, dg, x, z);
       float xi = std::trunc(x), zi = std::trunc(z);  // properFraction: integer part truncates toward zero
       float xpp = x - xi, zpp = z - zi;
       float xp = std::fabs(xpp), zp = std::fabs(zpp);
       float lo = lw / 2, hi = 1.0f - lo;
-      if (xp < lo || zp < lo || xp > hi || zp > hi) id = t.child[1]; else id = t.child[0];
+      return evalSpectrumTexture(sc, (xp < lo || zp < lo || xp > hi || zp > hi) ? t.child[1] : t.child[0], dg);
    }
-   return sConst(0);
+   case BLINGCU_TEX_BLEND: {   // spectrumBlend (Texture.hs:129-141)
+      Spec v1 = evalSpectrumTexture(sc, t.child[0], dg), v2 = evalSpectrumTexture(sc, t.child[1], dg);
+      float x = evalScalarTexture(sc.textures, t.aux, dg);
+      if (x <= 0) return v1;
+      if (x >= 1) return v2;
+      return sScale(v1, 1 - x) + sScale(v2, x);
+   }
+   case BLINGCU_TEX_GRADIENT: {   // gradient (Texture.hs:239-253); the IR holds gradCols sorted (mkGradient :232-237)
+      float f = evalScalarTexture(sc.textures, t.aux, dg);
+      const blingcu_texture *cols = &sc.textures[t.child[0]]; int n = t.child[1];
+      float gmin = cols[0].f[0], gmax = cols[n - 1].f[0];
+      if (f <= gmin) return fromC(cols[0].s);
+      if (f >= gmax) return fromC(cols[n - 1].s);
+      int idx = 0; while (!(cols[idx].f[0] > f)) ++idx;   // fromJust $ V.findIndex ((> f) . fst)
+      const blingcu_texture &e0 = cols[idx - 1], &e1 = cols[idx];
+      float weight = (f - e0.f[0]) / (e1.f[0] - e0.f[0]);
+      return sScale(fromC(e0.s), 1 - weight) + sScale(fromC(e1.s), weight);
+   }
+   default: return sConst(0);
+   }
 }
 
 // ----------------------------------------------------------------------------- materials (Material.hs:32-96)
@@ -88,7 +108,10 @@ static Bsdf makeBsdf(const Scene &sc, const Hit &hit) {
          dgs.n = ns;
       }
    } else matId = sc.geo.shapes[pr.idx].material;
-   const blingcu_material &m = sc.materials[matId];
+   const blingcu_material &m0 = sc.materials[matId];
+   if (m0.bump) dgs = bump(sc.textures, m0.bump - 1, hit.dg, dgs);   // bumpMapped d mat dgg dgs = mat dgg $ bump d dgg dgs (Reflection.hs:344-345)
+   blingcu_material m = m0;   // ScalarTexture parameters (sigma, ior, rough, ...) are evaluated at the shading geometry
+   for (int i = 0; i < 3; ++i) if (m0.ftex[i]) m.f[i] = evalScalarTexture(sc.textures, m0.ftex[i] - 1, dgs);
    Bsdf b; b.n = 0;
    switch (m.kind) {
    case BLINGCU_MAT_MATTE: {
