@@ -17,7 +17,7 @@ LIB_PATH = _PKG / "libblingcu.so"
 
 # every symbol include/blingcu.h declares
 SYMBOLS = ["create", "destroy", "last_error", "upload_scene", "trace_nearest", "trace_occluded", "trace_stats",
-           "render_pass", "render_slice", "render_samples", "read_film", "clear_film", "film_add_host", "film_device",
+           "render_pass", "render_slice", "render_samples", "eval_texture", "read_film", "clear_film", "film_add_host", "film_device",
            "synchronize", "set_stream", "get_stats", "reset_stats", "set_option", "sample_extent", "kernel_times"]
 
 
@@ -45,6 +45,7 @@ def load_library(path=LIB_PATH, prefix="blingcu"):
     f("render_pass").argtypes = [P, C.c_uint32, C.c_uint64]
     f("render_slice").argtypes = [P, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32]
     f("render_samples").argtypes = [P, C.c_uint32, C.c_uint64, P, P, P, C.c_size_t, P, P]
+    f("eval_texture").argtypes = [P, C.c_int32, P, P, C.c_size_t, P]
     f("read_film").argtypes = [P, P]
     f("clear_film").argtypes = [P]
     f("film_add_host").argtypes = [P, P]
@@ -138,6 +139,13 @@ class Context:
         self._chk(self._f("render_samples")(self._h, pass_index, seed, px.ctypes.data, py.ctypes.data, sample.ctypes.data, n,
                                             L.ctypes.data, xy.ctypes.data))
         return L, xy
+
+    def eval_texture(self, texture: int, p, uv) -> np.ndarray:
+        """`Texture a` at explicit (dgP, (dgU, dgV)) points: (n, 16) spectra; scalar textures answer in column 0."""
+        p = np.ascontiguousarray(p, np.float32).reshape(-1, 3); uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        out = np.zeros((len(p), 16), np.float32)
+        self._chk(self._f("eval_texture")(self._h, texture, p.ctypes.data, uv.ctypes.data, len(p), out.ctypes.data))
+        return out
 
     def read_film(self, out: np.ndarray = None) -> np.ndarray:
         if out is None:

@@ -52,6 +52,10 @@ static thread_local std::string g_createError;
       if (!c || (n && (!px || !py || !s || !L || !xy))) return BLINGCU_EINVAL;                                                   \
       return c->p.be.guard(c->p.err, [&]() { return c->p.renderSamples(pass, seed, px, py, s, n, L, xy); });                      \
    }                                                                                                                             \
+   int PFX##_eval_texture(PFX##_ctx_t *c, int32_t tex, const float *p, const float *uv, size_t n, float *out) {                  \
+      if (!c || (n && (!p || !uv || !out))) return BLINGCU_EINVAL;                                                               \
+      return c->p.be.guard(c->p.err, [&]() { return c->p.evalTexture(tex, p, uv, n, out); });                                    \
+   }                                                                                                                             \
    int PFX##_read_film(PFX##_ctx_t *c, float *wxyz) {                                                                            \
       if (!c || !wxyz) return BLINGCU_EINVAL;                                                                                    \
       if (!c->p.uploaded) { c->p.err = "no scene"; return BLINGCU_ESTATE; }                                                      \

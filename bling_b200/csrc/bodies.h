@@ -405,6 +405,20 @@ struct HitToAbiBody {   // kernel hit (t, b1, b2, ref) -> ABI hit {t, prim id, b
    }
 };
 
+// blingcu_eval_texture: one texture-table entry at explicit points
+struct EvalTextureBody {
+   const DScene *sc; int tex; const float *p, *uv; float *out;
+   HD void operator()(uint32_t i) const {
+      const DScene &S = *sc;
+      DG dg; dg.p = mk3(p[3 * i], p[3 * i + 1], p[3 * i + 2]); dg.u = uv[2 * i]; dg.v = uv[2 * i + 1];
+      dg.n = mk3(0, 0, 1); dg.dpdu = mk3(1, 0, 0); dg.dpdv = mk3(0, 1, 0);
+      Spec s = sConst(0);
+      if (S.textures[tex].kind >= BLINGCU_STEX_CONSTANT) s.v[0] = evalScalarTexture(S, tex, dg);
+      else s = SpectrumValue<BL_BLEND_DEPTH>::eval(S, tex, dg);
+      for (int k = 0; k < NB; ++k) out[(size_t)NB * i + k] = s.v[k];
+   }
+};
+
 struct AddFilmBody { F4 *dst; const F4 *src; HD void operator()(uint32_t i) const { F4 a = dst[i], b = src[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; dst[i] = a; } };
 
 }  // namespace bl

@@ -40,7 +40,7 @@ struct Pipeline {
    std::vector<void *> sceneAllocs;
    PathState ps{}; std::vector<void *> stateAllocs;
    F4 *film = nullptr;
-   uint32_t npix = 0;
+   uint32_t npix = 0, nTextures = 0;
    uint32_t batchTarget = 1u << 26;   // paths per wavefront (~490 B of state each: 33 GB at the cap, sized for 180 GB HBM)
    int maxLeaf = 2;
    uint64_t nNodes = 0, nItems = 0;
@@ -171,7 +171,7 @@ struct Pipeline {
       { std::vector<int32_t> tprim(nt ? nt : 1, 0); for (size_t i = 0; i < nt; ++i) tprim[i] = itemPrim[i]; hs.tri_prim = up<int32_t>(tprim.data(), tprim.size()); }
       hs.shapes = up<blingcu_shape>(ir->shapes, ns); hs.bvh.shapes = hs.shapes;
       hs.materials = up<blingcu_material>(ir->materials, ir->n_materials);
-      hs.textures = up<blingcu_texture>(ir->textures, ir->n_textures);
+      hs.textures = up<blingcu_texture>(ir->textures, ir->n_textures); nTextures = ir->n_textures;
       hs.lights = up<blingcu_light>(ir->lights, ir->n_lights); hs.n_lights = (int)ir->n_lights;
       hs.has_box = 0; for (size_t j = 0; j < ns; ++j) if (ir->shapes[j].kind == BLINGCU_SHAPE_BOX) hs.has_box = 1;
       {
@@ -402,6 +402,19 @@ struct Pipeline {
          outXY[2 * i] = xy[i].x; outXY[2 * i + 1] = xy[i].y;
       }
       be.free(dpx); be.free(dpy); be.free(ds);
+      return 0;
+   }
+
+   int evalTexture(int tex, const float *p, const float *uv, size_t n, float *out) {
+      if (!uploaded) return fail(BLINGCU_ESTATE, "eval_texture before upload_scene");
+      if (tex < 0 || (uint32_t)tex >= nTextures) return fail(BLINGCU_EINVAL, "texture out of range");
+      if (n == 0) return 0;
+      if (n > 0x7fffffffu) return fail(BLINGCU_EINVAL, "too many points");
+      float *dp = (float *)be.alloc(12 * n), *duv = (float *)be.alloc(8 * n), *dout = (float *)be.alloc(64 * n);
+      be.upload(dp, p, 12 * n); be.upload(duv, uv, 8 * n);
+      be.tag(BLINGCU_KC_OTHER); be.run(EvalTextureBody{dscene, tex, dp, duv, dout}, (uint32_t)n);
+      be.download(out, dout, 64 * n);
+      be.free(dp); be.free(duv); be.free(dout);
       return 0;
    }
 

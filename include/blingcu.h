@@ -277,6 +277,11 @@ int blingcu_render_slice(blingcu_ctx *, uint32_t pass_index, uint64_t seed, uint
 int blingcu_render_samples(blingcu_ctx *, uint32_t pass_index, uint64_t seed, const int32_t *px,
                            const int32_t *py, const uint32_t *sample, size_t n, float *out_L, float *out_xy);
 
+/* debug/parity: `Texture a = DifferentialGeometry -> a` (Texture.hs:60-64) of texture-table entry `texture` at n explicit
+ * points: p = n*3 world positions (dgP), uv = n*2 surface parameters (dgU, dgV) -- the only DG fields a texture in scope
+ * reads. out = n*16 floats: the spectrum, or for a BLINGCU_STEX_* entry its value in out[16*i] (rest 0). */
+int blingcu_eval_texture(blingcu_ctx *, int32_t texture, const float *p, const float *uv, size_t n, float *out);
+
 /* film = Img._imgP layout [H][W]{weight, X*w, Y*w, Z*w} f32 (Image.hs:123-129,291-299) */
 int blingcu_read_film(blingcu_ctx *, float *wxyz);
 int blingcu_clear_film(blingcu_ctx *);

@@ -602,6 +602,18 @@ int oracle_reset_stats(oracle_ctx *c) {
    return 0;
 }
 
+int oracle_eval_texture(oracle_ctx *c, int32_t tex, const float *p, const float *uv, size_t n, float *out) {
+   if (tex < 0 || (size_t)tex >= c->sc.textures.size()) return 1;
+   for (size_t i = 0; i < n; ++i) {
+      DG dg = mkDg(mk(p[3 * i], p[3 * i + 1], p[3 * i + 2]), uv[2 * i], uv[2 * i + 1], mk(1, 0, 0), mk(0, 1, 0));
+      Spec s = sConst(0);
+      if (c->sc.textures[tex].kind >= BLINGCU_STEX_CONSTANT) s.v[0] = evalScalarTexture(c->sc.textures, tex, dg);
+      else s = evalSpectrumTexture(c->sc, tex, dg);
+      std::memcpy(out + 16 * i, s.v, sizeof(s.v));
+   }
+   return 0;
+}
+
 // unit-test hooks: BSDF sampling/evaluation of a material at a canonical frame, filter/film on a single tile
 int oracle_add_sample_tile(oracle_ctx *c, int wx0, int wx1, int wy0, int wy1, float sx, float sy, const float *L16,
                            float *out_tile, int *ox, int *oy, int *w, int *h) {

@@ -21,6 +21,7 @@ int oracle_read_film(oracle_ctx *, float *wxyz);
 int oracle_clear_film(oracle_ctx *);
 int oracle_get_stats(oracle_ctx *, blingcu_stats *);
 int oracle_reset_stats(oracle_ctx *);
+int oracle_eval_texture(oracle_ctx *, int32_t texture, const float *p, const float *uv, size_t n, float *out);
 int oracle_add_sample_tile(oracle_ctx *, int wx0, int wx1, int wy0, int wy1, float sx, float sy, const float *L16,
                            float *out_tile, int *ox, int *oy, int *w, int *h);
 #ifdef __cplusplus

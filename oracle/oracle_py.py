@@ -38,6 +38,7 @@ def lib():
         L.oracle_clear_film.argtypes = [P]
         L.oracle_get_stats.argtypes = [P, C.POINTER(IR.Stats)]
         L.oracle_reset_stats.argtypes = [P]
+        L.oracle_eval_texture.argtypes = [P, C.c_int32, P, P, C.c_size_t, P]
         L.oracle_add_sample_tile.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, P, P] + [C.POINTER(C.c_int)] * 4
         _LIB = L
     return _LIB
@@ -91,6 +92,12 @@ class Oracle:
         _chk(lib().oracle_render_samples(self._h, pass_index, seed, px.ctypes.data, py.ctypes.data, sample.ctypes.data, n,
                                          L.ctypes.data, xy.ctypes.data), "render_samples")
         return L, xy
+
+    def eval_texture(self, texture, p, uv):
+        p = np.ascontiguousarray(p, np.float32).reshape(-1, 3); uv = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        out = np.zeros((len(p), 16), np.float32)
+        _chk(lib().oracle_eval_texture(self._h, texture, p.ctypes.data, uv.ctypes.data, len(p), out.ctypes.data), "eval_texture")
+        return out
 
     def render_slice(self, pass_index, seed, s_begin, s_end, threads=1):
         _chk(lib().oracle_render_slice(self._h, pass_index, seed, s_begin, s_end, threads), "render_slice")
