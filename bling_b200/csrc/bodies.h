@@ -10,10 +10,13 @@
 
 namespace bl {
 
-enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MISANY = 4, C_DROPPED = 5, C_MISCULL = 6, C_EXTCULL = 7, C_MAT0 = 8, N_COUNTERS = 8 + 2 + BLINGCU_MAT_KINDS };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + shade kind
+enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MISANY = 4, C_DROPPED = 5, C_MISCULL = 6, C_EXTCULL = 7, C_MAT0 = 8, C_SPAWN = 8 + 17, C_OVERFLOW, N_COUNTERS };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + shade kind
 // shade kinds: the material kinds, then SK_TEXTURED = materials whose textures compute (textures.h); upload puts the
 // shade kind of each primitive's material into its hit reference
-enum { SK_TEXTURED = BLINGCU_MAT_KINDS, N_SHADE_KINDS = 2 + BLINGCU_MAT_KINDS };
+// Textured materials are spread over N_TEX_QUEUES queues by material (kind values SK_TEXTURED .. 15 of the 4-bit field of the
+// hit reference), so that one launch of the general kernel runs few materials: its code is large and warps that sit in
+// different materials starve each other's instruction fetch.
+enum { SK_TEXTURED = BLINGCU_MAT_KINDS, N_TEX_QUEUES = 16 - BLINGCU_MAT_KINDS, N_SHADE_KINDS = 1 + 16 };
 enum { S_SAMPLES = 0, S_CAM, S_EXT, S_MIS, S_SHADOW, S_DROPPED, S_MISCULL, S_MISANY, S_EXTCULL, N_STATS = 12 };
 
 struct PathState {
@@ -33,6 +36,7 @@ struct PathState {
    uint32_t *qA, *qB;      // active queues (ping-pong)
    uint32_t *qShadow, *qMis, *qMisAny;   // qMis: nearest-hit MIS rays (area lights); qMisAny: any-hit MIS rays (infinite lights)
    uint32_t *qMat;         // N_SHADE_KINDS * cap
+   uint32_t *root;         // direct-lighting integrator: slot of the camera sample a spawned branch belongs to
    uint32_t *counters;     // N_COUNTERS
    unsigned long long *stats;   // N_STATS
 };
@@ -47,6 +51,15 @@ HD void storeSpec4(F4 *base, uint32_t cap, uint32_t i, const Spec &s) {
 }
 HD void storeRay(F4 *o, F4 *d, uint32_t i, const Ray &r) { F4 a, b; a.x = r.o.x; a.y = r.o.y; a.z = r.o.z; a.w = r.tmin; b.x = r.d.x; b.y = r.d.y; b.z = r.d.z; b.w = r.tmax; o[i] = a; d[i] = b; }
 HD Ray loadRay(const F4 *o, const F4 *d, uint32_t i) { F4 a = o[i], b = d[i]; Ray r; r.o = mk3(a.x, a.y, a.z); r.tmin = a.w; r.d = mk3(b.x, b.y, b.z); r.tmax = b.w; return r; }
+
+// L[slot] += s with atomics (direct-lighting integrator: several branch slots feed one camera sample)
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void addSpec4Atomic(F4 *base, uint32_t cap, uint32_t i, const Spec &s) {
+   BL_UNROLL for (int q = 0; q < 4; ++q) { float *p = (float *)(base + (size_t)q * cap + i); BL_UNROLL for (int k = 0; k < 4; ++k) atomicAdd(p + k, s.v[4 * q + k]); }
+}
+#else
+inline void addSpec4Atomic(F4 *base, uint32_t cap, uint32_t i, const Spec &s) { storeSpec4(base, cap, i, loadSpec4(base, cap, i) + s); }
+#endif
 
 // queue append: warp-aggregated atomic on the device, plain increment in the single-threaded emulator
 #if defined(__CUDA_ARCH__)
@@ -139,6 +152,63 @@ struct ShadeMissBody {   // Path.hs:43-47
 };
 
 // ------------------------------------------------------------------------------------------ K5 shade (hit)
+// sampleOneLight (Scene.hs:110-118) at one vertex, shared by the path and the direct-lighting shade bodies: queues the
+// NEE shadow ray and the BSDF-MIS ray of slot i with their pending contributions (already x T x nLights).
+// T (16 registers) is re-read from L1/L2 at each use instead of being kept live: the shade kernels are register-bound.
+template <class M>
+HD void directAtVertex(const DScene &S, const PathState &ps, uint32_t i, const Bsdf &bsdf, V3 wo, V3 p, V3 n, float eps,
+                       float lNumU, float lD1, float lD2, float bCompU, float bD1, float bD2) {
+   int lc = S.n_lights;
+   if (lc > 0) {   // sampleOneLight (Scene.hs:110-118)
+      int ln = (lc == 1) ? 0 : imin((int)floorf(lNumU * (float)lc), lc - 1);
+      const blingcu_light &lt = S.lights[ln];
+      float lcf = (lc == 1) ? 1.0f : (float)lc;
+      {   // sampleLightMis (Scene.hs:61-69)
+         LightSample ls; lightSampleOf<M>(S, lt, p, eps, n, lD1, lD2, ls);
+         if (ls.pdf != 0 && !isBlack(ls.de)) {
+            Spec f = evalBsdfOf<M>(bsdf, wo, ls.wi);
+            if (!isBlack(f)) {
+               float w = ls.delta ? 1 / ls.pdf : powerHeuristic(ls.pdf, bsdfPdfOf<M>(bsdf, wo, ls.wi)) / ls.pdf;
+               Spec c = sScale(f * ls.de, w);
+               if (lc > 1) c = sScale(c, lcf);
+               storeSpec4(ps.PS, ps.cap, i, loadSpec4(ps.T, ps.cap, i) * c);
+               storeRay(ps.shO, ps.shD, i, ls.testRay);
+               qPush(ps.qShadow, ps.counters + C_SHADOW, i);
+            }
+         }
+      }
+      {   // sampleBsdfMis (Scene.hs:71-82): the ray is traced now, the light lookup happens in the resolve bodies.
+         // The reference traces a nearest-hit ray and keeps the sample only if the hit primitive IS the chosen
+         // light, or, on a miss, adds `le l ray`. Same result with less traversal:
+         //   infinite light  -> only hit/miss matters: any-hit query (qMisAny) -- unless the scene holds a Box shape:
+         //                      the reference's Box answers `intersects` for a ray that starts inside it but not
+         //                      `intersect` (Shape.hs:86-93 vs :235), so there the nearest-hit query is kept;
+         //   area light      -> a ray that does not even reach the light's own shape contributes nothing: culled;
+         //   delta lights    -> never hit, `le` is black: culled.
+         BsdfSample bs; sampleBsdfOf<M>(bsdf, wo, bCompU, bD1, bD2, bs);
+         if (bs.pdf != 0 && !isBlack(bs.f)) {
+            Ray mr; mr.o = p; mr.d = bs.wi; mr.tmin = eps; mr.tmax = BL_INF;
+            const bool inf = lt.kind == BLINGCU_LIGHT_INFINITE;
+            bool any = inf && !S.has_box, keep = inf;
+            if (lt.kind == BLINGCU_LIGHT_AREA) {
+               const blingcu_shape &ls = S.shapes[lt.shape];
+               float tl; DG dgl;
+               keep = shapeIntersect<false>(ls, transRay(ls.w2o, mr), tl, dgl);
+            }
+            if (keep) {
+               Spec c = bs.f;
+               if (lc > 1) c = sScale(c, lcf);
+               storeSpec4(ps.PM, ps.cap, i, loadSpec4(ps.T, ps.cap, i) * c);
+               storeRay(ps.miO, ps.miD, i, mr);
+               F2 info; info.x = bs.pdf; info.y = i2f(ln); ps.miInfo[i] = info;
+               if (any) qPush(ps.qMisAny, ps.counters + C_MISANY, i);
+               else qPush(ps.qMis, ps.counters + C_MIS, i);
+            } else cntAdd(ps.counters + C_MISCULL, 1u);
+         }
+      }
+   }
+}
+
 template <int MATKIND>
 struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118; one instantiation per material kind (material-sorted queues)
    typedef MatOf<MATKIND> M;
@@ -153,7 +223,7 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118; one instantiation pe
       SurfaceHit sh; DG dgs;
       surfaceAt(S, ray, hv.x, hv.y, hv.z, f2i(hv.w), sh, dgs);
       Spec texScratch[M::TX ? 4 : 1];   // computed texture values of the textured instantiation (unused otherwise)
-      Bsdf bsdf; makeBsdf<M>(S, sh, dgs, bsdf, texScratch);
+      Bsdf bsdf; makeBsdfOf<M>(S, sh, dgs, bsdf, texScratch);
       // T (16 registers) is re-read from L1/L2 at each use instead of being kept live across the whole body: the
       // kernel is register-bound (occupancy), not bandwidth-bound
 #define BL_T() loadSpec4(ps.T, ps.cap, i)
@@ -171,62 +241,14 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118; one instantiation pe
       float lD1, lD2; rnd2D(smp, 1 + 3 * depth, lD1, lD2);
       float bCompU = rnd1D(smp, 2 + 4 * depth);
       float bD1, bD2; rnd2D(smp, 2 + 3 * depth, bD1, bD2);
-      int lc = S.n_lights;
-      if (lc > 0) {   // sampleOneLight (Scene.hs:110-118)
-         int ln = (lc == 1) ? 0 : imin((int)floorf(lNumU * (float)lc), lc - 1);
-         const blingcu_light &lt = S.lights[ln];
-         float lcf = (lc == 1) ? 1.0f : (float)lc;
-         {   // sampleLightMis (Scene.hs:61-69)
-            LightSample ls; lightSample(S, lt, p, eps, n, lD1, lD2, ls);
-            if (ls.pdf != 0 && !isBlack(ls.de)) {
-               Spec f = evalBsdf<M>(bsdf, wo, ls.wi);
-               if (!isBlack(f)) {
-                  float w = ls.delta ? 1 / ls.pdf : powerHeuristic(ls.pdf, bsdfPdf<M>(bsdf, wo, ls.wi)) / ls.pdf;
-                  Spec c = sScale(f * ls.de, w);
-                  if (lc > 1) c = sScale(c, lcf);
-                  storeSpec4(ps.PS, ps.cap, i, BL_T() * c);
-                  storeRay(ps.shO, ps.shD, i, ls.testRay);
-                  qPush(ps.qShadow, ps.counters + C_SHADOW, i);
-               }
-            }
-         }
-         {   // sampleBsdfMis (Scene.hs:71-82): the ray is traced now, the light lookup happens in the resolve bodies.
-            // The reference traces a nearest-hit ray and keeps the sample only if the hit primitive IS the chosen
-            // light, or, on a miss, adds `le l ray`. Same result with less traversal:
-            //   infinite light  -> only hit/miss matters: any-hit query (qMisAny) -- unless the scene holds a Box shape:
-            //                      the reference's Box answers `intersects` for a ray that starts inside it but not
-            //                      `intersect` (Shape.hs:86-93 vs :235), so there the nearest-hit query is kept;
-            //   area light      -> a ray that does not even reach the light's own shape contributes nothing: culled;
-            //   delta lights    -> never hit, `le` is black: culled.
-            BsdfSample bs; sampleBsdf<M>(bsdf, wo, bCompU, bD1, bD2, bs);
-            if (bs.pdf != 0 && !isBlack(bs.f)) {
-               Ray mr; mr.o = p; mr.d = bs.wi; mr.tmin = eps; mr.tmax = BL_INF;
-               const bool inf = lt.kind == BLINGCU_LIGHT_INFINITE;
-               bool any = inf && !S.has_box, keep = inf;
-               if (lt.kind == BLINGCU_LIGHT_AREA) {
-                  const blingcu_shape &ls = S.shapes[lt.shape];
-                  float tl; DG dgl;
-                  keep = shapeIntersect<false>(ls, transRay(ls.w2o, mr), tl, dgl);
-               }
-               if (keep) {
-                  Spec c = bs.f;
-                  if (lc > 1) c = sScale(c, lcf);
-                  storeSpec4(ps.PM, ps.cap, i, BL_T() * c);
-                  storeRay(ps.miO, ps.miD, i, mr);
-                  F2 info; info.x = bs.pdf; info.y = i2f(ln); ps.miInfo[i] = info;
-                  if (any) qPush(ps.qMisAny, ps.counters + C_MISANY, i);
-                  else qPush(ps.qMis, ps.counters + C_MIS, i);
-               } else cntAdd(ps.counters + C_MISCULL, 1u);
-            }
-         }
-      }
+      directAtVertex<M>(S, ps, i, bsdf, wo, p, n, eps, lNumU, lD1, lD2, bCompU, bD1, bD2);
       // Russian roulette (Path.hs:68-72)
       float pc = (depth <= 7) ? 1.0f : hminf(0.75f, sY(S, BL_T()));
       float x = rnd1D(smp, 3 + 4 * depth);
       if (x > pc) return;
       float uc = rnd1D(smp, 0 + 4 * depth);
       float ud1, ud2; rnd2D(smp, 0 + 3 * depth, ud1, ud2);
-      BsdfSample s; sampleBsdf<M>(bsdf, wo, uc, ud1, ud2, s);
+      BsdfSample s; sampleBsdfOf<M>(bsdf, wo, uc, ud1, ud2, s);
       if (s.pdf == 0 || isBlack(s.f)) return;
       // The vertex this ray would find has depth == maxDepth: nextVertex returns l there (Path.hs:51), and a miss only
       // adds light after a SPECULAR bounce (Path.hs:43-47). After a non-specular sample the ray decides nothing, so
@@ -249,8 +271,19 @@ struct ResolveShadowBody {   // Scene.hs:64: `occluded scene ray` -> black
       storeSpec4(ps.L, ps.cap, i, loadSpec4(ps.L, ps.cap, i) + loadSpec4(ps.PS, ps.cap, i));
    }
 };
-struct ResolveMisBody {   // Scene.hs:75-82
-   const DScene *sc; PathState ps;
+// where a slot's radiance goes: itself (path integrator; camera samples of the direct-lighting integrator), or the camera
+// sample a spawned branch belongs to
+HD uint32_t rootOf(const PathState &ps, uint32_t nRoot, uint32_t i) { return i < nRoot ? i : ps.root[i]; }
+struct DlResolveShadowBody {
+   PathState ps; uint32_t nRoot;
+   HD void operator()(uint32_t i) const {
+      if (ps.occl[i]) return;
+      addSpec4Atomic(ps.L, ps.cap, rootOf(ps, nRoot, i), loadSpec4(ps.PS, ps.cap, i));
+   }
+};
+template <bool DL>
+struct ResolveMisBodyT {   // Scene.hs:75-82
+   const DScene *sc; PathState ps; uint32_t nRoot;
    HD void operator()(uint32_t i) const {
       const DScene &S = *sc;
       F4 hv = ps.mihit[i];
@@ -274,12 +307,16 @@ struct ResolveMisBody {   // Scene.hs:75-82
       }
       float w = powerHeuristic(info.x, lightPdf(S, l, ray.o, ray.d));   // Q3: also for specular samples
       Spec c = sScale(loadSpec4(ps.PM, ps.cap, i) * li, w);
-      storeSpec4(ps.L, ps.cap, i, loadSpec4(ps.L, ps.cap, i) + c);
+      if (DL) addSpec4Atomic(ps.L, ps.cap, rootOf(ps, nRoot, i), c);
+      else storeSpec4(ps.L, ps.cap, i, loadSpec4(ps.L, ps.cap, i) + c);
    }
 };
+typedef ResolveMisBodyT<false> ResolveMisBody;
+typedef ResolveMisBodyT<true> DlResolveMisBody;
 
-struct ResolveMisAnyBody {   // Scene.hs:75-82, miss branch: `le l ray` of an infinite light
-   const DScene *sc; PathState ps;
+template <bool DL>
+struct ResolveMisAnyBodyT {   // Scene.hs:75-82, miss branch: `le l ray` of an infinite light
+   const DScene *sc; PathState ps; uint32_t nRoot;
    HD void operator()(uint32_t i) const {
       if (ps.occlM[i]) return;
       const DScene &S = *sc;
@@ -290,7 +327,69 @@ struct ResolveMisAnyBody {   // Scene.hs:75-82, miss branch: `le l ray` of an in
       if (isBlack(li)) return;
       float w = powerHeuristic(info.x, lightPdf(S, l, ray.o, ray.d));   // Q3: also for specular samples
       Spec c = sScale(loadSpec4(ps.PM, ps.cap, i) * li, w);
-      storeSpec4(ps.L, ps.cap, i, loadSpec4(ps.L, ps.cap, i) + c);
+      if (DL) addSpec4Atomic(ps.L, ps.cap, rootOf(ps, nRoot, i), c);
+      else storeSpec4(ps.L, ps.cap, i, loadSpec4(ps.L, ps.cap, i) + c);
+   }
+};
+typedef ResolveMisAnyBodyT<false> ResolveMisAnyBody;
+typedef ResolveMisAnyBodyT<true> DlResolveMisAnyBody;
+
+// ------------------------------------------------------------------------------------------ direct-lighting integrator
+// Integrator/DirectLighting.hs:23-58 on the same wavefront: one launch per depth over the active queue.
+//   directLighting d: miss -> black; hit -> sampleOneLight + intLe int wo + f_r * L(reflected) + f_t * L(transmitted)
+// where the two continuations follow only SPECULAR components (`cont`, :47-58: sampleBsdf' t bsdf wo 0.5 (0.5, 0.5)) and stop
+// at d + 1 == maxDepth. The recursion is a tree: the first continuation stays in the slot, the second is spawned into a
+// fresh slot (C_SPAWN); every slot adds its radiance to the camera sample it descends from (rootOf) with atomics.
+// One instantiation for all material kinds (MatOf<SK_TEXTURED>: every BxDF, computing textures).
+struct DlShadeBody {
+   typedef MatOf<SK_TEXTURED> M;
+   const DScene *sc; PathState ps; uint32_t *qNext; uint32_t nRoot;
+   HD void operator()(uint32_t i) const {
+      const DScene &S = *sc;
+      F4 hv = ps.hit[i];
+      if (f2i(hv.w) == BL_REF_MISS) return;
+      Ray ray = loadRay(ps.rayO, ps.rayD, i);
+      const int depth = (int)(ps.meta[i] & 0xffu);
+      Sampler smp = mkSampler(S, ps.kp[i], ps.sidx[i]);
+      SurfaceHit sh; DG dgs;
+      surfaceAt(S, ray, hv.x, hv.y, hv.z, f2i(hv.w), sh, dgs);
+      Spec texScratch[4];
+      Bsdf bsdf; makeBsdfOf<M>(S, sh, dgs, bsdf, texScratch);
+      const uint32_t root = rootOf(ps, nRoot, i);
+      V3 wo = -ray.d, n = bsdf.cs.n, p = bsdf.p; float eps = sh.eps;
+      if (sh.light >= 0) {   // intLe int wo (:45): unlike the path integrator (Q1) the test uses wo
+         const blingcu_light &el = S.lights[sh.light];
+         if (el.kind == BLINGCU_LIGHT_AREA && areaEmits(sh.dgg.n, wo)) addSpec4Atomic(ps.L, ps.cap, root, loadSpec4(ps.T, ps.cap, i) * loadSpec(el.s.v));
+      }
+      float uln = rnd1D(smp, 0 + 2 * depth);
+      float uld1, uld2; rnd2D(smp, 0 + 2 * depth, uld1, uld2);
+      float ubc = rnd1D(smp, 1 + 2 * depth);
+      float ubd1, ubd2; rnd2D(smp, 1 + 2 * depth, ubd1, ubd2);
+      directAtVertex<M>(S, ps, i, bsdf, wo, p, n, eps, uln, uld1, uld2, ubc, ubd1, ubd2);
+      if (depth + 1 == S.max_depth) return;   // cont: d == md -> black
+      const Spec T = loadSpec4(ps.T, ps.cap, i);
+      const uint64_t kp = ps.kp[i]; const uint32_t sidx = ps.sidx[i];
+      bool first = true;
+      for (int c = 0; c < 2; ++c) {
+         BsdfSample s; sampleBsdfSpecularGeneral(bsdf, BX_SPECULAR | (c == 0 ? BX_REFLECTION : BX_TRANSMISSION), wo, s);
+         if (s.pdf == 0) continue;
+         uint32_t j = i;
+         if (!first) {
+#if defined(__CUDA_ARCH__)
+            j = atomicAdd(ps.counters + C_SPAWN, 1u);
+#else
+            j = ps.counters[C_SPAWN]++;
+#endif
+            if (j >= ps.cap) { ps.counters[C_OVERFLOW] = 1u; continue; }   // the host re-runs the batch with more head-room
+            ps.root[j] = root; ps.kp[j] = kp; ps.sidx[j] = sidx;
+         }
+         first = false;
+         Ray nr; nr.o = p; nr.d = s.wi; nr.tmin = eps; nr.tmax = BL_INF;
+         storeRay(ps.rayO, ps.rayD, j, nr);
+         storeSpec4(ps.T, ps.cap, j, s.f * T);
+         ps.meta[j] = (uint32_t)(depth + 1) | (1u << 8);
+         qPush(qNext, ps.counters + C_NEXT, j);
+      }
    }
 };
 
@@ -310,7 +409,7 @@ struct BeginBatchBody {
    HD void operator()(uint32_t) const {
       uint32_t *c = ps.counters;
       for (int k = 0; k < N_COUNTERS; ++k) if (k != C_DROPPED) c[k] = 0;
-      c[C_ACTIVE] = n;
+      c[C_ACTIVE] = n; c[C_SPAWN] = n;
       statAdd(ps.stats + S_CAM, n); statAdd(ps.stats + S_SAMPLES, n);
    }
 };

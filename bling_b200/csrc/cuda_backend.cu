@@ -233,10 +233,15 @@ struct CudaBackend {
       Scope sc_(this);
       kRunQueueHeavy<ShadeHitBody<MK>><<<gridFor(bound, 128, resident(kRunQueueHeavy<ShadeHitBody<MK>>, 128)), 128, 0, stream>>>(b, q, cnt);
    }
-   void runQueue(const ResolveMisBody &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
+   template <bool DL> void runQueue(const ResolveMisBodyT<DL> &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
       if (bound == 0) return;
       Scope sc_(this);
-      kRunQueueHeavy<ResolveMisBody><<<gridFor(bound, 128, resident(kRunQueueHeavy<ResolveMisBody>, 128)), 128, 0, stream>>>(b, q, cnt);
+      kRunQueueHeavy<ResolveMisBodyT<DL>><<<gridFor(bound, 128, resident(kRunQueueHeavy<ResolveMisBodyT<DL>>, 128)), 128, 0, stream>>>(b, q, cnt);
+   }
+   void runQueue(const DlShadeBody &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
+      if (bound == 0) return;
+      Scope sc_(this);
+      kRunQueueHeavy<DlShadeBody><<<gridFor(bound, 128, resident(kRunQueueHeavy<DlShadeBody>, 128)), 128, 0, stream>>>(b, q, cnt);
    }
    void traceNearest(const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc, const F4 *o, const F4 *d, F4 *hit) {
       if (!n) return;

@@ -164,8 +164,9 @@ struct SamplerConst {
    int nuShift;            // log2(nu) when nu is a power of two, else -1
    float du, dv, invN;
 };
-HD SamplerConst mkSamplerConst(int nu, int nv, int sampleDepth, int stratified) {
-   SamplerConst k; k.nu = nu; k.nv = nv; k.n1d = 4 * sampleDepth; k.n2d = 3 * sampleDepth; k.stratified = stratified;   // Path.hs:18-36
+// n1d / n2d = the integrator's sampleCount1D / sampleCount2D (Path.hs:18-36: 4 sd, 3 sd; DirectLighting.hs:18-19: 2 md, 2 md)
+HD SamplerConst mkSamplerConst(int nu, int nv, int n1d, int n2d, int stratified) {
+   SamplerConst k; k.nu = nu; k.nv = nv; k.n1d = n1d; k.n2d = n2d; k.stratified = stratified;
    k.N = (uint32_t)(nu * nv); k.wmask = k.N > 1 ? smear(k.N) : 0u; k.pow2N = (k.N & (k.N - 1)) == 0;
    k.nuShift = -1; for (int b = 0; b < 31; ++b) if ((1u << b) == (uint32_t)nu) k.nuShift = b;
    k.du = 1.0f / (float)nu; k.dv = 1.0f / (float)nv; k.invN = 1.0f / (float)k.N;

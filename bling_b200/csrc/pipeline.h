@@ -65,6 +65,8 @@ struct Pipeline {
       if (ir->width <= 0 || ir->height <= 0) return fail(BLINGCU_EINVAL, "bad image size");
       if (ir->nu <= 0 || ir->nv <= 0) return fail(BLINGCU_EINVAL, "bad sampler");
       if (ir->max_depth < 0 || ir->max_depth > 254) return fail(BLINGCU_EINVAL, "max_depth out of range");
+      if (ir->integrator_kind != BLINGCU_INTEGRATOR_PATH && ir->integrator_kind != BLINGCU_INTEGRATOR_DIRECT) return fail(BLINGCU_EINVAL, "unknown integrator");
+      if (ir->integrator_kind == BLINGCU_INTEGRATOR_DIRECT && ir->max_depth > 24) return fail(BLINGCU_EINVAL, "direct lighting: max_depth out of range");
       size_t nt = (size_t)ir->n_triangles, ns = ir->n_shapes, nprim = nt + ns;
       // ---- validate indices
       for (size_t i = 0; i < nt; ++i) if (ir->tri_material[i] < 0 || (uint32_t)ir->tri_material[i] >= ir->n_materials) return fail(BLINGCU_EINVAL, "triangle material out of range");
@@ -129,7 +131,7 @@ struct Pipeline {
       }
       // shade kind per material: its kind, or SK_TEXTURED when its textures compute (the slow, general shade kernel)
       std::vector<int> shadeKind(ir->n_materials ? ir->n_materials : 1, 0);
-      for (uint32_t i = 0; i < ir->n_materials; ++i) shadeKind[i] = materialComputes(ir, ir->materials[i]) ? (int)SK_TEXTURED : ir->materials[i].kind;
+      { int nTex = 0; for (uint32_t i = 0; i < ir->n_materials; ++i) shadeKind[i] = materialComputes(ir, ir->materials[i]) ? (int)SK_TEXTURED + (nTex++ % N_TEX_QUEUES) : ir->materials[i].kind; }
       BvhBuildInput bi; bi.n = nprim; bi.lo = lo.data(); bi.hi = hi.data(); bi.max_leaf = maxLeaf;
       bi.threads = (int)std::max(1u, std::thread::hardware_concurrency());
       BvhBuildOutput bo;
@@ -193,7 +195,11 @@ struct Pipeline {
       hs.EW = hs.ex1 - hs.ex0 + 1; hs.EH = hs.ey1 - hs.ey0 + 1;
       hs.sampler_kind = ir->sampler_kind; hs.nu = ir->nu; hs.nv = ir->nv;
       hs.max_depth = ir->max_depth; hs.sample_depth = ir->sample_depth;
-      hs.smp = mkSamplerConst(hs.nu, hs.nv, hs.sample_depth, hs.sampler_kind == BLINGCU_SAMPLER_STRATIFIED);
+      hs.integrator = ir->integrator_kind;
+      const bool direct = hs.integrator == BLINGCU_INTEGRATOR_DIRECT;
+      hs.smp = mkSamplerConst(hs.nu, hs.nv, direct ? 2 * hs.max_depth : 4 * hs.sample_depth, direct ? 2 * hs.max_depth : 3 * hs.sample_depth,
+                              hs.sampler_kind == BLINGCU_SAMPLER_STRATIFIED);
+      dlHeadroom = 2;
       for (int i = 0; i < NB; ++i) { hs.cieX[i] = ir->cie_x.v[i]; hs.cieY[i] = ir->cie_y.v[i]; hs.cieZ[i] = ir->cie_z.v[i]; }
       hs.ySum = ir->cie_y_sum;
       for (int b = 0; b < 7; ++b) for (int i = 0; i < NB; ++i) hs.illum[b][i] = ir->illum_basis[b].v[i];
@@ -220,6 +226,7 @@ struct Pipeline {
       ps.meta = st<uint32_t>(c); ps.kp = st<uint64_t>(c); ps.sidx = st<uint32_t>(c); ps.spos = st<F2>(c); ps.xyz = st<F4>(c);
       ps.qA = st<uint32_t>(c); ps.qB = st<uint32_t>(c); ps.qShadow = st<uint32_t>(c); ps.qMis = st<uint32_t>(c); ps.qMisAny = st<uint32_t>(c);
       ps.qMat = st<uint32_t>((size_t)N_SHADE_KINDS * c);
+      ps.root = st<uint32_t>(hs.integrator == BLINGCU_INTEGRATOR_DIRECT ? c : 1);
       ps.counters = st<uint32_t>(N_COUNTERS); ps.stats = st<unsigned long long>(N_STATS);
       be.zero(ps.counters, sizeof(uint32_t) * N_COUNTERS); be.zero(ps.stats, sizeof(unsigned long long) * N_STATS);
       return 0;
@@ -248,8 +255,8 @@ struct Pipeline {
                case BLINGCU_MAT_SHINYMETAL: be.runQueue(ShadeHitBody<BLINGCU_MAT_SHINYMETAL>{dscene, ps, qb}, qk, ck, bound); break;
                case BLINGCU_MAT_TRANSMATTE: be.runQueue(ShadeHitBody<BLINGCU_MAT_TRANSMATTE>{dscene, ps, qb}, qk, ck, bound); break;
                case BLINGCU_MAT_SUBSTRATE: be.runQueue(ShadeHitBody<BLINGCU_MAT_SUBSTRATE>{dscene, ps, qb}, qk, ck, bound); break;
-               case SK_TEXTURED: be.runQueue(ShadeHitBody<SK_TEXTURED>{dscene, ps, qb}, qk, ck, bound); break;
-               default: be.runQueue(ShadeHitBody<BLINGCU_MAT_BLACKBODY>{dscene, ps, qb}, qk, ck, bound); break;
+               case BLINGCU_MAT_BLACKBODY: be.runQueue(ShadeHitBody<BLINGCU_MAT_BLACKBODY>{dscene, ps, qb}, qk, ck, bound); break;
+               default: be.runQueue(ShadeHitBody<SK_TEXTURED>{dscene, ps, qb}, qk, ck, bound); break;   // SK_TEXTURED + queue
                }
                launches++;
             }
@@ -346,12 +353,37 @@ struct Pipeline {
       return 0;
    }
 
+   // direct-lighting integrator (bodies.h::DlShadeBody): n camera samples in slots [0, n), spawned branches behind them
+   void bouncesDirect(uint32_t n) {
+      uint32_t *qa = ps.qA, *qb = ps.qB;
+      const uint32_t bound = ps.cap;   // a queue may hold spawned slots too
+      for (int d = 0; d < hs.max_depth; ++d) {
+         be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(qa, ps.counters + C_ACTIVE, bound, dscene, ps.rayO, ps.rayD, ps.hit);
+         be.tag(BLINGCU_KC_SHADE); be.runQueue(DlShadeBody{dscene, ps, qb, n}, qa, ps.counters + C_ACTIVE, bound);
+         be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl);
+         launches += 3;
+         if (hasInfinite && !hasBox) { be.traceAny(ps.qMisAny, ps.counters + C_MISANY, bound, dscene, ps.miO, ps.miD, ps.occlM); launches++; }
+         if (hasArea || (hasInfinite && hasBox)) { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, bound, dscene, ps.miO, ps.miD, ps.mihit); launches++; }
+         be.tag(BLINGCU_KC_RESOLVE); be.runQueue(DlResolveShadowBody{ps, n}, ps.qShadow, ps.counters + C_SHADOW, bound);
+         launches++;
+         if (hasArea || (hasInfinite && hasBox)) { be.runQueue(DlResolveMisBody{dscene, ps, n}, ps.qMis, ps.counters + C_MIS, bound); launches++; }
+         if (hasInfinite && !hasBox) { be.runQueue(DlResolveMisAnyBody{dscene, ps, n}, ps.qMisAny, ps.counters + C_MISANY, bound); launches++; }
+         be.tag(BLINGCU_KC_OTHER); be.run(AdvanceBody{ps}, 1); launches++;
+         uint32_t *t = qa; qa = qb; qb = t;
+      }
+   }
+   // Slots for n camera samples of the direct-lighting integrator: every glass-like vertex spawns one extra slot. Starts at
+   // 2 n and doubles when a batch reports C_OVERFLOW (the batch is then re-run: nothing has reached the film yet); 2^maxDepth n
+   // always suffices.
+   uint32_t dlHeadroom = 2;
+   bool dlOverflowed() { be.sync(); uint32_t f = 0; be.download(&f, ps.counters + C_OVERFLOW, sizeof(f)); return f != 0; }
+
    bool kindPresent[N_SHADE_KINDS] = {};
    bool hasInfinite = false, hasArea = false, hasBox = false;
    void scanKinds(const blingcu_scene *ir) {
       for (int k = 0; k < N_SHADE_KINDS; ++k) kindPresent[k] = false;
       kindPresent[0] = true;
-      for (uint32_t i = 0; i < ir->n_materials; ++i) kindPresent[1 + (materialComputes(ir, ir->materials[i]) ? (int)SK_TEXTURED : ir->materials[i].kind)] = true;
+      { int nTex = 0; for (uint32_t i = 0; i < ir->n_materials; ++i) kindPresent[1 + (materialComputes(ir, ir->materials[i]) ? (int)SK_TEXTURED + (nTex++ % N_TEX_QUEUES) : ir->materials[i].kind)] = true; }
       hasInfinite = hasArea = hasBox = false;
       for (uint32_t i = 0; i < ir->n_shapes; ++i) hasBox |= ir->shapes[i].kind == BLINGCU_SHAPE_BOX;
       for (uint32_t i = 0; i < ir->n_lights; ++i) { hasInfinite |= ir->lights[i].kind == BLINGCU_LIGHT_INFINITE; hasArea |= ir->lights[i].kind == BLINGCU_LIGHT_AREA; }
@@ -361,17 +393,25 @@ struct Pipeline {
       if (!uploaded) return fail(BLINGCU_ESTATE, "render before upload_scene");
       uint32_t spp = (uint32_t)(hs.nu * hs.nv);
       if (sBegin > sEnd || sEnd > spp) return fail(BLINGCU_EINVAL, "sample range out of bounds");
-      uint32_t kmax = std::max(1u, batchTarget / npix);
+      const bool direct = hs.integrator == BLINGCU_INTEGRATOR_DIRECT;
+      uint32_t kmax = std::max(1u, (direct ? batchTarget / 4 : batchTarget) / npix);
       uint32_t need = std::min(kmax, std::max(1u, sEnd - sBegin)) * npix;
-      ensureState(need);
+      if (!direct) ensureState(need);
       auto t0 = be.timerStart();
       for (uint32_t s = sBegin; s < sEnd;) {
          uint32_t k = std::min(kmax, sEnd - s);
          uint32_t n = k * npix;
+         if (direct) {
+            if ((uint64_t)n * dlHeadroom > 0x7fffffffull) return fail(BLINGCU_EINVAL, "direct lighting: wavefront too large");
+            ensureState(n * dlHeadroom);
+         }
          be.tag(BLINGCU_KC_OTHER); be.run(BeginBatchBody{ps, n}, 1);
          be.tag(BLINGCU_KC_RAYGEN); be.run(RaygenBody{dscene, ps, seed, pass, s, npix, nullptr, nullptr, nullptr}, n);
          launches += 2;
-         bounces(n);
+         if (direct) {
+            bouncesDirect(n);
+            if (dlOverflowed()) { dlHeadroom *= 2; continue; }   // same batch again with twice the slots
+         } else bounces(n);
          be.tag(BLINGCU_KC_FILM); be.run(FinalizeBody{dscene, ps}, n);
          be.run(FilmBody{dscene, ps, film, k, npix}, (uint32_t)hs.W * (uint32_t)hs.H);
          launches += 2;
@@ -387,12 +427,19 @@ struct Pipeline {
       if (n > 0x7fffffffu) return fail(BLINGCU_EINVAL, "too many samples");
       for (size_t i = 0; i < n; ++i)
          if (px[i] < hs.ex0 || px[i] > hs.ex1 || py[i] < hs.ey0 || py[i] > hs.ey1 || smp[i] >= (uint32_t)(hs.nu * hs.nv)) return fail(BLINGCU_EINVAL, "sample outside the sample extent");
-      ensureState((uint32_t)n);
+      const bool direct = hs.integrator == BLINGCU_INTEGRATOR_DIRECT;
       int32_t *dpx = (int32_t *)be.alloc(4 * n), *dpy = (int32_t *)be.alloc(4 * n); uint32_t *ds = (uint32_t *)be.alloc(4 * n);
       be.upload(dpx, px, 4 * n); be.upload(dpy, py, 4 * n); be.upload(ds, smp, 4 * n);
-      be.run(BeginBatchBody{ps, (uint32_t)n}, 1);
-      be.run(RaygenBody{dscene, ps, seed, pass, 0, npix, dpx, dpy, ds}, (uint32_t)n);
-      bounces((uint32_t)n);
+      for (;;) {
+         if (direct && (uint64_t)n * dlHeadroom > 0x7fffffffull) { be.free(dpx); be.free(dpy); be.free(ds); return fail(BLINGCU_EINVAL, "direct lighting: wavefront too large"); }
+         ensureState((uint32_t)n * (direct ? dlHeadroom : 1u));
+         be.run(BeginBatchBody{ps, (uint32_t)n}, 1);
+         be.run(RaygenBody{dscene, ps, seed, pass, 0, npix, dpx, dpy, ds}, (uint32_t)n);
+         if (!direct) { bounces((uint32_t)n); break; }
+         bouncesDirect((uint32_t)n);
+         if (!dlOverflowed()) break;
+         dlHeadroom *= 2;
+      }
       be.sync();
       std::vector<F4> L(4 * (size_t)ps.cap); std::vector<F2> xy(n);
       for (int q = 0; q < 4; ++q) be.download(L.data() + (size_t)q * n, ps.L + (size_t)q * ps.cap, sizeof(F4) * n);

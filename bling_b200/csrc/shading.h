@@ -29,6 +29,7 @@ struct DScene {
    int W, H; float fw, fh;
    int ex0, ex1, ey0, ey1, EW, EH;   // sample extent (Image.hs:162-168)
    int sampler_kind, nu, nv, max_depth, sample_depth;
+   int integrator;             // BLINGCU_INTEGRATOR_*
    SamplerConst smp;           // per-scene sampler constants (hd.h)
    float cieX[NB], cieY[NB], cieZ[NB], ySum;
    float illum[7][NB];         // r g b c m y w
@@ -165,6 +166,11 @@ enum { FR_NOOP = 0, FR_DIELECTRIC, FR_CONDUCTOR };
 // TX: the material's textures may COMPUTE (scalar textures, blends, gradients, bump mapping; textures.h) -- only the
 // "textured" shade queue (kind index BLINGCU_MAT_KINDS, assigned by upload to such materials) is instantiated with it.
 struct AnyMat { static const unsigned KM = 0x3fu, FM = 0x7u; static const int NC = 2, MK = -1; static const bool TX = false; };
+// GenMat: AnyMat whose per-component BxDF calls go to ONE out-of-line copy each (bxdf*General below) -- used by the general
+// shade kernels, whose code size is what limits them (see "out-of-line general versions")
+struct GenMat : AnyMat {};
+template <class M> struct IsGen { static const bool v = false; };
+template <> struct IsGen<GenMat> { static const bool v = true; };
 template <int MATKIND> struct MatOf : AnyMat {};
 template <> struct MatOf<BLINGCU_MAT_KINDS> : AnyMat { static const bool TX = true; };
 #define BL_K(k) (1u << (k))
@@ -358,6 +364,13 @@ HD void bxdfSample(const BxDF &b, V3 wo, float u1, float u2, Spec &f, V3 &wi, fl
    f = sConst(0); wi = wo; pdf = 0;
 }
 
+HDNI void bxdfEvalGeneral(const BxDF &b, V3 wo, V3 wi, Spec &f) { f = bxdfEval<AnyMat>(b, wo, wi); }
+HDNI float bxdfPdfGeneral(const BxDF &b, V3 wo, V3 wi) { return bxdfPdf<AnyMat>(b, wo, wi); }
+HDNI void bxdfSampleGeneral(const BxDF &b, V3 wo, float u1, float u2, Spec &f, V3 &wi, float &pdf) { bxdfSample<AnyMat>(b, wo, u1, u2, f, wi, pdf); }
+template <class M> HD Spec bxdfEvalOf(const BxDF &b, V3 wo, V3 wi) { if (IsGen<M>::v) { Spec f; bxdfEvalGeneral(b, wo, wi, f); return f; } return bxdfEval<M>(b, wo, wi); }
+template <class M> HD float bxdfPdfOf(const BxDF &b, V3 wo, V3 wi) { if (IsGen<M>::v) return bxdfPdfGeneral(b, wo, wi); return bxdfPdf<M>(b, wo, wi); }
+template <class M> HD void bxdfSampleOf(const BxDF &b, V3 wo, float u1, float u2, Spec &f, V3 &wi, float &pdf) { if (IsGen<M>::v) bxdfSampleGeneral(b, wo, u1, u2, f, wi, pdf); else bxdfSample<M>(b, wo, u1, u2, f, wi, pdf); }
+
 struct Bsdf { int n; BxDF bx[2]; Frame cs; V3 p, ng; };
 struct BsdfSample { int type; float pdf; Spec f; V3 wi; };
 
@@ -374,7 +387,7 @@ HD void sampleBsdf(const Bsdf &bsdf, V3 woW, float uComp, float u1, float u2, Bs
    const int sNum = (M::NC == 1) ? 0 : imax(0, imin(cntm - 1, (int)floorf(uComp * cntf)));
    const BxDF &bx = bsdf.bx[sNum];
    Spec fS; V3 wi = mk3(0, 1, 0); float pdfp = 0;
-   bxdfSample<M>(bx, wo, u1, u2, fS, wi, pdfp);
+   bxdfSampleOf<M>(bx, wo, u1, u2, fS, wi, pdfp);
    V3 wiW = localToWorld(bsdf.cs, wi);
    float sideTest = dot3(wiW, bsdf.ng) / dot3(woW, bsdf.ng);
    if (pdfp == 0 || sideTest == 0) return;
@@ -384,10 +397,30 @@ HD void sampleBsdf(const Bsdf &bsdf, V3 woW, float uComp, float u1, float u2, Bs
    if (bx.type & BX_SPECULAR) { out.pdf = pdfp * invCnt; out.f = sScale(fS, cntf); return; }
    if (M::NC == 1 || cntm == 1) { out.pdf = pdfp; out.f = fS; return; }
    const BxDF &o = bsdf.bx[1 - sNum];
-   float pdf = (pdfp + bxdfPdf<M>(o, wo, wi)) * invCnt;
+   float pdf = (pdfp + bxdfPdfOf<M>(o, wo, wi)) * invCnt;
    Spec fOthers = sConst(0);
-   if (bxMatch(o, wantTrans)) fOthers = fOthers + bxdfEval<M>(o, wi, wo);
+   if (bxMatch(o, wantTrans)) fOthers = fOthers + bxdfEvalOf<M>(o, wi, wo);
    out.pdf = pdf; out.f = sScale(sScale(fS, pdfp) + fOthers, 1 / pdf);
+}
+// sampleBsdf' flags (Reflection.hs:271-272,278-316), adj = False, for the SPECULAR component filters of the direct-lighting
+// integrator (DirectLighting.hs:50-52: [Specular, Reflection] and [Specular, Transmission]). bxdfMatches b flags =
+// (type b .&. flags) == type b (:119-121,185-186); every material in scope has at most ONE component per such filter,
+// so the sample is that component's: pdf' / 1, f * 1.
+template <class M = AnyMat>
+HD void sampleBsdfSpecular(const Bsdf &bsdf, int flags, V3 woW, BsdfSample &out) {
+   out.type = BX_REFLECTION | BX_DIFFUSE; out.pdf = 0; out.f = sConst(0); out.wi = mk3(0, 1, 0);
+   int pick = -1;
+   BL_UNROLL for (int i = 0; i < 2; ++i) if (i < bsdf.n && pick < 0 && (bsdf.bx[i].type & flags) == bsdf.bx[i].type) pick = i;
+   if (pick < 0) return;
+   const BxDF &bx = bsdf.bx[pick];
+   V3 wo = worldToLocal(bsdf.cs, woW);
+   Spec fS; V3 wi = mk3(0, 1, 0); float pdfp = 0;
+   bxdfSampleOf<M>(bx, wo, 0.5f, 0.5f, fS, wi, pdfp);
+   V3 wiW = localToWorld(bsdf.cs, wi);
+   float sideTest = dot3(wiW, bsdf.ng) / dot3(woW, bsdf.ng);
+   if (pdfp == 0 || sideTest == 0) return;
+   if (!bxMatch(bx, sideTest < 0)) return;
+   out.type = bx.type; out.wi = wiW; out.pdf = pdfp; out.f = fS;
 }
 // Reflection.hs:318-332, adj = False
 template <class M = AnyMat>
@@ -400,7 +433,7 @@ HD Spec evalBsdf(const Bsdf &bsdf, V3 woW, V3 wiW) {
    bool wantTrans = sideTest < 0;
    V3 wo = worldToLocal(bsdf.cs, woW), wi = worldToLocal(bsdf.cs, wiW);
    Spec f = sConst(0);
-   BL_UNROLL for (int i = 0; i < M::NC; ++i) if (i < bsdf.n && bxMatch(bsdf.bx[i], wantTrans)) f = f + bxdfEval<M>(bsdf.bx[i], wi, wo);
+   BL_UNROLL for (int i = 0; i < M::NC; ++i) if (i < bsdf.n && bxMatch(bsdf.bx[i], wantTrans)) f = f + bxdfEvalOf<M>(bsdf.bx[i], wi, wo);
    return f;
 }
 template <class M = AnyMat>
@@ -408,7 +441,7 @@ HD float bsdfPdf(const Bsdf &bsdf, V3 woW, V3 wiW) {   // Reflection.hs:251-257 
    if (M::KM == 0u || bsdf.n == 0) return 0;
    V3 wo = worldToLocal(bsdf.cs, woW), wi = worldToLocal(bsdf.cs, wiW);
    float s = 0;
-   BL_UNROLL for (int i = 0; i < M::NC; ++i) if (i < bsdf.n) s = s + bxdfPdf<M>(bsdf.bx[i], wo, wi);
+   BL_UNROLL for (int i = 0; i < M::NC; ++i) if (i < bsdf.n) s = s + bxdfPdfOf<M>(bsdf.bx[i], wo, wi);
    return s / (float)bsdf.n;
 }
 
@@ -721,6 +754,24 @@ HD float lightPdf(const DScene &sc, const blingcu_light &l, V3 p, V3 wiW) {   //
    }
    return 0;
 }
+
+// ------------------------------------------------------------------------------------------ out-of-line general versions
+// The general (any material kind) shade kernels -- textured queue, direct-lighting integrator -- inline every BxDF with its
+// 16-band arithmetic at each call site: ~700 KB of code, and ncu shows them starved by instruction fetch
+// (stall no_instruction 47 warps per issue, profiles/r01_texshade.md). They call these shared copies instead; the
+// per-kind kernels (M::TX == false) keep the inlined, specialised code.
+HDNI void sampleBsdfGeneral(const Bsdf &b, V3 wo, float uc, float u1, float u2, BsdfSample &o) { sampleBsdf<GenMat>(b, wo, uc, u1, u2, o); }
+HDNI void sampleBsdfSpecularGeneral(const Bsdf &b, int flags, V3 wo, BsdfSample &o) { sampleBsdfSpecular<GenMat>(b, flags, wo, o); }
+HDNI void evalBsdfGeneral(const Bsdf &b, V3 wo, V3 wi, Spec &f) { f = evalBsdf<GenMat>(b, wo, wi); }
+HDNI float bsdfPdfGeneral(const Bsdf &b, V3 wo, V3 wi) { return bsdfPdf<GenMat>(b, wo, wi); }
+HDNI void lightSampleGeneral(const DScene &sc, const blingcu_light &l, V3 p, float eps, V3 n, float u1, float u2, LightSample &o) { lightSample(sc, l, p, eps, n, u1, u2, o); }
+HDNI void makeBsdfGeneral(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b, Spec *scratch) { makeBsdf<MatOf<BLINGCU_MAT_KINDS> >(sc, sh, dgs, b, scratch); }
+// dispatchers: M::TX is a compile-time constant
+template <class M> HD void sampleBsdfOf(const Bsdf &b, V3 wo, float uc, float u1, float u2, BsdfSample &o) { if (M::TX) sampleBsdfGeneral(b, wo, uc, u1, u2, o); else sampleBsdf<M>(b, wo, uc, u1, u2, o); }
+template <class M> HD Spec evalBsdfOf(const Bsdf &b, V3 wo, V3 wi) { if (M::TX) { Spec f; evalBsdfGeneral(b, wo, wi, f); return f; } return evalBsdf<M>(b, wo, wi); }
+template <class M> HD float bsdfPdfOf(const Bsdf &b, V3 wo, V3 wi) { if (M::TX) return bsdfPdfGeneral(b, wo, wi); return bsdfPdf<M>(b, wo, wi); }
+template <class M> HD void lightSampleOf(const DScene &sc, const blingcu_light &l, V3 p, float eps, V3 n, float u1, float u2, LightSample &o) { if (M::TX) lightSampleGeneral(sc, l, p, eps, n, u1, u2, o); else lightSample(sc, l, p, eps, n, u1, u2, o); }
+template <class M> HD void makeBsdfOf(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b, Spec *scratch) { if (M::TX) makeBsdfGeneral(sc, sh, dgs, b, scratch); else makeBsdf<M>(sc, sh, dgs, b, scratch); }
 
 // ------------------------------------------------------------------------------------------ camera (Camera.hs:49-76)
 HD Ray fireRay(const blingcu_camera &c, float ix, float iy, float lu, float lv) {

@@ -22,6 +22,7 @@ LIGHT_INFINITE, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_AREA = range(4)
 ENV_CONSTANT, ENV_RGBTABLE, ENV_SUNSKY = range(3)
 CAM_PERSPECTIVE, CAM_ENVIRONMENT = range(2)
 SAMPLER_STRATIFIED, SAMPLER_RANDOM = range(2)
+INTEGRATOR_PATH, INTEGRATOR_DIRECT = range(2)
 
 f32 = C.c_float
 i32 = C.c_int32
@@ -89,7 +90,7 @@ class SceneC(C.Structure):
                 ("width", i32), ("height", i32), ("filter_w", f32), ("filter_h", f32), ("filter_table", f32 * 256),
                 ("sampler_kind", i32), ("nu", i32), ("nv", i32), ("max_depth", i32), ("sample_depth", i32),
                 ("cie_x", Spectrum), ("cie_y", Spectrum), ("cie_z", Spectrum), ("cie_y_sum", f32),
-                ("illum_basis", Spectrum * 7)]
+                ("illum_basis", Spectrum * 7), ("integrator_kind", i32)]
 
 
 class Ray(C.Structure):
@@ -173,6 +174,7 @@ class SceneIR:
     nv: int = 2
     max_depth: int = 7
     sample_depth: int = 3
+    integrator_kind: int = INTEGRATOR_PATH
     cie_x: np.ndarray = field(default_factory=lambda: np.zeros(16, np.float32))
     cie_y: np.ndarray = field(default_factory=lambda: np.zeros(16, np.float32))
     cie_z: np.ndarray = field(default_factory=lambda: np.zeros(16, np.float32))
@@ -244,6 +246,7 @@ class SceneIR:
         set_arr(sc.filter_table, self.filter_table)
         sc.sampler_kind, sc.nu, sc.nv = self.sampler_kind, self.nu, self.nv
         sc.max_depth, sc.sample_depth = self.max_depth, self.sample_depth
+        sc.integrator_kind = self.integrator_kind
         set_arr(sc.cie_x.v, self.cie_x); set_arr(sc.cie_y.v, self.cie_y); set_arr(sc.cie_z.v, self.cie_z)
         sc.cie_y_sum = self.cie_y_sum
         for i in range(7):
@@ -290,6 +293,7 @@ class SceneIR:
         d["illum_basis"] = np.asarray(self.illum_basis, np.float32)
         d["name"] = np.frombuffer(self.name.encode(), np.uint8)
         d["abi"] = np.array([2], np.int32)
+        d["integrator_kind"] = np.array([self.integrator_kind], np.int32)
         np.savez_compressed(path, **d)
 
     @staticmethod
@@ -333,4 +337,5 @@ class SceneIR:
         ir.cie_x, ir.cie_y, ir.cie_z = z["cie"][0], z["cie"][1], z["cie"][2]
         ir.illum_basis = z["illum_basis"]
         ir.name = z["name"].tobytes().decode()
+        if "integrator_kind" in z: ir.integrator_kind = int(z["integrator_kind"][0])
         return ir

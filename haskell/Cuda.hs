@@ -33,6 +33,8 @@ foreign import ccall safe "blingcu_render_slice"  c_render_slice :: Ptr Ctx -> W
 foreign import ccall safe "blingcu_read_film"     c_read_film    :: Ptr Ctx -> Ptr CFloat -> IO CInt
 foreign import ccall safe "blingcu_trace_nearest" c_trace_nearest :: Ptr Ctx -> Ptr CFloat -> CSize -> Ptr CFloat -> IO CInt
 foreign import ccall safe "blingcu_get_stats"     c_get_stats    :: Ptr Ctx -> Ptr Word64 -> IO CInt
+-- parity hook: a texture-table entry at explicit (dgP, (dgU, dgV)) points, to hold against the Haskell `Texture a` closure
+foreign import ccall safe "blingcu_eval_texture"  c_eval_texture :: Ptr Ctx -> Int32 -> Ptr CFloat -> Ptr CFloat -> CSize -> Ptr CFloat -> IO CInt
 
 -- | `renderer { cuda device 0 seed 42 }` in a .bling file (IO/RendererParser.hs:26-51 gains one case)
 data CudaRenderer = CR { crDevice :: Int, crSeed :: Word64 }

@@ -108,6 +108,8 @@ enum {
 
 enum { BLINGCU_CAM_PERSPECTIVE = 0, BLINGCU_CAM_ENVIRONMENT = 1 };
 enum { BLINGCU_SAMPLER_STRATIFIED = 0, BLINGCU_SAMPLER_RANDOM = 1 };
+/* Integrator/Path.hs:30-39 (max_depth, sample_depth) and, SURVEY §8(f)4, Integrator/DirectLighting.hs:13-21 (max_depth) */
+enum { BLINGCU_INTEGRATOR_PATH = 0, BLINGCU_INTEGRATOR_DIRECT = 1 };
 
 typedef struct blingcu_spectrum { float v[BLINGCU_BANDS]; } blingcu_spectrum;
 
@@ -223,6 +225,8 @@ typedef struct blingcu_scene {
    blingcu_spectrum cie_x, cie_y, cie_z;
    float cie_y_sum;
    blingcu_spectrum illum_basis[7];
+
+   int32_t integrator_kind; /* BLINGCU_INTEGRATOR_*; 0 (path) keeps every older caller's meaning */
 } blingcu_scene;
 
 typedef struct blingcu_ray { float o[3]; float tmin; float d[3]; float tmax; } blingcu_ray;

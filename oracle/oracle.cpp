@@ -27,6 +27,7 @@ struct Scene {
    float fw, fh;
    float ftbl[256];
    int samplerKind, nu, nv, maxDepth, sampleDepth;
+   int integrator = BLINGCU_INTEGRATOR_PATH;
    bool useKd = true;
    // film
    std::vector<float> film;  // H*W*4
@@ -365,6 +366,42 @@ static Spec pathLi(const Scene &sc, const SampleCtx &smp, Ray ray, RayCounters &
    }
 }
 
+// ----------------------------------------------------------------------------- Integrator/DirectLighting.hs:23-58
+static Spec directLighting(const Scene &sc, const SampleCtx &smp, int d, const Ray &r, RayCounters &rc);
+static Spec dlCont(const Scene &sc, const SampleCtx &smp, float e, int d, const Bsdf &bsdf, V3 wo, int t, RayCounters &rc) {   // :47-58
+   if (d == sc.maxDepth) return sConst(0);
+   BsdfSample bs = sampleBsdfFlags(bsdf, t, wo, 0.5f, 0.5f, 0.5f);
+   if (bs.pdf == 0) return sConst(0);
+   Ray ray{bsdf.p, bs.wi, e, kInf};
+   rc.ext++;
+   Spec l = directLighting(sc, smp, d, ray, rc);
+   return bs.f * l;
+}
+static Spec directLighting(const Scene &sc, const SampleCtx &smp, int d, const Ray &r, RayCounters &rc) {   // :25-45
+   Hit hit = sceneIntersect(sc, r);
+   if (!hit.valid) return sConst(0);   // maybe (return black)
+   float uln = rnd1D(smp, 0 + 2 * d);
+   float uld1, uld2; rnd2D(smp, 0 + 2 * d, uld1, uld2);
+   float ubc = rnd1D(smp, 1 + 2 * d);
+   float ubd1, ubd2; rnd2D(smp, 1 + 2 * d, ubd1, ubd2);
+   Bsdf bsdf = makeBsdf(sc, hit);
+   V3 p = bsdf.p, n = bsdf.cs.n, wo = -r.d;
+   float e = hit.eps;
+   Spec l = sConst(0);   // sampleOneLight (Scene.hs:110-118)
+   int lc = (int)sc.lights.size();
+   if (lc > 0) {
+      int ln = (lc == 1) ? 0 : std::min((int)std::floor(uln * (float)lc), lc - 1);
+      const blingcu_light &lt = sc.lights[ln];
+      Spec ls = sampleLightMis(sc, lightSample(sc, lt, p, e, n, uld1, uld2), bsdf, wo, rc);
+      Spec bs = sampleBsdfMis(sc, ln, sampleBsdf(bsdf, wo, ubc, ubd1, ubd2), p, e, rc);
+      l = ls + bs;
+      if (lc > 1) l = sScale(l, (float)lc);
+   }
+   Spec re = dlCont(sc, smp, e, d + 1, bsdf, wo, BX_SPECULAR | BX_REFLECTION, rc);
+   Spec tr = dlCont(sc, smp, e, d + 1, bsdf, wo, BX_SPECULAR | BX_TRANSMISSION, rc);
+   return ((l + re) + tr) + intLe(sc, hit, wo);
+}
+
 // ----------------------------------------------------------------------------- film (Image.hs)
 struct Window { int x0, x1, y0, y1; };  // inclusive (Sampling.hs:36-41)
 static Window sampleExtent(const Scene &sc) {  // Image.hs:162-168
@@ -421,7 +458,8 @@ static SampleCtx mkSampleCtx(const Scene &sc, const Window &ext, uint64_t seed, 
    uint32_t pix = (uint32_t)(iy - ext.y0) * ew + (uint32_t)(ix - ext.x0);
    SampleCtx c;
    c.kp = pixelKey(seed, pass, pix); c.s = s; c.nu = sc.nu; c.nv = sc.nv;
-   c.n1d = 4 * sc.sampleDepth; c.n2d = 3 * sc.sampleDepth;
+   if (sc.integrator == BLINGCU_INTEGRATOR_DIRECT) { c.n1d = 2 * sc.maxDepth; c.n2d = 2 * sc.maxDepth; }   // DirectLighting.hs:18-19
+   else { c.n1d = 4 * sc.sampleDepth; c.n2d = 3 * sc.sampleDepth; }
    c.stratified = sc.samplerKind == BLINGCU_SAMPLER_STRATIFIED;
    return c;
 }
@@ -432,6 +470,7 @@ static Spec renderSample(const Scene &sc, const Window &ext, uint64_t seed, uint
    float ox, oy, lu, lv; cameraSample(c, ox, oy, lu, lv);
    sx = (float)ix + ox; sy = (float)iy + oy;
    Ray r = fireRay(sc, sx, sy, lu, lv);
+   if (sc.integrator == BLINGCU_INTEGRATOR_DIRECT) { rc.cam++; return directLighting(sc, c, 0, r, rc); }
    return pathLi(sc, c, r, rc);
 }
 
@@ -495,7 +534,7 @@ int oracle_create(const blingcu_scene *ir, int build_kdtree, oracle_ctx **out) {
    sc.W = ir->width; sc.H = ir->height; sc.fw = ir->filter_w; sc.fh = ir->filter_h;
    std::memcpy(sc.ftbl, ir->filter_table, sizeof(sc.ftbl));
    sc.samplerKind = ir->sampler_kind; sc.nu = ir->nu; sc.nv = ir->nv;
-   sc.maxDepth = ir->max_depth; sc.sampleDepth = ir->sample_depth;
+   sc.maxDepth = ir->max_depth; sc.sampleDepth = ir->sample_depth; sc.integrator = ir->integrator_kind;
    sc.film.assign((size_t)sc.W * sc.H * 4, 0.0f);
    sc.useKd = build_kdtree != 0;
    if (sc.useKd) sc.geo.buildKd();

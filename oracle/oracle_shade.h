@@ -404,6 +404,36 @@ static inline BsdfSample sampleBsdf(const Bsdf &bsdf, V3 woW, float uComp, float
    Spec fSum = sScale(sScale(fSample, pdfp) + fOthers, 1 / pdf);
    return BsdfSample{bx.type, pdf, fSum, wiW};
 }
+// Reflection.hs:278-316 with adj = False and a component filter: bsm = filter (`bxdfMatches` flags) bs, where
+// bxdfMatches b flags = (type b .&. flags) == type b (:119-121,185-186). DirectLighting.hs:50-52 calls it with
+// [Specular, Reflection] and [Specular, Transmission].
+static inline BsdfSample sampleBsdfFlags(const Bsdf &bsdf, int flags, V3 woW, float uComp, float uDir1, float uDir2) {
+   BsdfSample empty{BX_REFLECTION | BX_DIFFUSE, 0, sConst(0), mk(0, 1, 0)};
+   const BxDF *bsm[2]; int cntm = 0;
+   for (int i = 0; i < bsdf.n; ++i) if ((bsdf.bx[i].type & flags) == bsdf.bx[i].type) bsm[cntm++] = &bsdf.bx[i];
+   if (cntm == 0) return empty;
+   V3 wo = worldToLocal(bsdf.cs, woW);
+   float cntf = (float)cntm, invCnt = 1 / cntf;
+   int sNum = std::max(0, std::min(cntm - 1, (int)std::floor(uComp * cntf)));
+   const BxDF &bx = *bsm[sNum];
+   Spec fSample = sConst(0); V3 wi = mk(0, 1, 0); float pdfp = 0;
+   bxdfSample(bx, wo, uDir1, uDir2, fSample, wi, pdfp);
+   V3 wiW = localToWorld(bsdf.cs, wi);
+   float sideTest = dot(wiW, bsdf.ng) / dot(woW, bsdf.ng);
+   if (pdfp == 0 || sideTest == 0) return empty;
+   bool wantTrans = sideTest < 0;
+   if (!(wantTrans ? isTrans(bx) : isRefl(bx))) return empty;
+   if (isSpec(bx)) return BsdfSample{bx.type, pdfp * invCnt, sScale(fSample, cntf), wiW};
+   if (cntm == 1) return BsdfSample{bx.type, pdfp, fSample, wiW};
+   float pdfSum = 0; Spec fOthers = sConst(0);
+   for (int i = 0; i < cntm; ++i) {
+      if (i == sNum) continue;
+      pdfSum = pdfSum + bxdfPdf(*bsm[i], wo, wi);
+      if (wantTrans ? isTrans(*bsm[i]) : isRefl(*bsm[i])) fOthers = fOthers + bxdfEval(*bsm[i], wi, wo);
+   }
+   float pdf = (pdfp + pdfSum) * invCnt;
+   return BsdfSample{bx.type, pdf, sScale(sScale(fSample, pdfp) + fOthers, 1 / pdf), wiW};
+}
 // Reflection.hs:318-332 with adj = False
 static inline Spec evalBsdf(const Bsdf &bsdf, V3 woW, V3 wiW) {
    float cosWo = dot(woW, bsdf.ng);

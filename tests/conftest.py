@@ -14,7 +14,7 @@ from bling_b200.host.loader import resized  # noqa: E402
 SCENES = ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"]      # BASELINE.json configs[0..3]
 # this repository's own coverage scenes (tests/golden/scenes_src/*.bling): every shape / material / light / camera /
 # sampler kind of SURVEY.md §8a that the config scenes do not reach
-COVERAGE = ["zoo", "envcam", "smooth", "extras", "textures"]
+COVERAGE = ["zoo", "envcam", "smooth", "extras", "textures", "direct", "blackbody-emission"]
 ALL_SCENES = SCENES + COVERAGE
 
 

@@ -35,7 +35,12 @@ CONFIGS = {
                     fixups=[(r"graphPaper 0.05", "graphPaper 0.05 map { uv 10 10 0 0 }")]),
     # cfg 4b: the HDR is a missing blob -> synthetic 1024x512 map; the SPPM renderer precedes the sampler one, fine
     "environment": dict(file="environment.bling", image_size=(1920, 1080), env_files={"*": synthetic_hdr()}),
+    # the one example that selects the direct-lighting integrator; parses as shipped (15 blackbody emitters)
+    "blackbody-emission": dict(file="blackbody-emission.bling"),
 }
+
+# this repository's own coverage scenes (tests/golden/scenes_src/*.bling), flattened by the same loader
+OWN = ["zoo", "envcam", "smooth", "extras", "textures", "direct"]
 
 
 def main():
@@ -49,5 +54,14 @@ def main():
               f"depth {ir.max_depth}/{ir.sample_depth}, extent {ir.sample_extent()}")
 
 
+def own():
+    src = ROOT / "tests" / "golden" / "scenes_src"
+    for name in OWN:
+        ir = load_scene(src / f"{name}.bling", name=name)
+        ir.save(OUT / f"{name}.npz")
+        print(f"{name}: {ir.n_prims} prims, {len(ir.lights)} lights, {len(ir.materials)} materials, {len(ir.textures)} textures")
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["own"]: own()
+    else: main()

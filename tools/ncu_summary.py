@@ -26,6 +26,8 @@ METRICS = [
     ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall branch_resolving"),
     ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected"),
     ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall math_pipe_throttle"),
+    ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall no_instruction (instruction fetch)"),
+    ("smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio", "stall imc_miss (constant cache)"),
 ]
 
 

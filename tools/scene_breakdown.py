@@ -1,14 +1,20 @@
 #!/usr/bin/env python
-"""Per-kernel-class device time of one timed slice of each named scene (BASELINE.json configs[0..3]) at config size."""
+"""Per-kernel-class device time of one timed slice of each named scene (BASELINE.json configs[0..3]) at config size.
+A name may carry a size, e.g. `textures@1920x1080x8` = that fixture at 1920x1080 with an 8x8 stratified sampler."""
 import sys
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 from bling_b200 import api, ir as IR
+from bling_b200.host.loader import resized
 
 names = sys.argv[1:] or ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"]
 for name in names:
+    name, _, size = name.partition("@")
     sc = IR.SceneIR.load(ROOT / "tests" / "golden" / "scenes" / f"{name}.npz")
+    if size:
+        w, h, n = (int(x) for x in size.split("x"))
+        sc = resized(sc, w, h, n, n)
     c = api.Context(0); c.upload_scene(sc)
     ex = c.sample_extent(); npx = (ex[1] - ex[0] + 1) * (ex[3] - ex[2] + 1)
     k = max(1, min(sc.spp // 2, int(48e6 // npx)))
