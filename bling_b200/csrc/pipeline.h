@@ -187,6 +187,15 @@ struct Pipeline {
          }
          hs.envs = up<blingcu_envmap>(envs.data(), envs.size());
       }
+      {
+         std::vector<blingcu_image> imgs(ir->n_images ? ir->images : nullptr, ir->n_images ? ir->images + ir->n_images : nullptr);
+         for (blingcu_image &im : imgs) {
+            if (im.width <= 0 || im.height <= 0 || im.channels <= 0 || !im.data) return fail(BLINGCU_EINVAL, "empty image");
+            im.data = up<float>(im.data, (size_t)im.width * im.height * im.channels);
+         }
+         hs.images = up<blingcu_image>(imgs.data(), imgs.size());
+         for (int b = 0; b < 7; ++b) for (int i = 0; i < NB; ++i) hs.refl[b][i] = ir->refl_basis[b].v[i];
+      }
       hs.ftbl = up<float>(ir->filter_table, 256);
       hs.cam = ir->camera;
       hs.W = ir->width; hs.H = ir->height; hs.fw = ir->filter_w; hs.fh = ir->filter_h;
@@ -278,12 +287,12 @@ struct Pipeline {
    static int matTexCount(int kind) {
       return (kind == BLINGCU_MAT_MATTE || kind == BLINGCU_MAT_MIRROR) ? 1 : (kind == BLINGCU_MAT_BLACKBODY ? 0 : (kind == BLINGCU_MAT_SHINYMETAL ? 4 : (kind == BLINGCU_MAT_SUBSTRATE ? 3 : 2)));
    }
-   static bool isScalarKind(int k) { return k >= BLINGCU_STEX_CONSTANT && k <= BLINGCU_STEX_CRYSTAL; }
+   static bool isScalarKind(int k) { return k >= BLINGCU_STEX_CONSTANT && k <= BLINGCU_STEX_IMAGE; }
    // nesting depth of blends below spectrum texture `id` (-1: malformed); selecting kinds do not count
    static int blendDepth(const blingcu_scene *ir, int id, int guard) {
       if (guard > 32 || id < 0 || (uint32_t)id >= ir->n_textures) return -1;
       const blingcu_texture &t = ir->textures[id];
-      if (t.kind == BLINGCU_TEX_CONSTANT || t.kind == BLINGCU_TEX_GRADIENT) return 0;
+      if (t.kind == BLINGCU_TEX_CONSTANT || t.kind == BLINGCU_TEX_GRADIENT || t.kind == BLINGCU_TEX_IMAGE) return 0;
       if (t.kind == BLINGCU_TEX_GRAPHPAPER || t.kind == BLINGCU_TEX_CHECKER || t.kind == BLINGCU_TEX_BLEND) {
          int a = blendDepth(ir, t.child[0], guard + 1), b = blendDepth(ir, t.child[1], guard + 1);
          if (a < 0 || b < 0) return -1;
@@ -294,7 +303,7 @@ struct Pipeline {
    static bool spectrumComputes(const blingcu_scene *ir, int id, int guard) {
       if (guard > 32) return true;
       const blingcu_texture &t = ir->textures[id];
-      if (t.kind == BLINGCU_TEX_BLEND || t.kind == BLINGCU_TEX_GRADIENT) return true;
+      if (t.kind == BLINGCU_TEX_BLEND || t.kind == BLINGCU_TEX_GRADIENT || t.kind == BLINGCU_TEX_IMAGE) return true;
       if (t.kind == BLINGCU_TEX_GRAPHPAPER || t.kind == BLINGCU_TEX_CHECKER) return spectrumComputes(ir, t.child[0], guard + 1) || spectrumComputes(ir, t.child[1], guard + 1);
       return false;
    }
@@ -334,6 +343,13 @@ struct Pipeline {
          case BLINGCU_STEX_CELLNOISE:
             if (t.aux < 0 || t.aux > 3) return fail(BLINGCU_EINVAL, "unknown cell-noise distance");
             break;
+         case BLINGCU_TEX_IMAGE: case BLINGCU_STEX_IMAGE: {
+            if (t.aux < 0 || (uint32_t)t.aux >= ir->n_images || !ir->images) return fail(BLINGCU_EINVAL, "image out of range");
+            const blingcu_image &im = ir->images[t.aux];
+            if (im.width <= 0 || im.height <= 0 || !im.data) return fail(BLINGCU_EINVAL, "empty image");
+            if (im.channels != (t.kind == BLINGCU_TEX_IMAGE ? 3 : 1)) return fail(BLINGCU_EINVAL, "image texture needs 3 channels, scalar image texture 1");
+            break;
+         }
          default: return fail(BLINGCU_EINVAL, "unknown texture kind");
          }
       }
@@ -359,7 +375,14 @@ struct Pipeline {
       const uint32_t bound = ps.cap;   // a queue may hold spawned slots too
       for (int d = 0; d < hs.max_depth; ++d) {
          be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(qa, ps.counters + C_ACTIVE, bound, dscene, ps.rayO, ps.rayD, ps.hit);
-         be.tag(BLINGCU_KC_SHADE); be.runQueue(DlShadeBody{dscene, ps, qb, n}, qa, ps.counters + C_ACTIVE, bound);
+         // the general shade kernel is instruction-fetch bound: one launch per material kind present keeps the code that is
+         // hot at any one time small (profiles/r01_general_shade.md)
+         be.tag(BLINGCU_KC_CLASSIFY); be.runQueue(ClassifyBody{dscene, ps}, qa, ps.counters + C_ACTIVE, bound);
+         be.tag(BLINGCU_KC_SHADE);
+         for (int k = 1; k < N_SHADE_KINDS; ++k) {
+            if (!kindPresent[k]) continue;
+            be.runQueue(DlShadeBody{dscene, ps, qb, n}, ps.qMat + (size_t)k * ps.cap, ps.counters + C_MAT0 + k, bound); launches++;
+         }
          be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl);
          launches += 3;
          if (hasInfinite && !hasBox) { be.traceAny(ps.qMisAny, ps.counters + C_MISANY, bound, dscene, ps.miO, ps.miD, ps.occlM); launches++; }

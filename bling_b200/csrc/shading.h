@@ -33,6 +33,8 @@ struct DScene {
    SamplerConst smp;           // per-scene sampler constants (hd.h)
    float cieX[NB], cieY[NB], cieZ[NB], ySum;
    float illum[7][NB];         // r g b c m y w
+   const blingcu_image *images;   // image textures (data pointers are device pointers)
+   float refl[7][NB];          // reflectance basis r g b c m y w (rgbToSpectrumRefl), image textures only
    uint8_t perm[256];          // noisePerms (Texture.hs:400-414), filled by upload; read by textures.h only
 };
 
@@ -595,8 +597,8 @@ HD void makeBsdf(const DScene &sc, const SurfaceHit &sh, const DG &dgsIn, Bsdf &
 }
 
 // ------------------------------------------------------------------------------------------ spectra conversions
-HD Spec rgbToSpectrumIllum(const DScene &sc, float r, float g, float b) {   // Spectrum.hs:146-159
-   const float *rb = sc.illum[0], *gb = sc.illum[1], *bb = sc.illum[2], *cb = sc.illum[3], *mb = sc.illum[4], *yb = sc.illum[5], *wb = sc.illum[6];
+HD Spec rgbToSpectrumBasis(const float (*basis)[NB], float r, float g, float b) {   // rgbToSpectrum (Spectrum.hs:146-159)
+   const float *rb = basis[0], *gb = basis[1], *bb = basis[2], *cb = basis[3], *mb = basis[4], *yb = basis[5], *wb = basis[6];
    const float *A, *B; float w, fa, fb;
    if (r <= g && r <= b) { w = r; if (g <= b) { A = cb; fa = g - r; B = bb; fb = b - g; } else { A = cb; fa = b - r; B = gb; fb = g - b; } }
    else if (g <= r && g <= b) { w = g; if (r <= b) { A = mb; fa = r - g; B = bb; fb = b - r; } else { A = mb; fa = b - g; B = rb; fb = r - b; } }
@@ -604,6 +606,7 @@ HD Spec rgbToSpectrumIllum(const DScene &sc, float r, float g, float b) {   // S
    Spec s; BL_UNROLL for (int i = 0; i < NB; ++i) s.v[i] = wb[i] * w + (A[i] * fa + B[i] * fb);
    return s;
 }
+HD Spec rgbToSpectrumIllum(const DScene &sc, float r, float g, float b) { return rgbToSpectrumBasis(sc.illum, r, g, b); }
 HD void spectrumToXYZ(const DScene &sc, const Spec &s, float &X, float &Y, float &Z) {   // Spectrum.hs:349-355
    float a = 0, b = 0, c = 0;
    BL_UNROLL for (int i = 0; i < NB; ++i) { a = a + sc.cieX[i] * s.v[i]; b = b + sc.cieY[i] * s.v[i]; c = c + sc.cieZ[i] * s.v[i]; }

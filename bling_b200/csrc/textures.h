@@ -98,6 +98,16 @@ HD float quasiCrystal(int octaves, float x, float y) {
    return (k & 1) ? 1 - v : v;
 }
 
+// ------------------------------------------------------------------------------------------ image lookups (:82-108)
+HD Spec rgbToSpectrumBasis(const float (*basis)[NB], float r, float g, float b);   // shading.h
+// mod' a b (:91-94): a - (a `div` b) * b, plus b when negative -- i.e. the mathematical modulus for b > 0
+HD int imageMod(float x, int b) { long long a = (long long)x, m = a % (long long)b; return (int)(m < 0 ? m + b : m); }
+// getPixel / getPixelScalar: px = mod' (floor (u * w)) w, py = mod' (floor (-v * h)) h, pixelAt i px py
+HD const float *imagePixel(const blingcu_image &im, float u, float v) {
+   int px = imageMod(floorf(u * (float)im.width), im.width), py = imageMod(floorf((-v) * (float)im.height), im.height);
+   return im.data + ((size_t)py * (size_t)im.width + (size_t)px) * (size_t)im.channels;
+}
+
 // ------------------------------------------------------------------------------------------ scalar textures
 // (out of line: called from many sites of the textured shade kernel)
 HDNI float evalScalarTexture(const DScene &sc, int id, const DG &dg) {
@@ -111,6 +121,7 @@ HDNI float evalScalarTexture(const DScene &sc, int id, const DG &dg) {
    case BLINGCU_STEX_FBM: v = fbm3d(sc.perm, t.aux, t.f[0], map3d(t.s.v, dg)); break;
    case BLINGCU_STEX_CELLNOISE: v = cellNoise(t.aux, map3d(t.s.v, dg)); break;
    case BLINGCU_STEX_CRYSTAL: { float x, y; map2d(t.s.v, dg, x, y); v = quasiCrystal(t.aux, x, y); break; }
+   case BLINGCU_STEX_IMAGE: { float x, y; map2d(t.s.v, dg, x, y); v = imagePixel(sc.images[t.aux], x, y)[0]; break; }
    default: break;
    }
    for (int k = n - 1; k >= 0; --k) v = as[k] + ss[k] * v;   // scaleTexture a s t = a + s * t
@@ -135,6 +146,11 @@ HD int selectSpectrumTexture(const DScene &sc, int id, const DG &dg) {
    }
    return id;
 }
+HD Spec imageSpectrum(const DScene &sc, const blingcu_texture &t, const DG &dg) {   // pixelSpectrum (:87-89); unGamma on the host
+   float x, y; map2d(t.s.v, dg, x, y);
+   const float *px = imagePixel(sc.images[t.aux], x, y);
+   return rgbToSpectrumBasis(sc.refl, px[0], px[1], px[2]);
+}
 template <int D> struct SpectrumValue {
    static HDNI Spec eval(const DScene &sc, int id, const DG &dg) {
       id = selectSpectrumTexture(sc, id, dg);
@@ -155,11 +171,16 @@ template <int D> struct SpectrumValue {
          float w = (f - st[idx - 1].f[0]) / (st[idx].f[0] - st[idx - 1].f[0]);
          return sScale(loadSpec(st[idx - 1].s.v), 1 - w) + sScale(loadSpec(st[idx].s.v), w);
       }
+      if (t.kind == BLINGCU_TEX_IMAGE) return imageSpectrum(sc, t, dg);
       return loadSpec(t.s.v);
    }
 };
 template <> struct SpectrumValue<0> {   // deepest level: upload rejects blends nested further
-   static HD Spec eval(const DScene &sc, int id, const DG &dg) { return loadSpec(sc.textures[selectSpectrumTexture(sc, id, dg)].s.v); }
+   static HD Spec eval(const DScene &sc, int id, const DG &dg) {
+      const blingcu_texture &t = sc.textures[selectSpectrumTexture(sc, id, dg)];
+      if (t.kind == BLINGCU_TEX_IMAGE) return imageSpectrum(sc, t, dg);
+      return loadSpec(t.s.v);
+   }
 };
 enum { BL_BLEND_DEPTH = 2 };
 

@@ -141,10 +141,12 @@ class PState:                    # ParserCore.hs:45-58
 
 
 class Loader:
-    def __init__(self, base: Path, env_files: Optional[dict] = None):
+    def __init__(self, base: Path, env_files: Optional[dict] = None, image_files: Optional[dict] = None):
         self.st = PState(base=base)
         self.ir = IR.SceneIR()
         self.env_files = env_files or {}
+        self.image_files = image_files or {}      # name -> uint8 array (h, w[, c]) standing in for a file on disk
+        self.image_ids = {}
         # IO/MaterialParser.hs:21-22 defaultMaterial
         self.st.material = self.add_material(IR.MAT_MATTE, [self.const_tex(S.rgb_refl((0.9, 0.9, 0.9)))], [0.0])
         self.st.renderer = dict(kind="sampler", sampler=("stratified", 2, 2), integrator=("path", 7, 3))  # RendererParser.hs:18-24
@@ -226,6 +228,9 @@ class Loader:
         elif tp == "crystal":
             octaves = tk.named_int("octaves")
             tid = self.add_texture(IR.STEX_CRYSTAL, aux=octaves, s=self.p_mapping2d(tk, "map"))
+        elif tp == "image":                  # pImageScalar (:104-111): readImageScalarMap accepts 8-bit greyscale only
+            tk.expect("{"); tk.expect("file"); img = self.load_image(tk.qstring(), 1)
+            tid = self.add_texture(IR.STEX_IMAGE, aux=img, s=self.p_mapping2d(tk, "map")); tk.expect("}")
         elif tp == "scale":
             a, sc = tk.flt(), tk.flt()
             inner = self.scalar_tex_id(self.p_scalar_texture(tk, "tex"))
@@ -234,6 +239,27 @@ class Loader:
             raise NotImplementedError(f"scalar texture {tp} (image textures: SURVEY §8(f)2, not built)")
         tk.expect("}")
         return ("tex", tid)
+
+    def load_image(self, name: str, channels: int) -> int:
+        """decodeImage stays on the host (JuicyPixels in bling, PIL in this stand-in). 3 channels: RGB8 (RGBA8 drops alpha,
+        YCbCr8 is converted) -> (c / 255) ** 2.2, i.e. `unGamma . f` of pixelSpectrum (Texture.hs:87-89); 1 channel: Y8 -> c / 255."""
+        key = (name, channels)
+        if key in self.image_ids: return self.image_ids[key]
+        if name in self.image_files: raw = np.asarray(self.image_files[name])
+        else:
+            from PIL import Image
+            im = Image.open(self.st.base / name)
+            if channels == 1:
+                if im.mode != "L": raise ValueError(f"unsupported image type {im.mode} for a scalar map (readImageScalarMap: Y8 only)")
+            else: im = im.convert("RGB")
+            raw = np.asarray(im)
+        raw = raw.reshape(raw.shape[0], raw.shape[1], -1)[..., :channels]
+        if raw.shape[2] != channels: raise ValueError("image channel count")
+        a = raw.astype(F) / F(255)
+        if channels == 3: a = np.power(a, F(2.2), dtype=F)
+        self.ir.images.append(np.ascontiguousarray(a, F))
+        self.image_ids[key] = len(self.ir.images) - 1
+        return self.image_ids[key]
 
     def scalar_tex_id(self, v) -> int:
         """A scalar-texture table entry for either form p_scalar_texture returns."""
@@ -256,6 +282,9 @@ class Loader:
             t = IR.Texture(); t.kind = IR.TEX_CHECKER; t.child[0] = c0; t.child[1] = c1
             IR.set_arr(t.f, list(sc))
             self.ir.textures.append(t); tid = len(self.ir.textures) - 1
+        elif tp == "image":                  # pImageTexture (:189-196) -> imageTexture over readImageTextureMap
+            tk.expect("{"); tk.expect("file"); img = self.load_image(tk.qstring(), 3)
+            tid = self.add_texture(IR.TEX_IMAGE, aux=img, s=self.p_mapping2d(tk, "map")); tk.expect("}")
         elif tp == "blend":                  # spectrumBlend (Texture.hs:129-141)
             c0 = self.p_spectrum_texture(tk, "tex1"); c1 = self.p_spectrum_texture(tk, "tex2")
             f = self.scalar_tex_id(self.p_scalar_texture(tk, "f"))
@@ -279,7 +308,7 @@ class Loader:
 
     def computes(self, tid: int) -> bool:
         t = self.ir.textures[tid]
-        if t.kind in (IR.TEX_BLEND, IR.TEX_GRADIENT): return True
+        if t.kind in (IR.TEX_BLEND, IR.TEX_GRADIENT, IR.TEX_IMAGE): return True
         if t.kind in (IR.TEX_GRAPHPAPER, IR.TEX_CHECKER): return self.computes(t.child[0]) or self.computes(t.child[1])
         return False
 
@@ -584,6 +613,7 @@ class Loader:
         ir.integrator_kind = IR.INTEGRATOR_DIRECT if integ[0] == "directLighting" else IR.INTEGRATOR_PATH
         ir.cie_x, ir.cie_y, ir.cie_z, ir.cie_y_sum = S.CIE_X, S.CIE_Y, S.CIE_Z, float(S.CIE_Y_SUM)
         ir.illum_basis = np.stack(S.ILLUM).astype(F)
+        ir.refl_basis = np.stack(S.REFL).astype(F)
         ir.name = name
         return ir
 
@@ -629,7 +659,7 @@ def resized(ir: IR.SceneIR, width: int, height: int, nu: int = None, nv: int = N
 
 
 def load_scene(path, *, fixups=(), image_size=None, sampler=None, integrator=None, filter=None, env_files=None,
-               drop_lines=(), name=None) -> IR.SceneIR:
+               drop_lines=(), name=None, image_files=None) -> IR.SceneIR:
     """Parses a `.bling` file into the IR.
     fixups: (regex, replacement) pairs applied to the text first (documented per config in tools/make_scenes.py).
     drop_lines: 1-based line numbers removed before parsing (e.g. a trailing `renderer { sppm ... }`)."""
@@ -640,7 +670,7 @@ def load_scene(path, *, fixups=(), image_size=None, sampler=None, integrator=Non
     for pat, rep in fixups: text = re.sub(pat, rep, text)
     if image_size is not None:               # must precede `camera {}` which captures the size (CameraParser.hs:30-38)
         text = re.sub(r"^\s*imageSize\s+\d+\s+\d+", f"imageSize {image_size[0]} {image_size[1]}", text, flags=re.M)
-    ld = Loader(path.parent, env_files)
+    ld = Loader(path.parent, env_files, image_files)
     ld.parse(text)
     if sampler is not None: ld.st.renderer["sampler"] = sampler
     if integrator is not None: ld.st.renderer["integrator"] = integrator

@@ -16,8 +16,8 @@ BANDS = 16
 
 SHAPE_BOX, SHAPE_CYLINDER, SHAPE_DISK, SHAPE_QUAD, SHAPE_SPHERE = range(5)
 MAT_MATTE, MAT_GLASS, MAT_MIRROR, MAT_PLASTIC, MAT_METAL, MAT_BLACKBODY, MAT_SHINYMETAL, MAT_TRANSMATTE, MAT_SUBSTRATE = range(9)
-TEX_CONSTANT, TEX_GRAPHPAPER, TEX_CHECKER, TEX_BLEND, TEX_GRADIENT = range(5)
-STEX_CONSTANT, STEX_SCALE, STEX_PERLIN, STEX_FBM, STEX_CELLNOISE, STEX_CRYSTAL = range(16, 22)
+TEX_CONSTANT, TEX_GRAPHPAPER, TEX_CHECKER, TEX_BLEND, TEX_GRADIENT, TEX_IMAGE = range(6)
+STEX_CONSTANT, STEX_SCALE, STEX_PERLIN, STEX_FBM, STEX_CELLNOISE, STEX_CRYSTAL, STEX_IMAGE = range(16, 23)
 LIGHT_INFINITE, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_AREA = range(4)
 ENV_CONSTANT, ENV_RGBTABLE, ENV_SUNSKY = range(3)
 CAM_PERSPECTIVE, CAM_ENVIRONMENT = range(2)
@@ -55,6 +55,10 @@ class MaterialV1(C.Structure):
     _fields_ = [("kind", i32), ("tex", i32 * 3), ("f", f32 * 3), ("tex3", i32)]
 
 
+class ImageC(C.Structure):
+    _fields_ = [("width", i32), ("height", i32), ("channels", i32), ("_pad", i32), ("data", PF)]
+
+
 class Light(C.Structure):
     _fields_ = [("kind", i32), ("shape", i32), ("env", i32), ("_pad", i32), ("v", f32 * 4), ("s", Spectrum)]
 
@@ -90,7 +94,8 @@ class SceneC(C.Structure):
                 ("width", i32), ("height", i32), ("filter_w", f32), ("filter_h", f32), ("filter_table", f32 * 256),
                 ("sampler_kind", i32), ("nu", i32), ("nv", i32), ("max_depth", i32), ("sample_depth", i32),
                 ("cie_x", Spectrum), ("cie_y", Spectrum), ("cie_z", Spectrum), ("cie_y_sum", f32),
-                ("illum_basis", Spectrum * 7), ("integrator_kind", i32)]
+                ("illum_basis", Spectrum * 7), ("integrator_kind", i32),
+                ("n_images", u32), ("images", C.POINTER(ImageC)), ("refl_basis", Spectrum * 7)]
 
 
 class Ray(C.Structure):
@@ -180,6 +185,8 @@ class SceneIR:
     cie_z: np.ndarray = field(default_factory=lambda: np.zeros(16, np.float32))
     cie_y_sum: float = 1.0
     illum_basis: np.ndarray = field(default_factory=lambda: np.zeros((7, 16), np.float32))
+    images: List[np.ndarray] = field(default_factory=list)    # (h, w, 3) or (h, w, 1) float32, see blingcu_image
+    refl_basis: np.ndarray = field(default_factory=lambda: np.zeros((7, 16), np.float32))
     name: str = ""
     cam_fov: float = 0.0   # python-side only: lets host.loader.resized() rebuild raster2cam
 
@@ -251,6 +258,13 @@ class SceneIR:
         sc.cie_y_sum = self.cie_y_sum
         for i in range(7):
             set_arr(sc.illum_basis[i].v, self.illum_basis[i])
+            set_arr(sc.refl_basis[i].v, self.refl_basis[i])
+        imgs = []
+        for a in self.images:
+            a = np.ascontiguousarray(a, np.float32); keep.append(a)
+            im = ImageC(); im.height, im.width, im.channels = a.shape; im.data = _fp(a)
+            imgs.append(im)
+        sc.n_images = len(imgs); sc.images = arr(imgs, ImageC)
         return sc, keep
 
     # ------------------------------------------------------------------ npz
@@ -294,6 +308,8 @@ class SceneIR:
         d["name"] = np.frombuffer(self.name.encode(), np.uint8)
         d["abi"] = np.array([2], np.int32)
         d["integrator_kind"] = np.array([self.integrator_kind], np.int32)
+        d["refl_basis"] = np.asarray(self.refl_basis, np.float32)
+        for i, a in enumerate(self.images): d[f"image{i}"] = np.asarray(a, np.float32)
         np.savez_compressed(path, **d)
 
     @staticmethod
@@ -338,4 +354,7 @@ class SceneIR:
         ir.illum_basis = z["illum_basis"]
         ir.name = z["name"].tobytes().decode()
         if "integrator_kind" in z: ir.integrator_kind = int(z["integrator_kind"][0])
+        if "refl_basis" in z: ir.refl_basis = z["refl_basis"]
+        i = 0
+        while f"image{i}" in z: ir.images.append(z[f"image{i}"]); i += 1
         return ir

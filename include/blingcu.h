@@ -82,6 +82,8 @@ enum {
    BLINGCU_TEX_BLEND = 3,      /* spectrumBlend: child[0]=tex1 child[1]=tex2 aux=scalar texture f                        */
    BLINGCU_TEX_GRADIENT = 4,   /* gradient: aux=scalar texture, child[0]=index of the first step, child[1]=step count; the
                                   steps are consecutive CONSTANT entries sorted by position f[0] (mkGradient sorts)      */
+   BLINGCU_TEX_IMAGE = 5,      /* imageTexture (Texture.hs:96-108,125-126): aux = index into images (3 channels),
+                                  s.v = 2-D mapping; the pixel becomes a spectrum with rgbToSpectrumRefl (refl_basis)    */
    /* scalar textures (MaterialParser.hs:123-154) */
    BLINGCU_STEX_CONSTANT = 16, /* f[0]                                                                                   */
    BLINGCU_STEX_SCALE = 17,    /* scaleTexture a s t = a + s * t: f[0]=a f[1]=s child[0]=t                               */
@@ -89,7 +91,9 @@ enum {
    BLINGCU_STEX_FBM = 19,      /* fbm (Texture.hs:329-339): aux=octaves f[0]=omega, s.v = 3-D mapping                    */
    BLINGCU_STEX_CELLNOISE = 20,/* cellNoise (Texture.hs:255-303): aux = distance (0 euclidian, 1 euclidian2, 2 manhattan,
                                   3 chebyshev), s.v = 3-D mapping                                                        */
-   BLINGCU_STEX_CRYSTAL = 21   /* quasiCrystal (Texture.hs:305-326): aux=octaves, s.v = 2-D mapping                      */
+   BLINGCU_STEX_CRYSTAL = 21,  /* quasiCrystal (Texture.hs:305-326): aux=octaves, s.v = 2-D mapping                      */
+   BLINGCU_STEX_IMAGE = 22     /* imageTexture over readImageScalarMap (Texture.hs:103-108,117-126): aux = index into
+                                  images (1 channel), s.v = 2-D mapping                                                  */
 };
 
 /* Light.hs:31-45 */
@@ -132,6 +136,14 @@ typedef struct blingcu_texture {
    float f[8];
    blingcu_spectrum s;
 } blingcu_texture;
+
+/* A decoded image (IO stays on the host: JuicyPixels in bling). channels == 3: (r, g, b) per pixel AFTER `fromIntegral x / 255`
+ * and `unGamma` (Texture.hs:87-89, Spectrum.hs:118-120); channels == 1: `fromIntegral x / 255` (Texture.hs:103-104).
+ * Row-major, row 0 first, as JuicyPixels' pixelAt i x y. */
+typedef struct blingcu_image {
+   int32_t width, height, channels, _pad;
+   const float *data; /* width * height * channels */
+} blingcu_image;
 
 typedef struct blingcu_material {
    int32_t kind;
@@ -227,6 +239,12 @@ typedef struct blingcu_scene {
    blingcu_spectrum illum_basis[7];
 
    int32_t integrator_kind; /* BLINGCU_INTEGRATOR_*; 0 (path) keeps every older caller's meaning */
+
+   /* image textures: decoded images and the reflectance basis r g b c m y w of rgbToSpectrumRefl
+    * (Spectrum.hs:128-145); both unused (0 / NULL) unless a BLINGCU_TEX_IMAGE / BLINGCU_STEX_IMAGE entry exists */
+   uint32_t n_images;
+   const blingcu_image *images;
+   blingcu_spectrum refl_basis[7];
 } blingcu_scene;
 
 typedef struct blingcu_ray { float o[3]; float tmin; float d[3]; float tmax; } blingcu_ray;

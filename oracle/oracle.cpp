@@ -16,6 +16,10 @@ struct Scene {
    Geometry geo;
    std::vector<blingcu_material> materials;
    std::vector<blingcu_texture> textures;
+   std::vector<blingcu_image> images;             // data pointers into imageData
+   std::vector<std::vector<float>> imageData;
+   Spec refl[7];                                  // rgbReflectance basis (Spectrum.hs:128-133)
+   TexEnv texEnv() const { return TexEnv{textures, images}; }
    std::vector<blingcu_light> lights;
    std::vector<blingcu_envmap> envs;
    std::vector<std::vector<float>> envData;  // owns copies of env arrays
@@ -58,13 +62,13 @@ static Spec evalSpectrumTexture(const Scene &sc, int id, const DG &dg) {
    }
    case BLINGCU_TEX_BLEND: {   // spectrumBlend (Texture.hs:129-141)
       Spec v1 = evalSpectrumTexture(sc, t.child[0], dg), v2 = evalSpectrumTexture(sc, t.child[1], dg);
-      float x = evalScalarTexture(sc.textures, t.aux, dg);
+      float x = evalScalarTexture(sc.texEnv(), t.aux, dg);
       if (x <= 0) return v1;
       if (x >= 1) return v2;
       return sScale(v1, 1 - x) + sScale(v2, x);
    }
    case BLINGCU_TEX_GRADIENT: {   // gradient (Texture.hs:239-253); the IR holds gradCols sorted (mkGradient :232-237)
-      float f = evalScalarTexture(sc.textures, t.aux, dg);
+      float f = evalScalarTexture(sc.texEnv(), t.aux, dg);
       const blingcu_texture *cols = &sc.textures[t.child[0]]; int n = t.child[1];
       float gmin = cols[0].f[0], gmax = cols[n - 1].f[0];
       if (f <= gmin) return fromC(cols[0].s);
@@ -73,6 +77,11 @@ static Spec evalSpectrumTexture(const Scene &sc, int id, const DG &dg) {
       const blingcu_texture &e0 = cols[idx - 1], &e1 = cols[idx];
       float weight = (f - e0.f[0]) / (e1.f[0] - e0.f[0]);
       return sScale(fromC(e0.s), 1 - weight) + sScale(fromC(e1.s), weight);
+   }
+   case BLINGCU_TEX_IMAGE: {   // imageTexture tm mapping dg = texMapEval tm (mapping dg); getPixel + pixelSpectrum (Texture.hs:87-101,125-126)
+      float x, y; mapping2d(t.s.v, dg, x, y);
+      const float *px = imagePixelAt(sc.images[t.aux], x, y);   // already (fromIntegral c / 255) ** 2.2 (unGamma, host side)
+      return rgbToSpectrum(sc.refl, px[0], px[1], px[2]);
    }
    default: return sConst(0);
    }
@@ -110,9 +119,9 @@ static Bsdf makeBsdf(const Scene &sc, const Hit &hit) {
       }
    } else matId = sc.geo.shapes[pr.idx].material;
    const blingcu_material &m0 = sc.materials[matId];
-   if (m0.bump) dgs = bump(sc.textures, m0.bump - 1, hit.dg, dgs);   // bumpMapped d mat dgg dgs = mat dgg $ bump d dgg dgs (Reflection.hs:344-345)
+   if (m0.bump) dgs = bump(sc.texEnv(), m0.bump - 1, hit.dg, dgs);   // bumpMapped d mat dgg dgs = mat dgg $ bump d dgg dgs (Reflection.hs:344-345)
    blingcu_material m = m0;   // ScalarTexture parameters (sigma, ior, rough, ...) are evaluated at the shading geometry
-   for (int i = 0; i < 3; ++i) if (m0.ftex[i]) m.f[i] = evalScalarTexture(sc.textures, m0.ftex[i] - 1, dgs);
+   for (int i = 0; i < 3; ++i) if (m0.ftex[i]) m.f[i] = evalScalarTexture(sc.texEnv(), m0.ftex[i] - 1, dgs);
    Bsdf b; b.n = 0;
    switch (m.kind) {
    case BLINGCU_MAT_MATTE: {
@@ -515,6 +524,13 @@ int oracle_create(const blingcu_scene *ir, int build_kdtree, oracle_ctx **out) {
    }
    sc.materials.assign(ir->materials, ir->materials + ir->n_materials);
    sc.textures.assign(ir->textures, ir->textures + ir->n_textures);
+   for (uint32_t i = 0; i < ir->n_images; ++i) {   // own the pixel data
+      blingcu_image im = ir->images[i];
+      sc.imageData.emplace_back(im.data, im.data + (size_t)im.width * im.height * im.channels);
+      sc.images.push_back(im);
+   }
+   for (size_t i = 0; i < sc.images.size(); ++i) sc.images[i].data = sc.imageData[i].data();
+   for (int b = 0; b < 7; ++b) sc.refl[b] = fromC(ir->refl_basis[b]);
    sc.lights.assign(ir->lights, ir->lights + ir->n_lights);
    sc.envs.assign(ir->envs, ir->envs + ir->n_envs);
    for (blingcu_envmap &e : sc.envs) {  // own the arrays
@@ -646,7 +662,7 @@ int oracle_eval_texture(oracle_ctx *c, int32_t tex, const float *p, const float 
    for (size_t i = 0; i < n; ++i) {
       DG dg = mkDg(mk(p[3 * i], p[3 * i + 1], p[3 * i + 2]), uv[2 * i], uv[2 * i + 1], mk(1, 0, 0), mk(0, 1, 0));
       Spec s = sConst(0);
-      if (c->sc.textures[tex].kind >= BLINGCU_STEX_CONSTANT) s.v[0] = evalScalarTexture(c->sc.textures, tex, dg);
+      if (c->sc.textures[tex].kind >= BLINGCU_STEX_CONSTANT) s.v[0] = evalScalarTexture(c->sc.texEnv(), tex, dg);
       else s = evalSpectrumTexture(c->sc, tex, dg);
       std::memcpy(out + 16 * i, s.v, sizeof(s.v));
    }

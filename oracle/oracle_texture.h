@@ -120,11 +120,27 @@ static inline void mapping2d(const float *m, const DG &dg, float &x, float &y) {
    y = dot(dg.p, mk(m[4], m[5], m[6])) + m[8];
 }
 
-static float evalScalarTexture(const std::vector<blingcu_texture> &tex, int id, const DG &dg) {   // MaterialParser.hs:113-154
+// Texture.hs:91-108: mod' a b = let a' = a - (a `div` b) * b in if a' < 0 then a' + b else a'; getPixel / getPixelScalar
+static inline long modP(long a, long b) {
+   long n = a / b; if ((a % b != 0) && ((a < 0) != (b < 0))) n -= 1;   // Haskell `div` rounds towards minus infinity
+   long ap = a - n * b;
+   return ap < 0 ? ap + b : ap;
+}
+static inline const float *imagePixelAt(const blingcu_image &im, float u, float v) {
+   long px = modP((long)std::floor(u * (float)im.width), im.width);
+   long py = modP((long)std::floor((-v) * (float)im.height), im.height);
+   return im.data + ((size_t)py * (size_t)im.width + (size_t)px) * (size_t)im.channels;
+}
+
+struct TexEnv { const std::vector<blingcu_texture> &tex; const std::vector<blingcu_image> &images; };
+
+static float evalScalarTexture(const TexEnv &env, int id, const DG &dg) {   // MaterialParser.hs:113-154
+   const std::vector<blingcu_texture> &tex = env.tex;
    const blingcu_texture &t = tex[id];
    switch (t.kind) {
+   case BLINGCU_STEX_IMAGE: { float x, y; mapping2d(t.s.v, dg, x, y); return imagePixelAt(env.images[t.aux], x, y)[0]; }   // fromIntegral x / 255 done by the host
    case BLINGCU_STEX_CONSTANT: return t.f[0];
-   case BLINGCU_STEX_SCALE: return t.f[0] + t.f[1] * evalScalarTexture(tex, t.child[0], dg);   // scaleTexture a s t dg = a + s * t dg
+   case BLINGCU_STEX_SCALE: return t.f[0] + t.f[1] * evalScalarTexture(env, t.child[0], dg);   // scaleTexture a s t dg = a + s * t dg
    case BLINGCU_STEX_PERLIN: { V3 q = transPoint(t.s.v, dg.p); return perlin3d(q.x, q.y, q.z); }
    case BLINGCU_STEX_FBM: return fbm(t.aux, t.f[0], transPoint(t.s.v, dg.p));
    case BLINGCU_STEX_CELLNOISE: return cellNoise(t.aux, transPoint(t.s.v, dg.p));
@@ -134,7 +150,7 @@ static float evalScalarTexture(const std::vector<blingcu_texture> &tex, int id, 
 }
 
 // Reflection.hs:347-377
-static DG bump(const std::vector<blingcu_texture> &tex, int d, const DG &dgg, const DG &dgs) {
+static DG bump(const TexEnv &tex, int d, const DG &dgg, const DG &dgs) {
    const float du = 0.01f, dv = 0.01f;
    DG dgeu = dgs; dgeu.p = dgs.p + scl(du, dgs.dpdu); dgeu.u = dgs.u + du;   // dgN of the shifted copies is never read
    DG dgev = dgs; dgev.p = dgs.p + scl(dv, dgs.dpdv); dgev.v = dgs.v + dv;

@@ -21,6 +21,7 @@ from oracle.oracle_py import Oracle  # noqa: E402
 
 W, H, NU, NV, PASSES, SEED = 80, 60, 4, 4, 256, 0xB11D6
 OUT = ROOT / "tests" / "golden" / "renders"
+NOISY = {"blackbody-emission"}   # fixtures whose per-channel mean carries a measured tolerance instead of 0.5 %
 
 
 def rel_mse(a, b):
@@ -41,9 +42,21 @@ def main(names):
         full = halves[0] + halves[1]
         xa, xb, xf = (image.film_xyz(f) for f in (halves[0], halves[1], full))
         floor = rel_mse(xa, xb)
+        extra = {}
+        if name in NOISY:
+            # the image MEAN of this scene does not converge to 0.5 % at 4096 spp (a few tiny, very bright emitters): measure
+            # the standard deviation of the mean from 8 independent 512-spp renders and let the test allow 4 sigma of the
+            # difference of two 4096-spp means instead
+            ms = []
+            for k in range(8):
+                o = Oracle(sc)
+                for p in range(1, 1 + PASSES // 8): o.render_pass(p, SEED + 1000 + k, threads=os.cpu_count())
+                ms.append(image.film_xyz(o.read_film()).mean((0, 1)))
+            ms = np.array(ms); sigma_full = (ms.std(0, ddof=1) / ms.mean(0)).max() / np.sqrt(8.0)
+            extra["mean_tol"] = max(5e-3, 4 * np.sqrt(2.0) * float(sigma_full))
         np.savez_compressed(OUT / f"{name}.npz", xyz=xf, cfg=np.array([W, H, NU, NV, PASSES]), relmse_halves=floor,
-                            relmse_bound=3 * floor, seed=SEED)
-        print(f"{name}: {time.time() - t:.0f}s, rel-MSE between 2048-spp halves {floor:.3e}, mean XYZ {xf.mean((0, 1))}", flush=True)
+                            relmse_bound=3 * floor, seed=SEED, **extra)
+        print(f"{name}: {time.time() - t:.0f}s, rel-MSE between 2048-spp halves {floor:.3e}, mean XYZ {xf.mean((0, 1))} {extra}", flush=True)
 
 
 if __name__ == "__main__":
