@@ -8,6 +8,11 @@ sys.path.insert(0, str(ROOT))
 from bling_b200 import api, ir as IR
 from bling_b200.host.loader import resized
 
+import os
+if os.environ.get("BLINGCU_LIB"):      # A/B: another build of the library (__graft_entry__.build_variant)
+    class _Ctx(api.Context):
+        _lib_path = Path(os.environ["BLINGCU_LIB"])
+    api.Context = _Ctx
 names = sys.argv[1:] or ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"]
 for name in names:
     name, _, size = name.partition("@")
