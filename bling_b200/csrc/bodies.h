@@ -393,6 +393,24 @@ struct DlShadeBody {
    }
 };
 
+// `debug normals` (mkNormalMap, Integrator/Debug.hs:23-33): the shading normal of the first hit as a reflectance spectrum
+struct NormalMapBody {
+   typedef MatOf<SK_TEXTURED> M;   // bump mapping moves the shading normal
+   const DScene *sc; PathState ps;
+   HD void operator()(uint32_t i) const {
+      const DScene &S = *sc;
+      F4 hv = ps.hit[i];
+      if (f2i(hv.w) == BL_REF_MISS) return;   // Nothing -> black (raygen left L = 0)
+      Ray ray = loadRay(ps.rayO, ps.rayD, i);
+      SurfaceHit sh; DG dgs;
+      surfaceAt(S, ray, hv.x, hv.y, hv.z, f2i(hv.w), sh, dgs);
+      Spec texScratch[4];
+      Bsdf bsdf; makeBsdfOf<M>(S, sh, dgs, bsdf, texScratch);
+      V3 n = bsdf.cs.n;
+      storeSpec4(ps.L, ps.cap, i, rgbToSpectrumBasis(S.refl, (1.0f + n.x) / 2, (1.0f + n.y) / 2, (1.0f + n.z) / 2));
+   }
+};
+
 // one thread: fold the queue counters into the statistics and rotate the queues (end of a bounce)
 struct AdvanceBody {
    PathState ps;

@@ -65,7 +65,7 @@ struct Pipeline {
       if (ir->width <= 0 || ir->height <= 0) return fail(BLINGCU_EINVAL, "bad image size");
       if (ir->nu <= 0 || ir->nv <= 0) return fail(BLINGCU_EINVAL, "bad sampler");
       if (ir->max_depth < 0 || ir->max_depth > 254) return fail(BLINGCU_EINVAL, "max_depth out of range");
-      if (ir->integrator_kind != BLINGCU_INTEGRATOR_PATH && ir->integrator_kind != BLINGCU_INTEGRATOR_DIRECT) return fail(BLINGCU_EINVAL, "unknown integrator");
+      if (ir->integrator_kind < BLINGCU_INTEGRATOR_PATH || ir->integrator_kind > BLINGCU_INTEGRATOR_NORMALS) return fail(BLINGCU_EINVAL, "unknown integrator");
       if (ir->integrator_kind == BLINGCU_INTEGRATOR_DIRECT && ir->max_depth > 24) return fail(BLINGCU_EINVAL, "direct lighting: max_depth out of range");
       size_t nt = (size_t)ir->n_triangles, ns = ir->n_shapes, nprim = nt + ns;
       // ---- validate indices
@@ -206,7 +206,8 @@ struct Pipeline {
       hs.max_depth = ir->max_depth; hs.sample_depth = ir->sample_depth;
       hs.integrator = ir->integrator_kind;
       const bool direct = hs.integrator == BLINGCU_INTEGRATOR_DIRECT;
-      hs.smp = mkSamplerConst(hs.nu, hs.nv, direct ? 2 * hs.max_depth : 4 * hs.sample_depth, direct ? 2 * hs.max_depth : 3 * hs.sample_depth,
+      const bool normals = hs.integrator == BLINGCU_INTEGRATOR_NORMALS;   // sampleCount1D = sampleCount2D = 0 (Debug.hs:24)
+      hs.smp = mkSamplerConst(hs.nu, hs.nv, normals ? 0 : (direct ? 2 * hs.max_depth : 4 * hs.sample_depth), normals ? 0 : (direct ? 2 * hs.max_depth : 3 * hs.sample_depth),
                               hs.sampler_kind == BLINGCU_SAMPLER_STRATIFIED);
       dlHeadroom = 2;
       for (int i = 0; i < NB; ++i) { hs.cieX[i] = ir->cie_x.v[i]; hs.cieY[i] = ir->cie_y.v[i]; hs.cieZ[i] = ir->cie_z.v[i]; }
@@ -395,6 +396,11 @@ struct Pipeline {
          uint32_t *t = qa; qa = qb; qb = t;
       }
    }
+   void bouncesNormals(uint32_t n) {
+      be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qA, ps.counters + C_ACTIVE, n, dscene, ps.rayO, ps.rayD, ps.hit);
+      be.tag(BLINGCU_KC_SHADE); be.runQueue(NormalMapBody{dscene, ps}, ps.qA, ps.counters + C_ACTIVE, n);
+      launches += 2;
+   }
    // Slots for n camera samples of the direct-lighting integrator: every glass-like vertex spawns one extra slot. Starts at
    // 2 n and doubles when a batch reports C_OVERFLOW (the batch is then re-run: nothing has reached the film yet); 2^maxDepth n
    // always suffices.
@@ -434,7 +440,8 @@ struct Pipeline {
          if (direct) {
             bouncesDirect(n);
             if (dlOverflowed()) { dlHeadroom *= 2; continue; }   // same batch again with twice the slots
-         } else bounces(n);
+         } else if (hs.integrator == BLINGCU_INTEGRATOR_NORMALS) bouncesNormals(n);
+         else bounces(n);
          be.tag(BLINGCU_KC_FILM); be.run(FinalizeBody{dscene, ps}, n);
          be.run(FilmBody{dscene, ps, film, k, npix}, (uint32_t)hs.W * (uint32_t)hs.H);
          launches += 2;
@@ -458,6 +465,7 @@ struct Pipeline {
          ensureState((uint32_t)n * (direct ? dlHeadroom : 1u));
          be.run(BeginBatchBody{ps, (uint32_t)n}, 1);
          be.run(RaygenBody{dscene, ps, seed, pass, 0, npix, dpx, dpy, ds}, (uint32_t)n);
+         if (hs.integrator == BLINGCU_INTEGRATOR_NORMALS) { bouncesNormals((uint32_t)n); break; }
          if (!direct) { bounces((uint32_t)n); break; }
          bouncesDirect((uint32_t)n);
          if (!dlOverflowed()) break;

@@ -113,7 +113,8 @@ enum {
 enum { BLINGCU_CAM_PERSPECTIVE = 0, BLINGCU_CAM_ENVIRONMENT = 1 };
 enum { BLINGCU_SAMPLER_STRATIFIED = 0, BLINGCU_SAMPLER_RANDOM = 1 };
 /* Integrator/Path.hs:30-39 (max_depth, sample_depth) and, SURVEY §8(f)4, Integrator/DirectLighting.hs:13-21 (max_depth) */
-enum { BLINGCU_INTEGRATOR_PATH = 0, BLINGCU_INTEGRATOR_DIRECT = 1 };
+enum { BLINGCU_INTEGRATOR_PATH = 0, BLINGCU_INTEGRATOR_DIRECT = 1,
+       BLINGCU_INTEGRATOR_NORMALS = 2 /* `debug normals`: mkNormalMap (Integrator/Debug.hs:23-33), needs refl_basis */ };
 
 typedef struct blingcu_spectrum { float v[BLINGCU_BANDS]; } blingcu_spectrum;
 
@@ -241,7 +242,8 @@ typedef struct blingcu_scene {
    int32_t integrator_kind; /* BLINGCU_INTEGRATOR_*; 0 (path) keeps every older caller's meaning */
 
    /* image textures: decoded images and the reflectance basis r g b c m y w of rgbToSpectrumRefl
-    * (Spectrum.hs:128-145); both unused (0 / NULL) unless a BLINGCU_TEX_IMAGE / BLINGCU_STEX_IMAGE entry exists */
+    * (Spectrum.hs:128-145); unused (0 / NULL) unless a BLINGCU_TEX_IMAGE / BLINGCU_STEX_IMAGE entry exists or the integrator
+    * is BLINGCU_INTEGRATOR_NORMALS (basis only) */
    uint32_t n_images;
    const blingcu_image *images;
    blingcu_spectrum refl_basis[7];

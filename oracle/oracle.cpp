@@ -468,6 +468,7 @@ static SampleCtx mkSampleCtx(const Scene &sc, const Window &ext, uint64_t seed, 
    SampleCtx c;
    c.kp = pixelKey(seed, pass, pix); c.s = s; c.nu = sc.nu; c.nv = sc.nv;
    if (sc.integrator == BLINGCU_INTEGRATOR_DIRECT) { c.n1d = 2 * sc.maxDepth; c.n2d = 2 * sc.maxDepth; }   // DirectLighting.hs:18-19
+   else if (sc.integrator == BLINGCU_INTEGRATOR_NORMALS) { c.n1d = 0; c.n2d = 0; }                            // Debug.hs:24
    else { c.n1d = 4 * sc.sampleDepth; c.n2d = 3 * sc.sampleDepth; }
    c.stratified = sc.samplerKind == BLINGCU_SAMPLER_STRATIFIED;
    return c;
@@ -480,6 +481,14 @@ static Spec renderSample(const Scene &sc, const Window &ext, uint64_t seed, uint
    sx = (float)ix + ox; sy = (float)iy + oy;
    Ray r = fireRay(sc, sx, sy, lu, lv);
    if (sc.integrator == BLINGCU_INTEGRATOR_DIRECT) { rc.cam++; return directLighting(sc, c, 0, r, rc); }
+   if (sc.integrator == BLINGCU_INTEGRATOR_NORMALS) {   // mkNormalMap (Integrator/Debug.hs:23-33)
+      rc.cam++;
+      Hit hit = sceneIntersect(sc, r);
+      if (!hit.valid) return sConst(0);
+      V3 n = makeBsdf(sc, hit).cs.n;                    // bsdfShadingNormal
+      V3 v = mk((1.0f + n.x) / 2, (1.0f + n.y) / 2, (1.0f + n.z) / 2);   // (vpromote 1 + n) / 2
+      return rgbToSpectrum(sc.refl, v.x, v.y, v.z);     // rgbToSpectrumRefl
+   }
    return pathLi(sc, c, r, rc);
 }
 

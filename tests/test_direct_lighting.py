@@ -112,3 +112,41 @@ def test_loader_reads_the_reference_direct_lighting_example():
 def test_gpu_branch_tree_and_headroom_retry():
     from bling_b200.api import Context
     _check_branch_tree(lambda: Context(0))
+
+
+# ------------------------------------------------------------------------------------------------ `debug normals`
+def _normals_scene():
+    sc = small(load_scene("textures"), 72, 44, 2, 2)      # bump-mapped objects: the SHADING normal is what is shown
+    sc.integrator_kind = IR.INTEGRATOR_NORMALS
+    return sc
+
+
+def _check_normal_map(make_ctx, exact):
+    sc = _normals_scene()
+    o = Oracle(sc)
+    x0, x1, y0, y1 = o.sample_extent()
+    xs, ys = np.meshgrid(np.arange(x0, x1 + 1), np.arange(y0, y1 + 1))
+    px, py = xs.ravel(), ys.ravel(); s = np.ones_like(px)
+    Lo, xyo = o.render_samples(1, 1, px, py, s)
+    c = make_ctx(); c.upload_scene(sc)
+    Lc, xyc = c.render_samples(1, 1, px, py, s)
+    c.render_pass(1, 5); film = c.read_film(); c.close()
+    assert np.array_equal(xyo, xyc)
+    if exact: assert np.array_equal(Lo, Lc)
+    else: assert (np.abs(Lo - Lc).max(1) < 1e-4).mean() > 0.999
+    assert (Lo.max(1) == 0).sum() > 20 and (Lo.max(1) > 0).sum() > 1000      # black where the ray leaves the scene
+    o.render_pass(1, 5, threads=4)
+    assert np.abs(film - o.read_film()).mean() <= 1e-5 * np.abs(film).mean()
+    # rgbToSpectrumRefl((1 + n) / 2): a flat, un-bumped ground would be one colour; the fbm bump makes it vary
+    assert np.unique(np.round(Lo[Lo.max(1) > 0], 3), axis=0).shape[0] > 100
+
+
+def test_emulated_normal_map_integrator_matches_oracle():
+    """mkNormalMap (Integrator/Debug.hs:23-33): rgbToSpectrumRefl ((1 + bsdfShadingNormal) / 2) of the first hit, black on a miss"""
+    _check_normal_map(EmuContext, exact=True)
+
+
+@pytest.mark.gpu
+def test_gpu_normal_map_integrator_matches_oracle():
+    from bling_b200.api import Context
+    _check_normal_map(lambda: Context(0), exact=False)
