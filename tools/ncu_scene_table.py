@@ -20,8 +20,11 @@ COLS = [("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots bus
 
 
 def klass(name):
-    if "kTracePersistent<(bool)0>" in name: return "trace nearest"
-    if "kTracePersistent<(bool)1>" in name: return "trace any"
+    if "kTracePersistent<(bool)0>" in name or "kTracePersistent<0>" in name: return "trace nearest"
+    if "kTracePersistent<(bool)1>" in name or "kTracePersistent<1>" in name: return "trace any"
+    if "ClassifyBody" in name: return "classify"
+    if "ShadeMissBody" in name: return "shade (miss)"
+    if "RaygenBody" in name: return "raygen"
     if "ShadeHitBody" in name: return "shade (hit)"
     if "Resolve" in name: return "resolve"
     if "kFilmTile" in name or "FilmBody" in name or "FinalizeBody" in name: return "film"
