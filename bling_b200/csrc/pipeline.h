@@ -423,11 +423,14 @@ struct Pipeline {
       uint32_t spp = (uint32_t)(hs.nu * hs.nv);
       if (sBegin > sEnd || sEnd > spp) return fail(BLINGCU_EINVAL, "sample range out of bounds");
       const bool direct = hs.integrator == BLINGCU_INTEGRATOR_DIRECT;
-      uint32_t kmax = std::max(1u, (direct ? batchTarget / 4 : batchTarget) / npix);
+      uint32_t kmax = std::max(1u, batchTarget / npix);
       uint32_t need = std::min(kmax, std::max(1u, sEnd - sBegin)) * npix;
       if (!direct) ensureState(need);
       auto t0 = be.timerStart();
       for (uint32_t s = sBegin; s < sEnd;) {
+         // direct lighting: the wavefront (camera samples x head-room) stays within the same slot budget, so more
+         // head-room means fewer sample indices per batch, not more memory
+         if (direct) kmax = std::max(1u, batchTarget / dlHeadroom / npix);
          uint32_t k = std::min(kmax, sEnd - s);
          uint32_t n = k * npix;
          if (direct) {

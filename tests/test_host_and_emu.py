@@ -118,9 +118,11 @@ def test_emulated_film_matches_oracle_tiles():
             assert se["rays_mis_culled"] > se["rays_mis"]
 
 
-def test_slices_and_batches_compose():
-    """render_pass == union of slices == any batch size (linearity of the film in the sample set)."""
-    sc = small(load_scene("glass-torus"), 32, 24, 4, 4)
+@pytest.mark.parametrize("name", ["glass-torus", "direct", "textures"])
+def test_slices_and_batches_compose(name):
+    """render_pass == union of slices == any batch size (linearity of the film in the sample set) -- also for the
+    direct-lighting integrator, whose batches carry spawned branch slots (the sharding unit of SURVEY §8e is the slice)."""
+    sc = small(load_scene(name), 32, 24, 4, 4)
     a = EmuContext(); a.upload_scene(sc); a.render_pass(3, 9)
     b = EmuContext(); b.set_option("batch_samples", 3000); b.upload_scene(sc)
     b.render_slice(3, 9, 0, 5); b.render_slice(3, 9, 5, 16)
