@@ -10,13 +10,12 @@
 
 namespace bl {
 
-enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MISANY = 4, C_DROPPED = 5, C_MISCULL = 6, C_EXTCULL = 7, C_MAT0 = 8, C_SPAWN = 8 + 17, C_OVERFLOW, N_COUNTERS };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + shade kind
-// shade kinds: the material kinds, then SK_TEXTURED = materials whose textures compute (textures.h); upload puts the
-// shade kind of each primitive's material into its hit reference
-// Textured materials are spread over N_TEX_QUEUES queues by material (kind values SK_TEXTURED .. 15 of the 4-bit field of the
-// hit reference), so that one launch of the general kernel runs few materials: its code is large and warps that sit in
-// different materials starve each other's instruction fetch.
-enum { SK_TEXTURED = BLINGCU_MAT_KINDS, N_TEX_QUEUES = 16 - BLINGCU_MAT_KINDS, N_SHADE_KINDS = 1 + 16 };
+enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MISANY = 4, C_DROPPED = 5, C_MISCULL = 6, C_EXTCULL = 7, C_MAT0 = 8, C_SPAWN = 8 + 19, C_OVERFLOW, N_COUNTERS };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + shade kind
+// Shade queues: 0 = miss, 1 + kind for the nine material kinds, 10 + kind for the same kinds with computing textures
+// (shade kind SK_TEX0 + kind in the hit reference; textures.h). Upload puts the shade kind of each primitive's material into
+// its hit reference, so classification never touches geometry or materials.
+enum { N_SHADE_KINDS = 1 + 2 * BLINGCU_MAT_KINDS };
+HD int shadeSlot(int shadeKind) { return shadeKind < SK_TEX0 ? 1 + shadeKind : 1 + BLINGCU_MAT_KINDS + (shadeKind - SK_TEX0); }
 enum { S_SAMPLES = 0, S_CAM, S_EXT, S_MIS, S_SHADOW, S_DROPPED, S_MISCULL, S_MISANY, S_EXTCULL, N_STATS = 12 };
 
 struct PathState {
@@ -131,7 +130,7 @@ struct ClassifyBody {
       if (href == BL_REF_MISS) kind = 0;
       else {
          if ((int)(ps.meta[i] & 0xffu) == S.max_depth) return;   // Path.hs:51: depth == md -> return l
-         kind = 1 + refKind(href);                                // the material kind travels in the hit record
+         kind = shadeSlot(refKind(href));                         // the shade kind travels in the hit record
       }
       qPush(ps.qMat + (size_t)kind * ps.cap, ps.counters + C_MAT0 + kind, i);
    }
@@ -340,9 +339,9 @@ typedef ResolveMisAnyBodyT<true> DlResolveMisAnyBody;
 // where the two continuations follow only SPECULAR components (`cont`, :47-58: sampleBsdf' t bsdf wo 0.5 (0.5, 0.5)) and stop
 // at d + 1 == maxDepth. The recursion is a tree: the first continuation stays in the slot, the second is spawned into a
 // fresh slot (C_SPAWN); every slot adds its radiance to the camera sample it descends from (rootOf) with atomics.
-// One instantiation for all material kinds (MatOf<SK_TEXTURED>: every BxDF, computing textures).
+// One instantiation for all material kinds (MatOf<SK_GENERAL>: every BxDF, computing textures, out-of-line general copies).
 struct DlShadeBody {
-   typedef MatOf<SK_TEXTURED> M;
+   typedef MatOf<SK_GENERAL> M;
    const DScene *sc; PathState ps; uint32_t *qNext; uint32_t nRoot;
    HD void operator()(uint32_t i) const {
       const DScene &S = *sc;
@@ -395,7 +394,7 @@ struct DlShadeBody {
 
 // `debug normals` (mkNormalMap, Integrator/Debug.hs:23-33): the shading normal of the first hit as a reflectance spectrum
 struct NormalMapBody {
-   typedef MatOf<SK_TEXTURED> M;   // bump mapping moves the shading normal
+   typedef MatOf<SK_GENERAL> M;   // bump mapping moves the shading normal
    const DScene *sc; PathState ps;
    HD void operator()(uint32_t i) const {
       const DScene &S = *sc;

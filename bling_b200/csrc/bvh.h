@@ -36,15 +36,16 @@ struct Bvh {
 };
 
 // Hit record. `prim` is the leaf item's REFERENCE, not the reference implementation's primitive id:
-//   bit 31 = analytic shape, bits 27..30 = material kind (BLINGCU_MAT_*), bits 0..26 = triangle / shape index;  -1 = miss.
+//   bit 31 = analytic shape, bits 26..30 = shade kind (BLINGCU_MAT_*, + 16 when the material's textures compute),
+//   bits 0..25 = triangle / shape index;  -1 = miss.
 // The wavefront classifies by material kind straight from this word and finds the geometry without an indirection;
 // the C ABI converts it to the primitive id of `mkScene`'s list on the way out (HitToAbiBody).
 struct HitRec { float t; int prim; float b1, b2; };
 #define BL_REF_MISS (-1)
 HD bool refIsShape(int ref) { return ((uint32_t)ref >> 31) != 0; }
-HD int refKind(int ref) { return (int)(((uint32_t)ref >> 27) & 15u); }
-HD uint32_t refIndex(int ref) { return (uint32_t)ref & 0x07ffffffu; }
-HD int mkRef(bool shape, int kind, uint32_t index) { return (int)((shape ? 0x80000000u : 0u) | ((uint32_t)kind << 27) | index); }
+HD int refKind(int ref) { return (int)(((uint32_t)ref >> 26) & 31u); }
+HD uint32_t refIndex(int ref) { return (uint32_t)ref & 0x03ffffffu; }
+HD int mkRef(bool shape, int kind, uint32_t index) { return (int)((shape ? 0x80000000u : 0u) | ((uint32_t)kind << 26) | index); }
 
 
 HD bool leafItemNearest(const Bvh &bvh, int item, Ray &r, HitRec &h) {

@@ -118,7 +118,7 @@ int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
    std::memset(&out, 0, sizeof(out));
    out.root = -1;
    if (in.n == 0) return 0;
-   if (in.n >= (1u << 27)) return 1;
+   if (in.n >= (1u << 26)) return 1;   // 26 index bits in the hit reference (bvh.h)
    Box scene; scene.reset();
    for (size_t i = 0; i < in.n; ++i) scene.grow(in.lo + 3 * i, in.hi + 3 * i);
    float ext = 0;

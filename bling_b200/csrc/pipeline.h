@@ -129,9 +129,9 @@ struct Pipeline {
          }
          itemPrim[it] = (int32_t)pid;
       }
-      // shade kind per material: its kind, or SK_TEXTURED when its textures compute (the slow, general shade kernel)
+      // shade kind per material: its kind, + SK_TEX0 when its textures compute (the kind's kernel with texture evaluation)
       std::vector<int> shadeKind(ir->n_materials ? ir->n_materials : 1, 0);
-      { int nTex = 0; for (uint32_t i = 0; i < ir->n_materials; ++i) shadeKind[i] = materialComputes(ir, ir->materials[i]) ? (int)SK_TEXTURED + (nTex++ % N_TEX_QUEUES) : ir->materials[i].kind; }
+      for (uint32_t i = 0; i < ir->n_materials; ++i) shadeKind[i] = ir->materials[i].kind + (materialComputes(ir, ir->materials[i]) ? (int)SK_TEX0 : 0);
       BvhBuildInput bi; bi.n = nprim; bi.lo = lo.data(); bi.hi = hi.data(); bi.max_leaf = maxLeaf;
       bi.threads = (int)std::max(1u, std::thread::hardware_concurrency());
       BvhBuildOutput bo;
@@ -256,18 +256,15 @@ struct Pipeline {
             for (int k = 1; k < N_SHADE_KINDS; ++k) {
                if (!kindPresent[k]) continue;
                const uint32_t *qk = ps.qMat + (size_t)k * cap; const uint32_t *ck = ps.counters + C_MAT0 + k;
-               switch (k - 1) {   // one instantiation of the shade kernel per material kind
-               case BLINGCU_MAT_MATTE: be.runQueue(ShadeHitBody<BLINGCU_MAT_MATTE>{dscene, ps, qb}, qk, ck, bound); break;
-               case BLINGCU_MAT_GLASS: be.runQueue(ShadeHitBody<BLINGCU_MAT_GLASS>{dscene, ps, qb}, qk, ck, bound); break;
-               case BLINGCU_MAT_MIRROR: be.runQueue(ShadeHitBody<BLINGCU_MAT_MIRROR>{dscene, ps, qb}, qk, ck, bound); break;
-               case BLINGCU_MAT_PLASTIC: be.runQueue(ShadeHitBody<BLINGCU_MAT_PLASTIC>{dscene, ps, qb}, qk, ck, bound); break;
-               case BLINGCU_MAT_METAL: be.runQueue(ShadeHitBody<BLINGCU_MAT_METAL>{dscene, ps, qb}, qk, ck, bound); break;
-               case BLINGCU_MAT_SHINYMETAL: be.runQueue(ShadeHitBody<BLINGCU_MAT_SHINYMETAL>{dscene, ps, qb}, qk, ck, bound); break;
-               case BLINGCU_MAT_TRANSMATTE: be.runQueue(ShadeHitBody<BLINGCU_MAT_TRANSMATTE>{dscene, ps, qb}, qk, ck, bound); break;
-               case BLINGCU_MAT_SUBSTRATE: be.runQueue(ShadeHitBody<BLINGCU_MAT_SUBSTRATE>{dscene, ps, qb}, qk, ck, bound); break;
-               case BLINGCU_MAT_BLACKBODY: be.runQueue(ShadeHitBody<BLINGCU_MAT_BLACKBODY>{dscene, ps, qb}, qk, ck, bound); break;
-               default: be.runQueue(ShadeHitBody<SK_TEXTURED>{dscene, ps, qb}, qk, ck, bound); break;   // SK_TEXTURED + queue
+               // one instantiation of the shade kernel per material kind, and one more per kind for materials whose textures compute
+#define BL_SHADE(K) case 1 + K: be.runQueue(ShadeHitBody<K>{dscene, ps, qb}, qk, ck, bound); break; \
+                    case 1 + BLINGCU_MAT_KINDS + K: be.runQueue(ShadeHitBody<SK_TEX0 + K>{dscene, ps, qb}, qk, ck, bound); break;
+               switch (k) {
+               BL_SHADE(BLINGCU_MAT_MATTE) BL_SHADE(BLINGCU_MAT_GLASS) BL_SHADE(BLINGCU_MAT_MIRROR) BL_SHADE(BLINGCU_MAT_PLASTIC) BL_SHADE(BLINGCU_MAT_METAL)
+               BL_SHADE(BLINGCU_MAT_BLACKBODY) BL_SHADE(BLINGCU_MAT_SHINYMETAL) BL_SHADE(BLINGCU_MAT_TRANSMATTE) BL_SHADE(BLINGCU_MAT_SUBSTRATE)
+               default: break;
                }
+#undef BL_SHADE
                launches++;
             }
             be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl);
@@ -412,7 +409,7 @@ struct Pipeline {
    void scanKinds(const blingcu_scene *ir) {
       for (int k = 0; k < N_SHADE_KINDS; ++k) kindPresent[k] = false;
       kindPresent[0] = true;
-      { int nTex = 0; for (uint32_t i = 0; i < ir->n_materials; ++i) kindPresent[1 + (materialComputes(ir, ir->materials[i]) ? (int)SK_TEXTURED + (nTex++ % N_TEX_QUEUES) : ir->materials[i].kind)] = true; }
+      for (uint32_t i = 0; i < ir->n_materials; ++i) kindPresent[shadeSlot(ir->materials[i].kind + (materialComputes(ir, ir->materials[i]) ? (int)SK_TEX0 : 0))] = true;
       hasInfinite = hasArea = hasBox = false;
       for (uint32_t i = 0; i < ir->n_shapes; ++i) hasBox |= ir->shapes[i].kind == BLINGCU_SHAPE_BOX;
       for (uint32_t i = 0; i < ir->n_lights; ++i) { hasInfinite |= ir->lights[i].kind == BLINGCU_LIGHT_INFINITE; hasArea |= ir->lights[i].kind == BLINGCU_LIGHT_AREA; }

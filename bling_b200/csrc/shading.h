@@ -165,26 +165,34 @@ enum { FR_NOOP = 0, FR_DIELECTRIC, FR_CONDUCTOR };
 // Compile-time description of what a material can contain. The shade kernel is launched once per material KIND
 // (material-sorted queues), so each launch is instantiated for its kind and the BxDF code of every other kind drops
 // out (fewer registers, more resident warps). AnyMat keeps everything (resolve kernels, generic callers).
-// TX: the material's textures may COMPUTE (scalar textures, blends, gradients, bump mapping; textures.h) -- only the
-// "textured" shade queue (kind index BLINGCU_MAT_KINDS, assigned by upload to such materials) is instantiated with it.
-struct AnyMat { static const unsigned KM = 0x3fu, FM = 0x7u; static const int NC = 2, MK = -1; static const bool TX = false; };
+// TX: the material's textures may COMPUTE (scalar textures, blends, gradients, images, bump mapping; textures.h): upload gives
+//     such materials the shade kind SK_TEX0 + kind, shaded by MatOf<SK_TEX0 + kind> = the kind's own traits with TX set.
+// GEN: the ANY-kind instantiation (direct-lighting and normal-map bodies): BSDF / light code goes through the out-of-line
+//     general copies below instead of being inlined (instruction fetch, profiles/r01_general_shade.md).
+enum { SK_GENERAL = BLINGCU_MAT_KINDS, SK_TEX0 = 16 };
+struct AnyMat { static const unsigned KM = 0x3fu, FM = 0x7u; static const int NC = 2, MK = -1; static const bool TX = false, GEN = false; };
 // GenMat: AnyMat whose per-component BxDF calls go to ONE out-of-line copy each (bxdf*General below) -- used by the general
 // shade kernels, whose code size is what limits them (see "out-of-line general versions")
 struct GenMat : AnyMat {};
 template <class M> struct IsGen { static const bool v = false; };
 template <> struct IsGen<GenMat> { static const bool v = true; };
 template <int MATKIND> struct MatOf : AnyMat {};
-template <> struct MatOf<BLINGCU_MAT_KINDS> : AnyMat { static const bool TX = true; };
+template <> struct MatOf<SK_GENERAL> : AnyMat { static const bool TX = true, GEN = true; };
 #define BL_K(k) (1u << (k))
-template <> struct MatOf<BLINGCU_MAT_MATTE> { static const unsigned KM = BL_K(0) | BL_K(1), FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_MATTE; static const bool TX = false; };
-template <> struct MatOf<BLINGCU_MAT_GLASS> { static const unsigned KM = BL_K(2) | BL_K(3), FM = BL_K(1); static const int NC = 2, MK = BLINGCU_MAT_GLASS; static const bool TX = false; };
-template <> struct MatOf<BLINGCU_MAT_MIRROR> { static const unsigned KM = BL_K(2), FM = BL_K(0); static const int NC = 1, MK = BLINGCU_MAT_MIRROR; static const bool TX = false; };
-template <> struct MatOf<BLINGCU_MAT_PLASTIC> { static const unsigned KM = BL_K(0) | BL_K(4), FM = BL_K(1); static const int NC = 2, MK = BLINGCU_MAT_PLASTIC; static const bool TX = false; };
-template <> struct MatOf<BLINGCU_MAT_METAL> { static const unsigned KM = BL_K(4), FM = BL_K(2); static const int NC = 1, MK = BLINGCU_MAT_METAL; static const bool TX = false; };
-template <> struct MatOf<BLINGCU_MAT_SHINYMETAL> { static const unsigned KM = BL_K(2) | BL_K(4), FM = BL_K(2); static const int NC = 2, MK = BLINGCU_MAT_SHINYMETAL; static const bool TX = false; };
-template <> struct MatOf<BLINGCU_MAT_TRANSMATTE> { static const unsigned KM = BL_K(0) | BL_K(1), FM = 0u; static const int NC = 2, MK = BLINGCU_MAT_TRANSMATTE; static const bool TX = false; };
-template <> struct MatOf<BLINGCU_MAT_SUBSTRATE> { static const unsigned KM = BL_K(5), FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_SUBSTRATE; static const bool TX = false; };
-template <> struct MatOf<BLINGCU_MAT_BLACKBODY> { static const unsigned KM = 0u, FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_BLACKBODY; static const bool TX = false; };
+template <> struct MatOf<BLINGCU_MAT_MATTE> { static const unsigned KM = BL_K(0) | BL_K(1), FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_MATTE; static const bool TX = false, GEN = false; };
+template <> struct MatOf<BLINGCU_MAT_GLASS> { static const unsigned KM = BL_K(2) | BL_K(3), FM = BL_K(1); static const int NC = 2, MK = BLINGCU_MAT_GLASS; static const bool TX = false, GEN = false; };
+template <> struct MatOf<BLINGCU_MAT_MIRROR> { static const unsigned KM = BL_K(2), FM = BL_K(0); static const int NC = 1, MK = BLINGCU_MAT_MIRROR; static const bool TX = false, GEN = false; };
+template <> struct MatOf<BLINGCU_MAT_PLASTIC> { static const unsigned KM = BL_K(0) | BL_K(4), FM = BL_K(1); static const int NC = 2, MK = BLINGCU_MAT_PLASTIC; static const bool TX = false, GEN = false; };
+template <> struct MatOf<BLINGCU_MAT_METAL> { static const unsigned KM = BL_K(4), FM = BL_K(2); static const int NC = 1, MK = BLINGCU_MAT_METAL; static const bool TX = false, GEN = false; };
+template <> struct MatOf<BLINGCU_MAT_SHINYMETAL> { static const unsigned KM = BL_K(2) | BL_K(4), FM = BL_K(2); static const int NC = 2, MK = BLINGCU_MAT_SHINYMETAL; static const bool TX = false, GEN = false; };
+template <> struct MatOf<BLINGCU_MAT_TRANSMATTE> { static const unsigned KM = BL_K(0) | BL_K(1), FM = 0u; static const int NC = 2, MK = BLINGCU_MAT_TRANSMATTE; static const bool TX = false, GEN = false; };
+template <> struct MatOf<BLINGCU_MAT_SUBSTRATE> { static const unsigned KM = BL_K(5), FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_SUBSTRATE; static const bool TX = false, GEN = false; };
+template <> struct MatOf<BLINGCU_MAT_BLACKBODY> { static const unsigned KM = 0u, FM = 0u; static const int NC = 1, MK = BLINGCU_MAT_BLACKBODY; static const bool TX = false, GEN = false; };
+
+#define BL_TEXMAT(K) template <> struct MatOf<SK_TEX0 + K> : MatOf<K> { static const bool TX = true; };
+BL_TEXMAT(BLINGCU_MAT_MATTE) BL_TEXMAT(BLINGCU_MAT_GLASS) BL_TEXMAT(BLINGCU_MAT_MIRROR) BL_TEXMAT(BLINGCU_MAT_PLASTIC) BL_TEXMAT(BLINGCU_MAT_METAL)
+BL_TEXMAT(BLINGCU_MAT_BLACKBODY) BL_TEXMAT(BLINGCU_MAT_SHINYMETAL) BL_TEXMAT(BLINGCU_MAT_TRANSMATTE) BL_TEXMAT(BLINGCU_MAT_SUBSTRATE)
+#undef BL_TEXMAT
 
 struct BxDF {
    int kind, type, fr, clamp01;   // clamp01: sClamp' applied to r on read (glass, mirror; Material.hs:63-64,71)
@@ -762,19 +770,19 @@ HD float lightPdf(const DScene &sc, const blingcu_light &l, V3 p, V3 wiW) {   //
 // The general (any material kind) shade kernels -- textured queue, direct-lighting integrator -- inline every BxDF with its
 // 16-band arithmetic at each call site: ~700 KB of code, and ncu shows them starved by instruction fetch
 // (stall no_instruction 47 warps per issue, profiles/r01_texshade.md). They call these shared copies instead; the
-// per-kind kernels (M::TX == false) keep the inlined, specialised code.
+// per-kind kernels (M::GEN == false, textured or not) keep the inlined, specialised code.
 HDNI void sampleBsdfGeneral(const Bsdf &b, V3 wo, float uc, float u1, float u2, BsdfSample &o) { sampleBsdf<GenMat>(b, wo, uc, u1, u2, o); }
 HDNI void sampleBsdfSpecularGeneral(const Bsdf &b, int flags, V3 wo, BsdfSample &o) { sampleBsdfSpecular<GenMat>(b, flags, wo, o); }
 HDNI void evalBsdfGeneral(const Bsdf &b, V3 wo, V3 wi, Spec &f) { f = evalBsdf<GenMat>(b, wo, wi); }
 HDNI float bsdfPdfGeneral(const Bsdf &b, V3 wo, V3 wi) { return bsdfPdf<GenMat>(b, wo, wi); }
 HDNI void lightSampleGeneral(const DScene &sc, const blingcu_light &l, V3 p, float eps, V3 n, float u1, float u2, LightSample &o) { lightSample(sc, l, p, eps, n, u1, u2, o); }
-HDNI void makeBsdfGeneral(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b, Spec *scratch) { makeBsdf<MatOf<BLINGCU_MAT_KINDS> >(sc, sh, dgs, b, scratch); }
-// dispatchers: M::TX is a compile-time constant
-template <class M> HD void sampleBsdfOf(const Bsdf &b, V3 wo, float uc, float u1, float u2, BsdfSample &o) { if (M::TX) sampleBsdfGeneral(b, wo, uc, u1, u2, o); else sampleBsdf<M>(b, wo, uc, u1, u2, o); }
-template <class M> HD Spec evalBsdfOf(const Bsdf &b, V3 wo, V3 wi) { if (M::TX) { Spec f; evalBsdfGeneral(b, wo, wi, f); return f; } return evalBsdf<M>(b, wo, wi); }
-template <class M> HD float bsdfPdfOf(const Bsdf &b, V3 wo, V3 wi) { if (M::TX) return bsdfPdfGeneral(b, wo, wi); return bsdfPdf<M>(b, wo, wi); }
-template <class M> HD void lightSampleOf(const DScene &sc, const blingcu_light &l, V3 p, float eps, V3 n, float u1, float u2, LightSample &o) { if (M::TX) lightSampleGeneral(sc, l, p, eps, n, u1, u2, o); else lightSample(sc, l, p, eps, n, u1, u2, o); }
-template <class M> HD void makeBsdfOf(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b, Spec *scratch) { if (M::TX) makeBsdfGeneral(sc, sh, dgs, b, scratch); else makeBsdf<M>(sc, sh, dgs, b, scratch); }
+HDNI void makeBsdfGeneral(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b, Spec *scratch) { makeBsdf<MatOf<SK_GENERAL> >(sc, sh, dgs, b, scratch); }
+// dispatchers: M::GEN is a compile-time constant
+template <class M> HD void sampleBsdfOf(const Bsdf &b, V3 wo, float uc, float u1, float u2, BsdfSample &o) { if (M::GEN) sampleBsdfGeneral(b, wo, uc, u1, u2, o); else sampleBsdf<M>(b, wo, uc, u1, u2, o); }
+template <class M> HD Spec evalBsdfOf(const Bsdf &b, V3 wo, V3 wi) { if (M::GEN) { Spec f; evalBsdfGeneral(b, wo, wi, f); return f; } return evalBsdf<M>(b, wo, wi); }
+template <class M> HD float bsdfPdfOf(const Bsdf &b, V3 wo, V3 wi) { if (M::GEN) return bsdfPdfGeneral(b, wo, wi); return bsdfPdf<M>(b, wo, wi); }
+template <class M> HD void lightSampleOf(const DScene &sc, const blingcu_light &l, V3 p, float eps, V3 n, float u1, float u2, LightSample &o) { if (M::GEN) lightSampleGeneral(sc, l, p, eps, n, u1, u2, o); else lightSample(sc, l, p, eps, n, u1, u2, o); }
+template <class M> HD void makeBsdfOf(const DScene &sc, const SurfaceHit &sh, const DG &dgs, Bsdf &b, Spec *scratch) { if (M::GEN) makeBsdfGeneral(sc, sh, dgs, b, scratch); else makeBsdf<M>(sc, sh, dgs, b, scratch); }
 
 // ------------------------------------------------------------------------------------------ camera (Camera.hs:49-76)
 HD Ray fireRay(const blingcu_camera &c, float ix, float iy, float lu, float lv) {
