@@ -10,12 +10,12 @@
 
 namespace bl {
 
-enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MISANY = 4, C_DROPPED = 5, C_MISCULL = 6, C_EXTCULL = 7, C_MAT0 = 8, C_SPAWN = 8 + 19, C_OVERFLOW, N_COUNTERS };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + shade kind
-// Shade queues: 0 = miss, 1 + kind for the nine material kinds, 10 + kind for the same kinds with computing textures
-// (shade kind SK_TEX0 + kind in the hit reference; textures.h). Upload puts the shade kind of each primitive's material into
-// its hit reference, so classification never touches geometry or materials.
-enum { N_SHADE_KINDS = 1 + 2 * BLINGCU_MAT_KINDS };
-HD int shadeSlot(int shadeKind) { return shadeKind < SK_TEX0 ? 1 + shadeKind : 1 + BLINGCU_MAT_KINDS + (shadeKind - SK_TEX0); }
+enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MISANY = 4, C_DROPPED = 5, C_MISCULL = 6, C_EXTCULL = 7, C_MAT0 = 8, C_SPAWN = 8 + 32, C_OVERFLOW, N_COUNTERS };   // C_MAT0 + kind: 0 = miss, 1.. = 1 + shade kind
+// Shade queues ("slots"; the slot of a primitive's material, minus one, is the 5-bit field of its hit reference, so
+// classification never touches geometry or materials): 0 = miss, 1 + kind for the nine material kinds, and from N_PLAIN_SLOTS on
+// ONE SLOT PER MATERIAL whose textures compute (textures.h), each launched with its kind's textured kernel: the texture code of
+// different materials in one launch starves instruction fetch (profiles/r01_general_shade.md).
+enum { N_PLAIN_SLOTS = 1 + BLINGCU_MAT_KINDS, MAX_TEX_SLOTS = 32 - N_PLAIN_SLOTS, N_SHADE_KINDS = 32 };
 enum { S_SAMPLES = 0, S_CAM, S_EXT, S_MIS, S_SHADOW, S_DROPPED, S_MISCULL, S_MISANY, S_EXTCULL, N_STATS = 12 };
 
 struct PathState {
@@ -34,7 +34,7 @@ struct PathState {
    F4 *xyz;                // finalised sample: X, Y, Z, valid
    uint32_t *qA, *qB;      // active queues (ping-pong)
    uint32_t *qShadow, *qMis, *qMisAny;   // qMis: nearest-hit MIS rays (area lights); qMisAny: any-hit MIS rays (infinite lights)
-   uint32_t *qMat;         // N_SHADE_KINDS * cap
+   uint32_t *qMat;         // (slots in use) * cap
    uint32_t *root;         // direct-lighting integrator: slot of the camera sample a spawned branch belongs to
    uint32_t *counters;     // N_COUNTERS
    unsigned long long *stats;   // N_STATS
@@ -130,7 +130,7 @@ struct ClassifyBody {
       if (href == BL_REF_MISS) kind = 0;
       else {
          if ((int)(ps.meta[i] & 0xffu) == S.max_depth) return;   // Path.hs:51: depth == md -> return l
-         kind = shadeSlot(refKind(href));                         // the shade kind travels in the hit record
+         kind = 1 + refKind(href);                                // the shade slot travels in the hit record
       }
       qPush(ps.qMat + (size_t)kind * ps.cap, ps.counters + C_MAT0 + kind, i);
    }

@@ -129,9 +129,10 @@ struct Pipeline {
          }
          itemPrim[it] = (int32_t)pid;
       }
-      // shade kind per material: its kind, + SK_TEX0 when its textures compute (the kind's kernel with texture evaluation)
+      // shade slot per material (bodies.h): its kind's, or its own when its textures compute; the reference carries slot - 1
+      scanKinds(ir);
       std::vector<int> shadeKind(ir->n_materials ? ir->n_materials : 1, 0);
-      for (uint32_t i = 0; i < ir->n_materials; ++i) shadeKind[i] = ir->materials[i].kind + (materialComputes(ir, ir->materials[i]) ? (int)SK_TEX0 : 0);
+      for (uint32_t i = 0; i < ir->n_materials; ++i) shadeKind[i] = matSlot[i] - 1;
       BvhBuildInput bi; bi.n = nprim; bi.lo = lo.data(); bi.hi = hi.data(); bi.max_leaf = maxLeaf;
       bi.threads = (int)std::max(1u, std::thread::hardware_concurrency());
       BvhBuildOutput bo;
@@ -218,16 +219,17 @@ struct Pipeline {
       npix = (uint32_t)hs.EW * (uint32_t)hs.EH;
       film = (F4 *)be.alloc(sizeof(F4) * (size_t)hs.W * hs.H);
       be.zero(film, sizeof(F4) * (size_t)hs.W * hs.H);
-      scanKinds(ir);
       uploaded = true;
       return 0;
    }
 
    template <class T> T *st(size_t n) { T *p = (T *)be.alloc(sizeof(T) * n); stateAllocs.push_back(p); return p; }
+   int qSlotsAlloc = 0;   // shade queues the state holds
    int ensureState(uint32_t cap) {
-      if (ps.cap >= cap) return 0;
+      if (ps.cap >= cap && qSlotsAlloc >= nSlots) return 0;
+      cap = std::max(cap, ps.cap);
       freeState();
-      ps.cap = cap;
+      ps.cap = cap; qSlotsAlloc = nSlots;
       size_t c = cap;
       ps.rayO = st<F4>(c); ps.rayD = st<F4>(c); ps.hit = st<F4>(c);
       ps.T = st<F4>(4 * c); ps.L = st<F4>(4 * c);
@@ -235,7 +237,7 @@ struct Pipeline {
       ps.miO = st<F4>(c); ps.miD = st<F4>(c); ps.mihit = st<F4>(c); ps.PM = st<F4>(4 * c); ps.miInfo = st<F2>(c);
       ps.meta = st<uint32_t>(c); ps.kp = st<uint64_t>(c); ps.sidx = st<uint32_t>(c); ps.spos = st<F2>(c); ps.xyz = st<F4>(c);
       ps.qA = st<uint32_t>(c); ps.qB = st<uint32_t>(c); ps.qShadow = st<uint32_t>(c); ps.qMis = st<uint32_t>(c); ps.qMisAny = st<uint32_t>(c);
-      ps.qMat = st<uint32_t>((size_t)N_SHADE_KINDS * c);
+      ps.qMat = st<uint32_t>((size_t)nSlots * c);
       ps.root = st<uint32_t>(hs.integrator == BLINGCU_INTEGRATOR_DIRECT ? c : 1);
       ps.counters = st<uint32_t>(N_COUNTERS); ps.stats = st<unsigned long long>(N_STATS);
       be.zero(ps.counters, sizeof(uint32_t) * N_COUNTERS); be.zero(ps.stats, sizeof(unsigned long long) * N_STATS);
@@ -253,16 +255,17 @@ struct Pipeline {
          be.tag(BLINGCU_KC_SHADE); be.runQueue(ShadeMissBody{dscene, ps}, ps.qMat, ps.counters + C_MAT0, bound);
          launches += 3;
          if (d < hs.max_depth) {
-            for (int k = 1; k < N_SHADE_KINDS; ++k) {
+            for (int k = 1; k < nSlots; ++k) {
                if (!kindPresent[k]) continue;
                const uint32_t *qk = ps.qMat + (size_t)k * cap; const uint32_t *ck = ps.counters + C_MAT0 + k;
-               // one instantiation of the shade kernel per material kind, and one more per kind for materials whose textures compute
-#define BL_SHADE(K) case 1 + K: be.runQueue(ShadeHitBody<K>{dscene, ps, qb}, qk, ck, bound); break; \
-                    case 1 + BLINGCU_MAT_KINDS + K: be.runQueue(ShadeHitBody<SK_TEX0 + K>{dscene, ps, qb}, qk, ck, bound); break;
-               switch (k) {
+               // one instantiation of the shade kernel per material kind, one more per kind for materials whose textures compute
+               // (launched once per such material), and the any-kind one for a slot that several kinds had to share
+#define BL_SHADE(K) case K: be.runQueue(ShadeHitBody<K>{dscene, ps, qb}, qk, ck, bound); break; \
+                    case SK_TEX0 + K: be.runQueue(ShadeHitBody<SK_TEX0 + K>{dscene, ps, qb}, qk, ck, bound); break;
+               switch (slotKernel[k]) {
                BL_SHADE(BLINGCU_MAT_MATTE) BL_SHADE(BLINGCU_MAT_GLASS) BL_SHADE(BLINGCU_MAT_MIRROR) BL_SHADE(BLINGCU_MAT_PLASTIC) BL_SHADE(BLINGCU_MAT_METAL)
                BL_SHADE(BLINGCU_MAT_BLACKBODY) BL_SHADE(BLINGCU_MAT_SHINYMETAL) BL_SHADE(BLINGCU_MAT_TRANSMATTE) BL_SHADE(BLINGCU_MAT_SUBSTRATE)
-               default: break;
+               default: be.runQueue(ShadeHitBody<SK_GENERAL>{dscene, ps, qb}, qk, ck, bound); break;
                }
 #undef BL_SHADE
                launches++;
@@ -377,7 +380,7 @@ struct Pipeline {
          // hot at any one time small (profiles/r01_general_shade.md)
          be.tag(BLINGCU_KC_CLASSIFY); be.runQueue(ClassifyBody{dscene, ps}, qa, ps.counters + C_ACTIVE, bound);
          be.tag(BLINGCU_KC_SHADE);
-         for (int k = 1; k < N_SHADE_KINDS; ++k) {
+         for (int k = 1; k < nSlots; ++k) {
             if (!kindPresent[k]) continue;
             be.runQueue(DlShadeBody{dscene, ps, qb, n}, ps.qMat + (size_t)k * ps.cap, ps.counters + C_MAT0 + k, bound); launches++;
          }
@@ -405,11 +408,24 @@ struct Pipeline {
    bool dlOverflowed() { be.sync(); uint32_t f = 0; be.download(&f, ps.counters + C_OVERFLOW, sizeof(f)); return f != 0; }
 
    bool kindPresent[N_SHADE_KINDS] = {};
+   int slotKernel[N_SHADE_KINDS] = {};   // which ShadeHitBody instantiation serves the slot (a shade kind, see shading.h)
+   int nSlots = N_PLAIN_SLOTS;           // slots in use: [0, nSlots)
+   std::vector<int> matSlot;             // material -> slot
    bool hasInfinite = false, hasArea = false, hasBox = false;
    void scanKinds(const blingcu_scene *ir) {
-      for (int k = 0; k < N_SHADE_KINDS; ++k) kindPresent[k] = false;
-      kindPresent[0] = true;
-      for (uint32_t i = 0; i < ir->n_materials; ++i) kindPresent[shadeSlot(ir->materials[i].kind + (materialComputes(ir, ir->materials[i]) ? (int)SK_TEX0 : 0))] = true;
+      for (int k = 0; k < N_SHADE_KINDS; ++k) { kindPresent[k] = false; slotKernel[k] = -1; }
+      kindPresent[0] = true; nSlots = N_PLAIN_SLOTS;
+      matSlot.assign(ir->n_materials ? ir->n_materials : 1, 1);
+      int nTex = 0;
+      for (uint32_t i = 0; i < ir->n_materials; ++i) {
+         const int kind = ir->materials[i].kind;
+         int slot, kernel;
+         if (materialComputes(ir, ir->materials[i])) { slot = N_PLAIN_SLOTS + (nTex++ % MAX_TEX_SLOTS); kernel = SK_TEX0 + kind; }
+         else { slot = 1 + kind; kernel = kind; }
+         if (slotKernel[slot] >= 0 && slotKernel[slot] != kernel) kernel = SK_GENERAL;   // more than MAX_TEX_SLOTS textured materials
+         slotKernel[slot] = kernel; kindPresent[slot] = true; matSlot[i] = slot;
+         nSlots = std::max(nSlots, slot + 1);
+      }
       hasInfinite = hasArea = hasBox = false;
       for (uint32_t i = 0; i < ir->n_shapes; ++i) hasBox |= ir->shapes[i].kind == BLINGCU_SHAPE_BOX;
       for (uint32_t i = 0; i < ir->n_lights; ++i) { hasInfinite |= ir->lights[i].kind == BLINGCU_LIGHT_INFINITE; hasArea |= ir->lights[i].kind == BLINGCU_LIGHT_AREA; }

@@ -295,3 +295,34 @@ def test_gpu_textures_match_oracle():
     ctx = Context(0); ctx.upload_scene(sc)
     _all_textures_match(ctx, sc, exact=False)
     ctx.close()
+
+
+def test_more_textured_materials_than_slots_share_the_general_kernel():
+    """Every material whose textures compute gets its own shade queue (22 of them); beyond that, queues are shared and a queue
+    that mixes material kinds is shaded by the any-kind kernel. 24 extra textured materials in front of the real ones force
+    both: results must not change."""
+    import copy
+    base = _texture_scene()
+    sc = copy.copy(base)
+    sc.materials = [IR.Material.from_buffer_copy(m) for m in base.materials]
+    sc.shapes = [IR.Shape.from_buffer_copy(s) for s in base.shapes]
+    stex = _find(base, IR.STEX_FBM)[0]
+    extra = []
+    for k in range(24):
+        m = IR.Material(); m.kind = (IR.MAT_PLASTIC, IR.MAT_MIRROR, IR.MAT_METAL)[k % 3]
+        m.tex[0] = 0; m.tex[1] = 0; m.tex[2] = -1; m.tex3 = -1; m.f[0] = 0.1; m.bump = stex + 1
+        extra.append(m)
+    sc.materials = extra + sc.materials
+    for s in sc.shapes: s.material += 24
+    sc.tri_material = base.tri_material + 24
+    o = Oracle(base)
+    x0, x1, y0, y1 = o.sample_extent()
+    rng = np.random.default_rng(11)
+    n = 1500
+    px, py, s = rng.integers(x0, x1 + 1, n), rng.integers(y0, y1 + 1, n), rng.integers(0, base.spp, n)
+    Lo, _ = o.render_samples(1, 5, px, py, s)
+    for scene in (base, sc):
+        e = EmuContext(); e.upload_scene(scene)
+        Le, _ = e.render_samples(1, 5, px, py, s); e.close()
+        rel = np.abs(Lo - Le).max(1) / (np.abs(Lo).max(1) + 1e-6)
+        assert (rel < 1e-4).mean() > 0.999, rel.max()
