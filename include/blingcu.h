@@ -279,7 +279,8 @@ int blingcu_create(int device, blingcu_ctx **out);
 void blingcu_destroy(blingcu_ctx *);
 const char *blingcu_last_error(const blingcu_ctx *); /* ctx may be NULL: last create() error */
 
-/* replaces mkScene (Scene.hs:37-43): copies the IR, builds the BVH, uploads. */
+/* replaces mkScene (Scene.hs:37-43): copies the IR, builds the BVH, uploads. At most 2^26 primitives (triangles + shapes):
+ * the hit reference keeps 26 index bits next to the 5-bit shade-queue slot. */
 int blingcu_upload_scene(blingcu_ctx *, const blingcu_scene *ir);
 
 /* replaces scIntersect / occluded (Scene.hs:45-51) on explicit ray batches -- parity check (a) */
