@@ -263,6 +263,8 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118; one instantiation pe
 };
 
 // ------------------------------------------------------------------------------------------ K6 resolve
+// On the GPU the any-hit traversal kernel does this when it retires an unoccluded ray (trace_kernels.cuh, fused NEE resolve);
+// this body is what the CPU emulator runs behind its any-hit loop.
 struct ResolveShadowBody {   // Scene.hs:64: `occluded scene ray` -> black
    PathState ps;
    HD void operator()(uint32_t i) const {

@@ -253,13 +253,12 @@ struct CudaBackend {
       Scope sc_(this);
       launchTraceAny(tcfg, stream, q, cnt, n, sc, o, d, occl);
    }
-#ifdef BL_FUSE_RESOLVE
+   // any-hit query that also resolves: L[slot] += P[slot] for every unoccluded ray (trace_kernels.cuh)
    void traceAnyFused(const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc, const F4 *o, const F4 *d, uint8_t *occl, F4 *L, const F4 *P, uint32_t cap) {
       if (!n) return;
       Scope sc_(this);
       launchTraceAny(tcfg, stream, q, cnt, n, sc, o, d, occl, L, P, cap);
    }
-#endif
    void traceStats(uint32_t n, const DScene *sc, const F4 *o, const F4 *d, F4 *hit, uint32_t *nodes, uint32_t *prims) {
       if (n) launchTraceStats(tcfg, stream, n, sc, o, d, hit, nodes, prims);
    }

@@ -270,19 +270,11 @@ struct Pipeline {
 #undef BL_SHADE
                launches++;
             }
-#ifdef BL_FUSE_RESOLVE   // experiment: the any-hit kernel resolves the NEE contribution itself (trace_kernels.cuh)
+            // shadow rays: the any-hit kernel resolves the NEE contribution itself (Scene.hs:64; trace_kernels.cuh "fused NEE resolve")
             be.tag(BLINGCU_KC_TRACE_ANY); be.traceAnyFused(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl, ps.L, ps.PS, cap);
             launches++;
-#else
-            be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl);
-            launches++;
-#endif
             if (hasInfinite && !hasBox) { be.traceAny(ps.qMisAny, ps.counters + C_MISANY, bound, dscene, ps.miO, ps.miD, ps.occlM); launches++; }
             if (hasArea || (hasInfinite && hasBox)) { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, bound, dscene, ps.miO, ps.miD, ps.mihit); launches++; }
-#ifndef BL_FUSE_RESOLVE
-            be.tag(BLINGCU_KC_RESOLVE); be.runQueue(ResolveShadowBody{ps}, ps.qShadow, ps.counters + C_SHADOW, bound);
-            launches++;
-#endif
             be.tag(BLINGCU_KC_RESOLVE);
             if (hasArea || (hasInfinite && hasBox)) { be.runQueue(ResolveMisBody{dscene, ps}, ps.qMis, ps.counters + C_MIS, bound); launches++; }
             if (hasInfinite && !hasBox) { be.runQueue(ResolveMisAnyBody{dscene, ps}, ps.qMisAny, ps.counters + C_MISANY, bound); launches++; }

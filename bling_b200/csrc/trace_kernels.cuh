@@ -111,20 +111,15 @@ __device__ __forceinline__ int ldsIf(uint32_t addr, int old, bool p) {   // pred
    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q ld.shared.b32 %0, [%1]; }" : "+r"(v) : "r"(addr), "r"((int)p) : "memory");
    return v;
 }
-// Experiment BL_FUSE_RESOLVE (tools/scene_breakdown.py A/B, profiles/r01_trace_experiments.md): the any-hit kernel adds the
-// pending NEE contribution of an UNOCCLUDED shadow ray to the path's radiance when it retires the ray, instead of writing an
-// occlusion flag for a separate resolve launch (ResolveShadowBody). Off in the product build.
-#ifdef BL_FUSE_RESOLVE
-#define BL_FUSE_PARAMS , F4 *__restrict__ fuseL, const F4 *__restrict__ fuseP, uint32_t fuseCap
-#define BL_FUSE_ARGS(L, P, cap) , L, P, cap
-#else
-#define BL_FUSE_PARAMS
-#define BL_FUSE_ARGS(L, P, cap)
-#endif
+// Fused NEE resolve (any-hit instantiation, fuseL != null): an UNOCCLUDED shadow ray adds its pending contribution to the path's
+// radiance when the kernel retires the ray (`L += pending`, one float4 quarter at a time; the retire path is cold and the
+// traversal registers are dead there: still 56 registers), instead of writing an occlusion flag for a separate resolve launch.
+// Same arithmetic in the same order as ResolveShadowBody: films are bit-identical; +1.4 .. 2.9 % on the named scenes
+// (profiles/r01_trace_experiments.md).
 template <bool ANY>
 __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLOCKS) kTracePersistent(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
                                                                  const DScene *__restrict__ sc, const F4 *__restrict__ O, const F4 *__restrict__ D,
-                                                                 F4 *__restrict__ hit, uint8_t *__restrict__ occl, uint32_t *__restrict__ work BL_FUSE_PARAMS) {
+                                                                 F4 *__restrict__ hit, uint8_t *__restrict__ occl, uint32_t *__restrict__ work, F4 *__restrict__ fuseL, const F4 *__restrict__ fuseP, uint32_t fuseCap) {
    extern __shared__ int sstack[];            // [level][TR_THREADS]: conflict-free, one column per thread
    const unsigned FULL = 0xffffffffu;
    const uint32_t total = cnt ? *cnt : n;
@@ -225,7 +220,6 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
       li = pop ? 0 : li;
       if (pop && !more) {
          if (ANY) {
-#ifdef BL_FUSE_RESOLVE
             if (fuseL) {   // L += pending, one quarter (float4) at a time
                for (int qq = 0; qq < 4; ++qq) {
                   const size_t at = (size_t)qq * fuseCap + slot;
@@ -233,9 +227,7 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
                   l.x += p_.x; l.y += p_.y; l.z += p_.z; l.w += p_.w;
                   fuseL[at] = l;
                }
-            } else
-#endif
-            occl[slot] = 0;
+            } else occl[slot] = 0;
          }
          cur = EMPTY;
       }
@@ -256,7 +248,7 @@ static inline void launchTraceNearest(TraceConfig &cfg, cudaStream_t st, const u
    if (cfg.variant == 0) { kTraceNearestSimple<<<traceGrid(cfg, n, 128), 128, 0, st>>>(q, cnt, n, sc, O, D, hit); return; }
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
-   kTracePersistent<false><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter BL_FUSE_ARGS(nullptr, nullptr, 0u));
+   kTracePersistent<false><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter, nullptr, nullptr, 0u);
 
 }
 static inline void launchTraceAny(TraceConfig &cfg, cudaStream_t st, const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc,
@@ -265,8 +257,7 @@ static inline void launchTraceAny(TraceConfig &cfg, cudaStream_t st, const uint3
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
    TraceConfig c9 = cfg; c9.blocksPerSm = cfg.blocksPerSm + 1;
-   kTracePersistent<true><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter BL_FUSE_ARGS(fuseL, fuseP, fuseCap));
-   (void)fuseL; (void)fuseP; (void)fuseCap;
+   kTracePersistent<true><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap);
 
 }
 static inline void launchTraceStats(TraceConfig &cfg, cudaStream_t st, uint32_t n, const DScene *sc, const F4 *O, const F4 *D, F4 *hit, uint32_t *nodes, uint32_t *prims) {

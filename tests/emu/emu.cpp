@@ -37,6 +37,12 @@ struct EmuBackend {
       bl::TraceAnyBody b{sc, o, d, occl};
       if (q) runQueue(b, q, cnt, n); else run(b, n);
    }
+   void traceAnyFused(const uint32_t *q, const uint32_t *cnt, uint32_t n, const bl::DScene *sc, const bl::F4 *o, const bl::F4 *d, uint8_t *occl, bl::F4 *L, const bl::F4 *P, uint32_t cap) {
+      traceAny(q, cnt, n, sc, o, d, occl);
+      bl::PathState ps{}; ps.cap = cap; ps.L = L; ps.PS = const_cast<bl::F4 *>(P); ps.occl = occl;
+      bl::ResolveShadowBody b{ps};
+      if (q) runQueue(b, q, cnt, n); else run(b, n);
+   }
    void traceStats(uint32_t n, const bl::DScene *sc, const bl::F4 *o, const bl::F4 *d, bl::F4 *hit, uint32_t *nodes, uint32_t *prims) {
       for (uint32_t i = 0; i < n; ++i) {
          nodes[i] = 0; prims[i] = 0;
