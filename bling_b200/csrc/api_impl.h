@@ -92,6 +92,7 @@ static thread_local std::string g_createError;
       std::string k(key);                                                                                                        \
       if (k == "batch_samples") { if (v < 1) return BLINGCU_EINVAL; c->p.batchTarget = (uint32_t)v; return 0; }                   \
       if (k == "bvh_leaf") { if (v < 1 || v > 15) return BLINGCU_EINVAL; c->p.maxLeaf = (int)v; return 0; }                       \
+      if (k == "fuse_resolve") { c->p.fuseResolveOpt = v < 0 ? -1 : (v > 0 ? 1 : 0); return 0; }                                  \
       if (c->p.be.setOption(k, v)) return 0;                                                                                     \
       c->p.err = "unknown option " + k;                                                                                          \
       return BLINGCU_EINVAL;                                                                                                     \

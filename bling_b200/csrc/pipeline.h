@@ -270,12 +270,19 @@ struct Pipeline {
 #undef BL_SHADE
                launches++;
             }
-            // shadow rays: the any-hit kernel resolves the NEE contribution itself (Scene.hs:64; trace_kernels.cuh "fused NEE resolve")
-            be.tag(BLINGCU_KC_TRACE_ANY); be.traceAnyFused(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl, ps.L, ps.PS, cap);
+            // shadow rays (Scene.hs:64). Small scenes: the any-hit kernel resolves the NEE contribution itself (trace_kernels.cuh
+            // "fused NEE resolve": one launch and the occlusion-flag round trip less, +1.4 .. 2.9 % on the named scenes). Large
+            // scenes keep the separate resolve launch: there the traversal kernel is the bottleneck and the extra scattered
+            // read-modify-write inside it costs more than the 9 ms stream it replaces (cfg 5: -1.2 %).
+            const bool fuse = fuseResolve();
+            be.tag(BLINGCU_KC_TRACE_ANY);
+            if (fuse) be.traceAnyFused(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl, ps.L, ps.PS, cap);
+            else be.traceAny(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl);
             launches++;
             if (hasInfinite && !hasBox) { be.traceAny(ps.qMisAny, ps.counters + C_MISANY, bound, dscene, ps.miO, ps.miD, ps.occlM); launches++; }
             if (hasArea || (hasInfinite && hasBox)) { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, bound, dscene, ps.miO, ps.miD, ps.mihit); launches++; }
             be.tag(BLINGCU_KC_RESOLVE);
+            if (!fuse) { be.runQueue(ResolveShadowBody{ps}, ps.qShadow, ps.counters + C_SHADOW, bound); launches++; }
             if (hasArea || (hasInfinite && hasBox)) { be.runQueue(ResolveMisBody{dscene, ps}, ps.qMis, ps.counters + C_MIS, bound); launches++; }
             if (hasInfinite && !hasBox) { be.runQueue(ResolveMisAnyBody{dscene, ps}, ps.qMisAny, ps.counters + C_MISANY, bound); launches++; }
          }
@@ -407,6 +414,8 @@ struct Pipeline {
    uint32_t dlHeadroom = 2;
    bool dlOverflowed() { be.sync(); uint32_t f = 0; be.download(&f, ps.counters + C_OVERFLOW, sizeof(f)); return f != 0; }
 
+   int fuseResolveOpt = -1;   // option "fuse_resolve": -1 = by scene size, 0 = never, 1 = always
+   bool fuseResolve() const { return fuseResolveOpt < 0 ? nItems <= (1u << 20) : fuseResolveOpt != 0; }
    bool kindPresent[N_SHADE_KINDS] = {};
    int slotKernel[N_SHADE_KINDS] = {};   // which ShadeHitBody instantiation serves the slot (a shade kind, see shading.h)
    int nSlots = N_PLAIN_SLOTS;           // slots in use: [0, nSlots)

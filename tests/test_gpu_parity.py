@@ -151,6 +151,19 @@ def test_converged_render_vs_golden(ctx, name):
     assert rel_mse(xg, xo) < float(g["relmse_bound"]), (name, rel_mse(xg, xo), float(g["relmse_bound"]))
 
 
+def test_fused_and_separate_nee_resolve_are_bit_identical(ctx):
+    """option "fuse_resolve" (pipeline.h): the any-hit kernel adds an unoccluded shadow ray's pending contribution when it
+    retires the ray, or a separate resolve launch does; same arithmetic in the same order -> identical films."""
+    sc = small(load_scene("cornell-box"), 64, 48, 4, 4)
+    films = []
+    for mode in (0, 1):
+        ctx.set_option("fuse_resolve", mode)
+        ctx.upload_scene(sc); ctx.render_pass(1, 7)
+        films.append(ctx.read_film())
+    ctx.set_option("fuse_resolve", -1)
+    assert np.array_equal(films[0], films[1])
+
+
 def test_slices_compose_and_sharding_full_size(ctx):
     """full cfg-1 size (512x512): pass == union of slices == 2-way shard sum; encode->decode style invariants."""
     sc = load_scene("cornell-box")

@@ -134,6 +134,18 @@ def test_slices_and_batches_compose(name):
     b.film_add_host(fa); assert np.array_equal(b.read_film(), fa)
 
 
+def test_fused_and_separate_nee_resolve_are_bit_identical():
+    """option "fuse_resolve": the any-hit query adds an unoccluded shadow ray's pending contribution itself (small scenes, the
+    default below 2^20 primitives) or a separate resolve launch does (large scenes): same arithmetic, same order."""
+    sc = small(load_scene("zoo"), 40, 28, 4, 4)
+    films = []
+    for mode in (0, 1, -1):
+        e = EmuContext(); e.set_option("fuse_resolve", mode); e.upload_scene(sc); e.render_pass(2, 13)
+        films.append((e.read_film(), e.stats()["kernel_launches"])); e.close()
+    assert np.array_equal(films[0][0], films[1][0]) and np.array_equal(films[1][0], films[2][0])
+    assert films[0][1] > films[1][1] == films[2][1]          # one launch per bounce less when fused; small scene: fused by default
+
+
 def test_edge_scenes_empty_and_unlit():
     """no primitives (every ray escapes to the environment) and no lights (black film, no NEE rays)."""
     from tests.conftest import stripped
