@@ -31,6 +31,30 @@ def test_abi_exports_every_declared_symbol():
 
 
 @pytest.mark.skipif(has_gpu(), reason="checks the no-GPU failure mode")
+def test_ctypes_mirror_matches_the_header_layout():
+    """bling_b200/ir.py mirrors include/blingcu.h by hand: hold every struct's size and every field's offset against what the
+    C compiler computes from the header (tools/abi_layout.py; the same table generates haskell/Layout.hs)."""
+    sys.path.insert(0, str(ROOT / "tools"))
+    import abi_layout
+    lay = abi_layout.layout()
+    mirror = {"blingcu_spectrum": IR.Spectrum, "blingcu_shape": IR.Shape, "blingcu_texture": IR.Texture, "blingcu_image": IR.ImageC,
+              "blingcu_material": IR.Material, "blingcu_light": IR.Light, "blingcu_sunsky": IR.SunSky, "blingcu_envmap": IR.EnvMap,
+              "blingcu_camera": IR.Camera, "blingcu_scene": IR.SceneC, "blingcu_ray": IR.Ray, "blingcu_hit": IR.Hit, "blingcu_stats": IR.Stats}
+    assert set(lay) == set(mirror)
+    import ctypes as C
+    for name, ty in mirror.items():
+        assert C.sizeof(ty) == lay[name]["sizeof"], name
+        fields = {f[0]: getattr(ty, f[0]).offset for f in ty._fields_}
+        assert fields == {k: v for k, v in lay[name].items() if k != "sizeof"}, name
+    hs = (ROOT / "haskell" / "Layout.hs").read_text()
+    assert hs == abi_layout.haskell(lay), "haskell/Layout.hs is stale: python tools/abi_layout.py --haskell"
+    # GHC is absent, so at least: every layout name the Haskell marshalling code uses exists in the generated table
+    defined = set(re.findall(r"^(\w+) ::", hs, flags=re.M))
+    for f in ("SceneIR.hs", "Cuda.hs"):
+        used = set(re.findall(r"\b(off[A-Z]\w+|sizeOf[A-Z]\w+)\b", (ROOT / "haskell" / f).read_text()))
+        assert used <= defined, (f, sorted(used - defined))
+
+
 def test_product_fails_loudly_without_gpu():
     """no CPU fallback: creating a context without a device is an error, not a silent CPU path."""
     with pytest.raises(api.BlingCuError) as e:
