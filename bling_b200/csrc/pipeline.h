@@ -66,7 +66,8 @@ struct Pipeline {
       if (ir->nu <= 0 || ir->nv <= 0) return fail(BLINGCU_EINVAL, "bad sampler");
       if (ir->max_depth < 0 || ir->max_depth > 254) return fail(BLINGCU_EINVAL, "max_depth out of range");
       if (ir->integrator_kind < BLINGCU_INTEGRATOR_PATH || ir->integrator_kind > BLINGCU_INTEGRATOR_NORMALS) return fail(BLINGCU_EINVAL, "unknown integrator");
-      if (ir->integrator_kind == BLINGCU_INTEGRATOR_DIRECT && ir->max_depth > 24) return fail(BLINGCU_EINVAL, "direct lighting: max_depth out of range");
+      // maxDepth 0 has no meaning there: `cont` stops at d == md with d starting at 1 (DirectLighting.hs:47-49), i.e. never
+      if (ir->integrator_kind == BLINGCU_INTEGRATOR_DIRECT && (ir->max_depth < 1 || ir->max_depth > 24)) return fail(BLINGCU_EINVAL, "direct lighting: max_depth out of range");
       size_t nt = (size_t)ir->n_triangles, ns = ir->n_shapes, nprim = nt + ns;
       // ---- validate indices
       for (size_t i = 0; i < nt; ++i) if (ir->tri_material[i] < 0 || (uint32_t)ir->tri_material[i] >= ir->n_materials) return fail(BLINGCU_EINVAL, "triangle material out of range");

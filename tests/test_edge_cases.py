@@ -1,0 +1,143 @@
+"""Edge cases of the hot path, kernel bodies (CPU emulator) against the oracle: degenerate and duplicated geometry, extreme
+ray ranges, far-away geometry, tiny films under wide filters, non-square strata (Q9), depth-0 integrators."""
+import copy
+
+import numpy as np
+import pytest
+
+from bling_b200 import ir as IR
+from oracle.oracle_py import Oracle
+from tests.conftest import compare_hits, load_scene, random_rays, small
+from tests.emu.emu_py import EmuContext
+
+
+def _tri_scene(verts, like="cornell-box"):
+    """the camera / film / lights of a fixture with its triangles replaced by `verts` (n, 9); shapes dropped"""
+    base = small(load_scene(like), 24, 18, 2, 2)
+    sc = copy.copy(base)
+    sc.tri_verts = np.asarray(verts, np.float32).reshape(-1, 9)
+    n = len(sc.tri_verts)
+    sc.tri_uvs = np.tile(np.array([0, 0, 1, 0, 1, 1], np.float32), (n, 1))
+    sc.tri_material = np.zeros(n, np.int32); sc.tri_normals = None; sc.tri_prim_id = None; sc.tri_prim_id_base = 0
+    sc.shapes = []
+    sc.lights = [l for l in base.lights if l.kind != IR.LIGHT_AREA]
+    return sc
+
+
+def _traversal_parity(sc, rays):
+    o = Oracle(sc); e = EmuContext(); e.upload_scene(sc)
+    ho, hb = o.trace_nearest(rays, mode="kd"), o.trace_nearest(rays, mode="brute")   # the reference's kd-tree, and brute force
+    assert compare_hits(ho, hb)[1] == 0
+    he = e.trace_nearest(rays)
+    oo, oe = o.trace_occluded(rays, mode="brute"), e.trace_occluded(rays)
+    e.close()
+    ties, bad = compare_hits(he, hb)
+    assert bad == 0, (ties, bad)
+    hit = hb["prim"] >= 0
+    assert np.array_equal(he["t"][hit & (he["prim"] == hb["prim"])], hb["t"][hit & (he["prim"] == hb["prim"])])   # bit-exact t
+    assert np.array_equal(oe.astype(bool), oo.astype(bool))
+    return ho, he, ties
+
+
+def test_degenerate_and_duplicate_triangles():
+    rng = np.random.default_rng(3)
+    good = (rng.random((40, 3, 3)) * 4 - 2).astype(np.float32)
+    point = np.repeat(rng.random((5, 1, 3)).astype(np.float32), 3, axis=1)               # all three vertices equal
+    a = rng.random((5, 3)).astype(np.float32); d = rng.random((5, 3)).astype(np.float32)
+    line = np.stack([a, a + d, a + 2 * d], 1)                                             # collinear
+    dup = np.concatenate([good[:6], good[:6]])                                            # exact duplicates: t-ties
+    sc = _tri_scene(np.concatenate([good, point, line, dup]).reshape(-1, 9))
+    rays = random_rays(sc, 4000, 1)
+    ho, he, ties = _traversal_parity(sc, rays)
+    n_good = 40
+    hit = he["prim"] >= 0
+    assert hit.sum() > 200
+    assert not np.isin(he["prim"][hit], np.arange(n_good, n_good + 10)).any()             # zero-area triangles are never hit
+
+
+def test_ray_ranges_that_exclude_everything():
+    sc = small(load_scene("zoo"), 24, 18, 2, 2)
+    rays = random_rays(sc, 3000, 2)
+    e = EmuContext(); e.upload_scene(sc); o = Oracle(sc)
+    full = e.trace_nearest(rays)
+    for name, tmin, tmax in (("inverted", 5.0, 1.0), ("empty", 0.0, 0.0), ("behind the far hit", 1e7, np.inf)):
+        r = rays.copy(); r["tmin"] = tmin; r["tmax"] = tmax
+        he, hb = e.trace_nearest(r), o.trace_nearest(r, mode="brute")
+        assert (he["prim"] < 0).all() and (hb["prim"] < 0).all(), name
+        assert not e.trace_occluded(r).any() and not o.trace_occluded(r).any(), name
+    # a range that ends exactly at the hit keeps it (t > tmax rejects, t == tmax does not: TriangleMesh.hs:181, Shape.hs)
+    hit = full["prim"] >= 0
+    r = rays[hit].copy(); r["tmin"] = 0; r["tmax"] = full["t"][hit]
+    he, hb = e.trace_nearest(r), o.trace_nearest(r, mode="brute")
+    ties, bad = compare_hits(he, hb)
+    assert bad == 0 and (he["prim"] >= 0).mean() > 0.95
+    e.close()
+
+
+def test_far_away_and_tiny_geometry_keep_bit_exact_hits():
+    rng = np.random.default_rng(5)
+    base = (rng.random((60, 3, 3)) * 2 - 1).astype(np.float32)
+    for offset, scale in ((1.0e6, 1.0), (0.0, 1.0e-4), (-3.0e5, 50.0)):
+        sc = _tri_scene((base * scale + offset).reshape(-1, 9))
+        rays = np.zeros(2000, IR.RAY_DTYPE)
+        c = rng.random((2000, 3)).astype(np.float32) * 2 - 1
+        d = rng.normal(size=(2000, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        rays["o"] = (c * scale * 3 + offset).astype(np.float32); rays["d"] = d.astype(np.float32)
+        rays["tmin"] = 0; rays["tmax"] = np.inf
+        _traversal_parity(sc, rays)
+
+
+@pytest.mark.parametrize("w,h,filt", [(1, 1, "wide"), (3, 2, "box"), (2, 5, "wide")])
+def test_tiny_films(w, h, filt):
+    """films smaller than the filter footprint: the sample extent is mostly apron (Image.hs:162-168), every sample reaches
+    every pixel, tile images clip on all sides (Q10)"""
+    sc = small(load_scene("cornell-box" if filt == "wide" else "ducky"), w, h, 3, 3)
+    if filt == "box": sc.filter_w = sc.filter_h = 0.5; sc.filter_table = np.ones(256, np.float32)
+    o = Oracle(sc); e = EmuContext(); e.upload_scene(sc)
+    assert o.sample_extent() == e.sample_extent()
+    o.render_pass(1, 3, threads=2); e.render_pass(1, 3)
+    fo, fe = o.read_film(), e.read_film(); e.close()
+    assert fo.shape == (h, w, 4)
+    assert np.allclose(fo[..., 0], fe[..., 0], rtol=1e-5, atol=1e-6)                       # filter weights: same sample positions
+    assert np.allclose(fo, fe, rtol=2e-3, atol=1e-5)
+
+
+def test_non_square_strata_follow_q9():
+    """Sampling.hs:168-171 derives BOTH jitter cells from `quotRem i nu` with du = 1 / nu, dv = 1 / nv: with nu != nv the image
+    samples do not tile the pixel. Reproduced, not fixed: positions must equal the oracle's exactly."""
+    sc = small(load_scene("glass-torus"), 12, 9, 3, 5)
+    o = Oracle(sc); e = EmuContext(); e.upload_scene(sc)
+    x0, x1, y0, y1 = o.sample_extent()
+    px = np.repeat(np.arange(x0, x1 + 1), 15); py = np.full_like(px, 2); s = np.tile(np.arange(15), x1 - x0 + 1)
+    Lo, xyo = o.render_samples(1, 4, px, py, s); Le, xye = e.render_samples(1, 4, px, py, s); e.close()
+    assert np.array_equal(xyo, xye)
+    fx = xyo[:, 0] - px                                                                    # offsets inside the pixel
+    assert fx.min() >= 0 and fx.max() <= 1.0 + 1e-6                                        # x: cells of width 1/3 cover [0, 1]
+    fy = xyo[:, 1] - py
+    assert fy.min() >= 0 and fy.max() <= 1.0 + 1e-6
+    rel = np.abs(Lo - Le).max(1) / (np.abs(Lo).max(1) + 1e-6)
+    assert (rel < 1e-4).mean() > 0.99
+
+
+@pytest.mark.parametrize("name", ["sun-sky", "direct"])
+def test_depth_zero_and_one(name):
+    """maxDepth 0: the path integrator returns at the first hit (`depth == md`, Path.hs:51) and only adds the environment on a
+    miss. Direct lighting has no maxDepth 0: `cont` compares d + 1 with md (DirectLighting.hs:47-49), so 0 would never stop;
+    upload rejects it. maxDepth 1 = one shaded vertex, no continuation."""
+    from bling_b200.api import BlingCuError
+    for md in (0, 1):
+        sc = small(load_scene(name), 30, 20, 2, 2); sc.max_depth = md; sc.sample_depth = min(sc.sample_depth, 1)
+        if sc.integrator_kind == IR.INTEGRATOR_DIRECT and md == 0:
+            e = EmuContext()
+            with pytest.raises(BlingCuError): e.upload_scene(sc)
+            e.close(); continue
+        o = Oracle(sc); e = EmuContext(); e.upload_scene(sc)
+        x0, x1, y0, y1 = o.sample_extent()
+        rng = np.random.default_rng(8)
+        px, py, s = rng.integers(x0, x1 + 1, 800), rng.integers(y0, y1 + 1, 800), rng.integers(0, 4, 800)
+        Lo, _ = o.render_samples(1, 6, px, py, s); Le, _ = e.render_samples(1, 6, px, py, s)
+        st = e.stats(); e.close()
+        rel = np.abs(Lo - Le).max(1) / (np.abs(Lo).max(1) + 1e-6)
+        assert (rel < 1e-4).mean() > 0.995, (name, md, rel.max())
+        if sc.integrator_kind == IR.INTEGRATOR_PATH and md == 0:
+            assert st["rays_shadow"] == 0 and st["rays_extension"] == 0                    # nothing is shaded at depth == md
