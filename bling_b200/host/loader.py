@@ -438,10 +438,69 @@ class Loader:
                 n = tk.qstring(); tk.expect("{"); mmap[n] = self.p_material_body(tk); tk.expect("}")
             tk.expect("}")
             out = [self.wavefront(st.base / fname, mmap)]
+        elif t == "bezier":                  # PrimitiveParser.hs:32-37 -> tesselateBezier (Primitive/Bezier.hs:80-105)
+            subdivs = tk.named_int("subdivs"); patches = []
+            while tk.peek() == "p":
+                tk.next(); tk.expect("{"); xs = []
+                while tk.peek() != "}":
+                    xs.append(tk.flt())
+                    if tk.peek() == ",": tk.next()
+                tk.expect("}")
+                if len(xs) != 48: raise ValueError("error parsing bezier patch: must give 48 values per patch")
+                patches.append(np.array(xs, F))
+            out = [self.tesselate_bezier(subdivs, patches)]
         else:
             raise NotImplementedError(f"primitive {t} (outside SURVEY §8)")
         tk.expect("}")
         return out
+
+    def tesselate_bezier(self, subdivs: int, patches) -> PrimRec:
+        """Primitive/Bezier.hs:26-105 in float32: (subdivs+1)^2 vertices per patch with p, the normal dpdu x dpdv (not normalised)
+        and uv = (i, j) * step; two triangles (v00 v10 v01) (v10 v11 v01) per cell; then mkTriangleMesh (TriangleMesh.hs:39-60):
+        points through o2w, normals through transNormal o2w."""
+        st = self.st
+        step = F(1) / F(subdivs)
+        us = [F(F(i) * step) for i in range(subdivs + 1)]
+
+        def bern(u):
+            i = F(1) - u
+            return [F(F(F(1) * i) * i) * i, F(F(F(3) * u) * i) * i, F(F(F(3) * u) * u) * i, F(F(F(1) * u) * u) * u]
+
+        def dbern(u):
+            i = F(1) - u
+            return [F(F(3) * -F(i * i)), F(F(3) * F(F(i * i) - F(F(F(2) * u) * i))), F(F(3) * F(F(F(F(2) * u) * i) - F(u * u))), F(F(3) * F(u * u))]
+
+        B, D = [bern(u) for u in us], [dbern(u) for u in us]
+        vstride = subdivs + 1
+        verts, uvs, nrms = [], [], []
+        for ctrl in patches:
+            def ev(bj, bi):                  # s o = sum [c (i*12 + j*3 + o) * bj j * bi i | i <- [0..3], j <- [0..3]]
+                out = np.zeros(3, F)
+                for o in range(3):
+                    acc = F(0)
+                    for i in range(4):
+                        for j in range(4): acc = F(acc + F(F(ctrl[i * 12 + j * 3 + o] * bj[j]) * bi[i]))
+                    out[o] = acc
+                return out
+            P = np.zeros((vstride * vstride, 3), F); N = np.zeros_like(P); UV = np.zeros((vstride * vstride, 2), F)
+            for i in range(vstride):         # evalv (bernstein (i * step)) ...: the OUTER index feeds `bu`
+                for j in range(vstride):
+                    k = i * vstride + j
+                    pt, dpdu, dpdv = ev(B[i], B[j]), ev(D[i], B[j]), ev(B[i], D[j])
+                    P[k] = T.trans_point(st.transform, pt)
+                    n = np.array([F(dpdu[1] * dpdv[2]) - F(dpdu[2] * dpdv[1]), -(F(dpdu[0] * dpdv[2]) - F(dpdu[2] * dpdv[0])),
+                                  F(dpdu[0] * dpdv[1]) - F(dpdu[1] * dpdv[0])], F)   # cross (Math.hs:345-348)
+                    N[k] = T.trans_normal(st.transform, n)
+                    UV[k] = (us[i], us[j])
+            for i in range(subdivs):
+                for j in range(subdivs):
+                    v00, v10 = i * vstride + j, (i + 1) * vstride + j
+                    v01, v11 = i * vstride + j + 1, (i + 1) * vstride + j + 1
+                    for tri in ((v00, v10, v01), (v10, v11, v01)):
+                        verts.append(P[list(tri)].ravel()); nrms.append(N[list(tri)].ravel()); uvs.append(UV[list(tri)].ravel())
+        n = len(verts)
+        return PrimRec("tris", verts=np.array(verts, F).reshape(n, 9), uvs=np.array(uvs, F).reshape(n, 6),
+                       normals=np.array(nrms, F).reshape(n, 9), mats=np.full(n, st.material, np.int32))
 
     def wavefront(self, path: Path, mmap: dict) -> PrimRec:   # IO/WaveFront.hs
         pts, nrm, uvs, faces, mtls = [], [], [], [], []

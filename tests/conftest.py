@@ -16,6 +16,8 @@ SCENES = ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environ
 # sampler kind of SURVEY.md §8a that the config scenes do not reach
 COVERAGE = ["zoo", "envcam", "smooth", "extras", "textures", "direct", "blackbody-emission"]
 ALL_SCENES = SCENES + COVERAGE
+# fixtures checked on the kernel-body emulator only (added after the round's GPU budget was spent)
+EMU_ONLY = ["gumbo"]
 
 
 def pytest_configure(config):

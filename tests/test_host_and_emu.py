@@ -14,7 +14,7 @@ import pytest
 from bling_b200 import api, ir as IR
 from bling_b200.renderer import CudaRenderer, PassDone, RenderJob, shard_range
 from oracle.oracle_py import Oracle
-from tests.conftest import ALL_SCENES, ROOT, SCENES, camera_rays, compare_hits, has_gpu, load_scene, random_rays, small
+from tests.conftest import ALL_SCENES, EMU_ONLY, ROOT, SCENES, camera_rays, compare_hits, has_gpu, load_scene, random_rays, small
 from tests.emu.emu_py import EmuContext
 
 
@@ -72,7 +72,7 @@ def test_ir_roundtrip(tmp_path):
     assert a.n_shapes == b.n_shapes == 7 and a.width == 1920
 
 
-@pytest.mark.parametrize("name", ALL_SCENES)
+@pytest.mark.parametrize("name", ALL_SCENES + EMU_ONLY)
 def test_emulated_traversal_matches_oracle(name):
     """parity (a) for the traversal BODY + BVH builder: prim id exact except measured t-ties, t within 1e-5."""
     sc = load_scene(name)
@@ -91,7 +91,7 @@ def test_emulated_traversal_matches_oracle(name):
     assert nodes.max() > 0 and prims.sum() > 0
 
 
-@pytest.mark.parametrize("name", ALL_SCENES)
+@pytest.mark.parametrize("name", ALL_SCENES + EMU_ONLY)
 def test_emulated_path_samples_match_oracle(name):
     """per-sample radiance of the wavefront bodies == oracle's recursive nextVertex on the same sampler SPEC."""
     sc = small(load_scene(name), 40, 30, 4, 4)

@@ -37,15 +37,19 @@ CONFIGS = {
     "environment": dict(file="environment.bling", image_size=(1920, 1080), env_files={"*": synthetic_hdr()}),
     # the one example that selects the direct-lighting integrator; parses as shipped (15 blackbody emitters)
     "blackbody-emission": dict(file="blackbody-emission.bling"),
+    # SURVEY §8(f)2 "mesh shading normals (bezier ...)": 102 Bezier patches, subdivs 16 -> 26 112 smooth-shaded triangles, thin lens.
+    # Stale syntax: `rgbeFile` is not a map type of LightParser.hs (-> `file`); the HDR is a missing blob -> synthetic map
+    "gumbo": dict(file="gumbo.bling", fixups=[(r"rgbeFile", "file")], env_files={"*": synthetic_hdr()}),
 }
 
 # this repository's own coverage scenes (tests/golden/scenes_src/*.bling), flattened by the same loader
 OWN = ["zoo", "envcam", "smooth", "extras", "textures", "direct"]
 
 
-def main():
+def main(only=()):
     OUT.mkdir(parents=True, exist_ok=True)
     for name, cfg in CONFIGS.items():
+        if only and name not in only: continue
         cfg = dict(cfg)
         ir = load_scene(EX / cfg.pop("file"), name=name, **cfg)
         ir.save(OUT / f"{name}.npz")
@@ -64,4 +68,4 @@ def own():
 
 if __name__ == "__main__":
     if sys.argv[1:] == ["own"]: own()
-    else: main()
+    else: main(sys.argv[1:])          # no arguments: every fixture; else the named ones
