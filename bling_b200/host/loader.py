@@ -438,6 +438,11 @@ class Loader:
                 n = tk.qstring(); tk.expect("{"); mmap[n] = self.p_material_body(tk); tk.expect("}")
             tk.expect("}")
             out = [self.wavefront(st.base / fname, mmap)]
+        elif t == "heightMap":               # PrimitiveParser.hs:39-45 -> heightMap elev (ns, nt) mat tr (Primitive/Heightmap.hs:22-49)
+            ns, nt = tk.integ(), tk.integ()
+            elev = self.p_scalar_map2d(tk)
+            tr = self.p_transform(tk)         # its OWN transform block, not the current transform
+            out = [self.height_map(elev, ns, nt, tr)]
         elif t == "bezier":                  # PrimitiveParser.hs:32-37 -> tesselateBezier (Primitive/Bezier.hs:80-105)
             subdivs = tk.named_int("subdivs"); patches = []
             while tk.peek() == "p":
@@ -453,6 +458,44 @@ class Loader:
             raise NotImplementedError(f"primitive {t} (outside SURVEY §8)")
         tk.expect("}")
         return out
+
+    def p_scalar_map2d(self, tk: Tokens):      # pScalarMap2d (MaterialParser.hs:239-251): a function (x, y) -> Float
+        from . import noise
+        tk.expect("{"); tp = tk.next()
+        if tp == "fbm":                        # texMap3dTo2d (fbm octaves omega) z
+            z = tk.flt(); octaves = tk.named_int("octaves"); omega = tk.named_float("omega")
+            fn = lambda x, y: noise.fbm(octaves, omega, (F(x), F(y), F(z)))
+        elif tp == "scale":
+            f = tk.flt(); inner = self.p_scalar_map2d(tk)
+            fn = lambda x, y: F(F(f) * inner(x, y))
+        else: raise ValueError(f"unknown scalar map type{tp}")
+        tk.expect("}")
+        return fn
+
+    def height_map(self, elev, ns: int, nt: int, tr: T.Transform) -> PrimRec:
+        """Primitive/Heightmap.hs:22-49 in float32: an ns x nt grid over [0,1]^2, two triangles per cell, shading normals from
+        central differences of the elevation, then mkTriangleMesh with the primitive's own transform."""
+        fns, fnt = F(ns), F(nt)
+        coords = [(F(F(x) / F(fns - F(1))), F(F(z) / F(fnt - F(1)))) for z in range(nt) for x in range(ns)]
+        ex, ez = F(F(1) / fns), F(F(1) / fnt)
+        P = np.zeros((ns * nt, 3), F); N = np.zeros_like(P); UV = np.zeros((ns * nt, 2), F)
+        for k, (x, z) in enumerate(coords):
+            P[k] = T.trans_point(tr, np.array([x, elev(x, z), z], F))
+            dx = F(elev(F(x - ex), z) - elev(F(x + ex), z)); dz = F(elev(x, F(z - ez)) - elev(x, F(z + ez)))
+            v = np.array([dx, F(ex + ez), dz], F)
+            l2 = F(F(F(v[0] * v[0]) + F(v[1] * v[1])) + F(v[2] * v[2]))
+            n = -(v * F(F(1) / F(np.sqrt(l2)))) if l2 != 0 else -np.array([0, 1, 0], F)     # normalize (Math.hs:358-362)
+            N[k] = T.trans_normal(tr, n.astype(F))
+            UV[k] = (F(x / F(fns - F(1))), F(z / F(fns - F(1))))                             # sic: both by fns - 1
+        vert = lambda x, y: x + y * ns
+        verts, uvs, nrms = [], [], []
+        for y in range(nt - 1):
+            for x in range(ns - 1):
+                for tri in ((vert(x, y), vert(x + 1, y), vert(x + 1, y + 1)), (vert(x, y), vert(x + 1, y + 1), vert(x, y + 1))):
+                    verts.append(P[list(tri)].ravel()); nrms.append(N[list(tri)].ravel()); uvs.append(UV[list(tri)].ravel())
+        n = len(verts)
+        return PrimRec("tris", verts=np.array(verts, F).reshape(n, 9), uvs=np.array(uvs, F).reshape(n, 6),
+                       normals=np.array(nrms, F).reshape(n, 9), mats=np.full(n, self.st.material, np.int32))
 
     def tesselate_bezier(self, subdivs: int, patches) -> PrimRec:
         """Primitive/Bezier.hs:26-105 in float32: (subdivs+1)^2 vertices per patch with p, the normal dpdu x dpdv (not normalised)

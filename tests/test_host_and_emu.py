@@ -261,3 +261,37 @@ def test_two_rank_sample_sharding_gloo(tmp_path):
     e = EmuContext(); e.upload_scene(sc); e.render_pass(1, 31)
     film1 = e.read_film()
     assert np.abs(film1 - film2).max() <= 1e-5 * np.abs(film1).max()
+
+
+def test_loader_bezier_and_heightmap_meshes(tmp_path):
+    """host side of SURVEY §8(f)2 "mesh shading normals": tesselateBezier (Primitive/Bezier.hs:80-105) and heightMap
+    (Primitive/Heightmap.hs:22-49) become world-space triangles with per-vertex normals and uvs."""
+    from bling_b200.host.loader import load_scene as parse
+    ctrl = [(x, (x * y) % 3 - 1.0, y) for y in range(4) for x in range(4)]      # 4 x 4 control points, row i = 12 floats
+    txt = ("filter box\nimageSize 16 12\n"
+           "renderer { sampler sampled { sampler { stratified 2 2 } integrator { path maxDepth 3 sampleDepth 1 } } }\n"
+           "camera { perspective fov 40 lensRadius 0 focalDistance 5 }\n"
+           "light { infinite { } l { constant rgbI 1 1 1 } }\n"
+           "transform { translate 10 0 0 }\n"
+           "prim { bezier subdivs 4 p { " + ", ".join(f"{c:g}" for p in ctrl for c in p) + " } }\n"
+           "newTransform { }\n"
+           "prim { heightMap 5 4 { scale 2 { fbm 0.5 octaves 2 omega 0.5 } } { scale 3 1 2 } }\n")
+    f = tmp_path / "m.bling"; f.write_text(txt)
+    sc = parse(f)
+    nb, nh = 4 * 4 * 2, (5 - 1) * (4 - 1) * 2
+    assert len(sc.tri_verts) == nb + nh and sc.tri_normals is not None and sc.tri_normals.shape == (nb + nh, 9)
+    # prims are prepended block by block (RenderJob.hs:49-52): the height map (parsed last) comes first
+    hm, bz = sc.tri_verts[:nh].reshape(-1, 3), sc.tri_verts[nh:].reshape(-1, 3)
+    assert np.allclose(hm[:, [0, 2]].min(0), [0, 0]) and np.allclose(hm[:, [0, 2]].max(0), [3, 2])    # [0,1]^2 scaled by (3, ., 2)
+    assert np.abs(hm[:, 1]).max() <= 2 * 1.5                                                         # |2 * fbm| stays small
+    # a Bezier patch interpolates its corner control points; the primitive was translated by +10 in x
+    corners = np.array([ctrl[0], ctrl[3], ctrl[12], ctrl[15]], np.float32) + np.array([10, 0, 0], np.float32)
+    for c in corners: assert np.abs(bz - c).sum(1).min() < 1e-5
+    assert np.array_equal(sc.tri_uvs[nh], np.array([0, 0, 0.25, 0, 0, 0.25], np.float32))            # (v00, v10, v01), step 1/4
+    n = sc.tri_normals[:nh].reshape(-1, 3)
+    assert np.allclose(np.linalg.norm(n * np.array([3, 1, 2], np.float32), axis=1), 1, atol=1e-4)    # unit normals through transNormal (scale 3 1 2)
+    o = Oracle(sc); e = EmuContext(); e.upload_scene(sc)
+    rays = random_rays(sc, 1500, 4)
+    ties, bad = compare_hits(e.trace_nearest(rays), o.trace_nearest(rays, mode="brute"))
+    assert bad == 0
+    e.close()

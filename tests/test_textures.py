@@ -20,61 +20,9 @@ F = np.float32
 
 
 # ------------------------------------------------------------------------------------------------ pure-Python statement
-def _perm():
-    # the table travels in the oracle source; the kernels get it from upload (pipeline.h). Parsed here from the oracle
-    # header so that this file holds no third copy of the numbers.
-    import re
-    from pathlib import Path
-    src = (Path(__file__).resolve().parent.parent / "oracle" / "oracle_texture.h").read_text()
-    i = src.index("kNoiseL[256] = {"); j = src.index("};", i)
-    l = [int(x) for x in re.findall(r"\d+", src[i + len("kNoiseL[256] = {"):j])]
-    assert sorted(l) == list(range(256))
-    return l + l
-
-
-PERM = _perm()
-
-
-def py_noise_weight(t):
-    t3 = F(F(t * t) * t); t4 = F(t3 * t)
-    return F(F(F(F(6) * t4) * t) - F(F(15) * t4)) + F(F(10) * t3)
-
-
-def py_grad(x, y, z, dx, dy, dz):
-    h = PERM[PERM[PERM[x] + y] + z] & 15
-    up = dx if (h < 8 or h in (12, 13)) else dy
-    vp = dy if (h < 4 or h in (12, 13)) else dz
-    u = -up if h & 1 else up
-    v = -vp if h & 2 else vp
-    return F(u + v)
-
-
-def py_lerp(t, a, b): return F(F(F(F(1) - t) * a) + F(t * b))
-
-
-def py_perlin(x, y, z):
-    x, y, z = F(x), F(y), F(z)
-    ixp, iyp, izp = math.floor(x), math.floor(y), math.floor(z)
-    dx, dy, dz = F(x - F(ixp)), F(y - F(iyp)), F(z - F(izp))
-    ix, iy, iz = ixp & 255, iyp & 255, izp & 255
-    o = F(1)
-    w = {}
-    for a in (0, 1):
-        for b in (0, 1):
-            for c in (0, 1):
-                w[a, b, c] = py_grad(ix + a, iy + b, iz + c, F(dx - o) if a else dx, F(dy - o) if b else dy, F(dz - o) if c else dz)
-    wx, wy, wz = py_noise_weight(dx), py_noise_weight(dy), py_noise_weight(dz)
-    x00, x10 = py_lerp(wx, w[0, 0, 0], w[1, 0, 0]), py_lerp(wx, w[0, 1, 0], w[1, 1, 0])
-    x01, x11 = py_lerp(wx, w[0, 0, 1], w[1, 0, 1]), py_lerp(wx, w[0, 1, 1], w[1, 1, 1])
-    return py_lerp(wz, py_lerp(wy, x00, x10), py_lerp(wy, x01, x11))
-
-
-def py_fbm(octaves, omega, p):
-    s, l, o = F(0), F(1), F(1)
-    for _ in range(octaves):
-        s = F(s + F(o * py_perlin(F(p[0] * l), F(p[1] * l), F(p[2] * l))))
-        l = F(F(1.99) * l); o = F(F(omega) * o)
-    return s
+# perlin / fbm: the HOST's float32 statement (bling_b200/host/noise.py, what the stand-in loader builds height maps with);
+# cellNoise: below, with Python big integers standing for Haskell's 64-bit Int
+from bling_b200.host.noise import fbm as py_fbm, perlin3d as py_perlin  # noqa: E402
 
 
 def _wrap64(v):   # Haskell Int arithmetic wraps at 64 bits (two's complement)

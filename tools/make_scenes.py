@@ -39,6 +39,9 @@ CONFIGS = {
     "blackbody-emission": dict(file="blackbody-emission.bling"),
     # SURVEY §8(f)2 "mesh shading normals (bezier ...)": 102 Bezier patches, subdivs 16 -> 26 112 smooth-shaded triangles, thin lens.
     # Stale syntax: `rgbeFile` is not a map type of LightParser.hs (-> `file`); the HDR is a missing blob -> synthetic map
+    # a height-map mesh (fbm elevation, central-difference shading normals) under `integrator { debug normals }`, `random 4`
+    # sampler; parses as shipped
+    "heightmap": dict(file="heightmap.bling"),
     "gumbo": dict(file="gumbo.bling", fixups=[(r"rgbeFile", "file")], env_files={"*": synthetic_hdr()}),
 }
 
