@@ -39,6 +39,10 @@ CONFIGS = {
     "blackbody-emission": dict(file="blackbody-emission.bling"),
     # SURVEY §8(f)2 "mesh shading normals (bezier ...)": 102 Bezier patches, subdivs 16 -> 26 112 smooth-shaded triangles, thin lens.
     # Stale syntax: `rgbeFile` is not a map type of LightParser.hs (-> `file`); the HDR is a missing blob -> synthetic map
+    # more reference examples that parse as shipped and exercise the widened rows: bump mapping over fbm; cellNoise with its four
+    # distance functions under bump + gradient; substrate with an fbm coating depth; Oren-Nayar and plastic test scenes
+    "bumpmap": dict(file="bumpmap.bling"), "cellnoise": dict(file="cellnoise.bling"), "substrate": dict(file="substrate.bling"),
+    "matte-test": dict(file="matte-test.bling"), "plastic-test": dict(file="plastic-test.bling"),
     # a height-map mesh (fbm elevation, central-difference shading normals) under `integrator { debug normals }`, `random 4`
     # sampler; parses as shipped
     "heightmap": dict(file="heightmap.bling"),
