@@ -17,7 +17,8 @@ SCENES = ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environ
 COVERAGE = ["zoo", "envcam", "smooth", "extras", "textures", "direct", "blackbody-emission"]
 ALL_SCENES = SCENES + COVERAGE
 # fixtures checked on the kernel-body emulator only (added after the round's GPU budget was spent)
-EMU_ONLY = ["gumbo", "heightmap", "bumpmap", "cellnoise", "substrate", "matte-test", "plastic-test"]
+EMU_ONLY = ["gumbo", "heightmap", "bumpmap", "cellnoise", "substrate", "matte-test", "plastic-test",
+            "trans-matte", "cornell-box-specular", "race", "crystal"]
 
 
 def pytest_configure(config):

@@ -43,6 +43,13 @@ CONFIGS = {
     # distance functions under bump + gradient; substrate with an fbm coating depth; Oren-Nayar and plastic test scenes
     "bumpmap": dict(file="bumpmap.bling"), "cellnoise": dict(file="cellnoise.bling"), "substrate": dict(file="substrate.bling"),
     "matte-test": dict(file="matte-test.bling"), "plastic-test": dict(file="plastic-test.bling"),
+    # examples whose LAST renderer line selects another renderer (SPPM / Metropolis): that line dropped, the sampler renderer above
+    # it becomes active, as for cfg 1. trans-matte: translucentMatte; cornell-box-specular: glass + mirror spheres; race: metal + plastic
+    "trans-matte": dict(file="trans-matte.bling", drop_lines=(24,)),
+    "cornell-box-specular": dict(file="cornell-box-specular.bling", drop_lines=(18,)),
+    "race": dict(file="race.bling", drop_lines=(25,)),
+    # blend of two constants by a quasi-crystal pattern; `rgbeFile` is stale syntax and the HDR a missing blob (as gumbo)
+    "crystal": dict(file="crystal.bling", fixups=[(r"rgbeFile", "file")], env_files={"*": synthetic_hdr()}),
     # a height-map mesh (fbm elevation, central-difference shading normals) under `integrator { debug normals }`, `random 4`
     # sampler; parses as shipped
     "heightmap": dict(file="heightmap.bling"),
