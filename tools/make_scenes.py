@@ -50,6 +50,15 @@ CONFIGS = {
     "race": dict(file="race.bling", drop_lines=(25,)),
     # blend of two constants by a quasi-crystal pattern; `rgbeFile` is stale syntax and the HDR a missing blob (as gumbo)
     "crystal": dict(file="crystal.bling", fixups=[(r"rgbeFile", "file")], env_files={"*": synthetic_hdr()}),
+    # stale syntax of older parser versions, rewritten like specular / sun-sky above (metal-test: its last renderer line selects the
+    # light tracer -> dropped): `stratified xSamples n ySamples m`,
+    # `transform { identity ...}` (= newTransform), graphPaper without map{}, `rgbeFile`
+    "shapes": dict(file="shapes.bling", fixups=[(r"stratified xSamples (\d+) ySamples (\d+)", r"stratified \1 \2"),
+                                                 (r"transform \{ identity", "newTransform {")] + RGB_FIX),
+    "geometric-light": dict(file="geometric-light.bling", fixups=[(r"stratified xSamples (\d+) ySamples (\d+)", r"stratified \1 \2"),
+                                                                   (r"graphPaper ([\d.]+)\s+tex1", r"graphPaper \1 map { uv 1 1 0 0 } tex1")] + RGB_FIX),
+    "metal-test": dict(file="metal-test.bling", drop_lines=(20,), fixups=[(r"graphPaper ([\d.]+)\s+tex1", r"graphPaper \1 map { uv 1 1 0 0 } tex1"), (r"rgbeFile", "file")],
+                       env_files={"*": synthetic_hdr()}),
     # a height-map mesh (fbm elevation, central-difference shading normals) under `integrator { debug normals }`, `random 4`
     # sampler; parses as shipped
     "heightmap": dict(file="heightmap.bling"),
