@@ -1,0 +1,124 @@
+"""Randomised differential test: scenes drawn from the whole grammar this path supports (every shape, material, texture, light,
+integrator, sampler and filter kind, random transforms) are written as `.bling` text, flattened by the stand-in loader and run
+through the kernel bodies (CPU emulator) and the oracle; per-sample radiance must agree. Deterministic seeds.
+(This kind of test found the Box `intersects` / `intersect` quirk of DESIGN §4d.)"""
+import numpy as np
+import pytest
+
+from bling_b200.host.loader import load_scene as parse
+from oracle.oracle_py import Oracle
+from tests.emu.emu_py import EmuContext
+
+
+def _rgb(r, kind="rgbR", lo=0.05, hi=0.95):
+    return f"{kind} {r.uniform(lo, hi):.3f} {r.uniform(lo, hi):.3f} {r.uniform(lo, hi):.3f}"
+
+
+def _map3d(r):
+    return f"map {{ identity {{ scale {r.uniform(0.5, 4):.2f} {r.uniform(0.5, 4):.2f} {r.uniform(0.5, 4):.2f} translate {r.uniform(-1, 1):.2f} {r.uniform(-1, 1):.2f} 0 }} }}"
+
+
+def _map2d(r):
+    if r.random() < 0.5: return f"map {{ uv {r.uniform(1, 8):.2f} {r.uniform(1, 8):.2f} {r.random():.2f} {r.random():.2f} }}"
+    return f"map {{ planar {r.uniform(0.2, 2):.2f} 0 0 0 {r.uniform(0.2, 2):.2f} {r.uniform(-1, 1):.2f} {r.random():.2f} {r.random():.2f} }}"
+
+
+def _scalar(r, depth=0):
+    k = r.integers(0, 6 if depth < 2 else 5)
+    if k == 0: return f"constant {r.uniform(0.01, 0.6):.3f}"
+    if k == 1: return f"perlin {_map3d(r)}"
+    if k == 2: return f"fbm octaves {r.integers(1, 4)} omega {r.uniform(0.3, 0.7):.2f} {_map3d(r)}"
+    if k == 3: return f"cellNoise {r.choice(['euclidian', 'euclidian2', 'manhattan', 'chebyshev'])} {_map3d(r)}"
+    if k == 4: return f"crystal octaves {r.integers(2, 8)} {_map2d(r)}"
+    return f"scale {r.uniform(0, 0.3):.3f} {r.uniform(0.05, 0.5):.3f} tex {{ {_scalar(r, depth + 1)} }}"
+
+
+def _spectrum_tex(r, depth=0):
+    k = r.integers(0, 5 if depth < 2 else 1)
+    if k == 0: return f"constant {_rgb(r)}"
+    if k == 1: return f"graphPaper {r.uniform(0.02, 0.2):.2f} {_map2d(r)} tex1 {{ {_spectrum_tex(r, depth + 1)} }} tex2 {{ {_spectrum_tex(r, depth + 1)} }}"
+    if k == 2: return f"checker {r.uniform(0.5, 3):.2f} {r.uniform(0.5, 3):.2f} {r.uniform(0.5, 3):.2f} tex1 {{ {_spectrum_tex(r, depth + 1)} }} tex2 {{ {_spectrum_tex(r, depth + 1)} }}"
+    if k == 3: return f"blend tex1 {{ {_spectrum_tex(r, 2)} }} tex2 {{ {_spectrum_tex(r, 2)} }} f {{ {_scalar(r)} }}"
+    steps = ", ".join(f"{p:.2f} {_rgb(r)}" for p in sorted(r.uniform(-0.2, 1.2, r.integers(1, 4))))
+    return f"gradient f {{ {_scalar(r)} }} steps {{ {steps} }}"
+
+
+def _small(r): return f"constant {r.uniform(0.005, 0.3):.4f}" if r.random() < 0.6 else _scalar(r)
+
+
+def _material(r):
+    k = r.integers(0, 9)
+    bump = f"bumpMap bump {{ scale 0 {r.uniform(0.05, 0.3):.2f} tex {{ {_scalar(r)} }} }} " if r.random() < 0.3 else ""
+    if k == 0: body = f"matte kd {{ {_spectrum_tex(r)} }} sigma {{ {_small(r) if r.random() < 0.5 else 'constant 0'} }}"
+    elif k == 1: body = f"glass ior {{ constant {r.uniform(1.1, 1.8):.2f} }} kr {{ constant {_rgb(r, lo=0.7, hi=1)} }} kt {{ {_spectrum_tex(r, 2)} }}"
+    elif k == 2: body = f"mirror kr {{ {_spectrum_tex(r)} }}"
+    elif k == 3: body = f"plastic kd {{ {_spectrum_tex(r)} }} ks {{ constant {_rgb(r)} }} rough {{ {_small(r)} }}"
+    elif k == 4: body = f"metal eta {{ constant {_rgb(r, lo=0.2, hi=2)} }} k {{ constant {_rgb(r, lo=1, hi=4)} }} rough {{ {_small(r)} }}"
+    elif k == 5: body = f"shinyMetal kr {{ constant {_rgb(r)} }} ks {{ constant {_rgb(r)} }} rough {{ {_small(r)} }}"
+    elif k == 6: body = f"transMatte kr {{ constant {_rgb(r)} }} kt {{ {_spectrum_tex(r, 1)} }} ks {{ constant {r.choice([0, 0.4])} }}"
+    elif k == 7: body = (f"substrate kd {{ {_spectrum_tex(r)} }} ks {{ constant {_rgb(r, hi=0.3)} }} ka {{ constant {_rgb(r)} }} "
+                         f"urough {{ {_small(r)} }} vrough {{ {_small(r)} }} depth {{ constant {r.choice([0, 0.3])} }}")
+    else: body = "blackbody"
+    return f"material {{ {bump}{body} }}"
+
+
+def _shape(r):
+    k = r.integers(0, 5)
+    if k == 0: return f"box pmin {-r.uniform(0.3, 1):.2f} {-r.uniform(0.3, 1):.2f} {-r.uniform(0.3, 1):.2f} pmax {r.uniform(0.3, 1):.2f} {r.uniform(0.3, 1):.2f} {r.uniform(0.3, 1):.2f}"
+    if k == 1: return f"cylinder radius {r.uniform(0.3, 0.9):.2f} zmin {-r.uniform(0.2, 1):.2f} zmax {r.uniform(0.2, 1):.2f} phiMax {r.choice([360, 270, 180])}"
+    if k == 2: return f"disk height {r.uniform(-0.3, 0.3):.2f} radius {r.uniform(0.5, 1.2):.2f} innerRadius {r.choice([0, 0.2])} phiMax {r.choice([360, 200])}"
+    if k == 3: return f"quad {r.uniform(0.4, 1.5):.2f} {r.uniform(0.4, 1.5):.2f}"
+    return f"sphere radius {r.uniform(0.4, 1.1):.2f}"
+
+
+def _transform(r, spread=3.0):
+    return (f"newTransform {{ rotateX {r.uniform(-180, 180):.1f} rotateY {r.uniform(-180, 180):.1f} scale {r.uniform(0.6, 1.5):.2f} {r.uniform(0.6, 1.5):.2f} {r.uniform(0.6, 1.5):.2f} "
+            f"translate {r.uniform(-spread, spread):.2f} {r.uniform(0.3, 2.5):.2f} {r.uniform(-spread, spread):.2f} }}")
+
+
+def random_scene_text(seed):
+    r = np.random.default_rng(seed)
+    md = int(r.integers(1, 6))
+    integ = f"directLighting maxDepth {md}" if r.random() < 0.3 else f"path maxDepth {md} sampleDepth {r.integers(0, 4)}"
+    smp = f"stratified {r.integers(1, 4)} {r.integers(1, 4)}" if r.random() < 0.7 else f"random {r.integers(1, 9)}"
+    filt = r.choice(["box", "triangle 2 2", "mitchell 2 2 0.333333 0.333333", "gauss 2 2 2", "sinc 3 3 3"])
+    out = [f"filter {filt}", "imageSize 40 30",
+           f"renderer {{ sampler sampled {{ sampler {{ {smp} }} integrator {{ {integ} }} }} }}",
+           f"transform {{ lookAt {{ pos {r.uniform(-2, 2):.2f} {r.uniform(2, 5):.2f} {-r.uniform(7, 10):.2f} look 0 1 0 up 0 1 0 }} }}",
+           f"camera {{ perspective fov {r.uniform(35, 60):.1f} lensRadius {r.choice([0, 0, 0.1])} focalDistance 9 }}", "newTransform { }"]
+    if r.random() < 0.8: out.append(f"light {{ infinite {{ rotateX -90 }} l {{ constant {_rgb(r, 'rgbI', 0.1, 1.0)} }} }}")
+    if r.random() < 0.5: out.append(f"light {{ point intensity {_rgb(r, 'rgbI', 5, 40)} position {r.uniform(-4, 4):.2f} {r.uniform(3, 6):.2f} {r.uniform(-4, 4):.2f} }}")
+    if r.random() < 0.5: out.append(f"light {{ directional intensity {_rgb(r, 'rgbI', 0.5, 3)} normal {r.uniform(-1, 1):.2f} 1 {r.uniform(-1, 1):.2f} }}")
+    out += [_material(r), "newTransform { rotateX -90 }", "prim { shape { quad 9 9 } }"]                      # a ground
+    for _ in range(int(r.integers(3, 8))):
+        out.append(_material(r))
+        emit = r.random() < 0.25
+        if emit: out.append(f"emission {{ {_rgb(r, 'rgbI', 3, 25)} }}")
+        out += [_transform(r), f"prim {{ shape {{ {_shape(r)} }} }}"]
+        if emit: out.append("emission { none }")
+    if r.random() < 0.7:                                                                                       # a small mesh
+        vs = r.uniform(-1, 1, (5, 3))
+        out += [_material(r), _transform(r), "prim { mesh vertexCount 5 faceCount 3 " + " ".join(f"v {a:.3f} {b:.3f} {c:.3f}" for a, b, c in vs) + " f 0 1 2 f 1 2 3 4 f 0 2 4 }"]
+    return "\n".join(out) + "\n"
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_random_scene_bodies_match_oracle(seed, tmp_path):
+    f = tmp_path / f"fuzz{seed}.bling"; f.write_text(random_scene_text(seed))
+    try:
+        sc = parse(f)
+    except NotImplementedError as ex:            # e.g. shinyMetal over a computing texture: the loader says so, nothing to compare
+        pytest.skip(str(ex))
+    o = Oracle(sc); e = EmuContext(); e.upload_scene(sc)
+    x0, x1, y0, y1 = o.sample_extent()
+    rng = np.random.default_rng(1000 + seed)
+    n = 700
+    px, py, s = rng.integers(x0, x1 + 1, n), rng.integers(y0, y1 + 1, n), rng.integers(0, sc.spp, n)
+    Lo, xyo = o.render_samples(1, 17 + seed, px, py, s)
+    Le, xye = e.render_samples(1, 17 + seed, px, py, s)
+    e.close()
+    assert np.array_equal(xyo, xye)
+    ok = np.isfinite(Lo).all(1) & np.isfinite(Le).all(1)
+    assert (np.isfinite(Lo).all(1) == np.isfinite(Le).all(1)).mean() > 0.995
+    rel = np.abs(Lo[ok] - Le[ok]).max(1) / (np.abs(Lo[ok]).max(1) + 1e-6)
+    assert (rel < 1e-4).mean() > 0.99, (seed, float((rel < 1e-4).mean()), float(rel.max()))
