@@ -7,6 +7,7 @@ import pytest
 
 from bling_b200.host.loader import load_scene as parse
 from oracle.oracle_py import Oracle
+from tests.conftest import compare_hits, random_rays
 from tests.emu.emu_py import EmuContext
 
 
@@ -110,6 +111,14 @@ def test_random_scene_bodies_match_oracle(seed, tmp_path):
     except NotImplementedError as ex:            # e.g. shinyMetal over a computing texture: the loader says so, nothing to compare
         pytest.skip(str(ex))
     o = Oracle(sc); e = EmuContext(); e.upload_scene(sc)
+    # parity (a) on random rays: primitive id exact except measured t-ties, t bit-exact, occlusion exact
+    rays = random_rays(sc, 1200, seed)
+    he, hb = e.trace_nearest(rays), o.trace_nearest(rays, mode="brute")
+    ties, bad = compare_hits(he, hb)
+    assert bad == 0 and ties <= 3, (ties, bad)
+    same = (he["prim"] == hb["prim"]) & (hb["prim"] >= 0)
+    assert np.array_equal(he["t"][same], hb["t"][same])
+    assert np.array_equal(e.trace_occluded(rays).astype(bool), o.trace_occluded(rays, mode="brute").astype(bool))
     x0, x1, y0, y1 = o.sample_extent()
     rng = np.random.default_rng(1000 + seed)
     n = 700
