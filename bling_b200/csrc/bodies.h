@@ -18,6 +18,7 @@ enum { C_ACTIVE = 0, C_NEXT = 1, C_SHADOW = 2, C_MIS = 3, C_MISANY = 4, C_DROPPE
 enum { N_PLAIN_SLOTS = 1 + BLINGCU_MAT_KINDS, MAX_TEX_SLOTS = 32 - N_PLAIN_SLOTS, N_SHADE_KINDS = 32 };
 enum { S_SAMPLES = 0, S_CAM, S_EXT, S_MIS, S_SHADOW, S_DROPPED, S_MISCULL, S_MISANY, S_EXTCULL, N_STATS = 12 };
 
+#define BL_MIS_NONFINITE 0x40000000   // miInfo.y: the BSDF-MIS weight is not finite (directAtVertex, ResolveMisBodyT)
 struct PathState {
    uint32_t cap;
    F4 *rayO, *rayD;        // extension ray: (o, tmin) (d, tmax)
@@ -26,7 +27,7 @@ struct PathState {
    F4 *shO, *shD, *PS;     // NEE shadow ray + pending contribution (already x T x nLights)
    uint8_t *occl, *occlM;  // shadow-ray / any-hit MIS-ray occlusion flags
    F4 *miO, *miD, *mihit, *PM;   // BSDF-MIS ray, its hit, pending T x f x nLights
-   F2 *miInfo;             // (bsdf pdf, light index bits)
+   F2 *miInfo;             // (bsdf pdf, light index bits | BL_MIS_NONFINITE)
    uint32_t *meta;         // depth | spec << 8
    uint64_t *kp;           // pixel key of the sampler
    uint32_t *sidx;         // sample index within the pixel
@@ -184,12 +185,18 @@ HD void directAtVertex(const DScene &S, const PathState &ps, uint32_t i, const B
          //                      `intersect` (Shape.hs:86-93 vs :235), so there the nearest-hit query is kept;
          //   area light      -> a ray that does not even reach the light's own shape contributes nothing: culled;
          //   delta lights    -> never hit, `le` is black: culled.
+         // All of that holds for a FINITE weight f and pdf. A non-finite one (the glossy sample / eval asymmetry Q7 with extreme
+         // parameters) times a black `le` is NaN in the reference (`sc (le l ray)` on a miss, `sc (intLe ..)` on the back of
+         // the light), and addSample then drops the whole sample (Image.hs:253-256): such a ray is always traced as the
+         // reference's nearest-hit query and carries BL_MIS_NONFINITE to the resolve body, which keeps the black cases.
          BsdfSample bs; sampleBsdfOf<M>(bsdf, wo, bCompU, bD1, bD2, bs);
          if (bs.pdf != 0 && !isBlack(bs.f)) {
             Ray mr; mr.o = p; mr.d = bs.wi; mr.tmin = eps; mr.tmax = BL_INF;
             const bool inf = lt.kind == BLINGCU_LIGHT_INFINITE;
-            bool any = inf && !S.has_box, keep = inf;
-            if (lt.kind == BLINGCU_LIGHT_AREA) {
+            const float bp2 = bs.pdf * bs.pdf;   // powerHeuristic squares the pdf: inf / inf beyond 1.8e19, 0 / 0 below 1e-23 (delta light)
+            const bool nf = sBad(bs.f) || !(bp2 > 0.0f && bp2 <= 3.402823466e38f);
+            bool any = inf && !S.has_box && !nf, keep = inf || nf;
+            if (lt.kind == BLINGCU_LIGHT_AREA && !nf) {
                const blingcu_shape &ls = S.shapes[lt.shape];
                float tl; DG dgl;
                keep = shapeIntersect<false>(ls, transRay(ls.w2o, mr), tl, dgl);
@@ -199,7 +206,7 @@ HD void directAtVertex(const DScene &S, const PathState &ps, uint32_t i, const B
                if (lc > 1) c = sScale(c, lcf);
                storeSpec4(ps.PM, ps.cap, i, loadSpec4(ps.T, ps.cap, i) * c);
                storeRay(ps.miO, ps.miD, i, mr);
-               F2 info; info.x = bs.pdf; info.y = i2f(ln); ps.miInfo[i] = info;
+               F2 info; info.x = bs.pdf; info.y = i2f(nf ? (ln | BL_MIS_NONFINITE) : ln); ps.miInfo[i] = info;
                if (any) qPush(ps.qMisAny, ps.counters + C_MISANY, i);
                else qPush(ps.qMis, ps.counters + C_MIS, i);
             } else cntAdd(ps.counters + C_MISCULL, 1u);
@@ -235,6 +242,10 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118; one instantiation pe
             storeSpec4(ps.L, ps.cap, i, L + BL_T() * loadSpec(el.s.v));
          }
       }
+      // A throughput that is not finite (meta bit 9, set where T is updated below) makes `l + t * lHere` (Path.hs:65) NaN or
+      // infinite at this vertex whatever lHere is -- also where lHere is black and nothing gets added here -- and addSample
+      // drops the sample (Image.hs:253-256): t * 0 reproduces that in exactly the bands the reference loses.
+      if (meta & (1u << 9)) storeSpec4(ps.L, ps.cap, i, loadSpec4(ps.L, ps.cap, i) + BL_T() * sConst(0));
       V3 n = bsdf.cs.n, p = bsdf.p; float eps = sh.eps;
       float lNumU = rnd1D(smp, 1 + 4 * depth);
       float lD1, lD2; rnd2D(smp, 1 + 3 * depth, lD1, lD2);
@@ -255,8 +266,9 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118; one instantiation pe
       if (depth + 1 == S.max_depth && !(s.type & BX_SPECULAR)) { cntAdd(ps.counters + C_EXTCULL, 1u); return; }
       Ray nr; nr.o = p; nr.d = s.wi; nr.tmin = eps; nr.tmax = BL_INF;
       storeRay(ps.rayO, ps.rayD, i, nr);
-      storeSpec4(ps.T, ps.cap, i, sScale(s.f * BL_T(), 1 / pc));   // Path.hs:82: no pdf / cosine factor, the weight carries them
-      ps.meta[i] = (uint32_t)(depth + 1) | (((s.type & BX_SPECULAR) ? 1u : 0u) << 8);
+      Spec tNext = sScale(s.f * BL_T(), 1 / pc);                   // Path.hs:82: no pdf / cosine factor, the weight carries them
+      storeSpec4(ps.T, ps.cap, i, tNext);
+      ps.meta[i] = (uint32_t)(depth + 1) | (((s.type & BX_SPECULAR) ? 1u : 0u) << 8) | ((sBad(tNext) ? 1u : 0u) << 9);
       qPush(qNext, ps.counters + C_NEXT, i);
 #undef BL_T
    }
@@ -289,7 +301,8 @@ struct ResolveMisBodyT {   // Scene.hs:75-82
       const DScene &S = *sc;
       F4 hv = ps.mihit[i];
       F2 info = ps.miInfo[i];
-      int ln = f2i(info.y);
+      const bool nf = (f2i(info.y) & BL_MIS_NONFINITE) != 0;          // non-finite weight: black `le` must still reach L (NaN)
+      int ln = f2i(info.y) & ~BL_MIS_NONFINITE;
       const blingcu_light &l = S.lights[ln];
       Ray ray = loadRay(ps.miO, ps.miD, i);
       const int href = f2i(hv.w);
@@ -300,11 +313,12 @@ struct ResolveMisBodyT {   // Scene.hs:75-82
          if (s.light != ln || l.kind != BLINGCU_LIGHT_AREA) return;   // Eq Light: same area-light id (Light.hs:48-50)
          SurfaceHit sh; DG dgs;
          surfaceAt(S, ray, hv.x, hv.y, hv.z, href, sh, dgs);
-         if (!areaEmits(sh.dgg.n, -ray.d)) return;                   // intLe int (-wi)
-         li = loadSpec(l.s.v);
+         if (areaEmits(sh.dgg.n, -ray.d)) li = loadSpec(l.s.v);       // intLe int (-wi)
+         else if (nf) li = sConst(0);
+         else return;
       } else {
          li = lightLe(S, l, ray.d);
-         if (isBlack(li)) return;
+         if (isBlack(li) && !nf) return;
       }
       float w = powerHeuristic(info.x, lightPdf(S, l, ray.o, ray.d));   // Q3: also for specular samples
       Spec c = sScale(loadSpec4(ps.PM, ps.cap, i) * li, w);
@@ -387,7 +401,11 @@ struct DlShadeBody {
          first = false;
          Ray nr; nr.o = p; nr.d = s.wi; nr.tmin = eps; nr.tmax = BL_INF;
          storeRay(ps.rayO, ps.rayD, j, nr);
-         storeSpec4(ps.T, ps.cap, j, s.f * T);
+         const Spec tNext = s.f * T;
+         storeSpec4(ps.T, ps.cap, j, tNext);
+         // `f * l` (:58) of a weight that is not finite is NaN or infinite whatever the continuation finds (black on a miss
+         // included): poison the camera sample now, in the bands the reference loses (cf. ShadeHitBody, meta bit 9)
+         if (sBad(tNext)) addSpec4Atomic(ps.L, ps.cap, root, tNext * sConst(0));
          ps.meta[j] = (uint32_t)(depth + 1) | (1u << 8);
          qPush(qNext, ps.counters + C_NEXT, j);
       }

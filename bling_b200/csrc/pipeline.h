@@ -276,15 +276,18 @@ struct Pipeline {
             // scenes keep the separate resolve launch: there the traversal kernel is the bottleneck and the extra scattered
             // read-modify-write inside it costs more than the 9 ms stream it replaces (cfg 5: -1.2 %).
             const bool fuse = fuseResolve();
+            // the nearest-hit BSDF-MIS queue serves area lights, infinite lights in scenes with a Box, and -- with ANY light --
+            // the samples whose weight is not finite (bodies.h, BL_MIS_NONFINITE; normally an empty queue: two idle launches)
+            const bool misNearest = hs.n_lights > 0;
             be.tag(BLINGCU_KC_TRACE_ANY);
             if (fuse) be.traceAnyFused(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl, ps.L, ps.PS, cap);
             else be.traceAny(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl);
             launches++;
             if (hasInfinite && !hasBox) { be.traceAny(ps.qMisAny, ps.counters + C_MISANY, bound, dscene, ps.miO, ps.miD, ps.occlM); launches++; }
-            if (hasArea || (hasInfinite && hasBox)) { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, bound, dscene, ps.miO, ps.miD, ps.mihit); launches++; }
+            if (misNearest) { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, bound, dscene, ps.miO, ps.miD, ps.mihit); launches++; }
             be.tag(BLINGCU_KC_RESOLVE);
             if (!fuse) { be.runQueue(ResolveShadowBody{ps}, ps.qShadow, ps.counters + C_SHADOW, bound); launches++; }
-            if (hasArea || (hasInfinite && hasBox)) { be.runQueue(ResolveMisBody{dscene, ps}, ps.qMis, ps.counters + C_MIS, bound); launches++; }
+            if (misNearest) { be.runQueue(ResolveMisBody{dscene, ps}, ps.qMis, ps.counters + C_MIS, bound); launches++; }
             if (hasInfinite && !hasBox) { be.runQueue(ResolveMisAnyBody{dscene, ps}, ps.qMisAny, ps.counters + C_MISANY, bound); launches++; }
          }
          be.tag(BLINGCU_KC_OTHER); be.run(AdvanceBody{ps}, 1); launches++;
@@ -382,6 +385,7 @@ struct Pipeline {
    void bouncesDirect(uint32_t n) {
       uint32_t *qa = ps.qA, *qb = ps.qB;
       const uint32_t bound = ps.cap;   // a queue may hold spawned slots too
+      const bool misNearest = hs.n_lights > 0;   // as in bounces(): also the home of non-finite BSDF-MIS weights
       for (int d = 0; d < hs.max_depth; ++d) {
          be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(qa, ps.counters + C_ACTIVE, bound, dscene, ps.rayO, ps.rayD, ps.hit);
          // the general shade kernel is instruction-fetch bound: one launch per material kind present keeps the code that is
@@ -395,10 +399,10 @@ struct Pipeline {
          be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(ps.qShadow, ps.counters + C_SHADOW, bound, dscene, ps.shO, ps.shD, ps.occl);
          launches += 3;
          if (hasInfinite && !hasBox) { be.traceAny(ps.qMisAny, ps.counters + C_MISANY, bound, dscene, ps.miO, ps.miD, ps.occlM); launches++; }
-         if (hasArea || (hasInfinite && hasBox)) { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, bound, dscene, ps.miO, ps.miD, ps.mihit); launches++; }
+         if (misNearest) { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, bound, dscene, ps.miO, ps.miD, ps.mihit); launches++; }
          be.tag(BLINGCU_KC_RESOLVE); be.runQueue(DlResolveShadowBody{ps, n}, ps.qShadow, ps.counters + C_SHADOW, bound);
          launches++;
-         if (hasArea || (hasInfinite && hasBox)) { be.runQueue(DlResolveMisBody{dscene, ps, n}, ps.qMis, ps.counters + C_MIS, bound); launches++; }
+         if (misNearest) { be.runQueue(DlResolveMisBody{dscene, ps, n}, ps.qMis, ps.counters + C_MIS, bound); launches++; }
          if (hasInfinite && !hasBox) { be.runQueue(DlResolveMisAnyBody{dscene, ps, n}, ps.qMisAny, ps.counters + C_MISANY, bound); launches++; }
          be.tag(BLINGCU_KC_OTHER); be.run(AdvanceBody{ps}, 1); launches++;
          uint32_t *t = qa; qa = qb; qb = t;

@@ -128,21 +128,19 @@ def test_random_scene_bodies_match_oracle(seed, tmp_path):
     # the film too (every filter kind, tile clipping) -- where the scene is well conditioned: random glossy parameters let some
     # scenes reach |L| ~ 1e26 with both signs (the reference's sample / eval asymmetries, Q7), and then the ORDER of the film sum
     # (tiles in the oracle, per-pixel gather in the kernels) decides the digits
+    o.render_pass(1, 3, threads=2); e.render_pass(1, 3)
+    fo, fe = o.read_film(), e.read_film()
+    # A NON-FINITE BSDF weight / MIS weight times a black `le` is NaN in the reference and the sample is dropped
+    # (Image.hs:253-256): the kernels trace such BSDF-MIS rays instead of culling them and poison L where the throughput
+    # is not finite, so the dropped samples agree exactly -- in every scene, also the ill-conditioned ones.
+    assert o.stats()["dropped_samples"] == e.stats()["dropped_samples"]
     if np.isfinite(Lo).all() and np.abs(Lo).max() < 1e3:
-        o.render_pass(1, 3, threads=2); e.render_pass(1, 3)
-        fo, fe = o.read_film(), e.read_film()
-        do, de = o.stats()["dropped_samples"], e.stats()["dropped_samples"]
-        # Known mismatch class: a NON-FINITE BSDF weight times a black `le` is NaN in the reference (the sample is
-        # dropped, Image.hs:253-256), while the kernels never trace a BSDF-MIS ray that cannot reach its light, so the sample
-        # survives as finite. Only scenes with exploding glossy weights have such samples; a handful per 10^4.
-        assert abs(do - de) <= 2e-3 * o.stats()["samples"] + 1
-        if do == de:
-            assert np.allclose(fo[..., 0], fe[..., 0], rtol=1e-4, atol=1e-6)
-            both = np.isfinite(fo).all(-1) & np.isfinite(fe).all(-1) & (np.abs(fo).max(-1) < 1e4)
-            assert both.mean() > 0.97 and np.allclose(fo[both], fe[both], rtol=5e-3, atol=1e-4)
+        assert np.allclose(fo[..., 0], fe[..., 0], rtol=1e-4, atol=1e-6)
+        both = np.isfinite(fo).all(-1) & np.isfinite(fe).all(-1) & (np.abs(fo).max(-1) < 1e4)
+        assert both.mean() > 0.97 and np.allclose(fo[both], fe[both], rtol=5e-3, atol=1e-4)
     e.close()
     assert np.array_equal(xyo, xye)
     ok = np.isfinite(Lo).all(1) & np.isfinite(Le).all(1)
-    assert (np.isfinite(Lo).all(1) == np.isfinite(Le).all(1)).mean() > 0.995
+    assert np.array_equal(np.isfinite(Lo).all(1), np.isfinite(Le).all(1))   # the same samples are lost to NaN / inf
     rel = np.abs(Lo[ok] - Le[ok]).max(1) / (np.abs(Lo[ok]).max(1) + 1e-6)
     assert (rel < 1e-4).mean() > 0.99, (seed, float((rel < 1e-4).mean()), float(rel.max()))
