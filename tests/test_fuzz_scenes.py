@@ -143,4 +143,5 @@ def test_random_scene_bodies_match_oracle(seed, tmp_path):
     ok = np.isfinite(Lo).all(1) & np.isfinite(Le).all(1)
     assert np.array_equal(np.isfinite(Lo).all(1), np.isfinite(Le).all(1))   # the same samples are lost to NaN / inf
     rel = np.abs(Lo[ok] - Le[ok]).max(1) / (np.abs(Lo[ok]).max(1) + 1e-6)
-    assert (rel < 1e-4).mean() > 0.99, (seed, float((rel < 1e-4).mean()), float(rel.max()))
+    # same libm on both sides: only the order of sums differs (measured over 400 random scenes x 2000 samples: max 6.3e-7)
+    assert rel.max() < 1e-5, (seed, float(rel.max()))
