@@ -141,3 +141,24 @@ def test_depth_zero_and_one(name):
         assert (rel < 1e-4).mean() > 0.995, (name, md, rel.max())
         if sc.integrator_kind == IR.INTEGRATOR_PATH and md == 0:
             assert st["rays_shadow"] == 0 and st["rays_extension"] == 0                    # nothing is shaded at depth == md
+
+
+@pytest.mark.parametrize("name", ["cornell-box", "cornell-box-specular", "pool"])
+def test_russian_roulette_beyond_depth_seven(name):
+    """Path.hs:68-72: from depth 8 on a path continues with probability min(0.75, Y(t)) and its throughput is divided by it. No
+    config reaches that branch with its own maxDepth (5); `examples/pool.bling` has maxDepth 10. Here maxDepth is 14, so thousands
+    of paths in the closed box pass the roulette several times; sample dimensions beyond sampleDepth wrap as in the reference."""
+    sc = small(load_scene(name), 40, 30, 2, 2); sc.max_depth = 14
+    sc8 = copy.copy(sc); sc8.max_depth = 8
+    o = Oracle(sc); e = EmuContext(); e.upload_scene(sc)
+    x0, x1, y0, y1 = o.sample_extent()
+    rng = np.random.default_rng(11)
+    n = 6000
+    px, py, s = rng.integers(x0, x1 + 1, n), rng.integers(y0, y1 + 1, n), rng.integers(0, 4, n)
+    Lo, _ = o.render_samples(1, 9, px, py, s); Le, _ = e.render_samples(1, 9, px, py, s)
+    L8, _ = Oracle(sc8).render_samples(1, 9, px, py, s)
+    e.close()
+    deep = np.abs(Lo - L8).max(1) > 0                       # samples that vertices at depth >= 8 contributed to
+    assert deep.sum() > (300 if name != "pool" else 3), (name, int(deep.sum()))
+    rel = np.abs(Lo - Le).max(1) / (np.abs(Lo).max(1) + 1e-6)
+    assert rel.max() < 1e-5, (name, float(rel.max()))

@@ -62,6 +62,12 @@ CONFIGS = {
     # a height-map mesh (fbm elevation, central-difference shading normals) under `integrator { debug normals }`, `random 4`
     # sampler; parses as shipped
     "heightmap": dict(file="heightmap.bling"),
+    # bump-mapped (fbm) glass water over a pool of BOX shapes, cylinders textured by a crystal blend, a blackbody
+    # emitter; the only example with maxDepth 10, i.e. the only one that reaches the Russian-roulette branch (depth > 7,
+    # Path.hs:68-72). Its last renderer line selects Metropolis (:17) -> dropped; stale `stratified xSamples n ySamples m` and the
+    # one-parameter `scale s tex` of an older parser (-> `scale 0 s tex`)
+    "pool": dict(file="pool.bling", drop_lines=(17,), fixups=[(r"stratified xSamples (\d+) ySamples (\d+)", r"stratified \1 \2"),
+                                                              (r"scale 0.2 tex", "scale 0 0.2 tex")]),
     "gumbo": dict(file="gumbo.bling", fixups=[(r"rgbeFile", "file")], env_files={"*": synthetic_hdr()}),
 }
 
