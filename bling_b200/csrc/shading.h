@@ -496,6 +496,8 @@ HD void surfaceAt(const DScene &sc, const Ray &ray, float t, float b1, float b2,
       dgs = sh.dgg;
       if (sc.tri_n) {   // triangleShadingGeometry (TriangleMesh.hs:122-134), o2w = mempty
          const float *N = sc.tri_n + 9 * (size_t)ref;
+         // nine zeros: a triangle of a mesh WITHOUT normals in a scene that also holds smooth meshes keeps its geometric frame
+         if (N[0] == 0 && N[1] == 0 && N[2] == 0 && N[3] == 0 && N[4] == 0 && N[5] == 0 && N[6] == 0 && N[7] == 0 && N[8] == 0) return;
          float b0 = 1 - b1 - b2;
          V3 ns = normalize3((scl(b0, mk3(N[0], N[1], N[2])) + scl(b1, mk3(N[3], N[4], N[5]))) + scl(b2, mk3(N[6], N[7], N[8])));
          V3 tsp = cross3(normalize3(sh.dgg.dpdu), ns);

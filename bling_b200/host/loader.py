@@ -684,8 +684,8 @@ class Loader:
                 n = len(p.verts)
                 verts.append(p.verts); uvs.append(p.uvs); mats.append(p.mats)
                 if any_n:
-                    if p.normals is None: raise NotImplementedError("mixed shaded/flat meshes")
-                    nrm.append(p.normals)
+                    # a mesh without normals beside smooth ones: nine zeros per triangle = flat shaded (blingcu.h)
+                    nrm.append(p.normals if p.normals is not None else np.zeros((n, 9), np.float32))
                 tpid.append(np.arange(pid, pid + n, dtype=np.int32)); pid += n
             else:
                 s = p.shape; s.prim_id = pid; pid += 1

@@ -42,7 +42,8 @@ data ShapeIR = ShapeIR
 data MeshIR = MeshIR
    { meshVerts :: !(SV.Vector Float)            -- ^ 9 per triangle
    , meshUVs :: !(SV.Vector Float)              -- ^ 6 per triangle (default 0,0,1,0,1,1: TriangleMesh.hs:119-120)
-   , meshNormals :: !(Maybe (SV.Vector Float))  -- ^ 9 per triangle
+   , meshNormals :: !(Maybe (SV.Vector Float))  -- ^ 9 per triangle; when some meshes of a scene have normals and others do not,
+                                                --   the marshaller writes nine zeros per triangle for a `Nothing` (blingcu.h: flat shaded)
    , meshMaterial :: !Int32, meshFirstPrimId :: !Int32 }
 
 data LightIR = LightIR { lgtKind :: !Int32, lgtShape :: !Int32, lgtEnv :: !Int32, lgtV :: ![Float], lgtS :: ![Float] }

@@ -211,7 +211,7 @@ typedef struct blingcu_scene {
    uint64_t n_triangles;
    const float *tri_verts;      /* n*9: p1 p2 p3                            */
    const float *tri_uvs;        /* n*6 (TriangleMesh.hs:119-120 default 0,0,1,0,1,1) */
-   const float *tri_normals;    /* n*9 or NULL (flat shaded)                */
+   const float *tri_normals;    /* n*9 or NULL (flat shaded); a triangle with nine zeros is flat shaded (mesh without normals beside smooth ones) */
    const int32_t *tri_material; /* n                                        */
    const int32_t *tri_prim_id;  /* n, or NULL => prim id = prim_id_base + i */
    int32_t tri_prim_id_base;

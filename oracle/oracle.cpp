@@ -108,14 +108,18 @@ static Bsdf makeBsdf(const Scene &sc, const Hit &hit) {
       if (!sc.triNormals.empty()) {  // triangleShadingGeometry (TriangleMesh.hs:122-134) with o2w = mempty
          const float *N = &sc.triNormals[9 * (size_t)pr.idx];
          V3 n0 = mk(N[0], N[1], N[2]), n1 = mk(N[3], N[4], N[5]), n2 = mk(N[6], N[7], N[8]);
+         bool flat = true;   // blingcu.h: nine zeros = a mesh without normals (Nothing in TriangleMesh.hs:39-60) beside smooth ones
+         for (int k = 0; k < 9; ++k) flat = flat && N[k] == 0;
          float b1 = hit.dg.b1, b2 = hit.dg.b2, b0 = 1 - b1 - b2;
-         V3 nsp = (scl(b0, n0) + scl(b1, n1)) + scl(b2, n2);
-         V3 ns = normalize(nsp);  // transNormal identity
-         V3 ssp = normalize(hit.dg.dpdu);
-         V3 tsp = cross(ssp, ns);
-         if (sqLen(tsp) > 0) { dgs.dpdu = cross(normalize(tsp), ns); dgs.dpdv = normalize(tsp); }
-         else { Frame f = coordinateSystem(ns); dgs.dpdu = f.s; dgs.dpdv = f.t; }
-         dgs.n = ns;
+         if (!flat) {
+            V3 nsp = (scl(b0, n0) + scl(b1, n1)) + scl(b2, n2);
+            V3 ns = normalize(nsp);  // transNormal identity
+            V3 ssp = normalize(hit.dg.dpdu);
+            V3 tsp = cross(ssp, ns);
+            if (sqLen(tsp) > 0) { dgs.dpdu = cross(normalize(tsp), ns); dgs.dpdv = normalize(tsp); }
+            else { Frame f = coordinateSystem(ns); dgs.dpdu = f.s; dgs.dpdv = f.t; }
+            dgs.n = ns;
+         }
       }
    } else matId = sc.geo.shapes[pr.idx].material;
    const blingcu_material &m0 = sc.materials[matId];

@@ -18,7 +18,7 @@ COVERAGE = ["zoo", "envcam", "smooth", "extras", "textures", "direct", "blackbod
 ALL_SCENES = SCENES + COVERAGE
 # fixtures checked on the kernel-body emulator only (added after the round's GPU budget was spent)
 EMU_ONLY = ["gumbo", "heightmap", "bumpmap", "cellnoise", "substrate", "matte-test", "plastic-test",
-            "trans-matte", "cornell-box-specular", "race", "crystal", "shapes", "geometric-light", "metal-test", "pool"]
+            "trans-matte", "cornell-box-specular", "race", "crystal", "shapes", "geometric-light", "metal-test", "pool", "cornell-box-underwater"]
 
 
 def pytest_configure(config):

@@ -162,3 +162,27 @@ def test_russian_roulette_beyond_depth_seven(name):
     assert deep.sum() > (300 if name != "pool" else 3), (name, int(deep.sum()))
     rel = np.abs(Lo - Le).max(1) / (np.abs(Lo).max(1) + 1e-6)
     assert rel.max() < 1e-5, (name, float(rel.max()))
+
+
+def test_flat_triangles_beside_smooth_ones():
+    """blingcu.h `tri_normals`: nine zeros mark a triangle of a mesh WITHOUT normals (TriangleMesh.hs:39-60 `Nothing`) in a scene
+    that also holds smooth meshes (examples/cornell-box-underwater.bling: Cornell walls beside a height-map water surface). Shown by
+    the `debug normals` integrator: zeroing every normal gives exactly the flat-shaded scene, zeroing half of them changes only
+    samples that the all-smooth and the all-flat scene disagree on, and kernels and oracle agree bit for bit."""
+    base = small(load_scene("smooth"), 48, 36, 2, 2); base.integrator_kind = IR.INTEGRATOR_NORMALS
+    base.refl_basis = load_scene("textures").refl_basis          # rgbToSpectrumRefl basis (the older fixture carries none)
+    nt = len(base.tri_verts)
+    assert base.tri_normals is not None and nt > 10
+    flat = copy.copy(base); flat.tri_normals = None
+    zeros = copy.copy(base); zeros.tri_normals = np.zeros((nt, 9), np.float32)
+    half = copy.copy(base); half.tri_normals = np.array(base.tri_normals, np.float32).reshape(nt, 9).copy(); half.tri_normals[::2] = 0
+    o = Oracle(base); x0, x1, y0, y1 = o.sample_extent()
+    xs, ys = np.meshgrid(np.arange(x0, x1 + 1), np.arange(y0, y1 + 1)); px, py = xs.ravel(), ys.ravel(); s = np.zeros_like(px)
+    L = {}
+    for k, sc in dict(smooth=base, flat=flat, zeros=zeros, half=half).items():
+        e = EmuContext(); e.upload_scene(sc); L[k], _ = e.render_samples(1, 2, px, py, s); e.close()
+        Lo, _ = Oracle(sc).render_samples(1, 2, px, py, s)
+        assert np.array_equal(L[k], Lo), k
+    assert np.array_equal(L["zeros"], L["flat"]) and not np.array_equal(L["smooth"], L["flat"])
+    as_smooth, as_flat = (L["half"] == L["smooth"]).all(1), (L["half"] == L["flat"]).all(1)
+    assert (as_smooth | as_flat).all() and (as_smooth & ~as_flat).sum() > 20 and (as_flat & ~as_smooth).sum() > 20

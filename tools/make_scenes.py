@@ -68,6 +68,9 @@ CONFIGS = {
     # one-parameter `scale s tex` of an older parser (-> `scale 0 s tex`)
     "pool": dict(file="pool.bling", drop_lines=(17,), fixups=[(r"stratified xSamples (\d+) ySamples (\d+)", r"stratified \1 \2"),
                                                               (r"scale 0.2 tex", "scale 0 0.2 tex")]),
+    # the Cornell box under a height-map water surface (smooth normals) next to its flat-shaded meshes (nine-zero normals, blingcu.h),
+    # glass, maxDepth 15, sinc filter; parses as shipped
+    "cornell-box-underwater": dict(file="cornell-box-underwater.bling"),
     "gumbo": dict(file="gumbo.bling", fixups=[(r"rgbeFile", "file")], env_files={"*": synthetic_hdr()}),
 }
 
