@@ -103,7 +103,7 @@ def random_scene_text(seed):
     return "\n".join(out) + "\n"
 
 
-@pytest.mark.parametrize("seed", range(32))
+@pytest.mark.parametrize("seed", range(100))
 def test_random_scene_bodies_match_oracle(seed, tmp_path):
     f = tmp_path / f"fuzz{seed}.bling"; f.write_text(random_scene_text(seed))
     try:
