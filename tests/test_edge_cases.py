@@ -186,3 +186,21 @@ def test_flat_triangles_beside_smooth_ones():
     assert np.array_equal(L["zeros"], L["flat"]) and not np.array_equal(L["smooth"], L["flat"])
     as_smooth, as_flat = (L["half"] == L["smooth"]).all(1), (L["half"] == L["flat"]).all(1)
     assert (as_smooth | as_flat).all() and (as_smooth & ~as_flat).sum() > 20 and (as_flat & ~as_smooth).sum() > 20
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_triangle_distributions_traversal_parity(seed):
+    """the quantised BVH4 against brute force on triangle sets it could get wrong: 1 .. 3000 triangles at scales 1e-3 .. 1e4,
+    small ones, slivers 2000 times longer than wide, exactly coplanar ones (flat boxes), big overlapping ones. Primitive ids agree
+    except t-ties (coplanar / overlapping sets have many), t bit for bit, occlusion exactly. (120 such sets scanned: none bad.)"""
+    r = np.random.default_rng(seed)
+    n = int(r.choice([1, 2, 3, 7, 50, 400, 3000]))
+    scale = 10.0 ** r.uniform(-3, 4)
+    kind = seed % 4
+    c = r.uniform(-1, 1, (n, 1, 3)) * scale
+    if kind == 0: v = c + r.normal(size=(n, 3, 3)) * scale * 0.05
+    elif kind == 1: v = c + r.normal(size=(n, 3, 3)) * scale * np.array([2.0, 0.001, 0.001])
+    elif kind == 2: v = c * np.array([1, 1, 0.0]) + r.normal(size=(n, 3, 3)) * scale * np.array([0.2, 0.2, 0])
+    else: v = c * 0.01 + r.normal(size=(n, 3, 3)) * scale * 0.5
+    sc = _tri_scene(v.reshape(n, 9).astype(np.float32))
+    _traversal_parity(sc, random_rays(sc, 2500, seed))
