@@ -41,13 +41,23 @@ struct PathState {
    unsigned long long *stats;   // N_STATS
 };
 
+// where quarter q (4 bands) of slot i's spectrum lives. Product layout: four float4 PLANES (coalesced while the queue is dense).
+// Experiment switch BL_SPEC_AOS (tools/ab_libs.py, not the product build): one 64-byte record per slot, which keeps 32-byte sectors
+// full when the queue has thinned out after the first bounces.
+HD size_t spec4At(uint32_t cap, uint32_t i, int q) {
+#ifdef BL_SPEC_AOS
+   return (size_t)i * 4 + q;
+#else
+   return (size_t)q * cap + i;
+#endif
+}
 HD Spec loadSpec4(const F4 *base, uint32_t cap, uint32_t i) {
    Spec s;
-   BL_UNROLL for (int q = 0; q < 4; ++q) { F4 v = base[(size_t)q * cap + i]; s.v[4 * q] = v.x; s.v[4 * q + 1] = v.y; s.v[4 * q + 2] = v.z; s.v[4 * q + 3] = v.w; }
+   BL_UNROLL for (int q = 0; q < 4; ++q) { F4 v = base[spec4At(cap, i, q)]; s.v[4 * q] = v.x; s.v[4 * q + 1] = v.y; s.v[4 * q + 2] = v.z; s.v[4 * q + 3] = v.w; }
    return s;
 }
 HD void storeSpec4(F4 *base, uint32_t cap, uint32_t i, const Spec &s) {
-   BL_UNROLL for (int q = 0; q < 4; ++q) { F4 v; v.x = s.v[4 * q]; v.y = s.v[4 * q + 1]; v.z = s.v[4 * q + 2]; v.w = s.v[4 * q + 3]; base[(size_t)q * cap + i] = v; }
+   BL_UNROLL for (int q = 0; q < 4; ++q) { F4 v; v.x = s.v[4 * q]; v.y = s.v[4 * q + 1]; v.z = s.v[4 * q + 2]; v.w = s.v[4 * q + 3]; base[spec4At(cap, i, q)] = v; }
 }
 HD void storeRay(F4 *o, F4 *d, uint32_t i, const Ray &r) { F4 a, b; a.x = r.o.x; a.y = r.o.y; a.z = r.o.z; a.w = r.tmin; b.x = r.d.x; b.y = r.d.y; b.z = r.d.z; b.w = r.tmax; o[i] = a; d[i] = b; }
 HD Ray loadRay(const F4 *o, const F4 *d, uint32_t i) { F4 a = o[i], b = d[i]; Ray r; r.o = mk3(a.x, a.y, a.z); r.tmin = a.w; r.d = mk3(b.x, b.y, b.z); r.tmax = b.w; return r; }
@@ -55,7 +65,7 @@ HD Ray loadRay(const F4 *o, const F4 *d, uint32_t i) { F4 a = o[i], b = d[i]; Ra
 // L[slot] += s with atomics (direct-lighting integrator: several branch slots feed one camera sample)
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ void addSpec4Atomic(F4 *base, uint32_t cap, uint32_t i, const Spec &s) {
-   BL_UNROLL for (int q = 0; q < 4; ++q) { float *p = (float *)(base + (size_t)q * cap + i); BL_UNROLL for (int k = 0; k < 4; ++k) atomicAdd(p + k, s.v[4 * q + k]); }
+   BL_UNROLL for (int q = 0; q < 4; ++q) { float *p = (float *)(base + spec4At(cap, i, q)); BL_UNROLL for (int k = 0; k < 4; ++k) atomicAdd(p + k, s.v[4 * q + k]); }
 }
 #else
 inline void addSpec4Atomic(F4 *base, uint32_t cap, uint32_t i, const Spec &s) { storeSpec4(base, cap, i, loadSpec4(base, cap, i) + s); }

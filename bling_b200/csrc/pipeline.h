@@ -503,10 +503,14 @@ struct Pipeline {
       }
       be.sync();
       std::vector<F4> L(4 * (size_t)ps.cap); std::vector<F2> xy(n);
+#ifdef BL_SPEC_AOS   // experiment layout (bodies.h::spec4At): one 64-byte record per slot
+      be.download(L.data(), ps.L, sizeof(F4) * 4 * n);
+#else
       for (int q = 0; q < 4; ++q) be.download(L.data() + (size_t)q * n, ps.L + (size_t)q * ps.cap, sizeof(F4) * n);
+#endif
       be.download(xy.data(), ps.spos, sizeof(F2) * n);
       for (size_t i = 0; i < n; ++i) {
-         for (int q = 0; q < 4; ++q) { F4 v = L[(size_t)q * n + i]; float *o = outL + 16 * i + 4 * q; o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+         for (int q = 0; q < 4; ++q) { F4 v = L[spec4At((uint32_t)n, (uint32_t)i, q)]; float *o = outL + 16 * i + 4 * q; o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
          outXY[2 * i] = xy[i].x; outXY[2 * i + 1] = xy[i].y;
       }
       be.free(dpx); be.free(dpy); be.free(ds);

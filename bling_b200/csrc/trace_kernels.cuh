@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
          if (ANY) {
             if (fuseL) {   // L += pending, one quarter (float4) at a time
                for (int qq = 0; qq < 4; ++qq) {
-                  const size_t at = (size_t)qq * fuseCap + slot;
+                  const size_t at = spec4At(fuseCap, slot, qq);
                   F4 l = fuseL[at]; const F4 p_ = fuseP[at];
                   l.x += p_.x; l.y += p_.y; l.z += p_.z; l.w += p_.w;
                   fuseL[at] = l;
