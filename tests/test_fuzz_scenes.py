@@ -87,7 +87,14 @@ def random_scene_text(seed):
            f"renderer {{ sampler sampled {{ sampler {{ {smp} }} integrator {{ {integ} }} }} }}",
            f"transform {{ lookAt {{ pos {r.uniform(-2, 2):.2f} {r.uniform(2, 5):.2f} {-r.uniform(7, 10):.2f} look 0 1 0 up 0 1 0 }} }}",
            f"camera {{ perspective fov {r.uniform(35, 60):.1f} lensRadius {r.choice([0, 0, 0.1])} focalDistance 9 }}", "newTransform { }"]
-    if r.random() < 0.8: out.append(f"light {{ infinite {{ rotateX -90 }} l {{ constant {_rgb(r, 'rgbI', 0.1, 1.0)} }} }}")
+    if r.random() < 0.8:
+        env = f"constant {_rgb(r, 'rgbI', 0.1, 1.0)}"
+        # seeds from 100 on (a separate stream, so that the scenes of the first hundred seeds stay what they were): half of the
+        # infinite lights are the Preetham sky of SunSky.hs with a random sun direction and turbidity
+        r2 = np.random.default_rng(50_000 + seed)
+        if seed >= 100 and r2.random() < 0.5:
+            env = f"sunSky east {r2.uniform(-1, 1):.2f} 0 {r2.uniform(0.2, 1):.2f} sunDir {r2.uniform(-1, 1):.2f} {r2.uniform(0.05, 1):.2f} {r2.uniform(-1, 1):.2f} turbidity {r2.uniform(2, 12):.1f}"
+        out.append(f"light {{ infinite {{ rotateX -90 }} l {{ {env} }} }}")
     if r.random() < 0.5: out.append(f"light {{ point intensity {_rgb(r, 'rgbI', 5, 40)} position {r.uniform(-4, 4):.2f} {r.uniform(3, 6):.2f} {r.uniform(-4, 4):.2f} }}")
     if r.random() < 0.5: out.append(f"light {{ directional intensity {_rgb(r, 'rgbI', 0.5, 3)} normal {r.uniform(-1, 1):.2f} 1 {r.uniform(-1, 1):.2f} }}")
     out += [_material(r), "newTransform { rotateX -90 }", "prim { shape { quad 9 9 } }"]                      # a ground
@@ -103,7 +110,7 @@ def random_scene_text(seed):
     return "\n".join(out) + "\n"
 
 
-@pytest.mark.parametrize("seed", range(100))
+@pytest.mark.parametrize("seed", range(140))
 def test_random_scene_bodies_match_oracle(seed, tmp_path):
     f = tmp_path / f"fuzz{seed}.bling"; f.write_text(random_scene_text(seed))
     try:
