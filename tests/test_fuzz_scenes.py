@@ -143,8 +143,9 @@ def test_random_scene_bodies_match_oracle(seed, tmp_path):
     assert o.stats()["dropped_samples"] == e.stats()["dropped_samples"]
     if np.isfinite(Lo).all() and np.abs(Lo).max() < 1e3:
         assert np.allclose(fo[..., 0], fe[..., 0], rtol=1e-4, atol=1e-6)
-        both = np.isfinite(fo).all(-1) & np.isfinite(fe).all(-1) & (np.abs(fo).max(-1) < 1e4)
-        assert both.mean() > 0.97 and np.allclose(fo[both], fe[both], rtol=5e-3, atol=1e-4)
+        assert np.array_equal(np.isfinite(fo), np.isfinite(fe))
+        both = np.isfinite(fo).all(-1)
+        assert both.mean() > 0.97 and np.allclose(fo[both], fe[both], rtol=5e-3, atol=1e-4 * max(1.0, float(np.abs(fo[both]).max())))
     e.close()
     assert np.array_equal(xyo, xye)
     ok = np.isfinite(Lo).all(1) & np.isfinite(Le).all(1)
