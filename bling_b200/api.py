@@ -18,7 +18,10 @@ LIB_PATH = _PKG / "libblingcu.so"
 # every symbol include/blingcu.h declares
 SYMBOLS = ["create", "destroy", "last_error", "upload_scene", "trace_nearest", "trace_occluded", "trace_stats",
            "render_pass", "render_slice", "render_samples", "eval_texture", "read_film", "clear_film", "film_add_host", "film_device",
-           "synchronize", "set_stream", "get_stats", "reset_stats", "set_option", "sample_extent", "kernel_times"]
+           "synchronize", "set_stream", "get_stats", "reset_stats", "set_option", "sample_extent", "kernel_times",
+           "comm_unique_id", "comm_init", "comm_init_all", "comm_destroy", "reduce_film", "reduce_film_group", "comm_wait",
+           "read_film_sum", "film_sum_device"]
+COMM_ID_BYTES = 128
 
 
 class BlingCuError(RuntimeError):
@@ -57,6 +60,15 @@ def load_library(path=LIB_PATH, prefix="blingcu"):
     f("set_option").argtypes = [P, C.c_char_p, C.c_double]
     f("sample_extent").argtypes = [P] + [C.POINTER(C.c_int32)] * 4
     f("kernel_times").argtypes = [P, P, P, C.c_int]
+    f("comm_unique_id").argtypes = [P]
+    f("comm_init").argtypes = [P, C.c_int, C.c_int, P]
+    f("comm_init_all").argtypes = [C.POINTER(P), C.c_int]
+    f("comm_destroy").argtypes = [P]
+    f("reduce_film").argtypes = [P, C.c_int]
+    f("reduce_film_group").argtypes = [C.POINTER(P), C.c_int, C.c_int]
+    f("comm_wait").argtypes = [P]
+    f("read_film_sum").argtypes = [P, P]
+    f("film_sum_device").argtypes = [P, C.POINTER(P), C.POINTER(C.c_size_t)]
     return L
 
 
@@ -162,6 +174,56 @@ class Context:
     def film_device(self):
         p = C.c_void_p(); n = C.c_size_t()
         self._chk(self._f("film_device")(self._h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    # ---- multi-GPU film sum (the library owns NCCL; include/blingcu.h "multi-GPU")
+    @classmethod
+    def comm_unique_id(cls) -> bytes:
+        """128 opaque bytes from rank 0, to be handed to every other rank (ncclGetUniqueId)."""
+        L = load_library(cls._lib_path, cls._prefix)
+        buf = (C.c_uint8 * COMM_ID_BYTES)()
+        rc = getattr(L, f"{cls._prefix}_comm_unique_id")(buf)
+        if rc != 0:
+            raise BlingCuError(rc, (getattr(L, f"{cls._prefix}_last_error")(None) or b"").decode())
+        return bytes(buf)
+
+    def comm_init(self, rank: int, nranks: int, comm_id: bytes = None):
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(comm_id) if comm_id is not None else None
+        self._chk(self._f("comm_init")(self._h, rank, nranks, buf))
+
+    @staticmethod
+    def _handles(ctxs):
+        return (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+
+    @classmethod
+    def comm_init_all(cls, ctxs):
+        """one process driving several contexts (one per device): rank i = ctxs[i]."""
+        rc = ctxs[0]._f("comm_init_all")(cls._handles(ctxs), len(ctxs))
+        for c in ctxs:
+            if rc != 0: c._chk(rc)
+
+    @classmethod
+    def reduce_film_group(cls, ctxs, root: int = -1):
+        rc = ctxs[0]._f("reduce_film_group")(cls._handles(ctxs), len(ctxs), root)
+        if rc != 0: ctxs[0]._chk(rc)
+
+    def comm_destroy(self): self._chk(self._f("comm_destroy")(self._h))
+
+    def reduce_film(self, root: int = -1):
+        """film_sum = sum over ranks of film (asynchronous; overlaps the next render call)."""
+        self._chk(self._f("reduce_film")(self._h, root))
+
+    def comm_wait(self): self._chk(self._f("comm_wait")(self._h))
+
+    def read_film_sum(self, out: np.ndarray = None) -> np.ndarray:
+        if out is None:
+            out = np.zeros((self.scene.height, self.scene.width, 4), np.float32)
+        self._chk(self._f("read_film_sum")(self._h, out.ctypes.data))
+        return out
+
+    def film_sum_device(self):
+        p = C.c_void_p(); n = C.c_size_t()
+        self._chk(self._f("film_sum_device")(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
     def synchronize(self): self._chk(self._f("synchronize")(self._h))

@@ -64,7 +64,7 @@ static thread_local std::string g_createError;
    int PFX##_clear_film(PFX##_ctx_t *c) {                                                                                        \
       if (!c) return BLINGCU_EINVAL;                                                                                             \
       if (!c->p.uploaded) { c->p.err = "no scene"; return BLINGCU_ESTATE; }                                                      \
-      return c->p.be.guard(c->p.err, [&]() { c->p.be.zero(c->p.film, sizeof(bl::F4) * (size_t)c->p.hs.W * c->p.hs.H); return 0; }); \
+      return c->p.be.guard(c->p.err, [&]() { c->p.be.waitReduced(); c->p.be.zero(c->p.film, sizeof(bl::F4) * (size_t)c->p.hs.W * c->p.hs.H); return 0; }); \
    }                                                                                                                             \
    int PFX##_film_add_host(PFX##_ctx_t *c, const float *wxyz) {                                                                  \
       if (!c || !wxyz) return BLINGCU_EINVAL;                                                                                    \
@@ -73,6 +73,7 @@ static thread_local std::string g_createError;
          size_t n = (size_t)c->p.hs.W * c->p.hs.H;                                                                               \
          bl::F4 *tmp = (bl::F4 *)c->p.be.alloc(sizeof(bl::F4) * n);                                                              \
          c->p.be.upload(tmp, wxyz, sizeof(bl::F4) * n);                                                                          \
+         c->p.be.waitReduced();                                                                                                  \
          c->p.be.run(bl::AddFilmBody{c->p.film, tmp}, (uint32_t)n);                                                              \
          c->p.be.sync(); c->p.be.free(tmp);                                                                                      \
          return 0; });                                                                                                           \
@@ -83,6 +84,49 @@ static thread_local std::string g_createError;
       *dptr = c->p.film; *nf = (size_t)c->p.hs.W * c->p.hs.H * 4;                                                                \
       return 0;                                                                                                                  \
    }                                                                                                                             \
+   int PFX##_comm_unique_id(uint8_t *id) {                                                                                       \
+      if (!id) return BLINGCU_EINVAL;                                                                                            \
+      return BACKEND::commUniqueId(id, bl::g_createError);                                                                       \
+   }                                                                                                                             \
+   int PFX##_comm_init(PFX##_ctx_t *c, int rank, int nranks, const uint8_t *id) {                                                \
+      if (!c || (nranks > 1 && !id)) return BLINGCU_EINVAL;                                                                      \
+      return c->p.be.guard(c->p.err, [&]() { return c->p.be.commInit(rank, nranks, id, c->p.err); });                             \
+   }                                                                                                                             \
+   int PFX##_comm_init_all(PFX##_ctx_t *const *cs, int n) {                                                                      \
+      if (!cs || n < 1) return BLINGCU_EINVAL;                                                                                   \
+      for (int i = 0; i < n; ++i) if (!cs[i]) return BLINGCU_EINVAL;                                                             \
+      uint8_t id[BLINGCU_COMM_ID_BYTES] = {0};                                                                                   \
+      int rc = 0;                                                                                                                \
+      if (n > 1) { rc = BACKEND::commUniqueId(id, cs[0]->p.err); if (rc) return rc; rc = BACKEND::groupStart(cs[0]->p.err); if (rc) return rc; } \
+      for (int i = 0; i < n && !rc; ++i) rc = cs[i]->p.be.guard(cs[i]->p.err, [&]() { return cs[i]->p.be.commInit(i, n, id, cs[i]->p.err); }); \
+      if (n > 1) { int re = BACKEND::groupEnd(cs[0]->p.err); if (!rc) rc = re; }                                                  \
+      return rc;                                                                                                                 \
+   }                                                                                                                             \
+   int PFX##_comm_destroy(PFX##_ctx_t *c) { if (!c) return BLINGCU_EINVAL; return c->p.be.guard(c->p.err, [&]() { c->p.be.commDestroy(); return 0; }); } \
+   int PFX##_reduce_film(PFX##_ctx_t *c, int root) {                                                                             \
+      return c ? c->p.be.guard(c->p.err, [&]() { return c->p.reduceFilm(root); }) : BLINGCU_EINVAL;                               \
+   }                                                                                                                             \
+   int PFX##_reduce_film_group(PFX##_ctx_t *const *cs, int n, int root) {                                                        \
+      if (!cs || n < 1) return BLINGCU_EINVAL;                                                                                   \
+      for (int i = 0; i < n; ++i) if (!cs[i]) return BLINGCU_EINVAL;                                                             \
+      int rc = 0;                                                                                                                \
+      if (n > 1) { rc = BACKEND::groupStart(cs[0]->p.err); if (rc) return rc; }                                                   \
+      for (int i = 0; i < n && !rc; ++i) rc = cs[i]->p.be.guard(cs[i]->p.err, [&]() { return cs[i]->p.reduceFilm(root); });       \
+      if (n > 1) { int re = BACKEND::groupEnd(cs[0]->p.err); if (!rc) rc = re; }                                                  \
+      return rc;                                                                                                                 \
+   }                                                                                                                             \
+   int PFX##_comm_wait(PFX##_ctx_t *c) { if (!c) return BLINGCU_EINVAL; return c->p.be.guard(c->p.err, [&]() { c->p.be.waitReduced(); return 0; }); } \
+   int PFX##_read_film_sum(PFX##_ctx_t *c, float *wxyz) {                                                                        \
+      if (!c || !wxyz) return BLINGCU_EINVAL;                                                                                    \
+      if (!c->p.uploaded || !c->p.filmSum) { c->p.err = "read_film_sum before reduce_film"; return BLINGCU_ESTATE; }             \
+      return c->p.be.guard(c->p.err, [&]() { c->p.be.downloadOnComm(wxyz, c->p.filmSum, sizeof(bl::F4) * (size_t)c->p.hs.W * c->p.hs.H); return 0; }); \
+   }                                                                                                                             \
+   int PFX##_film_sum_device(PFX##_ctx_t *c, void **dptr, size_t *nf) {                                                          \
+      if (!c || !dptr || !nf) return BLINGCU_EINVAL;                                                                             \
+      if (!c->p.uploaded || !c->p.filmSum) { c->p.err = "film_sum_device before reduce_film"; return BLINGCU_ESTATE; }           \
+      *dptr = c->p.filmSum; *nf = (size_t)c->p.hs.W * c->p.hs.H * 4;                                                             \
+      return 0;                                                                                                                  \
+   }                                                                                                                             \
    int PFX##_set_stream(PFX##_ctx_t *c, void *stream) { return c ? c->p.be.guard(c->p.err, [&]() { c->p.be.setStream(stream); return 0; }) : BLINGCU_EINVAL; } \
    int PFX##_synchronize(PFX##_ctx_t *c) { return c ? c->p.be.guard(c->p.err, [&]() { c->p.be.sync(); return 0; }) : BLINGCU_EINVAL; } \
    int PFX##_get_stats(PFX##_ctx_t *c, blingcu_stats *o) { return (c && o) ? c->p.be.guard(c->p.err, [&]() { return c->p.getStats(o); }) : BLINGCU_EINVAL; } \
@@ -90,7 +134,7 @@ static thread_local std::string g_createError;
    int PFX##_set_option(PFX##_ctx_t *c, const char *key, double v) {                                                             \
       if (!c || !key) return BLINGCU_EINVAL;                                                                                     \
       std::string k(key);                                                                                                        \
-      if (k == "batch_samples") { if (v < 1) return BLINGCU_EINVAL; c->p.batchTarget = (uint32_t)v; return 0; }                   \
+      if (k == "batch_samples") { if (!(v >= 1) || v > 2147483648.0) return BLINGCU_EINVAL; c->p.batchTarget = (uint32_t)v; return 0; }                  \
       if (k == "bvh_leaf") { if (v < 1 || v > 15) return BLINGCU_EINVAL; c->p.maxLeaf = (int)v; return 0; }                       \
       if (k == "fuse_resolve") { c->p.fuseResolveOpt = v < 0 ? -1 : (v > 0 ? 1 : 0); return 0; }                                  \
       if (c->p.be.setOption(k, v)) return 0;                                                                                     \

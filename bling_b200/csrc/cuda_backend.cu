@@ -8,7 +8,9 @@
 // without a host round trip. Grids are sized in multiples of the SM count.
 #include "api_impl.h"
 #include "trace_kernels.cuh"
+#include "comm.h"
 #include <cuda_runtime.h>
+#include <cstring>
 #include <utility>
 #include <vector>
 
@@ -137,6 +139,9 @@ struct CudaBackend {
       // the traversal stack lives in dynamic shared memory: allow the builder's worst case (BL_STACK levels)
       cudaFuncSetAttribute(kTracePersistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceSmemBytes(BL_STACK));
       cudaFuncSetAttribute(kTracePersistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceSmemBytes(BL_STACK));
+      cudaFuncSetAttribute(kTraceWarpQ<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceWarpQSmemBytes(BL_STACK));
+      cudaFuncSetAttribute(kTraceWarpQ<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceWarpQSmemBytes(BL_STACK));
+      cudaFuncSetAttribute(kTraceWarpQ<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceWarpQSmemBytes(BL_STACK));
       return 0;
    }
    // run on a caller-owned stream (e.g. torch's current stream, so an NCCL all-reduce of the film orders after the
@@ -145,6 +150,10 @@ struct CudaBackend {
    void shutdown() {
       if (device >= 0) cudaSetDevice(device);
       if (stream) cudaStreamSynchronize(stream);
+      commDestroy();
+      if (fc.stream) { cudaStreamDestroy(fc.stream); fc.stream = nullptr; }
+      if (fc.rendered) { cudaEventDestroy(fc.rendered); fc.rendered = nullptr; }
+      if (fc.reduced) { cudaEventDestroy(fc.reduced); fc.reduced = nullptr; }
       if (tcfg.workCounter) { cudaFree(tcfg.workCounter); tcfg.workCounter = nullptr; }
       if (tcfg.travCounters) { cudaFree(tcfg.travCounters); tcfg.travCounters = nullptr; }
       if (ownStream) { cudaStreamDestroy(ownStream); ownStream = nullptr; }
@@ -176,6 +185,68 @@ struct CudaBackend {
       return false;
    }
    void setMaxStack(int m) { tcfg.maxStack = m; }
+   // ---- film reduction over ranks (comm.h). Per-process mode: comm_unique_id on one rank, comm_init on every rank. In-process
+   // mode (one host thread driving several contexts, e.g. a Haskell host): comm_init_all / reduce_film_group wrap the same
+   // calls in ncclGroupStart/End.
+   FilmComm fc;
+   int commEnsure(std::string &err) {
+      if (fc.stream) return 0;
+      if (cudaStreamCreateWithFlags(&fc.stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&fc.rendered, cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&fc.reduced, cudaEventDisableTiming) != cudaSuccess) { err = "comm stream/event creation failed"; return BLINGCU_ECUDA; }
+      return 0;
+   }
+   static int commUniqueId(uint8_t *id, std::string &err) {
+      NcclApi &N = ncclApi();
+      if (!N.load()) { err = N.err; return BLINGCU_EUNSUPPORTED; }
+      NcclUniqueId u; int rc = N.GetUniqueId(&u);
+      if (rc != kNcclSuccess) { err = N.what(rc); return BLINGCU_ECUDA; }
+      std::memcpy(id, u.internal, sizeof(u.internal));
+      return 0;
+   }
+   static int groupStart(std::string &err) { NcclApi &N = ncclApi(); if (!N.load()) { err = N.err; return BLINGCU_EUNSUPPORTED; } int rc = N.GroupStart(); if (rc != kNcclSuccess) { err = N.what(rc); return BLINGCU_ECUDA; } return 0; }
+   static int groupEnd(std::string &err) { NcclApi &N = ncclApi(); int rc = N.GroupEnd(); if (rc != kNcclSuccess) { err = N.what(rc); return BLINGCU_ECUDA; } return 0; }
+   int commInit(int rank, int nranks, const uint8_t *id, std::string &err) {
+      if (nranks < 1 || rank < 0 || rank >= nranks) { err = "comm_init: rank out of range"; return BLINGCU_EINVAL; }
+      commDestroy();
+      int rc = commEnsure(err); if (rc) return rc;
+      fc.rank = rank; fc.nranks = nranks;
+      if (nranks == 1) return 0;   // nothing to talk to: reduce_film is a device copy
+      NcclApi &N = ncclApi();
+      if (!N.load()) { err = N.err; return BLINGCU_EUNSUPPORTED; }
+      NcclUniqueId u; std::memcpy(u.internal, id, sizeof(u.internal));
+      CU(cudaSetDevice(device));
+      int nr = N.CommInitRank(&fc.comm, nranks, u, rank);
+      if (nr != kNcclSuccess) { fc.comm = nullptr; fc.nranks = 1; fc.rank = 0; err = N.what(nr); return BLINGCU_ECUDA; }
+      return 0;
+   }
+   void commDestroy() {
+      if (fc.stream) cudaStreamSynchronize(fc.stream);
+      if (fc.comm) { ncclApi().CommDestroy(fc.comm); fc.comm = nullptr; }
+      fc.rank = 0; fc.nranks = 1; fc.pending = false;
+   }
+   // film_sum = sum over ranks of film (root < 0: on every rank; else on `root` only), enqueued behind everything rendered so
+   // far, on the reduction's own stream
+   int reduceFilm(const float *film, float *filmSum, size_t nFloats, int root, std::string &err) {
+      int rc = commEnsure(err); if (rc) return rc;
+      if (root >= fc.nranks) { err = "reduce_film: root out of range"; return BLINGCU_EINVAL; }
+      waitReduced();   // one reduction in flight at a time (film_sum is a single buffer)
+      CU(cudaEventRecord(fc.rendered, stream));
+      CU(cudaStreamWaitEvent(fc.stream, fc.rendered, 0));
+      if (fc.comm) {
+         NcclApi &N = ncclApi();
+         int nr = root < 0 ? N.AllReduce(film, filmSum, nFloats, kNcclFloat32, kNcclSum, fc.comm, fc.stream)
+                           : N.Reduce(film, filmSum, nFloats, kNcclFloat32, kNcclSum, root, fc.comm, fc.stream);
+         if (nr != kNcclSuccess) { err = N.what(nr); return BLINGCU_ECUDA; }
+      } else CU(cudaMemcpyAsync(filmSum, film, nFloats * sizeof(float), cudaMemcpyDeviceToDevice, fc.stream));
+      CU(cudaEventRecord(fc.reduced, fc.stream));
+      fc.pending = true; fc.reductions++; fc.bytes += nFloats * sizeof(float);
+      return 0;
+   }
+   // the compute stream waits (on the device) for the reduction in flight: called before anything writes `film` again
+   void waitReduced() { if (fc.pending) { cudaStreamWaitEvent(stream, fc.reduced, 0); fc.pending = false; } }
+   void syncComm() { if (fc.stream) cudaStreamSynchronize(fc.stream); }
+   void downloadOnComm(void *d, const void *s, size_t n) { CU(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, fc.stream ? fc.stream : stream)); CU(cudaStreamSynchronize(fc.stream ? fc.stream : stream)); }
+
    void *alloc(size_t n) { void *p = nullptr; CU(cudaMalloc(&p, n ? n : 1)); return p; }
    void free(void *p) { if (p) cudaFree(p); }
    void upload(void *d, const void *s, size_t n) { CU(cudaMemcpyAsync(d, s, n, cudaMemcpyHostToDevice, stream)); CU(cudaStreamSynchronize(stream)); }
@@ -253,6 +324,7 @@ struct CudaBackend {
       Scope sc_(this);
       launchTraceAny(tcfg, stream, q, cnt, n, sc, o, d, occl);
    }
+   bool fusesResolve() const { return tcfg.variant != 0; }   // the reference-point kernels of variant 0 only write occlusion flags
    // any-hit query that also resolves: L[slot] += P[slot] for every unoccluded ray (trace_kernels.cuh)
    void traceAnyFused(const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc, const F4 *o, const F4 *d, uint8_t *occl, F4 *L, const F4 *P, uint32_t cap) {
       if (!n) return;

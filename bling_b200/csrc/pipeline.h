@@ -40,6 +40,7 @@ struct Pipeline {
    std::vector<void *> sceneAllocs;
    PathState ps{}; std::vector<void *> stateAllocs;
    F4 *film = nullptr;
+   F4 *filmSum = nullptr;     // sum of the films of all ranks (comm.h), valid after reduce_film
    uint32_t npix = 0, nTextures = 0;
    uint32_t batchTarget = 1u << 26;   // paths per wavefront (~490 B of state each: 33 GB at the cap, sized for 180 GB HBM)
    int maxLeaf = 2;
@@ -56,8 +57,8 @@ struct Pipeline {
       sceneAllocs.push_back(d);
       return d;
    }
-   void freeScene() { freeTraceScratch(); for (void *p : sceneAllocs) be.free(p); sceneAllocs.clear(); dscene = nullptr; if (film) { be.free(film); film = nullptr; } uploaded = false; }
-   void freeState() { for (void *p : stateAllocs) be.free(p); stateAllocs.clear(); ps = PathState{}; }
+   void freeScene() { be.syncComm(); freeTraceScratch(); for (void *p : sceneAllocs) be.free(p); sceneAllocs.clear(); dscene = nullptr; if (film) { be.free(film); film = nullptr; } if (filmSum) { be.free(filmSum); filmSum = nullptr; } uploaded = false; }
+   void freeState() { for (void *p : stateAllocs) be.free(p); stateAllocs.clear(); ps = PathState{}; qSlotsAlloc = 0; rootAlloc = 0; }
 
    int upload(const blingcu_scene *ir) {
       freeScene();
@@ -69,6 +70,9 @@ struct Pipeline {
       // maxDepth 0 has no meaning there: `cont` stops at d == md with d starting at 1 (DirectLighting.hs:47-49), i.e. never
       if (ir->integrator_kind == BLINGCU_INTEGRATOR_DIRECT && (ir->max_depth < 1 || ir->max_depth > 24)) return fail(BLINGCU_EINVAL, "direct lighting: max_depth out of range");
       size_t nt = (size_t)ir->n_triangles, ns = ir->n_shapes, nprim = nt + ns;
+      if (nt && (!ir->tri_verts || !ir->tri_material)) return fail(BLINGCU_EINVAL, "triangles without tri_verts / tri_material");
+      if (ns && !ir->shapes) return fail(BLINGCU_EINVAL, "n_shapes > 0 without shapes");
+      if ((ir->n_materials && !ir->materials) || (ir->n_textures && !ir->textures) || (ir->n_lights && !ir->lights) || (ir->n_envs && !ir->envs)) return fail(BLINGCU_EINVAL, "table count > 0 with a null table");
       // ---- validate indices
       for (size_t i = 0; i < nt; ++i) if (ir->tri_material[i] < 0 || (uint32_t)ir->tri_material[i] >= ir->n_materials) return fail(BLINGCU_EINVAL, "triangle material out of range");
       for (size_t i = 0; i < ns; ++i) {
@@ -164,7 +168,8 @@ struct Pipeline {
       {
          std::vector<F4> tp(3 * (nt ? nt : 1)); std::vector<F2> tu(3 * (nt ? nt : 1));
          for (size_t i = 0; i < nt; ++i) {
-            const float *v = ir->tri_verts + 9 * i, *u = ir->tri_uvs + 6 * i;
+            static const float kDefaultUv[6] = {0, 0, 1, 0, 1, 1};   // TriangleMesh.hs:119-120
+            const float *v = ir->tri_verts + 9 * i, *u = ir->tri_uvs ? ir->tri_uvs + 6 * i : kDefaultUv;
             tp[3 * i] = F4{v[0], v[1], v[2], i2f(ir->tri_material[i])};
             tp[3 * i + 1] = F4{v[3], v[4], v[5], 0}; tp[3 * i + 2] = F4{v[6], v[7], v[8], 0};
             tu[3 * i] = F2{u[0], u[1]}; tu[3 * i + 1] = F2{u[2], u[3]}; tu[3 * i + 2] = F2{u[4], u[5]};
@@ -226,11 +231,13 @@ struct Pipeline {
 
    template <class T> T *st(size_t n) { T *p = (T *)be.alloc(sizeof(T) * n); stateAllocs.push_back(p); return p; }
    int qSlotsAlloc = 0;   // shade queues the state holds
+   uint32_t rootAlloc = 0;   // entries of ps.root (cap for the direct-lighting integrator, 1 otherwise)
    int ensureState(uint32_t cap) {
-      if (ps.cap >= cap && qSlotsAlloc >= nSlots) return 0;
+      const uint32_t rootNeed = hs.integrator == BLINGCU_INTEGRATOR_DIRECT ? std::max(cap, ps.cap) : 1u;
+      if (ps.cap >= cap && qSlotsAlloc >= nSlots && rootAlloc >= rootNeed) return 0;
       cap = std::max(cap, ps.cap);
       freeState();
-      ps.cap = cap; qSlotsAlloc = nSlots;
+      ps.cap = cap; qSlotsAlloc = nSlots; rootAlloc = rootNeed;
       size_t c = cap;
       ps.rayO = st<F4>(c); ps.rayD = st<F4>(c); ps.hit = st<F4>(c);
       ps.T = st<F4>(4 * c); ps.L = st<F4>(4 * c);
@@ -239,7 +246,7 @@ struct Pipeline {
       ps.meta = st<uint32_t>(c); ps.kp = st<uint64_t>(c); ps.sidx = st<uint32_t>(c); ps.spos = st<F2>(c); ps.xyz = st<F4>(c);
       ps.qA = st<uint32_t>(c); ps.qB = st<uint32_t>(c); ps.qShadow = st<uint32_t>(c); ps.qMis = st<uint32_t>(c); ps.qMisAny = st<uint32_t>(c);
       ps.qMat = st<uint32_t>((size_t)nSlots * c);
-      ps.root = st<uint32_t>(hs.integrator == BLINGCU_INTEGRATOR_DIRECT ? c : 1);
+      ps.root = st<uint32_t>(rootAlloc);
       ps.counters = st<uint32_t>(N_COUNTERS); ps.stats = st<unsigned long long>(N_STATS);
       be.zero(ps.counters, sizeof(uint32_t) * N_COUNTERS); be.zero(ps.stats, sizeof(unsigned long long) * N_STATS);
       return 0;
@@ -275,7 +282,7 @@ struct Pipeline {
             // "fused NEE resolve": one launch and the occlusion-flag round trip less, +1.4 .. 2.9 % on the named scenes). Large
             // scenes keep the separate resolve launch: there the traversal kernel is the bottleneck and the extra scattered
             // read-modify-write inside it costs more than the 9 ms stream it replaces (cfg 5: -1.2 %).
-            const bool fuse = fuseResolve();
+            const bool fuse = fuseResolve() && be.fusesResolve();
             // the nearest-hit BSDF-MIS queue serves area lights, infinite lights in scenes with a Box, and -- with ANY light --
             // the samples whose weight is not finite (bodies.h, BL_MIS_NONFINITE; normally an empty queue: two idle launches)
             const bool misNearest = hs.n_lights > 0;
@@ -460,18 +467,21 @@ struct Pipeline {
          if (direct) kmax = std::max(1u, batchTarget / dlHeadroom / npix);
          uint32_t k = std::min(kmax, sEnd - s);
          uint32_t n = k * npix;
+         unsigned long long statSnap[N_STATS]; uint64_t launchSnap = launches;
          if (direct) {
-            if ((uint64_t)n * dlHeadroom > 0x7fffffffull) return fail(BLINGCU_EINVAL, "direct lighting: wavefront too large");
+            if ((uint64_t)n * dlHeadroom > 0x7fffffffull) return fail(BLINGCU_EINVAL, "direct lighting: the branch tree of one sample index needs more than 2^31 path slots (reduce the image size or max_depth)");
             ensureState(n * dlHeadroom);
+            be.sync(); be.download(statSnap, ps.stats, sizeof(statSnap));   // a batch that overflows is re-run: its counts must not stay
          }
          be.tag(BLINGCU_KC_OTHER); be.run(BeginBatchBody{ps, n}, 1);
          be.tag(BLINGCU_KC_RAYGEN); be.run(RaygenBody{dscene, ps, seed, pass, s, npix, nullptr, nullptr, nullptr}, n);
          launches += 2;
          if (direct) {
             bouncesDirect(n);
-            if (dlOverflowed()) { dlHeadroom *= 2; continue; }   // same batch again with twice the slots
+            if (dlOverflowed()) { dlHeadroom *= 2; be.upload(ps.stats, statSnap, sizeof(statSnap)); launches = launchSnap; continue; }   // same batch again with twice the slots
          } else if (hs.integrator == BLINGCU_INTEGRATOR_NORMALS) bouncesNormals(n);
          else bounces(n);
+         be.waitReduced();   // a film reduction still in flight reads `film`: it has overlapped everything up to here
          be.tag(BLINGCU_KC_FILM); be.run(FinalizeBody{dscene, ps}, n);
          be.run(FilmBody{dscene, ps, film, k, npix}, (uint32_t)hs.W * (uint32_t)hs.H);
          launches += 2;
@@ -562,6 +572,14 @@ struct Pipeline {
          be.download(outOccl, dC, n);
       }
       return 0;
+   }
+
+   // film_sum = sum over the communicator's ranks of film (asynchronous; see comm.h)
+   int reduceFilm(int root) {
+      if (!uploaded) return fail(BLINGCU_ESTATE, "reduce_film before upload_scene");
+      const size_t nf = (size_t)hs.W * hs.H * 4;
+      if (!filmSum) filmSum = (F4 *)be.alloc(nf * sizeof(float));
+      return be.reduceFilm((const float *)film, (float *)filmSum, nf, root, err);
    }
 
    int getStats(blingcu_stats *out) {

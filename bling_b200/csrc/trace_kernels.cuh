@@ -237,6 +237,10 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
 // levels of shared-memory stack per thread: the builder's worst case (a pop precedes every push burst of <= 3)
 static inline size_t traceSmemBytes(int maxStack) { int lv = maxStack < TR_SS ? maxStack : TR_SS; if (lv < 1) lv = 1; return (size_t)lv * TR_THREADS * sizeof(int); }
 
+}  // namespace bl
+#include "trace_warpq.cuh"
+namespace bl {
+
 static inline uint32_t traceGrid(const TraceConfig &cfg, uint32_t n, uint32_t raysPerBlock) {
    uint32_t need = (n + raysPerBlock - 1) / raysPerBlock;
    uint32_t full = (uint32_t)cfg.sms * (uint32_t)cfg.blocksPerSm;
@@ -248,6 +252,7 @@ static inline void launchTraceNearest(TraceConfig &cfg, cudaStream_t st, const u
    if (cfg.variant == 0) { kTraceNearestSimple<<<traceGrid(cfg, n, 128), 128, 0, st>>>(q, cnt, n, sc, O, D, hit); return; }
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
+   if (cfg.variant >= 2) { kTraceWarpQ<false, true><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter, nullptr, nullptr, 0u); return; }
    kTracePersistent<false><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter, nullptr, nullptr, 0u);
 
 }
@@ -257,6 +262,8 @@ static inline void launchTraceAny(TraceConfig &cfg, cudaStream_t st, const uint3
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
    TraceConfig c9 = cfg; c9.blocksPerSm = cfg.blocksPerSm + 1;
+   if (cfg.variant == 2) { kTraceWarpQ<true, true><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap); return; }
+   if (cfg.variant >= 3) { kTraceWarpQ<true, false><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap); return; }
    kTracePersistent<true><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap);
 
 }

@@ -1,0 +1,214 @@
+// trace_warpq.cuh -- variant 2 of K2 trace_nearest / K3 trace_any: persistent warps with a WARP-LEVEL LEAF QUEUE.
+// Replaces the per-ray recursion of KdTree.hs:210-246 like variant 1 (trace_kernels.cuh), same nodes, same child order,
+// same primitive tests (bit-identical t / b1 / b2).
+//
+// Why: ncu on variant 1 showed ~21.5 of 32 lanes active per instruction, and the warp model of tools/travsim.cpp on the real
+// cfg-5 ray streams says where the rest goes: a majority-vote step runs the node code with the ~13 lanes that stand at a
+// leaf idle, and the leaf code with only ~13.6 lanes busy. Here a lane NEVER waits at a leaf:
+//   * a lane that reaches a leaf appends (lane, item) pairs to a per-warp ring in shared memory and pops on;
+//   * as soon as 32 pairs are queued ALL 32 lanes test one pair each -- the ray comes from its owner lane by shuffle, the
+//     shrunken tmax (nearest hit) goes back through a shared-memory atomicMin on an order-preserving key, the hit record
+//     through a per-lane shared-memory slot, an any-hit through a per-lane flag;
+//   * a ray whose stack runs dry waits (WAITING) until its queued pairs are through, then retires.
+// Model (profiles/r02_travsim.md): node steps 21.4 -> 28.2 lanes, leaf steps 13.6 -> 31.9 lanes, ~1.35x fewer warp
+// instructions per ray. The nearest hit found is independent of the order of the tests except for exact t-ties, where the
+// pair queued LATER wins, as in the sequential order of variant 1 (t == tmax is accepted, TriangleMesh.hs:180).
+#pragma once
+
+namespace bl {
+
+#define TQ_CAP 128        // ring entries per warp: < 32 left over + at most 2 per lane per trip
+#ifndef TQ_FLUSH
+#define TQ_FLUSH 32       // run a leaf pass once this many pairs are queued (<= 32)
+#endif
+#define TQ_WARPS (TR_THREADS / 32)
+#define TQ_HEAD_WORDS (TQ_WARPS * TQ_CAP + TR_THREADS + 4 * TR_THREADS)   // rings, per-lane key / flag, per-lane hit record
+
+// order-preserving float <-> uint32 key (so that atomicMin on the key is a float min for any sign)
+__device__ __forceinline__ uint32_t fkey(float f) { const uint32_t b = __float_as_uint(f); return b ^ ((uint32_t)((int)b >> 31) | 0x80000000u); }
+__device__ __forceinline__ float fkeyInv(uint32_t k) { return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu)); }
+
+template <bool ANY, bool SORTED>
+__global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLOCKS) kTraceWarpQ(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
+                                                                 const DScene *__restrict__ sc, const F4 *__restrict__ O, const F4 *__restrict__ D,
+                                                                 F4 *__restrict__ hit, uint8_t *__restrict__ occl, uint32_t *__restrict__ work, F4 *__restrict__ fuseL, const F4 *__restrict__ fuseP, uint32_t fuseCap) {
+   extern __shared__ int sstack[];
+   const unsigned FULL = 0xffffffffu;
+   const uint32_t total = cnt ? *cnt : n;
+   const Bvh bvh = sc->bvh;
+   const unsigned lane = threadIdx.x & 31u;
+   const unsigned ltMask = (1u << lane) - 1u;
+   const unsigned wbase = threadIdx.x & ~31u;   // first thread of my warp
+   uint32_t *const sq = (uint32_t *)sstack + (threadIdx.x >> 5) * TQ_CAP;              // my warp's ring
+   uint32_t *const sown = (uint32_t *)sstack + TQ_WARPS * TQ_CAP;                      // [thread]: tmax key (nearest) / occluded flag (any)
+   F4 *const shit = (F4 *)((uint32_t *)sstack + TQ_WARPS * TQ_CAP + TR_THREADS);       // [thread]: best hit so far (nearest)
+   const uint32_t stackBase = (uint32_t)__cvta_generic_to_shared(sstack + TQ_HEAD_WORDS + threadIdx.x);
+   const uint32_t LV = TR_THREADS * (uint32_t)sizeof(int);
+   int tail_[BL_STACK - TR_SS];
+   const int EMPTY = (int)0x80000000, WAITING = (int)0x80000001;   // leaf references are > WAITING (bvh.h: ~((first << 4) | count))
+   int cur = EMPTY, li = 0, sp = 0;
+   uint32_t slot = 0;
+   uint32_t qhead = 0, qtail = 0, lastSeq = 0;   // absolute ring positions (warp-uniform) and the position behind my last pair
+   bool occ = false;
+   Ray r; RayPre pre;
+   bool exhausted = false;
+   r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.tmin = 0; r.tmax = 0; pre.idir = mk3(0, 0, 0); pre.ood = mk3(0, 0, 0);
+
+   for (;;) {
+      bool atNode = cur >= 0;
+      unsigned mBusy = __ballot_sync(FULL, cur != EMPTY);
+      // ---- refill idle lanes (warp-uniform decision)
+      if (!exhausted && __popc(mBusy) <= 32 - TR_REFILL) {
+         const unsigned idle = ~mBusy;
+         uint32_t base = 0;
+         const int leader = __ffs(idle) - 1;
+         if ((int)lane == leader) base = atomicAdd(work, (uint32_t)__popc(idle));
+         base = __shfl_sync(FULL, base, leader);
+         if (cur == EMPTY) {
+            const uint32_t k = base + __popc(idle & ltMask);
+            if (k < total) {
+               slot = q ? q[k] : k;
+               r = loadRay(O, D, slot);
+               pre = rayPre(r);
+               if (ANY) sown[threadIdx.x] = 0u;
+               else { sown[threadIdx.x] = fkey(r.tmax); F4 v_; v_.x = 0; v_.y = 0; v_.z = 0; v_.w = i2f(-1); shit[threadIdx.x] = v_; }
+               sp = 0; li = 0; occ = false; lastSeq = qtail;
+               cur = (bvh.root >= 0) ? bvh.root : WAITING;   // empty scene: nothing to wait for either
+            }
+         }
+         if (base + (uint32_t)__popc(idle) >= total) exhausted = true;
+         atNode = cur >= 0;
+         mBusy = __ballot_sync(FULL, cur != EMPTY);
+      }
+      if (mBusy == 0) { if (exhausted) break; continue; }
+      bool pop = false;
+      // ---- node step for every lane that stands at an inner node
+      if (__any_sync(FULL, atNode)) {
+         if (atNode) {
+            const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
+            F4 n0, n1, n2, n3;
+            ld8(np, n0, n1); ld8(np + 2, n2, n3);
+            float tn[4];
+            node4Near(n0, n2, n3, r, pre, tn);
+            int c[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};
+            if (SORTED) {
+               sort4(tn, c);   // nearest first, misses (+inf) last
+               const bool h0 = tn[0] < BL_INF, h1 = tn[1] < BL_INF, h2 = tn[2] < BL_INF, h3 = tn[3] < BL_INF;
+               const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
+               const int r0 = c[0], r1 = c[1], r2 = c[2], r3 = c[3];
+               const int l1 = sp + nh - 2, l2 = l1 - 1, l3 = l1 - 2;
+               if (l1 < TR_SS) {
+                  const uint32_t top = stackBase + (uint32_t)l1 * LV;
+                  stsIf(top, r1, h1); stsIf(top - LV, r2, h2); stsIf(top - 2 * LV, r3, h3);
+               } else {
+                  if (h1) { if (l1 < TR_SS) stsIf(stackBase + (uint32_t)l1 * LV, r1, true); else tail_[l1 - TR_SS] = r1; }
+                  if (h2) { if (l2 < TR_SS) stsIf(stackBase + (uint32_t)l2 * LV, r2, true); else tail_[l2 - TR_SS] = r2; }
+                  if (h3) { if (l3 < TR_SS) stsIf(stackBase + (uint32_t)l3 * LV, r3, true); else tail_[l3 - TR_SS] = r3; }
+               }
+               sp += (nh > 0) ? nh - 1 : 0;
+               cur = r0; li = 0;
+               pop = !h0;
+            } else {
+               // any-hit, unsorted (variant 3): the answer does not depend on the order and the warp model shows the same
+               // number of node visits in slot order (tools/travsim.cpp), so the five compare-exchanges are dropped: enter
+               // the first child hit, push the others as they come
+               const bool h0 = tn[0] < BL_INF, h1 = tn[1] < BL_INF, h2 = tn[2] < BL_INF, h3 = tn[3] < BL_INF;
+               const bool p1 = h1 && h0, p2 = h2 && (h0 || h1), p3 = h3 && (h0 || h1 || h2);
+               const int l1 = sp, l2 = sp + (int)p1, l3 = l2 + (int)p2;
+               if (l3 < TR_SS) { stsIf(stackBase + (uint32_t)l1 * LV, c[1], p1); stsIf(stackBase + (uint32_t)l2 * LV, c[2], p2); stsIf(stackBase + (uint32_t)l3 * LV, c[3], p3); }
+               else {
+                  if (p1) { if (l1 < TR_SS) stsIf(stackBase + (uint32_t)l1 * LV, c[1], true); else tail_[l1 - TR_SS] = c[1]; }
+                  if (p2) { if (l2 < TR_SS) stsIf(stackBase + (uint32_t)l2 * LV, c[2], true); else tail_[l2 - TR_SS] = c[2]; }
+                  if (p3) { if (l3 < TR_SS) stsIf(stackBase + (uint32_t)l3 * LV, c[3], true); else tail_[l3 - TR_SS] = c[3]; }
+               }
+               sp = l3 + (int)p3;
+               cur = h0 ? c[0] : (h1 ? c[1] : (h2 ? c[2] : c[3])); li = 0;
+               pop = !(h0 || h1 || h2 || h3);
+            }
+         }
+      }
+      // ---- lanes that stand at a leaf (entered just now, or popped last trip) queue up to two of its items and move on
+      {
+         const bool atLeaf = cur < 0 && cur > WAITING && !pop;
+         if (__any_sync(FULL, atLeaf)) {
+            const int enc = ~cur; const int first = enc >> 4, cntl = enc & 15;
+            const int rem = atLeaf ? cntl - li : 0;
+            const unsigned b1 = __ballot_sync(FULL, rem >= 1), b2 = __ballot_sync(FULL, rem >= 2);
+            const uint32_t at = qtail + (uint32_t)__popc(b1 & ltMask) + (uint32_t)__popc(b2 & ltMask);
+            if (rem >= 1) sq[at & (TQ_CAP - 1)] = (lane << 27) | (uint32_t)(first + li);
+            if (rem >= 2) sq[(at + 1) & (TQ_CAP - 1)] = (lane << 27) | (uint32_t)(first + li + 1);
+            qtail += (uint32_t)__popc(b1) + (uint32_t)__popc(b2);
+            if (atLeaf) { li += 2; lastSeq = qtail; pop = li >= cntl; }
+         }
+      }
+      // ---- pop (predicated load); with an empty stack the ray waits for its queued pairs
+      {
+         const bool more = sp != 0;
+         sp -= (pop && more) ? 1 : 0;
+         if (pop && more && sp >= TR_SS) cur = tail_[sp - TR_SS];
+         else cur = ldsIf(stackBase + (uint32_t)sp * LV, cur, pop && more);
+         li = pop ? 0 : li;
+         if (pop && !more) cur = WAITING;
+      }
+      // ---- leaf passes: 32 pairs at a time; a partial batch only when nobody could do anything else
+      {
+         uint32_t qn = qtail - qhead;
+         const bool canWalk = __any_sync(FULL, cur > WAITING);   // some lane stands at a node or at a leaf
+         if (qn >= (uint32_t)TQ_FLUSH || (!canWalk && qn > 0u)) {
+            __syncwarp();   // ring writes of this trip
+            do {
+               const uint32_t nb = qn < 32u ? qn : 32u;
+               const uint32_t e = sq[(qhead + lane) & (TQ_CAP - 1)];
+               const bool valid = lane < nb;
+               const int owner = (int)(e >> 27); const int item = (int)(e & 0x07ffffffu);
+               Ray rr;
+               rr.o.x = __shfl_sync(FULL, r.o.x, owner); rr.o.y = __shfl_sync(FULL, r.o.y, owner); rr.o.z = __shfl_sync(FULL, r.o.z, owner);
+               rr.d.x = __shfl_sync(FULL, r.d.x, owner); rr.d.y = __shfl_sync(FULL, r.d.y, owner); rr.d.z = __shfl_sync(FULL, r.d.z, owner);
+               rr.tmin = __shfl_sync(FULL, r.tmin, owner);
+               if (ANY) rr.tmax = __shfl_sync(FULL, r.tmax, owner); else rr.tmax = fkeyInv(sown[wbase + owner]);
+               bool found = false;
+               if (ANY) {
+                  if (valid) found = leafItemAny(bvh, item, rr);
+                  if (found) sown[wbase + owner] = 1u;
+                  __syncwarp();
+                  if (sown[threadIdx.x] != 0u && cur != EMPTY && !occ) { occ = true; sp = 0; cur = WAITING; }   // my ray is occluded: drop the rest of its walk
+               } else {
+                  HitRec hh; hh.t = 0; hh.prim = -1; hh.b1 = hh.b2 = 0;
+                  if (valid) found = leafItemNearest(bvh, item, rr, hh);
+                  const unsigned mh = __ballot_sync(FULL, found);
+                  if (mh) {
+                     const uint32_t key = fkey(hh.t);
+                     if (found) atomicMin(&sown[wbase + owner], key);
+                     __syncwarp();
+                     bool win = found && sown[wbase + owner] == key;
+                     const unsigned mw = __ballot_sync(FULL, win);
+                     if (win) { const unsigned peers = __match_any_sync(mw, owner); win = (31 - __clz((int)peers)) == (int)lane; }   // equal t: the pair queued last
+                     if (win) { F4 v_; v_.x = hh.t; v_.y = hh.b1; v_.z = hh.b2; v_.w = i2f(hh.prim); shit[wbase + owner] = v_; }
+                     __syncwarp();
+                     r.tmax = fkeyInv(sown[threadIdx.x]);
+                  }
+               }
+               qhead += nb; qn -= nb;
+            } while (qn >= (uint32_t)TQ_FLUSH);
+         }
+      }
+      // ---- retire rays whose walk is over and whose pairs are all through
+      if (cur == WAITING && (int)(qhead - lastSeq) >= 0) {
+         if (ANY) {
+            if (fuseL && !occ) {   // fused NEE resolve (trace_kernels.cuh): L += pending, one quarter at a time
+               for (int qq = 0; qq < 4; ++qq) {
+                  const size_t at = spec4At(fuseCap, slot, qq);
+                  F4 l = fuseL[at]; const F4 p_ = fuseP[at];
+                  l.x += p_.x; l.y += p_.y; l.z += p_.z; l.w += p_.w;
+                  fuseL[at] = l;
+               }
+            } else if (!fuseL) occl[slot] = occ ? 1 : 0;
+         } else hit[slot] = shit[threadIdx.x];
+         cur = EMPTY;
+      }
+   }
+}
+
+static inline size_t traceWarpQSmemBytes(int maxStack) { return TQ_HEAD_WORDS * sizeof(uint32_t) + traceSmemBytes(maxStack); }
+
+}  // namespace bl

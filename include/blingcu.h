@@ -40,7 +40,8 @@ enum {
    BLINGCU_EINVAL = 1,  /* bad argument / malformed IR                    */
    BLINGCU_ECUDA = 2,   /* CUDA runtime error                             */
    BLINGCU_ENOGPU = 3,  /* no usable device: there is NO CPU fallback      */
-   BLINGCU_ESTATE = 4   /* call out of order (e.g. render before upload)  */
+   BLINGCU_ESTATE = 4,  /* call out of order (e.g. render before upload)  */
+   BLINGCU_EUNSUPPORTED = 5 /* NCCL is not available to this process (multi-GPU film reduction only) */
 };
 
 /* Shape.hs:23-38 */
@@ -311,12 +312,35 @@ int blingcu_eval_texture(blingcu_ctx *, int32_t texture, const float *p, const f
 int blingcu_read_film(blingcu_ctx *, float *wxyz);
 int blingcu_clear_film(blingcu_ctx *);
 int blingcu_film_add_host(blingcu_ctx *, const float *wxyz); /* film += host buffer (resume / manual reduce) */
-int blingcu_film_device(blingcu_ctx *, void **dptr, size_t *n_floats); /* for NCCL allreduce by the host */
+int blingcu_film_device(blingcu_ctx *, void **dptr, size_t *n_floats); /* zero-copy view for the host */
 int blingcu_synchronize(blingcu_ctx *);
 /* enqueue all further work of this context on a caller-owned CUDA stream (cudaStream_t passed as void*), e.g. the
  * stream the host's NCCL all-reduce of the film runs on; NULL restores the context's own stream. Render calls are
  * asynchronous with respect to the host; read_film / get_stats / synchronize wait. */
 int blingcu_set_stream(blingcu_ctx *, void *cuda_stream);
+
+/* ---- multi-GPU: the film sum over GPUs, the one exchange of the path. Replaces the sequential addTile merge
+ * of prender (Rendering.hs:130-134, Image.hs:178-199). Every GPU holds a full scene replica and renders its share of the
+ * sample indices (blingcu_render_slice) into a private film; blingcu_reduce_film sums the films with ncclAllReduce over
+ * NVLink / NVSwitch (root >= 0: ncclReduce onto that rank only) into a second device buffer, `film_sum`, so the private films
+ * keep accumulating. The library owns the communicator and a reduction stream; NCCL is bound at run time (libnccl.so.2).
+ * The reduction is ASYNCHRONOUS: it starts once everything enqueued so far has rendered and overlaps the next render call up
+ * to that call's film kernels. blingcu_read_film_sum waits for it.
+ *   one process per GPU:  rank 0 calls blingcu_comm_unique_id and hands the 128 bytes to the other processes (MPI, a file,
+ *                         torch.distributed ...); every process then calls blingcu_comm_init(ctx, rank, nranks, id);
+ *   one process, n GPUs:  (a Haskell host) n contexts on n devices, blingcu_comm_init_all(ctxs, n); per pass
+ *                         blingcu_render_slice on each context (asynchronous), then blingcu_reduce_film_group(ctxs, n, root).
+ * Without a communicator (or nranks == 1) film_sum is a device copy of film. */
+#define BLINGCU_COMM_ID_BYTES 128
+int blingcu_comm_unique_id(uint8_t id[BLINGCU_COMM_ID_BYTES]);
+int blingcu_comm_init(blingcu_ctx *, int rank, int nranks, const uint8_t id[BLINGCU_COMM_ID_BYTES]);
+int blingcu_comm_init_all(blingcu_ctx *const *ctxs, int n);
+int blingcu_comm_destroy(blingcu_ctx *);
+int blingcu_reduce_film(blingcu_ctx *, int root);
+int blingcu_reduce_film_group(blingcu_ctx *const *ctxs, int n, int root);
+int blingcu_comm_wait(blingcu_ctx *);                       /* the context's render stream waits (on the device) for the reduction in flight */
+int blingcu_read_film_sum(blingcu_ctx *, float *wxyz);      /* waits for the reduction, copies film_sum [H][W][4] to the host */
+int blingcu_film_sum_device(blingcu_ctx *, void **dptr, size_t *n_floats);
 
 int blingcu_get_stats(blingcu_ctx *, blingcu_stats *out);
 int blingcu_reset_stats(blingcu_ctx *);

@@ -187,6 +187,41 @@ def test_edge_scenes_empty_and_unlit():
             assert (e.trace_nearest(rays)["prim"] == -1).all() and not e.trace_occluded(rays).any()
 
 
+def test_state_follows_the_integrator_on_a_reused_context():
+    """ADVICE r1 (high), emulator leg: path scene first, then a direct-lighting scene that needs fewer slots."""
+    e = EmuContext()
+    e.upload_scene(small(load_scene("cornell-box"), 40, 40, 2, 2)); e.render_pass(1, 3)
+    dl = small(load_scene("direct"), 24, 16, 2, 2)
+    e.upload_scene(dl); e.render_pass(1, 5)
+    fe = e.read_film(); e.close()
+    e2 = EmuContext(); e2.upload_scene(dl); e2.render_pass(1, 5)
+    assert np.array_equal(fe, e2.read_film())            # same film as a fresh context
+    e2.close()
+
+
+def test_null_uvs_default_and_null_tables_are_rejected():
+    """tri_uvs == NULL means the default (0,0,1,0,1,1) of TriangleMesh.hs:119-120; null geometry tables
+    with a non-zero count are BLINGCU_EINVAL instead of a crash; batch_samples is range-checked."""
+    import ctypes as C
+    sc = small(load_scene("cornell-box"), 24, 24, 2, 2)
+    e = EmuContext()
+    c, keep = sc.to_c()
+    c.tri_uvs = None
+    e._chk(e._f("upload_scene")(e._h, C.byref(c))); e.scene = sc
+    e.render_pass(1, 2); f0 = e.read_film()
+    sc2 = small(load_scene("cornell-box"), 24, 24, 2, 2)
+    sc2.tri_uvs = np.tile(np.array([0, 0, 1, 0, 1, 1], np.float32), (len(sc2.tri_material), 1))
+    e.upload_scene(sc2); e.render_pass(1, 2)
+    assert np.array_equal(f0, e.read_film())
+    c, keep = sc.to_c()
+    c.tri_verts = None
+    assert e._f("upload_scene")(e._h, C.byref(c)) == 1
+    for bad in (0.5, 1e12, float("nan")):
+        with pytest.raises(api.BlingCuError):
+            e.set_option("batch_samples", bad)
+    e.close()
+
+
 def test_api_error_paths():
     e = EmuContext()
     with pytest.raises(api.BlingCuError) as ex:

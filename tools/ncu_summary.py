@@ -46,6 +46,15 @@ def main():
             continue
         i = col[m]
         print(f"| {label} (`{m}`) | {units[i]} | " + " | ".join(r[i] for r in data) + " |")
+    # every pipe-utilisation / instruction-count / L1 wavefront column the capture holds
+    import re
+    extra = re.compile(r"(sm__inst_executed_pipe_.*pct_of_peak_sustained_active|sm__pipe_.*cycles_active.*pct_of_peak_sustained_active|smsp__inst_executed\.sum$|"
+                       r"l1tex__data_pipe_lsu_wavefronts.*pct|l1tex__data_pipe_lsu_wavefronts\.sum$|l1tex__lsu_writeback_active.*pct|smsp__warps_eligible\.avg\.per_cycle_active|"
+                       r"smsp__average_warp_latency_per_inst_issued|l1tex__t_sectors_pipe_lsu_mem_global_op_ld\.sum$|lts__t_sectors_srcunit_tex_op_read\.sum$)")
+    for h in hdr:
+        if extra.search(h) and h not in dict(METRICS):
+            i = col[h]
+            print(f"| `{h}` | {units[i]} | " + " | ".join(r[i] for r in data) + " |")
 
 
 if __name__ == "__main__":

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--rays", type=int, default=4_000_000)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--option", action="append", default=[])
+    ap.add_argument("--variants", type=int, nargs="*", default=None, help="trace_variant values to time in ONE context (scene uploaded once)")
     a = ap.parse_args()
     scene = make_soup(a.tris, 64, 36, 1, 1)
     from tests.conftest import camera_rays
@@ -43,7 +44,9 @@ def main():
             k, v = kv.split("="); c.set_option(k, float(v))
         c.upload_scene(scene)
         c.set_option("profile_kernels", 1)
-        for name, rays in batches.items():
+        for variant in (a.variants or [None]):
+          if variant is not None: c.set_option("trace_variant", variant)
+          for name, rays in batches.items():
             c.trace_nearest(rays); c.trace_occluded(rays)          # warm-up
             c.reset_stats()
             for _ in range(a.reps):
@@ -53,7 +56,7 @@ def main():
             for _ in range(a.reps):
                 c.trace_occluded(rays)
             kt = c.kernel_times(); ms_a = kt["trace_any"][0] / a.reps
-            print(f"{Path(lib).name:28s} {name:8s} nearest {ms_n:7.3f} ms = {a.rays / ms_n / 1e3:7.1f} Mrays/s   any {ms_a:7.3f} ms = {a.rays / ms_a / 1e3:7.1f} Mrays/s", flush=True)
+            print(f"{Path(lib).name:28s} v{variant} {name:8s} nearest {ms_n:7.3f} ms = {a.rays / ms_n / 1e3:7.1f} Mrays/s   any {ms_a:7.3f} ms = {a.rays / ms_a / 1e3:7.1f} Mrays/s", flush=True)
         c.close()
 
 
