@@ -15,8 +15,12 @@ value      = camera samples fully processed (raygen .. film) by ALL ranks / max-
              resident in HBM (CUDA events on the launching stream).
 e2e        = the same metric through the renderer seam (CudaRenderer: pass -> film on the HOST, PassDone), film
              device->host copy inside the timed region; e2e_trace = blingcu_trace_nearest on HOST ray/hit buffers.
-roofline   = trace_nearest (the dominant kernel): algorithmic bytes per ray x rays per launch / mean
-             launch duration measured live with CUDA events around every launch, vs measured HBM copy bandwidth.
+roofline   = the traversal kernel class that takes most of the step (any-hit on cfg 5), `roofline_nearest` = the other one:
+             algorithmic bytes per ray (node visits / primitive tests counted by the SAME kernels in an extra
+             untimed step) x rays per launch / mean launch duration measured live with CUDA events around every launch.
+             bound = "l1": ncu shows DRAM at 8-25 % and the SMs' L1 data pipe as the busiest unit (scattered 32-byte
+             sectors, one per cycle per SM), so `peak` = SMs x SM clock x 32 B; the HBM view (measured copy bandwidth)
+             is kept beside it as `hbm`, and the ncu counters of the committed capture of this command as `ncu`.
 cpu_baseline / --impl reference = oracle/ (C++ restatement of the reference's CPU algorithm, kd-tree and all)
              on the host cores, bounded sample of the same workload.
 """
@@ -38,7 +42,8 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "path-traced camera samples per second, whole job (Mrays/s in `mrays_per_s`)"
 UNIT = "Msamples/s"
-NODE_BYTES, ITEM_BYTES, RAY_IN_BYTES, HIT_OUT_BYTES = 64, 48, 32, 16     # bling_b200/csrc/bvh.h layout
+NODE_BYTES, ITEM_BYTES, RAY_IN_BYTES, HIT_OUT_BYTES = 64, 64, 32, 16     # bling_b200/csrc/bvh.h layout (leaf items padded to 64 B)
+L1_BYTES_PER_CLK = 32     # scattered global loads move one 32-byte sector per cycle through an SM's L1 data pipe (profiles/r02_trace_warpq.md)
 SEED = 0xB11D6
 
 
@@ -59,6 +64,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-scenes", action="store_true", help="skip the per-scene throughput table (BASELINE.json configs[0..3])")
     ap.add_argument("--option", action="append", default=[], help="key=value passed to blingcu_set_option")
+    ap.add_argument("--lib", default=None, help="A/B builds: another build of libblingcu.so (__graft_entry__.build_variant)")
     return ap.parse_args()
 
 
@@ -171,9 +177,11 @@ def measured_peak():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
-def committed_traffic():
-    """dram bytes per trace_nearest launch from the committed ncu --set full capture of this command (profiles/)."""
-    p = ROOT / "profiles" / "traffic.json"
+def committed_json(name):
+    """a summary of an ncu capture of THIS command, committed under profiles/ (tools/make_r02_profiles.py): r02_traffic.json = DRAM
+    bytes per ray and kernel class over every traversal launch of one step, r02_trace_counters.json = issue-slot utilisation, threads
+    per instruction, L1 / L2 hit rates, pipe utilisations of one launch per class."""
+    p = ROOT / "profiles" / name
     if p.exists():
         try:
             return json.loads(p.read_text())
@@ -203,6 +211,8 @@ def run_b200(a):
     t0 = time.perf_counter()
     scene = build_scene(a)
     t_scene = time.perf_counter() - t0
+    if a.lib:
+        api.Context._lib_path = Path(a.lib)
     ctx = api.Context(local)
     for kv in a.option:
         k, v = kv.split("="); ctx.set_option(k, float(v))
@@ -217,7 +227,12 @@ def run_b200(a):
     class _Dev:
         def __init__(s, ptr, n): s.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
     film_t = torch.as_tensor(_Dev(fptr, fn), device=torch.device("cuda", local))
-    film_sum = torch.empty_like(film_t) if world > 1 else None
+    if world > 1:
+        # the film sum is the LIBRARY's (blingcu_reduce_film: ncclAllReduce on its own stream, overlapped with the next
+        # slice); torch.distributed only carries the communicator id to the other ranks and serves barrier / max-over-ranks
+        box = [api.Context.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(rank, world, box[0])
 
     sps = a.sps
     spp = scene.spp
@@ -229,8 +244,7 @@ def run_b200(a):
         s1 = min(spp, s0 + sps)
         ctx.render_slice(p, SEED, s0, s1)
         if world > 1 and reduce:
-            film_sum.copy_(film_t)
-            dist.all_reduce(film_sum, op=dist.ReduceOp.SUM)
+            ctx.reduce_film()            # film_sum = sum over ranks (asynchronous)
 
     def barrier():
         if world > 1:
@@ -249,6 +263,8 @@ def run_b200(a):
         ev0.record(stream)
         for i in range(a.steps):
             step(a.warmup + i)
+        if world > 1:
+            ctx.comm_wait()              # the render stream waits for the last reduction: it is inside the timed region
         ev1.record(stream)
         barrier()
         ms = ev0.elapsed_time(ev1)
@@ -271,7 +287,7 @@ def run_b200(a):
         mrays = (rays_n + rays_s) / (ms_max * 1e-3) / 1e6
 
         # ---- traversal counters for the roofline: one more (untimed) step with the instrumented kernel on rank 0
-        roofline = None
+        roofline = None; roofline_other = None
         if rank == 0:
             ctx.set_option("traversal_stats", 1); ctx.reset_stats()
             film_keep = film_t.clone()
@@ -280,36 +296,57 @@ def run_b200(a):
             film_t.copy_(film_keep)
             s2 = ctx.stats()
             ctx.set_option("traversal_stats", 0)
-            n_nodes = s2["nodes_traversed"] / max(1, s2["rays_counted"])
-            n_prims = s2["intersections"] / max(1, s2["rays_counted"])
-            b_ray = RAY_IN_BYTES + HIT_OUT_BYTES + n_nodes * NODE_BYTES + n_prims * ITEM_BYTES
-            tn_ms, tn_launches = kt["trace_nearest"]
-            my_rays_n = float(st["rays_camera"] + st["rays_extension"] + st["rays_mis"] - st["rays_mis_any"])
             peak, peak_src = measured_peak()
-            achieved = my_rays_n * b_ray / (tn_ms * 1e-3) / 1e9 if tn_ms > 0 else 0.0
-            tr = committed_traffic()
-            roofline = {"kernel": "kTracePersistent<nearest> (bling_b200/csrc/trace_kernels.cuh)", "bound": "hbm",
-                        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                        "traffic": (tr or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+            prop = torch.cuda.get_device_properties(local)
+            sm_mhz = (clk or {}).get("sm_mhz") or (clk or {}).get("sm_max_mhz") or 1965.0
+            l1_peak = prop.multi_processor_count * sm_mhz * 1e6 * L1_BYTES_PER_CLK / 1e9
+            ncu = committed_json("r02_trace_counters.json")
+            tr = committed_json("r02_traffic.json")
+
+            def class_roofline(cls, label, out_bytes, nodes, prims, counted, my_rays):
+                n_nodes, n_prims = nodes / max(1, counted), prims / max(1, counted)
+                b_ray = RAY_IN_BYTES + out_bytes + n_nodes * NODE_BYTES + n_prims * ITEM_BYTES
+                c_ms, c_launches = kt[cls]
+                live = max(1, c_launches // 2) if cls == "trace_nearest" else max(1, c_launches)   # every second nearest-hit launch is the (empty) MIS queue
+                achieved = my_rays * b_ray / (c_ms * 1e-3) / 1e9 if c_ms > 0 else 0.0
+                per_ray = ((tr or {}).get(cls) or {}).get("dram_bytes_per_ray")
+                return {"kernel": label, "bound": "l1", "achieved": achieved, "peak": l1_peak, "unit": "GB/s", "frac": achieved / l1_peak,
+                        "peak_source": f"{prop.multi_processor_count} SMs x {sm_mhz:.0f} MHz x {L1_BYTES_PER_CLK} B/clk: the L1 data pipe moves one 32-byte sector per cycle "
+                                       "per SM for scattered loads, and ncu shows it as the busiest unit of this kernel (DRAM 8-25 %)",
+                        "hbm": {"achieved": achieved, "peak": peak, "frac": achieved / peak, "peak_source": peak_src,
+                                "note": "algorithmic bytes against HBM copy bandwidth: most of them are served by L2 (hit rate 60-80 %), this is not what limits the kernel"},
+                        "traffic": per_ray * my_rays / live if per_ray else None,
+                        "traffic_source": (tr or {}).get("source") if per_ray else None,
                         "bytes_per_ray": b_ray, "nodes_per_ray": n_nodes, "prims_per_ray": n_prims,
-                        "rays_per_launch": my_rays_n / max(1, tn_launches), "launches": tn_launches,
-                        "ms_per_launch": tn_ms / max(1, tn_launches),
-                        "share_of_step": tn_ms / ms if ms > 0 else None,
-                        "mrays_per_s_in_kernel": my_rays_n / (tn_ms * 1e-3) / 1e6 if tn_ms > 0 else None,
-                        "kernel_ms_by_class": {k: round(v[0], 3) for k, v in kt.items()},
-                        "launches_by_class": {k: v[1] for k, v in kt.items()}}
+                        "rays_per_launch": my_rays / live, "launches": c_launches, "ms_per_launch": c_ms / live,
+                        "share_of_step": c_ms / ms if ms > 0 else None,
+                        "mrays_per_s_in_kernel": my_rays / (c_ms * 1e-3) / 1e6 if c_ms > 0 else None,
+                        "ncu": (ncu or {}).get(cls)}
+            my_rays_n = float(st["rays_camera"] + st["rays_extension"] + st["rays_mis"] - st["rays_mis_any"])
+            my_rays_a = float(st["rays_shadow"] + st["rays_mis_any"])
+            r_near = class_roofline("trace_nearest", "kTraceWarpQ<nearest> (bling_b200/csrc/trace_warpq.cuh)", HIT_OUT_BYTES,
+                                    s2["nodes_traversed"], s2["intersections"], s2["rays_counted"], my_rays_n)
+            r_any = class_roofline("trace_any", "kTraceWarpQ<any> (bling_b200/csrc/trace_warpq.cuh)", 1,
+                                   s2["any_nodes_traversed"], s2["any_intersections"], s2["any_rays_counted"], my_rays_a)
+            roofline, roofline_other = (r_any, r_near) if kt["trace_any"][0] >= kt["trace_nearest"][0] else (r_near, r_any)
+            roofline["kernel_ms_by_class"] = {k: round(v[0], 3) for k, v in kt.items()}
+            roofline["launches_by_class"] = {k: v[1] for k, v in kt.items()}
 
         # ---- e2e: the renderer seam with the film landing in HOST memory every step
         e2e = None; e2e_trace = None
         if not a.no_e2e:
             film_bytes = fn * 4
             host = torch.empty(fn, dtype=torch.float32).pin_memory()
+            host_np = host.numpy()
             barrier(); ctx.reset_stats()
             t0 = time.perf_counter()
             for i in range(a.steps):
                 step(a.warmup + a.steps + i)
-                host.copy_(film_sum if world > 1 else film_t, non_blocking=True)
-                stream.synchronize()                              # PassDone: the host owns the image now
+                if world > 1:
+                    ctx.read_film_sum(host_np)                    # waits for the reduction, film_sum -> pinned host memory
+                else:
+                    host.copy_(film_t, non_blocking=True)
+                    stream.synchronize()                          # PassDone: the host owns the image now
             barrier()
             dt = time.perf_counter() - t0
             se = ctx.stats()
@@ -391,7 +428,7 @@ def run_b200(a):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "mrays_per_s": mrays, "n_gpus": n_gpus, "steps": a.steps,
                 "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, n_gpus),
-                "clocks": clk, "e2e": e2e, "e2e_trace": e2e_trace, "gpu_launches": int(launches), "roofline": roofline,
+                "clocks": clk, "e2e": e2e, "e2e_trace": e2e_trace, "gpu_launches": int(launches), "roofline": roofline, "roofline_other": roofline_other,
                 "cpu_baseline": cpu_baseline,
                 "rays": {"nearest_hit_queries": rays_n, "any_hit_queries": rays_s, "per_sample": (rays_n + rays_s) / max(1.0, samples)},
                 "bvh": {"nodes": st["bvh_nodes"], "leaf_items": st["bvh_leaf_items"], "max_stack": st["bvh_max_stack"]},

@@ -20,7 +20,7 @@ SYMBOLS = ["create", "destroy", "last_error", "upload_scene", "trace_nearest", "
            "render_pass", "render_slice", "render_samples", "eval_texture", "read_film", "clear_film", "film_add_host", "film_device",
            "synchronize", "set_stream", "get_stats", "reset_stats", "set_option", "sample_extent", "kernel_times",
            "comm_unique_id", "comm_init", "comm_init_all", "comm_destroy", "reduce_film", "reduce_film_group", "comm_wait",
-           "read_film_sum", "film_sum_device"]
+           "read_film_sum", "film_sum_device", "host_alloc", "host_free"]
 COMM_ID_BYTES = 128
 
 
@@ -69,6 +69,8 @@ def load_library(path=LIB_PATH, prefix="blingcu"):
     f("comm_wait").argtypes = [P]
     f("read_film_sum").argtypes = [P, P]
     f("film_sum_device").argtypes = [P, C.POINTER(P), C.POINTER(C.c_size_t)]
+    f("host_alloc").argtypes = [P, C.c_size_t, C.POINTER(P)]
+    f("host_free").argtypes = [P, P]
     return L
 
 
@@ -97,6 +99,9 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
+            for p in getattr(self, "_pinned", []):
+                self._f("host_free")(self._h, C.c_void_p(p))
+            self._pinned = []
             self._f("destroy")(self._h); self._h = None
 
     def __del__(self):
@@ -121,13 +126,24 @@ class Context:
         return tuple(x.value for x in v)
 
     # ---- explicit ray batches
-    def trace_nearest(self, rays: np.ndarray) -> np.ndarray:
-        rays = np.ascontiguousarray(rays, IR.RAY_DTYPE); out = np.zeros(len(rays), IR.HIT_DTYPE)
+    def host_array(self, n: int, dtype) -> np.ndarray:
+        """an n-element array in page-locked host memory (blingcu_host_alloc): ray / hit buffers in it are transferred in
+        place by trace_nearest / trace_occluded. Freed with the context (or host_free)."""
+        dt = np.dtype(dtype); p = C.c_void_p()
+        self._chk(self._f("host_alloc")(self._h, max(1, n * dt.itemsize), C.byref(p)))
+        buf = (C.c_uint8 * max(1, n * dt.itemsize)).from_address(p.value)
+        self._pinned = getattr(self, "_pinned", []); self._pinned.append(p.value)
+        return np.frombuffer(buf, dtype=dt, count=n)
+
+    def trace_nearest(self, rays: np.ndarray, out: np.ndarray = None) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, IR.RAY_DTYPE)
+        if out is None: out = np.zeros(len(rays), IR.HIT_DTYPE)
         self._chk(self._f("trace_nearest")(self._h, rays.ctypes.data, len(rays), out.ctypes.data))
         return out
 
-    def trace_occluded(self, rays: np.ndarray) -> np.ndarray:
-        rays = np.ascontiguousarray(rays, IR.RAY_DTYPE); out = np.zeros(len(rays), np.uint8)
+    def trace_occluded(self, rays: np.ndarray, out: np.ndarray = None) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, IR.RAY_DTYPE)
+        if out is None: out = np.zeros(len(rays), np.uint8)
         self._chk(self._f("trace_occluded")(self._h, rays.ctypes.data, len(rays), out.ctypes.data))
         return out
 

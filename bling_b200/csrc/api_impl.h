@@ -84,6 +84,12 @@ static thread_local std::string g_createError;
       *dptr = c->p.film; *nf = (size_t)c->p.hs.W * c->p.hs.H * 4;                                                                \
       return 0;                                                                                                                  \
    }                                                                                                                             \
+   int PFX##_host_alloc(PFX##_ctx_t *c, size_t bytes, void **out) {                                                              \
+      if (!c || !out) return BLINGCU_EINVAL;                                                                                     \
+      *out = nullptr;                                                                                                            \
+      return c->p.be.guard(c->p.err, [&]() { *out = c->p.be.hostAlloc(bytes); return 0; });                                       \
+   }                                                                                                                             \
+   int PFX##_host_free(PFX##_ctx_t *c, void *p) { if (!c) return BLINGCU_EINVAL; return c->p.be.guard(c->p.err, [&]() { c->p.be.hostFree(p); return 0; }); } \
    int PFX##_comm_unique_id(uint8_t *id) {                                                                                       \
       if (!id) return BLINGCU_EINVAL;                                                                                            \
       return BACKEND::commUniqueId(id, bl::g_createError);                                                                       \

@@ -18,8 +18,11 @@
 // limiter with 128-byte nodes (one L1 wavefront per lane per 16 bytes); 64-byte nodes halve it and halve the
 // L2/DRAM bytes per visit. The builder (bvh_build.cpp) builds a binned-SAH binary tree, collapses it into 4-wide
 // nodes by repeatedly opening the child with the largest area, then quantises.
-// Leaf item = 48 B = 3 x 16-byte loads:
-//   triangle: (p1.xyz, ref) (e1.xyz, 0) (e2.xyz, -)       shape: (-, -, -, ref) (-, -, -, 1 + shape index) -      (ref: see HitRec)
+// Leaf item = 64 B = 2 x 32-byte loads (BL_ITEM_F4 = 4; the fourth float4 is padding):
+//   triangle: (p1.xyz, ref) (e1.xyz, 0) (e2.xyz, -) -       shape: (-, -, -, ref) (-, -, -, 1 + shape index) - -      (ref: see HitRec)
+// Why padded: ncu (profiles/r02_trace_warpq.md) shows the L1 data pipe as the busiest unit of the traversal kernels, and for
+// scattered accesses it moves one 32-byte sector per load instruction per lane: a 48-byte record read as three LDG.128 costs three
+// wavefronts, a 64-byte record read as two LDG.256 costs two. DRAM and L2 (8-25 % / 33-44 % busy) have room for the extra 16 bytes.
 // Boxes are inflated by the builder, so the slab test needs no epsilon (see bvh_build.cpp).
 #pragma once
 #include "geom.h"
@@ -48,8 +51,26 @@ HD uint32_t refIndex(int ref) { return (uint32_t)ref & 0x03ffffffu; }
 HD int mkRef(bool shape, int kind, uint32_t index) { return (int)((shape ? 0x80000000u : 0u) | ((uint32_t)kind << 26) | index); }
 
 
+#ifndef BL_ITEM_F4
+#define BL_ITEM_F4 4     // F4 per leaf item (64 B); 3 = the packed 48-byte records of round 1 (A/B builds only)
+#endif
+#if defined(__CUDACC__)
+__device__ __forceinline__ void ld8(const F4 *p, F4 &a, F4 &b) {   // one 32-byte load (LDG.E.256 on sm_100)
+   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+#endif
+HD void ldItem(const F4 *items, int item, F4 &q0, F4 &q1, F4 &q2) {
+   const F4 *p = items + (size_t)BL_ITEM_F4 * (size_t)item;
+#if defined(__CUDA_ARCH__) && BL_ITEM_F4 == 4
+   F4 q3; ld8(p, q0, q1); ld8(p + 2, q2, q3);
+#else
+   q0 = ld4(p); q1 = ld4(p + 1); q2 = ld4(p + 2);
+#endif
+}
+
 HD bool leafItemNearest(const Bvh &bvh, int item, Ray &r, HitRec &h) {
-   F4 q0 = ld4(bvh.items + 3 * item), q1 = ld4(bvh.items + 3 * item + 1), q2 = ld4(bvh.items + 3 * item + 2);   // one 48-byte record, three independent LDG.128
+   F4 q0, q1, q2; ldItem(bvh.items, item, q0, q1, q2);
    int tag = f2i(q1.w);
    if (tag == 0) {
       float t, b1, b2;
@@ -64,7 +85,7 @@ HD bool leafItemNearest(const Bvh &bvh, int item, Ray &r, HitRec &h) {
    return true;
 }
 HD bool leafItemAny(const Bvh &bvh, int item, const Ray &r) {
-   F4 q0 = ld4(bvh.items + 3 * item), q1 = ld4(bvh.items + 3 * item + 1), q2 = ld4(bvh.items + 3 * item + 2);   // one 48-byte record, three independent LDG.128
+   F4 q0, q1, q2; ldItem(bvh.items, item, q0, q1, q2);
    int tag = f2i(q1.w);
    if (tag == 0) {
       float t, b1, b2;
@@ -82,11 +103,13 @@ HD bool leafItemAny(const Bvh &bvh, int item, const Ray &r) {
 #else
 #define BL_FMA(a, b, c) fmaf(a, b, c)
 #endif
-struct RayPre { V3 idir, ood; };   // 1/d and o/d: plane distance = plane * idir - ood (one FMA)
-// |1/d| is clamped to 1e18 so that plane * idir - ood never evaluates inf - inf: an axis-parallel ray then sees
+struct RayPre { V3 idir; };   // 1/d: plane distance = (plane - o) * idir; the node-constant part (P - o) * idir is folded into the FMA's addend
+// |1/d| is clamped to 1e18 so that the distances never evaluate inf - inf: an axis-parallel ray then sees
 // (-huge, +huge) when its origin is inside the slab and two same-signed huge values (a miss) when it is outside.
+// (Round 1 also kept o/d per ray; that cost three registers the 64-register traversal kernels do not have -- ncu showed them
+// spilled and re-read from local memory at every node step -- for no fewer instructions: (P - o) * idir is one FADD + one FMUL.)
 HD float safeInv(float d) { return fminf(fmaxf(1.0f / d, -1e18f), 1e18f); }
-HD RayPre rayPre(const Ray &r) { RayPre p; p.idir = mk3(safeInv(r.d.x), safeInv(r.d.y), safeInv(r.d.z)); p.ood = p.idir * r.o; return p; }
+HD RayPre rayPre(const Ray &r) { RayPre p; p.idir = mk3(safeInv(r.d.x), safeInv(r.d.y), safeInv(r.d.z)); return p; }
 
 HD uint32_t f2u(float f) { return (uint32_t)f2i(f); }
 HD float u2f(uint32_t u) { return i2f((int)u); }
@@ -108,10 +131,10 @@ HD void node4Near(const F4 &n0, const F4 &n2, const F4 &n3, const Ray &r, const 
 #endif
    const uint32_t E = f2u(n0.w);
    const float ax = u2f((E & 0xffu) << 23) * p.idir.x, ay = u2f(((E >> 8) & 0xffu) << 23) * p.idir.y, az = u2f(((E >> 16) & 0xffu) << 23) * p.idir.z;
-   // addend: P/d - o/d - 2^23 * cell/d
-   const float bx = BL_FMA(-8388608.0f, ax, BL_FMA(n0.x, p.idir.x, -p.ood.x));
-   const float by = BL_FMA(-8388608.0f, ay, BL_FMA(n0.y, p.idir.y, -p.ood.y));
-   const float bz = BL_FMA(-8388608.0f, az, BL_FMA(n0.z, p.idir.z, -p.ood.z));
+   // addend: (P - o)/d - 2^23 * cell/d
+   const float bx = BL_FMA(-8388608.0f, ax, (n0.x - r.o.x) * p.idir.x);
+   const float by = BL_FMA(-8388608.0f, ay, (n0.y - r.o.y) * p.idir.y);
+   const float bz = BL_FMA(-8388608.0f, az, (n0.z - r.o.z) * p.idir.z);
    const uint32_t qlx = f2u(n2.x), qly = f2u(n2.y), qlz = f2u(n2.z), qhx = f2u(n2.w), qhy = f2u(n3.x), qhz = f2u(n3.y);
    const bool px = p.idir.x >= 0.0f, py = p.idir.y >= 0.0f, pz = p.idir.z >= 0.0f;
    const uint32_t nx = px ? qlx : qhx, fx = px ? qhx : qlx, ny = py ? qly : qhy, fy = py ? qhy : qly, nz = pz ? qlz : qhz, fz = pz ? qhz : qlz;

@@ -10,7 +10,9 @@
 #include "trace_kernels.cuh"
 #include "comm.h"
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <cstring>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -117,11 +119,11 @@ struct CudaBackend {
       recs.clear();
    }
    void kernelTimes(double *ms, uint64_t *l, int n) { collect(); for (int i = 0; i < n; ++i) { ms[i] = i < BLINGCU_KC_COUNT ? clsMs[i] : 0; l[i] = i < BLINGCU_KC_COUNT ? clsLaunches[i] : 0; } }
-   void resetProfile() { collect(); for (int i = 0; i < BLINGCU_KC_COUNT; ++i) { clsMs[i] = 0; clsLaunches[i] = 0; } if (tcfg.travCounters) cudaMemsetAsync(tcfg.travCounters, 0, 3 * sizeof(unsigned long long), stream); }
-   void traversalTotals(uint64_t &nodes, uint64_t &prims, uint64_t &rays) {
-      nodes = prims = rays = 0;
+   void resetProfile() { collect(); for (int i = 0; i < BLINGCU_KC_COUNT; ++i) { clsMs[i] = 0; clsLaunches[i] = 0; } if (tcfg.travCounters) cudaMemsetAsync(tcfg.travCounters, 0, 6 * sizeof(unsigned long long), stream); }
+   void traversalTotals(uint64_t *six) {   // nearest-hit nodes, prims, rays; any-hit nodes, prims, rays
+      for (int i = 0; i < 6; ++i) six[i] = 0;
       if (!tcfg.travCounters) return;
-      unsigned long long h[3]; download(h, tcfg.travCounters, sizeof(h)); nodes = h[0]; prims = h[1]; rays = h[2];
+      unsigned long long h[6]; download(h, tcfg.travCounters, sizeof(h)); for (int i = 0; i < 6; ++i) six[i] = h[i];
    }
 
    int init(int dev, std::string &err) {
@@ -139,9 +141,12 @@ struct CudaBackend {
       // the traversal stack lives in dynamic shared memory: allow the builder's worst case (BL_STACK levels)
       cudaFuncSetAttribute(kTracePersistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceSmemBytes(BL_STACK));
       cudaFuncSetAttribute(kTracePersistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceSmemBytes(BL_STACK));
-      cudaFuncSetAttribute(kTraceWarpQ<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceWarpQSmemBytes(BL_STACK));
-      cudaFuncSetAttribute(kTraceWarpQ<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceWarpQSmemBytes(BL_STACK));
-      cudaFuncSetAttribute(kTraceWarpQ<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceWarpQSmemBytes(BL_STACK));
+      const int wq = (int)traceWarpQSmemBytes(BL_STACK);
+      cudaFuncSetAttribute(kTraceWarpQ<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
+      cudaFuncSetAttribute(kTraceWarpQ<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
+      cudaFuncSetAttribute(kTraceWarpQ<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
+      cudaFuncSetAttribute(kTraceWarpQ<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
+      cudaFuncSetAttribute(kTraceWarpQ<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
       return 0;
    }
    // run on a caller-owned stream (e.g. torch's current stream, so an NCCL all-reduce of the film orders after the
@@ -154,6 +159,8 @@ struct CudaBackend {
       if (fc.stream) { cudaStreamDestroy(fc.stream); fc.stream = nullptr; }
       if (fc.rendered) { cudaEventDestroy(fc.rendered); fc.rendered = nullptr; }
       if (fc.reduced) { cudaEventDestroy(fc.reduced); fc.reduced = nullptr; }
+      freeTracePipe();
+      if (sIn) { cudaStreamDestroy(sIn); sIn = nullptr; } if (sOut) { cudaStreamDestroy(sOut); sOut = nullptr; }
       if (tcfg.workCounter) { cudaFree(tcfg.workCounter); tcfg.workCounter = nullptr; }
       if (tcfg.travCounters) { cudaFree(tcfg.travCounters); tcfg.travCounters = nullptr; }
       if (ownStream) { cudaStreamDestroy(ownStream); ownStream = nullptr; }
@@ -178,13 +185,16 @@ struct CudaBackend {
       if (k == "profile_kernels") { collect(); profile = v != 0; return true; }
       if (k == "traversal_stats") {
          tcfg.countStats = v != 0;
-         if (tcfg.countStats && !tcfg.travCounters) { tcfg.travCounters = (unsigned long long *)alloc(3 * sizeof(unsigned long long)); zero(tcfg.travCounters, 3 * sizeof(unsigned long long)); }
+         if (tcfg.countStats && !tcfg.travCounters) { tcfg.travCounters = (unsigned long long *)alloc(6 * sizeof(unsigned long long)); zero(tcfg.travCounters, 6 * sizeof(unsigned long long)); }
          return true;
       }
       if (k == "trace_blocks_per_sm") { tcfg.blocksPerSm = (int)v; return true; }
+      if (k == "trace_chunk") { if (!(v >= 1024) || v > 2147483647.0) return false; traceChunk = (size_t)v; return true; }
+      if (k == "copy_threads") { if (!(v >= 1) || v > 64) return false; copyThreads = (int)v; return true; }
       return false;
    }
    void setMaxStack(int m) { tcfg.maxStack = m; }
+   void setBvh(const Bvh &b) { tcfg.bvh = b; }
    // ---- film reduction over ranks (comm.h). Per-process mode: comm_unique_id on one rank, comm_init on every rank. In-process
    // mode (one host thread driving several contexts, e.g. a Haskell host): comm_init_all / reduce_film_group wrap the same
    // calls in ncclGroupStart/End.
@@ -246,6 +256,91 @@ struct CudaBackend {
    void waitReduced() { if (fc.pending) { cudaStreamWaitEvent(stream, fc.reduced, 0); fc.pending = false; } }
    void syncComm() { if (fc.stream) cudaStreamSynchronize(fc.stream); }
    void downloadOnComm(void *d, const void *s, size_t n) { CU(cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToHost, fc.stream ? fc.stream : stream)); CU(cudaStreamSynchronize(fc.stream ? fc.stream : stream)); }
+
+   // ---- explicit ray batches on HOST buffers (blingcu_trace_nearest / _occluded), pipelined: the batch is cut into chunks and
+   // three of them are in flight at any time -- chunk k+1 goes host -> device on the copy-in stream while chunk k is traced on the
+   // context's stream and chunk k-1 goes device -> host on the copy-out stream (PCIe is full duplex). Buffers that are already
+   // page-locked (blingcu_host_alloc, cudaHostRegister, torch pin_memory) are used as they are; pageable ones are staged through
+   // the context's own pinned ring by a few helper threads (one memcpy thread moves ~10 GB/s, the link 50).
+   enum { TB_SLOTS = 3 };
+   struct TraceSlot { void *hIn = nullptr, *hOut = nullptr; F4 *dR = nullptr, *dO = nullptr, *dD = nullptr, *dH = nullptr; uint8_t *dC = nullptr; cudaEvent_t in = nullptr, done = nullptr, out = nullptr; };
+   TraceSlot tslot[TB_SLOTS]; size_t tchunkCap = 0; cudaStream_t sIn = nullptr, sOut = nullptr;
+   size_t traceChunk = 1u << 20;   // rays per chunk (option "trace_chunk")
+   int copyThreads = 4;            // helper threads for pageable host buffers (option "copy_threads")
+   void freeTracePipe() {
+      for (TraceSlot &t : tslot) {
+         if (t.hIn) cudaFreeHost(t.hIn); if (t.hOut) cudaFreeHost(t.hOut);
+         cudaFree(t.dR); cudaFree(t.dO); cudaFree(t.dD); cudaFree(t.dH); cudaFree(t.dC);
+         if (t.in) cudaEventDestroy(t.in); if (t.done) cudaEventDestroy(t.done); if (t.out) cudaEventDestroy(t.out);
+         t = TraceSlot{};
+      }
+      tchunkCap = 0;
+   }
+   void ensureTracePipe(size_t chunk) {
+      if (!sIn) { CU(cudaStreamCreateWithFlags(&sIn, cudaStreamNonBlocking)); CU(cudaStreamCreateWithFlags(&sOut, cudaStreamNonBlocking)); }
+      if (chunk <= tchunkCap) return;
+      freeTracePipe();
+      for (TraceSlot &t : tslot) {
+         CU(cudaMallocHost(&t.hIn, chunk * sizeof(blingcu_ray))); CU(cudaMallocHost(&t.hOut, chunk * sizeof(blingcu_hit)));
+         CU(cudaMalloc(&t.dR, chunk * 2 * sizeof(F4))); CU(cudaMalloc(&t.dO, chunk * sizeof(F4))); CU(cudaMalloc(&t.dD, chunk * sizeof(F4)));
+         CU(cudaMalloc(&t.dH, chunk * sizeof(F4))); CU(cudaMalloc(&t.dC, chunk));
+         CU(cudaEventCreateWithFlags(&t.in, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&t.out, cudaEventDisableTiming));
+      }
+      tchunkCap = chunk;
+   }
+   static bool isPinned(const void *p) {
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+      return a.type == cudaMemoryTypeHost;
+   }
+   void parallelCopy(void *dst, const void *src, size_t n) {
+      const int nt = (n < (4u << 20) || copyThreads <= 1) ? 1 : copyThreads;
+      if (nt == 1) { std::memcpy(dst, src, n); return; }
+      std::vector<std::thread> th;
+      const size_t per = (n / nt + 4095) & ~(size_t)4095;
+      for (int i = 1; i < nt; ++i) { const size_t b = std::min(n, per * i), e = std::min(n, per * (i + 1)); if (e > b) th.emplace_back([=]() { std::memcpy((char *)dst + b, (const char *)src + b, e - b); }); }
+      std::memcpy(dst, src, std::min(n, per));
+      for (std::thread &t : th) t.join();
+   }
+   // returns false when the backend does not take the batch (never here); hits are converted to ABI form on the device
+   bool traceHostBatch(const blingcu_ray *rays, size_t n, blingcu_hit *outHit, uint8_t *outOccl, const DScene *dscene) {
+      const size_t chunk = std::min(n, traceChunk);
+      ensureTracePipe(chunk);
+      const bool pinIn = isPinned(rays), pinOut = outHit ? isPinned(outHit) : isPinned(outOccl);
+      const size_t nChunks = (n + chunk - 1) / chunk;
+      const size_t outStride = outHit ? sizeof(blingcu_hit) : 1;
+      auto drain = [&](size_t k) {   // chunk k has landed in its slot's staging buffer: hand it to the caller's (pageable) buffer
+         TraceSlot &t = tslot[k % TB_SLOTS];
+         CU(cudaEventSynchronize(t.out));
+         if (!pinOut) { const size_t b = k * chunk, m = std::min(chunk, n - b); parallelCopy((char *)(outHit ? (void *)outHit : (void *)outOccl) + b * outStride, t.hOut, m * outStride); }
+      };
+      for (size_t k = 0; k < nChunks; ++k) {
+         TraceSlot &t = tslot[k % TB_SLOTS];
+         if (k >= TB_SLOTS) drain(k - TB_SLOTS);   // the slot is free again (its device buffers and staging too)
+         const size_t b = k * chunk, m = std::min(chunk, n - b);
+         const void *src = rays + b;
+         if (!pinIn) { parallelCopy(t.hIn, src, m * sizeof(blingcu_ray)); src = t.hIn; }
+         CU(cudaMemcpyAsync(t.dR, src, m * sizeof(blingcu_ray), cudaMemcpyHostToDevice, sIn));
+         CU(cudaEventRecord(t.in, sIn));
+         CU(cudaStreamWaitEvent(stream, t.in, 0));
+         tag(BLINGCU_KC_OTHER); run(SplitRaysBody{t.dR, t.dO, t.dD}, (uint32_t)m);
+         void *dsrc;
+         if (outHit) {
+            tag(BLINGCU_KC_TRACE_NEAREST); traceNearest(nullptr, nullptr, (uint32_t)m, dscene, t.dO, t.dD, t.dH);
+            tag(BLINGCU_KC_OTHER); run(HitToAbiBody{dscene, t.dH}, (uint32_t)m);
+            dsrc = t.dH;
+         } else { tag(BLINGCU_KC_TRACE_ANY); traceAny(nullptr, nullptr, (uint32_t)m, dscene, t.dO, t.dD, t.dC); dsrc = t.dC; }
+         CU(cudaEventRecord(t.done, stream));
+         CU(cudaStreamWaitEvent(sOut, t.done, 0));
+         void *dst = pinOut ? (void *)((char *)(outHit ? (void *)outHit : (void *)outOccl) + b * outStride) : t.hOut;
+         CU(cudaMemcpyAsync(dst, dsrc, m * outStride, cudaMemcpyDeviceToHost, sOut));
+         CU(cudaEventRecord(t.out, sOut));
+      }
+      for (size_t k = (nChunks > TB_SLOTS ? nChunks - TB_SLOTS : 0); k < nChunks; ++k) drain(k);
+      return true;
+   }
+   void *hostAlloc(size_t n) { void *p = nullptr; CU(cudaMallocHost(&p, n ? n : 1)); return p; }
+   void hostFree(void *p) { if (p) cudaFreeHost(p); }
 
    void *alloc(size_t n) { void *p = nullptr; CU(cudaMalloc(&p, n ? n : 1)); return p; }
    void free(void *p) { if (p) cudaFree(p); }

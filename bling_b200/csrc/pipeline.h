@@ -142,10 +142,10 @@ struct Pipeline {
       bi.threads = (int)std::max(1u, std::thread::hardware_concurrency());
       BvhBuildOutput bo;
       if (bvhBuild(bi, bo)) return fail(BLINGCU_EINVAL, "too many primitives");
-      std::vector<F4> items(3 * (nprim ? nprim : 1));
+      std::vector<F4> items((size_t)BL_ITEM_F4 * (nprim ? nprim : 1), F4{0, 0, 0, 0});
       for (size_t k = 0; k < nprim; ++k) {
          uint32_t src = bo.order[k];
-         F4 *q = &items[3 * k];
+         F4 *q = &items[(size_t)BL_ITEM_F4 * k];
          if (src < nt) {
             const float *v = ir->tri_verts + 9 * (size_t)src;
             q[0] = F4{v[0], v[1], v[2], i2f(mkRef(false, shadeKind[ir->tri_material[src]], (uint32_t)src))};
@@ -178,7 +178,7 @@ struct Pipeline {
          hs.tri_n = (ir->tri_normals && nt) ? up<float>(ir->tri_normals, 9 * nt) : nullptr;
       }
       { std::vector<int32_t> tprim(nt ? nt : 1, 0); for (size_t i = 0; i < nt; ++i) tprim[i] = itemPrim[i]; hs.tri_prim = up<int32_t>(tprim.data(), tprim.size()); }
-      hs.shapes = up<blingcu_shape>(ir->shapes, ns); hs.bvh.shapes = hs.shapes;
+      hs.shapes = up<blingcu_shape>(ir->shapes, ns); hs.bvh.shapes = hs.shapes; be.setBvh(hs.bvh);
       hs.materials = up<blingcu_material>(ir->materials, ir->n_materials);
       hs.textures = up<blingcu_texture>(ir->textures, ir->n_textures); nTextures = ir->n_textures;
       hs.lights = up<blingcu_light>(ir->lights, ir->n_lights); hs.n_lights = (int)ir->n_lights;
@@ -549,6 +549,8 @@ struct Pipeline {
       if (!uploaded) return fail(BLINGCU_ESTATE, "trace before upload_scene");
       if (n == 0) return 0;
       if (n > 0x7fffffffu) return fail(BLINGCU_EINVAL, "too many rays");
+      // the product backend pipelines host batches (copy-in, traversal and copy-out of neighbouring chunks overlap)
+      if (!nodes && be.traceHostBatch(rays, n, outHit, outOccl, dscene)) return 0;
       if (n > tbCap) {
          freeTraceScratch();
          tb[0] = be.alloc(sizeof(F4) * 2 * n); tb[1] = be.alloc(sizeof(F4) * n); tb[2] = be.alloc(sizeof(F4) * n);
@@ -590,7 +592,7 @@ struct Pipeline {
          out->samples = s[S_SAMPLES]; out->rays_camera = s[S_CAM]; out->rays_extension = s[S_EXT]; out->rays_mis = s[S_MIS];
          out->rays_shadow = s[S_SHADOW]; out->dropped_samples = s[S_DROPPED]; out->rays_mis_culled = s[S_MISCULL]; out->rays_ext_culled = s[S_EXTCULL]; out->rays_mis_any = s[S_MISANY];
       }
-      be.traversalTotals(out->nodes_traversed, out->intersections, out->rays_counted);
+      { uint64_t t6[6]; be.traversalTotals(t6); out->nodes_traversed = t6[0]; out->intersections = t6[1]; out->rays_counted = t6[2]; out->any_nodes_traversed = t6[3]; out->any_intersections = t6[4]; out->any_rays_counted = t6[5]; }
       out->kernel_launches = launches; out->bvh_nodes = nNodes; out->bvh_leaf_items = nItems; lastMs = be.timerRead(lastMs); out->last_pass_ms = lastMs; out->bvh_max_stack = (uint64_t)hs.bvh.max_stack;
       return 0;
    }

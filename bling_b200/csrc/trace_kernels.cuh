@@ -14,12 +14,13 @@ namespace bl {
 
 struct TraceConfig {
    int sms = 148;
-   int variant = 1;
+   int variant = 3;                   // 0 reference point, 1 majority-vote stepping (round 1), 2 warp-level leaf queue, 3 = 2 with unsorted any-hit (the product)
    int blocksPerSm = 8;
    int maxStack = 64;                 // worst-case stack entries of the uploaded tree (Bvh::max_stack)
    uint32_t *workCounter = nullptr;   // device, one uint32 per launch slot
    bool countStats = false;           // option "traversal_stats": nearest-hit launches count node fetches / primitive tests
-   unsigned long long *travCounters = nullptr;   // device: nodes, prims, rays
+   unsigned long long *travCounters = nullptr;   // device: nodes, prims, rays of the nearest-hit launches, then the same three of the any-hit launches
+   Bvh bvh{};                         // host copy of the uploaded accelerator's (device) pointers: kernel parameter of variant 2 / 3
 };
 
 // ---------------------------------------------------------------------------------------------- variant 0
@@ -97,10 +98,6 @@ __global__ void __launch_bounds__(128) kTraceNearestCount(const uint32_t *__rest
 #define TR_LEAF_W 6       // vote weights (quarters): leaf step when TR_LEAF_W * #leaf lanes > 4 * #node lanes
 #endif
 
-__device__ __forceinline__ void ld8(const F4 *p, F4 &a, F4 &b) {   // one 32-byte load (LDG.E.256 on sm_100)
-   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
-}
 
 // ---- small PTX helpers: keep the hot loop free of compiler-made branches and generic->shared address conversions
 __device__ __forceinline__ void stsIf(uint32_t addr, int v, bool p) {   // predicated st.shared.b32
@@ -136,7 +133,7 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
    uint32_t slot = 0;
    Ray r; RayPre pre;
    bool exhausted = false;
-   r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.tmin = 0; r.tmax = 0; pre.idir = mk3(0, 0, 0); pre.ood = mk3(0, 0, 0);
+   r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.tmin = 0; r.tmax = 0; pre.idir = mk3(0, 0, 0);
 
    for (;;) {
       // ---- where does every lane stand?
@@ -248,11 +245,16 @@ static inline uint32_t traceGrid(const TraceConfig &cfg, uint32_t n, uint32_t ra
 }
 static inline void launchTraceNearest(TraceConfig &cfg, cudaStream_t st, const uint32_t *q, const uint32_t *cnt, uint32_t n, const DScene *sc,
                                       const F4 *O, const F4 *D, F4 *hit) {
-   if (cfg.countStats && cfg.travCounters) { kTraceNearestCount<<<traceGrid(cfg, n, 128), 128, 0, st>>>(q, cnt, n, sc, O, D, hit, cfg.travCounters); return; }
+   if (cfg.countStats && cfg.travCounters && cfg.variant < 2) { kTraceNearestCount<<<traceGrid(cfg, n, 128), 128, 0, st>>>(q, cnt, n, sc, O, D, hit, cfg.travCounters); return; }
    if (cfg.variant == 0) { kTraceNearestSimple<<<traceGrid(cfg, n, 128), 128, 0, st>>>(q, cnt, n, sc, O, D, hit); return; }
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
-   if (cfg.variant >= 2) { kTraceWarpQ<false, true><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter, nullptr, nullptr, 0u); return; }
+   if (cfg.variant >= 2) {
+      // option "traversal_stats": the SAME kernel with counters (node visits / primitive tests of the product's own schedule)
+      if (cfg.countStats && cfg.travCounters) kTraceWarpQ<false, true, true><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter, nullptr, nullptr, 0u, cfg.bvh, cfg.travCounters);
+      else kTraceWarpQ<false, true, false><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter, nullptr, nullptr, 0u, cfg.bvh, nullptr);
+      return;
+   }
    kTracePersistent<false><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter, nullptr, nullptr, 0u);
 
 }
@@ -262,8 +264,12 @@ static inline void launchTraceAny(TraceConfig &cfg, cudaStream_t st, const uint3
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
    TraceConfig c9 = cfg; c9.blocksPerSm = cfg.blocksPerSm + 1;
-   if (cfg.variant == 2) { kTraceWarpQ<true, true><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap); return; }
-   if (cfg.variant >= 3) { kTraceWarpQ<true, false><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap); return; }
+   if (cfg.variant == 2) { kTraceWarpQ<true, true, false><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap, cfg.bvh, nullptr); return; }
+   if (cfg.variant >= 3) {
+      if (cfg.countStats && cfg.travCounters) kTraceWarpQ<true, false, true><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap, cfg.bvh, cfg.travCounters + 3);
+      else kTraceWarpQ<true, false, false><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap, cfg.bvh, nullptr);
+      return;
+   }
    kTracePersistent<true><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap);
 
 }

@@ -22,27 +22,43 @@ namespace bl {
 #define TQ_FLUSH 32       // run a leaf pass once this many pairs are queued (<= 32)
 #endif
 #define TQ_WARPS (TR_THREADS / 32)
-#define TQ_HEAD_WORDS (TQ_WARPS * TQ_CAP + TR_THREADS + 4 * TR_THREADS)   // rings, per-lane key / flag, per-lane hit record
+#define TQ_WARP_BYTES (TQ_CAP * 4 + 32 * 4 + 32 * 16 + 32 * 32)   // per warp: ring, per-lane key / flag, per-lane hit record, per-lane ray (o, tmin)(d, tmax)
+#define TQ_HEAD_WORDS (TQ_WARPS * TQ_WARP_BYTES / 4)
 
 // order-preserving float <-> uint32 key (so that atomicMin on the key is a float min for any sign)
 __device__ __forceinline__ uint32_t fkey(float f) { const uint32_t b = __float_as_uint(f); return b ^ ((uint32_t)((int)b >> 31) | 0x80000000u); }
 __device__ __forceinline__ float fkeyInv(uint32_t k) { return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xffffffffu)); }
 
-template <bool ANY, bool SORTED>
+// shared memory through 32-bit shared-window addresses: generic pointers cost an address conversion (S2UR + ULEA + LEA) per access
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) { asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory"); }
+__device__ __forceinline__ F4 lds128(uint32_t a) { F4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ void sminU32(uint32_t a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+
+template <bool ANY, bool SORTED, bool STATS>
 __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLOCKS) kTraceWarpQ(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
                                                                  const DScene *__restrict__ sc, const F4 *__restrict__ O, const F4 *__restrict__ D,
-                                                                 F4 *__restrict__ hit, uint8_t *__restrict__ occl, uint32_t *__restrict__ work, F4 *__restrict__ fuseL, const F4 *__restrict__ fuseP, uint32_t fuseCap) {
+                                                                 F4 *__restrict__ hit, uint8_t *__restrict__ occl, uint32_t *__restrict__ work, F4 *__restrict__ fuseL, const F4 *__restrict__ fuseP, uint32_t fuseCap,
+                                                                 const Bvh bvh,     // the accelerator's pointers as a kernel PARAMETER: constant-bank operands instead of six registers
+                                                                 unsigned long long *__restrict__ totals) {   // STATS: node visits, primitive tests, rays of THIS kernel (TraversalStats, KdTree.hs:252-258)
    extern __shared__ int sstack[];
    const unsigned FULL = 0xffffffffu;
    const uint32_t total = cnt ? *cnt : n;
-   const Bvh bvh = sc->bvh;
-   const unsigned lane = threadIdx.x & 31u;
+   // lane id and the two shared-window addresses the hot loop uses come out of volatile asm so that they stay in registers: left
+   // to itself the compiler rematerialises them at every use (S2R SR_TID.X, S2UR SR_CgaCtaId, ULEA ...: the S2R latency
+   // sits on the critical path of every push, pop and queue append)
+   unsigned lane; asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
    const unsigned ltMask = (1u << lane) - 1u;
-   const unsigned wbase = threadIdx.x & ~31u;   // first thread of my warp
-   uint32_t *const sq = (uint32_t *)sstack + (threadIdx.x >> 5) * TQ_CAP;              // my warp's ring
-   uint32_t *const sown = (uint32_t *)sstack + TQ_WARPS * TQ_CAP;                      // [thread]: tmax key (nearest) / occluded flag (any)
-   F4 *const shit = (F4 *)((uint32_t *)sstack + TQ_WARPS * TQ_CAP + TR_THREADS);       // [thread]: best hit so far (nearest)
-   const uint32_t stackBase = (uint32_t)__cvta_generic_to_shared(sstack + TQ_HEAD_WORDS + threadIdx.x);
+   uint32_t sqA, stackBase;
+   {
+      const uint32_t sBase = (uint32_t)__cvta_generic_to_shared(sstack);
+      asm volatile("mov.u32 %0, %1;" : "=r"(sqA) : "r"(sBase + (threadIdx.x >> 5) * (uint32_t)TQ_WARP_BYTES));     // my warp's ring
+      asm volatile("mov.u32 %0, %1;" : "=r"(stackBase) : "r"(sBase + (TQ_HEAD_WORDS + threadIdx.x) * 4u));           // my stack column
+   }
+   const uint32_t sownW = sqA + TQ_CAP * 4u;        // [lane] of my warp: tmax key (nearest) / occluded flag (any)
+   const uint32_t shitW = sownW + 32u * 4u;         // [lane] of my warp: best hit so far (nearest)
+   const uint32_t srayW = shitW + 32u * 16u;        // [lane] of my warp: (o, tmin)(d, tmax) for the lanes that test my pairs
    const uint32_t LV = TR_THREADS * (uint32_t)sizeof(int);
    int tail_[BL_STACK - TR_SS];
    const int EMPTY = (int)0x80000000, WAITING = (int)0x80000001;   // leaf references are > WAITING (bvh.h: ~((first << 4) | count))
@@ -52,10 +68,10 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
    bool occ = false;
    Ray r; RayPre pre;
    bool exhausted = false;
-   r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.tmin = 0; r.tmax = 0; pre.idir = mk3(0, 0, 0); pre.ood = mk3(0, 0, 0);
+   r.o = mk3(0, 0, 0); r.d = mk3(0, 0, 1); r.tmin = 0; r.tmax = 0; pre.idir = mk3(0, 0, 0);
+   unsigned long long stN = 0, stP = 0, stR = 0;   // STATS only
 
    for (;;) {
-      bool atNode = cur >= 0;
       unsigned mBusy = __ballot_sync(FULL, cur != EMPTY);
       // ---- refill idle lanes (warp-uniform decision)
       if (!exhausted && __popc(mBusy) <= 32 - TR_REFILL) {
@@ -68,124 +84,128 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
             const uint32_t k = base + __popc(idle & ltMask);
             if (k < total) {
                slot = q ? q[k] : k;
+               if (STATS) stR++;
                r = loadRay(O, D, slot);
                pre = rayPre(r);
-               if (ANY) sown[threadIdx.x] = 0u;
-               else { sown[threadIdx.x] = fkey(r.tmax); F4 v_; v_.x = 0; v_.y = 0; v_.z = 0; v_.w = i2f(-1); shit[threadIdx.x] = v_; }
+               sts128(srayW + lane * 32u, r.o.x, r.o.y, r.o.z, r.tmin); sts128(srayW + lane * 32u + 16u, r.d.x, r.d.y, r.d.z, r.tmax);
+               if (ANY) sts32(sownW + lane * 4u, 0u);
+               else { sts32(sownW + lane * 4u, fkey(r.tmax)); sts128(shitW + lane * 16u, 0.0f, 0.0f, 0.0f, i2f(-1)); }
                sp = 0; li = 0; occ = false; lastSeq = qtail;
                cur = (bvh.root >= 0) ? bvh.root : WAITING;   // empty scene: nothing to wait for either
             }
          }
          if (base + (uint32_t)__popc(idle) >= total) exhausted = true;
-         atNode = cur >= 0;
          mBusy = __ballot_sync(FULL, cur != EMPTY);
       }
       if (mBusy == 0) { if (exhausted) break; continue; }
-      bool pop = false;
+      int pop = 0;
       // ---- node step for every lane that stands at an inner node
-      if (__any_sync(FULL, atNode)) {
-         if (atNode) {
-            const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
-            F4 n0, n1, n2, n3;
-            ld8(np, n0, n1); ld8(np + 2, n2, n3);
-            float tn[4];
-            node4Near(n0, n2, n3, r, pre, tn);
-            int c[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};
-            if (SORTED) {
-               sort4(tn, c);   // nearest first, misses (+inf) last
-               const bool h0 = tn[0] < BL_INF, h1 = tn[1] < BL_INF, h2 = tn[2] < BL_INF, h3 = tn[3] < BL_INF;
-               const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
-               const int r0 = c[0], r1 = c[1], r2 = c[2], r3 = c[3];
-               const int l1 = sp + nh - 2, l2 = l1 - 1, l3 = l1 - 2;
-               if (l1 < TR_SS) {
-                  const uint32_t top = stackBase + (uint32_t)l1 * LV;
-                  stsIf(top, r1, h1); stsIf(top - LV, r2, h2); stsIf(top - 2 * LV, r3, h3);
-               } else {
-                  if (h1) { if (l1 < TR_SS) stsIf(stackBase + (uint32_t)l1 * LV, r1, true); else tail_[l1 - TR_SS] = r1; }
-                  if (h2) { if (l2 < TR_SS) stsIf(stackBase + (uint32_t)l2 * LV, r2, true); else tail_[l2 - TR_SS] = r2; }
-                  if (h3) { if (l3 < TR_SS) stsIf(stackBase + (uint32_t)l3 * LV, r3, true); else tail_[l3 - TR_SS] = r3; }
-               }
-               sp += (nh > 0) ? nh - 1 : 0;
-               cur = r0; li = 0;
-               pop = !h0;
+      if (cur >= 0) {
+         if (STATS) stN++;
+         const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
+         F4 n0, n1, n2, n3;
+         ld8(np, n0, n1); ld8(np + 2, n2, n3);
+         float tn[4];
+         node4Near(n0, n2, n3, r, pre, tn);
+         int c[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};
+         if (SORTED) {
+            sort4(tn, c);   // nearest first, misses (+inf) last
+            const bool h0 = tn[0] < BL_INF, h1 = tn[1] < BL_INF, h2 = tn[2] < BL_INF, h3 = tn[3] < BL_INF;
+            const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
+            const int l1 = sp + nh - 2, l2 = l1 - 1, l3 = l1 - 2;
+            if (l1 < TR_SS) {
+               const uint32_t top = stackBase + (uint32_t)l1 * LV;
+               stsIf(top, c[1], h1); stsIf(top - LV, c[2], h2); stsIf(top - 2 * LV, c[3], h3);
             } else {
-               // any-hit, unsorted (variant 3): the answer does not depend on the order and the warp model shows the same
-               // number of node visits in slot order (tools/travsim.cpp), so the five compare-exchanges are dropped: enter
-               // the first child hit, push the others as they come
-               const bool h0 = tn[0] < BL_INF, h1 = tn[1] < BL_INF, h2 = tn[2] < BL_INF, h3 = tn[3] < BL_INF;
-               const bool p1 = h1 && h0, p2 = h2 && (h0 || h1), p3 = h3 && (h0 || h1 || h2);
-               const int l1 = sp, l2 = sp + (int)p1, l3 = l2 + (int)p2;
-               if (l3 < TR_SS) { stsIf(stackBase + (uint32_t)l1 * LV, c[1], p1); stsIf(stackBase + (uint32_t)l2 * LV, c[2], p2); stsIf(stackBase + (uint32_t)l3 * LV, c[3], p3); }
-               else {
-                  if (p1) { if (l1 < TR_SS) stsIf(stackBase + (uint32_t)l1 * LV, c[1], true); else tail_[l1 - TR_SS] = c[1]; }
-                  if (p2) { if (l2 < TR_SS) stsIf(stackBase + (uint32_t)l2 * LV, c[2], true); else tail_[l2 - TR_SS] = c[2]; }
-                  if (p3) { if (l3 < TR_SS) stsIf(stackBase + (uint32_t)l3 * LV, c[3], true); else tail_[l3 - TR_SS] = c[3]; }
-               }
-               sp = l3 + (int)p3;
-               cur = h0 ? c[0] : (h1 ? c[1] : (h2 ? c[2] : c[3])); li = 0;
-               pop = !(h0 || h1 || h2 || h3);
+               if (h1) { if (l1 < TR_SS) stsIf(stackBase + (uint32_t)l1 * LV, c[1], true); else tail_[l1 - TR_SS] = c[1]; }
+               if (h2) { if (l2 < TR_SS) stsIf(stackBase + (uint32_t)l2 * LV, c[2], true); else tail_[l2 - TR_SS] = c[2]; }
+               if (h3) { if (l3 < TR_SS) stsIf(stackBase + (uint32_t)l3 * LV, c[3], true); else tail_[l3 - TR_SS] = c[3]; }
             }
+            sp += (nh > 0) ? nh - 1 : 0;
+            cur = c[0];
+            pop = h0 ? 0 : 1;
+         } else {
+            // any-hit, unsorted (variant 3): the answer does not depend on the order and the warp model shows the same
+            // number of node visits in slot order (tools/travsim.cpp), so the five compare-exchanges are dropped: enter
+            // the first child hit, push the others as they come
+            const bool h0 = tn[0] < BL_INF, h1 = tn[1] < BL_INF, h2 = tn[2] < BL_INF, h3 = tn[3] < BL_INF;
+            const bool p1 = h1 && h0, p2 = h2 && (h0 || h1), p3 = h3 && (h0 || h1 || h2);
+            const int l1 = sp, l2 = sp + (int)p1, l3 = l2 + (int)p2;
+            if (l3 < TR_SS) { stsIf(stackBase + (uint32_t)l1 * LV, c[1], p1); stsIf(stackBase + (uint32_t)l2 * LV, c[2], p2); stsIf(stackBase + (uint32_t)l3 * LV, c[3], p3); }
+            else {
+               if (p1) { if (l1 < TR_SS) stsIf(stackBase + (uint32_t)l1 * LV, c[1], true); else tail_[l1 - TR_SS] = c[1]; }
+               if (p2) { if (l2 < TR_SS) stsIf(stackBase + (uint32_t)l2 * LV, c[2], true); else tail_[l2 - TR_SS] = c[2]; }
+               if (p3) { if (l3 < TR_SS) stsIf(stackBase + (uint32_t)l3 * LV, c[3], true); else tail_[l3 - TR_SS] = c[3]; }
+            }
+            sp = l3 + (int)p3;
+            cur = h0 ? c[0] : (h1 ? c[1] : (h2 ? c[2] : c[3]));
+            pop = (h0 || h1 || h2 || h3) ? 0 : 1;
          }
+         li = 0;
       }
       // ---- lanes that stand at a leaf (entered just now, or popped last trip) queue up to two of its items and move on
       {
-         const bool atLeaf = cur < 0 && cur > WAITING && !pop;
-         if (__any_sync(FULL, atLeaf)) {
-            const int enc = ~cur; const int first = enc >> 4, cntl = enc & 15;
-            const int rem = atLeaf ? cntl - li : 0;
-            const unsigned b1 = __ballot_sync(FULL, rem >= 1), b2 = __ballot_sync(FULL, rem >= 2);
+         const bool atLeaf = cur < 0 && cur > WAITING && pop == 0;
+         const int enc = ~cur;
+         const int rem = atLeaf ? (enc & 15) - li : 0;
+         const unsigned b1 = __ballot_sync(FULL, rem >= 1);
+         if (b1) {
+            const unsigned b2 = __ballot_sync(FULL, rem >= 2);
             const uint32_t at = qtail + (uint32_t)__popc(b1 & ltMask) + (uint32_t)__popc(b2 & ltMask);
-            if (rem >= 1) sq[at & (TQ_CAP - 1)] = (lane << 27) | (uint32_t)(first + li);
-            if (rem >= 2) sq[(at + 1) & (TQ_CAP - 1)] = (lane << 27) | (uint32_t)(first + li + 1);
+            const uint32_t ent = (lane << 27) | (uint32_t)((enc >> 4) + li);
+            if (rem >= 1) sts32(sqA + ((at & (TQ_CAP - 1)) << 2), ent);
+            if (rem >= 2) sts32(sqA + (((at + 1u) & (TQ_CAP - 1)) << 2), ent + 1u);
             qtail += (uint32_t)__popc(b1) + (uint32_t)__popc(b2);
-            if (atLeaf) { li += 2; lastSeq = qtail; pop = li >= cntl; }
+            if (rem >= 1) { li += 2; lastSeq = qtail; }
          }
+         if (atLeaf && rem <= 2) pop = 1;   // everything of this leaf is queued (or it is empty)
       }
       // ---- pop (predicated load); with an empty stack the ray waits for its queued pairs
       {
-         const bool more = sp != 0;
-         sp -= (pop && more) ? 1 : 0;
-         if (pop && more && sp >= TR_SS) cur = tail_[sp - TR_SS];
-         else cur = ldsIf(stackBase + (uint32_t)sp * LV, cur, pop && more);
-         li = pop ? 0 : li;
-         if (pop && !more) cur = WAITING;
+         const bool doPop = pop != 0 && sp != 0;
+         if (pop != 0) { li = 0; if (sp == 0) cur = WAITING; }
+         sp -= doPop ? 1 : 0;
+         if (doPop && sp >= TR_SS) cur = tail_[sp - TR_SS];
+         else cur = ldsIf(stackBase + (uint32_t)sp * LV, cur, doPop);
       }
       // ---- leaf passes: 32 pairs at a time; a partial batch only when nobody could do anything else
       {
          uint32_t qn = qtail - qhead;
-         const bool canWalk = __any_sync(FULL, cur > WAITING);   // some lane stands at a node or at a leaf
-         if (qn >= (uint32_t)TQ_FLUSH || (!canWalk && qn > 0u)) {
+         if (qn >= (uint32_t)TQ_FLUSH || (qn > 0u && !__any_sync(FULL, cur > WAITING))) {
             __syncwarp();   // ring writes of this trip
             do {
                const uint32_t nb = qn < 32u ? qn : 32u;
-               const uint32_t e = sq[(qhead + lane) & (TQ_CAP - 1)];
+               const uint32_t e = lds32(sqA + (((qhead + lane) & (TQ_CAP - 1)) << 2));
                const bool valid = lane < nb;
+               if (STATS && valid) stP++;
                const int owner = (int)(e >> 27); const int item = (int)(e & 0x07ffffffu);
+               // the owner's ray from its shared-memory copy: two LDS.128 (bank = owner lane: conflict-free, equal owners broadcast)
+               // instead of eight shuffles, and the direction does not have to live in the owner's registers at all
                Ray rr;
-               rr.o.x = __shfl_sync(FULL, r.o.x, owner); rr.o.y = __shfl_sync(FULL, r.o.y, owner); rr.o.z = __shfl_sync(FULL, r.o.z, owner);
-               rr.d.x = __shfl_sync(FULL, r.d.x, owner); rr.d.y = __shfl_sync(FULL, r.d.y, owner); rr.d.z = __shfl_sync(FULL, r.d.z, owner);
-               rr.tmin = __shfl_sync(FULL, r.tmin, owner);
-               if (ANY) rr.tmax = __shfl_sync(FULL, r.tmax, owner); else rr.tmax = fkeyInv(sown[wbase + owner]);
-               bool found = false;
+               { const F4 a = lds128(srayW + (uint32_t)owner * 32u), b = lds128(srayW + (uint32_t)owner * 32u + 16u);
+                 rr.o = mk3(a.x, a.y, a.z); rr.tmin = a.w; rr.d = mk3(b.x, b.y, b.z); rr.tmax = b.w; }
                if (ANY) {
+                  bool found = false;
                   if (valid) found = leafItemAny(bvh, item, rr);
-                  if (found) sown[wbase + owner] = 1u;
+                  if (found) sts32(sownW + (uint32_t)owner * 4u, 1u);
                   __syncwarp();
-                  if (sown[threadIdx.x] != 0u && cur != EMPTY && !occ) { occ = true; sp = 0; cur = WAITING; }   // my ray is occluded: drop the rest of its walk
+                  if (lds32(sownW + lane * 4u) != 0u && cur != EMPTY && !occ) { occ = true; sp = 0; cur = WAITING; }   // my ray is occluded: drop the rest of its walk
                } else {
+                  rr.tmax = fkeyInv(lds32(sownW + (uint32_t)owner * 4u));
                   HitRec hh; hh.t = 0; hh.prim = -1; hh.b1 = hh.b2 = 0;
+                  bool found = false;
                   if (valid) found = leafItemNearest(bvh, item, rr, hh);
                   const unsigned mh = __ballot_sync(FULL, found);
                   if (mh) {
                      const uint32_t key = fkey(hh.t);
-                     if (found) atomicMin(&sown[wbase + owner], key);
+                     if (found) sminU32(sownW + (uint32_t)owner * 4u, key);
                      __syncwarp();
-                     bool win = found && sown[wbase + owner] == key;
+                     bool win = found && lds32(sownW + (uint32_t)owner * 4u) == key;
                      const unsigned mw = __ballot_sync(FULL, win);
                      if (win) { const unsigned peers = __match_any_sync(mw, owner); win = (31 - __clz((int)peers)) == (int)lane; }   // equal t: the pair queued last
-                     if (win) { F4 v_; v_.x = hh.t; v_.y = hh.b1; v_.z = hh.b2; v_.w = i2f(hh.prim); shit[wbase + owner] = v_; }
+                     if (win) sts128(shitW + (uint32_t)owner * 16u, hh.t, hh.b1, hh.b2, i2f(hh.prim));
                      __syncwarp();
-                     r.tmax = fkeyInv(sown[threadIdx.x]);
+                     r.tmax = fkeyInv(lds32(sownW + lane * 4u));
                   }
                }
                qhead += nb; qn -= nb;
@@ -203,9 +223,13 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
                   fuseL[at] = l;
                }
             } else if (!fuseL) occl[slot] = occ ? 1 : 0;
-         } else hit[slot] = shit[threadIdx.x];
+         } else hit[slot] = lds128(shitW + lane * 16u);
          cur = EMPTY;
       }
+   }
+   if (STATS) {
+      for (int o = 16; o > 0; o >>= 1) { stN += __shfl_down_sync(FULL, stN, o); stP += __shfl_down_sync(FULL, stP, o); stR += __shfl_down_sync(FULL, stR, o); }
+      if (lane == 0 && stR) { atomicAdd(totals, stN); atomicAdd(totals + 1, stP); atomicAdd(totals + 2, stR); }
    }
 }
 

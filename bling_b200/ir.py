@@ -109,7 +109,8 @@ class Hit(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("samples", u64), ("rays_camera", u64), ("rays_extension", u64), ("rays_mis", u64),
                 ("rays_shadow", u64), ("dropped_samples", u64), ("nodes_traversed", u64), ("intersections", u64), ("rays_counted", u64),
-                ("kernel_launches", u64), ("bvh_nodes", u64), ("bvh_leaf_items", u64), ("last_pass_ms", C.c_double), ("bvh_max_stack", u64), ("rays_mis_culled", u64), ("rays_ext_culled", u64), ("rays_mis_any", u64)]
+                ("kernel_launches", u64), ("bvh_nodes", u64), ("bvh_leaf_items", u64), ("last_pass_ms", C.c_double), ("bvh_max_stack", u64), ("rays_mis_culled", u64), ("rays_ext_culled", u64), ("rays_mis_any", u64),
+                ("any_nodes_traversed", u64), ("any_intersections", u64), ("any_rays_counted", u64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -8,9 +8,15 @@ Reference interface (Graphics/Bling/Rendering.hs):
 
 `CudaRenderer.render(job, report)` is `prender` (:111-140) with the tile loop replaced by the CUDA core: upload
 the flat scene once, then per pass { render this rank's sample shard; sum films over ranks; report PassDone }.
-Multi-GPU = one process per GPU (torch.distributed, NCCL): every rank holds a full scene replica and renders the
-sample indices [rank*spp/world, (rank+1)*spp/world) of every pixel; the only exchange is one all-reduce(sum) of
-the [H][W][4] f32 film per report, the analogue of the reference's sequential addTile merge.
+Multi-GPU: every GPU holds a full scene replica and renders the sample indices [rank*spp/world, (rank+1)*spp/world) of
+every pixel; the only exchange is one sum of the [H][W][4] f32 films per report, the analogue of the
+reference's sequential addTile merge. The LIBRARY does it (blingcu_reduce_film: ncclAllReduce on its own stream,
+overlapping the next pass); the host only hands the communicator id around:
+  * `CudaRenderer`       one process per GPU (torchrun): torch.distributed is the launcher plumbing that carries the 128-byte
+                         id from rank 0 to the others (an MPI broadcast or a file would do the same);
+  * `MultiDeviceRenderer` one process driving n contexts (what a single Haskell process would do): blingcu_comm_init_all +
+                         blingcu_reduce_film_group.
+With a gloo process group (the CPU tests of the host logic, emulator contexts) the films are summed on the host instead.
 """
 from __future__ import annotations
 
@@ -53,13 +59,6 @@ def shard_range(spp: int, rank: int, world: int):
     return (spp * rank) // world, (spp * (rank + 1)) // world
 
 
-class _DevFilm:
-    """zero-copy view of the device film for torch (``__cuda_array_interface__``)."""
-
-    def __init__(self, ptr, n_floats):
-        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-
-
 class CudaRenderer:
     """The `Renderer` instance backed by libblingcu.so (keyword `renderer { cuda sampled {...} }` on the bling side)."""
 
@@ -84,10 +83,16 @@ class CudaRenderer:
     def pretty_print(self) -> str:
         return "cuda sampler renderer"
 
+    def _library_comm(self) -> bool:
+        """the library's own communicator sums the films (real GPUs); host-side sum otherwise (gloo CPU tests)."""
+        return self._dist is not None and self.world > 1 and self._dist.get_backend(self._pg) == "nccl"
+
     def upload(self, job: RenderJob):
-        if self._dist is not None and self.world > 1 and self._dist.get_backend(self._pg) == "nccl":
-            import torch
-            self.ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+        if self._library_comm() and not getattr(self, "_comm_ready", False):
+            box = [type(self.ctx).comm_unique_id() if self.rank == 0 else None]
+            self._dist.broadcast_object_list(box, src=0, group=self._pg)
+            self.ctx.comm_init(self.rank, self.world, box[0])
+            self._comm_ready = True
         self.ctx.upload_scene(job.scene)
         self._job = job
 
@@ -102,19 +107,12 @@ class CudaRenderer:
         sc = self._job.scene
         if self._dist is None or self.world == 1:
             return self.ctx.read_film()
+        if self._library_comm():
+            self.ctx.reduce_film()                 # asynchronous ncclAllReduce into film_sum on the library's stream
+            return self.ctx.read_film_sum()        # waits for it
         import torch
-        dist = self._dist
-        backend = dist.get_backend(self._pg)
-        if backend == "nccl":
-            # the pass was enqueued on torch's current stream (blingcu_set_stream in upload()), so the copy and
-            # the all-reduce order after it on the device; the only host sync is the final .cpu()
-            ptr, n = self.ctx.film_device()
-            local = torch.as_tensor(_DevFilm(ptr, n), device=torch.device("cuda", torch.cuda.current_device()))
-            total = local.clone()
-            dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self._pg)
-            return total.cpu().numpy().reshape(sc.height, sc.width, 4)
         total = torch.from_numpy(self.ctx.read_film())     # gloo (CPU tests of the host logic)
-        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=self._pg)
+        self._dist.all_reduce(total, op=self._dist.ReduceOp.SUM, group=self._pg)
         return total.numpy()
 
     def render(self, job: RenderJob, report: ProgressReporter, first_pass: int = 1):
@@ -139,3 +137,41 @@ class CudaRenderer:
 
     def close(self):
         self.ctx.close()
+
+
+class MultiDeviceRenderer:
+    """One process, one context per device (SURVEY.md §8b `blingcu_create(devices, ndev)` in spirit): what a single Haskell
+    process binding the C ABI does to use every GPU of the box. Render calls are asynchronous, so one host thread keeps all
+    devices busy; blingcu_reduce_film_group sums the films (ncclGroupStart/End around one all-reduce per context)."""
+
+    def __init__(self, devices, seed: int = 0x5EED, context_cls=api.Context):
+        self.seed = seed
+        self.ctxs = [context_cls(d) if context_cls is api.Context else context_cls() for d in devices]
+        self._cls = context_cls
+        self._cls.comm_init_all(self.ctxs)
+        self._job = None
+
+    def upload(self, job: RenderJob):
+        for c in self.ctxs:
+            c.upload_scene(job.scene)
+        self._job = job
+
+    def render_pass(self, pass_num: int) -> np.ndarray:
+        spp, n = self._job.scene.spp, len(self.ctxs)
+        for r, c in enumerate(self.ctxs):
+            s0, s1 = shard_range(spp, r, n)
+            if s1 > s0:
+                c.render_slice(pass_num, self.seed, s0, s1)
+        self._cls.reduce_film_group(self.ctxs, root=0)
+        return self.ctxs[0].read_film_sum()
+
+    def render(self, job: RenderJob, report: ProgressReporter, first_pass: int = 1):
+        self.upload(job)
+        report(Started())
+        p = first_pass
+        while report(PassDone(p, self.render_pass(p), 1.0)):
+            p += 1
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()

@@ -271,6 +271,7 @@ typedef struct blingcu_stats {
    uint64_t rays_ext_culled;   /* extension rays NOT traced: their vertex would have depth == maxDepth after a non-specular
                                   bounce, where neither a hit nor a miss contributes (Path.hs:43-51); rays_extension = traced */
    uint64_t rays_mis_any;      /* the part of rays_mis traced as any-hit queries (infinite lights: only hit/miss matters) */
+   uint64_t any_nodes_traversed, any_intersections, any_rays_counted; /* the traversal triple of the ANY-hit kernel while "traversal_stats" = 1 */
 } blingcu_stats;
 
 typedef struct blingcu_ctx blingcu_ctx;
@@ -287,6 +288,11 @@ int blingcu_upload_scene(blingcu_ctx *, const blingcu_scene *ir);
 /* replaces scIntersect / occluded (Scene.hs:45-51) on explicit ray batches -- parity check (a) */
 int blingcu_trace_nearest(blingcu_ctx *, const blingcu_ray *rays, size_t n, blingcu_hit *out);
 int blingcu_trace_occluded(blingcu_ctx *, const blingcu_ray *rays, size_t n, uint8_t *out);
+/* Host batches are pipelined in chunks (option "trace_chunk", default 2^20 rays): copy-in, traversal and copy-out of
+ * neighbouring chunks overlap. Page-locked buffers (blingcu_host_alloc, or memory the caller registered with CUDA) are
+ * transferred in place; pageable ones go through the context's pinned staging ring (option "copy_threads" helper threads). */
+int blingcu_host_alloc(blingcu_ctx *, size_t bytes, void **out);   /* page-locked host memory for ray / hit / film buffers */
+int blingcu_host_free(blingcu_ctx *, void *p);
 /* same as trace_nearest with per-ray node visits / primitive tests (dbgTraverse, KdTree.hs:260-281) */
 int blingcu_trace_stats(blingcu_ctx *, const blingcu_ray *rays, size_t n, blingcu_hit *out,
                         uint32_t *nodes, uint32_t *prims);

@@ -21,11 +21,15 @@ struct EmuBackend {
    void sync() {}
    void setStream(void *) {}
    void setMaxStack(int) {}
+   bool traceHostBatch(const blingcu_ray *, size_t, blingcu_hit *, uint8_t *, const bl::DScene *) { return false; }
+   void *hostAlloc(size_t n) { return std::malloc(n ? n : 1); }
+   void hostFree(void *p) { std::free(p); }
+   void setBvh(const bl::Bvh &) {}
    void setFilm(int, int, float, float) {}
    double timerRead(double last) { return last; }
    void tag(int) {}
    void kernelTimes(double *ms, uint64_t *l, int n) { for (int i = 0; i < n; ++i) { ms[i] = 0; l[i] = 0; } }
-   void traversalTotals(uint64_t &a, uint64_t &b, uint64_t &c) { a = b = c = 0; }
+   void traversalTotals(uint64_t *six) { for (int i = 0; i < 6; ++i) six[i] = 0; }
    void resetProfile() {}
    std::chrono::steady_clock::time_point timerStart() { return std::chrono::steady_clock::now(); }
    double timerStop(std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }

@@ -44,7 +44,7 @@ def test_nearest_and_any_hit_parity(ctx, name, variant):
     assert np.array_equal(got["b1"][same], ref["b1"][same])
     occ = ctx.trace_occluded(rays)
     assert (occ != o.trace_occluded(rays, mode)).mean() < 2e-3
-    ctx.set_option("trace_variant", 1)
+    ctx.set_option("trace_variant", 3)
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
@@ -63,7 +63,7 @@ def test_soup_traversal_parity(ctx, variant):
     assert len(ctx.trace_nearest(rays[:0])) == 0 and len(ctx.trace_occluded(rays[:1])) == 1
     h, nodes, prims = ctx.trace_stats(rays[:4096])
     assert np.array_equal(h["prim"], got["prim"][:4096]) and nodes.mean() > 5
-    ctx.set_option("trace_variant", 1)
+    ctx.set_option("trace_variant", 3)
 
 
 @pytest.mark.parametrize("name", ["cornell-box", "ducky", "zoo", "glass-torus"])
@@ -80,7 +80,7 @@ def test_traversal_variants_agree_bit_for_bit(ctx, name):
         film = ctx.read_film()
         ctx.upload_scene(sc)
         res[v] = (ctx.trace_nearest(rays), ctx.trace_occluded(rays), film)
-    ctx.set_option("trace_variant", 1)
+    ctx.set_option("trace_variant", 3)
     for v in (2, 3, 0):
         for f in ("t", "prim", "b1", "b2"):
             assert np.array_equal(res[v][0][f], res[1][0][f]), (name, v, f)
@@ -216,6 +216,90 @@ def test_slices_compose_and_sharding_full_size(ctx):
     assert np.isfinite(full).all() and (full[..., 0] > 0).all()
 
 
+def test_host_batches_are_pipelined_in_chunks(ctx):
+    """blingcu_trace_nearest / _occluded on HOST buffers: chunked, three chunks in flight (copy-in | traversal | copy-out). Same
+    answers whatever the chunk size, from pageable buffers (staged through the pinned ring by helper threads) and from
+    page-locked ones (blingcu_host_alloc: transferred in place); ragged last chunk; a batch smaller than one chunk."""
+    sc = load_scene("ducky")
+    ctx.upload_scene(sc)
+    rays = np.concatenate([random_rays(sc, 70_001, 41), camera_rays(None, sc, 50_000, 42)])
+    ctx.set_option("trace_chunk", 1 << 20)
+    want_h, want_o = ctx.trace_nearest(rays), ctx.trace_occluded(rays)           # one chunk
+    assert (want_h["prim"] >= 0).mean() > 0.05
+    for chunk, threads in ((1024, 1), (4096, 4), (50_000, 2)):
+        ctx.set_option("trace_chunk", chunk); ctx.set_option("copy_threads", threads)
+        got_h, got_o = ctx.trace_nearest(rays), ctx.trace_occluded(rays)
+        for f in ("t", "prim", "b1", "b2"):
+            assert np.array_equal(got_h[f], want_h[f]), (chunk, f)
+        assert np.array_equal(got_o, want_o), chunk
+    pin_r = ctx.host_array(len(rays), IR.RAY_DTYPE); pin_r[:] = rays
+    pin_h = ctx.host_array(len(rays), IR.HIT_DTYPE); pin_o = ctx.host_array(len(rays), np.uint8)
+    ctx.set_option("trace_chunk", 30_000)
+    ctx.trace_nearest(pin_r, out=pin_h); ctx.trace_occluded(pin_r, out=pin_o)
+    assert np.array_equal(pin_h, want_h) and np.array_equal(pin_o, want_o)
+    ctx.trace_nearest(rays[:7], out=pin_h[:7])                                    # pageable in, pinned out, less than a chunk
+    assert np.array_equal(pin_h[:7], want_h[:7])
+    ctx.set_option("trace_chunk", 1 << 20); ctx.set_option("copy_threads", 4)
+    with pytest.raises(api.BlingCuError):
+        ctx.set_option("trace_chunk", 5)
+
+
+def test_traversal_counters_of_the_product_kernels(ctx):
+    """option traversal_stats: the SAME warp-queue kernels with counters (nearest-hit and any-hit separately); results unchanged."""
+    sc = make_soup(200_000, 64, 36, 2, 2)
+    ctx.upload_scene(sc)
+    rays = random_rays(sc, 100_000, 5)
+    want_h, want_o = ctx.trace_nearest(rays), ctx.trace_occluded(rays)
+    ctx.set_option("traversal_stats", 1); ctx.reset_stats()
+    got_h, got_o = ctx.trace_nearest(rays), ctx.trace_occluded(rays)
+    st = ctx.stats()
+    ctx.set_option("traversal_stats", 0)
+    assert np.array_equal(got_h, want_h) and np.array_equal(got_o, want_o)
+    assert st["rays_counted"] == st["any_rays_counted"] == len(rays)
+    assert 5 < st["nodes_traversed"] / len(rays) < 200 and 0.5 < st["intersections"] / len(rays) < 100
+    assert 0 < st["any_nodes_traversed"] <= st["nodes_traversed"] * 1.5 and st["any_intersections"] > 0
+    _, nodes, prims = ctx.trace_stats(rays[:20_000])                             # per-ray counts of the sequential walk (dbgTraverse)
+    assert abs(nodes.mean() / (st["nodes_traversed"] / len(rays)) - 1) < 0.25    # the leaf queue tests against a slightly stale tmax
+
+
+def test_film_reduction_is_a_consistent_snapshot(ctx):
+    """blingcu_reduce_film on a one-rank communicator: film_sum is the film as of the reduce call even though the next slice is
+    enqueued right behind it (the reduction runs on its own stream and the next slice's film kernels wait for it)."""
+    sc = small(load_scene("cornell-box"), 256, 192, 4, 4)
+    ctx.upload_scene(sc); ctx.comm_init(0, 1)
+    ctx.render_slice(1, 5, 0, 8); want = ctx.read_film()
+    ctx.clear_film()
+    ctx.render_slice(1, 5, 0, 8); ctx.reduce_film(); ctx.render_slice(1, 5, 8, 16)
+    got = ctx.read_film_sum()
+    assert np.array_equal(got, want)
+    assert ctx.read_film()[..., 0].sum() > 1.5 * want[..., 0].sum()        # the private film went on accumulating
+    ctx.comm_destroy()
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs (gpurun --gpus 2)")
+def test_two_devices_in_one_process_sum_their_films():
+    """one process, two contexts (the Haskell host's mode): blingcu_comm_init_all + blingcu_reduce_film_group over NCCL"""
+    from bling_b200.renderer import MultiDeviceRenderer
+    sc = small(load_scene("cornell-box"), 200, 150, 4, 4)
+    one = api.Context(0); one.upload_scene(sc); one.render_pass(1, 0x5EED); full = one.read_film(); one.close()
+    r = MultiDeviceRenderer([0, 1], seed=0x5EED)
+    imgs = []
+    r.render(RenderJob(sc), lambda p: (imgs.append(p.final_img.copy()) or len(imgs) < 2) if isinstance(p, PassDone) else True)
+    assert np.abs(imgs[0] - full).max() <= 1e-5 * np.abs(full).max()
+    api.Context.reduce_film_group(r.ctxs, root=-1)
+    a, b = r.ctxs[0].read_film_sum(), r.ctxs[1].read_film_sum()
+    assert np.array_equal(a, b) and np.abs(a - imgs[1]).max() <= 1e-6 * np.abs(a).max()
+    r.close()
+
+
 def test_renderer_host_api(ctx):
     sc = small(load_scene("specular"), 64, 64, 2, 2)
     r = CudaRenderer(device=0, seed=9)
@@ -251,7 +335,7 @@ def test_cfg5_full_size_properties(ctx):
         ref = ctx.trace_nearest(rays[:200_000])
         assert np.array_equal(ref["prim"], hit["prim"][:200_000]) and np.array_equal(ref["t"], hit["t"][:200_000])
         if v == 2: assert np.array_equal(ctx.trace_occluded(rays), occ)
-    ctx.set_option("trace_variant", 1)
+    ctx.set_option("trace_variant", 3)
     # the oracle's SAH kd-tree (KdTree.hs restated) over the same 10 M triangles: prim id exact, t / b1 / b2 bit-exact
     o = Oracle(sc, kdtree=True)
     sub = np.concatenate([rays[:125_000], rays[500_000:625_000]])

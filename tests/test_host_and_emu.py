@@ -23,7 +23,7 @@ def test_abi_exports_every_declared_symbol():
     so = g.build_cuda()
     hdr = (ROOT / "include" / "blingcu.h").read_text()
     declared = sorted(set(re.findall(r"\b(blingcu_[a-z_]+)\s*\(", hdr)))
-    assert len(declared) == len(api.SYMBOLS) == 22
+    assert len(declared) == len(api.SYMBOLS) == 33
     L = ctypes.CDLL(str(so))
     for name in declared:
         assert hasattr(L, name), name
@@ -222,6 +222,18 @@ def test_null_uvs_default_and_null_tables_are_rejected():
     e.close()
 
 
+def test_host_array_and_out_buffers():
+    """blingcu_host_alloc / host_free and caller-provided output buffers through the binding (emulator: plain malloc)"""
+    sc = small(load_scene("cornell-box"), 16, 16, 1, 1)
+    e = EmuContext(); e.upload_scene(sc)
+    rays = random_rays(sc, 257, 3)
+    pr = e.host_array(len(rays), IR.RAY_DTYPE); pr[:] = rays
+    ph = e.host_array(len(rays), IR.HIT_DTYPE)
+    assert e.trace_nearest(pr, out=ph) is ph and np.array_equal(ph, e.trace_nearest(rays))
+    assert len(e.host_array(0, np.uint8)) == 0
+    e.close()
+
+
 def test_api_error_paths():
     e = EmuContext()
     with pytest.raises(api.BlingCuError) as ex:
@@ -254,6 +266,38 @@ def test_renderer_progressive_loop():
     assert [p for p, _ in seen] == [1, 2, 3]
     assert seen[0][1] < seen[1][1] < seen[2][1]            # filter weights accumulate over passes
     assert abs(seen[2][1] / seen[0][1] - 3.0) < 2e-2
+
+
+def test_in_process_group_reduce_sums_the_films():
+    """blingcu_comm_init_all + blingcu_reduce_film_group (one process driving several contexts, the Haskell host's mode): film_sum
+    is the sum of the private films on every rank (root < 0) or on the root only, the private films stay untouched, and the
+    sample shards of the contexts compose to the single-context pass. Emulator leg: the host logic of include/blingcu.h."""
+    from bling_b200.renderer import MultiDeviceRenderer
+    sc = small(load_scene("cornell-box"), 40, 30, 4, 4)
+    one = EmuContext(); one.upload_scene(sc); one.render_pass(1, 0x5EED); full = one.read_film(); one.close()
+    r = MultiDeviceRenderer([0, 1, 2], seed=0x5EED, context_cls=EmuContext)
+    imgs = []
+    r.render(RenderJob(sc), lambda p: (imgs.append(p.final_img.copy()) or len(imgs) < 2) if isinstance(p, PassDone) else True)
+    assert np.abs(imgs[0] - full).max() <= 1e-5 * np.abs(full).max()                 # shards 0-5, 5-10, 10-16 compose
+    privates = [c.read_film() for c in r.ctxs]
+    assert np.abs(sum(privates) - imgs[1]).max() <= 1e-5 * np.abs(imgs[1]).max()     # film_sum == sum of the private films
+    assert all(p[..., 0].sum() < imgs[1][..., 0].sum() for p in privates)
+    EmuContext.reduce_film_group(r.ctxs, root=-1)                                     # all-reduce: every rank gets the sum
+    sums = [c.read_film_sum() for c in r.ctxs]
+    assert all(np.array_equal(s_, sums[0]) for s_ in sums[1:])
+    with pytest.raises(api.BlingCuError) as ex:                                       # a lone reduce on a 3-rank communicator
+        r.ctxs[0].reduce_film()
+    assert ex.value.code == 5
+    with pytest.raises(api.BlingCuError):
+        EmuContext.reduce_film_group(r.ctxs, root=7)
+    r.close()
+    solo = EmuContext(); solo.upload_scene(sc); solo.render_pass(1, 3)
+    with pytest.raises(api.BlingCuError):
+        solo.read_film_sum()                                                          # nothing reduced yet
+    solo.comm_init(0, 1); solo.reduce_film()
+    assert np.array_equal(solo.read_film_sum(), solo.read_film())                     # one rank: film_sum is a copy
+    assert len(EmuContext.comm_unique_id()) == api.COMM_ID_BYTES
+    solo.close()
 
 
 def test_shard_range_partitions():

@@ -5,6 +5,8 @@ NOTE: these are outputs of the CPU restatement, not of GHC-built bling (absent: 
 The rel-MSE bound is 3x the rel-MSE between two independent 2048-spp halves of the oracle render (the noise floor).
 
     python tools/make_golden_renders.py [scene ...]
+    python tools/make_golden_renders.py --quarter [scene ...]     # SURVEY §8(d) "converged parity": 1/4 linear CONFIG size, 4096 spp
+                                                                  # -> tests/golden/renders_quarter/ (hours of CPU: run it niced)
 """
 import os
 import sys
@@ -28,9 +30,17 @@ def rel_mse(a, b):
     return float(np.mean((a - b) ** 2 / (b ** 2 + 1e-3)))
 
 
-def main(names):
+QUARTER = {"cornell-box": (128, 128), "glass-torus": (256, 256), "specular": (256, 256), "ducky": (480, 270), "sun-sky": (480, 270),
+           "environment": (480, 270)}   # BASELINE.json configs[0..3] at 1/4 linear size
+
+
+def main(names, quarter=False):
+    global W, H, NU, NV, PASSES, OUT
+    if quarter:
+        OUT = ROOT / "tests" / "golden" / "renders_quarter"; NU, NV, PASSES = 8, 8, 64
     OUT.mkdir(parents=True, exist_ok=True)
     for name in names:
+        if quarter: W, H = QUARTER[name]
         sc = resized(IR.SceneIR.load(ROOT / "tests" / "golden" / "scenes" / f"{name}.npz"), W, H, NU, NV)
         t = time.time()
         halves = []
@@ -54,10 +64,11 @@ def main(names):
                 ms.append(image.film_xyz(o.read_film()).mean((0, 1)))
             ms = np.array(ms); sigma_full = (ms.std(0, ddof=1) / ms.mean(0)).max() / np.sqrt(8.0)
             extra["mean_tol"] = max(5e-3, 4 * np.sqrt(2.0) * float(sigma_full))
-        np.savez_compressed(OUT / f"{name}.npz", xyz=xf, cfg=np.array([W, H, NU, NV, PASSES]), relmse_halves=floor,
+        np.savez_compressed(OUT / f"{name}.npz", xyz=xf.astype(np.float32), cfg=np.array([W, H, NU, NV, PASSES]), relmse_halves=floor,
                             relmse_bound=3 * floor, seed=SEED, **extra)
         print(f"{name}: {time.time() - t:.0f}s, rel-MSE between 2048-spp halves {floor:.3e}, mean XYZ {xf.mean((0, 1))} {extra}", flush=True)
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:] or ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"])
+    args = [x for x in sys.argv[1:] if x != "--quarter"]
+    main(args or ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"], quarter="--quarter" in sys.argv)

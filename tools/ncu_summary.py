@@ -33,7 +33,7 @@ METRICS = [
 
 def main():
     rep = sys.argv[1]
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}

@@ -125,7 +125,7 @@ struct Lane {
 };
 
 struct Stats {
-   double nsIdle = 0, nsWait = 0, nsLeaf = 0; double rays = 0, nodes = 0, prims = 0, trips = 0, nodeSteps = 0, leafSteps = 0, nodeLanes = 0, leafLanes = 0, cost = 0, popCulls = 0, lines = 0;
+   double nsIdle = 0, nsWait = 0, nsLeaf = 0, distinctLines = 0; double rays = 0, nodes = 0, prims = 0, trips = 0, nodeSteps = 0, leafSteps = 0, nodeLanes = 0, leafLanes = 0, cost = 0, popCulls = 0, lines = 0;
    void add(const Stats &o) { rays += o.rays; nodes += o.nodes; prims += o.prims; trips += o.trips; nodeSteps += o.nodeSteps; leafSteps += o.leafSteps; nodeLanes += o.nodeLanes; leafLanes += o.leafLanes; cost += o.cost; popCulls += o.popCulls; lines += o.lines; }
 };
 
@@ -190,7 +190,7 @@ static Stats simulate(const WTree &T, const Policy &P, const std::vector<Ray> &r
             for (auto &L : lanes) if (!L.active) {
                if (head < n) {
                   L.active = true; L.slot = (uint32_t)head; L.r = rays[head]; head++;
-                  RayPre p = rayPre(L.r); L.idir = p.idir; L.ood = p.ood;
+                  RayPre p = rayPre(L.r); L.idir = p.idir;
                   L.sp = 0; L.cur = T.root; L.li = 0; L.h = HitRec{0, -1, 0, 0}; L.occluded = false;
                }
             }
@@ -262,7 +262,7 @@ static Stats simulateDeferred(const WTree &T, const Policy &P, const std::vector
             for (auto &L : lanes) if (!L.active) {
                if (head < n) {
                   L.active = true; L.slot = (uint32_t)head; L.r = rays[head]; head++;
-                  RayPre p = rayPre(L.r); L.idir = p.idir; L.ood = p.ood;
+                  RayPre p = rayPre(L.r); L.idir = p.idir;
                   L.sp = 0; L.cur = T.root; L.li = 0; L.h = HitRec{0, -1, 0, 0}; L.occluded = false;
                }
             }
@@ -312,6 +312,7 @@ static Stats simulateDeferred(const WTree &T, const Policy &P, const std::vector
          // node step
          if (nNode > 0) {
             S.nodeSteps++; S.nodeLanes += nNode; S.cost += P.cNode;
+            { int ids[32], m = 0; for (auto &L : lanes) if (L.active && L.cur >= 0 && L.cur < WAIT) ids[m++] = L.cur; std::sort(ids, ids + m); int dn = 0, dl = 0; for (int i = 0; i < m; ++i) { if (i == 0 || ids[i] != ids[i - 1]) dn++; if (i == 0 || (ids[i] >> 1) != (ids[i - 1] >> 1)) dl++; } S.lines += dn; S.popCulls += 0; S.distinctLines += dl; }
             for (auto &L : lanes) { if (!L.active) S.nsIdle++; else if (L.cur == WAIT) S.nsWait++; else if (L.cur < 0) S.nsLeaf++; }
             for (auto &L : lanes) if (L.active && L.cur >= 0 && L.cur < WAIT) { nodeStep(T, P, L, ANY, S); if (L.cur == POPPED) popNext(L); }
          }
@@ -353,7 +354,7 @@ static std::vector<Ray> sortRays(const std::vector<Ray> &rays, float ext, int ce
 static void report(const char *pop, const Policy &P, const Stats &S) {
    printf("%-10s %-26s rays %8.0f | nodes/ray %6.2f prims/ray %6.2f | trips/ray %6.3f | lanes node %5.2f leaf %5.2f | popculls/ray %5.2f | winst/ray %7.1f\n", pop, P.name, S.rays, S.nodes / S.rays,
           S.prims / S.rays, S.trips / S.rays, S.nodeLanes / std::max(1.0, S.nodeSteps), S.leafLanes / std::max(1.0, S.leafSteps), S.popCulls / S.rays, S.cost / S.rays);
-   if (S.nsIdle + S.nsWait + S.nsLeaf > 0) printf("      during node steps: idle %.2f wait %.2f at-leaf %.2f lanes\n", S.nsIdle / S.nodeSteps, S.nsWait / S.nodeSteps, S.nsLeaf / S.nodeSteps);
+   if (S.nsIdle + S.nsWait + S.nsLeaf > 0) printf("      during node steps: idle %.2f wait %.2f at-leaf %.2f lanes; distinct nodes per step %.2f, distinct 128-byte lines %.2f (of %.2f lanes)\n", S.nsIdle / S.nodeSteps, S.nsWait / S.nodeSteps, S.nsLeaf / S.nodeSteps, S.lines / S.nodeSteps, S.distinctLines / S.nodeSteps, S.nodeLanes / S.nodeSteps);
    fflush(stdout);
 }
 
@@ -428,6 +429,7 @@ int main(int argc, char **argv) {
 
    if (const char *f = getenv("POLS")) { std::vector<Policy> keep; keep.push_back(pols[0]); std::string fs(f); for (size_t i = 1; i < pols.size(); ++i) if (fs.find(std::string("|") + pols[i].name + "|") != std::string::npos) keep.push_back(pols[i]); pols = keep; }
    std::vector<Ray> ext_ = cam;
+   if (getenv("RANDOM_RAYS")) { ext_.clear(); for (int i = 0; i < 60000; ++i) { Ray r; r.o = mk3((u01r(rk) * 2 - 1) * ext, (u01r(rk) * 2 - 1) * ext, (u01r(rk) * 2 - 1) * ext); r.d = uniformSphere(rk); r.tmin = 1e-3f; r.tmax = BL_INF; ext_.push_back(r); } }
    for (int depth = 0; depth <= 2; ++depth) {
       // nearest-hit population `ext_` at this depth
       std::vector<HitRec> hits;
