@@ -364,16 +364,23 @@ def run_b200(a):
             if rank == 0:
                 # explicit ray batches through the C ABI on HOST buffers (parity API)
                 from tests.conftest import camera_rays
-                nr = 4_000_000
+                from bling_b200 import ir as IR_
+                nr = 8_000_000
                 rays = camera_rays(None, scene, nr, 11)
-                ctx.trace_nearest(rays)                      # warm-up at full size (grow-only device scratch)
-                t0 = time.perf_counter()
-                reps = 3
-                for _ in range(reps):
-                    ctx.trace_nearest(rays)
-                dt2 = (time.perf_counter() - t0) / reps
-                e2e_trace = {"value": nr / dt2 / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": nr * 32, "d2h_bytes_per_step": nr * 16,
-                             "what": "blingcu_trace_nearest, 4M primary-like rays, host ray buffer in / host hit buffer out"}
+                e2e_trace = {"unit": "Mrays/s", "h2d_bytes_per_step": nr * 32, "d2h_bytes_per_step": nr * 16,
+                             "what": "blingcu_trace_nearest, 8M primary-like rays, HOST ray buffer in / HOST hit buffer out, pipelined in 1M-ray "
+                                     "chunks (copy-in | traversal | copy-out overlap): `value` from page-locked buffers (blingcu_host_alloc), "
+                                     "`pageable` from ordinary numpy arrays staged through the library's pinned ring"}
+                pin_r = ctx.host_array(nr, IR_.RAY_DTYPE); pin_r[:] = rays
+                pin_h = ctx.host_array(nr, IR_.HIT_DTYPE)
+                out_p = np.zeros(nr, IR_.HIT_DTYPE)
+                for key, (src, dst) in (("value", (pin_r, pin_h)), ("pageable", (rays, out_p))):
+                    ctx.trace_nearest(src, out=dst)              # warm-up at full size (staging ring, device scratch)
+                    t0 = time.perf_counter()
+                    reps = 3
+                    for _ in range(reps):
+                        ctx.trace_nearest(src, out=dst)
+                    e2e_trace[key] = nr / ((time.perf_counter() - t0) / reps) / 1e6
 
     # ---- the named scenes of BASELINE.json configs[0..3] at their config sizes, on all N GPUs: every rank renders k
     # sample indices of its own pass (pass 1 + rank: independent sample sets, the same weak scaling as the headline),
@@ -381,6 +388,7 @@ def run_b200(a):
     scenes = None
     if not a.no_scenes:
         scenes = {}
+        scene_ncu = committed_json("r02_named_scenes.json") or {}
         from bling_b200 import ir as IR
         for name in ("cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"):
             f = ROOT / "tests" / "golden" / "scenes" / f"{name}.npz"
@@ -416,8 +424,22 @@ def run_b200(a):
             scenes[name] = {"size": [sc.width, sc.height], "prims": sc.n_prims, "samples": ns,
                             "msamples_per_s": ns / (ms2 * 1e-3) / 1e6, "mrays_per_s": nr / (ms2 * 1e-3) / 1e6,
                             "rays_per_sample": nr / max(1.0, ns), "launches_per_gpu": s3["kernel_launches"],
-                            "hbm_roofline": "n/a (scene lives in L1/L2)" if sc.n_prims < 1000 else "see roofline of cfg 5"}
+                            "hbm_roofline": "n/a (scene lives in L1/L2)" if sc.n_prims < 1000 else "see roofline of cfg 5",
+                            # SURVEY 8(d), cache-resident configs: issue-slot utilisation, L2 hit rate, warp execution efficiency
+                            # (one ncu --metrics pass of tools/scene_breakdown.py per scene, committed: tools/ncu_scene_table.py)
+                            "ncu": scene_ncu.get(name)}
             c2.close()
+            if rank == 0 and world == 1 and not a.no_cpu_baseline:
+                # the reference's CPU algorithm (oracle/, all host cores) on ONE sample index of the same scene at the same size
+                from oracle.oracle_py import Oracle
+                cores = os.cpu_count() or 1
+                orc = Oracle(sc, kdtree=sc.n_prims > 64)
+                t0 = time.perf_counter(); orc.render_slice(1, SEED, 0, 1, threads=cores); dt_o = time.perf_counter() - t0
+                so = orc.stats(); orc.close()
+                ro = so["rays_camera"] + so["rays_extension"] + so["rays_mis"] + so["rays_shadow"]
+                scenes[name]["cpu_baseline"] = {"value": so["samples"] / dt_o / 1e6, "unit": UNIT, "mrays_per_s": ro / dt_o / 1e6, "cores": cores,
+                                                "kind": "port", "sample": f"1 of {sc.spp} sample indices per pixel at {sc.width}x{sc.height}: "
+                                                                          f"{so['samples']} samples in {dt_o:.2f} s"}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

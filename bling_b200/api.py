@@ -20,7 +20,7 @@ SYMBOLS = ["create", "destroy", "last_error", "upload_scene", "trace_nearest", "
            "render_pass", "render_slice", "render_samples", "eval_texture", "read_film", "clear_film", "film_add_host", "film_device",
            "synchronize", "set_stream", "get_stats", "reset_stats", "set_option", "sample_extent", "kernel_times",
            "comm_unique_id", "comm_init", "comm_init_all", "comm_destroy", "reduce_film", "reduce_film_group", "comm_wait",
-           "read_film_sum", "film_sum_device", "host_alloc", "host_free"]
+           "read_film_sum", "film_sum_device", "host_alloc", "host_free", "upload_kdtree", "trace_kdtree"]
 COMM_ID_BYTES = 128
 
 
@@ -71,6 +71,8 @@ def load_library(path=LIB_PATH, prefix="blingcu"):
     f("film_sum_device").argtypes = [P, C.POINTER(P), C.POINTER(C.c_size_t)]
     f("host_alloc").argtypes = [P, C.c_size_t, C.POINTER(P)]
     f("host_free").argtypes = [P, P]
+    f("upload_kdtree").argtypes = [P, P, C.c_uint32, C.c_int32, P, C.c_size_t, P]
+    f("trace_kdtree").argtypes = [P, P, C.c_size_t, P, P, P]
     return L
 
 
@@ -146,6 +148,19 @@ class Context:
         if out is None: out = np.zeros(len(rays), np.uint8)
         self._chk(self._f("trace_occluded")(self._h, rays.ctypes.data, len(rays), out.ctypes.data))
         return out
+
+    def upload_kdtree(self, nodes: np.ndarray, leaf_prims: np.ndarray, root: int, bounds):
+        """the HOST's own kd-tree (KdTree.hs:29-33, flattened; IR.KDNODE_DTYPE) as an alternative accelerator input"""
+        nodes = np.ascontiguousarray(nodes, IR.KDNODE_DTYPE); leaf = np.ascontiguousarray(leaf_prims, np.uint32)
+        b = np.ascontiguousarray(bounds, np.float32)
+        self._chk(self._f("upload_kdtree")(self._h, nodes.ctypes.data, len(nodes), int(root), leaf.ctypes.data if len(leaf) else None, len(leaf), b.ctypes.data))
+
+    def trace_kdtree(self, rays: np.ndarray):
+        """`traverse` of KdTree.hs:223-242 over the uploaded kd-tree: hits + per-ray (nodesTraversed, intersections) of dbgTraverse"""
+        rays = np.ascontiguousarray(rays, IR.RAY_DTYPE); out = np.zeros(len(rays), IR.HIT_DTYPE)
+        nodes = np.zeros(len(rays), np.uint32); prims = np.zeros(len(rays), np.uint32)
+        self._chk(self._f("trace_kdtree")(self._h, rays.ctypes.data, len(rays), out.ctypes.data, nodes.ctypes.data, prims.ctypes.data))
+        return out, nodes, prims
 
     def trace_stats(self, rays: np.ndarray):
         rays = np.ascontiguousarray(rays, IR.RAY_DTYPE); out = np.zeros(len(rays), IR.HIT_DTYPE)

@@ -84,6 +84,13 @@ static thread_local std::string g_createError;
       *dptr = c->p.film; *nf = (size_t)c->p.hs.W * c->p.hs.H * 4;                                                                \
       return 0;                                                                                                                  \
    }                                                                                                                             \
+   int PFX##_upload_kdtree(PFX##_ctx_t *c, const blingcu_kdnode *nodes, uint32_t nn, int32_t root, const uint32_t *leaf, size_t nl, const float *bounds) { \
+      return c ? c->p.be.guard(c->p.err, [&]() { return c->p.uploadKd(nodes, nn, root, leaf, nl, bounds); }) : BLINGCU_EINVAL;       \
+   }                                                                                                                             \
+   int PFX##_trace_kdtree(PFX##_ctx_t *c, const blingcu_ray *r, size_t n, blingcu_hit *o, uint32_t *nodes, uint32_t *prims) {    \
+      if (!c || (n && (!r || !o || !nodes || !prims))) return BLINGCU_EINVAL;                                                    \
+      return c->p.be.guard(c->p.err, [&]() { return c->p.traceKd(r, n, o, nodes, prims); });                                      \
+   }                                                                                                                             \
    int PFX##_host_alloc(PFX##_ctx_t *c, size_t bytes, void **out) {                                                              \
       if (!c || !out) return BLINGCU_EINVAL;                                                                                     \
       *out = nullptr;                                                                                                            \

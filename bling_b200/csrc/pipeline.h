@@ -14,6 +14,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 namespace bl {
@@ -40,6 +41,8 @@ struct Pipeline {
    std::vector<void *> sceneAllocs;
    PathState ps{}; std::vector<void *> stateAllocs;
    F4 *film = nullptr;
+   KdTreeDev kd{}; std::vector<void *> kdAllocs; size_t nPrims = 0; bool kdUploaded = false;   // the host's kd-tree (kdtree.h)
+   const int32_t *primRefDev = nullptr;
    F4 *filmSum = nullptr;     // sum of the films of all ranks (comm.h), valid after reduce_film
    uint32_t npix = 0, nTextures = 0;
    uint32_t batchTarget = 1u << 26;   // paths per wavefront (~490 B of state each: 33 GB at the cap, sized for 180 GB HBM)
@@ -57,7 +60,8 @@ struct Pipeline {
       sceneAllocs.push_back(d);
       return d;
    }
-   void freeScene() { be.syncComm(); freeTraceScratch(); for (void *p : sceneAllocs) be.free(p); sceneAllocs.clear(); dscene = nullptr; if (film) { be.free(film); film = nullptr; } if (filmSum) { be.free(filmSum); filmSum = nullptr; } uploaded = false; }
+   void freeKd() { for (void *p : kdAllocs) be.free(p); kdAllocs.clear(); kdUploaded = false; }
+   void freeScene() { be.syncComm(); freeKd(); freeTraceScratch(); for (void *p : sceneAllocs) be.free(p); sceneAllocs.clear(); dscene = nullptr; if (film) { be.free(film); film = nullptr; } if (filmSum) { be.free(filmSum); filmSum = nullptr; } uploaded = false; }
    void freeState() { for (void *p : stateAllocs) be.free(p); stateAllocs.clear(); ps = PathState{}; qSlotsAlloc = 0; rootAlloc = 0; }
 
    int upload(const blingcu_scene *ir) {
@@ -157,7 +161,11 @@ struct Pipeline {
             q[2] = F4{0, 0, 0, 0};
          }
       }
+      std::vector<int32_t> primHitRef(nprim ? nprim : 1, BL_REF_MISS);
+      for (size_t i = 0; i < nt; ++i) primHitRef[itemPrim[i]] = mkRef(false, shadeKind[ir->tri_material[i]], (uint32_t)i);
+      for (size_t j = 0; j < ns; ++j) primHitRef[itemPrim[nt + j]] = mkRef(true, shadeKind[ir->shapes[j].material], (uint32_t)j);
       std::memset(&hs, 0, sizeof(hs));
+      primRefDev = up<int32_t>(primHitRef.data(), primHitRef.size()); nPrims = nprim;
       hs.bvh.nodes = up<F4>(bo.nodes, BL_NODE_F4 * (size_t)bo.n_nodes);
       hs.bvh.items = up<F4>(items.data(), items.size());
       hs.bvh.root = bo.root; hs.bvh.n_nodes = bo.n_nodes; hs.bvh.max_stack = bo.max_stack;
@@ -573,6 +581,57 @@ struct Pipeline {
          be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(nullptr, nullptr, (uint32_t)n, dscene, dO, dD, dC);
          be.download(outOccl, dC, n);
       }
+      return 0;
+   }
+
+   // ---- the host's kd-tree as an alternative accelerator input (kdtree.h)
+   int uploadKd(const blingcu_kdnode *nodes, uint32_t nNodesKd, int32_t root, const uint32_t *leaf, size_t nLeaf, const float *bounds) {
+      if (!uploaded) return fail(BLINGCU_ESTATE, "upload_kdtree before upload_scene");
+      freeKd();
+      if (!nodes || nNodesKd == 0 || !bounds || (nLeaf && !leaf)) return fail(BLINGCU_EINVAL, "kd-tree without nodes / bounds / leaf primitives");
+      if (root < 0 || (uint32_t)root >= nNodesKd) return fail(BLINGCU_EINVAL, "kd-tree root out of range");
+      // every reference in range, no child pointing backwards at the root, depth within the traversal stack
+      for (uint32_t i = 0; i < nNodesKd; ++i) {
+         const blingcu_kdnode &n = nodes[i];
+         if (n.left < 0) { if ((size_t)n.first + n.count > nLeaf) return fail(BLINGCU_EINVAL, "kd-tree leaf range out of bounds"); }
+         else if ((uint32_t)n.left >= nNodesKd || n.right < 0 || (uint32_t)n.right >= nNodesKd || n.axis < 0 || n.axis > 2) return fail(BLINGCU_EINVAL, "kd-tree interior node malformed");
+      }
+      for (size_t i = 0; i < nLeaf; ++i) if (leaf[i] >= nPrims) return fail(BLINGCU_EINVAL, "kd-tree leaf primitive out of range");
+      {
+         std::vector<std::pair<int32_t, int>> st; st.emplace_back(root, 1); size_t visited = 0;
+         while (!st.empty()) {
+            auto [ni, depth] = st.back(); st.pop_back();
+            if (++visited > (size_t)nNodesKd) return fail(BLINGCU_EINVAL, "kd-tree is not a tree");
+            if (depth > BL_KD_STACK) return fail(BLINGCU_EINVAL, "kd-tree deeper than the traversal stack");
+            const blingcu_kdnode &n = nodes[ni];
+            if (n.left >= 0) { st.emplace_back(n.left, depth + 1); st.emplace_back(n.right, depth + 1); }
+         }
+      }
+      auto upk = [&](const void *src, size_t bytes) { void *d = be.alloc(bytes); be.upload(d, src, bytes); kdAllocs.push_back(d); return d; };
+      kd.nodes = (const blingcu_kdnode *)upk(nodes, sizeof(blingcu_kdnode) * nNodesKd);
+      static const uint32_t none = 0;
+      kd.leaf = (const uint32_t *)upk(nLeaf ? leaf : &none, sizeof(uint32_t) * (nLeaf ? nLeaf : 1));
+      kd.primRef = primRefDev; kd.root = root;
+      for (int k = 0; k < 3; ++k) { kd.lo[k] = bounds[k]; kd.hi[k] = bounds[3 + k]; }
+      kdUploaded = true;
+      return 0;
+   }
+   int traceKd(const blingcu_ray *rays, size_t n, blingcu_hit *outHit, uint32_t *nodes, uint32_t *prims) {
+      if (!kdUploaded) return fail(BLINGCU_ESTATE, "trace_kdtree before upload_kdtree");
+      if (n == 0) return 0;
+      if (n > 0x7fffffffu) return fail(BLINGCU_EINVAL, "too many rays");
+      if (n > tbCap) {
+         freeTraceScratch();
+         tb[0] = be.alloc(sizeof(F4) * 2 * n); tb[1] = be.alloc(sizeof(F4) * n); tb[2] = be.alloc(sizeof(F4) * n);
+         tb[3] = be.alloc(sizeof(F4) * n); tb[4] = be.alloc(4 * n); tb[5] = be.alloc(4 * n);
+         tbCap = n;
+      }
+      F4 *dR = (F4 *)tb[0], *dO = (F4 *)tb[1], *dD = (F4 *)tb[2], *dH = (F4 *)tb[3]; uint32_t *dN = (uint32_t *)tb[4], *dP = (uint32_t *)tb[5];
+      be.upload(dR, rays, sizeof(F4) * 2 * n);
+      be.tag(BLINGCU_KC_OTHER); be.run(SplitRaysBody{dR, dO, dD}, (uint32_t)n);
+      be.run(TraceKdBody{dscene, kd, dO, dD, dH, dN, dP}, (uint32_t)n);
+      be.run(HitToAbiBody{dscene, dH}, (uint32_t)n);
+      be.download(outHit, dH, sizeof(F4) * n); be.download(nodes, dN, 4 * n); be.download(prims, dP, 4 * n);
       return 0;
    }
 

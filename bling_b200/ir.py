@@ -116,8 +116,13 @@ class Stats(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class KdNode(C.Structure):   # blingcu_kdnode
+    _fields_ = [("left", C.c_int32), ("right", C.c_int32), ("split", C.c_float), ("axis", C.c_int32), ("first", C.c_uint32), ("count", C.c_uint32)]
+
+
 RAY_DTYPE = np.dtype([("o", np.float32, 3), ("tmin", np.float32), ("d", np.float32, 3), ("tmax", np.float32)])
 HIT_DTYPE = np.dtype([("t", np.float32), ("prim", np.int32), ("b1", np.float32), ("b2", np.float32)])
+KDNODE_DTYPE = np.dtype([("left", np.int32), ("right", np.int32), ("split", np.float32), ("axis", np.int32), ("first", np.uint32), ("count", np.uint32)])   # blingcu_kdnode
 
 
 def _fp(a: Optional[np.ndarray]):

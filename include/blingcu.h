@@ -304,6 +304,18 @@ int blingcu_render_pass(blingcu_ctx *, uint32_t pass_index, uint64_t seed);
  * render_pass == render_slice(0, nu*nv). */
 int blingcu_render_slice(blingcu_ctx *, uint32_t pass_index, uint64_t seed, uint32_t s_begin, uint32_t s_end);
 
+/* SURVEY 8(f)3 -- the HOST's own accelerator as an alternative input: bling's SAH kd-tree (Primitive/KdTree.hs:29-33) flattened
+ * into an array. Interior: children `left` / `right`, split position and axis; Leaf: left = -1 and the primitive ids
+ * leaf_prims[first .. first + count) in the leaf's own order. blingcu_trace_kdtree walks it exactly as `traverse` does
+ * (KdTree.hs:223-242; entered through intersectAABB on `bounds` = lo xyz, hi xyz) on the uploaded scene's primitives and returns,
+ * per ray, the hit and the two counters of dbgTraverse / TraversalStats (KdTree.hs:252-281) -- so a host can check the GPU against
+ * its own tree node for node. The product's render path does not use it (it traverses the library's BVH). */
+typedef struct blingcu_kdnode { int32_t left, right; float split; int32_t axis; uint32_t first, count; } blingcu_kdnode;
+int blingcu_upload_kdtree(blingcu_ctx *, const blingcu_kdnode *nodes, uint32_t n_nodes, int32_t root,
+                          const uint32_t *leaf_prims, size_t n_leaf_prims, const float bounds[6]);
+int blingcu_trace_kdtree(blingcu_ctx *, const blingcu_ray *rays, size_t n, blingcu_hit *out,
+                         uint32_t *nodes_traversed, uint32_t *intersections);
+
 /* debug/parity: radiance of individual samples (no film). pixel coordinates are in sample-extent
  * space (may be negative, Image.hs:162-168); out_L = n*16 floats; out_xy = n*2 image positions. */
 int blingcu_render_samples(blingcu_ctx *, uint32_t pass_index, uint64_t seed, const int32_t *px,

@@ -589,6 +589,29 @@ int oracle_trace_nearest(oracle_ctx *c, const blingcu_ray *rays, size_t n, bling
    if (intersections) *intersections = ni;
    return 0;
 }
+int oracle_export_kdtree(oracle_ctx *c, blingcu_kdnode *nodes, uint32_t *n_nodes, uint32_t *leaf_prims, size_t *n_leaf_prims, int32_t *root, float bounds[6]) {
+   const Geometry &g = c->sc.geo;
+   if (!g.kd_built) return BLINGCU_ESTATE;
+   *n_nodes = (uint32_t)g.nodes.size(); *n_leaf_prims = g.leafPrims.size(); *root = g.root;
+   bounds[0] = g.bounds.lo.x; bounds[1] = g.bounds.lo.y; bounds[2] = g.bounds.lo.z; bounds[3] = g.bounds.hi.x; bounds[4] = g.bounds.hi.y; bounds[5] = g.bounds.hi.z;
+   if (nodes) for (size_t i = 0; i < g.nodes.size(); ++i) {
+      const KdNode &n = g.nodes[i];
+      nodes[i].left = n.left; nodes[i].right = n.right; nodes[i].split = n.sp; nodes[i].axis = n.axis; nodes[i].first = n.first; nodes[i].count = n.count;
+   }
+   if (leaf_prims) for (size_t i = 0; i < g.leafPrims.size(); ++i) leaf_prims[i] = g.leafPrims[i];
+   return 0;
+}
+int oracle_trace_kd_stats(oracle_ctx *c, const blingcu_ray *rays, size_t n, blingcu_hit *out, uint32_t *nodes_traversed, uint32_t *intersections) {
+   if (!c->sc.geo.kd_built) return BLINGCU_ESTATE;
+   for (size_t i = 0; i < n; ++i) {
+      uint64_t nt = 0, ni = 0;
+      Hit h = c->sc.geo.kdNearest(toRay(rays[i]), &nt, &ni);
+      out[i].t = h.valid ? h.t : 0; out[i].prim = h.valid ? h.prim : -1;
+      out[i].b1 = (h.valid && h.dg.tri) ? h.dg.b1 : 0; out[i].b2 = (h.valid && h.dg.tri) ? h.dg.b2 : 0;
+      nodes_traversed[i] = (uint32_t)nt; intersections[i] = (uint32_t)ni;
+   }
+   return 0;
+}
 int oracle_trace_occluded(oracle_ctx *c, const blingcu_ray *rays, size_t n, uint8_t *out, int mode) {
    if (mode == 1 && !c->sc.geo.kd_built) return BLINGCU_ESTATE;
    for (size_t i = 0; i < n; ++i) {

@@ -12,6 +12,10 @@ int oracle_create(const blingcu_scene *ir, int build_kdtree, oracle_ctx **out);
 void oracle_destroy(oracle_ctx *);
 int oracle_trace_nearest(oracle_ctx *, const blingcu_ray *rays, size_t n, blingcu_hit *out, int mode,
                          uint64_t *nodes_traversed, uint64_t *intersections);
+/* the kd-tree of KdTree.hs as a flat array (the form a host hands to blingcu_upload_kdtree) and per-ray dbgTraverse counters */
+int oracle_export_kdtree(oracle_ctx *, blingcu_kdnode *nodes, uint32_t *n_nodes, uint32_t *leaf_prims, size_t *n_leaf_prims,
+                         int32_t *root, float bounds[6]);   /* nodes / leaf_prims may be NULL: sizes only */
+int oracle_trace_kd_stats(oracle_ctx *, const blingcu_ray *rays, size_t n, blingcu_hit *out, uint32_t *nodes_traversed, uint32_t *intersections);
 int oracle_trace_occluded(oracle_ctx *, const blingcu_ray *rays, size_t n, uint8_t *out, int mode);
 int oracle_sample_extent(oracle_ctx *, int32_t *x0, int32_t *x1, int32_t *y0, int32_t *y1);
 int oracle_render_samples(oracle_ctx *, uint32_t pass, uint64_t seed, const int32_t *px, const int32_t *py,

@@ -31,6 +31,8 @@ def lib():
         L.oracle_destroy.argtypes = [P]; L.oracle_destroy.restype = None
         L.oracle_trace_nearest.argtypes = [P, P, C.c_size_t, P, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.oracle_trace_occluded.argtypes = [P, P, C.c_size_t, P, C.c_int]
+        L.oracle_export_kdtree.argtypes = [P, P, C.POINTER(C.c_uint32), P, C.POINTER(C.c_size_t), C.POINTER(C.c_int32), P]
+        L.oracle_trace_kd_stats.argtypes = [P, P, C.c_size_t, P, P, P]
         L.oracle_sample_extent.argtypes = [P] + [C.POINTER(C.c_int32)] * 4
         L.oracle_render_samples.argtypes = [P, C.c_uint32, C.c_uint64, P, P, P, C.c_size_t, P, P]
         L.oracle_render_slice.argtypes = [P, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int]
@@ -74,6 +76,21 @@ class Oracle:
                                         C.byref(nt), C.byref(ni)), "trace_nearest")
         self.last_traversal = (nt.value, ni.value)
         return out
+
+    def kdtree_flat(self):
+        """(nodes, leaf_prims, root, bounds): the SAH kd-tree of KdTree.hs as the flat arrays blingcu_upload_kdtree takes"""
+        nn, nl, root = C.c_uint32(), C.c_size_t(), C.c_int32(); b = (C.c_float * 6)()
+        _chk(lib().oracle_export_kdtree(self._h, None, C.byref(nn), None, C.byref(nl), C.byref(root), b), "export_kdtree")
+        nodes = np.zeros(nn.value, IR.KDNODE_DTYPE); leaf = np.zeros(max(1, nl.value), np.uint32)
+        _chk(lib().oracle_export_kdtree(self._h, nodes.ctypes.data, C.byref(nn), leaf.ctypes.data, C.byref(nl), C.byref(root), b), "export_kdtree")
+        return nodes, leaf[:nl.value], root.value, np.array(list(b), np.float32)
+
+    def trace_kd_stats(self, rays: np.ndarray):
+        """kd-tree traversal with the per-ray counters of dbgTraverse (KdTree.hs:260-281)"""
+        rays = np.ascontiguousarray(rays, IR.RAY_DTYPE); out = np.zeros(len(rays), IR.HIT_DTYPE)
+        nt = np.zeros(len(rays), np.uint32); ni = np.zeros(len(rays), np.uint32)
+        _chk(lib().oracle_trace_kd_stats(self._h, rays.ctypes.data, len(rays), out.ctypes.data, nt.ctypes.data, ni.ctypes.data), "trace_kd_stats")
+        return out, nt, ni
 
     def trace_occluded(self, rays: np.ndarray, mode="brute"):
         rays = np.ascontiguousarray(rays, IR.RAY_DTYPE); out = np.zeros(len(rays), np.uint8)

@@ -189,6 +189,28 @@ def test_converged_render_vs_golden(ctx, name):
     assert rel_mse(xg, xo) < float(g["relmse_bound"]), (name, rel_mse(xg, xo), float(g["relmse_bound"]))
 
 
+@pytest.mark.parametrize("name", ["cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"])
+def test_converged_render_quarter_config_size(ctx, name):
+    """SURVEY 8(d) "converged parity": BASELINE.json configs[0..3] at 1/4 LINEAR config size (cornell-box 128x128, glass-torus /
+    specular 256x256, ducky / sun-sky / environment 480x270), 4096 spp on the GPU vs the committed 4096-spp oracle render made
+    with a different seed (tools/make_golden_renders.py --quarter): rel-MSE within 3x the oracle's own noise floor (two
+    independent 2048-spp halves) and per-channel mean within 0.5 %."""
+    f = ROOT / "tests" / "golden" / "renders_quarter" / f"{name}.npz"
+    if not f.exists():
+        pytest.skip("quarter-size golden render not generated")
+    g = np.load(f)
+    w, h, nu, nv, passes = (int(x) for x in g["cfg"])
+    assert nu * nv * passes >= 4096
+    sc = small(load_scene(name), w, h, nu, nv)
+    ctx.upload_scene(sc)
+    for p in range(1, passes + 1):
+        ctx.render_pass(p, 0xC0FFEE)
+    xg, xo = image.film_xyz(ctx.read_film()), g["xyz"]
+    for c in range(3):
+        assert abs(xg[..., c].mean() / xo[..., c].mean() - 1) < 5e-3, (name, c, xg[..., c].mean() / xo[..., c].mean())
+    assert rel_mse(xg, xo) < float(g["relmse_bound"]), (name, rel_mse(xg, xo), float(g["relmse_bound"]))
+
+
 def test_fused_and_separate_nee_resolve_are_bit_identical(ctx):
     """option "fuse_resolve" (pipeline.h): the any-hit kernel adds an unoccluded shadow ray's pending contribution when it
     retires the ray, or a separate resolve launch does; same arithmetic in the same order -> identical films."""
@@ -260,6 +282,15 @@ def test_traversal_counters_of_the_product_kernels(ctx):
     assert 0 < st["any_nodes_traversed"] <= st["nodes_traversed"] * 1.5 and st["any_intersections"] > 0
     _, nodes, prims = ctx.trace_stats(rays[:20_000])                             # per-ray counts of the sequential walk (dbgTraverse)
     assert abs(nodes.mean() / (st["nodes_traversed"] / len(rays)) - 1) < 0.25    # the leaf queue tests against a slightly stale tmax
+
+
+@pytest.mark.parametrize("name", ["zoo", "ducky", "soup"])
+def test_reference_kdtree_on_the_gpu(name):
+    """SURVEY 8(f)3 on the GPU (see tests/test_host_and_emu.py::_check_reference_kdtree)"""
+    from tests.test_host_and_emu import _check_reference_kdtree
+    sc = make_soup(200_000, 64, 36, 2, 2) if name == "soup" else load_scene(name)
+    c, *_ = _check_reference_kdtree(lambda: api.Context(0), sc, 40_000)
+    c.close()
 
 
 def test_film_reduction_is_a_consistent_snapshot(ctx):
@@ -346,6 +377,14 @@ def test_cfg5_full_size_properties(ctx):
     assert same.sum() > 50_000
     for f in ("t", "b1", "b2"):
         assert np.array_equal(got[f][same], want[f][same]), f
+    # SURVEY 8(f)3 at 10 M triangles: the same kd-tree, flattened and walked on the GPU, node for node
+    nodes, leaf, root, bounds = o.kdtree_flat()
+    ctx.upload_kdtree(nodes, leaf, root, bounds)
+    wk, wn, wi = o.trace_kd_stats(sub[:100_000])
+    gk, gn, gi = ctx.trace_kdtree(sub[:100_000])
+    for f in ("t", "prim", "b1", "b2"):
+        assert np.array_equal(gk[f], wk[f]), f
+    assert np.array_equal(gn, wn) and np.array_equal(gi, wi)
     o.close()
     ctx.reset_stats(); ctx.clear_film()
     ctx.render_slice(1, 7, 0, 2); a = ctx.read_film(); st = ctx.stats()

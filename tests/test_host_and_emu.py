@@ -23,7 +23,7 @@ def test_abi_exports_every_declared_symbol():
     so = g.build_cuda()
     hdr = (ROOT / "include" / "blingcu.h").read_text()
     declared = sorted(set(re.findall(r"\b(blingcu_[a-z_]+)\s*\(", hdr)))
-    assert len(declared) == len(api.SYMBOLS) == 33
+    assert len(declared) == len(api.SYMBOLS) == 35
     L = ctypes.CDLL(str(so))
     for name in declared:
         assert hasattr(L, name), name
@@ -39,7 +39,9 @@ def test_ctypes_mirror_matches_the_header_layout():
     lay = abi_layout.layout()
     mirror = {"blingcu_spectrum": IR.Spectrum, "blingcu_shape": IR.Shape, "blingcu_texture": IR.Texture, "blingcu_image": IR.ImageC,
               "blingcu_material": IR.Material, "blingcu_light": IR.Light, "blingcu_sunsky": IR.SunSky, "blingcu_envmap": IR.EnvMap,
-              "blingcu_camera": IR.Camera, "blingcu_scene": IR.SceneC, "blingcu_ray": IR.Ray, "blingcu_hit": IR.Hit, "blingcu_stats": IR.Stats}
+              "blingcu_camera": IR.Camera, "blingcu_scene": IR.SceneC, "blingcu_ray": IR.Ray, "blingcu_hit": IR.Hit, "blingcu_stats": IR.Stats,
+              "blingcu_kdnode": IR.KdNode}
+    assert IR.KDNODE_DTYPE.itemsize == lay["blingcu_kdnode"]["sizeof"] and all(IR.KDNODE_DTYPE.fields[k][1] == v for k, v in lay["blingcu_kdnode"].items() if k != "sizeof")
     assert set(lay) == set(mirror)
     import ctypes as C
     for name, ty in mirror.items():
@@ -220,6 +222,48 @@ def test_null_uvs_default_and_null_tables_are_rejected():
         with pytest.raises(api.BlingCuError):
             e.set_option("batch_samples", bad)
     e.close()
+
+
+def _check_reference_kdtree(make_ctx, sc, nrays):
+    """the oracle's SAH kd-tree (KdTree.hs restated), flattened, uploaded as an alternative accelerator input and
+    walked by kdtree.h exactly as `traverse` does: every hit field AND the per-ray dbgTraverse counters equal the oracle's."""
+    o = Oracle(sc, kdtree=True)
+    nodes, leaf, root, bounds = o.kdtree_flat()
+    c = make_ctx(); c.upload_scene(sc); c.upload_kdtree(nodes, leaf, root, bounds)
+    rays = np.concatenate([random_rays(sc, nrays, 17), camera_rays(None, sc, nrays, 18)])
+    want, wn, wi = o.trace_kd_stats(rays)
+    got, gn, gi = c.trace_kdtree(rays)
+    for f in ("t", "prim", "b1", "b2"):
+        assert np.array_equal(got[f], want[f]), f
+    assert np.array_equal(gn, wn) and np.array_equal(gi, wi)          # TraversalStats, ray by ray
+    assert (want["prim"] >= 0).mean() > 0.05 and wn.max() > 3
+    bvh = c.trace_nearest(rays)                                       # and the product's own accelerator finds the same hits
+    ties, bad = compare_hits(bvh, want)
+    assert bad == 0
+    return c, nodes, leaf, root, bounds
+
+
+@pytest.mark.parametrize("name", ["cornell-box", "zoo", "ducky"])
+def test_emulated_reference_kdtree_traversal(name):
+    c, nodes, leaf, root, bounds = _check_reference_kdtree(EmuContext, load_scene(name), 3000 if name == "ducky" else 6000)
+    # malformed trees are rejected, not walked
+    bad = nodes.copy(); inner = np.flatnonzero(bad["left"] >= 0)
+    if len(inner):
+        bad["right"][inner[0]] = len(bad) + 5
+        with pytest.raises(api.BlingCuError):
+            c.upload_kdtree(bad, leaf, root, bounds)
+        loop = nodes.copy(); loop["left"][inner[0]] = root
+        with pytest.raises(api.BlingCuError):
+            c.upload_kdtree(loop, leaf, root, bounds)
+    with pytest.raises(api.BlingCuError):
+        c.upload_kdtree(nodes, leaf + 10_000_000, root, bounds)
+    with pytest.raises(api.BlingCuError):
+        c.trace_kdtree(np.zeros(1, IR.RAY_DTYPE))                     # the failed uploads dropped the tree
+    c.close()
+    fresh = EmuContext()
+    with pytest.raises(api.BlingCuError):
+        fresh.upload_kdtree(nodes, leaf, root, bounds)                # no scene yet
+    fresh.close()
 
 
 def test_host_array_and_out_buffers():

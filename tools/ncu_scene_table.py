@@ -20,6 +20,8 @@ COLS = [("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots bus
 
 
 def klass(name):
+    if "kTraceWarpQ<(bool)0" in name or "kTraceWarpQ<0" in name: return "trace nearest"
+    if "kTraceWarpQ<(bool)1" in name or "kTraceWarpQ<1" in name: return "trace any"
     if "kTracePersistent<(bool)0>" in name or "kTracePersistent<0>" in name: return "trace nearest"
     if "kTracePersistent<(bool)1>" in name or "kTracePersistent<1>" in name: return "trace any"
     if "ClassifyBody" in name: return "classify"
@@ -32,7 +34,9 @@ def klass(name):
 
 
 def main():
-    out = ["# r01 -- named scenes (BASELINE.json configs[0..3]) at config size: where the time goes and how the SMs are used", "",
+    TAG = sys.argv[1] if len(sys.argv) > 1 else "r02"
+    summary = {}
+    out = [f"# {TAG} -- named scenes (BASELINE.json configs[0..3]) at config size: where the time goes and how the SMs are used", "",
            "SURVEY §8(d): these scenes hold 4 - 14 129 primitives and live in L1/L2, so the HBM roofline does not apply; reported instead:",
            "issue-slot utilisation, warp execution efficiency (threads per executed instruction), cache hit rates.", "",
            "`ncu --metrics gpu__time_duration.sum,smsp__issue_active…,lts__t_sector_hit_rate.pct,smsp__thread_inst_executed_per_inst_executed.ratio,"
@@ -64,7 +68,14 @@ def main():
             if a["t"] <= 0: continue
             out.append(f"| {k} | {a['n']} | {100 * a['t'] / tot:.1f} % | " + " | ".join(f"{a[m] / a['t']:.1f}" for m, _ in COLS) + " |")
         out.append("")
-    (ROOT / "profiles" / "r01_named_scenes.md").write_text("\n".join(out) + "\n")
+        whole = {m: sum(a[m] for a in agg.values()) / tot for m, _ in COLS}
+        summary[scene] = {"source": f"ncu --metrics pass of tools/scene_breakdown.py {scene} (profiles/{TAG}_named_scenes.md); duration-weighted over every launch of one slice",
+                          "issue_slots_busy_pct": whole[COLS[0][0]], "threads_per_instruction": whole[COLS[1][0]], "warp_execution_efficiency_pct": 100 * whole[COLS[1][0]] / 32,
+                          "l2_hit_pct": whole[COLS[2][0]], "l1_hit_pct": whole[COLS[3][0]], "dram_pct_of_peak": whole[COLS[4][0]], "occupancy_pct": whole[COLS[5][0]],
+                          "share_of_gpu_time": {k: a["t"] / tot for k, a in agg.items() if a["t"] > 0}}
+    import json
+    (ROOT / "profiles" / f"{TAG}_named_scenes.json").write_text(json.dumps(summary, indent=1) + "\n")
+    (ROOT / "profiles" / f"{TAG}_named_scenes.md").write_text("\n".join(out) + "\n")
     print("\n".join(out))
 
 
