@@ -589,6 +589,47 @@ int oracle_trace_nearest(oracle_ctx *c, const blingcu_ray *rays, size_t n, bling
    if (intersections) *intersections = ni;
    return 0;
 }
+int oracle_debug_eval(int what, const float *in, float *out) {
+   auto spec = [](const float *p) { Spec r; for (int i = 0; i < NB; ++i) r.v[i] = p[i]; return r; };
+   auto put = [](float *o, const Spec &sp) { for (int i = 0; i < NB; ++i) o[i] = sp.v[i]; };
+   auto v3 = [](const float *p) { return mk(p[0], p[1], p[2]); };
+   auto mfBx = [&](float e, const Spec &r) { BxDF b{}; b.kind = K_MICROFACET; b.type = BX_REFLECTION | BX_GLOSSY; b.r = r; b.fr = FR_DIELECTRIC; b.etai = 1; b.etat = 1.5f; b.e = e; b.flip = false; return b; };
+   switch (what) {
+   case 1: put(out, frDielectric(in[0], in[1], in[2])); return 0;
+   case 2: put(out, frConductor(spec(in), spec(in + 16), in[32])); return 0;
+   case 3: { V3 wh = v3(in + 1); out[0] = blinnD(in[0], wh); out[1] = blinnPdf(in[0], wh); out[2] = mfG(v3(in + 4), v3(in + 7), wh); return 0; }
+   case 4: {
+      BxDF b = mfBx(in[0], spec(in + 1));
+      V3 wo = v3(in + 17), wi = v3(in + 20);
+      put(out, bxdfEval(b, wo, wi)); out[16] = bxdfPdf(b, wo, wi);
+      Spec f = sConst(0); V3 ws = mk(0, 0, 0); float pdf = 0;
+      bxdfSample(b, wo, in[23], in[24], f, ws, pdf);
+      put(out + 17, f); out[33] = ws.x; out[34] = ws.y; out[35] = ws.z; out[36] = pdf;
+      return 0;
+   }
+   case 5: {
+      Bsdf bs{}; bs.n = 2;
+      bs.bx[0] = BxDF{}; bs.bx[0].kind = K_LAMBERT; bs.bx[0].type = BX_REFLECTION | BX_DIFFUSE; bs.bx[0].r = spec(in); bs.bx[0].flip = false;
+      bs.bx[1] = mfBx(in[32], spec(in + 16));
+      bs.cs.s = v3(in + 33); bs.cs.t = v3(in + 36); bs.cs.n = v3(in + 39); bs.ng = v3(in + 42); bs.p = mk(0, 0, 0);
+      V3 woW = v3(in + 45), wiW = v3(in + 48);
+      put(out, evalBsdf(bs, woW, wiW)); out[16] = bsdfPdf(bs, woW, wiW);
+      BsdfSample smp = sampleBsdf(bs, woW, in[51], in[52], in[53]);
+      out[17] = (float)smp.type; out[18] = smp.pdf; put(out + 19, smp.f); out[35] = smp.wi.x; out[36] = smp.wi.y; out[37] = smp.wi.z;
+      return 0;
+   }
+   case 6: {
+      blingcu_shape sh{}; sh.kind = (int)in[0]; for (int i = 0; i < 6; ++i) sh.p[i] = in[1 + i];
+      for (int i = 0; i < 16; ++i) { sh.o2w[i] = (i % 5 == 0) ? 1.0f : 0.0f; sh.w2o[i] = sh.o2w[i]; }
+      V3 pt = v3(in + 7), ps, ns;
+      sampleShape(sh, pt, in[10], in[11], ps, ns);
+      out[0] = ps.x; out[1] = ps.y; out[2] = ps.z; out[3] = ns.x; out[4] = ns.y; out[5] = ns.z;
+      out[6] = shapePdf(sh, pt, v3(in + 12));
+      return 0;
+   }
+   default: return BLINGCU_EINVAL;
+   }
+}
 int oracle_export_kdtree(oracle_ctx *c, blingcu_kdnode *nodes, uint32_t *n_nodes, uint32_t *leaf_prims, size_t *n_leaf_prims, int32_t *root, float bounds[6]) {
    const Geometry &g = c->sc.geo;
    if (!g.kd_built) return BLINGCU_ESTATE;

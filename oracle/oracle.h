@@ -26,6 +26,13 @@ int oracle_clear_film(oracle_ctx *);
 int oracle_get_stats(oracle_ctx *, blingcu_stats *);
 int oracle_reset_stats(oracle_ctx *);
 int oracle_eval_texture(oracle_ctx *, int32_t texture, const float *p, const float *uv, size_t n, float *out);
+/* single functions of oracle_shade.h at explicit arguments, for tests/test_third_statement.py (a pure-Python statement of the same
+ * Haskell text held against this one). what: 1 frDielectric(etai, etat, cosi) -> 16; 2 frConductor(eta16, k16, cosi) -> 16;
+ * 3 Blinn (e, wh3, wo3, wi3) -> D, pdf, mfG; 4 microfacet BxDF with frDielectric 1 1.5 (e, r16, wo3, wi3, u1, u2) -> eval16, pdf,
+ * sampled f16, wi3, pdf; 5 plastic-like Bsdf [Lambertian kd, Microfacet Blinn e (frDielectric 1 1.5) ks] (kd16, ks16, e, s3, t3, n3,
+ * ng3, woW3, wiW3, uComp, u1, u2) -> evalBsdf16, bsdfPdf, sample type, pdf, f16, wi3; 6 shape sampling (kind, p0..p5, pt3, u1, u2, wi3)
+ * -> ps3, ns3, shapePdf(pt, wi) */
+int oracle_debug_eval(int what, const float *in, float *out);
 int oracle_add_sample_tile(oracle_ctx *, int wx0, int wx1, int wy0, int wy1, float sx, float sy, const float *L16,
                            float *out_tile, int *ox, int *oy, int *w, int *h);
 #ifdef __cplusplus

@@ -31,6 +31,7 @@ def lib():
         L.oracle_destroy.argtypes = [P]; L.oracle_destroy.restype = None
         L.oracle_trace_nearest.argtypes = [P, P, C.c_size_t, P, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.oracle_trace_occluded.argtypes = [P, P, C.c_size_t, P, C.c_int]
+        L.oracle_debug_eval.argtypes = [C.c_int, P, P]
         L.oracle_export_kdtree.argtypes = [P, P, C.POINTER(C.c_uint32), P, C.POINTER(C.c_size_t), C.POINTER(C.c_int32), P]
         L.oracle_trace_kd_stats.argtypes = [P, P, C.c_size_t, P, P, P]
         L.oracle_sample_extent.argtypes = [P] + [C.POINTER(C.c_int32)] * 4
@@ -44,6 +45,16 @@ def lib():
         L.oracle_add_sample_tile.argtypes = [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, P, P] + [C.POINTER(C.c_int)] * 4
         _LIB = L
     return _LIB
+
+
+def debug_eval(what: int, args, n_out: int) -> np.ndarray:
+    """oracle_debug_eval: one function of oracle_shade.h at explicit arguments (tests/test_third_statement.py)"""
+    a = np.ascontiguousarray(np.concatenate([np.atleast_1d(np.asarray(x, np.float32)).ravel() for x in args]), np.float32)
+    out = np.zeros(n_out, np.float32)
+    rc = lib().oracle_debug_eval(what, a.ctypes.data, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"oracle_debug_eval({what}) failed with code {rc}")
+    return out
 
 
 def _chk(rc, what):
