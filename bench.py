@@ -114,6 +114,18 @@ def cpu_reference_run(scene, a, steps, warmup):
             "seconds": dt, "ms_per_step": dt / max(1, steps) * 1e3}
 
 
+def reference_toolchain():
+    """BASELINE.md plan item 6 / VERDICT r1 next-5(iv): is there a Haskell toolchain on this box that could build real bling?
+    (bling's own sources are not on the bench box either -- /root/reference exists only in the build container -- so this is a
+    probe that is reported, not a build: with GHC present the CPU arm would still be the restatement, and the line says so.)"""
+    import shutil
+    found = {t: shutil.which(t) for t in ("ghc", "stack", "cabal")}
+    src = Path("/root/reference/bling.cabal").exists()
+    return {**found, "bling_sources_present": src,
+            "note": "no Haskell toolchain on this box: the CPU arm is oracle/ (C++ restatement, kind \"port\")" if not any(found.values())
+                    else "a Haskell toolchain is present; bling's sources are " + ("present" if src else "absent") + ": the CPU arm is still oracle/ (kind \"port\")"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -126,6 +138,7 @@ def run_reference(a):
             "config": workload_config(a, a.gpus), "gpu_launches": 0,
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "reference_toolchain": reference_toolchain(),
             "note": "oracle/ C++ restatement of bling's CPU path (the Haskell reference cannot be built here: no GHC)"}
     print(json.dumps(line), flush=True)
 
@@ -451,7 +464,7 @@ def run_b200(a):
                 "warmup": a.warmup, "ms_per_step": ms_max / a.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(a, n_gpus),
                 "clocks": clk, "e2e": e2e, "e2e_trace": e2e_trace, "gpu_launches": int(launches), "roofline": roofline, "roofline_other": roofline_other,
-                "cpu_baseline": cpu_baseline,
+                "cpu_baseline": cpu_baseline, "reference_toolchain": reference_toolchain(),
                 "rays": {"nearest_hit_queries": rays_n, "any_hit_queries": rays_s, "per_sample": (rays_n + rays_s) / max(1.0, samples)},
                 "bvh": {"nodes": st["bvh_nodes"], "leaf_items": st["bvh_leaf_items"], "max_stack": st["bvh_max_stack"]},
                 "scenes": scenes}

@@ -42,8 +42,8 @@ def test_nearest_and_any_hit_parity(ctx, name, variant):
     assert same.sum() > 1000
     assert np.array_equal(got["t"][same], ref["t"][same])                      # bit-exact t
     assert np.array_equal(got["b1"][same], ref["b1"][same])
-    occ = ctx.trace_occluded(rays)
-    assert (occ != o.trace_occluded(rays, mode)).mean() < 2e-3
+    # measured on the B200 (tools/gpu_parity_diag.py, profiles/r02_parity_diag.md): 0 differing flags of 40 000 on every scene
+    assert np.array_equal(ctx.trace_occluded(rays), o.trace_occluded(rays, mode))
     ctx.set_option("trace_variant", 3)
 
 
@@ -118,12 +118,18 @@ def test_path_samples_match_oracle(ctx, name):
     Lg, xyg = ctx.render_samples(2, 77, px, py, s)
     assert np.array_equal(xyo, xyg)                                            # sampler SPEC is integer-exact
     rel = np.abs(Lo - Lg).max(1) / (np.abs(Lo).max(1) + 1e-6)
-    # libm differences (CUDA vs glibc sin/cos/pow/acos) move a few paths across discontinuities
-    assert (rel < 1e-3).mean() > 0.995, (name, (rel < 1e-3).mean())
-    # mean radiance, with the brightest 0.5 % of samples clipped: one firefly path that libm moves across a discontinuity
-    # (a specular chain onto a small emitter) may not decide the comparison of 20000 samples
+    # libm differences (CUDA vs glibc sin/cos/pow/acos) move a few paths across discontinuities. Measured on the B200
+    # (tools/gpu_parity_diag.py, profiles/r02_parity_diag.md): at most 0.03 % of the samples differ by more than 1e-3 (none on the
+    # six config scenes), at most 0.36 % by more than 1e-5; the bounds are twice the worst scene
+    assert (rel > 1e-3).mean() <= 6e-4, (name, (rel > 1e-3).mean())
+    assert (rel > 1e-5).mean() <= 7e-3, (name, (rel > 1e-5).mean())
+    if name in ("cornell-box", "glass-torus", "specular", "ducky", "sun-sky", "environment"):
+        assert (rel > 1e-3).sum() == 0, (name, (rel > 1e-3).sum())
+        assert abs(Lg.mean() / Lo.mean() - 1) < 1e-5                       # unclipped
+    # mean radiance with the brightest 0.5 % of samples clipped (one firefly that libm moves across a discontinuity -- `extras`: a
+    # specular chain onto a small emitter -- may not decide the comparison of 20 000 samples): measured <= 1.3e-4
     cap = np.percentile(Lo, 99.5)
-    assert abs(np.minimum(Lg, cap).mean() / np.minimum(Lo, cap).mean() - 1) < 5e-3
+    assert abs(np.minimum(Lg, cap).mean() / np.minimum(Lo, cap).mean() - 1) < 5e-4
 
 
 @pytest.mark.parametrize("name", ALL_SCENES)
