@@ -41,12 +41,15 @@ struct PathState {
    unsigned long long *stats;   // N_STATS
 };
 
-// where quarter q (4 bands) of slot i's spectrum lives. Product layout: four float4 PLANES (coalesced while the queue is dense).
-// Experiment switch BL_SPEC_AOS (tools/ab_libs.py, not the product build): one 64-byte record per slot, which keeps 32-byte sectors
-// full when the queue has thinned out after the first bounces.
+// where quarter q (4 bands) of slot i's spectrum lives. Product layout since round 2: ONE 64-BYTE RECORD per slot and spectrum
+// (two full 32-byte sectors whatever the queue looks like). Round 1 kept four float4 planes (`[q * cap + i]`, coalesced while
+// the queue is dense): after the first bounces the queue entries are increasing but sparse, a plane access then uses half of each
+// sector, and ncu had the shade kernels on the DRAM sector rate of exactly these scattered accesses. Measured on the B200
+// (tools/gpu_r02_f.sh, profiles/r02_shade_layout.md): shade -14 .. -23 %, the named scenes +6 .. +14 %, films bit-identical.
+// BL_SPEC_PLANES rebuilds the old layout for A/B (tools/ab_libs.py).
 HD size_t spec4At(uint32_t cap, uint32_t i, int q) {
-#ifdef BL_SPEC_AOS
-   return (size_t)i * 4 + q;
+#ifndef BL_SPEC_PLANES
+   (void)cap; return (size_t)i * 4 + q;
 #else
    return (size_t)q * cap + i;
 #endif

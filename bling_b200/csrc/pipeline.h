@@ -521,7 +521,7 @@ struct Pipeline {
       }
       be.sync();
       std::vector<F4> L(4 * (size_t)ps.cap); std::vector<F2> xy(n);
-#ifdef BL_SPEC_AOS   // experiment layout (bodies.h::spec4At): one 64-byte record per slot
+#ifndef BL_SPEC_PLANES   // product layout (bodies.h::spec4At): one 64-byte record per slot
       be.download(L.data(), ps.L, sizeof(F4) * 4 * n);
 #else
       for (int q = 0; q < 4; ++q) be.download(L.data() + (size_t)q * n, ps.L + (size_t)q * ps.cap, sizeof(F4) * n);

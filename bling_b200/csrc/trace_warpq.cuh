@@ -36,6 +36,18 @@ __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, fl
 __device__ __forceinline__ F4 lds128(uint32_t a) { F4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sminU32(uint32_t a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
+// L[slot] += P[slot], one quarter at a time. Out of line on purpose: the any-hit kernels live at 56 registers (9 CTAs per SM)
+// and this once-per-ray tail must not take part in the hot loop's register allocation (inlined, it pushed three loop-carried
+// values into local memory when the spectrum layout changed: +18 % kernel time on cfg 5, tools/gpu_r02_f.sh).
+__device__ __noinline__ void fuseAddPending(F4 *__restrict__ L, const F4 *__restrict__ P, uint32_t cap, uint32_t slot) {
+   for (int qq = 0; qq < 4; ++qq) {
+      const size_t at = spec4At(cap, slot, qq);
+      F4 l = L[at]; const F4 p_ = P[at];
+      l.x += p_.x; l.y += p_.y; l.z += p_.z; l.w += p_.w;
+      L[at] = l;
+   }
+}
+
 template <bool ANY, bool SORTED, bool STATS>
 __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLOCKS) kTraceWarpQ(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
                                                                  const DScene *__restrict__ sc, const F4 *__restrict__ O, const F4 *__restrict__ D,
@@ -215,14 +227,8 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
       // ---- retire rays whose walk is over and whose pairs are all through
       if (cur == WAITING && (int)(qhead - lastSeq) >= 0) {
          if (ANY) {
-            if (fuseL && !occ) {   // fused NEE resolve (trace_kernels.cuh): L += pending, one quarter at a time
-               for (int qq = 0; qq < 4; ++qq) {
-                  const size_t at = spec4At(fuseCap, slot, qq);
-                  F4 l = fuseL[at]; const F4 p_ = fuseP[at];
-                  l.x += p_.x; l.y += p_.y; l.z += p_.z; l.w += p_.w;
-                  fuseL[at] = l;
-               }
-            } else if (!fuseL) occl[slot] = occ ? 1 : 0;
+            if (fuseL && !occ) fuseAddPending(fuseL, fuseP, fuseCap, slot);   // fused NEE resolve (trace_kernels.cuh): L += pending
+            else if (!fuseL) occl[slot] = occ ? 1 : 0;
          } else hit[slot] = lds128(shitW + lane * 16u);
          cur = EMPTY;
       }
