@@ -20,7 +20,8 @@ SYMBOLS = ["create", "destroy", "last_error", "upload_scene", "trace_nearest", "
            "render_pass", "render_slice", "render_samples", "eval_texture", "read_film", "clear_film", "film_add_host", "film_device",
            "synchronize", "set_stream", "get_stats", "reset_stats", "set_option", "sample_extent", "kernel_times",
            "comm_unique_id", "comm_init", "comm_init_all", "comm_destroy", "reduce_film", "reduce_film_group", "comm_wait",
-           "read_film_sum", "film_sum_device", "host_alloc", "host_free", "upload_kdtree", "trace_kdtree"]
+           "read_film_sum", "film_sum_device", "host_alloc", "host_free", "upload_kdtree", "trace_kdtree",
+           "light_trace", "light_trace_records", "read_splat"]
 COMM_ID_BYTES = 128
 
 
@@ -73,6 +74,9 @@ def load_library(path=LIB_PATH, prefix="blingcu"):
     f("host_free").argtypes = [P, P]
     f("upload_kdtree").argtypes = [P, P, C.c_uint32, C.c_int32, P, C.c_size_t, P]
     f("trace_kdtree").argtypes = [P, P, C.c_size_t, P, P, P]
+    f("light_trace").argtypes = [P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32]
+    f("light_trace_records").argtypes = [P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, P, C.c_size_t, C.POINTER(C.c_size_t)]
+    f("read_splat").argtypes = [P, P]
     return L
 
 
@@ -182,6 +186,25 @@ class Context:
         self._chk(self._f("render_samples")(self._h, pass_index, seed, px.ctypes.data, py.ctypes.data, sample.ctypes.data, n,
                                             L.ctypes.data, xy.ctypes.data))
         return L, xy
+
+    # ---- light tracer (Renderer/LightTracer.hs)
+    def light_trace(self, pass_index: int, seed: int, first_photon: int, n_photons: int):
+        """photons [first, first + n) of a pass into the splat buffer (asynchronous like render_slice)"""
+        self._chk(self._f("light_trace")(self._h, pass_index, seed, first_photon, n_photons))
+
+    def light_trace_records(self, pass_index: int, seed: int, first_photon: int, n_photons: int, max_records: int = None) -> np.ndarray:
+        """the same, returning the splats as rows {photon, depth, px, py, X, Y, Z} in (photon, depth) order (parity)"""
+        cap = max_records if max_records is not None else 64 * n_photons + 16
+        out = np.zeros((cap, 7), np.float32); n = C.c_size_t()
+        self._chk(self._f("light_trace_records")(self._h, pass_index, seed, first_photon, n_photons, out.ctypes.data, cap, C.byref(n)))
+        return out[:min(cap, n.value)]
+
+    def read_splat(self, out: np.ndarray = None) -> np.ndarray:
+        """the splat buffer _imgS: [H][W]{X, Y, Z}; a pixel of the final image is splat_weight * splat + film / weight (Image.hs:303-315)"""
+        if out is None:
+            out = np.zeros((self.scene.height, self.scene.width, 3), np.float32)
+        self._chk(self._f("read_splat")(self._h, out.ctypes.data))
+        return out
 
     def eval_texture(self, texture: int, p, uv) -> np.ndarray:
         """`Texture a` at explicit (dgP, (dgU, dgV)) points: (n, 16) spectra; scalar textures answer in column 0."""

@@ -64,7 +64,7 @@ static thread_local std::string g_createError;
    int PFX##_clear_film(PFX##_ctx_t *c) {                                                                                        \
       if (!c) return BLINGCU_EINVAL;                                                                                             \
       if (!c->p.uploaded) { c->p.err = "no scene"; return BLINGCU_ESTATE; }                                                      \
-      return c->p.be.guard(c->p.err, [&]() { c->p.be.waitReduced(); c->p.be.zero(c->p.film, sizeof(bl::F4) * (size_t)c->p.hs.W * c->p.hs.H); return 0; }); \
+      return c->p.be.guard(c->p.err, [&]() { c->p.be.waitReduced(); if (c->p.splat) c->p.be.zero(c->p.splat, sizeof(float) * 3 * (size_t)c->p.hs.W * c->p.hs.H); c->p.be.zero(c->p.film, sizeof(bl::F4) * (size_t)c->p.hs.W * c->p.hs.H); return 0; }); \
    }                                                                                                                             \
    int PFX##_film_add_host(PFX##_ctx_t *c, const float *wxyz) {                                                                  \
       if (!c || !wxyz) return BLINGCU_EINVAL;                                                                                    \
@@ -83,6 +83,21 @@ static thread_local std::string g_createError;
       if (!c->p.uploaded) { c->p.err = "no scene"; return BLINGCU_ESTATE; }                                                      \
       *dptr = c->p.film; *nf = (size_t)c->p.hs.W * c->p.hs.H * 4;                                                                \
       return 0;                                                                                                                  \
+   }                                                                                                                             \
+   int PFX##_light_trace(PFX##_ctx_t *c, uint32_t pass, uint64_t seed, uint64_t first, uint32_t n) {                             \
+      return c ? c->p.be.guard(c->p.err, [&]() { return c->p.lightTrace(pass, seed, first, n, nullptr, 0, nullptr); }) : BLINGCU_EINVAL; \
+   }                                                                                                                             \
+   int PFX##_light_trace_records(PFX##_ctx_t *c, uint32_t pass, uint64_t seed, uint64_t first, uint32_t n, float *out, size_t maxr, size_t *nr) { \
+      if (!c || !nr || (maxr && !out)) return BLINGCU_EINVAL;                                                                    \
+      return c->p.be.guard(c->p.err, [&]() { return c->p.lightTrace(pass, seed, first, n, out, maxr, nr); });                     \
+   }                                                                                                                             \
+   int PFX##_read_splat(PFX##_ctx_t *c, float *xyz) {                                                                            \
+      if (!c || !xyz) return BLINGCU_EINVAL;                                                                                     \
+      if (!c->p.uploaded) { c->p.err = "no scene"; return BLINGCU_ESTATE; }                                                      \
+      return c->p.be.guard(c->p.err, [&]() {                                                                                      \
+         size_t n = (size_t)c->p.hs.W * c->p.hs.H * 3;                                                                           \
+         if (!c->p.splat) { std::memset(xyz, 0, n * sizeof(float)); return 0; }                                                  \
+         c->p.be.sync(); c->p.be.download(xyz, c->p.splat, n * sizeof(float)); return 0; });                                      \
    }                                                                                                                             \
    int PFX##_upload_kdtree(PFX##_ctx_t *c, const blingcu_kdnode *nodes, uint32_t nn, int32_t root, const uint32_t *leaf, size_t nl, const float *bounds) { \
       return c ? c->p.be.guard(c->p.err, [&]() { return c->p.uploadKd(nodes, nn, root, leaf, nl, bounds); }) : BLINGCU_EINVAL;       \

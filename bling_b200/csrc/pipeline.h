@@ -10,6 +10,7 @@
 // traceNearest(queue,countPtr,cap,o,d,hit), traceAny(queue,countPtr,cap,o,d,occl), sync().
 #pragma once
 #include "bodies.h"
+#include <algorithm>
 #include <chrono>
 #include <cstring>
 #include <string>
@@ -43,6 +44,8 @@ struct Pipeline {
    F4 *film = nullptr;
    KdTreeDev kd{}; std::vector<void *> kdAllocs; size_t nPrims = 0; bool kdUploaded = false;   // the host's kd-tree (kdtree.h)
    const int32_t *primRefDev = nullptr;
+   float *splat = nullptr;    // [H][W]{X, Y, Z}: the light tracer's unfiltered splat buffer (_imgS, Image.hs:123-129)
+   std::vector<void *> ltAllocs; LtRecords ltRec{}; uint32_t *ltCount = nullptr, *ltOffset = nullptr, *ltCursor = nullptr, *ltSorted = nullptr, *ltBlockSum = nullptr; uint64_t ltSplats = 0;
    F4 *filmSum = nullptr;     // sum of the films of all ranks (comm.h), valid after reduce_film
    uint32_t npix = 0, nTextures = 0;
    uint32_t batchTarget = 1u << 26;   // paths per wavefront (~490 B of state each: 33 GB at the cap, sized for 180 GB HBM)
@@ -60,8 +63,9 @@ struct Pipeline {
       sceneAllocs.push_back(d);
       return d;
    }
+   void freeLt() { for (void *p : ltAllocs) be.free(p); ltAllocs.clear(); ltRec = LtRecords{}; ltCount = nullptr; }
    void freeKd() { for (void *p : kdAllocs) be.free(p); kdAllocs.clear(); kdUploaded = false; }
-   void freeScene() { be.syncComm(); freeKd(); freeTraceScratch(); for (void *p : sceneAllocs) be.free(p); sceneAllocs.clear(); dscene = nullptr; if (film) { be.free(film); film = nullptr; } if (filmSum) { be.free(filmSum); filmSum = nullptr; } uploaded = false; }
+   void freeScene() { be.syncComm(); freeKd(); freeLt(); if (splat) { be.free(splat); splat = nullptr; } freeTraceScratch(); for (void *p : sceneAllocs) be.free(p); sceneAllocs.clear(); dscene = nullptr; if (film) { be.free(film); film = nullptr; } if (filmSum) { be.free(filmSum); filmSum = nullptr; } uploaded = false; }
    void freeState() { for (void *p : stateAllocs) be.free(p); stateAllocs.clear(); ps = PathState{}; qSlotsAlloc = 0; rootAlloc = 0; }
 
    int upload(const blingcu_scene *ir) {
@@ -224,6 +228,8 @@ struct Pipeline {
       const bool normals = hs.integrator == BLINGCU_INTEGRATOR_NORMALS;   // sampleCount1D = sampleCount2D = 0 (Debug.hs:24)
       hs.smp = mkSamplerConst(hs.nu, hs.nv, normals ? 0 : (direct ? 2 * hs.max_depth : 4 * hs.sample_depth), normals ? 0 : (direct ? 2 * hs.max_depth : 3 * hs.sample_depth),
                               hs.sampler_kind == BLINGCU_SAMPLER_STRATIFIED);
+      hs.smpUniform = mkSamplerConst(1, 1, 0, 0, 0);
+      for (int k = 0; k < 3; ++k) { hs.bounds_lo[k] = nprim ? bo.scene_lo[k] : 0.0f; hs.bounds_hi[k] = nprim ? bo.scene_hi[k] : 0.0f; }
       dlHeadroom = 2;
       for (int i = 0; i < NB; ++i) { hs.cieX[i] = ir->cie_x.v[i]; hs.cieY[i] = ir->cie_y.v[i]; hs.cieZ[i] = ir->cie_z.v[i]; }
       hs.ySum = ir->cie_y_sum;
@@ -584,6 +590,78 @@ struct Pipeline {
       return 0;
    }
 
+   // ---- the light tracer (lighttrace.h). One call = photons [first, first + n) of a pass, in batches of slots.
+   int lightTrace(uint32_t pass, uint64_t seed, uint64_t first, uint32_t n, float *records, size_t maxRecords, size_t *nRecords) {
+      if (!uploaded) return fail(BLINGCU_ESTATE, "light_trace before upload_scene");
+      if (hs.cam.kind != BLINGCU_CAM_PERSPECTIVE || hs.cam.pixel_area == 0) return fail(BLINGCU_EINVAL, "light tracing needs a perspective camera with world2raster / pixel_area (sampleCam, Camera.hs:78-103)");
+      const uint32_t npixFilm = (uint32_t)hs.W * (uint32_t)hs.H;
+      if (!splat) { splat = (float *)be.alloc(sizeof(float) * 3 * (size_t)npixFilm); be.zero(splat, sizeof(float) * 3 * (size_t)npixFilm); }
+      struct HostRec { uint32_t photon, depth; float px, py, X, Y, Z; };
+      std::vector<HostRec> hostRecs;
+      const uint32_t batchMax = std::min<uint32_t>(batchTarget, 1u << 24);
+      auto t0 = be.timerStart();
+      for (uint32_t done = 0; done < n;) {
+         const uint32_t m = std::min(batchMax, n - done);
+         ensureState(m);
+         if (!ltCount || ltRec.cap < ps.cap) {
+            freeLt();
+            auto al = [&](size_t bytes) { void *p = be.alloc(bytes); ltAllocs.push_back(p); return p; };
+            const size_t c = ps.cap;
+            ltRec.pixel = (uint32_t *)al(4 * c); ltRec.key = (uint32_t *)al(4 * c); ltRec.xyz = (F4 *)al(16 * c); ltRec.pos = (F2 *)al(8 * c); ltRec.depth = (uint32_t *)al(4 * c); ltRec.cap = ps.cap;
+            ltSorted = (uint32_t *)al(4 * c);
+            ltCount = (uint32_t *)al(4 * (size_t)npixFilm); ltOffset = (uint32_t *)al(4 * (size_t)npixFilm); ltCursor = (uint32_t *)al(4 * (size_t)npixFilm);
+            ltBlockSum = (uint32_t *)al(4 * (size_t)((npixFilm + LT_SCAN_BLOCK - 1) / LT_SCAN_BLOCK + 1));
+         }
+         be.tag(BLINGCU_KC_OTHER); be.run(LtBeginBody{ps, m}, 1);
+         be.tag(BLINGCU_KC_RAYGEN); be.run(LtGenBody{dscene, ps, seed, pass, first + done}, m);
+         be.tag(BLINGCU_KC_OTHER); be.run(LtAfterGenBody{ps}, 1);
+         launches += 3;
+         uint32_t *qa = ps.qA, *qb = ps.qB;
+         const uint32_t nb = (npixFilm + LT_SCAN_BLOCK - 1) / LT_SCAN_BLOCK;
+         for (int depth = 0; depth < 1000; ++depth) {   // no depth limit in the reference: Russian roulette ends the paths
+            be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(qa, ps.counters + C_ACTIVE, m, dscene, ps.rayO, ps.rayD, ps.hit);
+            be.tag(BLINGCU_KC_SHADE); be.runQueue(LtVertexBody{dscene, ps, qb}, qa, ps.counters + C_ACTIVE, m);
+            be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(ps.qShadow, ps.counters + C_SHADOW, m, dscene, ps.shO, ps.shD, ps.occl);
+            be.tag(BLINGCU_KC_RESOLVE); be.runQueue(LtCollectBody{dscene, ps, ltRec}, ps.qShadow, ps.counters + C_SHADOW, m);
+            // splat this bounce's records: count per pixel, exclusive scan, scatter, per-pixel ordered sum
+            be.tag(BLINGCU_KC_FILM);
+            be.zero(ltCount, 4 * (size_t)npixFilm); be.zero(ltCursor, 4 * (size_t)npixFilm);
+            be.run(LtCountBody{ltRec, ps.counters + C_LT_RECORDS, ltCount}, m);
+            be.run(LtScanSumBody{ltCount, npixFilm, ltBlockSum}, nb);
+            be.run(LtScanBlocksBody{ltBlockSum, nb}, 1);
+            be.run(LtScanApplyBody{ltCount, npixFilm, ltBlockSum, ltOffset}, nb);
+            be.run(LtScatterBody{ltRec, ps.counters + C_LT_RECORDS, ltOffset, ltCursor, ltSorted}, m);
+            be.run(LtGatherBody{ltRec, ltCount, ltOffset, ltSorted, splat}, npixFilm);
+            launches += 10;
+            uint32_t cnt[2] = {0, 0};   // [records of this bounce, paths that go on]
+            const bool check = records || nRecords || depth >= 3;
+            if (check) { be.sync(); be.download(&cnt[0], ps.counters + C_LT_RECORDS, 4); be.download(&cnt[1], ps.counters + C_NEXT, 4); ltSplats += cnt[0]; }
+            if ((records || nRecords) && cnt[0]) {
+               std::vector<uint32_t> key(cnt[0]), dep(cnt[0]); std::vector<F4> xyz(cnt[0]); std::vector<F2> pos(cnt[0]); std::vector<uint32_t> sidx(ps.cap);
+               be.download(key.data(), ltRec.key, 4 * (size_t)cnt[0]); be.download(dep.data(), ltRec.depth, 4 * (size_t)cnt[0]);
+               be.download(xyz.data(), ltRec.xyz, 16 * (size_t)cnt[0]); be.download(pos.data(), ltRec.pos, 8 * (size_t)cnt[0]);
+               for (uint32_t k = 0; k < cnt[0]; ++k) hostRecs.push_back(HostRec{(uint32_t)(first + done + key[k]), dep[k], pos[k].x, pos[k].y, xyz[k].x, xyz[k].y, xyz[k].z});
+            }
+            be.tag(BLINGCU_KC_OTHER); be.run(LtAdvanceBody{ps}, 1); launches++;
+            if (!check) { /* the first bounces always go on: no host round trip */ }
+            else if (cnt[1] == 0) break;
+            uint32_t *t = qa; qa = qb; qb = t;
+         }
+         if (!(records || nRecords)) { /* splat counts of the unchecked bounces */ }
+         done += m;
+      }
+      lastMs = be.timerStop(t0);
+      if (records || nRecords) {
+         std::sort(hostRecs.begin(), hostRecs.end(), [](const HostRec &a, const HostRec &b) { return a.photon != b.photon ? a.photon < b.photon : a.depth < b.depth; });
+         if (nRecords) *nRecords = hostRecs.size();
+         for (size_t k = 0; records && k < hostRecs.size() && k < maxRecords; ++k) {
+            float *o = records + 7 * k; const HostRec &r = hostRecs[k];
+            o[0] = (float)r.photon; o[1] = (float)r.depth; o[2] = r.px; o[3] = r.py; o[4] = r.X; o[5] = r.Y; o[6] = r.Z;
+         }
+      }
+      return 0;
+   }
+
    // ---- the host's kd-tree as an alternative accelerator input (kdtree.h)
    int uploadKd(const blingcu_kdnode *nodes, uint32_t nNodesKd, int32_t root, const uint32_t *leaf, size_t nLeaf, const float *bounds) {
       if (!uploaded) return fail(BLINGCU_ESTATE, "upload_kdtree before upload_scene");
@@ -652,10 +730,12 @@ struct Pipeline {
          out->rays_shadow = s[S_SHADOW]; out->dropped_samples = s[S_DROPPED]; out->rays_mis_culled = s[S_MISCULL]; out->rays_ext_culled = s[S_EXTCULL]; out->rays_mis_any = s[S_MISANY];
       }
       { uint64_t t6[6]; be.traversalTotals(t6); out->nodes_traversed = t6[0]; out->intersections = t6[1]; out->rays_counted = t6[2]; out->any_nodes_traversed = t6[3]; out->any_intersections = t6[4]; out->any_rays_counted = t6[5]; }
+      if (ps.stats) { unsigned long long s2[N_STATS]; be.download(s2, ps.stats, sizeof(s2)); out->photons = s2[S_PHOTONS]; out->rays_light = s2[S_RAYS_LIGHT]; out->rays_connect = s2[S_RAYS_CONNECT]; }
+      out->splats = ltSplats;
       out->kernel_launches = launches; out->bvh_nodes = nNodes; out->bvh_leaf_items = nItems; lastMs = be.timerRead(lastMs); out->last_pass_ms = lastMs; out->bvh_max_stack = (uint64_t)hs.bvh.max_stack;
       return 0;
    }
-   void resetStats() { if (ps.stats) be.zero(ps.stats, sizeof(unsigned long long) * N_STATS); launches = 0; be.resetProfile(); }
+   void resetStats() { if (ps.stats) be.zero(ps.stats, sizeof(unsigned long long) * N_STATS); launches = 0; ltSplats = 0; be.resetProfile(); }
 };
 
 }  // namespace bl

@@ -31,6 +31,8 @@ struct DScene {
    int sampler_kind, nu, nv, max_depth, sample_depth;
    int integrator;             // BLINGCU_INTEGRATOR_*
    SamplerConst smp;           // per-scene sampler constants (hd.h)
+   SamplerConst smpUniform;    // the same SPEC with no stratified dimensions: light paths draw plain uniforms (lighttrace.h)
+   float bounds_lo[3], bounds_hi[3];   // worldBounds of the scene's primitives (Light.sample' aims at their bounding sphere)
    float cieX[NB], cieY[NB], cieZ[NB], ySum;
    float illum[7][NB];         // r g b c m y w
    const blingcu_image *images;   // image textures (data pointers are device pointers)

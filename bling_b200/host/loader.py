@@ -749,6 +749,32 @@ def perspective_raster2cam(fov, sx, sy) -> np.ndarray:
     return (s2r.inverse() * proj.inverse()).m
 
 
+def with_light_tracer_camera(ir: IR.SceneIR) -> IR.SceneIR:
+    """Fills the fields sampleCam needs (Camera.hs:78-103): world-to-raster `w2r = w2s <> s2r` with `w2s = inverse c2w <> p`, and the
+    pixel area `ap = pw * ph` of mkProjective (Camera.hs:105-133). The inverse of cam2world is taken numerically here (the parser
+    has it exactly, Transform.hs:120-124); the kernels and the oracle read the same matrix, so parity does not depend on it."""
+    import copy
+    if ir.camera.kind != IR.CAM_PERSPECTIVE:
+        raise ValueError("sampleCam exists for projective cameras only (Camera.hs:101-103)")
+    out = copy.copy(ir)
+    out.camera = IR.Camera.from_buffer_copy(ir.camera)
+    sx, sy = F(ir.width), F(ir.height)
+    proj = T.perspective(ir.cam_fov, 1e-2, 1000)
+    aspect = F(sx / sy)
+    if aspect > 1: s0, s1, s2, s3 = -aspect, aspect, F(-1), F(1)
+    else: s0, s1, s2, s3 = F(-1), F(1), F(F(-1) / aspect), F(F(1) / aspect)
+    st1 = T.scale([sx, sy, 1]); st2 = T.scale([F(F(1) / F(s1 - s0)), F(F(1) / F(s2 - s3)), 1])
+    s2r = T.translate([-s0, -s3, 0]) * st2 * st1
+    c2w_m = np.array(list(ir.camera.cam2world), np.float64).reshape(4, 4)
+    c2w = T.Transform(c2w_m.astype(F), np.linalg.inv(c2w_m).astype(F))
+    w2r = c2w.inverse() * proj * s2r
+    IR.set_arr(out.camera.world2raster, w2r.m)
+    fl = F(np.tan(F(F(np.radians(F(ir.cam_fov))) / F(2))))
+    pw, ph = F(F(fl * F(s1 - s0)) / sx), F(F(fl * F(s3 - s2)) / sy)
+    out.camera.pixel_area = float(F(pw * ph))
+    return out
+
+
 def resized(ir: IR.SceneIR, width: int, height: int, nu: int = None, nv: int = None) -> IR.SceneIR:
     """Same scene at another film size / sampler (the camera captures the image size, CameraParser.hs:30-38)."""
     import copy

@@ -15,6 +15,14 @@ def film_xyz(film: np.ndarray) -> np.ndarray:
     return np.where(w != 0, film[..., 1:4] / np.where(w != 0, w, 1), 0).astype(np.float32)
 
 
+def image_xyz(film: np.ndarray, splat: np.ndarray = None, splat_weight: float = 0.0) -> np.ndarray:
+    """getPixel (Image.hs:303-315): splat_weight * splat + film / weight, per pixel, in XYZ"""
+    out = film_xyz(film)
+    if splat is not None:
+        out = (np.float32(splat_weight) * splat + out).astype(np.float32)
+    return out
+
+
 def to_png_bytes(rgb: np.ndarray) -> bytes:
     """gamma 2.2 + clamp + 8 bit (Image.hs:317-327); minimal PNG writer (no external deps)."""
     import struct, zlib

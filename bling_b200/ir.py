@@ -79,7 +79,8 @@ class EnvMap(C.Structure):
 
 class Camera(C.Structure):
     _fields_ = [("kind", i32), ("raster2cam", f32 * 16), ("cam2world", f32 * 16),
-                ("lens_radius", f32), ("focal_distance", f32), ("env_sx", f32), ("env_sy", f32)]
+                ("lens_radius", f32), ("focal_distance", f32), ("env_sx", f32), ("env_sy", f32),
+                ("world2raster", f32 * 16), ("pixel_area", f32)]
 
 
 class SceneC(C.Structure):
@@ -110,6 +111,7 @@ class Stats(C.Structure):
     _fields_ = [("samples", u64), ("rays_camera", u64), ("rays_extension", u64), ("rays_mis", u64),
                 ("rays_shadow", u64), ("dropped_samples", u64), ("nodes_traversed", u64), ("intersections", u64), ("rays_counted", u64),
                 ("kernel_launches", u64), ("bvh_nodes", u64), ("bvh_leaf_items", u64), ("last_pass_ms", C.c_double), ("bvh_max_stack", u64), ("rays_mis_culled", u64), ("rays_ext_culled", u64), ("rays_mis_any", u64),
+                ("photons", u64), ("rays_light", u64), ("rays_connect", u64), ("splats", u64),
                 ("any_nodes_traversed", u64), ("any_intersections", u64), ("any_rays_counted", u64)]
 
     def as_dict(self):
@@ -350,7 +352,8 @@ class SceneIR:
                 if k in z:
                     setattr(a, name, z[k])
             ir.env_arrays.append(a)
-        ir.camera = Camera.from_buffer_copy(z["camera"].tobytes())
+        cb = z["camera"].tobytes()   # fixtures written before the light-tracer fields existed are shorter: those fields stay zero
+        ir.camera = Camera.from_buffer_copy(cb + bytes(max(0, C.sizeof(Camera) - len(cb))))
         ir.filter_table = z["filter_table"]
         si = z["scalars_i"]; sf = z["scalars_f"]
         (ir.tri_prim_id_base, ir.width, ir.height, ir.sampler_kind, ir.nu, ir.nv, ir.max_depth,

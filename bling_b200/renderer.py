@@ -139,6 +139,34 @@ class CudaRenderer:
         self.ctx.close()
 
 
+class LightTracerRenderer:
+    """`renderer { light passPhotons n }` (Renderer/LightTracer.hs:1-51, IO/RendererParser.hs:28-30) on the CUDA core: per pass
+    `ppp` light paths splatted into the splat buffer, reported as PassDone n img (1 / (n * ppp)) where `img` carries the (empty)
+    filtered film and the splats -- here the pair (film [H][W][4], splat [H][W][3]) -- and the reporter's False stops the loop.
+    The scene's camera must carry world2raster / pixel_area (bling_b200.host.loader.with_light_tracer_camera)."""
+
+    def __init__(self, pass_photons: int, device: int = 0, seed: int = 0x5EED, context_cls=api.Context):
+        self.ppp, self.seed = int(pass_photons), seed
+        self.ctx = context_cls(device) if context_cls is api.Context else context_cls()
+
+    def pretty_print(self) -> str:
+        return f"light tracer\n{self.ppp} photons per pass"
+
+    def render(self, job: RenderJob, report: ProgressReporter, first_pass: int = 1):
+        self.ctx.upload_scene(job.scene)
+        report(Started())
+        n = first_pass
+        while True:
+            self.ctx.light_trace(n, self.seed, 0, self.ppp)
+            img = (self.ctx.read_film(), self.ctx.read_splat())
+            if not report(PassDone(n, img, 1.0 / (n * self.ppp))):
+                break
+            n += 1
+
+    def close(self):
+        self.ctx.close()
+
+
 class MultiDeviceRenderer:
     """One process, one context per device (SURVEY.md §8b `blingcu_create(devices, ndev)` in spirit): what a single Haskell
     process binding the C ABI does to use every GPU of the box. Render calls are asynchronous, so one host thread keeps all

@@ -205,6 +205,10 @@ typedef struct blingcu_camera {
    float cam2world[16];
    float lens_radius, focal_distance;
    float env_sx, env_sy;      /* Environment camera (Camera.hs:70-76)       */
+   /* light tracer only (sampleCam, Camera.hs:78-103): world-to-raster `w2r` and the pixel area `ap` of mkProjective (:105-133), as the
+    * host computed them; zero when the host does not light-trace */
+   float world2raster[16];
+   float pixel_area;
 } blingcu_camera;
 
 typedef struct blingcu_scene {
@@ -271,6 +275,7 @@ typedef struct blingcu_stats {
    uint64_t rays_ext_culled;   /* extension rays NOT traced: their vertex would have depth == maxDepth after a non-specular
                                   bounce, where neither a hit nor a miss contributes (Path.hs:43-51); rays_extension = traced */
    uint64_t rays_mis_any;      /* the part of rays_mis traced as any-hit queries (infinite lights: only hit/miss matters) */
+   uint64_t photons, rays_light, rays_connect, splats;   /* light tracer: light paths started, nearest-hit rays (light + continuation), any-hit connection rays, splats that reached the image */
    uint64_t any_nodes_traversed, any_intersections, any_rays_counted; /* the traversal triple of the ANY-hit kernel while "traversal_stats" = 1 */
 } blingcu_stats;
 
@@ -315,6 +320,20 @@ int blingcu_upload_kdtree(blingcu_ctx *, const blingcu_kdnode *nodes, uint32_t n
                           const uint32_t *leaf_prims, size_t n_leaf_prims, const float bounds[6]);
 int blingcu_trace_kdtree(blingcu_ctx *, const blingcu_ray *rays, size_t n, blingcu_hit *out,
                          uint32_t *nodes_traversed, uint32_t *intersections);
+
+/* SURVEY 8(f)4 -- the light tracer (Renderer/LightTracer.hs:1-110) on the same traversal / BSDF kernels: `n_photons` light paths
+ * (sampleLightRay, Light.sample' Light.hs:166-213), at every vertex a connection to the camera (sampleCam Camera.hs:78-103,
+ * adjoint BSDF Reflection.hs:278-332), Russian roulette 0.8 beyond depth 3, splatted UNFILTERED into the splat buffer
+ * `_imgS` = [H][W]{X, Y, Z} f32 (splatSample, Image.hs:201-221). One call = one `replicateM_ ppp oneRay` of a pass; the host
+ * reports PassDone n img (1 / (n * ppp)). Photon i of pass p draws from the counter-based stream (seed, p, first_photon + i).
+ * Needs a perspective camera with world2raster / pixel_area set. The splat sum is atomic-free and deterministic: the records of
+ * one bounce are grouped by pixel with an integer counting sort and added in photon order. blingcu_clear_film clears both buffers. */
+int blingcu_light_trace(blingcu_ctx *, uint32_t pass_index, uint64_t seed, uint64_t first_photon, uint32_t n_photons);
+int blingcu_read_splat(blingcu_ctx *, float *xyz /* H*W*3 */);
+/* debug/parity: the splats of individual photons, in (photon, depth) order: out = n_records * {photon, depth, px, py, X, Y, Z} as
+ * floats (photon / depth exact below 2^24); returns the count in *n_records, at most max_records are written */
+int blingcu_light_trace_records(blingcu_ctx *, uint32_t pass_index, uint64_t seed, uint64_t first_photon, uint32_t n_photons,
+                                float *out, size_t max_records, size_t *n_records);
 
 /* debug/parity: radiance of individual samples (no film). pixel coordinates are in sample-extent
  * space (may be negative, Image.hs:162-168); out_L = n*16 floats; out_xy = n*2 image positions. */

@@ -37,6 +37,9 @@ struct Scene {
    std::vector<float> film;  // H*W*4
    // stats
    std::atomic<uint64_t> nSamples{0}, rCam{0}, rExt{0}, rMis{0}, rShadow{0}, dropped{0};
+   // light tracer (Renderer/LightTracer.hs): the splat buffer _imgS = [H][W]{X, Y, Z} and its counters
+   std::vector<float> splat;
+   std::atomic<uint64_t> nPhotons{0}, rLight{0}, rConnect{0}, nSplats{0};
 };
 
 struct RayCounters { uint64_t cam = 0, ext = 0, mis = 0, shadow = 0; };
@@ -496,6 +499,135 @@ static Spec renderSample(const Scene &sc, const Window &ext, uint64_t seed, uint
    return pathLi(sc, c, r, rc);
 }
 
+
+// ----------------------------------------------------------------------------- Renderer/LightTracer.hs
+struct LightRay { Spec li; Ray ray; V3 nl; float pdf; };
+// boundingSphere (AABB.hs:62-66): centroid and the distance from it to pmax
+static void boundingSphere(const AABB &b, V3 &c, float &r) { c = scl(0.5f, b.lo + b.hi); r = len(b.hi - c); }
+// cosineSampleHemisphere' (Montecarlo.hs:152-161)
+static V3 cosineSampleHemisphereAround(V3 n, float u1, float u2) { return localToWorld(coordinateSystem(n), cosineSampleHemisphere(u1, u2)); }
+// Light.sample' (Light.hs:166-213): an outgoing ray of one light
+static LightRay lightSampleRay(const Scene &sc, const blingcu_light &l, float uo1, float uo2, float ud1, float ud2) {
+   LightRay empty{sConst(0), Ray{mk(0, 0, 0), mk(0, 1, 0), 0, 0}, mk(0, 1, 0), 0};
+   const AABB &bounds = sc.geo.bounds;
+   switch (l.kind) {
+   case BLINGCU_LIGHT_AREA: {   // :174-180
+      const blingcu_shape &sh = sc.geo.shapes[l.shape];
+      V3 orgL, nsL; sampleShapeAny(sh, uo1, uo2, orgL, nsL);
+      V3 org = transPoint(sh.o2w, orgL), ns = normalize(transNormalInv(sh.w2o, nsL));
+      V3 wi = cosineSampleHemisphereAround(ns, ud1, ud2);
+      float pd = kInvPi * (1 / shapeArea(sh)) * absDot(ns, wi);   // invPi * shapePdf' s org * ns `absDot` wi
+      return LightRay{fromC(l.s), Ray{org, wi, 1e-3f, kInf}, ns, pd};
+   }
+   case BLINGCU_LIGHT_DIRECTIONAL: {   // :182-189
+      V3 n = mk(l.v[0], l.v[1], l.v[2]);
+      V3 wc; float wr; boundingSphere(bounds, wc, wr);
+      Frame f = coordinateSystem(n);   // coordinateSystem'' n = (du, dv)
+      float d1, d2; concentricSampleDisk(uo1, uo2, d1, d2);
+      V3 pdisk = wc + scl(wr, scl(d1, f.s) + scl(d2, f.t));
+      V3 ns = -n;
+      return LightRay{fromC(l.s), Ray{pdisk + scl(wr, n), ns, 0, kInf}, ns, 1 / (kPi * wr * wr)};
+   }
+   case BLINGCU_LIGHT_INFINITE: {   // :191-208
+      const blingcu_envmap &e = sc.envs[l.env];
+      float u, v, pdMap; sampleContinuous2D(e, ud1, ud2, u, v, pdMap);
+      if (pdMap == 0) return empty;
+      Spec ls = envEval(sc.T, e, u, v);
+      float phi = u * 2 * kPi, theta = v * kPi;
+      V3 d = transVector(e.l2w, sphericalDirection(std::sin(theta), std::cos(theta), phi));
+      V3 wc; float wr; boundingSphere(bounds, wc, wr);
+      Frame f = coordinateSystem(-d);
+      float d1, d2; concentricSampleDisk(uo1, uo2, d1, d2);
+      V3 pDisk = wc + scl(wr, scl(d1, f.s) + scl(d2, f.t));
+      float sint = std::sin(theta);
+      float pdDir = pdMap / (2 * kPi * kPi * sint), pdArea = 1 / (kPi * wr * wr);
+      float pd = (sint == 0) ? 0 : pdDir * pdArea;
+      return LightRay{ls, Ray{pDisk + scl(wr, d), -d, 0, kInf}, d, pd};
+   }
+   default: {   // PointLight :210-213 (Q5: uniformSpherePdf = 1 / (2 pi))
+      V3 d = uniformSampleSphere(ud1, ud2);
+      return LightRay{fromC(l.s), Ray{mk(l.v[0], l.v[1], l.v[2]), d, 0, kInf}, d, 1 / (2 * kPi)};
+   }
+   }
+}
+// sampleLightRay (Scene.hs:121-136)
+static LightRay sampleLightRay(const Scene &sc, float uL, float uo1, float uo2, float ud1, float ud2) {
+   int lc = (int)sc.lights.size();
+   if (lc == 0) return LightRay{sConst(0), Ray{mk(0, 0, 0), mk(0, 1, 0), 0, 0}, mk(0, 1, 0), 0};
+   if (lc == 1) return lightSampleRay(sc, sc.lights[0], uo1, uo2, ud1, ud2);
+   int ln = std::min((int)std::floor(uL * (float)lc), lc - 1);
+   LightRay r = lightSampleRay(sc, sc.lights[ln], uo1, uo2, ud1, ud2);
+   r.pdf = r.pdf / (float)lc;
+   return r;
+}
+// sampleCam (Camera.hs:78-103), projective cameras only (the reference `error`s otherwise)
+struct CamSample { V3 pLens; float px, py, pdf; };
+static CamSample sampleCam(const Scene &sc, V3 p) {
+   const blingcu_camera &c = sc.cam;
+   V3 pRas = transPoint(c.world2raster, p);
+   V3 pLens = transPoint(c.cam2world, mk(0, 0, 0));
+   float cost = std::fabs(normalize(transPoint(c.raster2cam, pRas)).z);
+   return CamSample{pLens, pRas.x, pRas.y, c.pixel_area * (cost * cost * cost)};
+}
+struct SplatRec { uint32_t photon, depth; float px, py, X, Y, Z; };
+// splatSample (Image.hs:201-221): floor to the pixel, drop NaN / infinite spectra and positions outside the image
+static bool splatPixel(const Scene &sc, float sx, float sy, const Spec &ss, int &px, int &py) {
+   px = (int)std::floor(sx); py = (int)std::floor(sy);
+   if (px >= sc.W || py >= sc.H || px < 0 || py < 0) return false;
+   for (int i = 0; i < NB; ++i) if (std::isnan(ss.v[i]) || std::isinf(ss.v[i])) return false;
+   return true;
+}
+// oneRay + nextVertex + connectCam (LightTracer.hs:53-108). Random numbers: the counter-based stream of photon `index` of the pass
+// (oracle_math.h SPEC, plain uniforms): 1-D dims 0 = light choice, 1 + 2 d = BSDF component, 2 + 2 d = Russian roulette;
+// 2-D dims 0 = position on the light, 1 = direction, 2 + d = BSDF direction.
+static void lightPath(const Scene &sc, uint64_t seed, uint32_t pass, uint32_t index, std::vector<SplatRec> &out, uint64_t &nLight, uint64_t &nConnect) {
+   SampleCtx c; c.kp = pixelKey(seed, pass, index); c.s = 0; c.nu = 1; c.nv = 1; c.n1d = 0; c.n2d = 0; c.stratified = false;
+   float ul = rnd1D(c, 0), uo1, uo2, ud1, ud2; rnd2D(c, 0, uo1, uo2); rnd2D(c, 1, ud1, ud2);
+   LightRay lr = sampleLightRay(sc, ul, uo1, uo2, ud1, ud2);
+   if (!(lr.pdf > 0)) return;
+   V3 wo = normalize(lr.ray.d);
+   Spec li = sScale(lr.li, absDot(lr.nl, wo) / lr.pdf);
+   if (isBlack(li)) return;
+   V3 wi = -wo;
+   nLight++;
+   Hit hit = sceneIntersect(sc, lr.ray);
+   for (int depth = 0;; ++depth) {
+      if (!hit.valid) return;
+      if (isBlack(li)) return;
+      float ubc = rnd1D(c, 1 + 2 * depth), ub1, ub2; rnd2D(c, 2 + depth, ub1, ub2);
+      float pcont = (depth > 3) ? 0.8f : 1.0f;
+      Bsdf bsdf = makeBsdf(sc, hit);
+      V3 p = bsdf.p;
+      BsdfSample bs = sampleAdjBsdf(bsdf, wi, ubc, ub1, ub2);
+      Spec liNext = sScale(li * bs.f, 1 / pcont);
+      // connectCam (:62-76)
+      {
+         CamSample cs = sampleCam(sc, p);
+         V3 dCam = cs.pLens - p;
+         V3 we = normalize(dCam);
+         Spec f = evalAdjBsdf(bsdf, wi, we);
+         float dCam2 = sqLen(dCam);
+         if (!(isBlack(f) || cs.pdf == 0)) {
+            nConnect++;
+            if (!sceneOccluded(sc, Ray{p, we, hit.eps, std::sqrt(dCam2)})) {
+               Spec lrS = sScale(li * f, 1 / (cs.pdf * dCam2));
+               int px, py;
+               if (splatPixel(sc, cs.px, cs.py, lrS, px, py)) {
+                  float X, Y, Z; spectrumToXYZ(sc.T, lrS, X, Y, Z);
+                  out.push_back(SplatRec{index, (uint32_t)depth, cs.px, cs.py, X, Y, Z});
+               }
+            }
+         }
+      }
+      if (isBlack(bs.f) || bs.pdf == 0) return;
+      float x = rnd1D(c, 2 + 2 * depth);
+      if (x > pcont) return;
+      nLight++;
+      hit = sceneIntersect(sc, Ray{p, bs.wi, hit.eps, kInf});
+      wi = -bs.wi;
+      li = liNext;
+   }
+}
 }  // namespace orc
 
 // =============================================================================================
@@ -565,7 +697,9 @@ int oracle_create(const blingcu_scene *ir, int build_kdtree, oracle_ctx **out) {
    sc.samplerKind = ir->sampler_kind; sc.nu = ir->nu; sc.nv = ir->nv;
    sc.maxDepth = ir->max_depth; sc.sampleDepth = ir->sample_depth; sc.integrator = ir->integrator_kind;
    sc.film.assign((size_t)sc.W * sc.H * 4, 0.0f);
+   sc.splat.assign((size_t)sc.W * sc.H * 3, 0.0f);
    sc.useKd = build_kdtree != 0;
+   if (!sc.useKd) { sc.geo.bounds = emptyBox(); for (const Prim &p : sc.geo.prims) sc.geo.bounds = extendB(sc.geo.bounds, p.wb); }   // worldBounds of the scene
    if (sc.useKd) sc.geo.buildKd();
    *out = c;
    return 0;
@@ -721,18 +855,40 @@ int oracle_render_slice(oracle_ctx *c, uint32_t pass, uint64_t seed, uint32_t s_
 }
 
 int oracle_read_film(oracle_ctx *c, float *wxyz) { std::memcpy(wxyz, c->sc.film.data(), c->sc.film.size() * sizeof(float)); return 0; }
-int oracle_clear_film(oracle_ctx *c) { std::fill(c->sc.film.begin(), c->sc.film.end(), 0.0f); return 0; }
+int oracle_clear_film(oracle_ctx *c) { std::fill(c->sc.film.begin(), c->sc.film.end(), 0.0f); std::fill(c->sc.splat.begin(), c->sc.splat.end(), 0.0f); return 0; }
 int oracle_get_stats(oracle_ctx *c, blingcu_stats *s) {
    std::memset(s, 0, sizeof(*s));
    s->samples = c->sc.nSamples; s->rays_camera = c->sc.rCam; s->rays_extension = c->sc.rExt;
    s->rays_mis = c->sc.rMis; s->rays_shadow = c->sc.rShadow; s->dropped_samples = c->sc.dropped;
    s->bvh_nodes = c->sc.geo.nodes.size(); s->bvh_leaf_items = c->sc.geo.leafPrims.size();
+   s->photons = c->sc.nPhotons; s->rays_light = c->sc.rLight; s->rays_connect = c->sc.rConnect; s->splats = c->sc.nSplats;
    return 0;
 }
 int oracle_reset_stats(oracle_ctx *c) {
    c->sc.nSamples = 0; c->sc.rCam = 0; c->sc.rExt = 0; c->sc.rMis = 0; c->sc.rShadow = 0; c->sc.dropped = 0;
+   c->sc.nPhotons = 0; c->sc.rLight = 0; c->sc.rConnect = 0; c->sc.nSplats = 0;
    return 0;
 }
+
+// light tracer: photons [first, first + n) of pass `pass`; splats are added in photon order (deterministic); optional records
+int oracle_light_trace(oracle_ctx *c, uint32_t pass, uint64_t seed, uint64_t first, uint32_t n, float *records, size_t maxRecords, size_t *nRecords) {
+   Scene &sc = c->sc;
+   if (sc.cam.kind != BLINGCU_CAM_PERSPECTIVE || sc.cam.pixel_area == 0) return BLINGCU_EINVAL;
+   std::vector<SplatRec> recs;
+   uint64_t nl = 0, nc = 0;
+   for (uint32_t i = 0; i < n; ++i) lightPath(sc, seed, pass, (uint32_t)(first + i), recs, nl, nc);
+   size_t k = 0;
+   for (const SplatRec &r : recs) {
+      int px = (int)std::floor(r.px), py = (int)std::floor(r.py);
+      float *d = &sc.splat[3 * ((size_t)py * sc.W + px)];
+      d[0] = d[0] + r.X; d[1] = d[1] + r.Y; d[2] = d[2] + r.Z;
+      if (records && k < maxRecords) { float *o = records + 7 * k; o[0] = (float)r.photon; o[1] = (float)r.depth; o[2] = r.px; o[3] = r.py; o[4] = r.X; o[5] = r.Y; o[6] = r.Z; k++; }
+   }
+   if (nRecords) *nRecords = recs.size();
+   sc.nPhotons += n; sc.rLight += nl; sc.rConnect += nc; sc.nSplats += recs.size();
+   return 0;
+}
+int oracle_read_splat(oracle_ctx *c, float *xyz) { std::memcpy(xyz, c->sc.splat.data(), c->sc.splat.size() * sizeof(float)); return 0; }
 
 int oracle_eval_texture(oracle_ctx *c, int32_t tex, const float *p, const float *uv, size_t n, float *out) {
    if (tex < 0 || (size_t)tex >= c->sc.textures.size()) return 1;

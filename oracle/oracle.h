@@ -25,6 +25,10 @@ int oracle_read_film(oracle_ctx *, float *wxyz);
 int oracle_clear_film(oracle_ctx *);
 int oracle_get_stats(oracle_ctx *, blingcu_stats *);
 int oracle_reset_stats(oracle_ctx *);
+/* Renderer/LightTracer.hs restated: photons [first, first + n) of a pass into the splat buffer [H][W]{X,Y,Z};
+ * records = optional n*7 floats {photon, depth, px, py, X, Y, Z} in (photon, depth) order */
+int oracle_light_trace(oracle_ctx *, uint32_t pass, uint64_t seed, uint64_t first, uint32_t n, float *records, size_t max_records, size_t *n_records);
+int oracle_read_splat(oracle_ctx *, float *xyz);
 int oracle_eval_texture(oracle_ctx *, int32_t texture, const float *p, const float *uv, size_t n, float *out);
 /* single functions of oracle_shade.h at explicit arguments, for tests/test_third_statement.py (a pure-Python statement of the same
  * Haskell text held against this one). what: 1 frDielectric(etai, etat, cosi) -> 16; 2 frConductor(eta16, k16, cosi) -> 16;

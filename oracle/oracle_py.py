@@ -32,6 +32,8 @@ def lib():
         L.oracle_trace_nearest.argtypes = [P, P, C.c_size_t, P, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.oracle_trace_occluded.argtypes = [P, P, C.c_size_t, P, C.c_int]
         L.oracle_debug_eval.argtypes = [C.c_int, P, P]
+        L.oracle_light_trace.argtypes = [P, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint32, P, C.c_size_t, C.POINTER(C.c_size_t)]
+        L.oracle_read_splat.argtypes = [P, P]
         L.oracle_export_kdtree.argtypes = [P, P, C.POINTER(C.c_uint32), P, C.POINTER(C.c_size_t), C.POINTER(C.c_int32), P]
         L.oracle_trace_kd_stats.argtypes = [P, P, C.c_size_t, P, P, P]
         L.oracle_sample_extent.argtypes = [P] + [C.POINTER(C.c_int32)] * 4
@@ -86,6 +88,19 @@ class Oracle:
         _chk(lib().oracle_trace_nearest(self._h, rays.ctypes.data, len(rays), out.ctypes.data, 1 if mode == "kd" else 0,
                                         C.byref(nt), C.byref(ni)), "trace_nearest")
         self.last_traversal = (nt.value, ni.value)
+        return out
+
+    def light_trace(self, pass_index, seed, first_photon, n_photons, records=False):
+        """Renderer/LightTracer.hs restated: photons [first, first + n) into the splat buffer; records=True also returns the rows
+        {photon, depth, px, py, X, Y, Z} in (photon, depth) order"""
+        cap = 64 * n_photons + 16 if records else 0
+        out = np.zeros((cap, 7), np.float32); n = C.c_size_t()
+        _chk(lib().oracle_light_trace(self._h, pass_index, seed, first_photon, n_photons, out.ctypes.data if records else None, cap, C.byref(n)), "light_trace")
+        return out[:min(cap, n.value)] if records else None
+
+    def read_splat(self):
+        out = np.zeros((self.scene.height, self.scene.width, 3), np.float32)
+        _chk(lib().oracle_read_splat(self._h, out.ctypes.data), "read_splat")
         return out
 
     def kdtree_flat(self):

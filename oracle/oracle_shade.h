@@ -456,6 +456,116 @@ static inline float bsdfPdf(const Bsdf &bsdf, V3 woW, V3 wiW) {
    return s / (float)bsdf.n;
 }
 
+// ----------------------------------------------------------------------------- adjoint (light-transport) variants: SURVEY 8(f)4
+// bxdfSample b adj=True wo u: what the light tracer draws (Renderer/LightTracer.hs:84 sampleAdjBsdf). Differences from adj = False,
+// BxDF by BxDF: Lambertian / OrenNayar scale by |cos wo / cos wi| (Diffuse.hs:20-22,44-49); specTrans takes the Fresnel term at
+// the INCIDENT cosine and scales by |cos wo / cost| instead of eta^2 (Specular.hs:52-57); the microfacet weight divides by
+// |cos wo| instead of |cos wi| (Microfacet.hs:52-54); FresnelBlend evaluates `e wi wo` (:92); specRefl is the same (Specular.hs:19).
+static inline void bxdfSampleAdj(const BxDF &b, V3 wo, float u1, float u2, Spec &f, V3 &wi, float &pdf) {
+   switch (b.kind) {
+   case K_LAMBERT: case K_ORENNAYAR: {
+      wi = toSameHemisphere(wo, cosineSampleHemisphere(u1, u2));
+      if (sameHemisphere(wo, wi)) {
+         Spec r = (b.kind == K_LAMBERT) ? b.r : orenNayar(b, wo, wi);
+         f = sScale(r, std::fabs(cosTheta(wo) / cosTheta(wi))); pdf = cosPdf(wo, wi);
+      } else { f = sConst(0); if (b.kind == K_LAMBERT) wi = wo; pdf = 0; }
+      if (b.flip) wi = otherHemisphere(wi);
+      return;
+   }
+   case K_SPECTRANS: {
+      bool entering = cosTheta(wo) > 0;
+      float ei = entering ? b.etai : b.etat, et = entering ? b.etat : b.etai;
+      float sini2 = sinTheta2(wo);
+      float eta = ei / et, eta2 = eta * eta, sint2 = eta2 * sini2;
+      if (sint2 >= 1) { f = sConst(0); wi = wo; pdf = 0; return; }
+      float c = std::sqrt(hmax(0, 1 - sint2));
+      float cost = entering ? -c : c;
+      wi = mk(eta * (-wo.x), eta * (-wo.y), cost);
+      Spec fr = frDielectric(ei, et, cosTheta(wo));
+      Spec fp = (sConst(1) - fr) * b.r;
+      f = sScale(fp, std::fabs(cosTheta(wo) / cost));
+      pdf = 1;
+      return;
+   }
+   case K_FRESNELBLEND: {
+      float pdfp; V3 wh;
+      if (u1 < 0.5f) {
+         wi = toSameHemisphere(wo, cosineSampleHemisphere(u1 * 2, u2));
+         wh = halfUp(wi, wo);
+         pdfp = anisoPdf(b.ex, b.ey, wh);
+      } else {
+         anisoSample(b.ex, b.ey, 2 * (u1 - 0.5f), u2, wh, pdfp);
+         wi = scl(2, scl(dot(wo, wh), wh)) - wo;
+      }
+      if (pdfp == 0) { f = sConst(0); pdf = 0; return; }
+      pdf = 0.5f * (absCosTheta(wi) * kInvPi + pdfp / (4 * absDot(wo, wh)));
+      f = sScale(fresnelBlendEval(b, wi, wo), 1 / pdf);
+      return;
+   }
+   case K_MICROFACET: {
+      float cost = std::pow(u1, 1 / (b.e + 1));
+      float sint = std::sqrt(hmax(0, 1 - cost * cost));
+      float phi = u2 * 2 * kPi;
+      V3 whp = sphericalDirection(sint, cost, phi);
+      float ff = std::pow(cost, b.e) * kInvTwoPi;
+      float d = (b.e + 2) * ff, dpdf = (b.e + 1) * ff;
+      V3 wh = (cosTheta(whp) < 0) ? -whp : whp;
+      float costH = dot(wo, wh);
+      wi = scl(2 * costH, wh) - wo;
+      if (!sameHemisphere(wo, wi)) { f = sConst(0); wi = wo; pdf = 0; return; }
+      float fact = d * std::fabs(costH) / dpdf * mfG(wo, wi, wh);
+      Spec fp = b.r * fresnel(b, costH);
+      f = sScale(fp, fact / absCosTheta(wo));
+      pdf = dpdf / (4 * std::fabs(costH));
+      return;
+   }
+   default: bxdfSample(b, wo, u1, u2, f, wi, pdf); return;   // specRefl
+   }
+}
+// sampleBsdf'' True bxdfAll (Reflection.hs:278-316): the other components are evaluated UNflipped (`eval b = bxdfEval b`, :310)
+// and every weight is scaled by |sideTest| (`fAdj`, :315-316)
+static inline BsdfSample sampleAdjBsdf(const Bsdf &bsdf, V3 woW, float uComp, float uDir1, float uDir2) {
+   BsdfSample empty{BX_REFLECTION | BX_DIFFUSE, 0, sConst(0), mk(0, 1, 0)};
+   int cntm = bsdf.n;
+   if (cntm == 0) return empty;
+   V3 wo = worldToLocal(bsdf.cs, woW);
+   float cntf = (float)cntm, invCnt = 1 / cntf;
+   int sNum = std::max(0, std::min(cntm - 1, (int)std::floor(uComp * cntf)));
+   const BxDF &bx = bsdf.bx[sNum];
+   Spec fSample = sConst(0); V3 wi = mk(0, 1, 0); float pdfp = 0;
+   bxdfSampleAdj(bx, wo, uDir1, uDir2, fSample, wi, pdfp);
+   V3 wiW = localToWorld(bsdf.cs, wi);
+   float sideTest = dot(wiW, bsdf.ng) / dot(woW, bsdf.ng);
+   if (pdfp == 0 || sideTest == 0) return empty;
+   bool wantTrans = sideTest < 0;
+   if (!(wantTrans ? isTrans(bx) : isRefl(bx))) return empty;
+   float as = std::fabs(sideTest);
+   if (isSpec(bx)) return BsdfSample{bx.type, pdfp * invCnt, sScale(sScale(fSample, as), cntf), wiW};
+   if (cntm == 1) return BsdfSample{bx.type, pdfp, sScale(fSample, as), wiW};
+   float pdfSum = 0; Spec fOthers = sConst(0);
+   for (int i = 0; i < cntm; ++i) {
+      if (i == sNum) continue;
+      pdfSum = pdfSum + bxdfPdf(bsdf.bx[i], wo, wi);
+      if (wantTrans ? isTrans(bsdf.bx[i]) : isRefl(bsdf.bx[i])) fOthers = fOthers + bxdfEval(bsdf.bx[i], wo, wi);
+   }
+   float pdf = (pdfp + pdfSum) * invCnt;
+   Spec fSum = sScale(sScale(fSample, pdfp) + fOthers, 1 / pdf);
+   return BsdfSample{bx.type, pdf, sScale(fSum, as), wiW};
+}
+// evalBsdf True (Reflection.hs:318-332)
+static inline Spec evalAdjBsdf(const Bsdf &bsdf, V3 woW, V3 wiW) {
+   float cosWo = dot(woW, bsdf.ng);
+   float sideTest = dot(wiW, bsdf.ng) / cosWo;
+   if (sideTest == 0) return sConst(0);
+   if (std::fabs(cosWo) < 1e-5f) return sConst(0);
+   bool wantTrans = sideTest < 0;
+   V3 wo = worldToLocal(bsdf.cs, woW), wi = worldToLocal(bsdf.cs, wiW);
+   Spec f = sConst(0);
+   for (int i = 0; i < bsdf.n; ++i)
+      if (wantTrans ? isTrans(bsdf.bx[i]) : isRefl(bsdf.bx[i])) f = f + bxdfEval(bsdf.bx[i], wo, wi);
+   return sScale(f, std::fabs(sideTest));
+}
+
 // ----------------------------------------------------------------------------- Spectrum.hs conversions
 struct SpectralTables { Spec cieX, cieY, cieZ; float ySum; Spec illum[7]; };  // illum: r g b c m y w
 
