@@ -62,8 +62,30 @@ HD Spec loadSpec4(const F4 *base, uint32_t cap, uint32_t i) {
 HD void storeSpec4(F4 *base, uint32_t cap, uint32_t i, const Spec &s) {
    BL_UNROLL for (int q = 0; q < 4; ++q) { F4 v; v.x = s.v[4 * q]; v.y = s.v[4 * q + 1]; v.z = s.v[4 * q + 2]; v.w = s.v[4 * q + 3]; base[spec4At(cap, i, q)] = v; }
 }
-HD void storeRay(F4 *o, F4 *d, uint32_t i, const Ray &r) { F4 a, b; a.x = r.o.x; a.y = r.o.y; a.z = r.o.z; a.w = r.tmin; b.x = r.d.x; b.y = r.d.y; b.z = r.d.z; b.w = r.tmax; o[i] = a; d[i] = b; }
-HD Ray loadRay(const F4 *o, const F4 *d, uint32_t i) { F4 a = o[i], b = d[i]; Ray r; r.o = mk3(a.x, a.y, a.z); r.tmin = a.w; r.d = mk3(b.x, b.y, b.z); r.tmax = b.w; return r; }
+// A ray is ONE 32-byte record {(o, tmin), (d, tmax)} -- the C ABI's blingcu_ray as it is -- so that a scattered access touches one
+// full 32-byte sector (round 1: separate `O` and `D` arrays = two half-used sectors per ray, in the traversal kernels and four
+// times over in every shade kernel, which sit on the sector rate of exactly such accesses). Every (o, d) pointer pair in the
+// kernels points INTO one interleaved array: d == o + 1, record i at o[2 i] / d[2 i].
+HD size_t rayAt2(uint32_t i) { return 2 * (size_t)i; }
+HD void storeRay(F4 *o, F4 *d, uint32_t i, const Ray &r) {
+   F4 a, b; a.x = r.o.x; a.y = r.o.y; a.z = r.o.z; a.w = r.tmin; b.x = r.d.x; b.y = r.d.y; b.z = r.d.z; b.w = r.tmax;
+#if defined(__CUDA_ARCH__)
+   (void)d;   // one 32-byte store (STG.E.256 on sm_100)
+   asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(o + rayAt2(i)), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w) : "memory");
+#else
+   o[rayAt2(i)] = a; d[rayAt2(i)] = b;
+#endif
+}
+HD Ray loadRay(const F4 *o, const F4 *d, uint32_t i) {
+   F4 a, b;
+#if defined(__CUDA_ARCH__)
+   (void)d;   // one 32-byte load (LDG.E.256)
+   asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(o + rayAt2(i)));
+#else
+   a = o[rayAt2(i)]; b = d[rayAt2(i)];
+#endif
+   Ray r; r.o = mk3(a.x, a.y, a.z); r.tmin = a.w; r.d = mk3(b.x, b.y, b.z); r.tmax = b.w; return r;
+}
 
 // L[slot] += s with atomics (direct-lighting integrator: several branch slots feed one camera sample)
 #if defined(__CUDA_ARCH__)
@@ -156,7 +178,7 @@ struct ShadeMissBody {   // Path.hs:43-47
    HD void operator()(uint32_t i) const {
       const DScene &S = *sc;
       if (!((ps.meta[i] >> 8) & 1u)) return;   // non-specular bounce: nothing
-      F4 d = ps.rayD[i];
+      F4 d = ps.rayD[rayAt2(i)];
       Spec sum = sConst(0);
       for (int l = 0; l < S.n_lights; ++l) sum = sum + lightLe(S, S.lights[l], mk3(d.x, d.y, d.z));
       Spec L = loadSpec4(ps.L, ps.cap, i), T = loadSpec4(ps.T, ps.cap, i);
@@ -543,7 +565,6 @@ struct FilmBody {
 };
 
 // explicit ray batches: ABI layout <-> kernel layout
-struct SplitRaysBody { const F4 *rays; F4 *o, *d; HD void operator()(uint32_t i) const { o[i] = rays[2 * (size_t)i]; d[i] = rays[2 * (size_t)i + 1]; } };
 struct HitToAbiBody {   // kernel hit (t, b1, b2, ref) -> ABI hit {t, prim id, b1, b2}
    const DScene *sc; F4 *h;
    HD void operator()(uint32_t i) const {

@@ -142,11 +142,14 @@ struct CudaBackend {
       cudaFuncSetAttribute(kTracePersistent<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceSmemBytes(BL_STACK));
       cudaFuncSetAttribute(kTracePersistent<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)traceSmemBytes(BL_STACK));
       const int wq = (int)traceWarpQSmemBytes(BL_STACK);
-      cudaFuncSetAttribute(kTraceWarpQ<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
-      cudaFuncSetAttribute(kTraceWarpQ<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
-      cudaFuncSetAttribute(kTraceWarpQ<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
-      cudaFuncSetAttribute(kTraceWarpQ<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
-      cudaFuncSetAttribute(kTraceWarpQ<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
+      cudaFuncSetAttribute(kTraceWarpQ<false, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
+      cudaFuncSetAttribute(kTraceWarpQ<false, true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
+      cudaFuncSetAttribute(kTraceWarpQ<true, true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
+      cudaFuncSetAttribute(kTraceWarpQ<true, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
+      cudaFuncSetAttribute(kTraceWarpQ<true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
+      cudaFuncSetAttribute(kTraceWarpQ<true, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
+      cudaFuncSetAttribute(kTraceWarpQ<true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
+      cudaFuncSetAttribute(kTraceWarpQ<true, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, wq);
       return 0;
    }
    // run on a caller-owned stream (e.g. torch's current stream, so an NCCL all-reduce of the film orders after the
@@ -263,14 +266,14 @@ struct CudaBackend {
    // page-locked (blingcu_host_alloc, cudaHostRegister, torch pin_memory) are used as they are; pageable ones are staged through
    // the context's own pinned ring by a few helper threads (one memcpy thread moves ~10 GB/s, the link 50).
    enum { TB_SLOTS = 3 };
-   struct TraceSlot { void *hIn = nullptr, *hOut = nullptr; F4 *dR = nullptr, *dO = nullptr, *dD = nullptr, *dH = nullptr; uint8_t *dC = nullptr; cudaEvent_t in = nullptr, done = nullptr, out = nullptr; };
+   struct TraceSlot { void *hIn = nullptr, *hOut = nullptr; F4 *dR = nullptr, *dH = nullptr; uint8_t *dC = nullptr; cudaEvent_t in = nullptr, done = nullptr, out = nullptr; };
    TraceSlot tslot[TB_SLOTS]; size_t tchunkCap = 0; cudaStream_t sIn = nullptr, sOut = nullptr;
    size_t traceChunk = 1u << 20;   // rays per chunk (option "trace_chunk")
    int copyThreads = 4;            // helper threads for pageable host buffers (option "copy_threads")
    void freeTracePipe() {
       for (TraceSlot &t : tslot) {
          if (t.hIn) cudaFreeHost(t.hIn); if (t.hOut) cudaFreeHost(t.hOut);
-         cudaFree(t.dR); cudaFree(t.dO); cudaFree(t.dD); cudaFree(t.dH); cudaFree(t.dC);
+         cudaFree(t.dR); cudaFree(t.dH); cudaFree(t.dC);
          if (t.in) cudaEventDestroy(t.in); if (t.done) cudaEventDestroy(t.done); if (t.out) cudaEventDestroy(t.out);
          t = TraceSlot{};
       }
@@ -282,7 +285,7 @@ struct CudaBackend {
       freeTracePipe();
       for (TraceSlot &t : tslot) {
          CU(cudaMallocHost(&t.hIn, chunk * sizeof(blingcu_ray))); CU(cudaMallocHost(&t.hOut, chunk * sizeof(blingcu_hit)));
-         CU(cudaMalloc(&t.dR, chunk * 2 * sizeof(F4))); CU(cudaMalloc(&t.dO, chunk * sizeof(F4))); CU(cudaMalloc(&t.dD, chunk * sizeof(F4)));
+         CU(cudaMalloc(&t.dR, chunk * 2 * sizeof(F4)));
          CU(cudaMalloc(&t.dH, chunk * sizeof(F4))); CU(cudaMalloc(&t.dC, chunk));
          CU(cudaEventCreateWithFlags(&t.in, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&t.done, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&t.out, cudaEventDisableTiming));
       }
@@ -323,13 +326,12 @@ struct CudaBackend {
          CU(cudaMemcpyAsync(t.dR, src, m * sizeof(blingcu_ray), cudaMemcpyHostToDevice, sIn));
          CU(cudaEventRecord(t.in, sIn));
          CU(cudaStreamWaitEvent(stream, t.in, 0));
-         tag(BLINGCU_KC_OTHER); run(SplitRaysBody{t.dR, t.dO, t.dD}, (uint32_t)m);
          void *dsrc;
          if (outHit) {
-            tag(BLINGCU_KC_TRACE_NEAREST); traceNearest(nullptr, nullptr, (uint32_t)m, dscene, t.dO, t.dD, t.dH);
+            tag(BLINGCU_KC_TRACE_NEAREST); traceNearest(nullptr, nullptr, (uint32_t)m, dscene, t.dR, t.dR + 1, t.dH);
             tag(BLINGCU_KC_OTHER); run(HitToAbiBody{dscene, t.dH}, (uint32_t)m);
             dsrc = t.dH;
-         } else { tag(BLINGCU_KC_TRACE_ANY); traceAny(nullptr, nullptr, (uint32_t)m, dscene, t.dO, t.dD, t.dC); dsrc = t.dC; }
+         } else { tag(BLINGCU_KC_TRACE_ANY); traceAny(nullptr, nullptr, (uint32_t)m, dscene, t.dR, t.dR + 1, t.dC); dsrc = t.dC; }
          CU(cudaEventRecord(t.done, stream));
          CU(cudaStreamWaitEvent(sOut, t.done, 0));
          void *dst = pinOut ? (void *)((char *)(outHit ? (void *)outHit : (void *)outOccl) + b * outStride) : t.hOut;

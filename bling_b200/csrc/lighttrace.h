@@ -193,7 +193,7 @@ struct LtGenBody {
       if (isBlack(li)) return;
       storeRay(ps.rayO, ps.rayD, i, lr.ray);
       storeSpec4(ps.T, ps.cap, i, li);
-      F4 w; w.x = -wo.x; w.y = -wo.y; w.z = -wo.z; w.w = 0; ps.miD[i] = w;   // wi of the first vertex
+      F4 w; w.x = -wo.x; w.y = -wo.y; w.z = -wo.z; w.w = 0; ps.miD[rayAt2(i)] = w;   // wi of the first vertex
       ps.meta[i] = 0u; ps.kp[i] = kp; ps.sidx[i] = i;
       qPush(ps.qA, ps.counters + C_ACTIVE, i);
    }
@@ -217,7 +217,7 @@ struct LtVertexBody {
       surfaceAt(S, ray, hv.x, hv.y, hv.z, f2i(hv.w), sh, dgs);
       Spec texScratch[4];
       Bsdf bsdf; makeBsdfGeneral(S, sh, dgs, bsdf, texScratch);
-      const F4 wv = ps.miD[i]; const V3 wi = mk3(wv.x, wv.y, wv.z);
+      const F4 wv = ps.miD[rayAt2(i)]; const V3 wi = mk3(wv.x, wv.y, wv.z);
       const V3 p = bsdf.p; const float eps = sh.eps;
       BsdfSample bs; sampleAdjBsdfGeneral(bsdf, wi, ubc, ub1, ub2, bs);
       {   // connectCam
@@ -238,7 +238,7 @@ struct LtVertexBody {
       Ray nr; nr.o = p; nr.d = bs.wi; nr.tmin = eps; nr.tmax = BL_INF;
       storeRay(ps.rayO, ps.rayD, i, nr);
       storeSpec4(ps.T, ps.cap, i, sScale(li * bs.f, 1 / pcont));
-      F4 w; w.x = -bs.wi.x; w.y = -bs.wi.y; w.z = -bs.wi.z; w.w = 0; ps.miD[i] = w;
+      F4 w; w.x = -bs.wi.x; w.y = -bs.wi.y; w.z = -bs.wi.z; w.w = 0; ps.miD[rayAt2(i)] = w;
       ps.meta[i] = (uint32_t)(depth + 1);
       qPush(qNext, ps.counters + C_NEXT, i);
    }

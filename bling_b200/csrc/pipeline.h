@@ -253,10 +253,10 @@ struct Pipeline {
       freeState();
       ps.cap = cap; qSlotsAlloc = nSlots; rootAlloc = rootNeed;
       size_t c = cap;
-      ps.rayO = st<F4>(c); ps.rayD = st<F4>(c); ps.hit = st<F4>(c);
+      ps.rayO = st<F4>(2 * c); ps.rayD = ps.rayO + 1; ps.hit = st<F4>(c);   // rays: one interleaved 32-byte record per slot (bodies.h::loadRay)
       ps.T = st<F4>(4 * c); ps.L = st<F4>(4 * c);
-      ps.shO = st<F4>(c); ps.shD = st<F4>(c); ps.PS = st<F4>(4 * c); ps.occl = st<uint8_t>(c); ps.occlM = st<uint8_t>(c);
-      ps.miO = st<F4>(c); ps.miD = st<F4>(c); ps.mihit = st<F4>(c); ps.PM = st<F4>(4 * c); ps.miInfo = st<F2>(c);
+      ps.shO = st<F4>(2 * c); ps.shD = ps.shO + 1; ps.PS = st<F4>(4 * c); ps.occl = st<uint8_t>(c); ps.occlM = st<uint8_t>(c);
+      ps.miO = st<F4>(2 * c); ps.miD = ps.miO + 1; ps.mihit = st<F4>(c); ps.PM = st<F4>(4 * c); ps.miInfo = st<F2>(c);
       ps.meta = st<uint32_t>(c); ps.kp = st<uint64_t>(c); ps.sidx = st<uint32_t>(c); ps.spos = st<F2>(c); ps.xyz = st<F4>(c);
       ps.qA = st<uint32_t>(c); ps.qB = st<uint32_t>(c); ps.qShadow = st<uint32_t>(c); ps.qMis = st<uint32_t>(c); ps.qMisAny = st<uint32_t>(c);
       ps.qMat = st<uint32_t>((size_t)nSlots * c);
@@ -567,13 +567,12 @@ struct Pipeline {
       if (!nodes && be.traceHostBatch(rays, n, outHit, outOccl, dscene)) return 0;
       if (n > tbCap) {
          freeTraceScratch();
-         tb[0] = be.alloc(sizeof(F4) * 2 * n); tb[1] = be.alloc(sizeof(F4) * n); tb[2] = be.alloc(sizeof(F4) * n);
+         tb[0] = be.alloc(sizeof(F4) * 2 * n); tb[1] = nullptr; tb[2] = nullptr;
          tb[3] = be.alloc(sizeof(F4) * n); tb[4] = be.alloc(4 * n); tb[5] = be.alloc(4 * n);
          tbCap = n;
       }
-      F4 *dR = (F4 *)tb[0], *dO = (F4 *)tb[1], *dD = (F4 *)tb[2], *dH = (F4 *)tb[3];
+      F4 *dR = (F4 *)tb[0], *dO = dR, *dD = dR + 1, *dH = (F4 *)tb[3];   // the ABI ray IS the kernels' ray record
       be.upload(dR, rays, sizeof(F4) * 2 * n);
-      be.tag(BLINGCU_KC_OTHER); be.run(SplitRaysBody{dR, dO, dD}, (uint32_t)n);
       if (outHit) {
          uint32_t *dN = (uint32_t *)tb[4], *dP = (uint32_t *)tb[5];
          if (nodes) be.traceStats((uint32_t)n, dscene, dO, dD, dH, dN, dP);
@@ -700,14 +699,13 @@ struct Pipeline {
       if (n > 0x7fffffffu) return fail(BLINGCU_EINVAL, "too many rays");
       if (n > tbCap) {
          freeTraceScratch();
-         tb[0] = be.alloc(sizeof(F4) * 2 * n); tb[1] = be.alloc(sizeof(F4) * n); tb[2] = be.alloc(sizeof(F4) * n);
+         tb[0] = be.alloc(sizeof(F4) * 2 * n); tb[1] = nullptr; tb[2] = nullptr;
          tb[3] = be.alloc(sizeof(F4) * n); tb[4] = be.alloc(4 * n); tb[5] = be.alloc(4 * n);
          tbCap = n;
       }
-      F4 *dR = (F4 *)tb[0], *dO = (F4 *)tb[1], *dD = (F4 *)tb[2], *dH = (F4 *)tb[3]; uint32_t *dN = (uint32_t *)tb[4], *dP = (uint32_t *)tb[5];
+      F4 *dR = (F4 *)tb[0], *dO = dR, *dD = dR + 1, *dH = (F4 *)tb[3]; uint32_t *dN = (uint32_t *)tb[4], *dP = (uint32_t *)tb[5];
       be.upload(dR, rays, sizeof(F4) * 2 * n);
-      be.tag(BLINGCU_KC_OTHER); be.run(SplitRaysBody{dR, dO, dD}, (uint32_t)n);
-      be.run(TraceKdBody{dscene, kd, dO, dD, dH, dN, dP}, (uint32_t)n);
+      be.tag(BLINGCU_KC_OTHER); be.run(TraceKdBody{dscene, kd, dO, dD, dH, dN, dP}, (uint32_t)n);
       be.run(HitToAbiBody{dscene, dH}, (uint32_t)n);
       be.download(outHit, dH, sizeof(F4) * n); be.download(nodes, dN, 4 * n); be.download(prims, dP, 4 * n);
       return 0;

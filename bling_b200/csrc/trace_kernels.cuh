@@ -250,9 +250,10 @@ static inline void launchTraceNearest(TraceConfig &cfg, cudaStream_t st, const u
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
    if (cfg.variant >= 2) {
+      TraceConfig cn = cfg; cn.blocksPerSm = cfg.blocksPerSm - (TR_MINBLOCKS - TQ_NEAR_BLOCKS);
       // option "traversal_stats": the SAME kernel with counters (node visits / primitive tests of the product's own schedule)
-      if (cfg.countStats && cfg.travCounters) kTraceWarpQ<false, true, true><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter, nullptr, nullptr, 0u, cfg.bvh, cfg.travCounters);
-      else kTraceWarpQ<false, true, false><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter, nullptr, nullptr, 0u, cfg.bvh, nullptr);
+      if (cfg.countStats && cfg.travCounters) kTraceWarpQ<false, true, true, false><<<traceGrid(cn, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter, nullptr, nullptr, 0u, cfg.bvh, cfg.travCounters);
+      else kTraceWarpQ<false, true, false, false><<<traceGrid(cn, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter, nullptr, nullptr, 0u, cfg.bvh, nullptr);
       return;
    }
    kTracePersistent<false><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, hit, nullptr, cfg.workCounter, nullptr, nullptr, 0u);
@@ -264,10 +265,18 @@ static inline void launchTraceAny(TraceConfig &cfg, cudaStream_t st, const uint3
    if (!cfg.workCounter) cudaMalloc(&cfg.workCounter, sizeof(uint32_t));
    cudaMemsetAsync(cfg.workCounter, 0, sizeof(uint32_t), st);
    TraceConfig c9 = cfg; c9.blocksPerSm = cfg.blocksPerSm + 1;
-   if (cfg.variant == 2) { kTraceWarpQ<true, true, false><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap, cfg.bvh, nullptr); return; }
+   if (cfg.variant == 2) {
+      if (fuseL) kTraceWarpQ<true, true, false, true><<<traceGrid(cfg, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap, cfg.bvh, nullptr);
+      else kTraceWarpQ<true, true, false, false><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, nullptr, nullptr, 0u, cfg.bvh, nullptr);
+      return;
+   }
    if (cfg.variant >= 3) {
-      if (cfg.countStats && cfg.travCounters) kTraceWarpQ<true, false, true><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap, cfg.bvh, cfg.travCounters + 3);
-      else kTraceWarpQ<true, false, false><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceWarpQSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap, cfg.bvh, nullptr);
+      const uint32_t g = traceGrid(fuseL ? cfg : c9, n, TR_THREADS); const size_t sm = traceWarpQSmemBytes(cfg.maxStack);   // the fused instantiation takes 64 registers: 8 CTAs per SM
+      if (cfg.countStats && cfg.travCounters) {
+         if (fuseL) kTraceWarpQ<true, false, true, true><<<g, TR_THREADS, sm, st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap, cfg.bvh, cfg.travCounters + 3);
+         else kTraceWarpQ<true, false, true, false><<<g, TR_THREADS, sm, st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, nullptr, nullptr, 0u, cfg.bvh, cfg.travCounters + 3);
+      } else if (fuseL) kTraceWarpQ<true, false, false, true><<<g, TR_THREADS, sm, st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap, cfg.bvh, nullptr);
+      else kTraceWarpQ<true, false, false, false><<<g, TR_THREADS, sm, st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, nullptr, nullptr, 0u, cfg.bvh, nullptr);
       return;
    }
    kTracePersistent<true><<<traceGrid(c9, n, TR_THREADS), TR_THREADS, traceSmemBytes(cfg.maxStack), st>>>(q, cnt, n, sc, O, D, nullptr, occl, cfg.workCounter, fuseL, fuseP, fuseCap);

@@ -21,6 +21,9 @@ namespace bl {
 #ifndef TQ_FLUSH
 #define TQ_FLUSH 32       // run a leaf pass once this many pairs are queued (<= 32)
 #endif
+#ifndef TQ_NEAR_BLOCKS
+#define TQ_NEAR_BLOCKS TR_MINBLOCKS   // resident CTAs per SM the nearest-hit instantiation is compiled for (A/B: 7 = 72 registers)
+#endif
 #define TQ_WARPS (TR_THREADS / 32)
 #define TQ_WARP_BYTES (TQ_CAP * 4 + 32 * 4 + 32 * 16 + 32 * 32)   // per warp: ring, per-lane key / flag, per-lane hit record, per-lane ray (o, tmin)(d, tmax)
 #define TQ_HEAD_WORDS (TQ_WARPS * TQ_WARP_BYTES / 4)
@@ -36,10 +39,14 @@ __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, fl
 __device__ __forceinline__ F4 lds128(uint32_t a) { F4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sminU32(uint32_t a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
-// L[slot] += P[slot], one quarter at a time. Out of line on purpose: the any-hit kernels live at 56 registers (9 CTAs per SM)
-// and this once-per-ray tail must not take part in the hot loop's register allocation (inlined, it pushed three loop-carried
-// values into local memory when the spectrum layout changed: +18 % kernel time on cfg 5, tools/gpu_r02_f.sh).
-__device__ __noinline__ void fuseAddPending(F4 *__restrict__ L, const F4 *__restrict__ P, uint32_t cap, uint32_t slot) {
+// L[slot] += P[slot], one quarter at a time: the fused NEE resolve of the any-hit kernels (trace_kernels.cuh). It is compiled
+// only into the FUSE instantiation: the any-hit kernels live at 56 registers (9 CTAs per SM) and this once-per-ray tail takes
+// part in the hot loop's register allocation -- with the record layout of the spectra (bodies.h::spec4At) it pushed loop-carried
+// values of the traversal into local memory (12 -> 44 bytes of spill stores), +18 % kernel time on cfg 5, which does not even
+// take this path (tools/gpu_r02_f.sh). An out-of-line function cured the spills but cost the small scenes, which DO take it for
+// every unoccluded shadow ray, up to a third of their speed (tools/gpu_r02_g.sh). The fused instantiation keeps the spills and
+// is still the faster way there (cornell-box any-hit 4.54 -> 3.30 ms).
+__device__ __forceinline__ void fuseAddPending(F4 *__restrict__ L, const F4 *__restrict__ P, uint32_t cap, uint32_t slot) {
    for (int qq = 0; qq < 4; ++qq) {
       const size_t at = spec4At(cap, slot, qq);
       F4 l = L[at]; const F4 p_ = P[at];
@@ -48,8 +55,8 @@ __device__ __noinline__ void fuseAddPending(F4 *__restrict__ L, const F4 *__rest
    }
 }
 
-template <bool ANY, bool SORTED, bool STATS>
-__global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLOCKS) kTraceWarpQ(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
+template <bool ANY, bool SORTED, bool STATS, bool FUSE>
+__global__ void __launch_bounds__(TR_THREADS, (ANY && !FUSE) ? TR_MINBLOCKS + 1 : (ANY ? TR_MINBLOCKS : TQ_NEAR_BLOCKS)) kTraceWarpQ(const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt, uint32_t n,
                                                                  const DScene *__restrict__ sc, const F4 *__restrict__ O, const F4 *__restrict__ D,
                                                                  F4 *__restrict__ hit, uint8_t *__restrict__ occl, uint32_t *__restrict__ work, F4 *__restrict__ fuseL, const F4 *__restrict__ fuseP, uint32_t fuseCap,
                                                                  const Bvh bvh,     // the accelerator's pointers as a kernel PARAMETER: constant-bank operands instead of six registers
@@ -227,8 +234,8 @@ __global__ void __launch_bounds__(TR_THREADS, ANY ? TR_MINBLOCKS + 1 : TR_MINBLO
       // ---- retire rays whose walk is over and whose pairs are all through
       if (cur == WAITING && (int)(qhead - lastSeq) >= 0) {
          if (ANY) {
-            if (fuseL && !occ) fuseAddPending(fuseL, fuseP, fuseCap, slot);   // fused NEE resolve (trace_kernels.cuh): L += pending
-            else if (!fuseL) occl[slot] = occ ? 1 : 0;
+            if (FUSE) { if (!occ) fuseAddPending(fuseL, fuseP, fuseCap, slot); }   // fused NEE resolve (trace_kernels.cuh): L += pending
+            else occl[slot] = occ ? 1 : 0;
          } else hit[slot] = lds128(shitW + lane * 16u);
          cur = EMPTY;
       }
