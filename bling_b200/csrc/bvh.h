@@ -124,7 +124,10 @@ HD float u2f(uint32_t u) { return i2f((int)u); }
 #endif
 
 // slab test of the four children of one quantised node against [r.tmin, r.tmax]: tn[k] = entry distance of child k,
-// +inf when the ray misses it.
+// +inf when the ray misses it. OVERLAP: tn[k] = entry - exit distance instead, i.e. minus the length of the ray inside child k:
+// <= 0 for a hit, > 0 (or NaN: a ray parallel to a slab it lies outside of, with tmax = inf) for a miss. The any-hit kernel
+// enters the child the ray stays in longest (trace_warpq.cuh).
+template <bool OVERLAP = false>
 HD void node4Near(const F4 &n0, const F4 &n2, const F4 &n3, const Ray &r, const RayPre &p, float tnear[4]) {
 #if defined(__CUDA_ARCH__)
    const uint32_t bl_k23 = f2u(n3.z);   // 0x4B000000
@@ -141,7 +144,8 @@ HD void node4Near(const F4 &n0, const F4 &n2, const F4 &n3, const Ray &r, const 
    BL_UNROLL for (int k = 0; k < 4; ++k) {
       float tn = fmaxf(fmaxf(BL_FMA(BL_QF(nx, k), ax, bx), BL_FMA(BL_QF(ny, k), ay, by)), fmaxf(BL_FMA(BL_QF(nz, k), az, bz), r.tmin));
       float tf = fminf(fminf(BL_FMA(BL_QF(fx, k), ax, bx), BL_FMA(BL_QF(fy, k), ay, by)), fminf(BL_FMA(BL_QF(fz, k), az, bz), r.tmax));
-      tnear[k] = (tn <= tf) ? tn : BL_INF;
+      if (OVERLAP) tnear[k] = tn - tf;
+      else tnear[k] = (tn <= tf) ? tn : BL_INF;
    }
 }
 // sort the four (entry distance, child reference) pairs by distance: 5 compare-exchanges, each one compare + four

@@ -25,8 +25,14 @@ namespace bl {
 #define TQ_NEAR_BLOCKS TR_MINBLOCKS   // resident CTAs per SM the nearest-hit instantiation is compiled for (A/B: 7 = 72 registers)
 #endif
 #define TQ_WARPS (TR_THREADS / 32)
-#define TQ_WARP_BYTES (TQ_CAP * 4 + 32 * 4 + 32 * 16 + 32 * 32)   // per warp: ring, per-lane key / flag, per-lane hit record, per-lane ray (o, tmin)(d, tmax)
-#define TQ_HEAD_WORDS (TQ_WARPS * TQ_WARP_BYTES / 4)
+#define TQ_STACK_OFF (TQ_CAP * 4 + 32 * 4 + 32 * 16 + 32 * 32 + 32 * 4)   // per warp: ring, per-lane key / flag, per-lane hit record, per-lane ray (o, tmin)(d, tmax), per-lane slot ...
+#define TQ_WARP_BYTES (TQ_STACK_OFF + TR_SS * 128)                     // ... and the warp's own stack [level][lane]
+// The stack lives in the WARP's region and the stack pointer is a shared-window ADDRESS (spA: the next free entry of my
+// column), so that every push and pop is one instruction with an immediate offset and neither a stack base nor a level count
+// has to stay in a register: ncu's source view of the previous layout ([level][thread] behind the four warps' heads) showed
+// the stack base spilled to local memory and re-read twice per trip, and -- with an L1 hit rate of 3 % -- 10 % of all warp
+// samples waiting on those LDLs (profiles/r02_trace_warpq.md). The ray's slot moved to shared memory for the same reason.
+#define TQ_LEVEL(spA_, sqA_) ((int)(((spA_) - (sqA_) - (uint32_t)TQ_STACK_OFF) >> 7))   // stack level of an entry address (lane * 4 < 128)
 
 // order-preserving float <-> uint32 key (so that atomicMin on the key is a float min for any sign)
 __device__ __forceinline__ uint32_t fkey(float f) { const uint32_t b = __float_as_uint(f); return b ^ ((uint32_t)((int)b >> 31) | 0x80000000u); }
@@ -37,6 +43,13 @@ __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 __device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) { asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory"); }
 __device__ __forceinline__ F4 lds128(uint32_t a) { F4 v; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory"); return v; }
+// L2 prefetch of data a LATER trip will load (TQ_PREFETCH): the kernels wait on memory (long-scoreboard stalls are half of all
+// warp samples, L2 hit rate 45-60 % on an 830 MB tree), and both the items a lane queues and the children it pushes are
+// certain to be read -- there is no culling on pop
+#ifndef TQ_PREFETCH
+#define TQ_PREFETCH 0     // bit 0: leaf items when they are queued, bit 1: inner children when they are pushed
+#endif
+__device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void sminU32(uint32_t a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // L[slot] += P[slot], one quarter at a time: the fused NEE resolve of the any-hit kernels (trace_kernels.cuh). It is compiled
@@ -69,20 +82,20 @@ __global__ void __launch_bounds__(TR_THREADS, (ANY && !FUSE) ? TR_MINBLOCKS + 1 
    // sits on the critical path of every push, pop and queue append)
    unsigned lane; asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane));
    const unsigned ltMask = (1u << lane) - 1u;
-   uint32_t sqA, stackBase;
+   uint32_t sqA;
    {
       const uint32_t sBase = (uint32_t)__cvta_generic_to_shared(sstack);
       asm volatile("mov.u32 %0, %1;" : "=r"(sqA) : "r"(sBase + (threadIdx.x >> 5) * (uint32_t)TQ_WARP_BYTES));     // my warp's ring
-      asm volatile("mov.u32 %0, %1;" : "=r"(stackBase) : "r"(sBase + (TQ_HEAD_WORDS + threadIdx.x) * 4u));           // my stack column
    }
    const uint32_t sownW = sqA + TQ_CAP * 4u;        // [lane] of my warp: tmax key (nearest) / occluded flag (any)
    const uint32_t shitW = sownW + 32u * 4u;         // [lane] of my warp: best hit so far (nearest)
    const uint32_t srayW = shitW + 32u * 16u;        // [lane] of my warp: (o, tmin)(d, tmax) for the lanes that test my pairs
-   const uint32_t LV = TR_THREADS * (uint32_t)sizeof(int);
+   const uint32_t sslotW = srayW + 32u * 32u;       // [lane] of my warp: the slot of the ray (needed again only when it retires)
+   const uint32_t SP_FAST = (uint32_t)TQ_STACK_OFF + TR_SS * 128u;   // spA - sqA below this: the entry lies in shared memory
    int tail_[BL_STACK - TR_SS];
    const int EMPTY = (int)0x80000000, WAITING = (int)0x80000001;   // leaf references are > WAITING (bvh.h: ~((first << 4) | count))
-   int cur = EMPTY, li = 0, sp = 0;
-   uint32_t slot = 0;
+   int cur = EMPTY, li = 0;
+   uint32_t spA = sqA + (uint32_t)TQ_STACK_OFF + lane * 4u;
    uint32_t qhead = 0, qtail = 0, lastSeq = 0;   // absolute ring positions (warp-uniform) and the position behind my last pair
    bool occ = false;
    Ray r; RayPre pre;
@@ -102,14 +115,15 @@ __global__ void __launch_bounds__(TR_THREADS, (ANY && !FUSE) ? TR_MINBLOCKS + 1 
          if (cur == EMPTY) {
             const uint32_t k = base + __popc(idle & ltMask);
             if (k < total) {
-               slot = q ? q[k] : k;
+               const uint32_t slot = q ? q[k] : k;
+               sts32(sslotW + lane * 4u, slot);
                if (STATS) stR++;
                r = loadRay(O, D, slot);
                pre = rayPre(r);
                sts128(srayW + lane * 32u, r.o.x, r.o.y, r.o.z, r.tmin); sts128(srayW + lane * 32u + 16u, r.d.x, r.d.y, r.d.z, r.tmax);
                if (ANY) sts32(sownW + lane * 4u, 0u);
                else { sts32(sownW + lane * 4u, fkey(r.tmax)); sts128(shitW + lane * 16u, 0.0f, 0.0f, 0.0f, i2f(-1)); }
-               sp = 0; li = 0; occ = false; lastSeq = qtail;
+               spA = sqA + (uint32_t)TQ_STACK_OFF + lane * 4u; li = 0; occ = false; lastSeq = qtail;
                cur = (bvh.root >= 0) ? bvh.root : WAITING;   // empty scene: nothing to wait for either
             }
          }
@@ -125,39 +139,56 @@ __global__ void __launch_bounds__(TR_THREADS, (ANY && !FUSE) ? TR_MINBLOCKS + 1 
          F4 n0, n1, n2, n3;
          ld8(np, n0, n1); ld8(np + 2, n2, n3);
          float tn[4];
-         node4Near(n0, n2, n3, r, pre, tn);
+         node4Near<!SORTED>(n0, n2, n3, r, pre, tn);   // unsorted (any-hit): tn = minus the length of the ray inside the child
          int c[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};
          if (SORTED) {
             sort4(tn, c);   // nearest first, misses (+inf) last
             const bool h0 = tn[0] < BL_INF, h1 = tn[1] < BL_INF, h2 = tn[2] < BL_INF, h3 = tn[3] < BL_INF;
             const int nh = (int)h0 + (int)h1 + (int)h2 + (int)h3;
-            const int l1 = sp + nh - 2, l2 = l1 - 1, l3 = l1 - 2;
-            if (l1 < TR_SS) {
-               const uint32_t top = stackBase + (uint32_t)l1 * LV;
-               stsIf(top, c[1], h1); stsIf(top - LV, c[2], h2); stsIf(top - 2 * LV, c[3], h3);
-            } else {
-               if (h1) { if (l1 < TR_SS) stsIf(stackBase + (uint32_t)l1 * LV, c[1], true); else tail_[l1 - TR_SS] = c[1]; }
-               if (h2) { if (l2 < TR_SS) stsIf(stackBase + (uint32_t)l2 * LV, c[2], true); else tail_[l2 - TR_SS] = c[2]; }
-               if (h3) { if (l3 < TR_SS) stsIf(stackBase + (uint32_t)l3 * LV, c[3], true); else tail_[l3 - TR_SS] = c[3]; }
+            const uint32_t top = spA + (uint32_t)((nh > 0) ? nh - 1 : 0) * 128u;   // the new stack pointer; c[1] goes right below it
+            if (top - sqA < SP_FAST + 128u) { stsIf(top - 128u, c[1], h1); stsIf(top - 256u, c[2], h2); stsIf(top - 384u, c[3], h3); }
+            else {
+               const int l1 = TQ_LEVEL(top, sqA) - 1, l2 = l1 - 1, l3 = l1 - 2;
+               if (h1) { if (l1 < TR_SS) stsIf(top - 128u, c[1], true); else tail_[l1 - TR_SS] = c[1]; }
+               if (h2) { if (l2 < TR_SS) stsIf(top - 256u, c[2], true); else tail_[l2 - TR_SS] = c[2]; }
+               if (h3) { if (l3 < TR_SS) stsIf(top - 384u, c[3], true); else tail_[l3 - TR_SS] = c[3]; }
             }
-            sp += (nh > 0) ? nh - 1 : 0;
+            if (TQ_PREFETCH & 2) {
+               if (h1 && c[1] >= 0) prefetchL2(bvh.nodes + BL_NODE_F4 * (size_t)c[1]);
+               if (h2 && c[2] >= 0) prefetchL2(bvh.nodes + BL_NODE_F4 * (size_t)c[2]);
+               if (h3 && c[3] >= 0) prefetchL2(bvh.nodes + BL_NODE_F4 * (size_t)c[3]);
+            }
+            spA = top;
             cur = c[0];
             pop = h0 ? 0 : 1;
          } else {
-            // any-hit, unsorted (variant 3): the answer does not depend on the order and the warp model shows the same
-            // number of node visits in slot order (tools/travsim.cpp), so the five compare-exchanges are dropped: enter
-            // the first child hit, push the others as they come
-            const bool h0 = tn[0] < BL_INF, h1 = tn[1] < BL_INF, h2 = tn[2] < BL_INF, h3 = tn[3] < BL_INF;
-            const bool p1 = h1 && h0, p2 = h2 && (h0 || h1), p3 = h3 && (h0 || h1 || h2);
-            const int l1 = sp, l2 = sp + (int)p1, l3 = l2 + (int)p2;
-            if (l3 < TR_SS) { stsIf(stackBase + (uint32_t)l1 * LV, c[1], p1); stsIf(stackBase + (uint32_t)l2 * LV, c[2], p2); stsIf(stackBase + (uint32_t)l3 * LV, c[3], p3); }
+            // any-hit (variant 3): the answer does not depend on the order, so there is no sort; but WHICH child is entered first
+            // decides how soon an occluder is found. The warp model (tools/travsim.cpp, profiles/r02_travsim.md) on the cfg-5
+            // shadow / BSDF-MIS rays: entering the nearest child or the first in slot order costs the same 44.5 node visits per
+            // ray, entering the child the ray stays in LONGEST costs 37.9 (-15 %): a long stretch inside a box of the soup is a
+            // likely hit. The others are pushed as they come.
+            const bool h0 = tn[0] <= 0.0f, h1 = tn[1] <= 0.0f, h2 = tn[2] <= 0.0f, h3 = tn[3] <= 0.0f;
+            const bool b01 = tn[1] < tn[0], b23 = tn[3] < tn[2];
+            const float k01 = b01 ? tn[1] : tn[0], k23 = b23 ? tn[3] : tn[2];
+            const bool bb = k23 < k01;                                       // a miss (> 0) never beats a hit (<= 0)
+            const bool p0 = h0 && (b01 || bb), p1 = h1 && (!b01 || bb), p2 = h2 && (b23 || !bb), p3 = h3 && (!b23 || !bb);
+            const uint32_t a0 = spA, a1 = a0 + (p0 ? 128u : 0u), a2 = a1 + (p1 ? 128u : 0u), a3 = a2 + (p2 ? 128u : 0u);
+            if (a3 - sqA < SP_FAST) { stsIf(a0, c[0], p0); stsIf(a1, c[1], p1); stsIf(a2, c[2], p2); stsIf(a3, c[3], p3); }
             else {
-               if (p1) { if (l1 < TR_SS) stsIf(stackBase + (uint32_t)l1 * LV, c[1], true); else tail_[l1 - TR_SS] = c[1]; }
-               if (p2) { if (l2 < TR_SS) stsIf(stackBase + (uint32_t)l2 * LV, c[2], true); else tail_[l2 - TR_SS] = c[2]; }
-               if (p3) { if (l3 < TR_SS) stsIf(stackBase + (uint32_t)l3 * LV, c[3], true); else tail_[l3 - TR_SS] = c[3]; }
+               const int l0 = TQ_LEVEL(a0, sqA), l1 = TQ_LEVEL(a1, sqA), l2 = TQ_LEVEL(a2, sqA), l3 = TQ_LEVEL(a3, sqA);
+               if (p0) { if (l0 < TR_SS) stsIf(a0, c[0], true); else tail_[l0 - TR_SS] = c[0]; }
+               if (p1) { if (l1 < TR_SS) stsIf(a1, c[1], true); else tail_[l1 - TR_SS] = c[1]; }
+               if (p2) { if (l2 < TR_SS) stsIf(a2, c[2], true); else tail_[l2 - TR_SS] = c[2]; }
+               if (p3) { if (l3 < TR_SS) stsIf(a3, c[3], true); else tail_[l3 - TR_SS] = c[3]; }
             }
-            sp = l3 + (int)p3;
-            cur = h0 ? c[0] : (h1 ? c[1] : (h2 ? c[2] : c[3]));
+            if (TQ_PREFETCH & 2) {
+               if (p0 && c[0] >= 0) prefetchL2(bvh.nodes + BL_NODE_F4 * (size_t)c[0]);
+               if (p1 && c[1] >= 0) prefetchL2(bvh.nodes + BL_NODE_F4 * (size_t)c[1]);
+               if (p2 && c[2] >= 0) prefetchL2(bvh.nodes + BL_NODE_F4 * (size_t)c[2]);
+               if (p3 && c[3] >= 0) prefetchL2(bvh.nodes + BL_NODE_F4 * (size_t)c[3]);
+            }
+            spA = a3 + (p3 ? 128u : 0u);
+            cur = bb ? (b23 ? c[3] : c[2]) : (b01 ? c[1] : c[0]);
             pop = (h0 || h1 || h2 || h3) ? 0 : 1;
          }
          li = 0;
@@ -174,6 +205,11 @@ __global__ void __launch_bounds__(TR_THREADS, (ANY && !FUSE) ? TR_MINBLOCKS + 1 
             const uint32_t ent = (lane << 27) | (uint32_t)((enc >> 4) + li);
             if (rem >= 1) sts32(sqA + ((at & (TQ_CAP - 1)) << 2), ent);
             if (rem >= 2) sts32(sqA + (((at + 1u) & (TQ_CAP - 1)) << 2), ent + 1u);
+            if (TQ_PREFETCH & 1) {
+               const F4 *ip = bvh.items + (size_t)BL_ITEM_F4 * (size_t)((enc >> 4) + li);
+               if (rem >= 1) prefetchL2(ip);
+               if (rem >= 2) prefetchL2(ip + BL_ITEM_F4);
+            }
             qtail += (uint32_t)__popc(b1) + (uint32_t)__popc(b2);
             if (rem >= 1) { li += 2; lastSeq = qtail; }
          }
@@ -181,11 +217,12 @@ __global__ void __launch_bounds__(TR_THREADS, (ANY && !FUSE) ? TR_MINBLOCKS + 1 
       }
       // ---- pop (predicated load); with an empty stack the ray waits for its queued pairs
       {
-         const bool doPop = pop != 0 && sp != 0;
-         if (pop != 0) { li = 0; if (sp == 0) cur = WAITING; }
-         sp -= doPop ? 1 : 0;
-         if (doPop && sp >= TR_SS) cur = tail_[sp - TR_SS];
-         else cur = ldsIf(stackBase + (uint32_t)sp * LV, cur, doPop);
+         const bool some = spA - sqA >= (uint32_t)TQ_STACK_OFF + 128u;   // my column holds an entry
+         const bool doPop = pop != 0 && some;
+         if (pop != 0) { li = 0; if (!some) cur = WAITING; }
+         spA -= doPop ? 128u : 0u;
+         if (doPop && spA - sqA >= SP_FAST) cur = tail_[TQ_LEVEL(spA, sqA) - TR_SS];
+         else cur = ldsIf(spA, cur, doPop);
       }
       // ---- leaf passes: 32 pairs at a time; a partial batch only when nobody could do anything else
       {
@@ -208,7 +245,7 @@ __global__ void __launch_bounds__(TR_THREADS, (ANY && !FUSE) ? TR_MINBLOCKS + 1 
                   if (valid) found = leafItemAny(bvh, item, rr);
                   if (found) sts32(sownW + (uint32_t)owner * 4u, 1u);
                   __syncwarp();
-                  if (lds32(sownW + lane * 4u) != 0u && cur != EMPTY && !occ) { occ = true; sp = 0; cur = WAITING; }   // my ray is occluded: drop the rest of its walk
+                  if (lds32(sownW + lane * 4u) != 0u && cur != EMPTY && !occ) { occ = true; spA = sqA + (uint32_t)TQ_STACK_OFF + lane * 4u; cur = WAITING; }   // my ray is occluded: drop the rest of its walk
                } else {
                   rr.tmax = fkeyInv(lds32(sownW + (uint32_t)owner * 4u));
                   HitRec hh; hh.t = 0; hh.prim = -1; hh.b1 = hh.b2 = 0;
@@ -233,6 +270,7 @@ __global__ void __launch_bounds__(TR_THREADS, (ANY && !FUSE) ? TR_MINBLOCKS + 1 
       }
       // ---- retire rays whose walk is over and whose pairs are all through
       if (cur == WAITING && (int)(qhead - lastSeq) >= 0) {
+         const uint32_t slot = lds32(sslotW + lane * 4u);
          if (ANY) {
             if (FUSE) { if (!occ) fuseAddPending(fuseL, fuseP, fuseCap, slot); }   // fused NEE resolve (trace_kernels.cuh): L += pending
             else occl[slot] = occ ? 1 : 0;
@@ -246,6 +284,6 @@ __global__ void __launch_bounds__(TR_THREADS, (ANY && !FUSE) ? TR_MINBLOCKS + 1 
    }
 }
 
-static inline size_t traceWarpQSmemBytes(int maxStack) { return TQ_HEAD_WORDS * sizeof(uint32_t) + traceSmemBytes(maxStack); }
+static inline size_t traceWarpQSmemBytes(int) { return (size_t)TQ_WARPS * TQ_WARP_BYTES; }   // the deep part of a stack (> TR_SS levels) lives in local memory
 
 }  // namespace bl

@@ -134,7 +134,7 @@ static std::vector<Tri> gItems;   // in leaf order
 static inline void nodeStep(const WTree &T, const Policy &P, Lane &L, bool ANY, Stats &S) {
    const WNode &nd = T.nodes[L.cur];
    S.nodes++;
-   float tn[8]; int rf[8]; int n = 0;
+   float tn[8], tfv[8], area[8]; int rf[8]; int n = 0;
    const int oct = (L.r.d.x < 0 ? 1 : 0) | (L.r.d.y < 0 ? 2 : 0) | (L.r.d.z < 0 ? 4 : 0);
    for (int kk = 0; kk < T.W; ++kk) {
       const int k = P.octant ? (kk ^ oct) & (T.W - 1) : kk;   // for W=4 only two axes' bits matter (approximation)
@@ -146,10 +146,33 @@ static inline void nodeStep(const WTree &T, const Policy &P, Lane &L, bool ANY, 
          if (id[a] < 0) std::swap(ta, tb);
          t0 = std::max(t0, ta); t1 = std::min(t1, tb);
       }
-      if (t0 <= t1) { tn[n] = t0; rf[n] = nd.ref[k]; n++; }
+      if (t0 <= t1) {
+         const float ex = nd.hi[k][0] - nd.lo[k][0], ey = nd.hi[k][1] - nd.lo[k][1], ez = nd.hi[k][2] - nd.lo[k][2];
+         area[n] = ex * ey + ey * ez + ez * ex;
+         tn[n] = t0; tfv[n] = t1; rf[n] = nd.ref[k]; n++;
+      }
    }
    if (n == 0) { L.cur = 0x7fffffff; return; }   // pop
-   if (P.sortChildren) {
+   if (ANY && P.anyOrder) {   // experimental any-hit orders: the key replaces the entry distance
+      for (int i = 0; i < n; ++i) {
+         float key = tn[i];
+         if (P.anyOrder == 1) key = -(tfv[i] - tn[i]);                       // longest overlap first
+         else if (P.anyOrder == 2) key = (rf[i] < 0 ? -1e30f : 0.0f) + tn[i];   // leaves first, then nearest
+         else if (P.anyOrder == 3) key = -tn[i];                              // farthest first
+         else if (P.anyOrder == 4) key = (rf[i] < 0 ? 1e30f : 0.0f) + tn[i];    // inner nodes first, leaves last
+         else if (P.anyOrder == 7) key = -area[i];                            // static: largest box first (a builder-time slot order, free at run time)
+         else if (P.anyOrder == 8) key = area[i];                             // static: smallest box first
+         tn[i] = key;
+      }
+      if (P.anyOrder == 5 || P.anyOrder == 6) {   // only the FIRST child is chosen by the key (5: longest overlap, 6: same, the rest reversed), the rest stay in slot order
+         for (int i = 0; i < n; ++i) tn[i] = -(tfv[i] - (tn[i]));
+         int b = 0; for (int i = 1; i < n; ++i) if (tn[i] < tn[b]) b = i;
+         float tb = tn[b]; int rb = rf[b];
+         for (int i = b; i > 0; --i) { tn[i] = tn[i - 1]; rf[i] = rf[i - 1]; }
+         tn[0] = tb; rf[0] = rb;
+      } else
+      for (int i = 1; i < n; ++i) { float t = tn[i]; int r = rf[i]; int j = i; while (j > 0 && tn[j - 1] > t) { tn[j] = tn[j - 1]; rf[j] = rf[j - 1]; --j; } tn[j] = t; rf[j] = r; }
+   } else if (P.sortChildren) {
       for (int i = 1; i < n; ++i) { float t = tn[i]; int r = rf[i]; int j = i; while (j > 0 && tn[j - 1] > t) { tn[j] = tn[j - 1]; rf[j] = rf[j - 1]; --j; } tn[j] = t; rf[j] = r; }
    } else if (P.nearestFirstOnly) {
       int b = 0; for (int i = 1; i < n; ++i) if (tn[i] < tn[b]) b = i;
@@ -426,6 +449,13 @@ int main(int argc, char **argv) {
    { Policy p = base; p.name = "defer bvh8 octant"; p.deferLeaves = true; p.W = 8; p.octant = true; p.sortChildren = false; p.cNode = 210; p.cTrip = 50; pols.push_back(p); }
    { Policy p = base; p.name = "defer bvh8 octant+cull"; p.deferLeaves = true; p.W = 8; p.octant = true; p.sortChildren = false; p.cullOnPop = true; p.cNode = 215; p.cTrip = 50; pols.push_back(p); }
    { Policy p = base; p.name = "defer cull"; p.deferLeaves = true; p.cullOnPop = true; p.cNode = 177; pols.push_back(p); }
+   { Policy p = base; p.name = "defer any:longest"; p.deferLeaves = true; p.anyOrder = 1; pols.push_back(p); }
+   { Policy p = base; p.name = "defer any:leaves-first"; p.deferLeaves = true; p.anyOrder = 2; pols.push_back(p); }
+   { Policy p = base; p.name = "defer any:farthest"; p.deferLeaves = true; p.anyOrder = 3; pols.push_back(p); }
+   { Policy p = base; p.name = "defer any:longest-first-only"; p.deferLeaves = true; p.anyOrder = 5; pols.push_back(p); }
+   { Policy p = base; p.name = "defer any:leaves-last"; p.deferLeaves = true; p.anyOrder = 4; pols.push_back(p); }
+   { Policy p = base; p.name = "defer any:static-largest"; p.deferLeaves = true; p.anyOrder = 7; p.cNode = 140; pols.push_back(p); }
+   { Policy p = base; p.name = "defer any:static-smallest"; p.deferLeaves = true; p.anyOrder = 8; p.cNode = 140; pols.push_back(p); }
 
    if (const char *f = getenv("POLS")) { std::vector<Policy> keep; keep.push_back(pols[0]); std::string fs(f); for (size_t i = 1; i < pols.size(); ++i) if (fs.find(std::string("|") + pols[i].name + "|") != std::string::npos) keep.push_back(pols[i]); pols = keep; }
    std::vector<Ray> ext_ = cam;
