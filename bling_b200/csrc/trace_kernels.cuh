@@ -86,7 +86,8 @@ __global__ void __launch_bounds__(128) kTraceNearestCount(const uint32_t *__rest
 // from the global queue with a warp-aggregated atomic once enough lanes have retired.
 #define TR_THREADS 128
 #ifndef TR_REFILL
-#define TR_REFILL 4       // refill once this many lanes are idle
+#define TR_REFILL 6       // refill once this many lanes are idle (a refill stalls the whole warp for three dependent loads; cfg 5:
+                          // 4 -> 589 / 628 ms nearest / any per 5 steps, 6 -> 585 / 622, 8 -> 589 / 624, 12 -> 610 / 631; tools/gpu_r02_q.sh)
 #endif
 #ifndef TR_MINBLOCKS
 #define TR_MINBLOCKS 8    // resident CTAs per SM of the nearest-hit kernel (64 registers); the any-hit kernel carries no hit

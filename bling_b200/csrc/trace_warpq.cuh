@@ -47,9 +47,11 @@ __device__ __forceinline__ F4 lds128(uint32_t a) { F4 v; asm volatile("ld.shared
 // warp samples, L2 hit rate 45-60 % on an 830 MB tree), and both the items a lane queues and the children it pushes are
 // certain to be read -- there is no culling on pop
 #ifndef TQ_PREFETCH
-#define TQ_PREFETCH 0     // bit 0: leaf items when they are queued, bit 1: inner children when they are pushed
+#define TQ_PREFETCH 0     // bit 0: leaf items when they are queued, bit 1: inner children when they are pushed (both into L2);
+                          // bit 2: the node of the NEXT trip into L1 as soon as it is known (after the pop), bit 3: both of its sectors
 #endif
 __device__ __forceinline__ void prefetchL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetchL1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void sminU32(uint32_t a, uint32_t v) { asm volatile("red.shared.min.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 
 // L[slot] += P[slot], one quarter at a time: the fused NEE resolve of the any-hit kernels (trace_kernels.cuh). It is compiled
@@ -223,6 +225,13 @@ __global__ void __launch_bounds__(TR_THREADS, (ANY && !FUSE) ? TR_MINBLOCKS + 1 
          spA -= doPop ? 128u : 0u;
          if (doPop && spA - sqA >= SP_FAST) cur = tail_[TQ_LEVEL(spA, sqA) - TR_SS];
          else cur = ldsIf(spA, cur, doPop);
+      }
+      if (TQ_PREFETCH & 4) {
+         if (cur >= 0) {
+            const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
+            prefetchL1(np);
+            if (TQ_PREFETCH & 8) prefetchL1(np + 2);
+         }
       }
       // ---- leaf passes: 32 pairs at a time; a partial batch only when nobody could do anything else
       {

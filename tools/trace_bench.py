@@ -24,6 +24,19 @@ def bounce_rays(n, seed, extent=100.0):
     return rays
 
 
+def morton_sorted(rays, extent=100.0, bits=6, octant_major=False):
+    """the same rays ordered by the Morton code of their origin's cell (and direction octant): how much the traversal kernels
+    would gain from binning the ray queues (profiles/r02_trace_warpq.md)"""
+    c = np.clip(((rays["o"] / extent + 1) * 0.5 * (1 << bits)).astype(np.int64), 0, (1 << bits) - 1)
+    key = np.zeros(len(rays), np.int64)
+    for b in range(bits):
+        for a in range(3):
+            key |= ((c[:, a] >> b) & 1) << (3 * b + a)
+    octant = ((rays["d"][:, 0] < 0) * 1 + (rays["d"][:, 1] < 0) * 2 + (rays["d"][:, 2] < 0) * 4).astype(np.int64)
+    key = (octant << (3 * bits)) | key if octant_major else (key << 3) | octant
+    return np.ascontiguousarray(rays[np.argsort(key, kind="stable")])
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lib", nargs="*", default=[str(api.LIB_PATH)])
@@ -31,11 +44,15 @@ def main():
     ap.add_argument("--rays", type=int, default=4_000_000)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--option", action="append", default=[])
+    ap.add_argument("--sorted", action="store_true", help="also time the bounce batch binned by origin cell / direction octant")
     ap.add_argument("--variants", type=int, nargs="*", default=None, help="trace_variant values to time in ONE context (scene uploaded once)")
     a = ap.parse_args()
     scene = make_soup(a.tris, 64, 36, 1, 1)
     from tests.conftest import camera_rays
     batches = {"bounce": bounce_rays(a.rays, 1), "primary": camera_rays(None, scene, a.rays, 2)}
+    if a.sorted:
+        batches["bnc-cell"] = morton_sorted(batches["bounce"]); batches["bnc-oct"] = morton_sorted(batches["bounce"], octant_major=True)
+        batches["bnc-cell4"] = morton_sorted(batches["bounce"], bits=4)
     for lib in a.lib:
         class Ctx(api.Context):
             _lib_path = Path(lib)
