@@ -653,6 +653,10 @@ class Loader:
             else: raise NotImplementedError(f"integrator {ik} (outside SURVEY §8)")
             tk.expect("}"); tk.expect("}"); tk.expect("}")
             self.st.renderer = dict(kind="sampler", sampler=smp, integrator=integ)
+        elif t == "light":                     # RendererParser.hs:28-30: mkLightTracer ppp
+            n = tk.named_int("passPhotons"); tk.expect("}")
+            # the sampler / integrator fields of the IR are unused by blingcu_light_trace; they keep their defaults
+            self.st.renderer = dict(kind="light", pass_photons=n, sampler=("stratified", 2, 2), integrator=("path", 7, 3))
         else:                                  # other renderers are recorded so "last one wins" stays visible
             depth = 1
             while depth: x = tk.next(); depth += (x == "{") - (x == "}")
@@ -670,8 +674,8 @@ class Loader:
     # ---- finish: mkScene (Scene.hs:37-43) + mkJob
     def finish(self, name="") -> IR.SceneIR:
         st, ir = self.st, self.ir
-        if st.renderer.get("kind") != "sampler":
-            raise ValueError(f"active renderer is {st.renderer['kind']!r}, not the sampler/path renderer (SURVEY F10)")
+        if st.renderer.get("kind") not in ("sampler", "light"):
+            raise ValueError(f"active renderer is {st.renderer['kind']!r}, not the sampler or the light-tracer renderer (SURVEY F10)")
         prims = [p for block in st.prims for p in block]
         # explicit lights first, then geometric lights in prim order
         lights = []
@@ -721,6 +725,9 @@ class Loader:
         ir.illum_basis = np.stack(S.ILLUM).astype(F)
         ir.refl_basis = np.stack(S.REFL).astype(F)
         ir.name = name
+        ir.pass_photons = 0
+        if st.renderer["kind"] == "light":     # the camera connection needs world2raster / pixel_area (Camera.hs:78-103)
+            ir = with_light_tracer_camera(ir); ir.pass_photons = int(st.renderer["pass_photons"])
         return ir
 
     def mk_light(self, l) -> IR.Light:

@@ -167,6 +167,14 @@ class LightTracerRenderer:
         self.ctx.close()
 
 
+def renderer_for(scene: IR.SceneIR, device: int = 0, seed: int = 0x5EED, context_cls=api.Context):
+    """The renderer the job's active `renderer {}` block names (RendererParser.hs:26-54, last one wins): the light tracer for
+    `renderer { light passPhotons n }` (the loader leaves n in `scene.pass_photons`), else the sampler renderer."""
+    if getattr(scene, "pass_photons", 0) > 0:
+        return LightTracerRenderer(scene.pass_photons, device, seed, context_cls)
+    return CudaRenderer(device, seed, context_cls=context_cls)
+
+
 class MultiDeviceRenderer:
     """One process, one context per device (SURVEY.md §8b `blingcu_create(devices, ndev)` in spirit): what a single Haskell
     process binding the C ABI does to use every GPU of the box. Render calls are asynchronous, so one host thread keeps all

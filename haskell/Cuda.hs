@@ -48,6 +48,9 @@ foreign import ccall safe "blingcu_eval_texture"  c_eval_texture :: Ptr Ctx -> I
 foreign import ccall safe "blingcu_comm_init_all"     c_comm_init_all     :: Ptr (Ptr Ctx) -> CInt -> IO CInt
 foreign import ccall safe "blingcu_reduce_film_group" c_reduce_film_group :: Ptr (Ptr Ctx) -> CInt -> CInt -> IO CInt
 foreign import ccall safe "blingcu_read_film_sum"     c_read_film_sum     :: Ptr Ctx -> Ptr CFloat -> IO CInt
+-- the light tracer (Renderer/LightTracer.hs): photons [first, first + n) of a pass into the splat buffer, [H][W]{X, Y, Z}
+foreign import ccall safe "blingcu_light_trace"       c_light_trace       :: Ptr Ctx -> Word32 -> Word64 -> Word64 -> Word32 -> IO CInt
+foreign import ccall safe "blingcu_read_splat"        c_read_splat        :: Ptr Ctx -> Ptr CFloat -> IO CInt
 
 -- | `renderer { cuda devices 0 1 2 3 seed 42 }` in a .bling file (IO/RendererParser.hs:26-51 gains one case)
 data CudaRenderer = CR { crDevices :: [Int], crSeed :: Word64 }
@@ -107,3 +110,29 @@ instance Renderer CudaRenderer where
                when cont $ pass (p + 1)
          pass (1 :: Int)
       forM_ ctxs c_destroy
+
+-- | `renderer { cudaLight passPhotons n }`: Renderer/LightTracer.hs:39-51 on the device. The splat buffer comes back as
+-- [H][W]{X, Y, Z} == Img._imgS (Image.hs:64-70), the film stays empty, and the reporter gets the same
+-- `PassDone n img (1 / (n * ppp))` the CPU light tracer sends. The scene IR's camera must carry world2raster and the
+-- pixel area (Camera.hs:78-103 sampleCam; `irCamera` fills them from the parser's transform).
+data CudaLightTracer = CLT { cltDevice :: Int, cltPassPhotons :: Int, cltSeed :: Word64 }
+
+instance Printable CudaLightTracer where
+   prettyPrint (CLT d n _) = PP.vcat [PP.text "CUDA light tracer on device" PP.<+> PP.int d, PP.int n PP.<+> PP.text "photons per pass"]
+
+instance Renderer CudaLightTracer where
+   render (CLT dev ppp seed) job report = do
+      c <- createOn dev
+      let (w, h) = jobImageSize job
+      withSceneIR (jobSceneIR job) $ \pir -> c_upload_scene c pir >>= check c
+      _ <- report Started
+      let pass p = do
+            c_light_trace c (fromIntegral p) seed 0 (fromIntegral ppp) >>= check c
+            ms <- SVM.new (w * h * 3)
+            SVM.unsafeWith ms $ \ptr -> c_read_splat c (castPtr ptr) >>= check c
+            splats <- SV.unsafeFreeze ms
+            let img = imageFromSplats w h (jobPixelFilter job) (V.convert splats)      -- an Image with empty _imgP and these _imgS
+            cont <- report (PassDone p img (1 / fromIntegral (p * ppp)))
+            when cont $ pass (p + 1)
+      pass (1 :: Int)
+      c_destroy c

@@ -123,6 +123,38 @@ def test_light_tracer_renderer_reports_passes_with_splat_weights():
     r.close()
 
 
+def test_loader_reads_the_light_renderer_block(tmp_path):
+    """`renderer { light passPhotons n }` (IO/RendererParser.hs:28-30), last renderer block wins (:53-54): the stand-in loader hands
+    the scene on with the camera fields sampleCam needs and `renderer_for` picks the light tracer"""
+    from bling_b200.host.loader import load_scene
+    from bling_b200.renderer import CudaRenderer, LightTracerRenderer, PassDone, RenderJob, renderer_for
+    text = """
+filter box
+renderer { sampler sampled { sampler { stratified 2 2 } integrator { path maxDepth 5 sampleDepth 3 } } }
+renderer { light passPhotons 700 }
+imageSize 24 16
+transform { lookAt { pos 0 3 -8 look 0 0 0 up 0 1 0 } }
+camera { perspective fov 40 lensRadius 0 focalDistance 10 }
+newTransform { }
+material { matte kd { constant rgbR 0.6 0.6 0.6 } sigma { constant 0 } }
+prim { mesh vertexCount 4 faceCount 1 v -3 0 -3 v -3 0 3 v 3 0 3 v 3 0 -3 f 0 1 2 3 }
+light { point intensity rgbI 30 30 30 position 0 2 0 }
+"""
+    f = tmp_path / "lt.bling"; f.write_text(text)
+    sc = load_scene(f)
+    assert sc.pass_photons == 700 and sc.camera.pixel_area > 0 and any(abs(x) > 0 for x in sc.camera.world2raster)
+    r = renderer_for(sc, context_cls=EmuContext)
+    assert isinstance(r, LightTracerRenderer) and r.ppp == 700
+    seen = []
+    r.render(RenderJob(sc), lambda p: (seen.append(p) or False) if isinstance(p, PassDone) else True)
+    assert seen and seen[0].splat_weight == 1 / 700
+    r.close()
+    f.write_text(text.replace("renderer { light passPhotons 700 }", ""))
+    sc2 = load_scene(f)
+    assert sc2.pass_photons == 0
+    r2 = renderer_for(sc2, context_cls=EmuContext); assert isinstance(r2, CudaRenderer); r2.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", SCENES)
 def test_gpu_light_tracer_matches_oracle(name):
