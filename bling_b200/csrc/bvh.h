@@ -54,16 +54,30 @@ HD int mkRef(bool shape, int kind, uint32_t index) { return (int)((shape ? 0x800
 #ifndef BL_ITEM_F4
 #define BL_ITEM_F4 4     // F4 per leaf item (64 B); 3 = the packed 48-byte records of round 1 (A/B builds only)
 #endif
+#ifndef BL_L2_POLICY
+#define BL_L2_POLICY 0   // A/B: bit 0 = leaf items with L2 evict_first (640 MB, little reuse), bit 1 = nodes with L2 evict_last
+#endif
 #if defined(__CUDACC__)
 __device__ __forceinline__ void ld8(const F4 *p, F4 &a, F4 &b) {   // one 32-byte load (LDG.E.256 on sm_100)
    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
 }
+// the same with an L2 eviction policy (the policy is a pure value: the compiler hoists its creation out of the loop)
+template <bool LAST>
+__device__ __forceinline__ void ld8Policy(const F4 *p, F4 &a, F4 &b) {
+   unsigned long long pol;
+   if (LAST) asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+   else asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+   asm volatile("ld.global.nc.L2::cache_hint.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p), "l"(pol));
+}
 #endif
 HD void ldItem(const F4 *items, int item, F4 &q0, F4 &q1, F4 &q2) {
    const F4 *p = items + (size_t)BL_ITEM_F4 * (size_t)item;
 #if defined(__CUDA_ARCH__) && BL_ITEM_F4 == 4
-   F4 q3; ld8(p, q0, q1); ld8(p + 2, q2, q3);
+   F4 q3;
+   if (BL_L2_POLICY & 1) { ld8Policy<false>(p, q0, q1); ld8Policy<false>(p + 2, q2, q3); }
+   else { ld8(p, q0, q1); ld8(p + 2, q2, q3); }
 #else
    q0 = ld4(p); q1 = ld4(p + 1); q2 = ld4(p + 2);
 #endif

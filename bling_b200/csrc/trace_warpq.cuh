@@ -139,7 +139,8 @@ __global__ void __launch_bounds__(TR_THREADS, (ANY && !FUSE) ? TR_MINBLOCKS + 1 
          if (STATS) stN++;
          const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
          F4 n0, n1, n2, n3;
-         ld8(np, n0, n1); ld8(np + 2, n2, n3);
+         if (BL_L2_POLICY & 2) { ld8Policy<true>(np, n0, n1); ld8Policy<true>(np + 2, n2, n3); }
+         else { ld8(np, n0, n1); ld8(np + 2, n2, n3); }
          float tn[4];
          node4Near<!SORTED>(n0, n2, n3, r, pre, tn);   // unsorted (any-hit): tn = minus the length of the ray inside the child
          int c[4] = {f2i(n1.x), f2i(n1.y), f2i(n1.z), f2i(n1.w)};

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Writes profiles/r02_trace_source_view.md: the per-instruction view of the traversal kernels (ncu source pages kept under
 profiles/*.source.csv.gz, tables by tools/ncu_source_regions.py), the ncu comparison of the two any-hit child orders
-(profiles/r02_any_slot.raw.csv / r02_any_longest.raw.csv) and the A/B log of the second half of round 2.
+(profiles/r02_any_slot.raw.csv.gz / r02_any_longest.raw.csv.gz) and the A/B log of the second half of round 2.
 usage: tools/make_r02_source_view.py"""
 import csv
 import subprocess
@@ -30,7 +30,8 @@ ORDER_METRICS = [
 
 def order_table():
     def load(f):
-        rows = list(csv.reader(open(P / f)))
+        import gzip, io
+        rows = list(csv.reader(io.TextIOWrapper(gzip.open(P / (f + ".gz"), "rb"))))
         return [dict(zip(rows[0], r)) for r in rows[2:]]
     a, b = load("r02_any_slot.raw.csv"), load("r02_any_longest.raw.csv")
     out = ["| metric | launch 1: slot order | launch 1: longest first | launch 2: slot order | launch 2: longest first |", "|---|---|---|---|---|"]
@@ -98,7 +99,7 @@ have the worse L2 hit rate, section 3):
 orders all visit the same number of nodes; entering the child with the largest `tfar - tnear` first visits 15 % fewer. Built as
 three compares on `node4Near<OVERLAP>`'s keys (+8 instructions per node step, 56 registers kept). The kernel's own counters over
 a cfg-5 step: **40.39 -> 35.53 node visits, 13.54 -> 12.93 primitive tests per any-hit ray**; algorithmic bytes per ray 3485 -> 3134.
-ncu on the same two launches with both builds (`r02_any_slot.raw.csv`, `r02_any_longest.raw.csv`, `tools/gpu_r02_k.sh`):
+ncu on the same two launches with both builds (`r02_any_slot.raw.csv.gz`, `r02_any_longest.raw.csv.gz`, `tools/gpu_r02_k.sh`):
 
 @ORDER@
 
@@ -121,6 +122,7 @@ honest algorithmic-bytes roofline does when work is removed without a matching g
 | L1 prefetch of the next trip's node right after the pop (~100 instructions ahead of its use) | `TQ_PREFETCH=4`, `tools/gpu_r02_p.sh` | 588 / 626 -> 636 / 668 |
 | the same, both sectors | `TQ_PREFETCH=12` | -> 875 / 917 |
 | rays reserved 32 at a time, one chunk ahead, `q[base + lane]` loaded once per chunk (refill = one shuffle + the ray load) | not kept; `tools/gpu_r02_m.sh` second run | 589 / 626 -> 602 / 680 (the extra warp-uniform state brought spill reloads back into the node step of the 56-register kernel) |
+| L2 eviction policies folded into the load descriptors: leaf items `evict_first` (640 MB, hardly reused), nodes `evict_last`, both | `BL_L2_POLICY=1/2/3`, `tools/gpu_r02_t.sh` | 584 / 621 -> 582 / 626, 585 / 620, 584 / 626: the L2 already keeps what is reused |
 | refill once 6 / 8 / 12 lanes are idle instead of 4 | `TR_REFILL`, `tools/gpu_r02_q.sh` | 589 / 628 -> **585 / 622** / 589 / 624 / 610 / 631: 6 is the product |
 | binning rays by origin cell and direction octant (upper bound: 4 M uniformly random rays, sorted on the host by Morton code) | `tools/trace_bench.py --sorted`, `tools/gpu_r02_r.sh` | nearest 781 -> 847 Mrays/s (+8 %), any 926 -> 964 (+4 %) for rays that start with NO order at all; the pipeline's queues are already pixel-ordered, and a device sort of 20-35 M keys per launch costs more than that |
 
