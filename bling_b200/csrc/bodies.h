@@ -592,5 +592,6 @@ struct EvalTextureBody {
 struct AddFilmBody { F4 *dst; const F4 *src; HD void operator()(uint32_t i) const { F4 a = dst[i], b = src[i]; a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; dst[i] = a; } };
 
 }  // namespace bl
-#include "lighttrace.h"   // the light tracer on the same kernels
+#include "lighttrace.h"
+#include "bidir.h"   // the light tracer on the same kernels
 #include "kdtree.h"   // the host's kd-tree as an alternative accelerator input (needs loadRay above)

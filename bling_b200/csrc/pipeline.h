@@ -66,7 +66,7 @@ struct Pipeline {
    void freeLt() { for (void *p : ltAllocs) be.free(p); ltAllocs.clear(); ltRec = LtRecords{}; ltCount = nullptr; }
    void freeKd() { for (void *p : kdAllocs) be.free(p); kdAllocs.clear(); kdUploaded = false; }
    void freeScene() { be.syncComm(); freeKd(); freeLt(); if (splat) { be.free(splat); splat = nullptr; } freeTraceScratch(); for (void *p : sceneAllocs) be.free(p); sceneAllocs.clear(); dscene = nullptr; if (film) { be.free(film); film = nullptr; } if (filmSum) { be.free(filmSum); filmSum = nullptr; } uploaded = false; }
-   void freeState() { for (void *p : stateAllocs) be.free(p); stateAllocs.clear(); ps = PathState{}; qSlotsAlloc = 0; rootAlloc = 0; }
+   void freeState() { for (void *p : stateAllocs) be.free(p); stateAllocs.clear(); ps = PathState{}; qSlotsAlloc = 0; rootAlloc = 0; bd = BdState{}; bdAlloc = 0; }
 
    int upload(const blingcu_scene *ir) {
       freeScene();
@@ -74,7 +74,8 @@ struct Pipeline {
       if (ir->width <= 0 || ir->height <= 0) return fail(BLINGCU_EINVAL, "bad image size");
       if (ir->nu <= 0 || ir->nv <= 0) return fail(BLINGCU_EINVAL, "bad sampler");
       if (ir->max_depth < 0 || ir->max_depth > 254) return fail(BLINGCU_EINVAL, "max_depth out of range");
-      if (ir->integrator_kind < BLINGCU_INTEGRATOR_PATH || ir->integrator_kind > BLINGCU_INTEGRATOR_NORMALS) return fail(BLINGCU_EINVAL, "unknown integrator");
+      if (ir->integrator_kind < BLINGCU_INTEGRATOR_PATH || ir->integrator_kind > BLINGCU_INTEGRATOR_BIDIR) return fail(BLINGCU_EINVAL, "unknown integrator");
+      if (ir->integrator_kind == BLINGCU_INTEGRATOR_BIDIR && (ir->max_depth < 1 || ir->max_depth > BL_BD_MAXDEPTH)) return fail(BLINGCU_EINVAL, "bidirectional integrator: max_depth out of range (1..16)");
       // maxDepth 0 has no meaning there: `cont` stops at d == md with d starting at 1 (DirectLighting.hs:47-49), i.e. never
       if (ir->integrator_kind == BLINGCU_INTEGRATOR_DIRECT && (ir->max_depth < 1 || ir->max_depth > 24)) return fail(BLINGCU_EINVAL, "direct lighting: max_depth out of range");
       size_t nt = (size_t)ir->n_triangles, ns = ir->n_shapes, nprim = nt + ns;
@@ -226,7 +227,9 @@ struct Pipeline {
       hs.integrator = ir->integrator_kind;
       const bool direct = hs.integrator == BLINGCU_INTEGRATOR_DIRECT;
       const bool normals = hs.integrator == BLINGCU_INTEGRATOR_NORMALS;   // sampleCount1D = sampleCount2D = 0 (Debug.hs:24)
-      hs.smp = mkSamplerConst(hs.nu, hs.nv, normals ? 0 : (direct ? 2 * hs.max_depth : 4 * hs.sample_depth), normals ? 0 : (direct ? 2 * hs.max_depth : 3 * hs.sample_depth),
+      const bool bidir = hs.integrator == BLINGCU_INTEGRATOR_BIDIR;       // s1d = smps1D * sd * 3 + 1, s2d = smps2D * sd * 3 + 2 (BidirPath.hs:44-48)
+      hs.smp = mkSamplerConst(hs.nu, hs.nv, normals ? 0 : (direct ? 2 * hs.max_depth : (bidir ? 12 * hs.sample_depth + 1 : 4 * hs.sample_depth)),
+                              normals ? 0 : (direct ? 2 * hs.max_depth : (bidir ? 9 * hs.sample_depth + 2 : 3 * hs.sample_depth)),
                               hs.sampler_kind == BLINGCU_SAMPLER_STRATIFIED);
       hs.smpUniform = mkSamplerConst(1, 1, 0, 0, 0);
       for (int k = 0; k < 3; ++k) { hs.bounds_lo[k] = nprim ? bo.scene_lo[k] : 0.0f; hs.bounds_hi[k] = nprim ? bo.scene_hi[k] : 0.0f; }
@@ -246,13 +249,22 @@ struct Pipeline {
    template <class T> T *st(size_t n) { T *p = (T *)be.alloc(sizeof(T) * n); stateAllocs.push_back(p); return p; }
    int qSlotsAlloc = 0;   // shade queues the state holds
    uint32_t rootAlloc = 0;   // entries of ps.root (cap for the direct-lighting integrator, 1 otherwise)
+   BdState bd = {};          // vertex records of the bidirectional integrator (bidir.h), allocated with the state when it is the integrator
+   int bdAlloc = 0;          // depth the records were allocated for
    int ensureState(uint32_t cap) {
       const uint32_t rootNeed = hs.integrator == BLINGCU_INTEGRATOR_DIRECT ? std::max(cap, ps.cap) : 1u;
-      if (ps.cap >= cap && qSlotsAlloc >= nSlots && rootAlloc >= rootNeed) return 0;
+      const int bdNeed = hs.integrator == BLINGCU_INTEGRATOR_BIDIR ? hs.max_depth : 0;
+      if (ps.cap >= cap && qSlotsAlloc >= nSlots && rootAlloc >= rootNeed && bdAlloc >= bdNeed) return 0;
       cap = std::max(cap, ps.cap);
       freeState();
-      ps.cap = cap; qSlotsAlloc = nSlots; rootAlloc = rootNeed;
+      ps.cap = cap; qSlotsAlloc = nSlots; rootAlloc = rootNeed; bdAlloc = bdNeed;
       size_t c = cap;
+      bd = BdState{};
+      if (bdNeed) {
+         const size_t v = 2 * (size_t)bdNeed * c;
+         bd.md = bdNeed; bd.vRay = st<F4>(2 * v); bd.vHit = st<F4>(v); bd.vWo = st<F4>(v); bd.vAlpha = st<F4>(4 * v);
+         bd.nVert = st<uint32_t>(2 * c); bd.D = st<F4>(4 * (size_t)bdNeed * c);
+      }
       ps.rayO = st<F4>(2 * c); ps.rayD = ps.rayO + 1; ps.hit = st<F4>(c);   // rays: one interleaved 32-byte record per slot (bodies.h::loadRay)
       ps.T = st<F4>(4 * c); ps.L = st<F4>(4 * c);
       ps.shO = st<F4>(2 * c); ps.shD = ps.shO + 1; ps.PS = st<F4>(4 * c); ps.occl = st<uint8_t>(c); ps.occlM = st<uint8_t>(c);
@@ -434,6 +446,42 @@ struct Pipeline {
       be.tag(BLINGCU_KC_SHADE); be.runQueue(NormalMapBody{dscene, ps}, ps.qA, ps.counters + C_ACTIVE, n);
       launches += 2;
    }
+   // bidirectional integrator (bidir.h): eye path with S0 / S1, light path, S1 weights, then every light vertex with every eye vertex
+   void bouncesBidir(uint32_t n) {
+      const int md = hs.max_depth;
+      const bool misNearest = hs.n_lights > 0;
+      be.zero(bd.D, sizeof(F4) * 4 * (size_t)md * ps.cap);
+      be.tag(BLINGCU_KC_OTHER); be.run(BdBeginBody{ps, bd}, n); launches++;
+      for (int side = 0; side < 2; ++side) {
+         uint32_t *qa = ps.qA, *qb = ps.qB;
+         if (side) { be.tag(BLINGCU_KC_RAYGEN); be.run(BdLightGenBody{dscene, ps, qa}, n); be.tag(BLINGCU_KC_OTHER); be.run(BdLightStartBody{ps, n}, 1); launches += 2; }
+         for (int d = 0; d < md; ++d) {
+            be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(qa, ps.counters + C_ACTIVE, n, dscene, ps.rayO, ps.rayD, ps.hit);
+            be.tag(BLINGCU_KC_SHADE); be.runQueue(BdVertexBody{dscene, ps, bd, qb, side, d}, qa, ps.counters + C_ACTIVE, n);
+            launches += 2;
+            if (!side) {   // estimateDirect of this eye vertex: the path integrator's queries, resolved into the depth's own plane
+               PathState pd = ps; pd.L = bd.D + (size_t)d * 4 * ps.cap;
+               be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(ps.qShadow, ps.counters + C_SHADOW, n, dscene, ps.shO, ps.shD, ps.occl); launches++;
+               if (hasInfinite && !hasBox) { be.traceAny(ps.qMisAny, ps.counters + C_MISANY, n, dscene, ps.miO, ps.miD, ps.occlM); launches++; }
+               if (misNearest) { be.tag(BLINGCU_KC_TRACE_NEAREST); be.traceNearest(ps.qMis, ps.counters + C_MIS, n, dscene, ps.miO, ps.miD, ps.mihit); launches++; }
+               be.tag(BLINGCU_KC_RESOLVE); be.runQueue(ResolveShadowBody{pd}, ps.qShadow, ps.counters + C_SHADOW, n); launches++;
+               if (misNearest) { be.runQueue(ResolveMisBody{dscene, pd}, ps.qMis, ps.counters + C_MIS, n); launches++; }
+               if (hasInfinite && !hasBox) { be.runQueue(ResolveMisAnyBody{dscene, pd}, ps.qMisAny, ps.counters + C_MISANY, n); launches++; }
+            }
+            be.tag(BLINGCU_KC_OTHER); be.run(AdvanceBody{ps}, 1); launches++;
+            uint32_t *t = qa; qa = qb; qb = t;
+         }
+      }
+      be.tag(BLINGCU_KC_RESOLVE); be.run(BdFinishBody{ps, bd}, n); launches++;
+      for (int s = 0; s < md; ++s)
+         for (int t = 0; t < md; ++t) {
+            be.tag(BLINGCU_KC_SHADE); be.run(BdConnectBody{dscene, ps, bd, s, t}, n);
+            be.tag(BLINGCU_KC_TRACE_ANY); be.traceAny(ps.qShadow, ps.counters + C_SHADOW, n, dscene, ps.shO, ps.shD, ps.occl);
+            be.tag(BLINGCU_KC_RESOLVE); be.runQueue(ResolveShadowBody{ps}, ps.qShadow, ps.counters + C_SHADOW, n);
+            be.tag(BLINGCU_KC_OTHER); be.run(AdvanceBody{ps}, 1);
+            launches += 4;
+         }
+   }
    // Slots for n camera samples of the direct-lighting integrator: every glass-like vertex spawns one extra slot. Starts at
    // 2 n and doubles when a batch reports C_OVERFLOW (the batch is then re-run: nothing has reached the film yet); 2^maxDepth n
    // always suffices.
@@ -471,7 +519,8 @@ struct Pipeline {
       uint32_t spp = (uint32_t)(hs.nu * hs.nv);
       if (sBegin > sEnd || sEnd > spp) return fail(BLINGCU_EINVAL, "sample range out of bounds");
       const bool direct = hs.integrator == BLINGCU_INTEGRATOR_DIRECT;
-      uint32_t kmax = std::max(1u, batchTarget / npix);
+      // the bidirectional integrator keeps 2 md vertex records per slot (~130 bytes each): smaller batches
+      uint32_t kmax = std::max(1u, (hs.integrator == BLINGCU_INTEGRATOR_BIDIR ? std::min(batchTarget, 1u << 21) : batchTarget) / npix);
       uint32_t need = std::min(kmax, std::max(1u, sEnd - sBegin)) * npix;
       if (!direct) ensureState(need);
       auto t0 = be.timerStart();
@@ -494,6 +543,7 @@ struct Pipeline {
             bouncesDirect(n);
             if (dlOverflowed()) { dlHeadroom *= 2; be.upload(ps.stats, statSnap, sizeof(statSnap)); launches = launchSnap; continue; }   // same batch again with twice the slots
          } else if (hs.integrator == BLINGCU_INTEGRATOR_NORMALS) bouncesNormals(n);
+         else if (hs.integrator == BLINGCU_INTEGRATOR_BIDIR) bouncesBidir(n);
          else bounces(n);
          be.waitReduced();   // a film reduction still in flight reads `film`: it has overlapped everything up to here
          be.tag(BLINGCU_KC_FILM); be.run(FinalizeBody{dscene, ps}, n);
@@ -520,6 +570,7 @@ struct Pipeline {
          be.run(BeginBatchBody{ps, (uint32_t)n}, 1);
          be.run(RaygenBody{dscene, ps, seed, pass, 0, npix, dpx, dpy, ds}, (uint32_t)n);
          if (hs.integrator == BLINGCU_INTEGRATOR_NORMALS) { bouncesNormals((uint32_t)n); break; }
+         if (hs.integrator == BLINGCU_INTEGRATOR_BIDIR) { bouncesBidir((uint32_t)n); break; }
          if (!direct) { bounces((uint32_t)n); break; }
          bouncesDirect((uint32_t)n);
          if (!dlOverflowed()) break;

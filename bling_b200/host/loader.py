@@ -646,6 +646,7 @@ class Loader:
             tk.expect("integrator"); tk.expect("{"); ik = tk.next()
             if ik == "path": integ = ("path", tk.named_int("maxDepth"), tk.named_int("sampleDepth"))
             elif ik == "directLighting": integ = ("directLighting", tk.named_int("maxDepth"), 0)   # IntegratorParser: mkDirectLightingIntegrator md
+            elif ik == "bidir": integ = ("bidir", tk.named_int("maxDepth"), tk.named_int("sampleDepth"))   # IntegratorParser: mkBidirPathIntegrator md sd
             elif ik == "debug":               # IntegratorParser.hs:27-35: kdtree and reference are `undefined` in Debug.hs
                 dt = tk.next()
                 if dt != "normals": raise NotImplementedError(f"debug integrator {dt} (undefined in the reference, Integrator/Debug.hs:19-21,35-36)")
@@ -720,7 +721,7 @@ class Loader:
         smp = st.renderer["sampler"]; integ = st.renderer["integrator"]
         ir.sampler_kind = IR.SAMPLER_STRATIFIED if smp[0] == "stratified" else IR.SAMPLER_RANDOM
         ir.nu, ir.nv = smp[1], smp[2]; ir.max_depth, ir.sample_depth = integ[1], integ[2]
-        ir.integrator_kind = {"directLighting": IR.INTEGRATOR_DIRECT, "normals": IR.INTEGRATOR_NORMALS}.get(integ[0], IR.INTEGRATOR_PATH)
+        ir.integrator_kind = {"directLighting": IR.INTEGRATOR_DIRECT, "normals": IR.INTEGRATOR_NORMALS, "bidir": IR.INTEGRATOR_BIDIR}.get(integ[0], IR.INTEGRATOR_PATH)
         ir.cie_x, ir.cie_y, ir.cie_z, ir.cie_y_sum = S.CIE_X, S.CIE_Y, S.CIE_Z, float(S.CIE_Y_SUM)
         ir.illum_basis = np.stack(S.ILLUM).astype(F)
         ir.refl_basis = np.stack(S.REFL).astype(F)

@@ -22,7 +22,7 @@ LIGHT_INFINITE, LIGHT_DIRECTIONAL, LIGHT_POINT, LIGHT_AREA = range(4)
 ENV_CONSTANT, ENV_RGBTABLE, ENV_SUNSKY = range(3)
 CAM_PERSPECTIVE, CAM_ENVIRONMENT = range(2)
 SAMPLER_STRATIFIED, SAMPLER_RANDOM = range(2)
-INTEGRATOR_PATH, INTEGRATOR_DIRECT, INTEGRATOR_NORMALS = range(3)
+INTEGRATOR_PATH, INTEGRATOR_DIRECT, INTEGRATOR_NORMALS, INTEGRATOR_BIDIR = range(4)
 
 f32 = C.c_float
 i32 = C.c_int32

@@ -115,7 +115,8 @@ enum { BLINGCU_CAM_PERSPECTIVE = 0, BLINGCU_CAM_ENVIRONMENT = 1 };
 enum { BLINGCU_SAMPLER_STRATIFIED = 0, BLINGCU_SAMPLER_RANDOM = 1 };
 /* Integrator/Path.hs:30-39 (max_depth, sample_depth) and, SURVEY §8(f)4, Integrator/DirectLighting.hs:13-21 (max_depth) */
 enum { BLINGCU_INTEGRATOR_PATH = 0, BLINGCU_INTEGRATOR_DIRECT = 1,
-       BLINGCU_INTEGRATOR_NORMALS = 2 /* `debug normals`: mkNormalMap (Integrator/Debug.hs:23-33), needs refl_basis */ };
+       BLINGCU_INTEGRATOR_NORMALS = 2 /* `debug normals`: mkNormalMap (Integrator/Debug.hs:23-33), needs refl_basis */,
+       BLINGCU_INTEGRATOR_BIDIR = 3 /* `bidir maxDepth sampleDepth`: mkBidirPathIntegrator (Integrator/BidirPath.hs:44-104) */ };
 
 typedef struct blingcu_spectrum { float v[BLINGCU_BANDS]; } blingcu_spectrum;
 

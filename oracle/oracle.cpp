@@ -475,11 +475,13 @@ static SampleCtx mkSampleCtx(const Scene &sc, const Window &ext, uint64_t seed, 
    SampleCtx c;
    c.kp = pixelKey(seed, pass, pix); c.s = s; c.nu = sc.nu; c.nv = sc.nv;
    if (sc.integrator == BLINGCU_INTEGRATOR_DIRECT) { c.n1d = 2 * sc.maxDepth; c.n2d = 2 * sc.maxDepth; }   // DirectLighting.hs:18-19
+   else if (sc.integrator == BLINGCU_INTEGRATOR_BIDIR) { c.n1d = 4 * sc.sampleDepth * 3 + 1; c.n2d = 3 * sc.sampleDepth * 3 + 2; }   // BidirPath.hs:44-48
    else if (sc.integrator == BLINGCU_INTEGRATOR_NORMALS) { c.n1d = 0; c.n2d = 0; }                            // Debug.hs:24
    else { c.n1d = 4 * sc.sampleDepth; c.n2d = 3 * sc.sampleDepth; }
    c.stratified = sc.samplerKind == BLINGCU_SAMPLER_STRATIFIED;
    return c;
 }
+static Spec bidirLi(const Scene &sc, const SampleCtx &smp, const Ray &r, RayCounters &rc);
 // one iteration of the `tile` body (Rendering.hs:142-150): fireRay >>= surfaceLi, then the camera sample position
 static Spec renderSample(const Scene &sc, const Window &ext, uint64_t seed, uint32_t pass, int ix, int iy, uint32_t s,
                          float &sx, float &sy, RayCounters &rc) {
@@ -488,6 +490,7 @@ static Spec renderSample(const Scene &sc, const Window &ext, uint64_t seed, uint
    sx = (float)ix + ox; sy = (float)iy + oy;
    Ray r = fireRay(sc, sx, sy, lu, lv);
    if (sc.integrator == BLINGCU_INTEGRATOR_DIRECT) { rc.cam++; return directLighting(sc, c, 0, r, rc); }
+   if (sc.integrator == BLINGCU_INTEGRATOR_BIDIR) return bidirLi(sc, c, r, rc);
    if (sc.integrator == BLINGCU_INTEGRATOR_NORMALS) {   // mkNormalMap (Integrator/Debug.hs:23-33)
       rc.cam++;
       Hit hit = sceneIntersect(sc, r);
@@ -560,6 +563,115 @@ static LightRay sampleLightRay(const Scene &sc, float uL, float uo1, float uo2, 
    r.pdf = r.pdf / (float)lc;
    return r;
 }
+// ----------------------------------------------------------------------------- Integrator/BidirPath.hs
+// sampleOneLight (Scene.hs:110-118) as estimateDirect of BidirPath.hs:151-164 calls it (the path integrator has it inline)
+static Spec sampleOneLight(const Scene &sc, V3 p, float eps, V3 n, V3 wo, const Bsdf &bsdf, float lNumU, float lDir1, float lDir2,
+                           float bCompU, float bDir1, float bDir2, RayCounters &rc) {
+   int lc = (int)sc.lights.size();
+   if (lc == 0) return sConst(0);
+   int ln = (lc == 1) ? 0 : std::min((int)std::floor(lNumU * (float)lc), lc - 1);
+   const blingcu_light &lt = sc.lights[ln];
+   Spec ls = sampleLightMis(sc, lightSample(sc, lt, p, eps, n, lDir1, lDir2), bsdf, wo, rc);
+   Spec bs = sampleBsdfMis(sc, ln, sampleBsdf(bsdf, wo, bCompU, bDir1, bDir2), p, eps, rc);
+   Spec direct = ls + bs;
+   if (lc > 1) direct = sScale(direct, (float)lc);
+   return direct;
+}
+struct BdVertex { V3 wi, wo; Hit hit; int type; Spec alpha; };   // data Vertex (:20-26)
+// nextVertex (:184-214). f1d d = base1 + smps1D * d * 3, f2d d = base2 + smps2D * d * 3 (smps1D = 4, smps2D = 3, :30-34). rrProb = 1
+// (:203), so the roulette never ends a path; the hit behind the LAST vertex (depth + 1 == md) decides nothing and is not traced.
+static std::vector<BdVertex> bdNextVertex(const Scene &sc, bool adj, V3 wi, Hit hit, Spec alpha, int base1, int base2,
+                                          const SampleCtx &smp, RayCounters &rc) {
+   std::vector<BdVertex> path;
+   for (int depth = 0;; ++depth) {
+      if (!hit.valid) break;                 // :186
+      if (depth == sc.maxDepth) break;       // :188
+      float ubc = rnd1D(smp, base1 + 12 * depth);
+      float ub1, ub2; rnd2D(smp, base2 + 9 * depth, ub1, ub2);
+      float rr = rnd1D(smp, 1 + base1 + 12 * depth);
+      Bsdf bsdf = makeBsdf(sc, hit);
+      BsdfSample bs = adj ? sampleAdjBsdf(bsdf, wi, ubc, ub1, ub2) : sampleBsdf(bsdf, wi, ubc, ub1, ub2);
+      path.push_back(BdVertex{wi, bs.wi, hit, bs.type, alpha});
+      if (isBlack(bs.f) || bs.pdf == 0) break;   // :209-211
+      const float rrProb = 1;
+      if (rr > rrProb) break;
+      alpha = sScale(bs.f * alpha, 1 / rrProb);
+      if (depth + 1 == sc.maxDepth) break;
+      rc.ext++;
+      hit = sceneIntersect(sc, Ray{bsdf.p, bs.wi, hit.eps, kInf});
+      wi = -bs.wi;
+   }
+   return path;
+}
+// contrib False md (:50-104). The reference's `connect` (:124-149) is called with the LIGHT vertex first and binds the second
+// field of each vertex (the SAMPLED direction _vwo) where its names say wi: restated as written, not as meant.
+static Spec bidirLi(const Scene &sc, const SampleCtx &smp, const Ray &r, RayCounters &rc) {
+   float ul = rnd1D(smp, 0), ulo1, ulo2, uld1, uld2; rnd2D(smp, 0, ulo1, ulo2); rnd2D(smp, 1, uld1, uld2);
+   // lightPath (:175-182)
+   LightRay lr = sampleLightRay(sc, ul, ulo1, ulo2, uld1, uld2);
+   V3 lwo = -lr.ray.d;
+   Spec li = sScale(lr.li, absDot(lr.nl, lwo) / lr.pdf);
+   rc.ext++;
+   std::vector<BdVertex> lp = bdNextVertex(sc, true, lwo, sceneIntersect(sc, lr.ray), li, 3 + 1, 3 + 2, smp, rc);
+   // eyePath (:168-172)
+   rc.cam++;
+   std::vector<BdVertex> ep = bdNextVertex(sc, false, -r.d, sceneIntersect(sc, r), sConst(1), 2 + 1, 2 + 2, smp, rc);
+   // countSpec (:111-122)
+   std::vector<float> nspec(ep.size() + lp.size() + 2, 0.0f);
+   for (size_t i = 0; i < ep.size(); ++i)
+      for (size_t j = 0; j < lp.size(); ++j)
+         if ((ep[i].type & BX_SPECULAR) || (lp[j].type & BX_SPECULAR)) nspec[i + j + 2] += 1;
+   // S1 subpaths (:69-72): estimateDirect (:151-164) at every eye vertex
+   Spec ld = sConst(0);
+   for (size_t i = 0; i < ep.size(); ++i) {
+      const BdVertex &v = ep[i]; const int depth = (int)i;
+      float lNumU = rnd1D(smp, 0 + 1 + 12 * depth);
+      float lDir1, lDir2; rnd2D(smp, 0 + 2 + 9 * depth, lDir1, lDir2);
+      float bCompU = rnd1D(smp, 1 + 1 + 12 * depth);
+      float bDir1, bDir2; rnd2D(smp, 1 + 2 + 9 * depth, bDir1, bDir2);
+      Bsdf bsdf = makeBsdf(sc, v.hit);
+      Spec lHere = sampleOneLight(sc, bsdf.p, v.hit.eps, bsdf.cs.n, v.wi, bsdf, lNumU, lDir1, lDir2, bCompU, bDir1, bDir2, rc);
+      Spec d = lHere * v.alpha;
+      ld = ld + sScale(d, 1 / (1 + (float)i - nspec[i + 1]));
+   }
+   // S0 subpaths (:79-83): emitters seen directly or through specular bounces; intLe is asked for the SAMPLED direction _vwo
+   Spec le = sConst(0);
+   for (size_t i = 0; i < ep.size(); ++i) {
+      bool prevSpec = (i == 0) ? true : (ep[i - 1].type & BX_SPECULAR) != 0;
+      if (prevSpec) le = le + ep[i].alpha * intLe(sc, ep[i].hit, ep[i].wo);
+   }
+   if (ep.empty() || lp.empty()) return ld + le;
+   // connections (:91-93, :124-149)
+   Spec l = sConst(0);
+   for (size_t s_ = 0; s_ < lp.size(); ++s_) {
+      Spec row = sConst(0);
+      for (size_t t_ = 0; t_ < ep.size(); ++t_) {
+         const BdVertex &a = lp[s_], &b = ep[t_];   // a plays the pattern's "eye vertex" (i = s), b its "light vertex" (j = t)
+         Spec c = sConst(0);
+         if (!(a.type & BX_SPECULAR) && !(b.type & BX_SPECULAR)) {
+            Bsdf bsdfe = makeBsdf(sc, a.hit), bsdfl = makeBsdf(sc, b.hit);
+            V3 pe = bsdfe.p, pl = bsdfl.p;
+            V3 d = pl - pe;
+            float wl = 0; V3 w = d;                           // normLen (Math.hs:356-363)
+            if (sqLen(d) != 0) { wl = len(d); w = scl(1 / wl, d); }
+            float g = 1 / sqLen(d);
+            Spec fe = evalBsdf(bsdfe, a.wo, w);
+            Spec fl = evalAdjBsdf(bsdfl, b.wo, -w);
+            if (!(isBlack(fe) || isBlack(fl))) {
+               rc.shadow++;
+               if (!sceneOccluded(sc, Ray{pe, w, a.hit.eps, wl - b.hit.eps})) {
+                  float pathWt = 1 / ((float)(s_ + t_ + 2) - nspec[s_ + t_ + 2]);
+                  c = sScale(a.alpha * fe * b.alpha * fl, g * pathWt);
+               }
+            }
+         }
+         row = row + c;
+      }
+      l = l + row;
+   }
+   return ld + le + l;
+}
+
 // sampleCam (Camera.hs:78-103), projective cameras only (the reference `error`s otherwise)
 struct CamSample { V3 pLens; float px, py, pdf; };
 static CamSample sampleCam(const Scene &sc, V3 p) {
