@@ -651,6 +651,7 @@ class Loader:
                 dt = tk.next()
                 if dt != "normals": raise NotImplementedError(f"debug integrator {dt} (undefined in the reference, Integrator/Debug.hs:19-21,35-36)")
                 integ = ("normals", 0, 0)
+            elif ik == "bidirnod": raise NotImplementedError("integrator bidirnod: `contrib True` is `undefined` in the reference (Integrator/BidirPath.hs:63-65)")
             else: raise NotImplementedError(f"integrator {ik} (outside SURVEY §8)")
             tk.expect("}"); tk.expect("}"); tk.expect("}")
             self.st.renderer = dict(kind="sampler", sampler=smp, integrator=integ)
