@@ -242,6 +242,8 @@ struct BvhBuildInput {
    const float *hi;      // n*3
    int max_leaf;         // 1..15
    int threads;
+   float trav_cost = 0;  // cost of visiting a node in units of one primitive test (SAH termination for ranges of <= 15 items); 0 = split whenever it lowers the test count
+   int force_leaf = 1;   // 1: a range of <= max_leaf items always becomes a leaf (round 1); 0: the SAH decides there too
 };
 struct BvhBuildOutput {
    F4 *nodes;            // malloc'ed, BL_NODE_F4*n_nodes (4-wide nodes)

@@ -38,6 +38,8 @@ struct Builder {
    std::atomic<int> nextNode{0};
    int maxLeaf;
    int parLevels;
+   float travCost = 0;
+   bool forceLeaf = true;
 
    int allocNode() { return nextNode.fetch_add(1); }
 
@@ -47,7 +49,7 @@ struct Builder {
       box.reset();
       Box cb; cb.reset();
       for (size_t i = b; i < e; ++i) { box.grow(items[i].lo, items[i].hi); cb.growP(items[i].c); }
-      if ((int)n <= maxLeaf) return ~(int)((b << 4) | n);
+      if ((int)n <= maxLeaf && (forceLeaf || n <= 1)) return ~(int)((b << 4) | n);
       size_t mid = 0;
       bool done = false;
       if (depth < 32) {
@@ -74,7 +76,7 @@ struct Builder {
             }
          }
          float leafCost = box.area() * (float)n;
-         if (bestAxis >= 0 && (bestCost < leafCost || (int)n > 15)) {
+         if (bestAxis >= 0 && (bestCost + travCost * box.area() < leafCost || (int)n > 15)) {
             float cmin = cb.lo[bestAxis], scale = NBINS / (cb.hi[bestAxis] - cb.lo[bestAxis]);
             auto it = std::partition(items.begin() + b, items.begin() + e, [&](const Item &x) {
                int k = std::min(NBINS - 1, std::max(0, (int)((x.c[bestAxis] - cmin) * scale)));
@@ -139,6 +141,7 @@ int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
       it.id = (uint32_t)i;
    }
    B.maxLeaf = std::min(15, std::max(1, in.max_leaf));
+   B.travCost = in.trav_cost; B.forceLeaf = in.force_leaf != 0;
    int th = std::max(1, in.threads);
    B.parLevels = 0; while ((1 << B.parLevels) < th) B.parLevels++;
    B.parLevels += 1;

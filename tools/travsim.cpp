@@ -409,6 +409,8 @@ int main(int argc, char **argv) {
    for (size_t i = 0; i < ntris; ++i) { Item &it = B.items[i]; for (int k = 0; k < 3; ++k) { it.lo[k] = lo[3 * i + k] - eps; it.hi[k] = hi[3 * i + k] + eps; it.c[k] = 0.5f * (lo[3 * i + k] + hi[3 * i + k]); } it.id = (uint32_t)i; }
    const int maxLeaf = getenv("MAXLEAF") ? atoi(getenv("MAXLEAF")) : 2;
    B.maxLeaf = maxLeaf; B.parLevels = 4;
+   if (getenv("TRAVCOST")) B.travCost = (float)atof(getenv("TRAVCOST"));      // SAH termination with a node-visit cost (bvh.h::BvhBuildInput)
+   if (getenv("FORCELEAF")) B.forceLeaf = atoi(getenv("FORCELEAF")) != 0;
    B.nodes = (F4 *)std::malloc(sizeof(F4) * 4 * (ntris + 1));
    Box rb; int root2 = B.build(0, ntris, 0, rb);
    gItems.resize(ntris); for (size_t i = 0; i < ntris; ++i) gItems[i] = tris[B.items[i].id];
