@@ -134,7 +134,39 @@ light { point intensity rgbI 30 30 30 position 0 2 0 }
     assert fo[..., 1:].max() > 0 and np.allclose(fo, fe, rtol=2e-5, atol=1e-7)
 
 
+def _check_fuzz(make_ctx, seed, tmp_path, tol, frac):
+    """the random scenes of tests/test_fuzz_scenes.py (every shape, material, texture and light kind, ill-conditioned glossy
+    parameters included) under the bidirectional integrator: the same samples are lost to NaN / infinity, the rest agree"""
+    from tests.test_fuzz_scenes import parse, random_scene_text
+    f = tmp_path / f"fuzz{seed}.bling"; f.write_text(random_scene_text(seed))
+    try:
+        sc = parse(f)
+    except NotImplementedError as ex:
+        pytest.skip(str(ex))
+    sc = bidir(sc, max_depth=1 + seed % 4, sample_depth=2)
+    o = Oracle(sc); c = make_ctx(); c.upload_scene(sc)
+    px, py, s = _samples(o, sc, 600, 1000 + seed)
+    Lo, _ = o.render_samples(1, 17 + seed, px, py, s); Lc, _ = c.render_samples(1, 17 + seed, px, py, s)
+    c.close(); o.close()
+    fo, fc = np.isfinite(Lo).all(1), np.isfinite(Lc).all(1)
+    assert (fo != fc).mean() <= 1 - frac, (seed, int((fo != fc).sum()))
+    both = fo & fc
+    rel = np.abs(Lo - Lc)[both].max(1) / (np.abs(Lo[both]).max(1) + 1e-6)
+    assert (rel < tol).mean() >= frac, (seed, rel.max(), int((rel >= tol).sum()))
+
+
+@pytest.mark.parametrize("seed", range(100, 130))
+def test_emulated_bidir_on_random_scenes(seed, tmp_path):
+    _check_fuzz(EmuContext, seed, tmp_path, 1e-4, 1.0)
+
+
 # ----------------------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(100, 112))
+def test_gpu_bidir_on_random_scenes(seed, tmp_path):
+    _check_fuzz(lambda: api.Context(0), seed, tmp_path, 1e-3, 0.99)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", SCENES)
 def test_gpu_bidir_samples_match_oracle(name):
