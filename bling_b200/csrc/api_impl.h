@@ -165,6 +165,7 @@ static thread_local std::string g_createError;
       if (k == "batch_samples") { if (!(v >= 1) || v > 2147483648.0) return BLINGCU_EINVAL; c->p.batchTarget = (uint32_t)v; return 0; }                  \
       if (k == "bvh_leaf") { if (v < 1 || v > 15) return BLINGCU_EINVAL; c->p.maxLeaf = (int)v; return 0; }                       \
       if (k == "bvh_trav_cost") { if (!(v >= 0 && v <= 64)) return BLINGCU_EINVAL; c->p.bvhTravCost = (float)v; return 0; }         \
+      if (k == "bvh_collapse_cp") { if (!(v >= 0 && v <= 64)) return BLINGCU_EINVAL; c->p.bvhCollapseCp = (float)v; return 0; }      \
       if (k == "bvh_force_leaf") { c->p.bvhForceLeaf = v != 0 ? 1 : 0; return 0; }                                               \
       if (k == "fuse_resolve") { c->p.fuseResolveOpt = v < 0 ? -1 : (v > 0 ? 1 : 0); return 0; }                                  \
       if (c->p.be.setOption(k, v)) return 0;                                                                                     \

@@ -9,12 +9,14 @@
 //   F4[0] = (P.x P.y P.z  E)      grid origin (f32) and the three grid exponents packed as biased float exponents
 //                                  (E = ex | ey << 8 | ez << 16, cell size 2^(e-127) per axis)
 //   F4[1] = child refs [0..3]      ref >= 0: node index. ref < 0: leaf, ~ref = (first_item << 4) | count
-//   F4[2] = (qlo.x qlo.y qlo.z qhi.x), F4[3] = (qhi.y qhi.z 0x4B000000 -)   each q word packs the byte of the four children
+//   F4[2] = (qlo.x qlo.y qlo.z qhi.x), F4[3] = (qhi.y qhi.z 0x47000000 -)   each q word packs the byte of the four children
 // Dequantised plane = P + cell * q. The ray/plane distance is ONE fma per plane: q_as_float * (cell/d) + (P/d - o/d),
-// with q_as_float built by a byte permute into the mantissa of 2^23 (bits 0x4B000000 | q) and the 2^23 folded into
-// the addend; that folding costs up to half a cell of accuracy, so the builder rounds every bound outwards by one
-// extra cell (and keeps bytes 0 and 255 free for it). Unused child slots carry qlo = 255 > qhi = 0, which the
-// direction-sign based near/far selection rejects on its own. Why quantise: ncu showed the LSU data pipe as the
+// with q_as_float built by a byte permute into the mantissa of 2^15 (bits 0x47000000 | q << 8 = 32768 + q exactly) and the
+// 2^15 folded into the addend. The folded addend is rounded at the magnitude of 2^15 cells, i.e. to 1/512 of a cell, so the
+// builder moves every bound out by 1/64 of a cell before it rounds to the grid. (Until the end of round 2 the byte went into
+// the LOW mantissa byte of 2^23; that addend is rounded to HALF a cell and every bound carried one extra cell per side, which
+// cost 3-5 % node visits and 5 % primitive tests on the cfg-5 ray streams: tools/travsim.cpp, QPAD.) Unused child slots
+// carry qlo = 255 > qhi = 0, which the direction-sign based near/far selection rejects on its own. Why quantise: ncu showed the LSU data pipe as the
 // limiter with 128-byte nodes (one L1 wavefront per lane per 16 bytes); 64-byte nodes halve it and halve the
 // L2/DRAM bytes per visit. The builder (bvh_build.cpp) builds a binned-SAH binary tree, collapses it into 4-wide
 // nodes by repeatedly opening the child with the largest area, then quantises.
@@ -127,14 +129,16 @@ HD RayPre rayPre(const Ray &r) { RayPre p; p.idir = mk3(safeInv(r.d.x), safeInv(
 
 HD uint32_t f2u(float f) { return (uint32_t)f2i(f); }
 HD float u2f(uint32_t u) { return i2f((int)u); }
-// float with bits 0x4B000000 | byte k of w  ==  2^23 + q   (one PRMT on the device)
+// float with bits 0x47000000 | (byte k of w) << 8  ==  2^15 + q   (one PRMT on the device)
+#define BL_QMAGIC 0x47000000u     // 32768.0f
+#define BL_QBIAS 32768.0f
 #if defined(__CUDA_ARCH__)
-// the 2^23 pattern comes from the node itself (word F4[3].z, written by the builder) so that it sits in a register and
+// the 2^15 pattern comes from the node itself (word F4[3].z, written by the builder) so that it sits in a register and
 // the byte selector can be the PRMT's immediate; as a literal it would take the immediate slot and every PRMT would
 // need a MOV of its selector first
-#define BL_QF(w, k) __uint_as_float(__byte_perm((w), bl_k23, 0x7650u + (k)))
+#define BL_QF(w, k) __uint_as_float(__byte_perm((w), bl_k23, 0x7604u + ((k) << 4)))
 #else
-#define BL_QF(w, k) u2f(0x4B000000u | (((w) >> (8 * (k))) & 0xffu))
+#define BL_QF(w, k) u2f(BL_QMAGIC | ((((w) >> (8 * (k))) & 0xffu) << 8))
 #endif
 
 // slab test of the four children of one quantised node against [r.tmin, r.tmax]: tn[k] = entry distance of child k,
@@ -144,14 +148,14 @@ HD float u2f(uint32_t u) { return i2f((int)u); }
 template <bool OVERLAP = false>
 HD void node4Near(const F4 &n0, const F4 &n2, const F4 &n3, const Ray &r, const RayPre &p, float tnear[4]) {
 #if defined(__CUDA_ARCH__)
-   const uint32_t bl_k23 = f2u(n3.z);   // 0x4B000000
+   const uint32_t bl_k23 = f2u(n3.z);   // BL_QMAGIC
 #endif
    const uint32_t E = f2u(n0.w);
    const float ax = u2f((E & 0xffu) << 23) * p.idir.x, ay = u2f(((E >> 8) & 0xffu) << 23) * p.idir.y, az = u2f(((E >> 16) & 0xffu) << 23) * p.idir.z;
-   // addend: (P - o)/d - 2^23 * cell/d
-   const float bx = BL_FMA(-8388608.0f, ax, (n0.x - r.o.x) * p.idir.x);
-   const float by = BL_FMA(-8388608.0f, ay, (n0.y - r.o.y) * p.idir.y);
-   const float bz = BL_FMA(-8388608.0f, az, (n0.z - r.o.z) * p.idir.z);
+   // addend: (P - o)/d - 2^15 * cell/d
+   const float bx = BL_FMA(-BL_QBIAS, ax, (n0.x - r.o.x) * p.idir.x);
+   const float by = BL_FMA(-BL_QBIAS, ay, (n0.y - r.o.y) * p.idir.y);
+   const float bz = BL_FMA(-BL_QBIAS, az, (n0.z - r.o.z) * p.idir.z);
    const uint32_t qlx = f2u(n2.x), qly = f2u(n2.y), qlz = f2u(n2.z), qhx = f2u(n2.w), qhy = f2u(n3.x), qhz = f2u(n3.y);
    const bool px = p.idir.x >= 0.0f, py = p.idir.y >= 0.0f, pz = p.idir.z >= 0.0f;
    const uint32_t nx = px ? qlx : qhx, fx = px ? qhx : qlx, ny = py ? qly : qhy, fy = py ? qhy : qly, nz = pz ? qlz : qhz, fz = pz ? qhz : qlz;
@@ -244,6 +248,7 @@ struct BvhBuildInput {
    int threads;
    float trav_cost = 0;  // cost of visiting a node in units of one primitive test (SAH termination for ranges of <= 15 items); 0 = split whenever it lowers the test count
    int force_leaf = 1;   // 1: a range of <= max_leaf items always becomes a leaf (round 1); 0: the SAH decides there too
+   float collapse_cp = 0; // > 0: SAH-optimal collapse (bvh_build.cpp::Collapse) with a primitive test costing collapse_cp node visits; 0: greedy collapse over leaves of <= max_leaf items
 };
 struct BvhBuildOutput {
    F4 *nodes;            // malloc'ed, BL_NODE_F4*n_nodes (4-wide nodes)

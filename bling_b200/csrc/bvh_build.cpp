@@ -2,6 +2,12 @@
 // mkKdTree/buildTree (KdTree.hs:107-203) for the GPU path; the tree shape is free to differ because the
 // traversal result (globally nearest hit) does not depend on it.
 //
+// Collapse (round 2, second half): the binary tree is built down to single items and a dynamic programme over it decides, per
+// subtree, whether it becomes one leaf (<= max_leaf items, cost = area * items * collapse_cp), one 4-wide node (cost = area + its
+// children) or is dissolved into 2 / 3 slots of its parent -- the SAH-optimal collapse of Ylitie, Karras, Laine 2017 (section 3.1)
+// restated for 4 slots. tools/travsim.cpp on the cfg-5 ray streams: same node visits as "open the largest child" over 2-item leaves,
+// a quarter to a third fewer primitive tests, fewer nodes in memory. collapse_cp = 0 keeps the greedy collapse of round 1.
+//
 // Item boxes are inflated by eps = 4e-6 * scene extent (+ 1e-30) on every side before they are merged, so the
 // slab test in bvh.h needs no epsilon: its rounding error (~2e-7 * t) is below eps * |1/d| for any ray that
 // starts within ~20 scene diameters.
@@ -114,6 +120,61 @@ struct Builder {
       return idx;
    }
 };
+// ---- SAH-optimal collapse: C(n, i) = cheapest representation of the binary subtree n in at most i slots of a 4-wide parent
+struct Collapse {
+   const F4 *bin = nullptr;
+   std::vector<float> c1, c2, c3;
+   std::vector<int> first, cnt;
+   float cp = 0; int pmax = 2;
+   static void childrenOf(const F4 *nodes, int idx, Box &l, int &lr, Box &r, int &rr) {
+      const F4 *np = nodes + 4 * (size_t)idx;
+      l.lo[0] = np[0].x; l.hi[0] = np[0].y; l.lo[1] = np[0].z; l.hi[1] = np[0].w; l.lo[2] = np[2].x; l.hi[2] = np[2].y;
+      r.lo[0] = np[1].x; r.hi[0] = np[1].y; r.lo[1] = np[1].z; r.hi[1] = np[1].w; r.lo[2] = np[2].z; r.hi[2] = np[2].w;
+      lr = f2i(np[3].x); rr = f2i(np[3].y);
+   }
+   float childC(int r, const Box &b, int i) const {
+      if (r < 0) return b.area() * (float)((~r) & 15) * cp;
+      return i == 1 ? c1[(size_t)r] : (i == 2 ? c2[(size_t)r] : c3[(size_t)r]);
+   }
+   // cheapest split of j slots between the two children of a binary node (a child never needs more than 3)
+   float dist(int lr, const Box &lb, int rr, const Box &rb, int j, int *kbest) const {
+      float best = BL_INF; int kb = 1;
+      for (int k = 1; k < j; ++k) {
+         const float c = childC(lr, lb, std::min(k, 3)) + childC(rr, rb, std::min(j - k, 3));
+         if (c < best) { best = c; kb = k; }
+      }
+      if (kbest) *kbest = kb;
+      return best;
+   }
+   float leafCost(int n, const Box &b) const { return cnt[(size_t)n] <= pmax ? b.area() * (float)cnt[(size_t)n] * cp : BL_INF; }
+   void solve(int n, Box &box) {   // post-order; the binary tree is at most ~60 levels deep
+      Box lb, rb, tmp; int lr, rr; childrenOf(bin, n, lb, lr, rb, rr);
+      if (lr >= 0) solve(lr, tmp);
+      if (rr >= 0) solve(rr, tmp);
+      box = lb; box.grow(rb);
+      const int lc = lr < 0 ? ((~lr) & 15) : cnt[(size_t)lr], rc = rr < 0 ? ((~rr) & 15) : cnt[(size_t)rr];
+      first[(size_t)n] = lr < 0 ? (int)((uint32_t)(~lr) >> 4) : first[(size_t)lr];   // the items of a subtree are contiguous, left before right
+      cnt[(size_t)n] = std::min(lc + rc, 1 << 20);
+      const float cint = dist(lr, lb, rr, rb, 4, nullptr) + box.area();
+      c1[(size_t)n] = std::min(leafCost(n, box), cint);
+      c2[(size_t)n] = std::min(dist(lr, lb, rr, rb, 2, nullptr), c1[(size_t)n]);
+      c3[(size_t)n] = std::min(dist(lr, lb, rr, rb, 3, nullptr), c2[(size_t)n]);
+   }
+   // the children that subtree r contributes to its wide parent when it may use i slots
+   template <class ChildT> void expand(int r, const Box &b, int i, ChildT *c, int &nc) const {
+      if (r < 0) { c[nc].box = b; c[nc].ref = r; nc++; return; }
+      if (i > 1) {
+         Box lb, rb; int lr, rr; childrenOf(bin, r, lb, lr, rb, rr);
+         int k; const float cd = dist(lr, lb, rr, rb, i, &k);
+         if (cd < (i == 2 ? c1[(size_t)r] : c2[(size_t)r])) { expand(lr, lb, k, c, nc); expand(rr, rb, i - k, c, nc); }
+         else expand(r, b, i - 1, c, nc);
+         return;
+      }
+      c[nc].box = b;
+      c[nc].ref = (leafCost(r, b) <= c1[(size_t)r]) ? ~(int)(((uint32_t)first[(size_t)r] << 4) | (uint32_t)cnt[(size_t)r]) : r;
+      nc++;
+   }
+};
 }  // namespace
 
 int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
@@ -140,7 +201,8 @@ int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
       }
       it.id = (uint32_t)i;
    }
-   B.maxLeaf = std::min(15, std::max(1, in.max_leaf));
+   const bool optimal = in.collapse_cp > 0;
+   B.maxLeaf = optimal ? 1 : std::min(15, std::max(1, in.max_leaf));   // optimal collapse: the DP forms the leaves
    B.travCost = in.trav_cost; B.forceLeaf = in.force_leaf != 0;
    int th = std::max(1, in.threads);
    B.parLevels = 0; while ((1 << B.parLevels) < th) B.parLevels++;
@@ -164,6 +226,12 @@ int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
    F4 *n4 = (F4 *)std::malloc(sizeof(F4) * BL_NODE_F4 * (size_t)(n2 + 1));
    int next4 = 0;
    struct Child { Box box; int ref; };
+   Collapse dp;
+   if (optimal) {
+      dp.bin = B.nodes; dp.cp = in.collapse_cp; dp.pmax = std::min(15, std::max(1, in.max_leaf));
+      dp.c1.assign((size_t)n2, 0); dp.c2.assign((size_t)n2, 0); dp.c3.assign((size_t)n2, 0); dp.first.assign((size_t)n2, 0); dp.cnt.assign((size_t)n2, 0);
+      Box bx; dp.solve(root, bx);
+   }
    auto childrenOf = [&](int idx, Child &l, Child &r) {
       const F4 *np = B.nodes + 4 * (size_t)idx;
       l.box.lo[0] = np[0].x; l.box.hi[0] = np[0].y; l.box.lo[1] = np[0].z; l.box.hi[1] = np[0].w; l.box.lo[2] = np[2].x; l.box.hi[2] = np[2].y;
@@ -178,6 +246,10 @@ int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
       Work w = work.back(); work.pop_back();
       Child c[4]; int nc = 2;
       childrenOf(w.n2idx, c[0], c[1]);
+      if (optimal) {
+         const Child l = c[0], r = c[1]; int k; dp.dist(l.ref, l.box, r.ref, r.box, 4, &k);
+         nc = 0; dp.expand(l.ref, l.box, k, c, nc); dp.expand(r.ref, r.box, 4 - k, c, nc);
+      } else
       while (nc < 4) {
          int best = -1; float bestArea = -1;
          for (int k = 0; k < nc; ++k) if (c[k].ref >= 0 && c[k].box.area() > bestArea) { bestArea = c[k].box.area(); best = k; }
@@ -195,33 +267,42 @@ int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
       }
       // inner children get their 4-wide index now: siblings are contiguous in memory
       for (int k = nc - 1; k >= 0; --k) if (k < nc && refs[k] >= 0) { int id = next4++; work.push_back(Work{refs[k], id}); refs[k] = id; }
-      // quantise the child boxes on a node-local grid of 2^e cells; bytes 1..254 cover the node box, every bound is
-      // rounded outwards and then moved out by one more cell (the kernel's folded 2^23 costs up to half a cell)
+      // quantise the child boxes on a node-local grid of 2^e cells: the grid origin lies 1/32 of a cell below the node box, every
+      // bound is moved out by 1/64 of a cell (the kernel's folded 2^15 is good to 1/512 of a cell, bvh.h) and then rounded
+      // outwards to the grid; the exponent grows until byte 255 covers the high bounds
       float P[3]; uint32_t E = 0; uint32_t qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0};
+      const double QPAD = 1.0 / 64.0;
       for (int a = 0; a < 3; ++a) {
          double lo = nb.lo[a], ext = (double)nb.hi[a] - (double)nb.lo[a];
          if (!(ext > 0)) ext = 0;
          int e = -100;
-         if (ext > 0) { e = (int)std::ceil(std::log2(ext / 252.0)); while (std::ldexp(252.0, e) < ext) e++; }
+         if (ext > 0) { e = (int)std::ceil(std::log2(ext / 254.0)); while (std::ldexp(254.0, e) < ext) e++; }
          e = std::max(-120, std::min(120, e));
-         double cell = std::ldexp(1.0, e);
-         float Pf = (float)(lo - cell);
-         while ((double)Pf + cell > lo) Pf = std::nextafterf(Pf, -BL_INF);   // byte 1 must not lie above the node's low bound
-         P[a] = Pf; E |= (uint32_t)(e + 127) << (8 * a);
-         for (int k = 0; k < 4; ++k) {
-            int ql = 255, qh = 0;   // unused slot: inverted, never hit
-            if (refs[k] != ~0) {
-               ql = (int)std::floor(((double)c[k].box.lo[a] - (double)Pf) / cell) - 1;
-               qh = (int)std::ceil(((double)c[k].box.hi[a] - (double)Pf) / cell) + 1;
-               ql = std::max(0, std::min(255, ql)); qh = std::max(0, std::min(255, qh));
+         for (;; ++e) {
+            const double cell = std::ldexp(1.0, e);
+            float Pf = (float)(lo - cell / 32);
+            while ((double)Pf + cell / 64 > lo) Pf = std::nextafterf(Pf, -BL_INF);   // byte 0 must lie at least 1/64 cell below the node's low bound
+            bool fits = true;
+            uint32_t wl = 0, wh = 0;
+            for (int k = 0; k < 4; ++k) {
+               int ql = 255, qh = 0;   // unused slot: inverted, never hit
+               if (refs[k] != ~0) {
+                  const double ul = ((double)c[k].box.lo[a] - (double)Pf) / cell - QPAD, uh = ((double)c[k].box.hi[a] - (double)Pf) / cell + QPAD;
+                  ql = (int)std::floor(ul); qh = (int)std::ceil(uh);
+                  if (qh > 255 && e < 120) fits = false;
+                  ql = std::max(0, std::min(255, ql)); qh = std::max(0, std::min(255, qh));
+               }
+               wl |= (uint32_t)ql << (8 * k); wh |= (uint32_t)qh << (8 * k);
             }
-            qlo[a] |= (uint32_t)ql << (8 * k); qhi[a] |= (uint32_t)qh << (8 * k);
+            if (!fits) continue;
+            P[a] = Pf; E |= (uint32_t)(e + 127) << (8 * a); qlo[a] = wl; qhi[a] = wh;
+            break;
          }
       }
       np[0] = F4{P[0], P[1], P[2], i2f((int)E)};
       np[1] = F4{i2f(refs[0]), i2f(refs[1]), i2f(refs[2]), i2f(refs[3])};
       np[2] = F4{i2f((int)qlo[0]), i2f((int)qlo[1]), i2f((int)qlo[2]), i2f((int)qhi[0])};
-      np[3] = F4{i2f((int)qhi[1]), i2f((int)qhi[2]), i2f(0x4B000000), 0};   // .z: the 2^23 bit pattern the kernel permutes bytes into
+      np[3] = F4{i2f((int)qhi[1]), i2f((int)qhi[2]), i2f((int)BL_QMAGIC), 0};   // .z: the 2^15 bit pattern the kernel permutes bytes into
    }
    // worst-case traversal stack (entries) of the push-all-then-pop scheme: children indices are always larger than
    // the parent's, so one reverse sweep suffices

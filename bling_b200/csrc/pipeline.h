@@ -49,8 +49,9 @@ struct Pipeline {
    F4 *filmSum = nullptr;     // sum of the films of all ranks (comm.h), valid after reduce_film
    uint32_t npix = 0, nTextures = 0;
    uint32_t batchTarget = 1u << 26;   // paths per wavefront (~490 B of state each: 33 GB at the cap, sized for 180 GB HBM)
-   int maxLeaf = 2;
+   int maxLeaf = 3;            // option bvh_leaf: most items a leaf may hold
    float bvhTravCost = 0; int bvhForceLeaf = 1;   // options bvh_trav_cost / bvh_force_leaf (bvh.h::BvhBuildInput)
+   float bvhCollapseCp = 0.5f;                        // option bvh_collapse_cp: > 0 = SAH-optimal collapse (bvh_build.cpp::Collapse)
    uint64_t nNodes = 0, nItems = 0;
    uint64_t launches = 0;
    double lastMs = 0;
@@ -148,7 +149,7 @@ struct Pipeline {
       scanKinds(ir);
       std::vector<int> shadeKind(ir->n_materials ? ir->n_materials : 1, 0);
       for (uint32_t i = 0; i < ir->n_materials; ++i) shadeKind[i] = matSlot[i] - 1;
-      BvhBuildInput bi; bi.n = nprim; bi.lo = lo.data(); bi.hi = hi.data(); bi.max_leaf = maxLeaf; bi.trav_cost = bvhTravCost; bi.force_leaf = bvhForceLeaf;
+      BvhBuildInput bi; bi.n = nprim; bi.lo = lo.data(); bi.hi = hi.data(); bi.max_leaf = maxLeaf; bi.trav_cost = bvhTravCost; bi.force_leaf = bvhForceLeaf; bi.collapse_cp = bvhCollapseCp;
       bi.threads = (int)std::max(1u, std::thread::hardware_concurrency());
       BvhBuildOutput bo;
       if (bvhBuild(bi, bo)) return fail(BLINGCU_EINVAL, "too many primitives");

@@ -93,6 +93,31 @@ def test_emulated_traversal_matches_oracle(name):
     assert nodes.max() > 0 and prims.sum() > 0
 
 
+@pytest.mark.parametrize("name", ["cornell-box", "zoo", "ducky", "glass-torus"])
+@pytest.mark.parametrize("cp,leaf", [(0.5, 3), (1.0, 1), (0.25, 8)])
+def test_optimal_collapse_gives_the_same_hits(name, cp, leaf):
+    """The SAH-optimal collapse (bvh_build.cpp::Collapse, option bvh_collapse_cp) changes the tree, never the answer: the
+    nearest hit is global, so prim / t / b1 / b2 and the occlusion flags equal those of the greedy tree bit for
+    bit (exact t-ties aside), and every leaf holds at most `bvh_leaf` items."""
+    sc = load_scene(name)
+    a = EmuContext(); a.set_option("bvh_collapse_cp", 0); a.set_option("bvh_leaf", 2); a.upload_scene(sc)    # round 1's greedy collapse
+    b = EmuContext(); b.set_option("bvh_collapse_cp", cp); b.set_option("bvh_leaf", leaf); b.upload_scene(sc)
+    rays = np.concatenate([random_rays(sc, 3000, 5), camera_rays(None, sc, 3000, 6)])
+    ha, hb = a.trace_nearest(rays), b.trace_nearest(rays)
+    ties, bad = compare_hits(hb, ha)
+    assert bad == 0 and ties <= 0.01 * len(rays), (ties, bad)
+    same = ha["prim"] == hb["prim"]
+    for f in ("t", "b1", "b2"):
+        assert np.array_equal(ha[f][same], hb[f][same])
+    assert np.array_equal(a.trace_occluded(rays), b.trace_occluded(rays))
+    _, _, pa = a.trace_stats(rays[:1500]); _, nb_, pb = b.trace_stats(rays[:1500])
+    assert nb_.max() > 0
+    if leaf == 1 and sc.n_prims > 4:
+        assert pb.sum() <= pa.sum()      # single-item leaves never test more primitives than the two-item leaves of the greedy tree
+    with pytest.raises(Exception):
+        b.set_option("bvh_collapse_cp", -1)
+
+
 @pytest.mark.parametrize("name", ALL_SCENES + EMU_ONLY)
 def test_emulated_path_samples_match_oracle(name):
     """per-sample radiance of the wavefront bodies == oracle's recursive nextVertex on the same sampler SPEC."""

@@ -20,7 +20,10 @@ for name in names:
     if size:
         w, h, n = (int(x) for x in size.split("x"))
         sc = resized(sc, w, h, n, n)
-    c = api.Context(0); c.upload_scene(sc)
+    c = api.Context(0)
+    for kv in filter(None, os.environ.get("BLINGCU_OPTIONS", "").split(",")):      # A/B: options set before the upload (builder knobs)
+        k_, _, v_ = kv.partition("="); c.set_option(k_, float(v_))
+    c.upload_scene(sc)
     ex = c.sample_extent(); npx = (ex[1] - ex[0] + 1) * (ex[3] - ex[2] + 1)
     k = max(1, min(sc.spp // 2, int(48e6 // npx)))
     c.render_slice(1, 1, 0, k); c.synchronize(); c.reset_stats(); c.set_option("profile_kernels", 1)

@@ -33,6 +33,47 @@ static void childrenOf(const F4 *nodes, int idx, Box &lb, int &lr, Box &rb, int 
    lr = f2i(np[3].x); rr = f2i(np[3].y);
 }
 
+// ---- SAH-optimal collapse by dynamic programming (Ylitie, Karras, Laine 2017, section 3.1) as an alternative to "open the largest child":
+// C(n, i) = cheapest way to represent the binary subtree n with at most i slots of its wide parent. DPCOLLAPSE="cn,cp,pmax"
+struct DPTab { std::vector<float> c1, c2, c3; std::vector<int> first, cnt; float cn = 1, cp = 1; int pmax = 2; int W = 4; const F4 *bin = nullptr; };
+static DPTab gDP;
+static inline float dpChildC(int r, const Box &b, int i) { if (r < 0) return b.area() * (float)((~r) & 15) * gDP.cp; return i == 1 ? gDP.c1[r] : (i == 2 ? gDP.c2[r] : gDP.c3[r]); }
+static inline float dpDist(int lr, const Box &lb, int rr, const Box &rb, int j, int *kbest) {
+   float best = BL_INF; int kb = 1;
+   for (int k = 1; k < j; ++k) { float c = dpChildC(lr, lb, std::min(k, 3)) + dpChildC(rr, rb, std::min(j - k, 3)); if (c < best) { best = c; kb = k; } }
+   if (kbest) *kbest = kb; return best;
+}
+static void dpRec(int n, Box &box) {
+   Box lb, rb; int lr, rr; childrenOf(gDP.bin, n, lb, lr, rb, rr);
+   Box tmp;
+   if (lr >= 0) dpRec(lr, tmp);
+   if (rr >= 0) dpRec(rr, tmp);
+   box = lb; box.grow(rb);
+   const int lf = lr < 0 ? ((~lr) >> 4) : gDP.first[lr], lc = lr < 0 ? ((~lr) & 15) : gDP.cnt[lr];
+   const int rc = rr < 0 ? ((~rr) & 15) : gDP.cnt[rr];
+   gDP.first[n] = lf; gDP.cnt[n] = lc + rc;
+   const float A = box.area();
+   const float cleaf = (lc + rc <= gDP.pmax) ? A * (float)(lc + rc) * gDP.cp : BL_INF;
+   const float cint = dpDist(lr, lb, rr, rb, gDP.W, nullptr) + A * gDP.cn;
+   gDP.c1[n] = std::min(cleaf, cint);
+   gDP.c2[n] = std::min(dpDist(lr, lb, rr, rb, 2, nullptr), gDP.c1[n]);
+   gDP.c3[n] = std::min(dpDist(lr, lb, rr, rb, 3, nullptr), gDP.c2[n]);
+}
+static void dpExpand(int r, const Box &b, int i, Box *cb, int *cr, int &nc) {
+   if (r < 0) { cb[nc] = b; cr[nc] = r; nc++; return; }
+   Box lb, rb; int lr, rr; childrenOf(gDP.bin, r, lb, lr, rb, rr);
+   if (i > 1) {
+      int k; const float cd = dpDist(lr, lb, rr, rb, i, &k);
+      const float cprev = i == 2 ? gDP.c1[r] : gDP.c2[r];
+      if (cd < cprev) { dpExpand(lr, lb, k, cb, cr, nc); dpExpand(rr, rb, i - k, cb, cr, nc); return; }
+      dpExpand(r, b, i - 1, cb, cr, nc); return;
+   }
+   const float A = b.area();
+   const float cleaf = (gDP.cnt[r] <= gDP.pmax) ? A * (float)gDP.cnt[r] * gDP.cp : BL_INF;
+   if (cleaf <= gDP.c1[r]) { cb[nc] = b; cr[nc] = ~((gDP.first[r] << 4) | gDP.cnt[r]); nc++; }
+   else { cb[nc] = b; cr[nc] = r; nc++; }
+}
+
 // collapse + 8-bit quantisation (same rounding rules as bvh_build.cpp); octantOrder: assign children to slots so that
 // slot ^ octant gives an approximate front-to-back order (Ylitie et al. 2017, greedy instead of auction)
 static WTree collapse(const F4 *bin, int root2, int W, bool quantise, bool octantOrder) {
@@ -45,6 +86,10 @@ static WTree collapse(const F4 *bin, int root2, int W, bool quantise, bool octan
       Work w = work.back(); work.pop_back();
       Box cb[8]; int cr[8]; int nc = 2;
       childrenOf(bin, w.n2, cb[0], cr[0], cb[1], cr[1]);
+      if (gDP.bin && W == gDP.W) {
+         Box lb = cb[0], rb = cb[1]; int lr = cr[0], rr = cr[1]; int k; dpDist(lr, lb, rr, rb, W, &k);
+         nc = 0; dpExpand(lr, lb, std::min(k, 3), cb, cr, nc); dpExpand(rr, rb, std::min(W - k, 3), cb, cr, nc);
+      } else
       while (nc < W) {
          int best = -1; float ba = -1;
          for (int k = 0; k < nc; ++k) if (cr[k] >= 0 && cb[k].area() > ba) { ba = cb[k].area(); best = k; }
@@ -76,12 +121,15 @@ static WTree collapse(const F4 *bin, int root2, int W, bool quantise, bool octan
       for (int s = 0; s < 8; ++s) { nd.ref[s] = ~0; for (int a = 0; a < 3; ++a) { nd.lo[s][a] = BL_INF; nd.hi[s][a] = -BL_INF; } }
       for (int a = 0; a < 3; ++a) {
          double lo = nb.lo[a], ext = (double)nb.hi[a] - (double)nb.lo[a]; if (!(ext > 0)) ext = 0;
-         int e = -100; if (ext > 0) { e = (int)std::ceil(std::log2(ext / 252.0)); while (std::ldexp(252.0, e) < ext) e++; }
-         double cell = std::ldexp(1.0, e); float Pf = (float)(lo - cell);
+         static const double qpad0 = getenv("QPAD") ? atof(getenv("QPAD")) : 1.0 / 64;   // QPAD=1: the rule until the end of round 2 (one extra cell per side)
+         const double span = qpad0 >= 1 ? 252.0 : 254.0;
+         int e = -100; if (ext > 0) { e = (int)std::ceil(std::log2(ext / span)); while (std::ldexp(span, e) < ext) e++; }
+         double cell = std::ldexp(1.0, e); float Pf = (float)(lo - (qpad0 >= 1 ? cell : cell / 32));
          for (int k = 0; k < nc; ++k) {
             int s = slotOf[k];
             if (quantise) {
-               int ql = (int)std::floor(((double)cb[k].lo[a] - (double)Pf) / cell) - 1, qh = (int)std::ceil(((double)cb[k].hi[a] - (double)Pf) / cell) + 1;
+               static const double qpad = getenv("QPAD") ? atof(getenv("QPAD")) : 1.0 / 64;   // cells every bound is moved out by after rounding (bvh_build.cpp)
+               int ql = (int)std::floor(((double)cb[k].lo[a] - (double)Pf) / cell - qpad), qh = (int)std::ceil(((double)cb[k].hi[a] - (double)Pf) / cell + qpad);
                ql = std::max(0, std::min(255, ql)); qh = std::max(0, std::min(255, qh));
                nd.lo[s][a] = (float)((double)Pf + cell * ql); nd.hi[s][a] = (float)((double)Pf + cell * qh);
             } else { nd.lo[s][a] = cb[k].lo[a]; nd.hi[s][a] = cb[k].hi[a]; }
@@ -415,7 +463,15 @@ int main(int argc, char **argv) {
    Box rb; int root2 = B.build(0, ntris, 0, rb);
    gItems.resize(ntris); for (size_t i = 0; i < ntris; ++i) gItems[i] = tris[B.items[i].id];
    printf("binary tree: %d nodes, %.1f s\n", B.nextNode.load(), std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
-   WTree T4 = collapse(B.nodes, root2, 4, true, false);
+   if (const char *dps = getenv("DPCOLLAPSE")) {
+      float cn = 1, cp = 1; int pm = maxLeaf; sscanf(dps, "%f,%f,%d", &cn, &cp, &pm);
+      gDP.cn = cn; gDP.cp = cp; gDP.pmax = std::min(15, pm); gDP.W = 4; gDP.bin = B.nodes;
+      const size_t nn = (size_t)B.nextNode.load();
+      gDP.c1.assign(nn, 0); gDP.c2.assign(nn, 0); gDP.c3.assign(nn, 0); gDP.first.assign(nn, 0); gDP.cnt.assign(nn, 0);
+      Box bx; if (root2 >= 0) dpRec(root2, bx);
+      printf("DP collapse: cn %.2f cp %.2f pmax %d, SAH cost of the root %.4g\n", cn, cp, gDP.pmax, root2 >= 0 ? gDP.c1[root2] / bx.area() : 0.0);
+   }
+   WTree T4 = collapse(B.nodes, root2, 4, getenv("NOQUANT") == nullptr, false);   // NOQUANT: what the 8-bit child boxes cost in visits
    WTree T8 = collapse(B.nodes, root2, 8, true, false);
    WTree T8o = collapse(B.nodes, root2, 8, true, true);
    printf("BVH4 %zu nodes, BVH8 %zu nodes\n", T4.nodes.size(), T8.nodes.size());
