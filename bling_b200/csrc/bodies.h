@@ -47,6 +47,9 @@ struct PathState {
 // sector, and ncu had the shade kernels on the DRAM sector rate of exactly these scattered accesses. Measured on the B200
 // (tools/gpu_r02_f.sh, profiles/r02_shade_layout.md): shade -14 .. -23 %, the named scenes +6 .. +14 %, films bit-identical.
 // BL_SPEC_PLANES rebuilds the old layout for A/B (tools/ab_libs.py).
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void pfL2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 HD size_t spec4At(uint32_t cap, uint32_t i, int q) {
 #ifndef BL_SPEC_PLANES
    (void)cap; return (size_t)i * 4 + q;
@@ -54,13 +57,34 @@ HD size_t spec4At(uint32_t cap, uint32_t i, int q) {
    return (size_t)q * cap + i;
 #endif
 }
+// The 64-byte record moves as TWO 32-byte accesses (LDG.E.256 / STG.E.256) instead of four 16-byte ones: the shade and resolve
+// kernels sit on the request rate of their scattered accesses, and a vertex reads the throughput record three times and writes three
+// more records (BL_SPEC_V8 0 rebuilds the four-access version for A/B). Records are 64-byte aligned (each array is its own cudaMalloc).
+#ifndef BL_SPEC_V8
+#define BL_SPEC_V8 1
+#endif
 HD Spec loadSpec4(const F4 *base, uint32_t cap, uint32_t i) {
    Spec s;
+#if defined(__CUDA_ARCH__) && BL_SPEC_V8 && !defined(BL_SPEC_PLANES)
+   (void)cap;
+   BL_UNROLL for (int h = 0; h < 2; ++h)
+      asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                   : "=f"(s.v[8 * h]), "=f"(s.v[8 * h + 1]), "=f"(s.v[8 * h + 2]), "=f"(s.v[8 * h + 3]), "=f"(s.v[8 * h + 4]), "=f"(s.v[8 * h + 5]), "=f"(s.v[8 * h + 6]), "=f"(s.v[8 * h + 7])
+                   : "l"(base + (size_t)i * 4 + 2 * h));
+#else
    BL_UNROLL for (int q = 0; q < 4; ++q) { F4 v = base[spec4At(cap, i, q)]; s.v[4 * q] = v.x; s.v[4 * q + 1] = v.y; s.v[4 * q + 2] = v.z; s.v[4 * q + 3] = v.w; }
+#endif
    return s;
 }
 HD void storeSpec4(F4 *base, uint32_t cap, uint32_t i, const Spec &s) {
+#if defined(__CUDA_ARCH__) && BL_SPEC_V8 && !defined(BL_SPEC_PLANES)
+   (void)cap;
+   BL_UNROLL for (int h = 0; h < 2; ++h)
+      asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(base + (size_t)i * 4 + 2 * h),
+                   "f"(s.v[8 * h]), "f"(s.v[8 * h + 1]), "f"(s.v[8 * h + 2]), "f"(s.v[8 * h + 3]), "f"(s.v[8 * h + 4]), "f"(s.v[8 * h + 5]), "f"(s.v[8 * h + 6]), "f"(s.v[8 * h + 7]) : "memory");
+#else
    BL_UNROLL for (int q = 0; q < 4; ++q) { F4 v; v.x = s.v[4 * q]; v.y = s.v[4 * q + 1]; v.z = s.v[4 * q + 2]; v.w = s.v[4 * q + 3]; base[spec4At(cap, i, q)] = v; }
+#endif
 }
 // A ray is ONE 32-byte record {(o, tmin), (d, tmax)} -- the C ABI's blingcu_ray as it is -- so that a scattered access touches one
 // full 32-byte sector (round 1: separate `O` and `D` arrays = two half-used sectors per ray, in the traversal kernels and four
@@ -254,6 +278,25 @@ template <int MATKIND>
 struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118; one instantiation per material kind (material-sorted queues)
    typedef MatOf<MATKIND> M;
    const DScene *sc; PathState ps; uint32_t *qNext;
+#if defined(__CUDA_ARCH__)
+   // Cross-item software pipeline of kRunQueueHeavy (cuda_backend.cu): while a thread shades slot k it already has the records of
+   // its NEXT slot on their way into L2. The shade kernels run at 20-25 % occupancy (128-168 registers: 16-band spectra) and ncu
+   // shows them waiting on three levels of dependent, scattered loads (queue entry -> path state -> geometry); more warps are not
+   // to be had, so the independence comes from the next loop iteration instead.
+   __device__ __forceinline__ void prefetchSlot(uint32_t s) const {          // level 1: what operator() reads by slot
+      pfL2(ps.rayO + rayAt2(s)); pfL2(ps.meta + s); pfL2(ps.kp + s); pfL2(ps.sidx + s);
+      pfL2(ps.T + spec4At(ps.cap, s, 0)); pfL2(ps.T + spec4At(ps.cap, s, 2));
+   }
+   __device__ __forceinline__ int peekHit(uint32_t s) const { return f2i(ps.hit[s].w); }   // a real load: its value addresses level 2
+   __device__ __forceinline__ void prefetchSurface(int href) const {         // level 2: the geometry surfaceAt() reads
+      if (href == BL_REF_MISS || refIsShape(href)) return;
+      const DScene &S = *sc;
+      const uint32_t ref = refIndex(href);
+      const F4 *tp = S.tri_p + 3 * (size_t)ref; pfL2(tp); pfL2(tp + 2);       // 48 bytes: one or two sectors
+      pfL2(S.tri_uv + 3 * (size_t)ref);
+      if (S.tri_n) { const float *N = S.tri_n + 9 * (size_t)ref; pfL2(N); pfL2(N + 8); }
+   }
+#endif
    HD void operator()(uint32_t i) const {
       const DScene &S = *sc;
       Ray ray = loadRay(ps.rayO, ps.rayD, i);

@@ -37,6 +37,36 @@ template <class B> __global__ void __launch_bounds__(128, SH_MINBLOCKS) kRunQueu
    uint32_t n = *cnt;
    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b(q[i]);
 }
+#ifndef SH_PREFETCH
+#define SH_PREFETCH 0     // 1: the hit-shading kernels prefetch their next slot (bodies.h::ShadeHitBody::prefetchSlot); 0: plain loop.
+                          // Measured (tools/gpu_r02_z3.sh): the pipelined loop is SLOWER -- shade 35.0 -> 42.0 ms per cfg-5 step, the named
+                          // scenes -1 .. -7 % -- although it hides two of the three load levels: the kernels sit on the request rate
+                          // of their scattered accesses (profiles/r01_shade_experiments.md), and eight prefetches plus two early loads
+                          // per item are eight more requests. Kept as an A/B build only.
+#endif
+// The same loop, software-pipelined over the items of one thread: at the top of iteration k the thread issues the loads that
+// ADDRESS iteration k + 1 (its hit reference, and the queue entry after it) and prefetches that slot's records; after the body,
+// when the hit reference has arrived, it prefetches the geometry behind it.
+template <int MK> __global__ void __launch_bounds__(128, SH_MINBLOCKS) kRunQueueShade(ShadeHitBody<MK> b, const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt) {
+   const uint32_t n = *cnt, stride = gridDim.x * blockDim.x;
+   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n) return;
+   uint32_t slot = q[i];
+   uint32_t next = (i + stride < n) ? q[i + stride] : slot;
+   for (;;) {
+      const bool more = i + stride < n;
+      int href = BL_REF_MISS; uint32_t next2 = next;
+      if (more) {
+         href = b.peekHit(next);
+         if (i + 2 * stride < n) next2 = q[i + 2 * stride];
+         b.prefetchSlot(next);
+      }
+      b(slot);
+      if (!more) break;
+      b.prefetchSurface(href);
+      i += stride; slot = next; next = next2;
+   }
+}
 
 // K7 film, tiled: one CTA per 16x16 film-pixel tile. For every sample index of the batch the samples of all sample pixels
 // that can reach the tile ((16 + 2R + 1)^2 of them) are staged in shared memory once, then every thread gathers its own
@@ -399,7 +429,11 @@ struct CudaBackend {
    template <int MK> void runQueue(const ShadeHitBody<MK> &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
       if (bound == 0) return;
       Scope sc_(this);
+#if SH_PREFETCH
+      kRunQueueShade<MK><<<gridFor(bound, 128, resident(kRunQueueShade<MK>, 128)), 128, 0, stream>>>(b, q, cnt);
+#else
       kRunQueueHeavy<ShadeHitBody<MK>><<<gridFor(bound, 128, resident(kRunQueueHeavy<ShadeHitBody<MK>>, 128)), 128, 0, stream>>>(b, q, cnt);
+#endif
    }
    template <bool DL> void runQueue(const ResolveMisBodyT<DL> &b, const uint32_t *q, const uint32_t *cnt, uint32_t bound) {
       if (bound == 0) return;

@@ -49,9 +49,14 @@ struct Pipeline {
    F4 *filmSum = nullptr;     // sum of the films of all ranks (comm.h), valid after reduce_film
    uint32_t npix = 0, nTextures = 0;
    uint32_t batchTarget = 1u << 26;   // paths per wavefront (~490 B of state each: 33 GB at the cap, sized for 180 GB HBM)
-   int maxLeaf = 3;            // option bvh_leaf: most items a leaf may hold
+   int maxLeaf = 0;            // option bvh_leaf: most items a leaf may hold; 0 = not set: 3 under the optimal collapse, 2 under the greedy one
    float bvhTravCost = 0; int bvhForceLeaf = 1;   // options bvh_trav_cost / bvh_force_leaf (bvh.h::BvhBuildInput)
-   float bvhCollapseCp = 0.5f;                        // option bvh_collapse_cp: > 0 = SAH-optimal collapse (bvh_build.cpp::Collapse)
+   // option bvh_collapse_cp: > 0 = SAH-optimal collapse (bvh_build.cpp::Collapse) with a primitive test costing that many node
+   // visits, 0 = the greedy collapse. Not set (< 0): 0.5 -- the ratio measured on cfg 5 (tools/gpu_r02_z1.sh: one node visit per
+   // ray costs 7.7 ms of the nearest-hit kernels' 350, one primitive test 4.1) -- for scenes of more than 4096 items, greedy
+   // below: in a scene that lives in L1 a node visit costs no more than a test, and merged leaves of large primitives lost the
+   // 31-primitive cornell-box 10 % (tools/gpu_r02_z2.sh).
+   float bvhCollapseCp = -1;
    uint64_t nNodes = 0, nItems = 0;
    uint64_t launches = 0;
    double lastMs = 0;
@@ -149,7 +154,9 @@ struct Pipeline {
       scanKinds(ir);
       std::vector<int> shadeKind(ir->n_materials ? ir->n_materials : 1, 0);
       for (uint32_t i = 0; i < ir->n_materials; ++i) shadeKind[i] = matSlot[i] - 1;
-      BvhBuildInput bi; bi.n = nprim; bi.lo = lo.data(); bi.hi = hi.data(); bi.max_leaf = maxLeaf; bi.trav_cost = bvhTravCost; bi.force_leaf = bvhForceLeaf; bi.collapse_cp = bvhCollapseCp;
+      BvhBuildInput bi; bi.n = nprim; bi.lo = lo.data(); bi.hi = hi.data(); bi.trav_cost = bvhTravCost; bi.force_leaf = bvhForceLeaf;
+      bi.collapse_cp = bvhCollapseCp >= 0 ? bvhCollapseCp : (nprim > 4096 ? 0.5f : 0.0f);
+      bi.max_leaf = maxLeaf > 0 ? maxLeaf : (bi.collapse_cp > 0 ? 3 : 2);
       bi.threads = (int)std::max(1u, std::thread::hardware_concurrency());
       BvhBuildOutput bo;
       if (bvhBuild(bi, bo)) return fail(BLINGCU_EINVAL, "too many primitives");

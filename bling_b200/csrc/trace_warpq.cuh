@@ -19,7 +19,9 @@ namespace bl {
 
 #define TQ_CAP 128        // ring entries per warp: < 32 left over + at most 2 per lane per trip
 #ifndef TQ_FLUSH
-#define TQ_FLUSH 32       // run a leaf pass once this many pairs are queued (<= 32)
+#define TQ_FLUSH 24       // run a leaf pass once this many pairs are queued (<= 32). Re-tuned on the round-2 tree (a third fewer pairs per
+                          // ray, so a ray whose stack has run dry waits longer for a full pass): 32 -> 24 any-hit -1.1 %, nearest-hit
+                          // unchanged; 16: +3 % / +2 % (tools/gpu_r02_z3.sh)
 #endif
 #ifndef TQ_NEAR_BLOCKS
 #define TQ_NEAR_BLOCKS TR_MINBLOCKS   // resident CTAs per SM the nearest-hit instantiation is compiled for (A/B: 7 = 72 registers)
