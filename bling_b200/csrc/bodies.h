@@ -292,9 +292,8 @@ struct ShadeHitBody {   // Path.hs:49-87 + Scene.hs:61-118; one instantiation pe
       if (href == BL_REF_MISS || refIsShape(href)) return;
       const DScene &S = *sc;
       const uint32_t ref = refIndex(href);
-      const F4 *tp = S.tri_p + 3 * (size_t)ref; pfL2(tp); pfL2(tp + 2);       // 48 bytes: one or two sectors
-      pfL2(S.tri_uv + 3 * (size_t)ref);
-      if (S.tri_n) { const float *N = S.tri_n + 9 * (size_t)ref; pfL2(N); pfL2(N + 8); }
+      const F4 *tp = S.tri_p + BL_TRI_F4 * (size_t)ref; pfL2(tp); pfL2(tp + 2);
+      if (S.tri_n) { const F4 *N = S.tri_n + 3 * (size_t)ref; pfL2(N); pfL2(N + 2); }
    }
 #endif
    HD void operator()(uint32_t i) const {

@@ -112,6 +112,7 @@ HD bool leafItemAny(const Bvh &bvh, int item, const Ray &r) {
 }
 
 #define BL_NODE_F4 4     // F4 per node (64 B)
+#define BL_TRI_F4 4      // F4 per triangle of the shading geometry (shading.h::DScene::tri_p)
 #define BL_STACK 192     // worst case 3 pushes per level of a 56-level binary tree; real scenes use < 48
 
 #if defined(__CUDA_ARCH__)

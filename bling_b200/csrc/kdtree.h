@@ -36,7 +36,7 @@ HD bool kdBoundsHit(const KdTreeDev &kd, const Ray &r, float &tn, float &tf) {
 HD void kdPrim(const DScene &S, int ref, Ray &r, HitRec &h) {
    if (!refIsShape(ref)) {
       const uint32_t i = refIndex(ref);
-      const F4 a = S.tri_p[3 * (size_t)i], b = S.tri_p[3 * (size_t)i + 1], c = S.tri_p[3 * (size_t)i + 2];
+      const F4 a = S.tri_p[BL_TRI_F4 * (size_t)i], b = S.tri_p[BL_TRI_F4 * (size_t)i + 1], c = S.tri_p[BL_TRI_F4 * (size_t)i + 2];
       const V3 p1 = mk3(a.x, a.y, a.z);
       float t, b1, b2;
       if (!triHit(p1, mk3(b.x, b.y, b.z) - p1, mk3(c.x, c.y, c.z) - p1, r, t, b1, b2)) return;   // e1, e2 as TriangleMesh.hs:169

@@ -188,16 +188,21 @@ struct Pipeline {
       std::free(bo.nodes); std::free(bo.order);
       // ---- shading geometry
       {
-         std::vector<F4> tp(3 * (nt ? nt : 1)); std::vector<F2> tu(3 * (nt ? nt : 1));
+         std::vector<F4> tp(BL_TRI_F4 * (nt ? nt : 1));   // one 64-byte record per triangle (shading.h::DScene)
          for (size_t i = 0; i < nt; ++i) {
             static const float kDefaultUv[6] = {0, 0, 1, 0, 1, 1};   // TriangleMesh.hs:119-120
             const float *v = ir->tri_verts + 9 * i, *u = ir->tri_uvs ? ir->tri_uvs + 6 * i : kDefaultUv;
-            tp[3 * i] = F4{v[0], v[1], v[2], i2f(ir->tri_material[i])};
-            tp[3 * i + 1] = F4{v[3], v[4], v[5], 0}; tp[3 * i + 2] = F4{v[6], v[7], v[8], 0};
-            tu[3 * i] = F2{u[0], u[1]}; tu[3 * i + 1] = F2{u[2], u[3]}; tu[3 * i + 2] = F2{u[4], u[5]};
+            tp[BL_TRI_F4 * i] = F4{v[0], v[1], v[2], i2f(ir->tri_material[i])};
+            tp[BL_TRI_F4 * i + 1] = F4{v[3], v[4], v[5], u[0]}; tp[BL_TRI_F4 * i + 2] = F4{v[6], v[7], v[8], u[1]};
+            tp[BL_TRI_F4 * i + 3] = F4{u[2], u[3], u[4], u[5]};
          }
-         hs.tri_p = up<F4>(tp.data(), tp.size()); hs.tri_uv = up<F2>(tu.data(), tu.size());
-         hs.tri_n = (ir->tri_normals && nt) ? up<float>(ir->tri_normals, 9 * nt) : nullptr;
+         hs.tri_p = up<F4>(tp.data(), tp.size());
+         hs.tri_n = nullptr;
+         if (ir->tri_normals && nt) {
+            std::vector<F4> tn(3 * nt);
+            for (size_t i = 0; i < nt; ++i) for (int k = 0; k < 3; ++k) { const float *n = ir->tri_normals + 9 * i + 3 * k; tn[3 * i + k] = F4{n[0], n[1], n[2], 0}; }
+            hs.tri_n = up<F4>(tn.data(), tn.size());
+         }
       }
       { std::vector<int32_t> tprim(nt ? nt : 1, 0); for (size_t i = 0; i < nt; ++i) tprim[i] = itemPrim[i]; hs.tri_prim = up<int32_t>(tprim.data(), tprim.size()); }
       hs.shapes = up<blingcu_shape>(ir->shapes, ns); hs.bvh.shapes = hs.shapes; be.setBvh(hs.bvh);

@@ -13,9 +13,11 @@ namespace bl {
 
 struct DScene {
    Bvh bvh;
-   const F4 *tri_p;            // 3 per triangle: (p1.xyz, material), (p2.xyz, -), (p3.xyz, -)
-   const F2 *tri_uv;           // 3 per triangle
-   const float *tri_n;         // 9 per triangle or null
+   // shading geometry of a triangle = ONE 64-byte record (two 32-byte loads; until the end of round 2: 3 x 16 bytes of vertices and
+   // 3 x 8 bytes of uvs in two arrays = six requests per shaded vertex, in kernels that sit on their request rate):
+   //   (p1.xyz, material) (p2.xyz, uv1.x) (p3.xyz, uv1.y) (uv2.x, uv2.y, uv3.x, uv3.y)
+   const F4 *tri_p;            // BL_TRI_F4 per triangle
+   const F4 *tri_n;            // vertex normals, 3 per triangle (n1.xyz, -)(n2.xyz, -)(n3.xyz, -): three 16-byte loads instead of nine scalar ones; or null
    const int32_t *tri_prim;    // per triangle: primitive id in mkScene's list (only the C-ABI hit conversion reads it)
    const blingcu_shape *shapes;
    const blingcu_material *materials;
@@ -488,16 +490,22 @@ struct SurfaceHit {   // what mkIntersection carries (Primitive.hs:49-65)
 HD void surfaceAt(const DScene &sc, const Ray &ray, float t, float b1, float b2, int href, SurfaceHit &sh, DG &dgs) {
    const uint32_t ref = refIndex(href);
    if (!refIsShape(href)) {
-      const F4 *tp = sc.tri_p + 3 * (size_t)ref;
-      F4 a = ld4(tp), b = ld4(tp + 1), c = ld4(tp + 2);
-      const F2 *up = sc.tri_uv + 3 * (size_t)ref;
-      float uv[6] = {up[0].x, up[0].y, up[1].x, up[1].y, up[2].x, up[2].y};
+      const F4 *tp = sc.tri_p + BL_TRI_F4 * (size_t)ref;
+      F4 a, b, c, u;
+#if defined(__CUDA_ARCH__)
+      ld8(tp, a, b); ld8(tp + 2, c, u);
+#else
+      a = ld4(tp); b = ld4(tp + 1); c = ld4(tp + 2); u = ld4(tp + 3);
+#endif
+      float uv[6] = {b.w, c.w, u.x, u.y, u.z, u.w};
       sh.dgg = triDG(mk3(a.x, a.y, a.z), mk3(b.x, b.y, b.z), mk3(c.x, c.y, c.z), uv, rayAt(ray, t), b1, b2);
       sh.eps = 1e-3f * t;   // TriangleMesh.hs:206
       sh.material = f2i(a.w); sh.light = -1;
       dgs = sh.dgg;
       if (sc.tri_n) {   // triangleShadingGeometry (TriangleMesh.hs:122-134), o2w = mempty
-         const float *N = sc.tri_n + 9 * (size_t)ref;
+         const F4 *np = sc.tri_n + 3 * (size_t)ref;
+         const F4 n1 = ld4(np), n2 = ld4(np + 1), n3 = ld4(np + 2);
+         const float N[9] = {n1.x, n1.y, n1.z, n2.x, n2.y, n2.z, n3.x, n3.y, n3.z};
          // nine zeros: a triangle of a mesh WITHOUT normals in a scene that also holds smooth meshes keeps its geometric frame
          if (N[0] == 0 && N[1] == 0 && N[2] == 0 && N[3] == 0 && N[4] == 0 && N[5] == 0 && N[6] == 0 && N[7] == 0 && N[8] == 0) return;
          float b0 = 1 - b1 - b2;
