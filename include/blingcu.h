@@ -391,7 +391,14 @@ enum {
 };
 int blingcu_kernel_times(blingcu_ctx *, double *ms, uint64_t *launches, int n_classes);
 
-/* tuning knobs (optional): "batch_samples" (paths per wavefront), "bvh_leaf" ... returns EINVAL if unknown */
+/* tuning knobs (optional; returns EINVAL if unknown or out of range). Builder knobs take effect at the next upload_scene:
+ *   "batch_samples"    paths per wavefront (1 .. 2^31)
+ *   "bvh_leaf"         most items a leaf of the library's BVH may hold (1 .. 15; not set: 3 under the optimal collapse, 2 under the greedy one)
+ *   "bvh_collapse_cp"  > 0: SAH-optimal collapse of the binary tree into 4-wide nodes with a primitive test costing this many node
+ *                      visits; 0: greedy collapse ("open the largest child"). Not set: 0.5 above 4096 items, greedy below
+ *   "bvh_trav_cost", "bvh_force_leaf"  SAH termination of the binary builder (measured flat, left at their defaults)
+ *   "trace_variant"    0-3: traversal kernel (3 = the product), "fuse_resolve", "trace_chunk", "copy_threads", "traversal_stats",
+ *                      "profile_kernels": see DESIGN.md */
 int blingcu_set_option(blingcu_ctx *, const char *key, double value);
 
 /* sample extent of the film: x0,x1,y0,y1 inclusive (Image.hs:162-168) */
