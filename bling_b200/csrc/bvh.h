@@ -59,7 +59,19 @@ HD int mkRef(bool shape, int kind, uint32_t index) { return (int)((shape ? 0x800
 #ifndef BL_L2_POLICY
 #define BL_L2_POLICY 0   // A/B: bit 0 = leaf items with L2 evict_first (640 MB, little reuse), bit 1 = nodes with L2 evict_last
 #endif
+#ifndef BL_L1_POLICY
+#define BL_L1_POLICY 0   // A/B: bit 0 = leaf items bypass L1 (no_allocate: 640 MB, read once per test), bit 1 = nodes with L1 evict_last
+#endif
 #if defined(__CUDACC__)
+// the same 32-byte load with an L1 policy: leaf items are never re-read by the SM that fetched them, the top of the tree always is
+__device__ __forceinline__ void ld8NoAlloc(const F4 *p, F4 &a, F4 &b) {
+   asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void ld8KeepL1(const F4 *p, F4 &a, F4 &b) {
+   asm volatile("ld.global.nc.L1::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
 __device__ __forceinline__ void ld8(const F4 *p, F4 &a, F4 &b) {   // one 32-byte load (LDG.E.256 on sm_100)
    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
@@ -79,6 +91,7 @@ HD void ldItem(const F4 *items, int item, F4 &q0, F4 &q1, F4 &q2) {
 #if defined(__CUDA_ARCH__) && BL_ITEM_F4 == 4
    F4 q3;
    if (BL_L2_POLICY & 1) { ld8Policy<false>(p, q0, q1); ld8Policy<false>(p + 2, q2, q3); }
+   else if (BL_L1_POLICY & 1) { ld8NoAlloc(p, q0, q1); ld8NoAlloc(p + 2, q2, q3); }
    else { ld8(p, q0, q1); ld8(p + 2, q2, q3); }
 #else
    q0 = ld4(p); q1 = ld4(p + 1); q2 = ld4(p + 2);

@@ -142,6 +142,7 @@ __global__ void __launch_bounds__(TR_THREADS, (ANY && !FUSE) ? TR_MINBLOCKS + 1 
          const F4 *np = bvh.nodes + BL_NODE_F4 * (size_t)cur;
          F4 n0, n1, n2, n3;
          if (BL_L2_POLICY & 2) { ld8Policy<true>(np, n0, n1); ld8Policy<true>(np + 2, n2, n3); }
+         else if (BL_L1_POLICY & 2) { ld8KeepL1(np, n0, n1); ld8KeepL1(np + 2, n2, n3); }
          else { ld8(np, n0, n1); ld8(np + 2, n2, n3); }
          float tn[4];
          node4Near<!SORTED>(n0, n2, n3, r, pre, tn);   // unsorted (any-hit): tn = minus the length of the ray inside the child
