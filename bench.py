@@ -325,10 +325,10 @@ def run_b200(a):
                 per_ray = ((tr or {}).get(cls) or {}).get("dram_bytes_per_ray")
                 return {"kernel": label, "bound": "l1", "achieved": achieved, "peak": l1_peak, "unit": "GB/s", "frac": achieved / l1_peak,
                         "peak_source": f"{prop.multi_processor_count} SMs x {sm_mhz:.0f} MHz x {L1_BYTES_PER_CLK} B/clk: the L1 data pipe moves one 32-byte sector per cycle "
-                                       "per SM for scattered loads, and ncu shows it as the busiest unit of this kernel (3/4 busy; issue slots 2/3, DRAM 12-39 %: "
+                                       "per SM for scattered loads, and ncu shows it as the busiest unit of this kernel (3/4 busy; issue slots 2/3, DRAM 10-34 %: "
                                        "the kernel sits on a balance of the two and of dependent-load latency, profiles/r02_trace_source_view.md)",
                         "hbm": {"achieved": achieved, "peak": peak, "frac": achieved / peak, "peak_source": peak_src,
-                                "note": "algorithmic bytes against HBM copy bandwidth: most of them are served by L2 (hit rate 47-74 %), this is not what limits the kernel"},
+                                "note": "algorithmic bytes against HBM copy bandwidth: most of them are served by L2 (hit rate 50-75 %), this is not what limits the kernel"},
                         "issue": None if not (ncu or {}).get(cls) else {
                             "achieved": ncu[cls].get("issue_slots_busy_pct"), "peak": 100.0, "unit": "% of issue slots", "threads_per_instruction": ncu[cls].get("threads_per_instruction"),
                             "l1_data_pipe_busy_pct": ncu[cls].get("l1_data_pipe_busy_pct"), "l1_hit_pct": ncu[cls].get("l1_hit_pct"), "l2_hit_pct": ncu[cls].get("l2_hit_pct"),

@@ -19,7 +19,8 @@
 // carry qlo = 255 > qhi = 0, which the direction-sign based near/far selection rejects on its own. Why quantise: ncu showed the LSU data pipe as the
 // limiter with 128-byte nodes (one L1 wavefront per lane per 16 bytes); 64-byte nodes halve it and halve the
 // L2/DRAM bytes per visit. The builder (bvh_build.cpp) builds a binned-SAH binary tree, collapses it into 4-wide
-// nodes by repeatedly opening the child with the largest area, then quantises.
+// nodes -- SAH-optimally by dynamic programming for scenes of more than 4096 items, else by repeatedly opening the child with the
+// largest area -- then quantises.
 // Leaf item = 64 B = 2 x 32-byte loads (BL_ITEM_F4 = 4; the fourth float4 is padding):
 //   triangle: (p1.xyz, ref) (e1.xyz, 0) (e2.xyz, -) -       shape: (-, -, -, ref) (-, -, -, 1 + shape index) - -      (ref: see HitRec)
 // Why padded: ncu (profiles/r02_trace_warpq.md) shows the L1 data pipe as the busiest unit of the traversal kernels, and for
