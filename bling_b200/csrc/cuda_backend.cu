@@ -33,7 +33,20 @@ template <class B> __global__ void __launch_bounds__(256) kRunQueue(B b, const u
 #ifndef SH_MINBLOCKS
 #define SH_MINBLOCKS 3
 #endif
-template <class B> __global__ void __launch_bounds__(128, SH_MINBLOCKS) kRunQueueHeavy(B b, const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt) {
+// Resident CTAs per SM the heavy kernels are compiled for: SH_MINBLOCKS (3: up to 168 registers), or 4 (128 registers) for the
+// hit-shading kernels of the material kinds in SH_KINDS4 (bit k = kind k): given 168 registers ptxas takes 160-162 for the plastic
+// and translucent-matte bodies, given 128 it needs 127 / 125 and still does not spill (cuobjdump -res-usage).
+#ifndef SH_KINDS4
+#define SH_KINDS4 0x88    // plastic, translucent matte: measured on the B200 (tools/gpu_r02_z10.sh) ducky +2.4 %, environment +2.8 %, sun-sky +11.2 %, films bit-identical
+#endif
+#ifndef SH_KINDS5
+#define SH_KINDS5 0       // A/B: kinds compiled for five CTAs per SM (102 registers)
+#endif
+template <class B> struct HeavyBlocks { static const int v = SH_MINBLOCKS; };
+template <int MK> struct HeavyBlocks<ShadeHitBody<MK>> {
+   static const int v = (MK >= 0 && MK < 16 && ((SH_KINDS5 >> MK) & 1)) ? 5 : ((MK >= 0 && MK < 16 && ((SH_KINDS4 >> MK) & 1)) ? 4 : SH_MINBLOCKS);
+};
+template <class B> __global__ void __launch_bounds__(128, HeavyBlocks<B>::v) kRunQueueHeavy(B b, const uint32_t *__restrict__ q, const uint32_t *__restrict__ cnt) {
    uint32_t n = *cnt;
    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) b(q[i]);
 }
