@@ -40,7 +40,9 @@ template <class B> __global__ void __launch_bounds__(256) kRunQueue(B b, const u
 #define SH_KINDS4 0x88    // plastic, translucent matte: measured on the B200 (tools/gpu_r02_z10.sh) ducky +2.4 %, environment +2.8 %, sun-sky +11.2 %, films bit-identical
 #endif
 #ifndef SH_KINDS5
-#define SH_KINDS5 0       // A/B: kinds compiled for five CTAs per SM (102 registers)
+#define SH_KINDS5 0x08    // plastic compiled for five CTAs per SM (96 registers, 112 bytes of spills): ducky +3.1 %, environment +1.9 %,
+                          // sun-sky -0.5 % over four (tools/gpu_r02_z12.sh). Matte at five: cfg 5 +0.4 %, but the all-matte, cache-resident
+                          // cornell-box -2.3 % (tools/gpu_r02_z11.sh: 0x1F) -- stays at four
 #endif
 template <class B> struct HeavyBlocks { static const int v = SH_MINBLOCKS; };
 template <int MK> struct HeavyBlocks<ShadeHitBody<MK>> {
