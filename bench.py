@@ -423,17 +423,23 @@ def run_b200(a):
             f2 = torch.as_tensor(_Dev(p2, n2), device=torch.device("cuda", local))
             with torch.cuda.stream(stream):
                 c2.render_slice(1 + rank, SEED, 0, k)
-                barrier(); c2.reset_stats()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-                c2.render_slice(1 + rank, SEED, k, 2 * k)
-                if world > 1:
-                    tot2 = f2.clone(); dist.all_reduce(tot2, op=dist.ReduceOp.SUM)
-                e1.record(stream)
-                barrier()
-                s3 = c2.stats()
-                rays = s3["rays_camera"] + s3["rays_extension"] + s3["rays_mis"] + s3["rays_shadow"]
-                v = torch.tensor([e0.elapsed_time(e1), float(s3["samples"]), float(rays)], dtype=torch.float64, device="cuda")
+                # the same slice three times, the MEDIAN reported: one slice is 20-60 ms, and a single shot once came back 30 % slow
+                # on a box where every other run of the scene agreed to 1 % (tools/gpu_r02_final3.sh / _final4.sh)
+                shots = []
+                for _rep in range(3):
+                    barrier(); c2.reset_stats()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(stream)
+                    c2.render_slice(1 + rank, SEED, k, 2 * k)
+                    if world > 1:
+                        tot2 = f2.clone(); dist.all_reduce(tot2, op=dist.ReduceOp.SUM)
+                    e1.record(stream)
+                    barrier()
+                    s3 = c2.stats()
+                    rays = s3["rays_camera"] + s3["rays_extension"] + s3["rays_mis"] + s3["rays_shadow"]
+                    shots.append((e0.elapsed_time(e1), float(s3["samples"]), float(rays)))
+                shots.sort()
+                v = torch.tensor(list(shots[1]), dtype=torch.float64, device="cuda")
                 if world > 1:
                     vm = v.clone(); dist.all_reduce(vm, op=dist.ReduceOp.MAX)
                     vs = v.clone(); dist.all_reduce(vs, op=dist.ReduceOp.SUM)

@@ -40,9 +40,11 @@ template <class B> __global__ void __launch_bounds__(256) kRunQueue(B b, const u
 #define SH_KINDS4 0x88    // plastic, translucent matte: measured on the B200 (tools/gpu_r02_z10.sh) ducky +2.4 %, environment +2.8 %, sun-sky +11.2 %, films bit-identical
 #endif
 #ifndef SH_KINDS5
-#define SH_KINDS5 0x08    // plastic compiled for five CTAs per SM (96 registers, 112 bytes of spills): ducky +3.1 %, environment +1.9 %,
-                          // sun-sky -0.5 % over four (tools/gpu_r02_z12.sh). Matte at five: cfg 5 +0.4 %, but the all-matte, cache-resident
-                          // cornell-box -2.3 % (tools/gpu_r02_z11.sh: 0x1F) -- stays at four
+#define SH_KINDS5 0       // A/B: kinds compiled for FIVE CTAs per SM (96 registers). Plastic alone (0x08) is faster in isolation (ducky +3.1 %,
+                          // environment +1.9 %, tools/gpu_r02_z12.sh) but spills: its stack frame grows from 280 to 392 bytes, the largest of any
+                          // kernel in a pass, and inside the full bench.py run (the cfg-5 context with its 33 GB of path state alive beside it)
+                          // sun-sky then came back at 660 instead of 935 Msamples/s, twice (tools/gpu_r02_final3.sh; presumably the driver
+                          // resizing local memory between launches). Matte at five: cfg 5 +0.4 %, cornell-box -2.3 % (0x1F, _z11.sh). Off.
 #endif
 template <class B> struct HeavyBlocks { static const int v = SH_MINBLOCKS; };
 template <int MK> struct HeavyBlocks<ShadeHitBody<MK>> {
