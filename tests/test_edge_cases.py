@@ -204,3 +204,38 @@ def test_random_triangle_distributions_traversal_parity(seed):
     else: v = c * 0.01 + r.normal(size=(n, 3, 3)) * scale * 0.5
     sc = _tri_scene(v.reshape(n, 9).astype(np.float32))
     _traversal_parity(sc, random_rays(sc, 2500, seed))
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("collapse", [(0.0, 2), (0.5, 3)])
+def test_rays_through_the_extremes_of_the_boxes(seed, collapse):
+    """The child boxes are 8-bit boxes moved out by 1/64 of a cell (bvh_build.cpp, bvh.h: the folded 2^15 of the dequantisation is good
+    to 1/512 of a cell). A box that came out too small by a hair would lose exactly the hits at its faces -- so aim rays at the
+    vertices and edges of the triangles, i.e. at the extremes of the leaf boxes, from all around, at scales 1e-3 .. 1e4 and offsets up
+    to 1e3 scales away from the origin (coarse float grid), for the greedy and the optimal collapse: the quantised tree must find
+    every hit brute force finds, t bit for bit."""
+    r = np.random.default_rng(1000 + seed)
+    n = int(r.choice([40, 400, 5000]))
+    scale = 10.0 ** r.uniform(-3, 4)
+    off = r.uniform(-1, 1, 3) * scale * (10.0 ** r.uniform(0, 3))
+    c = off + r.uniform(-1, 1, (n, 1, 3)) * scale
+    v = (c + r.normal(size=(n, 3, 3)) * scale * (0.02 if seed % 2 else 0.2)).astype(np.float32)
+    sc = _tri_scene(v.reshape(n, 9))
+    m = 3000
+    tri = r.integers(0, n, m)
+    w = r.dirichlet([0.3, 0.3, 0.3], m); w[: m // 2] = np.eye(3)[r.integers(0, 3, m // 2)]      # half exactly at a vertex, half near an edge
+    target = (v[tri].astype(np.float64) * w[:, :, None]).sum(1)
+    d = r.normal(size=(m, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    dist = scale * 10.0 ** r.uniform(-1, 1.5, (m, 1))
+    rays = np.zeros(m, dtype=random_rays(sc, 1, 0).dtype)
+    rays["o"] = (target - d * dist).astype(np.float32); rays["d"] = d.astype(np.float32)
+    rays["tmin"] = 0.0; rays["tmax"] = np.inf
+    o = Oracle(sc); e = EmuContext(); e.set_option("bvh_collapse_cp", collapse[0]); e.set_option("bvh_leaf", collapse[1]); e.upload_scene(sc)
+    hb = o.trace_nearest(rays, mode="brute"); he = e.trace_nearest(rays)
+    oo, oe = o.trace_occluded(rays, mode="brute"), e.trace_occluded(rays)
+    e.close()
+    ties, bad = compare_hits(he, hb)
+    assert bad == 0, (ties, bad)
+    same = (hb["prim"] >= 0) & (he["prim"] == hb["prim"])
+    assert same.sum() > m // 4 and np.array_equal(he["t"][same], hb["t"][same])
+    assert np.array_equal(oe.astype(bool), oo.astype(bool))
