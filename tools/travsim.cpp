@@ -5,6 +5,9 @@
 // primitive tests, warp trips, lanes active per step and a warp-instruction estimate from per-step costs read off the
 // SASS of the shipped kernel. Test/tool code only (not linked into the product).
 //   g++ -O2 -fopenmp -std=c++17 -I bling_b200/csrc tools/travsim.cpp -o /tmp/travsim && /tmp/travsim [ntris] [rows]
+// Environment knobs: POLS="|name|name|" (policies to run beside the base), MAXLEAF, TRAVCOST, FORCELEAF (binary builder), DPCOLLAPSE="cn,cp,pmax"
+// (SAH-optimal collapse instead of the greedy one), QPAD (cells a child bound is moved out by: 1 = the rule until late in round 2, default 1/64),
+// NOQUANT (exact child boxes), SORTED, RANDOM_RAYS. The PRODUCT tree of cfg 5 is `MAXLEAF=1 DPCOLLAPSE=1,0.5,3` (profiles/r02_tree_and_requests.md).
 #include "../bling_b200/csrc/bvh_build.cpp"
 #include <chrono>
 #include <cstdio>
