@@ -209,6 +209,10 @@ def test_random_triangle_distributions_traversal_parity(seed):
 @pytest.mark.parametrize("seed", range(8))
 @pytest.mark.parametrize("collapse", [(0.0, 2), (0.5, 3)])
 def test_rays_through_the_extremes_of_the_boxes(seed, collapse):
+    extreme_rays_case(seed, collapse, EmuContext)
+
+
+def extreme_rays_case(seed, collapse, make_ctx):
     """The child boxes are 8-bit boxes moved out by 1/64 of a cell (bvh_build.cpp, bvh.h: the folded 2^15 of the dequantisation is good
     to 1/512 of a cell). A box that came out too small by a hair would lose exactly the hits at its faces -- so aim rays at the
     vertices and edges of the triangles, i.e. at the extremes of the leaf boxes, from all around, at scales 1e-3 .. 1e4 and offsets up
@@ -230,7 +234,7 @@ def test_rays_through_the_extremes_of_the_boxes(seed, collapse):
     rays = np.zeros(m, dtype=random_rays(sc, 1, 0).dtype)
     rays["o"] = (target - d * dist).astype(np.float32); rays["d"] = d.astype(np.float32)
     rays["tmin"] = 0.0; rays["tmax"] = np.inf
-    o = Oracle(sc); e = EmuContext(); e.set_option("bvh_collapse_cp", collapse[0]); e.set_option("bvh_leaf", collapse[1]); e.upload_scene(sc)
+    o = Oracle(sc); e = make_ctx(); e.set_option("bvh_collapse_cp", collapse[0]); e.set_option("bvh_leaf", collapse[1]); e.upload_scene(sc)
     hb = o.trace_nearest(rays, mode="brute"); he = e.trace_nearest(rays)
     oo, oe = o.trace_occluded(rays, mode="brute"), e.trace_occluded(rays)
     e.close()

@@ -47,6 +47,15 @@ def test_nearest_and_any_hit_parity(ctx, name, variant):
     ctx.set_option("trace_variant", 3)
 
 
+@pytest.mark.parametrize("seed", [0, 3, 5])
+@pytest.mark.parametrize("collapse", [(0.0, 2), (0.5, 3)])
+def test_rays_through_the_extremes_of_the_boxes_gpu(seed, collapse):
+    """GPU leg of tests/test_edge_cases.py::test_rays_through_the_extremes_of_the_boxes: the device's one-FMA dequantisation (PRMT into the
+    mantissa of 2^15) against brute force on rays aimed at the faces of the leaf boxes."""
+    from tests.test_edge_cases import extreme_rays_case
+    extreme_rays_case(seed, collapse, lambda: api.Context(0))
+
+
 @pytest.mark.parametrize("variant", [0, 1, 2, 3])
 def test_soup_traversal_parity(ctx, variant):
     """200k-triangle soup (same generator as cfg 5): GPU BVH vs the oracle's kd-tree; empty and ragged batches."""
