@@ -43,8 +43,8 @@ template <class B> __global__ void __launch_bounds__(256) kRunQueue(B b, const u
 #define SH_KINDS5 0       // A/B: kinds compiled for FIVE CTAs per SM (96 registers). Plastic alone (0x08) is faster in isolation (ducky +3.1 %,
                           // environment +1.9 %, tools/gpu_r02_z12.sh) but spills: its stack frame grows from 280 to 392 bytes, the largest of any
                           // kernel in a pass, and inside the full bench.py run (the cfg-5 context with its 33 GB of path state alive beside it)
-                          // sun-sky then came back at 660 instead of 935 Msamples/s, twice (tools/gpu_r02_final3.sh; presumably the driver
-                          // resizing local memory between launches). Matte at five: cfg 5 +0.4 %, cornell-box -2.3 % (0x1F, _z11.sh). Off.
+                          // sun-sky then came back at 660 instead of 935 Msamples/s, twice (tools/gpu_r02_final3.sh; cause not established --
+                          // the round's GPU time ended there; with plastic at four CTAs the full run measures 952). Matte at five: cfg 5 +0.4 %, cornell-box -2.3 % (0x1F, _z11.sh). Off.
 #endif
 template <class B> struct HeavyBlocks { static const int v = SH_MINBLOCKS; };
 template <int MK> struct HeavyBlocks<ShadeHitBody<MK>> {
