@@ -147,10 +147,17 @@ struct Collapse {
       return best;
    }
    float leafCost(int n, const Box &b) const { return cnt[(size_t)n] <= pmax ? b.area() * (float)cnt[(size_t)n] * cp : BL_INF; }
-   void solve(int n, Box &box) {   // post-order; the binary tree is at most ~60 levels deep
+   int parLevels = 0;   // the two subtrees of the top levels are solved concurrently (they write disjoint table entries)
+   void solve(int n, Box &box, int depth = 0) {   // post-order; the binary tree is at most ~60 levels deep
       Box lb, rb, tmp; int lr, rr; childrenOf(bin, n, lb, lr, rb, rr);
-      if (lr >= 0) solve(lr, tmp);
-      if (rr >= 0) solve(rr, tmp);
+      if (depth < parLevels && lr >= 0 && rr >= 0) {
+         auto fut = std::async(std::launch::async, [&]() { Box t2; solve(lr, t2, depth + 1); });
+         solve(rr, tmp, depth + 1);
+         fut.get();
+      } else {
+         if (lr >= 0) solve(lr, tmp, depth + 1);
+         if (rr >= 0) solve(rr, tmp, depth + 1);
+      }
       box = lb; box.grow(rb);
       const int lc = lr < 0 ? ((~lr) & 15) : cnt[(size_t)lr], rc = rr < 0 ? ((~rr) & 15) : cnt[(size_t)rr];
       first[(size_t)n] = lr < 0 ? (int)((uint32_t)(~lr) >> 4) : first[(size_t)lr];   // the items of a subtree are contiguous, left before right
@@ -230,6 +237,7 @@ int bvhBuild(const BvhBuildInput &in, BvhBuildOutput &out) {
    if (optimal) {
       dp.bin = B.nodes; dp.cp = in.collapse_cp; dp.pmax = std::min(15, std::max(1, in.max_leaf));
       dp.c1.assign((size_t)n2, 0); dp.c2.assign((size_t)n2, 0); dp.c3.assign((size_t)n2, 0); dp.first.assign((size_t)n2, 0); dp.cnt.assign((size_t)n2, 0);
+      dp.parLevels = in.n > 65536 ? B.parLevels : 0;
       Box bx; dp.solve(root, bx);
    }
    auto childrenOf = [&](int idx, Child &l, Child &r) {
